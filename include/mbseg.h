@@ -1,0 +1,121 @@
+/*
+ * mbseg.h -- C ABI of libmbseg.so: the B200-native (sm_100a) segmentation hot path of microbeSEG.
+ *
+ * The reference (hip-satomi/microbeSEG) is pure Python; it has no FFI.  The drop-in boundary is
+ * its L2 Python operator surface; the host-side mirror of that surface
+ * lives in microbeseg_b200/ and binds the entry points below with ctypes.
+ * Every entry point cites the reference code whose arithmetic it replaces.
+ *
+ * Conventions
+ *   - all pointers are DEVICE pointers unless the name ends in _host;
+ *   - `stream` is a cudaStream_t passed as void*;
+ *   - return value: 0 = ok, nonzero = error, message via mbs_last_error() (thread local);
+ *   - no allocation inside hot calls: scratch comes from a caller-owned workspace whose size is
+ *     returned by the matching *_workspace_bytes() query;
+ *   - activations are NHWC bf16; distance maps are float32 (H,W); masks are uint16 (H,W).
+ */
+#ifndef MBSEG_H_
+#define MBSEG_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---------------------------------------------------------------------------------------- */
+/* library                                                                                  */
+/* ---------------------------------------------------------------------------------------- */
+const char *mbs_last_error(void);
+int mbs_version(void);
+/* number of kernel launches issued by this library on the calling thread since the last reset
+ * (bench.py reports it as gpu_launches). */
+int64_t mbs_launch_count(int reset);
+/* 1 if a tcgen05/TMA pipeline barrier timed out in any kernel since the last reset (the kernels
+ * bail out instead of hanging the device); -1 if the flag could not be read. */
+int mbs_debug_flags(int reset);
+
+/* ---------------------------------------------------------------------------------------- */
+/* U-Net building blocks (replace torch.nn/cuDNN calls made by src/utils/unets.py)           */
+/* ---------------------------------------------------------------------------------------- */
+enum { MBS_ACT_NONE = 0, MBS_ACT_RELU = 1, MBS_ACT_LEAKYRELU = 2, MBS_ACT_ELU = 3, MBS_ACT_MISH = 4 };
+enum { MBS_IN_U8 = 0, MBS_IN_U16 = 1, MBS_IN_F32 = 2 };
+enum { MBS_CONV3X3_S1 = 0, MBS_CONV3X3_S2 = 1, MBS_CONVT2X2_S2 = 2 };
+
+/*
+ * First encoder conv fused with min-max normalisation and top/left padding.
+ * Replaces: frame min/max normalisation `2*(f32(img)-min)/(max-min)-1`
+ *   (src/inference/infer.py:346, infer_script_local.py:130), zero_pad_model_input
+ *   (src/utils/utils.py:124-163, pads TOP/LEFT with pad_val=frame_min, i.e. -1 after
+ *   normalisation) and ConvBlock's first Conv2d(1,C,3,p=1)+act+BatchNorm2d(eval)
+ *   (src/utils/unets.py:112-134).
+ * img: raw frame (H,W) of in_dtype; output (Hp,Wp,C) bf16 with Hp=H+pad_y, Wp=W+pad_x.
+ * weight: [C][9] f32 (ky*3+kx), bias/scale/shift: [C] f32 (scale/shift = folded eval BN).
+ * norm_lo/norm_hi: frame min / max as floats; pad pixels take the value norm_lo.
+ */
+int mbs_first_conv(const void *img, int in_dtype, int H, int W, int pad_y, int pad_x, float norm_lo,
+                   float norm_hi, const float *weight, const float *bias, const float *scale,
+                   const float *shift, int C, int act, void *out_nhwc_bf16, int out_ld, int out_coff,
+                   void *stream);
+
+/*
+ * Implicit-GEMM convolution on the tcgen05 tensor cores (TMA-fed, TMEM accumulators, fused
+ * epilogue bias -> activation -> BatchNorm(eval) affine -> bf16).
+ * Replaces: nn.Conv2d(3x3,s1,p1) / nn.Conv2d(3x3,s2,p1) / nn.ConvTranspose2d(2x2,s2) followed by
+ *   the activation and nn.BatchNorm2d of ConvBlock / ConvPool / TranspConvBlock
+ *   (src/utils/unets.py:92-173, 176-226, 229-264), the channel concat torch.cat([up, skip],1)
+ *   (src/utils/unets.py:492,502; expressed as two K sources), and optionally the final
+ *   Conv2d(C,1,1) head (src/utils/unets.py:460-461,494,504) fused into the epilogue.
+ */
+typedef struct {
+    int mode;            /* MBS_CONV3X3_S1 / MBS_CONV3X3_S2 / MBS_CONVT2X2_S2 */
+    int N, H, W;         /* input batch / height / width (both sources) */
+    /* source 0 and (optional) source 1: NHWC bf16 views with `ld` channels per pixel, the
+     * source's channels start at element offset `coff` and number `C` (multiple of 64). */
+    const void *src0; int C0, ld0, coff0;
+    const void *src1; int C1, ld1, coff1;
+    /* packed weights bf16: conv: [Cout][9][C0+C1]; convT: [4*Cout][C0] with row (dy*2+dx)*Cout+co */
+    const void *weight;
+    int Cout;            /* output channels (multiple of 64) */
+    const float *bias, *scale, *shift;   /* [Cout] f32 */
+    int act;
+    /* destination NHWC bf16 view (may be NULL when only the head output is wanted) */
+    void *dst; int ldd, coffd;
+    /* optional fused 1x1 head (requires Cout == 64): head_out[n][y][x] = sum_c y_c*head_w[c] + head_b */
+    const float *head_w; float head_b; float *head_out;
+} mbs_conv_desc;
+
+int mbs_conv_gemm(const mbs_conv_desc *d, void *stream);
+/* pack helpers: f32 reference-layout weights -> bf16 GEMM layout (device to device) */
+int mbs_pack_conv3x3_weight(const float *w_oihw, int Cout, int Cin, void *packed_bf16, void *stream);
+int mbs_pack_convT2x2_weight(const float *w_iohw, int Cin, int Cout, void *packed_bf16, void *stream);
+
+/* ---------------------------------------------------------------------------------------- */
+/* distance post-processing (replaces src/inference/postprocessing.py:7-59)                 */
+/* ---------------------------------------------------------------------------------------- */
+size_t mbs_postproc_workspace_bytes(int H, int W);
+/*
+ * border, cell: float32 device arrays, element (y,x) at [y*ld + x] (ld in elements; a crop of a
+ * padded network output is expressed through the base pointer and ld).  out: uint16 (H,W) dense.
+ * info_host (optional, 8 x int64 on the host): [0]=#seed components before filtering,
+ *   [1]=#markers, [2]=#minimax relaxation sweeps, [3]=1 if the exact sequential flood was needed
+ *   (value ties), [4]=#ambiguous pixels, others reserved.  Passing info_host forces a stream sync.
+ */
+int mbs_distance_postprocessing(const float *border, const float *cell, int H, int W, int ld,
+                                float th_seed, float th_cell, uint16_t *out, void *workspace,
+                                size_t workspace_bytes, int64_t *info_host, void *stream);
+
+/* individual stages, exposed for stage-level parity tests */
+int mbs_pp_front(const float *border, const float *cell, int H, int W, int ld, float th_seed,
+                 float th_cell, float *cell_smooth, uint8_t *mask, uint8_t *seed, void *stream);
+int mbs_pp_label8(const uint8_t *binary, int H, int W, int32_t *labels, int32_t *n_out,
+                  void *workspace, size_t workspace_bytes, void *stream);
+int mbs_pp_watershed(const float *image, const int32_t *markers, const uint8_t *mask, int H, int W,
+                     int32_t *labels_out, void *workspace, size_t workspace_bytes,
+                     int64_t *info_host, int force_sequential, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MBSEG_H_ */

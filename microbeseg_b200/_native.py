@@ -1,0 +1,75 @@
+"""ctypes binding of libmbseg.so (the C ABI declared in include/mbseg.h).
+
+There is deliberately no fallback: if the library is missing or a call fails, a RuntimeError is
+raised (the reference's callers catch RuntimeError around net(), src/inference/infer.py:352-356).
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libmbseg.so")
+_lib = None
+
+c_void_p, c_int, c_float, c_size_t, c_int64 = (ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_size_t,
+                                               ctypes.c_int64)
+
+
+class ConvDesc(ctypes.Structure):
+    """mirror of mbs_conv_desc (include/mbseg.h)"""
+    _fields_ = [("mode", c_int), ("N", c_int), ("H", c_int), ("W", c_int),
+                ("src0", c_void_p), ("C0", c_int), ("ld0", c_int), ("coff0", c_int),
+                ("src1", c_void_p), ("C1", c_int), ("ld1", c_int), ("coff1", c_int),
+                ("weight", c_void_p), ("Cout", c_int),
+                ("bias", c_void_p), ("scale", c_void_p), ("shift", c_void_p), ("act", c_int),
+                ("dst", c_void_p), ("ldd", c_int), ("coffd", c_int),
+                ("head_w", c_void_p), ("head_b", c_float), ("head_out", c_void_p)]
+
+
+_SIGS = {
+    "mbs_last_error": (ctypes.c_char_p, []),
+    "mbs_version": (c_int, []),
+    "mbs_launch_count": (c_int64, [c_int]),
+    "mbs_debug_flags": (c_int, [c_int]),
+    "mbs_first_conv": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_float, c_float, c_void_p, c_void_p,
+                               c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_void_p]),
+    "mbs_conv_gemm": (c_int, [ctypes.POINTER(ConvDesc), c_void_p]),
+    "mbs_pack_conv3x3_weight": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p]),
+    "mbs_pack_convT2x2_weight": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p]),
+    "mbs_postproc_workspace_bytes": (c_size_t, [c_int, c_int]),
+    "mbs_distance_postprocessing": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_float, c_void_p,
+                                            c_void_p, c_size_t, c_void_p, c_void_p]),
+    "mbs_pp_front": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_float, c_void_p, c_void_p, c_void_p,
+                             c_void_p]),
+    "mbs_pp_label8": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "mbs_pp_watershed": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_size_t, c_void_p,
+                                 c_int, c_void_p]),
+}
+
+
+def lib():
+    """Load libmbseg.so; raise RuntimeError (never fall back) if it is not built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(nvcc, sm_100a). microbeseg_b200 has no CPU or library fallback.")
+        L = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGS.items():
+            fn = getattr(L, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib
+
+
+def check(rc, what=""):
+    if rc != 0:
+        msg = lib().mbs_last_error().decode(errors="replace")
+        raise RuntimeError(f"libmbseg {what} failed (code {rc}): {msg}")
+
+
+def stream_ptr(stream=None):
+    import torch
+    s = stream if stream is not None else torch.cuda.current_stream()
+    return c_void_p(s.cuda_stream)

@@ -1,0 +1,654 @@
+// U-Net building blocks for sm_100a: implicit-GEMM convolutions on tcgen05 tensor cores.
+//
+// Replaces the cuDNN calls behind src/utils/unets.py (ConvBlock :92-173, ConvPool :176-226,
+// TranspConvBlock :229-264, DUNet.forward :463-506 incl. torch.cat and the 1x1 heads).
+//
+// Design (one CTA = one 128-pixel x BN-channel output tile):
+//   * activations are NHWC bf16; an output tile is an 8x16 pixel patch, so the A operand of tap
+//     (ky,kx) is the same patch shifted by (ky-1,kx-1): one 4-D TMA box load per (tap, 64-channel
+//     chunk), out-of-bounds rows/cols zero-filled by TMA = the conv's zero padding, for free;
+//   * stride-2 convs use the TMA traversal stride (elementStrides=2) on the same tensor;
+//   * ConvTranspose2d(2,2) is a plain GEMM [pixels,Cin]x[Cin,4*Cout] with a pixel-shuffle scatter
+//     in the epilogue; torch.cat([up,skip]) is a second K source (second tensor map);
+//   * smem tiles are 128B-swizzled K-major, consumed by tcgen05.mma (cta_group::1, M=128,
+//     N=BN, K=16) with fp32 accumulators in TMEM; 4 epilogue warps read TMEM with tcgen05.ld and
+//     apply bias -> activation -> BatchNorm(eval) affine -> bf16 (and the fused 1x1 head);
+//   * warp roles: warp0 = TMA producer, warp1 = TMEM alloc + MMA issuer, warps2-5 = epilogue.
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstring>
+#include <mutex>
+
+#include "../../include/mbseg.h"
+#include "common.cuh"
+
+namespace {
+
+constexpr int TILE_W = 16;
+constexpr int TILE_H = 8;
+constexpr int BM = 128;  // TILE_W * TILE_H
+constexpr int BK = 64;   // bf16 elements per K chunk = 128 bytes = one swizzle row
+constexpr int A_BYTES = BM * BK * 2;
+constexpr int NUM_THREADS = 192;
+
+struct ConvKParams {
+    int mode, act;
+    int tiles_x, tiles_y;     // tiles over the GEMM-M pixel grid
+    int Hm, Wm;               // GEMM-M pixel grid dims (conv: output dims; convT: input dims)
+    int chunks0, chunks1;     // 64-channel chunks of source 0 / source 1
+    int taps;                 // 9 (conv) or 1 (convT)
+    int n_tiles;              // GEMM-N tiles
+    int Cout;
+    const float *bias, *scale, *shift;
+    __nv_bfloat16 *dst;
+    int ldd, coffd, Hd, Wd;   // destination view
+    const float *head_w;
+    float head_b;
+    float *head_out;
+};
+
+// ------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// Set when a barrier wait exceeds its cycle budget: the kernel then runs to completion with
+// garbage instead of hanging the GPU; hosts/tests read it through mbs_debug_flags().
+__device__ int g_mbar_timeout = 0;
+
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > 4000000000ll) {  // ~2 s: something is wrong, never hang the device
+            atomicExch(&g_mbar_timeout, 1);
+            return;
+        }
+    }
+}
+__device__ __forceinline__ void fence_barrier_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1,
+                                            int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, "
+        "%6}], [%2];" ::"r"(dst),
+        "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], "
+        "[%2];" ::"r"(dst),
+        "l"(map), "r"(bar), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap *map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                         uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major, 128-byte swizzle shared-memory matrix descriptor (sm_100 UMMA).
+//   [0,14)  start address >> 4      [16,30) leading byte offset >> 4 (unused for swizzled K-major)
+//   [32,46) stride byte offset >> 4 (1024 B between 8-row groups)    [46,48) version = 1
+//   [61,64) layout type: 2 = SWIZZLE_128B
+__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= static_cast<uint64_t>((saddr & 0x3FFFFu) >> 4);
+    d |= static_cast<uint64_t>(1) << 16;
+    d |= static_cast<uint64_t>(1024 >> 4) << 32;
+    d |= static_cast<uint64_t>(1) << 46;
+    d |= static_cast<uint64_t>(2) << 61;
+    return d;
+}
+// kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, M=128, N=BN.
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(N >> 3) << 17) |
+           (static_cast<uint32_t>(M >> 4) << 24);
+}
+
+__device__ __forceinline__ float apply_act(float v, int act) {
+    switch (act) {
+        case MBS_ACT_RELU: return fmaxf(v, 0.0f);
+        case MBS_ACT_LEAKYRELU: return v > 0.0f ? v : 0.01f * v;
+        case MBS_ACT_ELU: return v > 0.0f ? v : expm1f(v);
+        case MBS_ACT_MISH: {
+            float sp = v > 20.0f ? v : log1pf(expf(v));
+            return v * tanhf(sp);
+        }
+        default: return v;
+    }
+}
+
+template <int BN, int STAGES>
+struct SmemPlan {
+    static constexpr int B_BYTES = BN * BK * 2;
+    static constexpr int OFF_A = 0;
+    static constexpr int OFF_B = STAGES * A_BYTES;
+    static constexpr int OFF_BAR = OFF_B + STAGES * B_BYTES;      // full[STAGES], empty[STAGES], tmem_full
+    static constexpr int OFF_TMEM = OFF_BAR + 8 * (2 * STAGES + 1);
+    static constexpr int OFF_PAR = OFF_TMEM + 8;                  // bias/scale/shift [3][BN] + head_w[BN]
+    static constexpr int TOTAL = OFF_PAR + 4 * BN * 4;
+    static constexpr int DYN_BYTES = TOTAL + 1024;                // slack for manual 1024-B alignment
+};
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
+                 const __grid_constant__ CUtensorMap tmB, const ConvKParams p) {
+    using Plan = SmemPlan<BN, STAGES>;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t base = (raw + 1023u) & ~1023u;
+    uint8_t *gbase = smem_raw + (base - raw);
+    const uint32_t sA = base + Plan::OFF_A;
+    const uint32_t sB = base + Plan::OFF_B;
+    const uint32_t sBar = base + Plan::OFF_BAR;
+    auto full_bar = [&](int s) { return sBar + 8u * s; };
+    auto empty_bar = [&](int s) { return sBar + 8u * (STAGES + s); };
+    const uint32_t tmem_full_bar = sBar + 8u * (2 * STAGES);
+    volatile uint32_t *tmem_ptr = reinterpret_cast<volatile uint32_t *>(gbase + Plan::OFF_TMEM);
+    float *s_par = reinterpret_cast<float *>(gbase + Plan::OFF_PAR);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    // tile decode: n-tile fastest so that consecutive CTAs reuse the same A patch out of L2
+    const int n_tile = blockIdx.x % p.n_tiles;
+    int m_tile = blockIdx.x / p.n_tiles;
+    const int tx = m_tile % p.tiles_x;
+    m_tile /= p.tiles_x;
+    const int ty = m_tile % p.tiles_y;
+    const int img = m_tile / p.tiles_y;
+    const int x0 = tx * TILE_W, y0 = ty * TILE_H;
+    const int n0 = n_tile * BN;
+    const int chunks = p.chunks0 + p.chunks1;
+    const int num_k_iters = p.taps * chunks;
+
+    if (threadIdx.x == 0) {
+        prefetch_tmap(&tmA0);
+        if (p.chunks1 > 0) prefetch_tmap(&tmA1);
+        prefetch_tmap(&tmB);
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(full_bar(s), 1);
+            mbar_init(empty_bar(s), 1);
+        }
+        mbar_init(tmem_full_bar, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) {
+        tmem_alloc(smem_u32(const_cast<uint32_t *>(tmem_ptr)), BN);
+    }
+    if (warp >= 2) {
+        // stage the per-channel epilogue parameters of this N tile
+        for (int j = threadIdx.x - 64; j < BN; j += NUM_THREADS - 64) {
+            const int col = n0 + j;
+            const int co = p.mode == MBS_CONVT2X2_S2 ? col % p.Cout : col;
+            s_par[j] = p.bias[co];
+            s_par[BN + j] = p.scale[co];
+            s_par[2 * BN + j] = p.shift[co];
+            s_par[3 * BN + j] = p.head_w ? p.head_w[co] : 0.0f;
+        }
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ===== TMA producer =====
+            for (int it = 0; it < num_k_iters; ++it) {
+                const int s = it % STAGES;
+                const uint32_t ph = (it / STAGES) & 1;
+                mbar_wait(empty_bar(s), ph ^ 1u);
+                mbar_expect_tx(full_bar(s), A_BYTES + Plan::B_BYTES);
+                const int tap = it / chunks;
+                const int cc = it - tap * chunks;
+                int cx, cy;
+                if (p.mode == MBS_CONV3X3_S1) {
+                    cx = x0 + (tap % 3) - 1;
+                    cy = y0 + (tap / 3) - 1;
+                } else if (p.mode == MBS_CONV3X3_S2) {
+                    cx = 2 * x0 + (tap % 3) - 1;
+                    cy = 2 * y0 + (tap / 3) - 1;
+                } else {
+                    cx = x0;
+                    cy = y0;
+                }
+                if (cc < p.chunks0)
+                    tma_load_4d(sA + s * A_BYTES, &tmA0, full_bar(s), cc * BK, cx, cy, img);
+                else
+                    tma_load_4d(sA + s * A_BYTES, &tmA1, full_bar(s), (cc - p.chunks0) * BK, cx, cy, img);
+                tma_load_2d(sB + s * Plan::B_BYTES, &tmB, full_bar(s), it * BK, n0);
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        // ===== MMA issuer (single thread) =====
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc(BM, BN);
+            for (int it = 0; it < num_k_iters; ++it) {
+                const int s = it % STAGES;
+                const uint32_t ph = (it / STAGES) & 1;
+                mbar_wait(full_bar(s), ph);
+                tcgen05_fence_after();
+                const uint64_t adesc = make_sw128_desc(sA + s * A_BYTES);
+                const uint64_t bdesc = make_sw128_desc(sB + s * Plan::B_BYTES);
+#pragma unroll
+                for (int k = 0; k < BK / 16; ++k) {
+                    // advance 32 bytes (16 bf16) inside the 128-byte swizzle row: +2 in the >>4 encoding
+                    umma_f16(tmem_base, adesc + 2u * k, bdesc + 2u * k, idesc, (it > 0 || k > 0) ? 1u : 0u);
+                }
+                umma_commit(empty_bar(s));  // frees the smem slot when these MMAs retire
+            }
+            umma_commit(tmem_full_bar);      // accumulator complete
+        }
+        __syncwarp();
+    } else {
+        // ===== epilogue: TMEM -> registers -> bias/act/BN -> bf16 -> global =====
+        const int quad = warp & 3;                 // TMEM lane quadrant this warp may access
+        const int row = quad * 32 + lane;          // tile row == pixel index inside the 8x16 patch
+        const int py = y0 + row / TILE_W;
+        const int px = x0 + row % TILE_W;
+        const bool in_img = (py < p.Hm) && (px < p.Wm);
+        mbar_wait(tmem_full_bar, 0);
+        tcgen05_fence_after();
+        float head_acc = 0.0f;
+#pragma unroll 1
+        for (int c = 0; c < BN; c += 32) {
+            uint32_t r[32];
+            tmem_ld32(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + c, r);
+            uint32_t packed[16];
+#pragma unroll
+            for (int j = 0; j < 32; j += 2) {
+                float v0 = __uint_as_float(r[j]) + s_par[c + j];
+                float v1 = __uint_as_float(r[j + 1]) + s_par[c + j + 1];
+                v0 = apply_act(v0, p.act);
+                v1 = apply_act(v1, p.act);
+                v0 = fmaf(v0, s_par[BN + c + j], s_par[2 * BN + c + j]);
+                v1 = fmaf(v1, s_par[BN + c + j + 1], s_par[2 * BN + c + j + 1]);
+                head_acc = fmaf(v0, s_par[3 * BN + c + j], head_acc);
+                head_acc = fmaf(v1, s_par[3 * BN + c + j + 1], head_acc);
+                __nv_bfloat162 h = __floats2bfloat162_rn(v0, v1);
+                packed[j >> 1] = *reinterpret_cast<uint32_t *>(&h);
+            }
+            if (in_img && p.dst) {
+                const int col = n0 + c;
+                size_t off;
+                if (p.mode == MBS_CONVT2X2_S2) {
+                    const int q = col / p.Cout;
+                    const int co = col - q * p.Cout;
+                    const int oy = 2 * py + (q >> 1), ox = 2 * px + (q & 1);
+                    off = ((static_cast<size_t>(img) * p.Hd + oy) * p.Wd + ox) * p.ldd + p.coffd + co;
+                } else {
+                    off = ((static_cast<size_t>(img) * p.Hd + py) * p.Wd + px) * p.ldd + p.coffd + col;
+                }
+                uint4 *d4 = reinterpret_cast<uint4 *>(p.dst + off);
+#pragma unroll
+                for (int q4 = 0; q4 < 4; ++q4)
+                    d4[q4] = make_uint4(packed[4 * q4], packed[4 * q4 + 1], packed[4 * q4 + 2], packed[4 * q4 + 3]);
+            }
+        }
+        if (p.head_out && in_img)
+            p.head_out[(static_cast<size_t>(img) * p.Hm + py) * p.Wm + px] = head_acc + p.head_b;
+        tcgen05_fence_before();
+    }
+    __syncthreads();
+    if (warp == 1) {
+        tcgen05_fence_after();
+        tmem_dealloc(tmem_base, BN);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// first layer: normalise + pad + Conv2d(1,C,3,p=1) + act + BN(eval), CUDA cores (K = 9)
+// ------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void first_conv_kernel(const T *__restrict__ img, int H, int W, int pad_y, int pad_x, float lo, float hi,
+                                  const float *__restrict__ weight, const float *__restrict__ bias,
+                                  const float *__restrict__ scale, const float *__restrict__ shift, int C, int act,
+                                  __nv_bfloat16 *__restrict__ out, int ld, int coff) {
+    extern __shared__ float s_w[];  // [C*9] weights, [C] bias, [C] scale, [C] shift
+    for (int i = threadIdx.x; i < C * 9; i += blockDim.x) s_w[i] = weight[i];
+    for (int i = threadIdx.x; i < C; i += blockDim.x) {
+        s_w[C * 9 + i] = bias[i];
+        s_w[C * 10 + i] = scale[i];
+        s_w[C * 11 + i] = shift[i];
+    }
+    __syncthreads();
+    const int Hp = H + pad_y, Wp = W + pad_x;
+    const int groups = C / 8;
+    const long long gid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    const long long pix = gid / groups;
+    const int cg = static_cast<int>(gid - pix * groups);
+    if (pix >= static_cast<long long>(Hp) * Wp) return;
+    const int Y = static_cast<int>(pix / Wp), X = static_cast<int>(pix - static_cast<long long>(Y) * Wp);
+    const float range = hi - lo;
+    float in[9];
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+        const int yy = Y + t / 3 - 1, xx = X + t % 3 - 1;
+        float v = 0.0f;  // conv zero padding outside the (padded) model input
+        if (yy >= 0 && yy < Hp && xx >= 0 && xx < Wp) {
+            float raw = lo;  // zero_pad_model_input pad value = frame min (utils.py:124, infer.py:256)
+            if (yy >= pad_y && xx >= pad_x) raw = static_cast<float>(img[static_cast<size_t>(yy - pad_y) * W + (xx - pad_x)]);
+            // 2 * (f32(img) - min) / (max - min) - 1, evaluated left to right in f32 (infer.py:346)
+            v = __fsub_rn(__fdiv_rn(__fmul_rn(2.0f, __fsub_rn(raw, lo)), range), 1.0f);
+        }
+        in[t] = v;
+    }
+    uint32_t packed[4];
+#pragma unroll
+    for (int j = 0; j < 8; j += 2) {
+        float o[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int c = cg * 8 + j + u;
+            float acc = 0.0f;
+#pragma unroll
+            for (int t = 0; t < 9; ++t) acc = fmaf(in[t], s_w[c * 9 + t], acc);
+            acc += s_w[C * 9 + c];
+            acc = apply_act(acc, act);
+            o[u] = fmaf(acc, s_w[C * 10 + c], s_w[C * 11 + c]);
+        }
+        __nv_bfloat162 h = __floats2bfloat162_rn(o[0], o[1]);
+        packed[j >> 1] = *reinterpret_cast<uint32_t *>(&h);
+    }
+    uint4 *d = reinterpret_cast<uint4 *>(out + static_cast<size_t>(pix) * ld + coff + cg * 8);
+    *d = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+}
+
+__global__ void pack_conv3x3_kernel(const float *__restrict__ w, int Cout, int Cin, __nv_bfloat16 *__restrict__ out) {
+    // out[o][t][c] = w[o][c][t]
+    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    const long long total = static_cast<long long>(Cout) * 9 * Cin;
+    if (i >= total) return;
+    const int c = static_cast<int>(i % Cin);
+    const int t = static_cast<int>((i / Cin) % 9);
+    const int o = static_cast<int>(i / (static_cast<long long>(Cin) * 9));
+    out[i] = __float2bfloat16_rn(w[(static_cast<size_t>(o) * Cin + c) * 9 + t]);
+}
+
+__global__ void pack_convT2x2_kernel(const float *__restrict__ w, int Cin, int Cout, __nv_bfloat16 *__restrict__ out) {
+    // out[(q*Cout + co)][ci] = w[ci][co][q],  q = dy*2+dx
+    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    const long long total = static_cast<long long>(4) * Cout * Cin;
+    if (i >= total) return;
+    const int ci = static_cast<int>(i % Cin);
+    const int row = static_cast<int>(i / Cin);
+    const int q = row / Cout, co = row % Cout;
+    out[i] = __float2bfloat16_rn(w[(static_cast<size_t>(ci) * Cout + co) * 4 + q]);
+}
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void *ptr = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(ptr);
+    });
+    return fn;
+}
+
+// NHWC bf16 activation view -> 4-D tensor map (C, W, H, N), box (64, bw, bh, 1), traversal stride es.
+int make_act_map(CUtensorMap *map, const void *base, int N, int H, int W, int C, int ld, int coff, int es) {
+    EncodeTiledFn enc = get_encode_fn();
+    MBS_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled entry point not available (no CUDA driver?)");
+    const char *p = static_cast<const char *>(base) + static_cast<size_t>(coff) * 2;
+    MBS_REQUIRE((reinterpret_cast<uintptr_t>(p) & 15) == 0, "activation view must be 16-byte aligned");
+    MBS_REQUIRE((ld * 2) % 16 == 0, "activation pixel stride must be a multiple of 16 bytes");
+    cuuint64_t dims[4] = {static_cast<cuuint64_t>(C), static_cast<cuuint64_t>(W), static_cast<cuuint64_t>(H),
+                          static_cast<cuuint64_t>(N)};
+    cuuint64_t strides[3] = {static_cast<cuuint64_t>(ld) * 2, static_cast<cuuint64_t>(W) * ld * 2,
+                             static_cast<cuuint64_t>(H) * W * ld * 2};
+    cuuint32_t box[4] = {static_cast<cuuint32_t>(BK), static_cast<cuuint32_t>(TILE_W * es),
+                         static_cast<cuuint32_t>(TILE_H * es), 1};
+    cuuint32_t estr[4] = {1, static_cast<cuuint32_t>(es), static_cast<cuuint32_t>(es), 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<char *>(p), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    MBS_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(activation N=%d H=%d W=%d C=%d ld=%d es=%d) failed: %d", N,
+                H, W, C, ld, es, static_cast<int>(r));
+    return 0;
+}
+
+// packed weights [rows][K] bf16 (K contiguous) -> 2-D tensor map, box (64, bn)
+int make_weight_map(CUtensorMap *map, const void *base, int rows, int K, int bn) {
+    EncodeTiledFn enc = get_encode_fn();
+    MBS_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled entry point not available (no CUDA driver?)");
+    MBS_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, "weights must be 16-byte aligned");
+    cuuint64_t dims[2] = {static_cast<cuuint64_t>(K), static_cast<cuuint64_t>(rows)};
+    cuuint64_t strides[1] = {static_cast<cuuint64_t>(K) * 2};
+    cuuint32_t box[2] = {static_cast<cuuint32_t>(BK), static_cast<cuuint32_t>(bn)};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    MBS_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(weights rows=%d K=%d) failed: %d", rows, K,
+                static_cast<int>(r));
+    return 0;
+}
+
+template <int BN, int STAGES>
+int launch_conv(const CUtensorMap &a0, const CUtensorMap &a1, const CUtensorMap &b, const ConvKParams &kp, int grid,
+                cudaStream_t stream) {
+    using Plan = SmemPlan<BN, STAGES>;
+    static bool configured = false;
+    if (!configured) {
+        MBS_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            Plan::DYN_BYTES));
+        configured = true;
+    }
+    conv_gemm_kernel<BN, STAGES><<<grid, NUM_THREADS, Plan::DYN_BYTES, stream>>>(a0, a1, b, kp);
+    MBS_CHECK_LAUNCH();
+    return 0;
+}
+
+}  // namespace
+
+extern "C" int mbs_conv_gemm(const mbs_conv_desc *d, void *stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    MBS_REQUIRE(d != nullptr, "null descriptor");
+    MBS_REQUIRE(d->mode >= 0 && d->mode <= 2, "bad conv mode %d", d->mode);
+    MBS_REQUIRE(d->C0 > 0 && d->C0 % BK == 0 && d->C1 >= 0 && d->C1 % BK == 0,
+                "input channels must be multiples of %d (got %d + %d)", BK, d->C0, d->C1);
+    MBS_REQUIRE(d->Cout > 0 && d->Cout % 64 == 0, "Cout must be a multiple of 64 (got %d)", d->Cout);
+    MBS_REQUIRE(d->mode != MBS_CONVT2X2_S2 || d->C1 == 0, "transposed conv takes a single source");
+    MBS_REQUIRE(d->mode != MBS_CONV3X3_S2 || (d->H % 2 == 0 && d->W % 2 == 0), "stride-2 conv needs even H, W");
+    MBS_REQUIRE(d->head_out == nullptr || (d->Cout == 64 && d->mode == MBS_CONV3X3_S1 && d->head_w),
+                "fused head needs Cout == 64, stride-1 conv and head weights");
+    MBS_REQUIRE(d->dst != nullptr || d->head_out != nullptr, "no output requested");
+    if (d->dst) {
+        MBS_REQUIRE(((reinterpret_cast<uintptr_t>(d->dst) + static_cast<size_t>(d->coffd) * 2) & 15) == 0 &&
+                        (d->ldd * 2) % 16 == 0,
+                    "destination view must be 16-byte aligned");
+    }
+
+    ConvKParams kp;
+    memset(&kp, 0, sizeof(kp));
+    kp.mode = d->mode;
+    kp.act = d->act;
+    const int es = d->mode == MBS_CONV3X3_S2 ? 2 : 1;
+    kp.Hm = d->mode == MBS_CONV3X3_S2 ? d->H / 2 : d->H;
+    kp.Wm = d->mode == MBS_CONV3X3_S2 ? d->W / 2 : d->W;
+    kp.tiles_x = mbs::cdiv(kp.Wm, TILE_W);
+    kp.tiles_y = mbs::cdiv(kp.Hm, TILE_H);
+    kp.chunks0 = d->C0 / BK;
+    kp.chunks1 = d->C1 / BK;
+    kp.taps = d->mode == MBS_CONVT2X2_S2 ? 1 : 9;
+    kp.Cout = d->Cout;
+    kp.bias = d->bias;
+    kp.scale = d->scale;
+    kp.shift = d->shift;
+    kp.dst = static_cast<__nv_bfloat16 *>(d->dst);
+    kp.ldd = d->ldd;
+    kp.coffd = d->coffd;
+    kp.Hd = d->mode == MBS_CONVT2X2_S2 ? 2 * d->H : kp.Hm;
+    kp.Wd = d->mode == MBS_CONVT2X2_S2 ? 2 * d->W : kp.Wm;
+    kp.head_w = d->head_out ? d->head_w : nullptr;
+    kp.head_b = d->head_b;
+    kp.head_out = d->head_out;
+
+    const int ncols = d->mode == MBS_CONVT2X2_S2 ? 4 * d->Cout : d->Cout;
+    const int K = kp.taps * (d->C0 + d->C1);
+    int bn = ncols % 256 == 0 ? 256 : (ncols % 128 == 0 ? 128 : 64);
+    kp.n_tiles = ncols / bn;
+
+    CUtensorMap a0, a1, b;
+    int rc = make_act_map(&a0, d->src0, d->N, d->H, d->W, d->C0, d->ld0, d->coff0, es);
+    if (rc) return rc;
+    if (d->C1 > 0) {
+        rc = make_act_map(&a1, d->src1, d->N, d->H, d->W, d->C1, d->ld1, d->coff1, es);
+        if (rc) return rc;
+    } else {
+        a1 = a0;
+    }
+    rc = make_weight_map(&b, d->weight, ncols, K, bn);
+    if (rc) return rc;
+
+    const long long grid_ll = static_cast<long long>(d->N) * kp.tiles_x * kp.tiles_y * kp.n_tiles;
+    MBS_REQUIRE(grid_ll > 0 && grid_ll < (1ll << 31), "grid too large");
+    const int grid = static_cast<int>(grid_ll);
+    if (bn == 256) return launch_conv<256, 4>(a0, a1, b, kp, grid, stream);
+    if (bn == 128) return launch_conv<128, 3>(a0, a1, b, kp, grid, stream);
+    return launch_conv<64, 4>(a0, a1, b, kp, grid, stream);
+}
+
+extern "C" int mbs_first_conv(const void *img, int in_dtype, int H, int W, int pad_y, int pad_x, float norm_lo,
+                              float norm_hi, const float *weight, const float *bias, const float *scale,
+                              const float *shift, int C, int act, void *out, int out_ld, int out_coff,
+                              void *stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    MBS_REQUIRE(C > 0 && C % 8 == 0 && C <= 256, "first conv: C must be a multiple of 8 and <= 256 (got %d)", C);
+    MBS_REQUIRE(((reinterpret_cast<uintptr_t>(out) + static_cast<size_t>(out_coff) * 2) & 15) == 0 &&
+                    (out_ld * 2) % 16 == 0,
+                "first conv: destination view must be 16-byte aligned");
+    const long long total = static_cast<long long>(H + pad_y) * (W + pad_x) * (C / 8);
+    const int threads = 256;
+    const long long blocks = (total + threads - 1) / threads;
+    MBS_REQUIRE(blocks < (1ll << 31), "first conv: grid too large");
+    const size_t smem = static_cast<size_t>(C) * 12 * sizeof(float);
+    __nv_bfloat16 *o = static_cast<__nv_bfloat16 *>(out);
+    switch (in_dtype) {
+        case MBS_IN_U8:
+            first_conv_kernel<uint8_t><<<static_cast<int>(blocks), threads, smem, stream>>>(
+                static_cast<const uint8_t *>(img), H, W, pad_y, pad_x, norm_lo, norm_hi, weight, bias, scale, shift, C,
+                act, o, out_ld, out_coff);
+            break;
+        case MBS_IN_U16:
+            first_conv_kernel<uint16_t><<<static_cast<int>(blocks), threads, smem, stream>>>(
+                static_cast<const uint16_t *>(img), H, W, pad_y, pad_x, norm_lo, norm_hi, weight, bias, scale, shift, C,
+                act, o, out_ld, out_coff);
+            break;
+        case MBS_IN_F32:
+            first_conv_kernel<float><<<static_cast<int>(blocks), threads, smem, stream>>>(
+                static_cast<const float *>(img), H, W, pad_y, pad_x, norm_lo, norm_hi, weight, bias, scale, shift, C,
+                act, o, out_ld, out_coff);
+            break;
+        default: MBS_REQUIRE(false, "first conv: unknown input dtype %d", in_dtype);
+    }
+    MBS_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int mbs_debug_flags(int reset) {
+    int v = 0;
+    if (cudaMemcpyFromSymbol(&v, g_mbar_timeout, sizeof(int)) != cudaSuccess) return -1;
+    if (reset) {
+        int z = 0;
+        cudaMemcpyToSymbol(g_mbar_timeout, &z, sizeof(int));
+    }
+    return v;
+}
+
+extern "C" int mbs_pack_conv3x3_weight(const float *w, int Cout, int Cin, void *packed, void *stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    const long long total = static_cast<long long>(Cout) * 9 * Cin;
+    pack_conv3x3_kernel<<<static_cast<int>((total + 255) / 256), 256, 0, stream>>>(
+        w, Cout, Cin, static_cast<__nv_bfloat16 *>(packed));
+    MBS_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int mbs_pack_convT2x2_weight(const float *w, int Cin, int Cout, void *packed, void *stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    const long long total = static_cast<long long>(4) * Cout * Cin;
+    pack_convT2x2_kernel<<<static_cast<int>((total + 255) / 256), 256, 0, stream>>>(
+        w, Cin, Cout, static_cast<__nv_bfloat16 *>(packed));
+    MBS_CHECK_LAUNCH();
+    return 0;
+}
