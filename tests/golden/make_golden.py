@@ -1,0 +1,63 @@
+"""Generates the committed golden fixtures under tests/golden/ (run in the build container).
+
+  python tests/golden/make_golden.py postproc     # oracle/postproc.py on seeded synthetic maps
+  python tests/golden/make_golden.py net          # the REAL reference DUNet (/root/reference) on CPU
+
+The post-processing goldens are produced by the oracle restatement (scikit-image cannot run in
+this image -> "parity unpinned" for the skimage pieces, see oracle/postproc.py); the network
+goldens are produced by importing the reference's own src/utils/unets.py, so they pin the
+network oracle (oracle/net.py) and the CUDA path to the real reference.
+"""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+
+
+def make_postproc():
+    from microbeseg_b200 import synthetic as sy
+    from oracle import postproc as op
+    cases = [(96, 128, 40, 11), (128, 128, 70, 12), (160, 100, 45, 13), (64, 64, 0, 14)]
+    for H, W, n_cells, seed in cases:
+        m = sy.synth_instance_mask(H, W, n_cells, seed)
+        border, cell = sy.synth_distance_maps(m, seed + 100)
+        out, im = op.distance_postprocessing(border, cell, 0.45, 0.10, return_intermediates=True)
+        np.savez_compressed(os.path.join(HERE, f"postproc_{H}x{W}_s{seed}.npz"), border=border, cell=cell,
+                            th_seed=0.45, th_cell=0.10, mask_u16=out, cell_smooth=im["cell"],
+                            n_markers=im["n_markers"])
+        print("postproc", H, W, seed, "objects", int(out.max()))
+
+
+def make_net():
+    sys.path.insert(0, "/root/reference")
+    import torch
+    from src.utils.unets import build_unet  # the real reference
+    from oracle import net as onet
+    torch.set_grad_enabled(False)
+    for tag, filters, act, H, W, seed in [("f64-128_relu", (64, 128), "relu", 64, 64, 21),
+                                          ("f64-256_mish", (64, 256), "mish", 48, 80, 22),
+                                          ("f64-1024_relu", (64, 1024), "relu", 64, 64, 23)]:
+        ref = build_unet("DU", act, "conv", "bn", torch.device("cpu"), 1, ch_in=1, ch_out=1, filters=list(filters))
+        sd = onet.seeded_state_dict(ref.state_dict(), seed)
+        ref.load_state_dict(sd)
+        ref.eval()
+        rng = np.random.default_rng(seed)
+        img = rng.integers(100, 4000, (H, W)).astype(np.uint16)
+        lo, hi = img.min(), img.max()
+        x = 2 * (img.astype(np.float32) - lo) / (hi - lo) - 1
+        border, cell = ref(torch.from_numpy(x[None, None]))
+        np.savez_compressed(os.path.join(HERE, f"net_{tag}_{H}x{W}_s{seed}.npz"), img=img, filters=np.array(filters),
+                            act=act, seed=seed, border=border[0, 0].numpy(), cell=cell[0, 0].numpy())
+        print("net", tag, float(border.abs().max()), float(cell.abs().max()))
+
+
+if __name__ == "__main__":
+    what = sys.argv[1:] or ["postproc", "net"]
+    if "postproc" in what:
+        make_postproc()
+    if "net" in what:
+        make_net()

@@ -1,0 +1,229 @@
+"""GPU parity tests: CUDA post-processing (through the C ABI) vs the oracle, bit-exact."""
+import ctypes
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+from scipy import ndimage
+
+from oracle import postproc as op
+from microbeseg_b200 import synthetic as sy
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+@pytest.fixture(scope="module")
+def pp(native_lib):
+    from microbeseg_b200 import postprocessing
+    return postprocessing
+
+
+def _dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def _front(native_lib, border, cell, th_seed=0.45, th_cell=0.10):
+    from microbeseg_b200 import _native as nat
+    H, W = cell.shape
+    b, c = _dev(border.astype(np.float32)), _dev(cell.astype(np.float32))
+    cs = torch.empty((H, W), dtype=torch.float32, device="cuda")
+    mask = torch.empty((H, W), dtype=torch.uint8, device="cuda")
+    seed = torch.empty((H, W), dtype=torch.uint8, device="cuda")
+    nat.check(native_lib.mbs_pp_front(b.data_ptr(), c.data_ptr(), H, W, W, th_seed, th_cell, cs.data_ptr(),
+                                      mask.data_ptr(), seed.data_ptr(), nat.stream_ptr()))
+    torch.cuda.synchronize()
+    return cs.cpu().numpy(), mask.cpu().numpy().astype(bool), seed.cpu().numpy().astype(bool)
+
+
+@pytest.mark.parametrize("shape", [(1, 1), (2, 3), (5, 4), (33, 31), (64, 64), (100, 37), (257, 300)])
+def test_front_end_bit_exact(native_lib, shape):
+    rng = np.random.default_rng(shape[0] * 1000 + shape[1])
+    cell = rng.normal(0.3, 0.4, shape).astype(np.float32)
+    border = rng.normal(0.2, 0.5, shape).astype(np.float32)
+    cs, mask, seed = _front(native_lib, border, cell)
+    ocs, omask, oseed = op.seed_mask_maps(border[..., None], cell[..., None], 0.45, 0.10)
+    assert np.array_equal(cs, ocs[..., 0])            # scipy.ndimage.gaussian_filter, bit for bit
+    assert np.array_equal(mask, omask[..., 0])
+    assert np.array_equal(seed, oseed[..., 0])
+
+
+def test_front_end_nan_inf(native_lib):
+    cell = np.full((8, 8), np.nan, np.float32)
+    border = np.full((8, 8), np.inf, np.float32)
+    cs, mask, seed = _front(native_lib, border, cell)
+    assert not mask.any() and not seed.any()
+
+
+@pytest.mark.parametrize("shape,p", [((1, 1), 1.0), ((7, 9), 0.5), ((64, 64), 0.45), ((130, 257), 0.6), ((300, 200), 0.3)])
+def test_label8_matches_ndimage(native_lib, shape, p):
+    from microbeseg_b200 import _native as nat
+    rng = np.random.default_rng(shape[1])
+    b = rng.random(shape) < p
+    H, W = shape
+    n = H * W
+    ws = torch.empty(n * 20 + (1 << 16), dtype=torch.uint8, device="cuda")
+    lab = torch.empty((H, W), dtype=torch.int32, device="cuda")
+    cnt = torch.zeros(1, dtype=torch.int32, device="cuda")
+    db = _dev(b.astype(np.uint8))
+    nat.check(native_lib.mbs_pp_label8(db.data_ptr(), H, W, lab.data_ptr(), cnt.data_ptr(),
+                                       ws.data_ptr(), ws.numel(), nat.stream_ptr()))
+    torch.cuda.synchronize()
+    ref, nref = op.label8(b)
+    assert int(cnt.item()) == nref
+    assert np.array_equal(lab.cpu().numpy(), ref)
+
+
+def _ws_gpu(native_lib, v, mk, mask, force=0):
+    from microbeseg_b200 import _native as nat
+    H, W = v.shape
+    n = H * W
+    ws = torch.empty(n * 32 + (1 << 16), dtype=torch.uint8, device="cuda")
+    out = torch.empty((H, W), dtype=torch.int32, device="cuda")
+    info = (ctypes.c_int64 * 8)()
+    dv, dmk, dmask = _dev(v.astype(np.float32)), _dev(mk.astype(np.int32)), _dev(mask.astype(np.uint8))
+    nat.check(native_lib.mbs_pp_watershed(dv.data_ptr(), dmk.data_ptr(),
+                                          dmask.data_ptr(), H, W, out.data_ptr(), ws.data_ptr(),
+                                          ws.numel(), ctypes.cast(info, ctypes.c_void_p), force, nat.stream_ptr()))
+    torch.cuda.synchronize()
+    return out.cpu().numpy(), list(info)
+
+
+def _random_flood_case(rng, quant):
+    H, W = int(rng.integers(3, 90)), int(rng.integers(3, 90))
+    v = rng.normal(size=(H, W))
+    if rng.random() < 0.6:
+        v = ndimage.gaussian_filter(v, rng.uniform(0.5, 4))
+    if quant:
+        v = np.round(v / v.std() * quant) / quant
+    v = v.astype(np.float32)
+    mask = rng.random((H, W)) < rng.uniform(0.5, 1.0)
+    mk = np.zeros((H, W), np.int32)
+    for k in range(int(rng.integers(1, 12))):
+        y, x = int(rng.integers(0, H)), int(rng.integers(0, W))
+        mk[y:y + int(rng.integers(1, 4)), x:x + int(rng.integers(1, 4))] = k + 1
+    return v, mk, mask
+
+
+def test_watershed_tie_free_random(native_lib):
+    rng = np.random.default_rng(77)
+    for _ in range(40):
+        v, mk, mask = _random_flood_case(rng, 0)
+        out, info = _ws_gpu(native_lib, v, mk, mask)
+        ref = op.watershed(v.astype(np.float64), mk, mask)
+        assert np.array_equal(out, ref)
+        assert info[3] == 0, "tie-free input must not need the sequential flood"
+
+
+def test_watershed_tie_heavy_random_uses_exact_fallback(native_lib):
+    rng = np.random.default_rng(78)
+    used = 0
+    for _ in range(40):
+        v, mk, mask = _random_flood_case(rng, int(rng.choice([2, 4, 16])))
+        out, info = _ws_gpu(native_lib, v, mk, mask)
+        ref = op.watershed(v.astype(np.float64), mk, mask)      # true skimage order incl. heap internals
+        assert np.array_equal(out, ref)
+        used += info[3]
+    assert used > 0
+
+
+def test_watershed_forced_sequential_and_flat_image(native_lib):
+    rng = np.random.default_rng(79)
+    v, mk, mask = _random_flood_case(rng, 0)
+    out, info = _ws_gpu(native_lib, v, mk, mask, force=1)
+    assert np.array_equal(out, op.watershed(v.astype(np.float64), mk, mask)) and info[3] == 1
+    # completely flat image (boundary_postprocessing floods image=mask): pure FIFO order
+    H, W = 40, 50
+    mask = rng.random((H, W)) < 0.9
+    mk = np.zeros((H, W), np.int32)
+    for k in range(6):
+        mk[int(rng.integers(0, H)), int(rng.integers(0, W))] = k + 1
+    v = mask.astype(np.float32)
+    out, info = _ws_gpu(native_lib, v, mk, mask)
+    assert np.array_equal(out, op.watershed(v.astype(np.float64), mk, mask))
+
+
+def test_golden_fixtures(pp):
+    for f in sorted(glob.glob(os.path.join(HERE, "golden", "postproc_*.npz"))):
+        g = np.load(f)
+        out = pp.distance_postprocessing(g["border"], g["cell"], float(g["th_seed"]), float(g["th_cell"]))
+        assert out.dtype == np.uint16 and out.shape == g["mask_u16"].shape
+        assert np.array_equal(out, g["mask_u16"]), f
+
+
+@pytest.mark.parametrize("H,W,cells,seed", [(128, 128, 60, 1), (512, 512, 300, 2), (300, 777, 250, 3),
+                                            (1024, 1024, 1300, 4)])
+def test_distance_postprocessing_bit_exact(pp, H, W, cells, seed):
+    m = sy.synth_instance_mask(H, W, cells, seed)
+    border, cell = sy.synth_distance_maps(m, seed + 50)
+    keep_b, keep_c = border.copy(), cell.copy()
+    out = pp.distance_postprocessing(border_prediction=border, cell_prediction=cell, th_cell=0.10, th_seed=0.45)
+    ref = op.distance_postprocessing(border, cell, 0.45, 0.10)
+    assert np.array_equal(border, keep_b) and np.array_equal(cell, keep_c)     # inputs untouched
+    assert np.array_equal(out, ref)
+    assert int(out.max()) > cells * 0.7
+    # (H,W) input, CUDA tensor input and other thresholds
+    out2 = pp.distance_postprocessing(torch.from_numpy(border[..., 0]).cuda(), torch.from_numpy(cell).cuda(), 0.35, 0.05)
+    assert np.array_equal(out2, op.distance_postprocessing(border, cell, 0.35, 0.05))
+
+
+def test_noisy_maps_with_pits(pp):
+    # heavy noise -> many non-marker minima (pits), removed seeds, split basins
+    m = sy.synth_instance_mask(384, 384, 200, 8)
+    border, cell = sy.synth_distance_maps(m, 9, noise=0.12)
+    out = pp.distance_postprocessing(border, cell, 0.45, 0.10)
+    assert np.array_equal(out, op.distance_postprocessing(border, cell, 0.45, 0.10))
+
+
+def test_edge_cases(pp):
+    z = np.zeros((40, 24, 1), np.float32)
+    assert (pp.distance_postprocessing(z, z, 0.45, 0.10) == 0).all()                 # no seeds
+    one = np.ones((40, 24, 1), np.float32)
+    out = pp.distance_postprocessing(z, one, 0.45, 0.10)                             # one seed floods all
+    assert np.array_equal(out, op.distance_postprocessing(z, one, 0.45, 0.10)) and (out == 1).all()
+    for shape in [(1, 1), (1, 9), (9, 1), (3, 5)]:
+        rng = np.random.default_rng(shape[0] + shape[1])
+        b = rng.random(shape + (1,)).astype(np.float32) * 0.3
+        c = rng.random(shape + (1,)).astype(np.float32)
+        assert np.array_equal(pp.distance_postprocessing(b, c, 0.45, 0.10), op.distance_postprocessing(b, c, 0.45, 0.10))
+
+
+def test_more_than_65535_labels_wrap(pp):
+    H = W = 1536
+    cell = np.zeros((H, W), np.float32)
+    yy, xx = np.mgrid[0:H, 0:W]
+    cell[((yy % 4) < 2) & ((xx % 5) < 3)] = 1.0          # 2x3 seeds on a 4x5 lattice -> 117k seeds
+    cell += np.random.default_rng(1).normal(0, 1e-3, (H, W)).astype(np.float32)
+    border = np.zeros((H, W), np.float32)
+    # th_cell high enough that the smoothed gaps fall out of the mask and seeds stay separate
+    out = pp.distance_postprocessing(border[..., None], cell[..., None], 0.45, 0.30)
+    ref = op.distance_postprocessing(border[..., None], cell[..., None], 0.45, 0.30)
+    from microbeseg_b200.postprocessing import last_info  # noqa: F401
+    assert np.array_equal(out, ref)
+    assert len(np.unique(ref)) > 60000
+
+
+def test_full_size_properties(pp):
+    # BASELINE config 3 size (4096^2, ~20k cells): size-independent properties + oracle spot check
+    m = sy.synth_instance_mask(4096, 4096, 20000, 4096)
+    border, cell = sy.synth_distance_maps(m, 4097)
+    b, c = torch.from_numpy(border[..., 0]).cuda(), torch.from_numpy(cell[..., 0]).cuda()
+    from microbeseg_b200 import postprocessing as P
+    out = P.distance_postprocessing_device(b, c, 0.45, 0.10, want_info=True).cpu().numpy().view(np.uint16)
+    info = dict(P.last_info)
+    cs = ndimage.gaussian_filter(cell, 0.5)[..., 0]
+    mask = cs > np.float32(0.10)
+    assert not (out[~mask] != 0).any()                      # nothing outside the mask
+    ids = np.unique(out[out > 0])
+    assert len(ids) == info["n_markers"] == ids.max()       # labels are exactly 1..m
+    assert 0.9 * 20000 < info["n_markers"] < 1.1 * 20000
+    # every label is one 4-connected region (flood from a single 8-connected marker inside a mask)
+    lab4, n4 = ndimage.label(out > 0)
+    # idempotence-style check: re-labelling by (out, component) gives the same count as labels
+    pairs = np.unique(np.stack([out[out > 0].astype(np.int64), lab4[out > 0].astype(np.int64)], 1), axis=0)
+    assert len(np.unique(pairs[:, 0])) == len(ids)
+    # oracle on a crop-independent sub-problem: full oracle run (takes a few seconds)
+    ref = op.distance_postprocessing(border, cell, 0.45, 0.10)
+    assert np.array_equal(out, ref)
