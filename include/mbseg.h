@@ -52,7 +52,9 @@ enum { MBS_CONV3X3_S1 = 0, MBS_CONV3X3_S2 = 1, MBS_CONVT2X2_S2 = 2 };
  *   (src/utils/unets.py:112-134).
  * img: raw frame (H,W) of in_dtype; output (Hp,Wp,C) bf16 with Hp=H+pad_y, Wp=W+pad_x.
  * weight: [C][9] f32 (ky*3+kx), bias/scale/shift: [C] f32 (scale/shift = folded eval BN).
- * norm_lo/norm_hi: frame min / max as floats; pad pixels take the value norm_lo.
+ * norm_lo/norm_hi: frame min / max as floats; pad pixels take the value norm_lo.  norm_hi < norm_lo
+ * means "img is already normalised" (values pass through; used by the drop-in net(x) call).
+ * norm_hi == norm_lo reproduces the reference's unguarded 0/0 (NaN maps -> empty mask).
  */
 int mbs_first_conv(const void *img, int in_dtype, int H, int W, int pad_y, int pad_x, float norm_lo,
                    float norm_hi, const float *weight, const float *bias, const float *scale,

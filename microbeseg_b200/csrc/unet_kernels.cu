@@ -397,7 +397,8 @@ __global__ void first_conv_kernel(const T *__restrict__ img, int H, int W, int p
             float raw = lo;  // zero_pad_model_input pad value = frame min (utils.py:124, infer.py:256)
             if (yy >= pad_y && xx >= pad_x) raw = static_cast<float>(img[static_cast<size_t>(yy - pad_y) * W + (xx - pad_x)]);
             // 2 * (f32(img) - min) / (max - min) - 1, evaluated left to right in f32 (infer.py:346)
-            v = __fsub_rn(__fdiv_rn(__fmul_rn(2.0f, __fsub_rn(raw, lo)), range), 1.0f);
+            // hi < lo: the caller already normalised the image (drop-in net(x) path) -> pass through
+            v = hi < lo ? raw : __fsub_rn(__fdiv_rn(__fmul_rn(2.0f, __fsub_rn(raw, lo)), range), 1.0f);
         }
         in[t] = v;
     }

@@ -1,0 +1,158 @@
+"""Frame loop of the reference's inference entry points on the CUDA path.
+
+Mirrors ``InferWorker.inference`` (src/inference/infer.py:328-376) and the per-frame loop of
+``infer_script_local.py:118-161``: per-frame min/max -> top/left padding to a tested size ->
+normalisation -> network -> crop of the pads -> distance post-processing -> uint16 mask.
+Differences are purely mechanical: the frame is uploaded raw (uint8/uint16) from pinned memory,
+normalisation + padding are fused into the first conv kernel, the distance maps never leave the
+GPU, and only the uint16 mask comes back.  Frames of a 2D+t stack are independent (per-frame
+min/max), so multi-GPU runs shard frames over ranks with no collective.
+"""
+import numpy as np
+import torch
+
+from . import postprocessing as pp
+from .utils import model_input_pads
+
+
+def shard_frames(num_frames, rank, world_size):
+    """Frame indices handled by ``rank``: t = rank (mod world_size)."""
+    return list(range(rank, num_frames, world_size))
+
+
+class FrameSegmenter:
+    """Reusable pinned/device staging for one frame size; double buffered."""
+
+    def __init__(self, net, ths, device=None):
+        self.net = net
+        self.th_cell, self.th_seed = float(ths[0]), float(ths[1])     # thresholds = [th_cell, th_seed]
+        self.device = torch.device(device) if device is not None else next(net.parameters()).device
+        if self.device.type != "cuda":
+            raise RuntimeError("microbeseg_b200.inference needs a CUDA device (no CPU fallback)")
+        self._stage = {}
+        self.copy_stream = torch.cuda.Stream(self.device)
+
+    def _staging(self, shape, dtype, slot):
+        key = (tuple(shape), dtype, slot)
+        st = self._stage.get(key)
+        if st is None:
+            tdt = {np.dtype(np.uint8): torch.uint8, np.dtype(np.uint16): torch.int16,
+                   np.dtype(np.float32): torch.float32}[np.dtype(dtype)]
+            st = dict(pin_in=torch.empty(shape, dtype=tdt).pin_memory(),
+                      dev_in=torch.empty(shape, dtype=tdt, device=self.device),
+                      dev_out=torch.empty(shape, dtype=torch.int16, device=self.device),
+                      pin_out=torch.empty(shape, dtype=torch.int16).pin_memory(),
+                      ev_in=torch.cuda.Event(), ev_out=torch.cuda.Event())
+            self._stage[key] = st
+        return st
+
+    @staticmethod
+    def _canon(frame):
+        frame = np.ascontiguousarray(frame)
+        if frame.dtype not in (np.uint8, np.uint16, np.float32):
+            frame = frame.astype(np.float32)
+        return frame
+
+    def submit(self, frame, slot=0, min_val=None, max_val=None, crop=None):
+        """Enqueue H2D + network + post-processing + D2H for one (H,W) frame; returns a handle.
+        ``crop=[py,px]``: the frame is already padded by the caller; crop the outputs by py/px."""
+        frame = self._canon(frame)
+        H, W = frame.shape
+        lo = frame.min() if min_val is None else min_val            # infer_script_local.py:124
+        hi = frame.max() if max_val is None else max_val
+        pads = model_input_pads(H, W) if crop is None else [0, 0]
+        if len(pads) < 2:
+            raise Exception('Image too big to pad. Use sliding windows')
+        st = self._staging((H, W), frame.dtype, slot)
+        st["crop"] = (0, 0) if crop is None else (int(crop[0]), int(crop[1]))
+        src = torch.from_numpy(frame.view(np.int16) if frame.dtype == np.uint16 else frame)
+        st["pin_in"].copy_(src)
+        main = torch.cuda.current_stream(self.device)
+        with torch.cuda.device(self.device):
+            st["dev_in"].copy_(st["pin_in"], non_blocking=True)
+            try:
+                border, cell = self.net.forward_frame(st["dev_in"], pads, float(lo), float(hi))
+            except RuntimeError:
+                # same contract as infer.py:352-356: a RuntimeError during net() yields an empty mask
+                st["dev_out"].zero_()
+                print('RuntimeError during inference (maybe not enough ram/vram?)')
+            else:
+                cy, cx = st["crop"]
+                b = border[0, 0, pads[0] + cy:, pads[1] + cx:]      # crop the pads (infer.py:358-359)
+                c = cell[0, 0, pads[0] + cy:, pads[1] + cx:]
+                dst = st["dev_out"] if (cy, cx) == (0, 0) else torch.empty(
+                    (H - cy, W - cx), dtype=torch.int16, device=self.device)
+                pp.distance_postprocessing_device(b, c, self.th_seed, self.th_cell, out=dst)
+                st["cropped"] = None if (cy, cx) == (0, 0) else dst
+            if st.get("cropped") is not None:
+                st["host_cropped"] = st["cropped"].cpu()
+            st["pin_out"].copy_(st["dev_out"], non_blocking=True)
+            st["ev_out"].record(main)
+        return st
+
+    @staticmethod
+    def result(handle):
+        handle["ev_out"].synchronize()
+        if handle.get("cropped") is not None:
+            return handle["host_cropped"].numpy().view(np.uint16).copy()
+        return handle["pin_out"].numpy().view(np.uint16).copy()
+
+    def segment(self, frame, min_val=None, max_val=None, crop=None):
+        return self.result(self.submit(frame, 0, min_val, max_val, crop))
+
+
+def segment_stack(net, stack, ths=(0.10, 0.45), device=None, frames=None, out=None):
+    """[T,H,W] stack -> [T,H,W] uint16 masks (infer_script_local.py:115-161).  ``frames`` selects the
+    frame indices to process (frame sharding); other rows of ``out`` are left untouched."""
+    stack = np.asarray(stack)
+    if stack.ndim == 2:
+        stack = stack[None]
+    T = stack.shape[0]
+    if out is None:
+        out = np.zeros(stack.shape, dtype=np.uint16)
+    seg = FrameSegmenter(net, ths, device)
+    todo = list(range(T)) if frames is None else list(frames)
+    pending = None
+    for k, t in enumerate(todo):
+        h = seg.submit(stack[t], slot=k & 1)
+        if pending is not None:
+            out[pending[0]] = seg.result(pending[1])
+        pending = (t, h)
+    if pending is not None:
+        out[pending[0]] = seg.result(pending[1])
+    return out
+
+
+class InferWorker:
+    """The numerical part of the reference's ``InferWorker`` (src/inference/infer.py:30-94, 328-376):
+    same constructor argument order; OMERO transport / Qt signals are out of scope."""
+
+    def __init__(self, img_id_list, inference_path, omero_username, omero_password, omero_host, omero_port, group_id,
+                 model, device, ths, channel=0, upload=True, overwrite=True, sliding_window=False,
+                 print_output=False):
+        import json
+        from pathlib import Path
+        from .unets import build_unet, get_weights
+        self.img_id_list, self.inference_path, self.device, self.ths = img_id_list, inference_path, device, ths
+        self.channel, self.upload, self.overwrite, self.print_output = channel, upload, overwrite, print_output
+        self.model = Path(model)
+        with open(self.model.parent / f"{self.model.stem}.json") as f:
+            self.model_settings = json.load(f)
+        arch = self.model_settings['architecture']
+        self.net = build_unet(unet_type=arch[0], act_fun=arch[2], pool_method=arch[1], normalization=arch[3],
+                              device=device, num_gpus=1, ch_in=1,
+                              ch_out=1 if self.model_settings['label_type'] == 'distance' else 3, filters=arch[4])
+        self.net = get_weights(net=self.net, weights=str(self.model.parent / f"{self.model.stem}.pth"),
+                               num_gpus=1, device=device)
+        self.net.eval()
+        self._seg = None
+
+    def inference(self, img, min_val, max_val, pads):
+        """``img`` is the already padded frame (infer.py:256-259); returns the uint16 mask without pads."""
+        if self.model_settings['label_type'] != 'distance':
+            raise NotImplementedError("boundary models are not built yet")
+        torch.set_grad_enabled(False)
+        if self._seg is None:
+            self._seg = FrameSegmenter(self.net, self.ths, self.device)
+        # the caller's padded frame is used as is (whatever its pad value); only the crop differs
+        return self._seg.segment(np.asarray(img), min_val, max_val, crop=pads)

