@@ -277,8 +277,9 @@ class _Engine:
         else:
             d.head_w, d.head_b, d.head_out = None, 0.0, None
         nat.check(self.L.mbs_conv_gemm(ctypes.byref(d), nat.stream_ptr()), name)
+        self.last_conv_launches += 1
 
-    def run(self, img, pad_y, pad_x, lo, hi):
+    def run(self, img, pad_y, pad_x, lo, hi, events=None):
         """img: [N,H,W] CUDA tensor (uint8 / uint16-as-int16 / float32).  hi < lo -> the values are
         already normalised (reference callers pass the normalised float image)."""
         if img.dtype not in _IN_CODES:
@@ -292,7 +293,10 @@ class _Engine:
             raise RuntimeError(f"model input {H}x{W} is not divisible by {div}; pad it with zero_pad_model_input")
         ch = self.chans
         img = img.contiguous()
+        self.last_conv_launches = 0
         with torch.cuda.device(self.device):
+            if events is not None:      # bench instrumentation: [start, after first conv, end]
+                events[0].record()
             t1 = [self._buf(f"t1_{l}", (n, H >> l, W >> l, ch[l])) for l in range(nl)]
             t2 = [self._buf(f"t2_{l}", (n, H >> l, W >> l, ch[l])) for l in range(nl)]
             skip = [self._buf(f"skip_{l}", (n, H >> l, W >> l, ch[l])) for l in range(nl)]
@@ -304,6 +308,8 @@ class _Engine:
                                                 packed.data_ptr(), bias.data_ptr(), scale.data_ptr(),
                                                 shift.data_ptr(), c0, self.act, t1[0][b].data_ptr(), c0, 0,
                                                 nat.stream_ptr()), "first_conv")
+            if events is not None:
+                events[1].record()
             for l in range(nl):
                 if l > 0:
                     self._conv(0, f"enc{l}a", n, H >> l, W >> l, pool[l - 1], None, t1[l])
@@ -325,6 +331,8 @@ class _Engine:
                         self._conv(0, f"{name}c{i}b", n, H, W, t2[0], None, None, head=self.p[name + "head"],
                                    head_out=out)
                 outs.append(out)
+            if events is not None:
+                events[2].record()
         return outs
 
 
