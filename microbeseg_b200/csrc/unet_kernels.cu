@@ -32,7 +32,8 @@ constexpr int TILE_H = 8;
 constexpr int BM = 128;  // TILE_W * TILE_H
 constexpr int BK = 64;   // bf16 elements per K chunk = 128 bytes = one swizzle row
 constexpr int A_BYTES = BM * BK * 2;
-constexpr int NUM_THREADS = 192;
+constexpr int EPI_WARPS = 8;                     // 2 per TMEM lane quadrant (column halves)
+constexpr int NUM_THREADS = 64 + 32 * EPI_WARPS;  // warp0 TMA, warp1 MMA, then the epilogue warps
 
 struct ConvKParams {
     int mode, act;
@@ -41,6 +42,7 @@ struct ConvKParams {
     int chunks0, chunks1;     // 64-channel chunks of source 0 / source 1
     int taps;                 // 9 (conv) or 1 (convT)
     int n_tiles;              // GEMM-N tiles
+    int num_tiles;            // total tiles (images x tiles_y x tiles_x x n_tiles)
     int Cout;
     const float *bias, *scale, *shift;
     __nv_bfloat16 *dst;
@@ -186,17 +188,22 @@ __device__ __forceinline__ float apply_act(float v, int act) {
 template <int BN, int STAGES>
 struct SmemPlan {
     static constexpr int B_BYTES = BN * BK * 2;
+    static constexpr int EPI_BYTES = EPI_WARPS * 1024 + 2 * 128 * 4;   // per warp 32 rows x 16 bf16; + head partials
     static constexpr int OFF_A = 0;
     static constexpr int OFF_B = STAGES * A_BYTES;
-    static constexpr int OFF_BAR = OFF_B + STAGES * B_BYTES;      // full[STAGES], empty[STAGES], tmem_full
-    static constexpr int OFF_TMEM = OFF_BAR + 8 * (2 * STAGES + 1);
-    static constexpr int OFF_PAR = OFF_TMEM + 8;                  // bias/scale/shift [3][BN] + head_w[BN]
-    static constexpr int TOTAL = OFF_PAR + 4 * BN * 4;
-    static constexpr int DYN_BYTES = TOTAL + 1024;                // slack for manual 1024-B alignment
+    static constexpr int OFF_EPI = OFF_B + STAGES * B_BYTES;
+    static constexpr int OFF_BAR = OFF_EPI + EPI_BYTES;           // full[S], empty[S], tmem_full[2], tmem_empty[2]
+    static constexpr int OFF_TMEM = OFF_BAR + 8 * (2 * STAGES + 4);
+    static constexpr int OFF_PAR = (OFF_TMEM + 8 + 15) / 16 * 16;  // bias/scale/shift/head_w, [4][Cout] floats (float4 reads)
+    static constexpr int FIXED = OFF_PAR + 1024;                  // + slack for the manual 1024-B alignment
+    static int dyn_bytes(int cout) { return FIXED + 4 * cout * 4; }
 };
 
-template <int BN, int STAGES>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+// Persistent, warp-specialised implicit-GEMM kernel.  Each CTA walks tiles t = blockIdx.x, +gridDim.x, ...
+// The smem ring (TMA <-> MMA) runs continuously across tiles; the accumulator is double buffered in
+// TMEM so that the epilogue of tile i overlaps the MMAs of tile i+1.
+template <int BN, int STAGES, int MIN_CTAS>
+__global__ void __launch_bounds__(NUM_THREADS, MIN_CTAS)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                  const __grid_constant__ CUtensorMap tmB, const ConvKParams p) {
     using Plan = SmemPlan<BN, STAGES>;
@@ -209,24 +216,16 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     const uint32_t sBar = base + Plan::OFF_BAR;
     auto full_bar = [&](int s) { return sBar + 8u * s; };
     auto empty_bar = [&](int s) { return sBar + 8u * (STAGES + s); };
-    const uint32_t tmem_full_bar = sBar + 8u * (2 * STAGES);
+    auto tfull_bar = [&](int b) { return sBar + 8u * (2 * STAGES + b); };
+    auto tempty_bar = [&](int b) { return sBar + 8u * (2 * STAGES + 2 + b); };
     volatile uint32_t *tmem_ptr = reinterpret_cast<volatile uint32_t *>(gbase + Plan::OFF_TMEM);
     float *s_par = reinterpret_cast<float *>(gbase + Plan::OFF_PAR);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-
-    // tile decode: n-tile fastest so that consecutive CTAs reuse the same A patch out of L2
-    const int n_tile = blockIdx.x % p.n_tiles;
-    int m_tile = blockIdx.x / p.n_tiles;
-    const int tx = m_tile % p.tiles_x;
-    m_tile /= p.tiles_x;
-    const int ty = m_tile % p.tiles_y;
-    const int img = m_tile / p.tiles_y;
-    const int x0 = tx * TILE_W, y0 = ty * TILE_H;
-    const int n0 = n_tile * BN;
     const int chunks = p.chunks0 + p.chunks1;
     const int num_k_iters = p.taps * chunks;
+    const int tiles_per_img = p.tiles_x * p.tiles_y;
 
     if (threadIdx.x == 0) {
         prefetch_tmap(&tmA0);
@@ -236,21 +235,19 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
             mbar_init(full_bar(s), 1);
             mbar_init(empty_bar(s), 1);
         }
-        mbar_init(tmem_full_bar, 1);
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(tfull_bar(b), 1);
+            mbar_init(tempty_bar(b), EPI_WARPS);   // one arrive per epilogue warp
+        }
         fence_barrier_init();
     }
-    if (warp == 1) {
-        tmem_alloc(smem_u32(const_cast<uint32_t *>(tmem_ptr)), BN);
-    }
+    if (warp == 1) tmem_alloc(smem_u32(const_cast<uint32_t *>(tmem_ptr)), 2 * BN);
     if (warp >= 2) {
-        // stage the per-channel epilogue parameters of this N tile
-        for (int j = threadIdx.x - 64; j < BN; j += NUM_THREADS - 64) {
-            const int col = n0 + j;
-            const int co = p.mode == MBS_CONVT2X2_S2 ? col % p.Cout : col;
-            s_par[j] = p.bias[co];
-            s_par[BN + j] = p.scale[co];
-            s_par[2 * BN + j] = p.shift[co];
-            s_par[3 * BN + j] = p.head_w ? p.head_w[co] : 0.0f;
+        for (int j = threadIdx.x - 64; j < p.Cout; j += NUM_THREADS - 64) {
+            s_par[j] = p.bias[j];
+            s_par[p.Cout + j] = p.scale[j];
+            s_par[2 * p.Cout + j] = p.shift[j];
+            s_par[3 * p.Cout + j] = p.head_w ? p.head_w[j] : 0.0f;
         }
     }
     tcgen05_fence_before();
@@ -261,29 +258,38 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     if (warp == 0) {
         if (lane == 0) {
             // ===== TMA producer =====
-            for (int it = 0; it < num_k_iters; ++it) {
-                const int s = it % STAGES;
-                const uint32_t ph = (it / STAGES) & 1;
-                mbar_wait(empty_bar(s), ph ^ 1u);
-                mbar_expect_tx(full_bar(s), A_BYTES + Plan::B_BYTES);
-                const int tap = it / chunks;
-                const int cc = it - tap * chunks;
-                int cx, cy;
-                if (p.mode == MBS_CONV3X3_S1) {
-                    cx = x0 + (tap % 3) - 1;
-                    cy = y0 + (tap / 3) - 1;
-                } else if (p.mode == MBS_CONV3X3_S2) {
-                    cx = 2 * x0 + (tap % 3) - 1;
-                    cy = 2 * y0 + (tap / 3) - 1;
-                } else {
-                    cx = x0;
-                    cy = y0;
+            int it_g = 0;  // ring position, continues across tiles
+            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+                const int n_tile = tile % p.n_tiles;
+                int m_tile = tile / p.n_tiles;
+                const int tx = m_tile % p.tiles_x;
+                const int ty = (m_tile / p.tiles_x) % p.tiles_y;
+                const int img = m_tile / tiles_per_img;
+                const int x0 = tx * TILE_W, y0 = ty * TILE_H, n0 = n_tile * BN;
+                for (int it = 0; it < num_k_iters; ++it, ++it_g) {
+                    const int s = it_g % STAGES;
+                    const uint32_t ph = (it_g / STAGES) & 1;
+                    mbar_wait(empty_bar(s), ph ^ 1u);
+                    mbar_expect_tx(full_bar(s), A_BYTES + Plan::B_BYTES);
+                    const int tap = it / chunks;
+                    const int cc = it - tap * chunks;
+                    int cx, cy;
+                    if (p.mode == MBS_CONV3X3_S1) {
+                        cx = x0 + (tap % 3) - 1;
+                        cy = y0 + (tap / 3) - 1;
+                    } else if (p.mode == MBS_CONV3X3_S2) {
+                        cx = 2 * x0 + (tap % 3) - 1;
+                        cy = 2 * y0 + (tap / 3) - 1;
+                    } else {
+                        cx = x0;
+                        cy = y0;
+                    }
+                    if (cc < p.chunks0)
+                        tma_load_4d(sA + s * A_BYTES, &tmA0, full_bar(s), cc * BK, cx, cy, img);
+                    else
+                        tma_load_4d(sA + s * A_BYTES, &tmA1, full_bar(s), (cc - p.chunks0) * BK, cx, cy, img);
+                    tma_load_2d(sB + s * Plan::B_BYTES, &tmB, full_bar(s), it * BK, n0);
                 }
-                if (cc < p.chunks0)
-                    tma_load_4d(sA + s * A_BYTES, &tmA0, full_bar(s), cc * BK, cx, cy, img);
-                else
-                    tma_load_4d(sA + s * A_BYTES, &tmA1, full_bar(s), (cc - p.chunks0) * BK, cx, cy, img);
-                tma_load_2d(sB + s * Plan::B_BYTES, &tmB, full_bar(s), it * BK, n0);
             }
         }
         __syncwarp();
@@ -291,76 +297,155 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         // ===== MMA issuer (single thread) =====
         if (lane == 0) {
             constexpr uint32_t idesc = make_idesc(BM, BN);
-            for (int it = 0; it < num_k_iters; ++it) {
-                const int s = it % STAGES;
-                const uint32_t ph = (it / STAGES) & 1;
-                mbar_wait(full_bar(s), ph);
+            int it_g = 0, lt = 0;
+            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++lt) {
+                const int buf = lt & 1;
+                mbar_wait(tempty_bar(buf), ((lt >> 1) & 1) ^ 1u);   // epilogue drained this accumulator
                 tcgen05_fence_after();
-                const uint64_t adesc = make_sw128_desc(sA + s * A_BYTES);
-                const uint64_t bdesc = make_sw128_desc(sB + s * Plan::B_BYTES);
+                const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(buf * BN);
+                for (int it = 0; it < num_k_iters; ++it, ++it_g) {
+                    const int s = it_g % STAGES;
+                    const uint32_t ph = (it_g / STAGES) & 1;
+                    mbar_wait(full_bar(s), ph);
+                    tcgen05_fence_after();
+                    const uint64_t adesc = make_sw128_desc(sA + s * A_BYTES);
+                    const uint64_t bdesc = make_sw128_desc(sB + s * Plan::B_BYTES);
 #pragma unroll
-                for (int k = 0; k < BK / 16; ++k) {
-                    // advance 32 bytes (16 bf16) inside the 128-byte swizzle row: +2 in the >>4 encoding
-                    umma_f16(tmem_base, adesc + 2u * k, bdesc + 2u * k, idesc, (it > 0 || k > 0) ? 1u : 0u);
+                    for (int k = 0; k < BK / 16; ++k) {
+                        // advance 32 bytes (16 bf16) inside the 128-byte swizzle row: +2 in the >>4 encoding
+                        umma_f16(tmem_d, adesc + 2u * k, bdesc + 2u * k, idesc, (it > 0 || k > 0) ? 1u : 0u);
+                    }
+                    umma_commit(empty_bar(s));  // frees the smem slot when these MMAs retire
                 }
-                umma_commit(empty_bar(s));  // frees the smem slot when these MMAs retire
+                umma_commit(tfull_bar(buf));     // accumulator of this tile complete
             }
-            umma_commit(tmem_full_bar);      // accumulator complete
         }
         __syncwarp();
     } else {
-        // ===== epilogue: TMEM -> registers -> bias/act/BN -> bf16 -> global =====
+        // ===== epilogue: TMEM -> registers -> bias/act/BN -> bf16 -> smem transpose -> coalesced global =====
+        const int e = warp - 2;
         const int quad = warp & 3;                 // TMEM lane quadrant this warp may access
+        const int half = e >> 2;                   // which half of the BN columns this warp converts
         const int row = quad * 32 + lane;          // tile row == pixel index inside the 8x16 patch
-        const int py = y0 + row / TILE_W;
-        const int px = x0 + row % TILE_W;
-        const bool in_img = (py < p.Hm) && (px < p.Wm);
-        mbar_wait(tmem_full_bar, 0);
-        tcgen05_fence_after();
-        float head_acc = 0.0f;
+        const uint32_t s_epi = base + Plan::OFF_EPI + static_cast<uint32_t>(e) * 1024u;
+        float *s_head = reinterpret_cast<float *>(gbase + Plan::OFF_EPI + EPI_WARPS * 1024);
+        const bool has_head = p.head_out != nullptr;
+        int lt = 0;
+        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++lt) {
+            const int n_tile = tile % p.n_tiles;
+            int m_tile = tile / p.n_tiles;
+            const int tx = m_tile % p.tiles_x;
+            const int ty = (m_tile / p.tiles_x) % p.tiles_y;
+            const int img = m_tile / tiles_per_img;
+            const int x0 = tx * TILE_W, y0 = ty * TILE_H, n0 = n_tile * BN;
+            const int buf = lt & 1;
+            mbar_wait(tfull_bar(buf), (lt >> 1) & 1);
+            tcgen05_fence_after();
+            float head_acc = 0.0f;
 #pragma unroll 1
-        for (int c = 0; c < BN; c += 32) {
-            uint32_t r[32];
-            tmem_ld32(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + c, r);
-            uint32_t packed[16];
-#pragma unroll
-            for (int j = 0; j < 32; j += 2) {
-                float v0 = __uint_as_float(r[j]) + s_par[c + j];
-                float v1 = __uint_as_float(r[j + 1]) + s_par[c + j + 1];
-                v0 = apply_act(v0, p.act);
-                v1 = apply_act(v1, p.act);
-                v0 = fmaf(v0, s_par[BN + c + j], s_par[2 * BN + c + j]);
-                v1 = fmaf(v1, s_par[BN + c + j + 1], s_par[2 * BN + c + j + 1]);
-                head_acc = fmaf(v0, s_par[3 * BN + c + j], head_acc);
-                head_acc = fmaf(v1, s_par[3 * BN + c + j + 1], head_acc);
-                __nv_bfloat162 h = __floats2bfloat162_rn(v0, v1);
-                packed[j >> 1] = *reinterpret_cast<uint32_t *>(&h);
-            }
-            if (in_img && p.dst) {
+            for (int c = half * (BN / 2); c < (half + 1) * (BN / 2); c += 32) {
+                uint32_t r[32];
+                tmem_ld32(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(buf * BN + c), r);
                 const int col = n0 + c;
-                size_t off;
+                int q = 0, co = col;
                 if (p.mode == MBS_CONVT2X2_S2) {
-                    const int q = col / p.Cout;
-                    const int co = col - q * p.Cout;
-                    const int oy = 2 * py + (q >> 1), ox = 2 * px + (q & 1);
-                    off = ((static_cast<size_t>(img) * p.Hd + oy) * p.Wd + ox) * p.ldd + p.coffd + co;
-                } else {
-                    off = ((static_cast<size_t>(img) * p.Hd + py) * p.Wd + px) * p.ldd + p.coffd + col;
+                    q = col / p.Cout;
+                    co = col - q * p.Cout;
                 }
-                uint4 *d4 = reinterpret_cast<uint4 *>(p.dst + off);
+                const float4 *pb = reinterpret_cast<const float4 *>(s_par + co);
+                const float4 *psc = reinterpret_cast<const float4 *>(s_par + p.Cout + co);
+                const float4 *psh = reinterpret_cast<const float4 *>(s_par + 2 * p.Cout + co);
+                float v[32];
 #pragma unroll
-                for (int q4 = 0; q4 < 4; ++q4)
-                    d4[q4] = make_uint4(packed[4 * q4], packed[4 * q4 + 1], packed[4 * q4 + 2], packed[4 * q4 + 3]);
+                for (int j = 0; j < 8; ++j) {
+                    const float4 b4 = pb[j], s4 = psc[j], t4 = psh[j];
+                    v[4 * j + 0] = fmaf(apply_act(__uint_as_float(r[4 * j + 0]) + b4.x, p.act), s4.x, t4.x);
+                    v[4 * j + 1] = fmaf(apply_act(__uint_as_float(r[4 * j + 1]) + b4.y, p.act), s4.y, t4.y);
+                    v[4 * j + 2] = fmaf(apply_act(__uint_as_float(r[4 * j + 2]) + b4.z, p.act), s4.z, t4.z);
+                    v[4 * j + 3] = fmaf(apply_act(__uint_as_float(r[4 * j + 3]) + b4.w, p.act), s4.w, t4.w);
+                }
+                if (has_head) {
+                    const float4 *phw = reinterpret_cast<const float4 *>(s_par + 3 * p.Cout + co);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const float4 w4 = phw[j];
+                        head_acc = fmaf(v[4 * j + 0], w4.x, head_acc);
+                        head_acc = fmaf(v[4 * j + 1], w4.y, head_acc);
+                        head_acc = fmaf(v[4 * j + 2], w4.z, head_acc);
+                        head_acc = fmaf(v[4 * j + 3], w4.w, head_acc);
+                    }
+                }
+                if (p.dst) {
+                    uint32_t packed[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        __nv_bfloat162 h2 = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+                        packed[j] = *reinterpret_cast<uint32_t *>(&h2);
+                    }
+                    // two passes of 16 columns: stage 32 rows x 32 B (16-byte chunks XOR-swizzled, conflict free),
+                    // then 2 lanes write one pixel's 32 contiguous bytes (a full sector), 16 pixels per instruction
+#pragma unroll
+                    for (int hh = 0; hh < 2; ++hh) {
+#pragma unroll
+                        for (int ch = 0; ch < 2; ++ch) {
+                            const uint32_t a = s_epi + lane * 32u + static_cast<uint32_t>((ch ^ ((lane >> 2) & 1)) * 16);
+                            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a),
+                                         "r"(packed[8 * hh + 4 * ch]), "r"(packed[8 * hh + 4 * ch + 1]),
+                                         "r"(packed[8 * hh + 4 * ch + 2]), "r"(packed[8 * hh + 4 * ch + 3])
+                                         : "memory");
+                        }
+                        __syncwarp();
+#pragma unroll
+                        for (int i = 0; i < 2; ++i) {
+                            const int rr = i * 16 + (lane >> 1);          // row inside this warp's 32
+                            const int ch = lane & 1;
+                            const int trow = quad * 32 + rr;
+                            const int qy = y0 + trow / TILE_W, qx = x0 + trow % TILE_W;
+                            uint32_t v0, v1, v2, v3;
+                            const uint32_t a = s_epi + rr * 32u + static_cast<uint32_t>((ch ^ ((rr >> 2) & 1)) * 16);
+                            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                                         : "=r"(v0), "=r"(v1), "=r"(v2), "=r"(v3)
+                                         : "r"(a)
+                                         : "memory");
+                            if (qy < p.Hm && qx < p.Wm) {
+                                size_t off;
+                                if (p.mode == MBS_CONVT2X2_S2) {
+                                    const int oy = 2 * qy + (q >> 1), ox = 2 * qx + (q & 1);
+                                    off = ((static_cast<size_t>(img) * p.Hd + oy) * p.Wd + ox) * p.ldd + p.coffd + co;
+                                } else {
+                                    off = ((static_cast<size_t>(img) * p.Hd + qy) * p.Wd + qx) * p.ldd + p.coffd + col;
+                                }
+                                *reinterpret_cast<uint4 *>(p.dst + off + hh * 16 + ch * 8) = make_uint4(v0, v1, v2, v3);
+                            }
+                        }
+                        __syncwarp();
+                    }
+                }
+            }
+            // all TMEM reads of this tile are complete (tcgen05.wait::ld inside tmem_ld32)
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+                asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tempty_bar(buf)) : "memory");
+            }
+            if (has_head) {
+                // the two column-half warps of a quadrant combine their partial dot products through smem
+                float *slot = s_head + (lt & 1) * 128 + row;
+                if (half == 1) *slot = head_acc;
+                asm volatile("bar.sync %0, 64;" ::"r"(1 + quad) : "memory");
+                if (half == 0) {
+                    const int py = y0 + row / TILE_W, px = x0 + row % TILE_W;
+                    if (py < p.Hm && px < p.Wm)
+                        p.head_out[(static_cast<size_t>(img) * p.Hm + py) * p.Wm + px] = (head_acc + *slot) + p.head_b;
+                }
             }
         }
-        if (p.head_out && in_img)
-            p.head_out[(static_cast<size_t>(img) * p.Hm + py) * p.Wm + px] = head_acc + p.head_b;
-        tcgen05_fence_before();
     }
+    tcgen05_fence_before();
     __syncthreads();
     if (warp == 1) {
         tcgen05_fence_after();
-        tmem_dealloc(tmem_base, BN);
+        tmem_dealloc(tmem_base, 2 * BN);
     }
 }
 
@@ -504,17 +589,29 @@ int make_weight_map(CUtensorMap *map, const void *base, int rows, int K, int bn)
     return 0;
 }
 
-template <int BN, int STAGES>
-int launch_conv(const CUtensorMap &a0, const CUtensorMap &a1, const CUtensorMap &b, const ConvKParams &kp, int grid,
+int sm_count() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    }
+    return n;
+}
+
+template <int BN, int STAGES, int CTAS_PER_SM>
+int launch_conv(const CUtensorMap &a0, const CUtensorMap &a1, const CUtensorMap &b, const ConvKParams &kp,
                 cudaStream_t stream) {
     using Plan = SmemPlan<BN, STAGES>;
-    static bool configured = false;
-    if (!configured) {
-        MBS_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                            Plan::DYN_BYTES));
-        configured = true;
+    static int configured_bytes = 0;
+    const int dyn = Plan::dyn_bytes(kp.Cout);
+    if (dyn > configured_bytes) {
+        MBS_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<BN, STAGES, CTAS_PER_SM>,
+                                            cudaFuncAttributeMaxDynamicSharedMemorySize, dyn));
+        configured_bytes = dyn;
     }
-    conv_gemm_kernel<BN, STAGES><<<grid, NUM_THREADS, Plan::DYN_BYTES, stream>>>(a0, a1, b, kp);
+    const int grid = kp.num_tiles < sm_count() * CTAS_PER_SM ? kp.num_tiles : sm_count() * CTAS_PER_SM;
+    conv_gemm_kernel<BN, STAGES, CTAS_PER_SM><<<grid, NUM_THREADS, dyn, stream>>>(a0, a1, b, kp);
     MBS_CHECK_LAUNCH();
     return 0;
 }
@@ -567,6 +664,8 @@ extern "C" int mbs_conv_gemm(const mbs_conv_desc *d, void *stream_) {
     const int ncols = d->mode == MBS_CONVT2X2_S2 ? 4 * d->Cout : d->Cout;
     const int K = kp.taps * (d->C0 + d->C1);
     int bn = ncols % 256 == 0 ? 256 : (ncols % 128 == 0 ? 128 : 64);
+    // transposed convs have a short K loop and are epilogue/bandwidth bound: prefer two resident CTAs
+    if (d->mode == MBS_CONVT2X2_S2 && d->C0 <= 256) bn = 128;
     kp.n_tiles = ncols / bn;
 
     CUtensorMap a0, a1, b;
@@ -581,12 +680,13 @@ extern "C" int mbs_conv_gemm(const mbs_conv_desc *d, void *stream_) {
     rc = make_weight_map(&b, d->weight, ncols, K, bn);
     if (rc) return rc;
 
-    const long long grid_ll = static_cast<long long>(d->N) * kp.tiles_x * kp.tiles_y * kp.n_tiles;
-    MBS_REQUIRE(grid_ll > 0 && grid_ll < (1ll << 31), "grid too large");
-    const int grid = static_cast<int>(grid_ll);
-    if (bn == 256) return launch_conv<256, 4>(a0, a1, b, kp, grid, stream);
-    if (bn == 128) return launch_conv<128, 3>(a0, a1, b, kp, grid, stream);
-    return launch_conv<64, 4>(a0, a1, b, kp, grid, stream);
+    const long long tiles_ll = static_cast<long long>(d->N) * kp.tiles_x * kp.tiles_y * kp.n_tiles;
+    MBS_REQUIRE(tiles_ll > 0 && tiles_ll < (1ll << 31), "too many tiles");
+    kp.num_tiles = static_cast<int>(tiles_ll);
+    MBS_REQUIRE(d->Cout <= 1024, "Cout > 1024 is not supported by the epilogue parameter staging");
+    if (bn == 256) return launch_conv<256, 4, 1>(a0, a1, b, kp, stream);
+    if (bn == 128) return launch_conv<128, 3, 2>(a0, a1, b, kp, stream);
+    return launch_conv<64, 4, 2>(a0, a1, b, kp, stream);
 }
 
 extern "C" int mbs_first_conv(const void *img, int in_dtype, int H, int W, int pad_y, int pad_x, float norm_lo,
