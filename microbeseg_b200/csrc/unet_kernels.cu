@@ -358,11 +358,39 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                 float v[32];
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
-                    const float4 b4 = pb[j], s4 = psc[j], t4 = psh[j];
-                    v[4 * j + 0] = fmaf(apply_act(__uint_as_float(r[4 * j + 0]) + b4.x, p.act), s4.x, t4.x);
-                    v[4 * j + 1] = fmaf(apply_act(__uint_as_float(r[4 * j + 1]) + b4.y, p.act), s4.y, t4.y);
-                    v[4 * j + 2] = fmaf(apply_act(__uint_as_float(r[4 * j + 2]) + b4.z, p.act), s4.z, t4.z);
-                    v[4 * j + 3] = fmaf(apply_act(__uint_as_float(r[4 * j + 3]) + b4.w, p.act), s4.w, t4.w);
+                    const float4 b4 = pb[j];
+                    v[4 * j + 0] = __uint_as_float(r[4 * j + 0]) + b4.x;
+                    v[4 * j + 1] = __uint_as_float(r[4 * j + 1]) + b4.y;
+                    v[4 * j + 2] = __uint_as_float(r[4 * j + 2]) + b4.z;
+                    v[4 * j + 3] = __uint_as_float(r[4 * j + 3]) + b4.w;
+                }
+                // one uniform branch per chunk (a per-element switch costs an indirect branch each)
+                switch (p.act) {
+                    case MBS_ACT_RELU:
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.0f);
+                        break;
+                    case MBS_ACT_LEAKYRELU:
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = v[j] > 0.0f ? v[j] : 0.01f * v[j];
+                        break;
+                    case MBS_ACT_ELU:
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = v[j] > 0.0f ? v[j] : expm1f(v[j]);
+                        break;
+                    case MBS_ACT_MISH:
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], MBS_ACT_MISH);
+                        break;
+                    default: break;
+                }
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float4 s4 = psc[j], t4 = psh[j];
+                    v[4 * j + 0] = fmaf(v[4 * j + 0], s4.x, t4.x);
+                    v[4 * j + 1] = fmaf(v[4 * j + 1], s4.y, t4.y);
+                    v[4 * j + 2] = fmaf(v[4 * j + 2], s4.z, t4.z);
+                    v[4 * j + 3] = fmaf(v[4 * j + 3], s4.w, t4.w);
                 }
                 if (has_head) {
                     const float4 *phw = reinterpret_cast<const float4 *>(s_par + 3 * p.Cout + co);
