@@ -1,0 +1,72 @@
+"""Host-side logic of the multi-GPU path (frame sharding, no collective on the data path), run with
+two gloo ranks on CPU; and the bench reference arm's JSON contract."""
+import json
+import os
+import subprocess
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _worker(rank, world, port, T, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    sys.path.insert(0, ROOT)
+    from microbeseg_b200.inference import shard_frames
+    mine = shard_frames(T, rank, world)
+    # each rank "segments" its frames (stand-in: frame index + 1) into its rows of the result array
+    out = np.zeros((T, 4), dtype=np.int64)
+    for t in mine:
+        out[t] = t + 1
+    # the host gathers masks; rows are disjoint, so a SUM reduce is a pure gather
+    ten = torch.from_numpy(out)
+    dist.all_reduce(ten, op=dist.ReduceOp.SUM)
+    times = torch.tensor([float(rank + 1)])
+    dist.all_reduce(times, op=dist.ReduceOp.MAX)          # max-over-ranks timing rule
+    if rank == 0:
+        q.put((ten.numpy().tolist(), float(times.item()), mine))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_frame_sharding_two_ranks_gloo():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    T, world, port = 7, 2, 29613
+    procs = [ctx.Process(target=_worker, args=(r, world, port, T, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res, tmax, mine0 = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert [row[0] for row in res] == list(range(1, T + 1))     # every frame exactly once
+    assert tmax == 2.0 and mine0 == [0, 2, 4, 6]
+
+
+def test_bench_reference_arm_contract():
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--ref-size", "128",
+                          "--steps-ref", "1", "--warmup-ref", "0"], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["unit"] == "Mpx/s" and line["value"] > 0
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["higher_is_better"] is True
+
+
+def test_zero_pad_model_input_matches_reference_semantics():
+    from microbeseg_b200.utils import min_max_normalization, model_input_pads, zero_pad_model_input
+    img = np.arange(1000 * 1000, dtype=np.uint16).reshape(1000, 1000)
+    out, pads = zero_pad_model_input(img, pad_val=7)
+    assert pads == [24, 24] and out.shape == (1024, 1024)
+    assert (out[:24] == 7).all() and (out[:, :24] == 7).all() and np.array_equal(out[24:, 24:], img)
+    assert model_input_pads(2048, 2048) == [0, 0] and model_input_pads(65, 8192) == [63, 0]
+    assert model_input_pads(9000, 100) == [28]          # reference quirk: one pad only, no exception
+    x = min_max_normalization(np.array([[0, 5, 10]], np.uint16))
+    assert x.dtype == np.float32 and x.tolist() == [[-1.0, 0.0, 1.0]]
