@@ -254,7 +254,7 @@ def main():
     n_conv_launch = eng.last_conv_launches
     conv_flops = (FLOP_PER_PX - FLOP_PER_PX_FIRST) * size * size
     achieved = conv_flops / (conv_ms_frame / 1e3) / 1e12
-    roofline = {"bound": "tensor", "kernel": "conv_gemm_kernel (tcgen05 implicit GEMM, all 39 launches of one frame)",
+    roofline = {"bound": "tensor", "kernel": "conv_gemm_kernel (tcgen05 implicit GEMM, all tensor-core launches of one frame)",
                 "achieved": achieved, "peak": peaks["tf_sustained"], "unit": "TFLOP/s", "frac": achieved / peaks["tf_sustained"],
                 "peak_source": peaks["src"] + " (sustained cuBLAS bf16)", "traffic": None,
                 "launches_per_frame": n_conv_launch, "avg_launch_ms": conv_ms_frame / max(n_conv_launch, 1),
