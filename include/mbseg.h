@@ -117,6 +117,26 @@ int mbs_pp_watershed(const float *image, const int32_t *markers, const uint8_t *
                      int32_t *labels_out, void *workspace, size_t workspace_bytes,
                      int64_t *info_host, int force_sequential, void *stream);
 
+/* ---------------------------------------------------------------------------------------- */
+/* training-label generation, distance method (replaces src/training/train_data_representations */
+/* .py:261-361 distance_label + :102-126 border_label + :40-72 bottom_hat_closing, and the     */
+/* max_mal of src/training/train.py:74-79); batched over crops                                 */
+/* ---------------------------------------------------------------------------------------- */
+size_t mbs_labels_workspace_bytes(int n_crops, int H, int W, int max_id);
+/* masks: uint16 [n_crops][H][W] instance ids (0 = background, ids <= max_id).
+ * max_mal_out: int32 [n_crops] = int(ceil(max regionprops.major_axis_length)) per crop. */
+int mbs_labels_max_mal(const uint16_t *masks, int n_crops, int H, int W, int max_id, int32_t *max_mal_out,
+                       void *workspace, size_t workspace_bytes, void *stream);
+/* search_radius >= 0: used for every crop (get_label passes int(ceil(0.75*max_mal)));
+ * search_radius < 0: derived per crop from its own max_mal on the device; radius_hint (>= the
+ * largest radius in the batch, or -1) only sizes the shared-memory window.
+ * cell_dist / neighbor_dist: float32 [n_crops][H][W].  error_out (optional, int32 [n_crops]):
+ * bit 0 = an instance window/bounding box did not fit in shared memory, bit 1 = more than 4096
+ * gap components. */
+int mbs_distance_labels(const uint16_t *masks, int n_crops, int H, int W, int max_id, int search_radius,
+                        int radius_hint, float *cell_dist, float *neighbor_dist, int32_t *max_mal_out,
+                        int32_t *error_out, void *workspace, size_t workspace_bytes, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,628 @@
+// Training-label generation for the distance method on the GPU (batched over crops).
+//
+// Replaces, per instance-mask crop:
+//   src/training/train.py:74-79                       max_mal = ceil(max regionprops.major_axis_length)
+//   src/training/train_data_representations.py:11-37  get_label(.., 'distance', max_mal)
+//   train_data_representations.py:261-361             distance_label  (cell + neighbour distances)
+//   train_data_representations.py:102-126             border_label
+//   train_data_representations.py:40-72               bottom_hat_closing
+//
+// The reference loops over instances in Python and runs two scipy EDTs per instance on a
+// (2R)x(2R) window plus a full-image binary_closing per instance.  Here one CTA owns one instance:
+// the window lives in shared memory, the two exact Euclidean distance transforms are done as a
+// column scan + row minimisation on integer squared distances (sqrt/division in float64 exactly as
+// scipy/numpy), and every pixel is written by the CTA of its own instance only, so the reference's
+// "+=" accumulation onto zeros is reproduced without atomics.  Everything else (border pixels,
+// bottom-hat gaps, gap statistics, rescaling, grey closing) is per-pixel / per-gap work.
+#include <cuda_runtime.h>
+
+#include <climits>
+#include <cstdint>
+#include <cstring>
+
+#include "../../include/mbseg.h"
+#include "common.cuh"
+
+namespace {
+
+struct CellStats {
+    unsigned long long cnt, sy, sx, syy, sxx, sxy;
+    int y0, y1, x0, x1;        // bounding box (inclusive)
+    int wy0, wy1, wx0, wx1;    // search window [wy0,wy1) x [wx0,wx1)
+};
+struct GapStats {
+    unsigned long long cnt, sy, sx, syy, sxx, sxy;
+    double bsum;               // sum of the raw neighbour map over the gap's outer 3x3 boundary
+};
+struct CropInfo {
+    int max_mal;               // ceil(max major axis length)
+    int radius;                // search radius actually used
+    int n_gaps;
+    int error;                 // bit 0: window too large for shared memory, bit 1: too many gaps
+};
+
+constexpr unsigned short kInf16 = 0xFFFF;
+
+__global__ void lab_init_stats_kernel(CellStats *cs, int total) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    CellStats z;
+    memset(&z, 0, sizeof(z));
+    z.y0 = INT_MAX; z.x0 = INT_MAX; z.y1 = -1; z.x1 = -1;
+    cs[i] = z;
+}
+
+__global__ void lab_accum_kernel(const uint16_t *__restrict__ masks, int H, int W, int ids, CellStats *cs) {
+    const int crop = blockIdx.z;
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= W || y >= H) return;
+    const int id = masks[(static_cast<size_t>(crop) * H + y) * W + x];
+    if (id == 0 || id >= ids) return;
+    CellStats *s = cs + static_cast<size_t>(crop) * ids + id;
+    atomicAdd(&s->cnt, 1ull);
+    atomicAdd(&s->sy, static_cast<unsigned long long>(y));
+    atomicAdd(&s->sx, static_cast<unsigned long long>(x));
+    atomicAdd(&s->syy, static_cast<unsigned long long>(y) * y);
+    atomicAdd(&s->sxx, static_cast<unsigned long long>(x) * x);
+    atomicAdd(&s->sxy, static_cast<unsigned long long>(x) * y);
+    atomicMin(&s->y0, y); atomicMax(&s->y1, y);
+    atomicMin(&s->x0, x); atomicMax(&s->x1, x);
+}
+
+// 4*sqrt(eigenvalue) of the inertia tensor [[mu02, -mu11], [-mu11, mu20]] / n  (skimage regionprops)
+__device__ void axis_lengths(unsigned long long cnt, unsigned long long sy, unsigned long long sx,
+                             unsigned long long syy, unsigned long long sxx, unsigned long long sxy, double *major,
+                             double *minor) {
+    const double n = static_cast<double>(cnt);
+    const double cy = static_cast<double>(sy) / n, cx = static_cast<double>(sx) / n;
+    const double mu20 = static_cast<double>(syy) - n * cy * cy;
+    const double mu02 = static_cast<double>(sxx) - n * cx * cx;
+    const double mu11 = static_cast<double>(sxy) - n * cx * cy;
+    const double a = mu02 / n, c = mu20 / n, b = -mu11 / n;
+    const double h = 0.5 * (a + c), d = sqrt(0.25 * (a - c) * (a - c) + b * b);
+    const double e1 = fmax(h + d, 0.0), e2 = fmax(h - d, 0.0);
+    *major = 4.0 * sqrt(e1);
+    *minor = 4.0 * sqrt(e2);
+}
+
+__global__ void lab_axes_kernel(const CellStats *cs, int ids, int total, CropInfo *info) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const CellStats s = cs[i];
+    if (s.cnt == 0) return;
+    double major, minor;
+    axis_lengths(s.cnt, s.sy, s.sx, s.syy, s.sxx, s.sxy, &major, &minor);
+    atomicMax(&info[i / ids].max_mal, static_cast<int>(ceil(major)));
+}
+
+__global__ void lab_window_kernel(CellStats *cs, int ids, int total, int H, int W, CropInfo *info, int radius_override) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    CropInfo *ci = info + i / ids;
+    // get_label: search_radius = int(np.ceil(0.75 * max_mal))
+    const int R = radius_override >= 0 ? radius_override : static_cast<int>(ceil(0.75 * static_cast<double>(ci->max_mal)));
+    if (i % ids == 0) ci->radius = R;
+    CellStats *s = cs + i;
+    if (s->cnt == 0) return;
+    const double n = static_cast<double>(s->cnt);
+    const double cy = rint(static_cast<double>(s->sy) / n), cx = rint(static_cast<double>(s->sx) / n);   // np.round
+    s->wy0 = static_cast<int>(fmax(cy - R, 0.0));
+    s->wy1 = static_cast<int>(fmin(cy + R, static_cast<double>(H)));
+    s->wx0 = static_cast<int>(fmax(cx - R, 0.0));
+    s->wx1 = static_cast<int>(fmin(cx + R, static_cast<double>(W)));
+}
+
+// ---------------------------------------------------------------------------------------------
+// one CTA per (instance, crop): exact EDT of the instance and of "everything but the other
+// instances" inside the search window (distance_label :280-330)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+lab_cell_kernel(const uint16_t *__restrict__ masks, int H, int W, int ids, const CellStats *cs, CropInfo *info,
+                float *__restrict__ cell_dist, double *__restrict__ nraw, int smem_cap_elems) {
+    const int crop = blockIdx.y;
+    const int id = blockIdx.x + 1;
+    if (id >= ids) return;
+    const CellStats s = cs[static_cast<size_t>(crop) * ids + id];
+    if (s.cnt == 0) return;
+    const int wh = s.wy1 - s.wy0, ww = s.wx1 - s.wx0;
+    if (wh <= 0 || ww <= 0) return;           // empty crop: np.max(...) of an empty EDT -> skipped
+    if (wh * ww > smem_cap_elems) {
+        if (threadIdx.x == 0) atomicOr(&info[crop].error, 1);
+        return;
+    }
+    extern __shared__ unsigned short sm[];
+    unsigned short *lab = sm;                 // [wh][ww] labels
+    unsigned short *g1 = sm + wh * ww;        // vertical distance to the nearest pixel with label != id (own pixels)
+    unsigned short *g2 = g1 + wh * ww;        // vertical distance to the nearest pixel of ANOTHER instance
+    __shared__ unsigned int s_max1, s_max2, s_any_bg, s_any_other, s_any_own;
+    if (threadIdx.x == 0) { s_max1 = 0; s_max2 = 0; s_any_bg = 0; s_any_other = 0; s_any_own = 0; }
+    const uint16_t *m = masks + static_cast<size_t>(crop) * H * W;
+    for (int i = threadIdx.x; i < wh * ww; i += blockDim.x) {
+        const int y = i / ww, x = i - y * ww;
+        lab[i] = m[static_cast<size_t>(s.wy0 + y) * W + s.wx0 + x];
+    }
+    __syncthreads();
+    // column scans (one thread per column): nearest site above / below
+    for (int x = threadIdx.x; x < ww; x += blockDim.x) {
+        int d1 = -1, d2 = -1;                 // distance to the last site seen going down (-1: none yet)
+        bool bg = false, other = false, own = false;
+        for (int y = 0; y < wh; ++y) {
+            const int l = lab[y * ww + x];
+            const bool site1 = l != id, site2 = l != 0 && l != id;
+            bg |= site1; other |= site2; own |= !site1;
+            d1 = site1 ? 0 : (d1 < 0 ? -1 : d1 + 1);
+            d2 = site2 ? 0 : (d2 < 0 ? -1 : d2 + 1);
+            g1[y * ww + x] = d1 < 0 ? kInf16 : static_cast<unsigned short>(d1);
+            g2[y * ww + x] = d2 < 0 ? kInf16 : static_cast<unsigned short>(d2);
+        }
+        d1 = -1; d2 = -1;
+        for (int y = wh - 1; y >= 0; --y) {
+            const int l = lab[y * ww + x];
+            const bool site1 = l != id, site2 = l != 0 && l != id;
+            d1 = site1 ? 0 : (d1 < 0 ? -1 : d1 + 1);
+            d2 = site2 ? 0 : (d2 < 0 ? -1 : d2 + 1);
+            if (d1 >= 0 && d1 < g1[y * ww + x]) g1[y * ww + x] = static_cast<unsigned short>(d1);
+            if (d2 >= 0 && d2 < g2[y * ww + x]) g2[y * ww + x] = static_cast<unsigned short>(d2);
+        }
+        if (bg) s_any_bg = 1;
+        if (other) s_any_other = 1;
+        if (own) s_any_own = 1;
+    }
+    __syncthreads();
+    if (!s_any_own) return;                   // instance has no pixel inside its window: max EDT == 0 -> `continue`
+    const bool any_bg = s_any_bg != 0, any_other = s_any_other != 0;
+    // row minimisation for the instance's pixels; squared distances are exact integers
+    unsigned int lmax1 = 0, lmax2 = 0;
+    for (int i = threadIdx.x; i < wh * ww; i += blockDim.x) {
+        if (lab[i] != id) continue;
+        const int y = i / ww, x = i - y * ww;
+        unsigned int b1 = 0xFFFFFFFFu, b2 = 0xFFFFFFFFu;
+        if (any_bg) {
+            for (int xx = 0; xx < ww; ++xx) {
+                const unsigned int g = g1[y * ww + xx];
+                if (g == kInf16) continue;
+                const unsigned int dx = static_cast<unsigned int>(xx > x ? xx - x : x - xx);
+                const unsigned int d = dx * dx + g * g;
+                b1 = d < b1 ? d : b1;
+            }
+        } else {
+            // scipy's feature transform of an all-foreground array points at (-1, 0)
+            b1 = static_cast<unsigned int>((y + 1) * (y + 1) + x * x);
+        }
+        if (any_other) {
+            for (int xx = 0; xx < ww; ++xx) {
+                const unsigned int g = g2[y * ww + xx];
+                if (g == kInf16) continue;
+                const unsigned int dx = static_cast<unsigned int>(xx > x ? xx - x : x - xx);
+                const unsigned int d = dx * dx + g * g;
+                b2 = d < b2 ? d : b2;
+            }
+        }
+        lmax1 = b1 > lmax1 ? b1 : lmax1;
+        if (any_other) lmax2 = b2 > lmax2 ? b2 : lmax2;
+        // park the exact squared distances in the output arrays (bit patterns); the same thread converts them
+        // below once the per-instance maxima are known
+        const size_t o = (static_cast<size_t>(crop) * H + s.wy0 + y) * W + s.wx0 + x;
+        cell_dist[o] = __uint_as_float(b1);
+        nraw[o] = __longlong_as_double(static_cast<long long>(any_other ? b2 : 0u));
+    }
+    atomicMax(&s_max1, lmax1);
+    atomicMax(&s_max2, lmax2);
+    __syncthreads();
+    const double max1 = sqrt(static_cast<double>(s_max1));               // np.max(EDT) (> 0: own pixels exist)
+    const double max2 = sqrt(static_cast<double>(s_max2));
+    const double den = fmin(max1 + 3.0, max2);                           // :321
+    for (int i = threadIdx.x; i < wh * ww; i += blockDim.x) {
+        if (lab[i] != id) continue;
+        const int y = i / ww, x = i - y * ww;
+        const size_t o = (static_cast<size_t>(crop) * H + s.wy0 + y) * W + s.wx0 + x;
+        const double d1 = sqrt(static_cast<double>(__float_as_uint(cell_dist[o])));
+        cell_dist[o] = static_cast<float>(d1 / max1);                    // :292, cast :361
+        double v = 0.0;
+        if (any_other) {
+            const double d2 = sqrt(static_cast<double>(static_cast<unsigned int>(__double_as_longlong(nraw[o]))));
+            double q = d2 / den;
+            q = q < 0.0 ? 0.0 : (q > 1.0 ? 1.0 : q);
+            v = 1.0 - q;                                                  // :327 (own mask == 1 here)
+        }
+        nraw[o] = v;
+    }
+}
+
+// per-instance binary_closing(nucleus, disk(3)) OR-ed into label_bin (bottom_hat_closing :50-55);
+// scipy's erosion uses border_value=0, i.e. pixels whose disk leaves the image are removed.
+__device__ __forceinline__ bool in_disk3(int dy, int dx) { return dy * dy + dx * dx <= 9; }
+
+__global__ void __launch_bounds__(256)
+lab_close_cell_kernel(const uint16_t *__restrict__ masks, int H, int W, int ids, const CellStats *cs, CropInfo *info,
+                      uint8_t *__restrict__ label_bin, int smem_cap_bytes) {
+    const int crop = blockIdx.y;
+    const int id = blockIdx.x + 1;
+    if (id >= ids) return;
+    const CellStats s = cs[static_cast<size_t>(crop) * ids + id];
+    if (s.cnt == 0) return;
+    const int bh = s.y1 - s.y0 + 1, bw = s.x1 - s.x0 + 1;
+    const int dh = bh + 6, dw = bw + 6;
+    if (bh * bw + dh * dw > smem_cap_bytes) {
+        if (threadIdx.x == 0) atomicOr(&info[crop].error, 1);
+        return;
+    }
+    extern __shared__ unsigned short sm[];
+    uint8_t *X = reinterpret_cast<uint8_t *>(sm);      // [bh][bw]
+    uint8_t *D = X + bh * bw;                          // [dh][dw], origin (y0-3, x0-3)
+    const uint16_t *m = masks + static_cast<size_t>(crop) * H * W;
+    for (int i = threadIdx.x; i < bh * bw; i += blockDim.x) {
+        const int y = i / bw, x = i - y * bw;
+        X[i] = m[static_cast<size_t>(s.y0 + y) * W + s.x0 + x] == id;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < dh * dw; i += blockDim.x) {
+        const int y = i / dw - 3, x = i % dw - 3;      // bbox coordinates
+        const int gy = s.y0 + y, gx = s.x0 + x;
+        bool v = false;
+        if (gy >= 0 && gy < H && gx >= 0 && gx < W) {
+            for (int dy = -3; dy <= 3 && !v; ++dy)
+                for (int dx = -3; dx <= 3; ++dx) {
+                    if (!in_disk3(dy, dx)) continue;
+                    const int yy = y + dy, xx = x + dx;
+                    if (yy >= 0 && yy < bh && xx >= 0 && xx < bw && X[yy * bw + xx]) { v = true; break; }
+                }
+        }
+        D[i] = v;
+    }
+    __syncthreads();
+    uint8_t *out = label_bin + static_cast<size_t>(crop) * H * W;
+    for (int i = threadIdx.x; i < bh * bw; i += blockDim.x) {
+        const int y = i / bw, x = i - y * bw;
+        bool v = true;
+        for (int dy = -3; dy <= 3 && v; ++dy)
+            for (int dx = -3; dx <= 3; ++dx) {
+                if (!in_disk3(dy, dx)) continue;
+                const int gy = s.y0 + y + dy, gx = s.x0 + x + dx;
+                if (gy < 0 || gy >= H || gx < 0 || gx >= W || !D[(y + dy + 3) * dw + (x + dx + 3)]) { v = false; break; }
+            }
+        if (v) out[static_cast<size_t>(s.y0 + y) * W + s.x0 + x] = 1;
+    }
+}
+
+// border_label(label) == 2  <=>  foreground pixel with a different positive id in its 3x3 neighbourhood
+__global__ void lab_border_kernel(const uint16_t *__restrict__ masks, int H, int W, uint8_t *__restrict__ border) {
+    const int crop = blockIdx.z;
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= W || y >= H) return;
+    const uint16_t *m = masks + static_cast<size_t>(crop) * H * W;
+    const int l = m[y * W + x];
+    bool b = false;
+    if (l) {
+        for (int dy = -1; dy <= 1; ++dy)
+            for (int dx = -1; dx <= 1; ++dx) {
+                const int yy = y + dy, xx = x + dx;
+                if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
+                const int o = m[yy * W + xx];
+                b |= (o != 0 && o != l);
+            }
+    }
+    border[(static_cast<size_t>(crop) * H + y) * W + x] = b;
+}
+
+__global__ void lab_dilate_kernel(const uint8_t *__restrict__ in, int H, int W, uint8_t *__restrict__ out) {
+    const int crop = blockIdx.z;
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= W || y >= H) return;
+    const uint8_t *p = in + static_cast<size_t>(crop) * H * W;
+    bool v = false;
+    for (int dy = -3; dy <= 3 && !v; ++dy)
+        for (int dx = -3; dx <= 3; ++dx) {
+            if (!in_disk3(dy, dx)) continue;
+            const int yy = y + dy, xx = x + dx;
+            if (yy >= 0 && yy < H && xx >= 0 && xx < W && p[yy * W + xx]) { v = true; break; }
+        }
+    out[(static_cast<size_t>(crop) * H + y) * W + x] = v;
+}
+// gap = ~label_bin & (erode(dilated) ^ label_bin)   (bottom_hat_closing :58-59)
+__global__ void lab_erode_gap_kernel(const uint8_t *__restrict__ dil, const uint8_t *__restrict__ label_bin, int H, int W,
+                                     uint8_t *__restrict__ gap) {
+    const int crop = blockIdx.z;
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= W || y >= H) return;
+    const uint8_t *p = dil + static_cast<size_t>(crop) * H * W;
+    bool v = true;
+    for (int dy = -3; dy <= 3 && v; ++dy)
+        for (int dx = -3; dx <= 3; ++dx) {
+            if (!in_disk3(dy, dx)) continue;
+            const int yy = y + dy, xx = x + dx;
+            if (yy < 0 || yy >= H || xx < 0 || xx >= W || !p[yy * W + xx]) { v = false; break; }
+        }
+    const size_t o = (static_cast<size_t>(crop) * H + y) * W + x;
+    const bool lb = label_bin[o] != 0;
+    gap[o] = (!lb) && (v != lb);
+}
+
+// ---------------------------------------------------------------------------------------------
+// gaps: 8-connected components per crop (union-find on global pixel indices), dense ids, statistics
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ int uf_find(volatile int *L, int a) {
+    int p = L[a];
+    while (p != a) { a = p; p = L[a]; }
+    return a;
+}
+__device__ __forceinline__ void uf_union(int *L, int a, int b) {
+    bool done;
+    do {
+        a = uf_find(L, a);
+        b = uf_find(L, b);
+        if (a < b) { int old = atomicMin(&L[b], a); done = (old == b); b = old; }
+        else if (b < a) { int old = atomicMin(&L[a], b); done = (old == a); a = old; }
+        else done = true;
+    } while (!done);
+}
+__global__ void gap_init_kernel(const uint8_t *__restrict__ gap, long long n, int *__restrict__ L) {
+    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i < n) L[i] = gap[i] ? static_cast<int>(i) : -1;
+}
+__global__ void gap_merge_kernel(const uint8_t *__restrict__ gap, int H, int W, int *L) {
+    const int crop = blockIdx.z;
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= W || y >= H) return;
+    const int base = crop * H * W;
+    const uint8_t *g = gap + base;
+    const int i = y * W + x;
+    if (!g[i]) return;
+    if (x > 0 && g[i - 1]) uf_union(L, base + i, base + i - 1);
+    if (y > 0) {
+        if (g[i - W]) uf_union(L, base + i, base + i - W);
+        else {
+            if (x > 0 && g[i - W - 1]) uf_union(L, base + i, base + i - W - 1);
+            if (x + 1 < W && g[i - W + 1]) uf_union(L, base + i, base + i - W + 1);
+        }
+    }
+}
+__global__ void gap_compress_ids_kernel(int *L, long long n, int HW, int max_gaps, CropInfo *info, int *gid) {
+    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (L[i] < 0) { gid[i] = -1; return; }
+    if (L[i] == i) {          // root claims a dense id inside its crop
+        const int crop = static_cast<int>(i / HW);
+        const int k = atomicAdd(&info[crop].n_gaps, 1);
+        if (k >= max_gaps) { atomicOr(&info[crop].error, 2); gid[i] = -1; }
+        else gid[i] = k;
+    }
+}
+__global__ void gap_resolve_kernel(int *L, long long n, int *gid) {
+    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n || L[i] < 0) return;
+    const int r = uf_find(L, static_cast<int>(i));
+    L[i] = r;
+}
+__global__ void gap_assign_kernel(const int *__restrict__ L, long long n, int *gid) {
+    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n || L[i] < 0 || L[i] == i) return;
+    gid[i] = gid[L[i]];
+}
+__global__ void gap_stats_kernel(const int *__restrict__ gid, const double *__restrict__ nraw, int H, int W, int max_gaps,
+                                 GapStats *gs) {
+    const int crop = blockIdx.z;
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= W || y >= H) return;
+    const size_t base = static_cast<size_t>(crop) * H * W;
+    const int *g = gid + base;
+    GapStats *S = gs + static_cast<size_t>(crop) * max_gaps;
+    const int me = g[y * W + x];
+    if (me >= 0) {
+        atomicAdd(&S[me].cnt, 1ull);
+        atomicAdd(&S[me].sy, static_cast<unsigned long long>(y));
+        atomicAdd(&S[me].sx, static_cast<unsigned long long>(x));
+        atomicAdd(&S[me].syy, static_cast<unsigned long long>(y) * y);
+        atomicAdd(&S[me].sxx, static_cast<unsigned long long>(x) * x);
+        atomicAdd(&S[me].sxy, static_cast<unsigned long long>(x) * y);
+    }
+    // obj_boundary = dilate3x3(obj) ^ obj : this pixel belongs to the boundary of every *other* gap it touches
+    const double v = nraw[base + y * W + x];
+    if (v == 0.0) return;
+    int seen[8];
+    int ns = 0;
+    for (int dy = -1; dy <= 1; ++dy)
+        for (int dx = -1; dx <= 1; ++dx) {
+            if (!dy && !dx) continue;
+            const int yy = y + dy, xx = x + dx;
+            if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
+            const int o = g[yy * W + xx];
+            if (o < 0 || o == me) continue;
+            bool dup = false;
+            for (int k = 0; k < ns; ++k) dup |= (seen[k] == o);
+            if (!dup) { seen[ns++] = o; atomicAdd(&S[o].bsum, v); }
+        }
+}
+
+// gap map (label_closed_corr) + max with raw neighbour map and touching borders + rescale + clip (:352-358)
+__global__ void lab_compose_kernel(const int *__restrict__ gid, const GapStats *__restrict__ gs, const uint8_t *__restrict__ border,
+                                   const double *__restrict__ nraw, int H, int W, int max_gaps, double *__restrict__ scaled) {
+    const int crop = blockIdx.z;
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= W || y >= H) return;
+    const size_t base = static_cast<size_t>(crop) * H * W;
+    const int *g = gid + base;
+    const int me = g[y * W + x];
+    float corr = 0.0f;
+    if (me >= 0) {
+        const GapStats s = gs[static_cast<size_t>(crop) * max_gaps + me];
+        const double th = s.cnt <= 20 ? 5.0 : (s.cnt <= 30 ? 8.0 : (s.cnt <= 50 ? 10.0 : 20.0));   // :342-349
+        if (s.bsum < th) {
+            corr = 0.0f;                                    // artefact: completely in the background
+        } else {
+            corr = 1.0f;
+            double major, minor;
+            axis_lengths(s.cnt, s.sy, s.sx, s.syy, s.sxx, s.sxy, &major, &minor);
+            if (minor >= 3.0) {
+                // ring = gap ^ binary_erosion(gap, cross), border_value = 0
+                const bool inner = y > 0 && y + 1 < H && x > 0 && x + 1 < W && g[(y - 1) * W + x] == me &&
+                                   g[(y + 1) * W + x] == me && g[y * W + x - 1] == me && g[y * W + x + 1] == me;
+                if (!inner) corr = 0.8f;
+            }
+        }
+    }
+    double v = nraw[base + y * W + x];
+    v = fmax(v, static_cast<double>(corr));
+    v = fmax(v, border[base + y * W + x] ? 1.0 : 0.0);
+    v = 1.0 / sqrt(0.65 + 0.5 * exp(-11.0 * (v - 0.75))) - 0.19;
+    v = v < 0.0 ? 0.0 : (v > 1.0 ? 1.0 : v);
+    scaled[base + y * W + x] = v;
+}
+
+__device__ __forceinline__ int reflect_idx(int i, int n) {
+    while (i < 0 || i >= n) {
+        if (i < 0) i = -i - 1;
+        if (i >= n) i = 2 * n - 1 - i;
+    }
+    return i;
+}
+// grey_closing(size=(3,3)) = 3x3 max filter then 3x3 min filter, mode 'reflect'
+template <bool IS_MAX, typename TOUT>
+__global__ void lab_grey_kernel(const double *__restrict__ in, int H, int W, TOUT *__restrict__ out) {
+    const int crop = blockIdx.z;
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= W || y >= H) return;
+    const double *p = in + static_cast<size_t>(crop) * H * W;
+    double v = p[y * W + x];
+    for (int dy = -1; dy <= 1; ++dy)
+        for (int dx = -1; dx <= 1; ++dx) {
+            const double o = p[reflect_idx(y + dy, H) * W + reflect_idx(x + dx, W)];
+            v = IS_MAX ? fmax(v, o) : fmin(v, o);
+        }
+    out[(static_cast<size_t>(crop) * H + y) * W + x] = static_cast<TOUT>(v);
+}
+
+inline size_t r256(size_t b) { return (b + 255) & ~static_cast<size_t>(255); }
+constexpr int kMaxGaps = 4096;
+
+}  // namespace
+
+extern "C" size_t mbs_labels_workspace_bytes(int n_crops, int H, int W, int max_id) {
+    const size_t px = static_cast<size_t>(n_crops) * H * W;
+    const size_t ids = static_cast<size_t>(max_id) + 1;
+    return r256(n_crops * ids * sizeof(CellStats)) + r256(n_crops * sizeof(CropInfo)) +
+           r256(static_cast<size_t>(n_crops) * kMaxGaps * sizeof(GapStats)) + 2 * r256(px * 8) /*nraw, scaled*/ +
+           4 * r256(px) /*label_bin, dil, gap, border*/ + 2 * r256(px * 4) /*L, gid*/ + 4096;
+}
+
+extern "C" int mbs_labels_max_mal(const uint16_t *masks, int n_crops, int H, int W, int max_id, int32_t *max_mal_out,
+                                  void *workspace, size_t workspace_bytes, void *stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    MBS_REQUIRE(n_crops > 0 && H > 0 && W > 0 && max_id >= 0 && max_id <= 65535 && max_mal_out, "labels_max_mal: bad arguments");
+    const int ids = max_id + 1;
+    const size_t need = r256(static_cast<size_t>(n_crops) * ids * sizeof(CellStats)) + r256(n_crops * sizeof(CropInfo));
+    MBS_REQUIRE(workspace_bytes >= need, "labels_max_mal: workspace too small");
+    CellStats *cs = reinterpret_cast<CellStats *>(workspace);
+    CropInfo *info = reinterpret_cast<CropInfo *>(static_cast<char *>(workspace) +
+                                                  r256(static_cast<size_t>(n_crops) * ids * sizeof(CellStats)));
+    const int total = n_crops * ids;
+    dim3 b2(32, 8), g3(mbs::cdiv(W, 32), mbs::cdiv(H, 8), n_crops);
+    MBS_CHECK_CUDA(cudaMemsetAsync(info, 0, n_crops * sizeof(CropInfo), stream));
+    lab_init_stats_kernel<<<mbs::cdiv(total, 256), 256, 0, stream>>>(cs, total);
+    MBS_CHECK_LAUNCH();
+    lab_accum_kernel<<<g3, b2, 0, stream>>>(masks, H, W, ids, cs);
+    MBS_CHECK_LAUNCH();
+    lab_axes_kernel<<<mbs::cdiv(total, 256), 256, 0, stream>>>(cs, ids, total, info);
+    MBS_CHECK_LAUNCH();
+    MBS_CHECK_CUDA(cudaMemcpy2DAsync(max_mal_out, sizeof(int), &info[0].max_mal, sizeof(CropInfo), sizeof(int), n_crops,
+                                     cudaMemcpyDeviceToDevice, stream));
+    return 0;
+}
+
+extern "C" int mbs_distance_labels(const uint16_t *masks, int n_crops, int H, int W, int max_id, int search_radius,
+                                   int radius_hint, float *cell_dist, float *neighbor_dist, int32_t *max_mal_out, int32_t *error_out,
+                                   void *workspace, size_t workspace_bytes, void *stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    MBS_REQUIRE(n_crops > 0 && H > 0 && W > 0 && max_id >= 0 && max_id <= 65535, "distance_labels: bad arguments");
+    const size_t px = static_cast<size_t>(n_crops) * H * W;
+    MBS_REQUIRE(px < (1ull << 31), "distance_labels: batch too large (use fewer crops per call)");
+    MBS_REQUIRE(workspace_bytes >= mbs_labels_workspace_bytes(n_crops, H, W, max_id), "distance_labels: workspace too small");
+    const int ids = max_id + 1;
+    char *p = static_cast<char *>(workspace);
+    auto take = [&](size_t bytes) { char *r = p; p += r256(bytes); return r; };
+    CellStats *cs = reinterpret_cast<CellStats *>(take(static_cast<size_t>(n_crops) * ids * sizeof(CellStats)));
+    CropInfo *info = reinterpret_cast<CropInfo *>(take(n_crops * sizeof(CropInfo)));
+    GapStats *gs = reinterpret_cast<GapStats *>(take(static_cast<size_t>(n_crops) * kMaxGaps * sizeof(GapStats)));
+    double *nraw = reinterpret_cast<double *>(take(px * 8));
+    double *scaled = reinterpret_cast<double *>(take(px * 8));
+    uint8_t *label_bin = reinterpret_cast<uint8_t *>(take(px));
+    uint8_t *dil = reinterpret_cast<uint8_t *>(take(px));
+    uint8_t *gap = reinterpret_cast<uint8_t *>(take(px));
+    uint8_t *border = reinterpret_cast<uint8_t *>(take(px));
+    int *L = reinterpret_cast<int *>(take(px * 4));
+    int *gid = reinterpret_cast<int *>(take(px * 4));
+
+    const int total = n_crops * ids;
+    dim3 b2(32, 8), g3(mbs::cdiv(W, 32), mbs::cdiv(H, 8), n_crops);
+    const int nb = static_cast<int>((px + 255) / 256);
+    MBS_CHECK_CUDA(cudaMemsetAsync(info, 0, n_crops * sizeof(CropInfo), stream));
+    MBS_CHECK_CUDA(cudaMemsetAsync(gs, 0, static_cast<size_t>(n_crops) * kMaxGaps * sizeof(GapStats), stream));
+    MBS_CHECK_CUDA(cudaMemsetAsync(nraw, 0, px * 8, stream));
+    MBS_CHECK_CUDA(cudaMemsetAsync(cell_dist, 0, px * 4, stream));
+    MBS_CHECK_CUDA(cudaMemsetAsync(label_bin, 0, px, stream));
+    lab_init_stats_kernel<<<mbs::cdiv(total, 256), 256, 0, stream>>>(cs, total);
+    MBS_CHECK_LAUNCH();
+    lab_accum_kernel<<<g3, b2, 0, stream>>>(masks, H, W, ids, cs);
+    MBS_CHECK_LAUNCH();
+    lab_axes_kernel<<<mbs::cdiv(total, 256), 256, 0, stream>>>(cs, ids, total, info);
+    MBS_CHECK_LAUNCH();
+    lab_window_kernel<<<mbs::cdiv(total, 256), 256, 0, stream>>>(cs, ids, total, H, W, info, search_radius);
+    MBS_CHECK_LAUNCH();
+    if (max_id > 0) {
+        // dynamic shared memory: as much as the device allows (opt-in), the kernels flag windows that do not fit
+        static int smem_opt = 0;
+        if (!smem_opt) {
+            int dev = 0;
+            cudaGetDevice(&dev);
+            cudaDeviceGetAttribute(&smem_opt, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+            smem_opt -= 1024;
+            MBS_CHECK_CUDA(cudaFuncSetAttribute(lab_cell_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_opt));
+            MBS_CHECK_CUDA(cudaFuncSetAttribute(lab_close_cell_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_opt));
+        }
+        // size the launch for the largest window the radius can produce, capped by the device limit
+        const int R = search_radius >= 0 ? search_radius : (radius_hint >= 0 ? radius_hint : (H > W ? H : W));
+        long long want = 3ll * 2 * (2ll * R) * (2ll * R);
+        const long long full = 3ll * 2 * H * W;
+        if (want > full) want = full;
+        int smem = want > smem_opt ? smem_opt : static_cast<int>(want);
+        if (smem < 4096) smem = 4096;
+        dim3 gc(max_id, n_crops);
+        lab_cell_kernel<<<gc, 256, smem, stream>>>(masks, H, W, ids, cs, info, cell_dist, nraw, smem / 6);
+        MBS_CHECK_LAUNCH();
+        long long wantc = 2ll * (static_cast<long long>(H) + 6) * (W + 6);
+        int smemc = wantc > smem_opt ? smem_opt : static_cast<int>(wantc);
+        lab_close_cell_kernel<<<gc, 256, smemc, stream>>>(masks, H, W, ids, cs, info, label_bin, smemc);
+        MBS_CHECK_LAUNCH();
+    }
+    lab_border_kernel<<<g3, b2, 0, stream>>>(masks, H, W, border);
+    MBS_CHECK_LAUNCH();
+    lab_dilate_kernel<<<g3, b2, 0, stream>>>(label_bin, H, W, dil);
+    MBS_CHECK_LAUNCH();
+    lab_erode_gap_kernel<<<g3, b2, 0, stream>>>(dil, label_bin, H, W, gap);
+    MBS_CHECK_LAUNCH();
+    gap_init_kernel<<<nb, 256, 0, stream>>>(gap, static_cast<long long>(px), L);
+    MBS_CHECK_LAUNCH();
+    gap_merge_kernel<<<g3, b2, 0, stream>>>(gap, H, W, L);
+    MBS_CHECK_LAUNCH();
+    gap_resolve_kernel<<<nb, 256, 0, stream>>>(L, static_cast<long long>(px), gid);
+    MBS_CHECK_LAUNCH();
+    gap_compress_ids_kernel<<<nb, 256, 0, stream>>>(L, static_cast<long long>(px), H * W, kMaxGaps, info, gid);
+    MBS_CHECK_LAUNCH();
+    gap_assign_kernel<<<nb, 256, 0, stream>>>(L, static_cast<long long>(px), gid);
+    MBS_CHECK_LAUNCH();
+    gap_stats_kernel<<<g3, b2, 0, stream>>>(gid, nraw, H, W, kMaxGaps, gs);
+    MBS_CHECK_LAUNCH();
+    lab_compose_kernel<<<g3, b2, 0, stream>>>(gid, gs, border, nraw, H, W, kMaxGaps, scaled);
+    MBS_CHECK_LAUNCH();
+    lab_grey_kernel<true, double><<<g3, b2, 0, stream>>>(scaled, H, W, nraw);        // nraw reused as the dilated map
+    MBS_CHECK_LAUNCH();
+    lab_grey_kernel<false, float><<<g3, b2, 0, stream>>>(nraw, H, W, neighbor_dist);
+    MBS_CHECK_LAUNCH();
+    if (max_mal_out)
+        MBS_CHECK_CUDA(cudaMemcpy2DAsync(max_mal_out, sizeof(int), &info[0].max_mal, sizeof(CropInfo), sizeof(int), n_crops,
+                                         cudaMemcpyDeviceToDevice, stream));
+    if (error_out)
+        MBS_CHECK_CUDA(cudaMemcpy2DAsync(error_out, sizeof(int), &info[0].error, sizeof(CropInfo), sizeof(int), n_crops,
+                                         cudaMemcpyDeviceToDevice, stream));
+    return 0;
+}

@@ -1,0 +1,104 @@
+"""Host-side mirror of the reference's label generation for the distance method (CUDA path).
+
+Same names / argument meaning as /root/reference/src/training/train_data_representations.py:
+``get_label(mask, 'distance', max_mal)`` (:11-37) and ``distance_label(label, search_radius)``
+(:261-361) return ``(cell_dist float32 (H,W), neighbor_dist float32 (H,W))``.  ``create_labels``
+is the numerical part of ``CreateLabelsWorker.create_labels`` (src/training/train.py:63-96) for a
+batch of crops: max_mal from the major axis lengths, then both maps, crops batched on the GPU.
+No CPU fallback.
+"""
+import numpy as np
+import torch
+
+from . import _native as nat
+
+_MAX_BATCH_PIXELS = 1 << 28          # crops per C-ABI call are chunked to stay under 2^31 pixels / few GiB scratch
+
+
+def _masks_to_device(masks, device):
+    m = np.ascontiguousarray(masks)
+    if m.ndim == 2:
+        m = m[None]
+    if m.dtype != np.uint16:
+        if m.min() < 0 or m.max() > 65535:
+            raise ValueError("instance ids must fit in uint16")
+        m = m.astype(np.uint16)
+    return torch.from_numpy(m.view(np.int16)).to(device), int(m.max())
+
+
+def _device():
+    if not torch.cuda.is_available():
+        raise RuntimeError("microbeseg_b200.labels needs a CUDA device (no CPU fallback)")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def _run(masks_dev, max_id, search_radius, radius_hint):
+    L = nat.lib()
+    n, H, W = masks_dev.shape
+    device = masks_dev.device
+    cell = torch.empty((n, H, W), dtype=torch.float32, device=device)
+    neigh = torch.empty((n, H, W), dtype=torch.float32, device=device)
+    mal = torch.zeros(n, dtype=torch.int32, device=device)
+    err = torch.zeros(n, dtype=torch.int32, device=device)
+    ws = torch.empty(L.mbs_labels_workspace_bytes(n, H, W, max_id), dtype=torch.uint8, device=device)
+    with torch.cuda.device(device):
+        nat.check(L.mbs_distance_labels(masks_dev.data_ptr(), n, H, W, max_id, int(search_radius), int(radius_hint),
+                                        cell.data_ptr(), neigh.data_ptr(), mal.data_ptr(), err.data_ptr(),
+                                        ws.data_ptr(), ws.numel(), nat.stream_ptr()), "distance_labels")
+    e = err.cpu().numpy()
+    if e.any():
+        raise RuntimeError(f"distance_labels: crops {np.flatnonzero(e).tolist()[:8]} exceeded a device limit "
+                           f"(bit0: instance window too large for shared memory, bit1: > 4096 gaps): {e[e != 0][:8]}")
+    return cell, neigh, mal
+
+
+def max_major_axis_lengths(masks):
+    """int(ceil(max major_axis_length)) per crop (train.py:74-79)."""
+    L = nat.lib()
+    dev, max_id = _masks_to_device(masks, _device())
+    n, H, W = dev.shape
+    out = torch.zeros(n, dtype=torch.int32, device=dev.device)
+    ws = torch.empty(L.mbs_labels_workspace_bytes(n, H, W, max_id), dtype=torch.uint8, device=dev.device)
+    nat.check(L.mbs_labels_max_mal(dev.data_ptr(), n, H, W, max_id, out.data_ptr(), ws.data_ptr(), ws.numel(),
+                                   nat.stream_ptr()), "labels_max_mal")
+    return out.cpu().numpy()
+
+
+def distance_label(label, search_radius):
+    """Cell and neighbor distance label creation (train_data_representations.py:261-361)."""
+    dev, max_id = _masks_to_device(label, _device())
+    cell, neigh, _ = _run(dev, max_id, int(search_radius), int(search_radius))
+    return cell[0].cpu().numpy(), neigh[0].cpu().numpy()
+
+
+def get_label(mask, label_type, max_mal):
+    """Calculate training data representation / label (train_data_representations.py:11-37)."""
+    if label_type == 'distance':
+        return distance_label(mask, search_radius=int(np.ceil(0.75 * max_mal)))
+    if label_type in ('boundary', 'border', 'adapted_border', 'j4', 'cell_dist', 'cell_dist_clipped'):
+        raise NotImplementedError(f"label type {label_type!r} is not built on the CUDA path (only 'distance')")
+    raise Exception('Label type not known')
+
+
+def create_labels_device(masks_dev, max_id, radius_hint=-1):
+    """Device-resident batch entry: int16-viewed uint16 masks [n,H,W] on the GPU -> (cell, neighbor, max_mal)."""
+    return _run(masks_dev, max_id, -1, radius_hint)
+
+
+def create_labels(masks):
+    """Batch version of CreateLabelsWorker.create_labels (train.py:63-96) for [n,H,W] masks.
+    Returns (cell_dist [n,H,W] f32, neighbor_dist [n,H,W] f32, max_mal [n] int)."""
+    masks = np.asarray(masks)
+    if masks.ndim == 2:
+        masks = masks[None]
+    n, H, W = masks.shape
+    per = max(1, min(n, _MAX_BATCH_PIXELS // (H * W)))
+    cells, neighs, mals = [], [], []
+    for s in range(0, n, per):
+        dev, max_id = _masks_to_device(masks[s:s + per], _device())
+        hint = int(np.ceil(0.75 * int(max_major_axis_lengths(masks[s:s + per]).max()))) if max_id > 0 else 0
+        c, nb, mal = _run(dev, max_id, -1, hint)
+        cells.append(c.cpu().numpy())
+        neighs.append(nb.cpu().numpy())
+        mals.append(mal.cpu().numpy())
+    return np.concatenate(cells), np.concatenate(neighs), np.concatenate(mals)

@@ -1,0 +1,79 @@
+"""GPU parity tests: label generation (distance method) through the C ABI vs oracle/labels.py.
+
+cell_dist involves only integer squared distances, IEEE sqrt and division -> bit exact.
+neighbor_dist additionally goes through exp() (numpy's and CUDA's float64 exp may differ in the last
+bit) -> after the float32 cast at most 1 float32 ulp (tolerance 1.2e-7 absolute on [0,1] maps)."""
+import numpy as np
+import pytest
+
+from oracle import labels as ol
+from microbeseg_b200 import synthetic as sy
+
+pytestmark = pytest.mark.gpu
+NEIGH_TOL = 1.2e-7
+
+
+@pytest.fixture(scope="module")
+def lab(native_lib):
+    from microbeseg_b200 import labels
+    return labels
+
+
+def _mask(H, W, n, seed):
+    return sy.synth_instance_mask(H, W, n, seed, (9.0, 16.0), (7.0, 12.0)).astype(np.uint16)
+
+
+def _check(got, ref, what=""):
+    (gc, gn), (rc, rn) = got, ref
+    assert gc.dtype == np.float32 and gn.dtype == np.float32 and gc.shape == rc.shape
+    assert np.array_equal(gc, rc), (what, np.abs(gc - rc).max())
+    assert np.abs(gn.astype(np.float64) - rn).max() <= NEIGH_TOL, (what, np.abs(gn - rn).max())
+
+
+@pytest.mark.parametrize("H,W,n,seed", [(320, 320, 120, 10000), (320, 320, 60, 10001), (128, 200, 40, 10002),
+                                        (64, 64, 6, 10003)])
+def test_distance_label_vs_oracle(lab, H, W, n, seed):
+    m = _mask(H, W, n, seed)
+    mal = ol.max_major_axis_length(m)
+    assert int(lab.max_major_axis_lengths(m)[0]) == mal
+    ref = ol.get_label(m, 'distance', mal)
+    got = lab.get_label(m, 'distance', mal)
+    _check(got, ref, (H, W, n))
+    assert (ref[1] > 0).mean() > 0.01          # the neighbour map is exercised
+
+
+def test_touching_cells_gaps_and_borders(lab):
+    # densely packed: many touching borders, bottom-hat gaps with rings, artefact gaps
+    m = _mask(256, 256, 150, 7)
+    (ref, im) = ol.distance_label(m, 20, return_intermediates=True)
+    assert im["label_border"].sum() > 50 and im["gaps"].max() > 5
+    _check(lab.distance_label(m, 20), ref, "dense")
+
+
+def test_edge_cases(lab):
+    z = np.zeros((64, 80), np.uint16)
+    _check(lab.distance_label(z, 10), ol.distance_label(z, 10), "empty")
+    one = np.zeros((64, 64), np.uint16)
+    one[20:40, 10:50] = 5                      # single instance, ids not starting at 1, window clips the cell
+    _check(lab.distance_label(one, 8), ol.distance_label(one, 8), "single clipped")
+    two = np.zeros((40, 40), np.uint16)
+    two[5:20, 5:20] = 1
+    two[5:20, 20:35] = 2                       # touching pair
+    two[0:3, 0:40] = 3                         # instance on the image edge (closing strips the rim)
+    _check(lab.distance_label(two, 12), ol.distance_label(two, 12), "touching")
+    full = np.full((30, 30), 9, np.uint16)     # all-foreground window: scipy's degenerate EDT
+    _check(lab.distance_label(full, 6), ol.distance_label(full, 6), "all foreground")
+    split = np.zeros((64, 64), np.uint16)      # one id in two blobs: centroid between them, window misses both
+    split[2:8, 2:8] = 4
+    split[56:62, 56:62] = 4
+    split[30:34, 30:34] = 2
+    _check(lab.distance_label(split, 5), ol.distance_label(split, 5), "split id")
+
+
+def test_batch_create_labels_matches_per_crop(lab):
+    masks = np.stack([_mask(160, 160, 30 + 5 * i, 20000 + i) for i in range(6)])
+    cells, neighs, mals = lab.create_labels(masks)
+    for i in range(len(masks)):
+        (rc, rn), mal = ol.create_labels(masks[i])
+        assert int(mals[i]) == mal
+        _check((cells[i], neighs[i]), (rc, rn), f"crop {i}")
