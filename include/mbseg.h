@@ -55,11 +55,15 @@ enum { MBS_CONV3X3_S1 = 0, MBS_CONV3X3_S2 = 1, MBS_CONVT2X2_S2 = 2 };
  * norm_lo/norm_hi: frame min / max as floats; pad pixels take the value norm_lo.  norm_hi < norm_lo
  * means "img is already normalised" (values pass through; used by the drop-in net(x) call).
  * norm_hi == norm_lo reproduces the reference's unguarded 0/0 (NaN maps -> empty mask).
- */
+ * lohi_dev (optional): device float[2] = {min, max} from mbs_frame_minmax; overrides norm_lo/hi. */
 int mbs_first_conv(const void *img, int in_dtype, int H, int W, int pad_y, int pad_x, float norm_lo,
-                   float norm_hi, const float *weight, const float *bias, const float *scale,
+                   float norm_hi, const float *lohi_dev, const float *weight, const float *bias, const float *scale,
                    const float *shift, int C, int act, void *out_nhwc_bf16, int out_ld, int out_coff,
                    void *stream);
+
+/* Frame min / max on the device (replaces np.min/np.max of the raw frame, infer_script_local.py:124,
+ * src/inference/infer.py:253): lohi_dev[0] = min, lohi_dev[1] = max as float; scratch8 = 8 bytes. */
+int mbs_frame_minmax(const void *img, int in_dtype, long long n, float *lohi_dev, void *scratch8, void *stream);
 
 /*
  * Implicit-GEMM convolution on the tcgen05 tensor cores (TMA-fed, TMEM accumulators, fused

@@ -21,6 +21,7 @@
 // pop order inside a level, hence equals skimage's for ANY tie-break; otherwise the image is
 // "ambiguous" (needs exact value ties between competing pixels) and the whole flood is re-run by
 // the sequential heap kernel, which restates skimage's algorithm including its binary heap.
+#include <cooperative_groups.h>
 #include <cuda_runtime.h>
 
 #include <cfloat>
@@ -164,10 +165,9 @@ struct Stats {
     unsigned long long total;   // seed pixels
     unsigned int n_comp;        // components before filtering
     unsigned int n_markers;     // components after filtering
-    unsigned int changed;       // relaxation flag
+    unsigned int changed[3];    // rotating "some tile changed in sweep s" flags (slot s % 3)
     unsigned int ambiguous;     // ambiguity counter
     unsigned int sweeps;
-    unsigned int pad;
 };
 
 __global__ void area_kernel(const int *__restrict__ L, int n, int *__restrict__ area, Stats *st) {
@@ -309,60 +309,95 @@ __global__ void ws_init_kernel(const float *__restrict__ img, int negate, const 
     Lv[i] = (mask[i] && markers[i] > 0) ? flood_value(img, i, negate) : kInf;
 }
 
-// One block relaxes a 32x32 tile (1-pixel halo) to its local fixed point in shared memory.
+// Minimax relaxation, one cooperative launch for all sweeps (no host round trip).  A block relaxes
+// 32x32 tiles (1-pixel halo) to their local fixed point in shared memory; sweeps are separated by a
+// grid-wide barrier and repeat until no tile changed.  A tile is revisited only if it or one of its
+// four neighbours changed in the previous sweep.
 __global__ void __launch_bounds__(256)
-ws_relax_kernel(const float *__restrict__ img, int negate, const int *__restrict__ markers,
-                const uint8_t *__restrict__ mask, int H, int W, float *Lv, Stats *st) {
+ws_relax_coop_kernel(const float *__restrict__ img, int negate, const int *__restrict__ markers,
+                     const uint8_t *__restrict__ mask, int H, int W, float *Lv, Stats *st, uint8_t *tile_changed) {
+    namespace cg = cooperative_groups;
+    cg::grid_group grid = cg::this_grid();
     __shared__ float sL[RT + 2][RT + 2];
-    const int x0 = blockIdx.x * RT, y0 = blockIdx.y * RT;
-    for (int i = threadIdx.x; i < (RT + 2) * (RT + 2); i += 256) {
-        const int r = i / (RT + 2), c = i % (RT + 2);
-        const int y = y0 + r - 1, x = x0 + c - 1;
-        sL[r][c] = (y >= 0 && y < H && x >= 0 && x < W) ? Lv[static_cast<size_t>(y) * W + x] : kInf;
-    }
-    // each thread owns 4 pixels: column tx, rows ty*4 .. ty*4+3
+    const int tiles_x = (W + RT - 1) / RT, tiles_y = (H + RT - 1) / RT;
+    const int ntiles = tiles_x * tiles_y;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-    float v[4];
-    bool act[4];
-    bool any_act = false;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        const int y = y0 + ty * 4 + k, x = x0 + tx;
-        act[k] = false;
-        v[k] = kInf;
-        if (y < H && x < W) {
-            const size_t i = static_cast<size_t>(y) * W + x;
-            if (mask[i] && markers[i] == 0) {
-                act[k] = true;
-                v[k] = flood_value(img, static_cast<int>(i), negate);
-            }
-        }
-        any_act |= act[k];
-    }
-    if (!__syncthreads_or(any_act)) return;
-    bool changed_any = false;
+    int sweep = 0;
     for (;;) {
-        bool changed = false;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            if (!act[k]) continue;
-            const int r = ty * 4 + k + 1, c = tx + 1;
-            const float m = fminf(fminf(sL[r - 1][c], sL[r + 1][c]), fminf(sL[r][c - 1], sL[r][c + 1]));
-            const float nl = fmaxf(v[k], m);
-            if (nl < sL[r][c]) {
-                sL[r][c] = nl;
-                changed = true;
+        const uint8_t *prev = tile_changed + ((sweep + 1) & 1) * ntiles;
+        uint8_t *cur = tile_changed + (sweep & 1) * ntiles;
+        bool block_changed = false;
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+            const int tyi = tile / tiles_x, txi = tile - tyi * tiles_x;
+            if (sweep > 0) {
+                const bool need = prev[tile] || (txi > 0 && prev[tile - 1]) || (txi + 1 < tiles_x && prev[tile + 1]) ||
+                                  (tyi > 0 && prev[tile - tiles_x]) || (tyi + 1 < tiles_y && prev[tile + tiles_x]);
+                if (!need) {
+                    if (threadIdx.x == 0) cur[tile] = 0;
+                    continue;
+                }
             }
-        }
-        changed_any |= changed;
-        if (!__syncthreads_or(changed)) break;
-    }
-    if (changed_any) {
+            const int x0 = txi * RT, y0 = tyi * RT;
+            __syncthreads();   // sL reuse across tiles
+            for (int i = threadIdx.x; i < (RT + 2) * (RT + 2); i += 256) {
+                const int r = i / (RT + 2), c = i % (RT + 2);
+                const int y = y0 + r - 1, x = x0 + c - 1;
+                sL[r][c] = (y >= 0 && y < H && x >= 0 && x < W) ? Lv[static_cast<size_t>(y) * W + x] : kInf;
+            }
+            float v[4];
+            bool act[4];
+            bool any_act = false;
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-            if (act[k]) Lv[static_cast<size_t>(y0 + ty * 4 + k) * W + x0 + tx] = sL[ty * 4 + k + 1][tx + 1];
+            for (int k = 0; k < 4; ++k) {
+                const int y = y0 + ty * 4 + k, x = x0 + tx;
+                act[k] = false;
+                v[k] = kInf;
+                if (y < H && x < W) {
+                    const size_t i = static_cast<size_t>(y) * W + x;
+                    if (mask[i] && markers[i] == 0) {
+                        act[k] = true;
+                        v[k] = flood_value(img, static_cast<int>(i), negate);
+                    }
+                }
+                any_act |= act[k];
+            }
+            bool changed_any = false;
+            if (__syncthreads_or(any_act)) {
+                for (;;) {
+                    bool changed = false;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        if (!act[k]) continue;
+                        const int r = ty * 4 + k + 1, c = tx + 1;
+                        const float m = fminf(fminf(sL[r - 1][c], sL[r + 1][c]), fminf(sL[r][c - 1], sL[r][c + 1]));
+                        const float nl = fmaxf(v[k], m);
+                        if (nl < sL[r][c]) {
+                            sL[r][c] = nl;
+                            changed = true;
+                        }
+                    }
+                    changed_any |= changed;
+                    if (!__syncthreads_or(changed)) break;
+                }
+                if (changed_any) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        if (act[k]) Lv[static_cast<size_t>(y0 + ty * 4 + k) * W + x0 + tx] = sL[ty * 4 + k + 1][tx + 1];
+                }
+            }
+            const bool tile_ch = __syncthreads_or(changed_any) != 0;
+            if (threadIdx.x == 0) cur[tile] = tile_ch ? 1 : 0;
+            block_changed |= tile_ch;
+        }
+        if (block_changed && threadIdx.x == 0) st->changed[sweep % 3] = 1;
+        __threadfence();
+        grid.sync();
+        const unsigned int flag = *reinterpret_cast<volatile unsigned int *>(&st->changed[sweep % 3]);
+        if (blockIdx.x == 0 && threadIdx.x == 0) st->changed[(sweep + 2) % 3] = 0;
+        ++sweep;
+        if (!flag) break;
     }
-    if (__syncthreads_or(changed_any) && threadIdx.x == 0) st->changed = 1;
+    if (blockIdx.x == 0 && threadIdx.x == 0) st->sweeps = static_cast<unsigned int>(sweep);
 }
 
 // parent codes
@@ -596,7 +631,7 @@ size_t label_ws_bytes(size_t n) {
     return r256(sizeof(Stats)) + r256(n * 4) /*area*/ + r256(n * 4) /*rank*/ + r256(tiles * 4) + r256(n * 4) /*roots*/;
 }
 size_t watershed_ws_bytes(size_t n) {
-    return r256(sizeof(Stats)) + 4 * r256(n * 4) /*Lv,parent,uf,src*/ + r256(n * sizeof(HeapItem));
+    return r256(sizeof(Stats)) + 4 * r256(n * 4) /*Lv,parent,uf,src*/ + r256(n * sizeof(HeapItem)) + r256(n / 64 + 4096);
 }
 
 // label + filter + rank.  roots: [n] int scratch/out (component root per pixel, -1 background)
@@ -626,29 +661,32 @@ int run_label_rank(const uint8_t *fg, int H, int W, int *roots, int *area, int *
 }
 
 int run_watershed(const float *img, int negate, const int *markers, const uint8_t *mask, int H, int W, int *lab,
-                  float *Lv, int *parent, int *uf, int *src, HeapItem *heap, Stats *st, Stats *st_host_pinned,
-                  int force_sequential, int *sweeps_out, cudaStream_t stream) {
+                  float *Lv, int *parent, int *uf, int *src, HeapItem *heap, Stats *st, uint8_t *tile_changed,
+                  int force_sequential, cudaStream_t stream) {
     const int n = H * W;
     const int nb = mbs::cdiv(n, 256);
     dim3 b2(32, 8), g2(mbs::cdiv(W, 32), mbs::cdiv(H, 8));
     dim3 gr(mbs::cdiv(W, RT), mbs::cdiv(H, RT));
-    int sweeps = 0;
     if (!force_sequential) {
         ws_init_kernel<<<nb, 256, 0, stream>>>(img, negate, markers, mask, n, Lv);
         MBS_CHECK_LAUNCH();
-        // relax until a sweep changes nothing; the flag is polled every 2 sweeps
-        for (;;) {
-            MBS_CHECK_CUDA(cudaMemsetAsync(&st->changed, 0, sizeof(unsigned int), stream));
-            ws_relax_kernel<<<gr, 256, 0, stream>>>(img, negate, markers, mask, H, W, Lv, st);
-            MBS_CHECK_LAUNCH();
-            ws_relax_kernel<<<gr, 256, 0, stream>>>(img, negate, markers, mask, H, W, Lv, st);
-            MBS_CHECK_LAUNCH();
-            sweeps += 2;
-            MBS_CHECK_CUDA(cudaMemcpyAsync(&st_host_pinned->changed, &st->changed, sizeof(unsigned int),
-                                           cudaMemcpyDeviceToHost, stream));
-            MBS_CHECK_CUDA(cudaStreamSynchronize(stream));
-            if (!st_host_pinned->changed) break;
-            MBS_REQUIRE(sweeps < 200000, "watershed relaxation did not converge");
+        // all sweeps in one cooperative launch; convergence is detected on the device
+        {
+            static int coop_blocks = 0;
+            if (coop_blocks == 0) {
+                int dev = 0, sms = 0, per_sm = 0;
+                MBS_CHECK_CUDA(cudaGetDevice(&dev));
+                MBS_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+                MBS_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ws_relax_coop_kernel, 256, 0));
+                coop_blocks = sms * (per_sm > 0 ? per_sm : 1);
+            }
+            const int ntiles = static_cast<int>(gr.x * gr.y);
+            int blocks = ntiles < coop_blocks ? ntiles : coop_blocks;
+            MBS_CHECK_CUDA(cudaMemsetAsync(tile_changed, 0, 2 * static_cast<size_t>(ntiles), stream));
+            void *args[] = {(void *)&img, (void *)&negate, (void *)&markers, (void *)&mask, (void *)&H, (void *)&W,
+                            (void *)&Lv, (void *)&st, (void *)&tile_changed};
+            MBS_CHECK_CUDA(cudaLaunchCooperativeKernel((void *)ws_relax_coop_kernel, dim3(blocks), dim3(256), args, 0, stream));
+            mbs::count_launch();
         }
         ws_parent_kernel<<<g2, b2, 0, stream>>>(Lv, markers, mask, H, W, parent, uf, src);
         MBS_CHECK_LAUNCH();
@@ -663,7 +701,6 @@ int run_watershed(const float *img, int negate, const int *markers, const uint8_
     }
     ws_sequential_kernel<<<1, 32, 0, stream>>>(img, negate, markers, mask, H, W, lab, heap, st, force_sequential);
     MBS_CHECK_LAUNCH();
-    if (sweeps_out) *sweeps_out = sweeps;
     return 0;
 }
 
@@ -682,7 +719,7 @@ extern "C" size_t mbs_postproc_workspace_bytes(int H, int W) {
     const size_t tiles = (n + SCAN_TILE - 1) / SCAN_TILE;
     // cell_s, mask, seed, roots, area, rank, tile counts, markers, Lv, parent, uf, src, lab, heap, stats
     return r256(n * 4) + 2 * r256(n) + 3 * r256(n * 4) + r256(tiles * 4) + r256(n * 4) + 4 * r256(n * 4) +
-           r256(n * 4) + r256(n * sizeof(HeapItem)) + r256(sizeof(Stats)) + 4096;
+           r256(n * 4) + r256(n * sizeof(HeapItem)) + r256(sizeof(Stats)) + r256(n / 64 + 4096) + 4096;
 }
 
 extern "C" int mbs_pp_front(const float *border, const float *cell, int H, int W, int ld, float th_seed, float th_cell,
@@ -754,19 +791,19 @@ extern "C" int mbs_pp_watershed(const float *image, const int32_t *markers, cons
     int *uf = cv.take<int>(n);
     int *src = cv.take<int>(n);
     HeapItem *heap = cv.take<HeapItem>(n);
+    uint8_t *tile_changed = cv.take<uint8_t>(n / 64 + 4096);
     MBS_REQUIRE(cv.ok, "watershed: workspace carve failed");
     Stats *hp = pinned_stats();
     MBS_REQUIRE(hp != nullptr, "watershed: cannot allocate pinned host memory");
     MBS_CHECK_CUDA(cudaMemsetAsync(st, 0, sizeof(Stats), stream));
-    int sweeps = 0;
-    int rc = run_watershed(image, 0, markers, mask, H, W, labels_out, Lv, parent, uf, src, heap, st, hp,
-                           force_sequential, &sweeps, stream);
+    int rc = run_watershed(image, 0, markers, mask, H, W, labels_out, Lv, parent, uf, src, heap, st, tile_changed,
+                           force_sequential, stream);
     if (rc) return rc;
     if (info_host) {
         MBS_CHECK_CUDA(cudaMemcpyAsync(hp, st, sizeof(Stats), cudaMemcpyDeviceToHost, stream));
         MBS_CHECK_CUDA(cudaStreamSynchronize(stream));
         memset(info_host, 0, 8 * sizeof(int64_t));
-        info_host[2] = sweeps;
+        info_host[2] = hp->sweeps;
         info_host[3] = (force_sequential || hp->ambiguous) ? 1 : 0;
         info_host[4] = hp->ambiguous;
     }
@@ -799,6 +836,7 @@ extern "C" int mbs_distance_postprocessing(const float *border, const float *cel
     int *src = cv.take<int>(n);
     int *lab = cv.take<int>(n);
     HeapItem *heap = cv.take<HeapItem>(n);
+    uint8_t *tile_changed = cv.take<uint8_t>(n / 64 + 4096);
     MBS_REQUIRE(cv.ok, "distance_postprocessing: workspace carve failed");
     Stats *hp = pinned_stats();
     MBS_REQUIRE(hp != nullptr, "distance_postprocessing: cannot allocate pinned host memory");
@@ -813,8 +851,7 @@ extern "C" int mbs_distance_postprocessing(const float *border, const float *cel
     if (rc) return rc;
     markers_kernel<<<nb, 256, 0, stream>>>(roots, rank, mask, nn, markers);
     MBS_CHECK_LAUNCH();
-    int sweeps = 0;
-    rc = run_watershed(cell_s, /*negate=*/1, markers, mask, H, W, lab, Lv, parent, uf, src, heap, st, hp, 0, &sweeps,
+    rc = run_watershed(cell_s, /*negate=*/1, markers, mask, H, W, lab, Lv, parent, uf, src, heap, st, tile_changed, 0,
                        stream);
     if (rc) return rc;
     to_u16_kernel<<<nb, 256, 0, stream>>>(lab, nn, out);
@@ -825,7 +862,7 @@ extern "C" int mbs_distance_postprocessing(const float *border, const float *cel
         memset(info_host, 0, 8 * sizeof(int64_t));
         info_host[0] = hp->n_comp;
         info_host[1] = hp->n_markers;
-        info_host[2] = sweeps;
+        info_host[2] = hp->sweeps;
         info_host[3] = hp->ambiguous ? 1 : 0;
         info_host[4] = hp->ambiguous;
     }

@@ -482,10 +482,14 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
 // ------------------------------------------------------------------------------------------
 template <typename T>
 __global__ void first_conv_kernel(const T *__restrict__ img, int H, int W, int pad_y, int pad_x, float lo, float hi,
-                                  const float *__restrict__ weight, const float *__restrict__ bias,
+                                  const float *__restrict__ lohi_dev, const float *__restrict__ weight, const float *__restrict__ bias,
                                   const float *__restrict__ scale, const float *__restrict__ shift, int C, int act,
                                   __nv_bfloat16 *__restrict__ out, int ld, int coff) {
     extern __shared__ float s_w[];  // [C*9] weights, [C] bias, [C] scale, [C] shift
+    if (lohi_dev) {                 // frame min / max computed on the device (mbs_frame_minmax)
+        lo = lohi_dev[0];
+        hi = lohi_dev[1];
+    }
     for (int i = threadIdx.x; i < C * 9; i += blockDim.x) s_w[i] = weight[i];
     for (int i = threadIdx.x; i < C; i += blockDim.x) {
         s_w[C * 9 + i] = bias[i];
@@ -534,6 +538,47 @@ __global__ void first_conv_kernel(const T *__restrict__ img, int H, int W, int p
     }
     uint4 *d = reinterpret_cast<uint4 *>(out + static_cast<size_t>(pix) * ld + coff + cg * 8);
     *d = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+}
+
+// frame min / max (np.min / np.max of the raw frame, infer_script_local.py:124) as ordered uint keys
+__device__ __forceinline__ unsigned int order_key(float f) {
+    const unsigned int u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float order_unkey(unsigned int k) {
+    return __uint_as_float((k & 0x80000000u) ? (k & 0x7FFFFFFFu) : ~k);
+}
+template <typename T>
+__device__ __forceinline__ unsigned int to_key(T v) { return static_cast<unsigned int>(v); }
+template <>
+__device__ __forceinline__ unsigned int to_key<float>(float v) { return order_key(v); }
+
+__global__ void minmax_init_kernel(unsigned int *keys) {
+    keys[0] = 0xFFFFFFFFu;
+    keys[1] = 0u;
+}
+template <typename T>
+__global__ void minmax_kernel(const T *__restrict__ img, long long n, unsigned int *keys) {
+    unsigned int lo = 0xFFFFFFFFu, hi = 0u;
+    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const unsigned int k = to_key<T>(img[i]);
+        lo = k < lo ? k : lo;
+        hi = k > hi ? k : hi;
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        const unsigned int a = __shfl_xor_sync(0xffffffffu, lo, o), b = __shfl_xor_sync(0xffffffffu, hi, o);
+        lo = a < lo ? a : lo;
+        hi = b > hi ? b : hi;
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicMin(&keys[0], lo);
+        atomicMax(&keys[1], hi);
+    }
+}
+__global__ void minmax_final_kernel(const unsigned int *keys, int is_float, float *lohi) {
+    lohi[0] = is_float ? order_unkey(keys[0]) : static_cast<float>(keys[0]);
+    lohi[1] = is_float ? order_unkey(keys[1]) : static_cast<float>(keys[1]);
 }
 
 __global__ void pack_conv3x3_kernel(const float *__restrict__ w, int Cout, int Cin, __nv_bfloat16 *__restrict__ out) {
@@ -718,7 +763,7 @@ extern "C" int mbs_conv_gemm(const mbs_conv_desc *d, void *stream_) {
 }
 
 extern "C" int mbs_first_conv(const void *img, int in_dtype, int H, int W, int pad_y, int pad_x, float norm_lo,
-                              float norm_hi, const float *weight, const float *bias, const float *scale,
+                              float norm_hi, const float *lohi_dev, const float *weight, const float *bias, const float *scale,
                               const float *shift, int C, int act, void *out, int out_ld, int out_coff,
                               void *stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
@@ -735,17 +780,17 @@ extern "C" int mbs_first_conv(const void *img, int in_dtype, int H, int W, int p
     switch (in_dtype) {
         case MBS_IN_U8:
             first_conv_kernel<uint8_t><<<static_cast<int>(blocks), threads, smem, stream>>>(
-                static_cast<const uint8_t *>(img), H, W, pad_y, pad_x, norm_lo, norm_hi, weight, bias, scale, shift, C,
+                static_cast<const uint8_t *>(img), H, W, pad_y, pad_x, norm_lo, norm_hi, lohi_dev, weight, bias, scale, shift, C,
                 act, o, out_ld, out_coff);
             break;
         case MBS_IN_U16:
             first_conv_kernel<uint16_t><<<static_cast<int>(blocks), threads, smem, stream>>>(
-                static_cast<const uint16_t *>(img), H, W, pad_y, pad_x, norm_lo, norm_hi, weight, bias, scale, shift, C,
+                static_cast<const uint16_t *>(img), H, W, pad_y, pad_x, norm_lo, norm_hi, lohi_dev, weight, bias, scale, shift, C,
                 act, o, out_ld, out_coff);
             break;
         case MBS_IN_F32:
             first_conv_kernel<float><<<static_cast<int>(blocks), threads, smem, stream>>>(
-                static_cast<const float *>(img), H, W, pad_y, pad_x, norm_lo, norm_hi, weight, bias, scale, shift, C,
+                static_cast<const float *>(img), H, W, pad_y, pad_x, norm_lo, norm_hi, lohi_dev, weight, bias, scale, shift, C,
                 act, o, out_ld, out_coff);
             break;
         default: MBS_REQUIRE(false, "first conv: unknown input dtype %d", in_dtype);
@@ -762,6 +807,26 @@ extern "C" int mbs_debug_flags(int reset) {
         cudaMemcpyToSymbol(g_mbar_timeout, &z, sizeof(int));
     }
     return v;
+}
+
+extern "C" int mbs_frame_minmax(const void *img, int in_dtype, long long n, float *lohi_dev, void *scratch8,
+                                void *stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    MBS_REQUIRE(n > 0 && lohi_dev && scratch8, "frame_minmax: bad arguments");
+    unsigned int *keys = static_cast<unsigned int *>(scratch8);
+    minmax_init_kernel<<<1, 1, 0, stream>>>(keys);
+    MBS_CHECK_LAUNCH();
+    const int blocks = static_cast<int>(n / 4096 + 1 < 1184 ? n / 4096 + 1 : 1184);
+    switch (in_dtype) {
+        case MBS_IN_U8: minmax_kernel<uint8_t><<<blocks, 256, 0, stream>>>(static_cast<const uint8_t *>(img), n, keys); break;
+        case MBS_IN_U16: minmax_kernel<uint16_t><<<blocks, 256, 0, stream>>>(static_cast<const uint16_t *>(img), n, keys); break;
+        case MBS_IN_F32: minmax_kernel<float><<<blocks, 256, 0, stream>>>(static_cast<const float *>(img), n, keys); break;
+        default: MBS_REQUIRE(false, "frame_minmax: unknown input dtype %d", in_dtype);
+    }
+    MBS_CHECK_LAUNCH();
+    minmax_final_kernel<<<1, 1, 0, stream>>>(keys, in_dtype == MBS_IN_F32, lohi_dev);
+    MBS_CHECK_LAUNCH();
+    return 0;
 }
 
 extern "C" int mbs_pack_conv3x3_weight(const float *w, int Cout, int Cin, void *packed, void *stream_) {

@@ -21,7 +21,9 @@ def shard_frames(num_frames, rank, world_size):
 
 
 class FrameSegmenter:
-    """Reusable pinned/device staging for one frame size; double buffered."""
+    """Reusable pinned/device staging for one frame size, double buffered.  H2D, compute and D2H run on
+    three streams chained by events, so the copy of frame k+1 and the read-back of frame k-1 overlap
+    the network of frame k; frame min/max are reduced on the GPU (no host pass over the pixels)."""
 
     def __init__(self, net, ths, device=None):
         self.net = net
@@ -30,10 +32,11 @@ class FrameSegmenter:
         if self.device.type != "cuda":
             raise RuntimeError("microbeseg_b200.inference needs a CUDA device (no CPU fallback)")
         self._stage = {}
-        self.copy_stream = torch.cuda.Stream(self.device)
+        self.h2d_stream = torch.cuda.Stream(self.device)
+        self.d2h_stream = torch.cuda.Stream(self.device)
 
     def _staging(self, shape, dtype, slot):
-        key = (tuple(shape), dtype, slot)
+        key = (tuple(shape), np.dtype(dtype).str, slot)
         st = self._stage.get(key)
         if st is None:
             tdt = {np.dtype(np.uint8): torch.uint8, np.dtype(np.uint16): torch.int16,
@@ -42,7 +45,9 @@ class FrameSegmenter:
                       dev_in=torch.empty(shape, dtype=tdt, device=self.device),
                       dev_out=torch.empty(shape, dtype=torch.int16, device=self.device),
                       pin_out=torch.empty(shape, dtype=torch.int16).pin_memory(),
-                      ev_in=torch.cuda.Event(), ev_out=torch.cuda.Event())
+                      lohi=torch.empty(2, dtype=torch.float32, device=self.device),
+                      scratch=torch.empty(2, dtype=torch.int32, device=self.device),
+                      ev_h2d=torch.cuda.Event(), ev_done=torch.cuda.Event(), ev_out=torch.cuda.Event())
             self._stage[key] = st
         return st
 
@@ -56,46 +61,62 @@ class FrameSegmenter:
     def submit(self, frame, slot=0, min_val=None, max_val=None, crop=None):
         """Enqueue H2D + network + post-processing + D2H for one (H,W) frame; returns a handle.
         ``crop=[py,px]``: the frame is already padded by the caller; crop the outputs by py/px."""
+        from .unets import frame_minmax
         frame = self._canon(frame)
         H, W = frame.shape
-        lo = frame.min() if min_val is None else min_val            # infer_script_local.py:124
-        hi = frame.max() if max_val is None else max_val
         pads = model_input_pads(H, W) if crop is None else [0, 0]
         if len(pads) < 2:
             raise Exception('Image too big to pad. Use sliding windows')
+        cy, cx = (0, 0) if crop is None else (int(crop[0]), int(crop[1]))
         st = self._staging((H, W), frame.dtype, slot)
-        st["crop"] = (0, 0) if crop is None else (int(crop[0]), int(crop[1]))
-        src = torch.from_numpy(frame.view(np.int16) if frame.dtype == np.uint16 else frame)
-        st["pin_in"].copy_(src)
+        st["ev_h2d"].synchronize()                  # the previous upload from this pinned buffer is done
+        st["pin_in"].copy_(torch.from_numpy(frame.view(np.int16) if frame.dtype == np.uint16 else frame))
         main = torch.cuda.current_stream(self.device)
         with torch.cuda.device(self.device):
-            st["dev_in"].copy_(st["pin_in"], non_blocking=True)
+            with torch.cuda.stream(self.h2d_stream):
+                self.h2d_stream.wait_event(st["ev_done"])          # compute that read dev_in (2 frames ago) is done
+                st["dev_in"].copy_(st["pin_in"], non_blocking=True)
+                st["ev_h2d"].record(self.h2d_stream)
+            main.wait_event(st["ev_h2d"])
+            main.wait_event(st["ev_out"])                          # read-back of this slot's previous mask is done
             try:
-                border, cell = self.net.forward_frame(st["dev_in"], pads, float(lo), float(hi))
+                if min_val is None or max_val is None:
+                    # frame min / max before padding (infer_script_local.py:124), reduced on the device
+                    lohi = frame_minmax(st["dev_in"], out=st["lohi"], scratch=st["scratch"])
+                    border, cell = self.net.forward_frame(st["dev_in"], pads, lohi_dev=lohi)
+                else:
+                    border, cell = self.net.forward_frame(st["dev_in"], pads, float(min_val), float(max_val))
             except RuntimeError:
                 # same contract as infer.py:352-356: a RuntimeError during net() yields an empty mask
                 st["dev_out"].zero_()
+                st["view"] = (cy, cx) if (cy, cx) != (0, 0) else None
                 print('RuntimeError during inference (maybe not enough ram/vram?)')
             else:
-                cy, cx = st["crop"]
                 b = border[0, 0, pads[0] + cy:, pads[1] + cx:]      # crop the pads (infer.py:358-359)
                 c = cell[0, 0, pads[0] + cy:, pads[1] + cx:]
-                dst = st["dev_out"] if (cy, cx) == (0, 0) else torch.empty(
-                    (H - cy, W - cx), dtype=torch.int16, device=self.device)
-                pp.distance_postprocessing_device(b, c, self.th_seed, self.th_cell, out=dst)
-                st["cropped"] = None if (cy, cx) == (0, 0) else dst
-            if st.get("cropped") is not None:
-                st["host_cropped"] = st["cropped"].cpu()
-            st["pin_out"].copy_(st["dev_out"], non_blocking=True)
-            st["ev_out"].record(main)
+                if (cy, cx) == (0, 0):
+                    pp.distance_postprocessing_device(b, c, self.th_seed, self.th_cell, out=st["dev_out"])
+                    st["view"] = None
+                else:
+                    small = pp.distance_postprocessing_device(b, c, self.th_seed, self.th_cell)
+                    st["dev_out"].zero_()
+                    st["dev_out"][cy:, cx:] = small
+                    st["view"] = (cy, cx)
+            st["ev_done"].record(main)
+            with torch.cuda.stream(self.d2h_stream):
+                self.d2h_stream.wait_event(st["ev_done"])
+                st["pin_out"].copy_(st["dev_out"], non_blocking=True)
+                st["ev_out"].record(self.d2h_stream)
         return st
 
     @staticmethod
     def result(handle):
         handle["ev_out"].synchronize()
-        if handle.get("cropped") is not None:
-            return handle["host_cropped"].numpy().view(np.uint16).copy()
-        return handle["pin_out"].numpy().view(np.uint16).copy()
+        out = handle["pin_out"].numpy().view(np.uint16)
+        v = handle.get("view")
+        if isinstance(v, tuple):
+            out = out[v[0]:, v[1]:]
+        return out.copy()
 
     def segment(self, frame, min_val=None, max_val=None, crop=None):
         return self.result(self.submit(frame, 0, min_val, max_val, crop))

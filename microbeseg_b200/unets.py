@@ -159,14 +159,15 @@ class DUNet(_NetBase):
         outs = self._forward_maps(x)
         return outs[0], outs[1]
 
-    def forward_frame(self, img, pads, lo, hi):
+    def forward_frame(self, img, pads, lo=0.0, hi=0.0, lohi_dev=None):
         """Fused entry used by the frame loop: raw (H,W) uint8/uint16/float32 CUDA frame ->
         (border, cell) float32 [1,1,Hp,Wp] of the padded size; normalisation
-        ``2*(x-lo)/(hi-lo)-1`` and top/left padding with ``lo`` happen inside the first kernel."""
+        ``2*(x-lo)/(hi-lo)-1`` and top/left padding with ``lo`` happen inside the first kernel.
+        ``lohi_dev`` (float32[2] CUDA tensor from ``frame_minmax``) keeps min/max on the device."""
         self._check_supported()
         if self.training:
             raise RuntimeError("microbeseg_b200: training-mode forward is not built yet (call net.eval())")
-        outs = self.engine().run(img[None], int(pads[0]), int(pads[1]), float(lo), float(hi))
+        outs = self.engine().run(img[None], int(pads[0]), int(pads[1]), float(lo), float(hi), lohi_dev=lohi_dev)
         return outs[0], outs[1]
 
 
@@ -181,6 +182,21 @@ class UNet(_NetBase):
         if self.ch_out != 1:
             raise NotImplementedError("multi-channel heads (boundary method) are not built yet")
         return self._forward_maps(x)[0]
+
+
+def frame_minmax(img, out=None, scratch=None):
+    """(min, max) of a raw CUDA frame as a float32[2] CUDA tensor (np.min/np.max of infer_script_local.py:124)."""
+    if img.dtype not in _IN_CODES:
+        raise RuntimeError(f"unsupported frame dtype {img.dtype}")
+    if out is None:
+        out = torch.empty(2, dtype=torch.float32, device=img.device)
+    if scratch is None:
+        scratch = torch.empty(2, dtype=torch.int32, device=img.device)
+    img = img.contiguous()
+    with torch.cuda.device(img.device):
+        nat.check(nat.lib().mbs_frame_minmax(img.data_ptr(), _IN_CODES[img.dtype], img.numel(), out.data_ptr(),
+                                             scratch.data_ptr(), nat.stream_ptr()), "frame_minmax")
+    return out
 
 
 class _Engine:
@@ -279,7 +295,7 @@ class _Engine:
         nat.check(self.L.mbs_conv_gemm(ctypes.byref(d), nat.stream_ptr()), name)
         self.last_conv_launches += 1
 
-    def run(self, img, pad_y, pad_x, lo, hi, events=None):
+    def run(self, img, pad_y, pad_x, lo, hi, events=None, lohi_dev=None):
         """img: [N,H,W] CUDA tensor (uint8 / uint16-as-int16 / float32).  hi < lo -> the values are
         already normalised (reference callers pass the normalised float image)."""
         if img.dtype not in _IN_CODES:
@@ -305,6 +321,7 @@ class _Engine:
             packed, bias, scale, shift, _, c0 = self.p["enc0a"]
             for b in range(n):
                 nat.check(self.L.mbs_first_conv(img[b].data_ptr(), _IN_CODES[img.dtype], h0, w0, pad_y, pad_x, lo, hi,
+                                                lohi_dev.data_ptr() if lohi_dev is not None else None,
                                                 packed.data_ptr(), bias.data_ptr(), scale.data_ptr(),
                                                 shift.data_ptr(), c0, self.act, t1[0][b].data_ptr(), c0, 0,
                                                 nat.stream_ptr()), "first_conv")

@@ -195,3 +195,28 @@ def test_segment_stack_end_to_end(native_lib):
     assert sorted(shard_frames(7, 0, 2) + shard_frames(7, 1, 2)) == list(range(7))
     half = segment_stack(net, stack, frames=shard_frames(3, 1, 2))
     assert np.array_equal(half[1], out[1]) and not half[0].any()
+
+
+def test_frame_minmax_on_device(native_lib):
+    from microbeseg_b200.unets import frame_minmax
+    rng = np.random.default_rng(3)
+    for arr in (rng.integers(7, 250, (33, 47)).astype(np.uint8), rng.integers(100, 60000, (64, 100)).astype(np.uint16),
+                rng.normal(0, 50, (50, 50)).astype(np.float32), -np.abs(rng.normal(3, 1, (9, 9))).astype(np.float32)):
+        t = torch.from_numpy(arr.view(np.int16) if arr.dtype == np.uint16 else arr).cuda()
+        lohi = frame_minmax(t).cpu().numpy()
+        assert lohi[0] == np.float32(arr.min()) and lohi[1] == np.float32(arr.max())
+
+
+def test_infer_worker_style_call_with_caller_padding(native_lib):
+    """InferWorker.inference(img_padded, min_val, max_val, pads) (infer.py:256-259, 328-376)."""
+    from microbeseg_b200 import synthetic as sy
+    from microbeseg_b200.inference import FrameSegmenter
+    from microbeseg_b200.utils import zero_pad_model_input
+    torch.set_grad_enabled(False)
+    net, sd = _build((64, 128), "relu", 61)
+    img = sy.synth_frame(100, 120, 11)
+    seg = FrameSegmenter(net, (0.10, 0.45))
+    direct = seg.segment(img)
+    padded, pads = zero_pad_model_input(img, pad_val=img.min())
+    via_pads = seg.segment(padded, img.min(), img.max(), crop=pads)
+    assert via_pads.shape == img.shape and np.array_equal(direct, via_pads)
