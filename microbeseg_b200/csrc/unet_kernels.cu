@@ -19,6 +19,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 
@@ -185,6 +186,144 @@ __device__ __forceinline__ float apply_act(float v, int act) {
     }
 }
 
+// Epilogue of one tile, executed by the 8 epilogue warps: TMEM -> registers -> bias / activation /
+// BatchNorm affine -> bf16 -> XOR-swizzled smem transpose -> full-sector global stores (+ fused 1x1 head).
+template <int BN, int TW>
+__device__ __forceinline__ void epilogue_tile(const ConvKParams &p, const float *s_par, uint32_t s_epi, float *s_head,
+                                              uint32_t tmem_base, uint32_t tfull, uint32_t tempty, int lt, int quad,
+                                              int half, int lane, int x0, int y0, int img, int n0, bool has_head) {
+    const int buf = lt & 1;
+    const int row = quad * 32 + lane;
+    mbar_wait(tfull, (lt >> 1) & 1);
+    tcgen05_fence_after();
+    float head_acc = 0.0f;
+#pragma unroll 1
+    for (int c = half * (BN / 2); c < (half + 1) * (BN / 2); c += 32) {
+        uint32_t r[32];
+        tmem_ld32(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(buf * BN + c), r);
+        const int col = n0 + c;
+        int q = 0, co = col;
+        if (p.mode == MBS_CONVT2X2_S2) {
+            q = col / p.Cout;
+            co = col - q * p.Cout;
+        }
+        const float4 *pb = reinterpret_cast<const float4 *>(s_par + co);
+        const float4 *psc = reinterpret_cast<const float4 *>(s_par + p.Cout + co);
+        const float4 *psh = reinterpret_cast<const float4 *>(s_par + 2 * p.Cout + co);
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float4 b4 = pb[j];
+            v[4 * j + 0] = __uint_as_float(r[4 * j + 0]) + b4.x;
+            v[4 * j + 1] = __uint_as_float(r[4 * j + 1]) + b4.y;
+            v[4 * j + 2] = __uint_as_float(r[4 * j + 2]) + b4.z;
+            v[4 * j + 3] = __uint_as_float(r[4 * j + 3]) + b4.w;
+        }
+        // one uniform branch per chunk (a per-element switch costs an indirect branch each)
+        switch (p.act) {
+            case MBS_ACT_RELU:
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.0f);
+                break;
+            case MBS_ACT_LEAKYRELU:
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = v[j] > 0.0f ? v[j] : 0.01f * v[j];
+                break;
+            case MBS_ACT_ELU:
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = v[j] > 0.0f ? v[j] : expm1f(v[j]);
+                break;
+            case MBS_ACT_MISH:
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], MBS_ACT_MISH);
+                break;
+            default: break;
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float4 s4 = psc[j], t4 = psh[j];
+            v[4 * j + 0] = fmaf(v[4 * j + 0], s4.x, t4.x);
+            v[4 * j + 1] = fmaf(v[4 * j + 1], s4.y, t4.y);
+            v[4 * j + 2] = fmaf(v[4 * j + 2], s4.z, t4.z);
+            v[4 * j + 3] = fmaf(v[4 * j + 3], s4.w, t4.w);
+        }
+        if (has_head) {
+            const float4 *phw = reinterpret_cast<const float4 *>(s_par + 3 * p.Cout + co);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float4 w4 = phw[j];
+                head_acc = fmaf(v[4 * j + 0], w4.x, head_acc);
+                head_acc = fmaf(v[4 * j + 1], w4.y, head_acc);
+                head_acc = fmaf(v[4 * j + 2], w4.z, head_acc);
+                head_acc = fmaf(v[4 * j + 3], w4.w, head_acc);
+            }
+        }
+        if (p.dst) {
+            uint32_t packed[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                __nv_bfloat162 h2 = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+                packed[j] = *reinterpret_cast<uint32_t *>(&h2);
+            }
+            // two passes of 16 columns: stage 32 rows x 32 B (16-byte chunks XOR-swizzled, conflict free),
+            // then 2 lanes write one pixel's 32 contiguous bytes (a full sector), 16 pixels per instruction
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+#pragma unroll
+                for (int ch = 0; ch < 2; ++ch) {
+                    const uint32_t a = s_epi + lane * 32u + static_cast<uint32_t>((ch ^ ((lane >> 2) & 1)) * 16);
+                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a),
+                                 "r"(packed[8 * hh + 4 * ch]), "r"(packed[8 * hh + 4 * ch + 1]),
+                                 "r"(packed[8 * hh + 4 * ch + 2]), "r"(packed[8 * hh + 4 * ch + 3])
+                                 : "memory");
+                }
+                __syncwarp();
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                    const int rr = i * 16 + (lane >> 1);          // row inside this warp's 32
+                    const int ch = lane & 1;
+                    const int trow = quad * 32 + rr;
+                    const int qy = y0 + trow / TW, qx = x0 + trow % TW;
+                    uint32_t v0, v1, v2, v3;
+                    const uint32_t a = s_epi + rr * 32u + static_cast<uint32_t>((ch ^ ((rr >> 2) & 1)) * 16);
+                    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                                 : "=r"(v0), "=r"(v1), "=r"(v2), "=r"(v3)
+                                 : "r"(a)
+                                 : "memory");
+                    if (qy < p.Hm && qx < p.Wm) {
+                        size_t off;
+                        if (p.mode == MBS_CONVT2X2_S2) {
+                            const int oy = 2 * qy + (q >> 1), ox = 2 * qx + (q & 1);
+                            off = ((static_cast<size_t>(img) * p.Hd + oy) * p.Wd + ox) * p.ldd + p.coffd + co;
+                        } else {
+                            off = ((static_cast<size_t>(img) * p.Hd + qy) * p.Wd + qx) * p.ldd + p.coffd + col;
+                        }
+                        *reinterpret_cast<uint4 *>(p.dst + off + hh * 16 + ch * 8) = make_uint4(v0, v1, v2, v3);
+                    }
+                }
+                __syncwarp();
+            }
+        }
+    }
+    // all TMEM reads of this tile are complete (tcgen05.wait::ld inside tmem_ld32)
+    tcgen05_fence_before();
+    __syncwarp();
+    if (lane == 0) {
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tempty) : "memory");
+    }
+    if (has_head) {
+        // the two column-half warps of a quadrant combine their partial dot products through smem
+        float *slot = s_head + (lt & 1) * 128 + row;
+        if (half == 1) *slot = head_acc;
+        asm volatile("bar.sync %0, 64;" ::"r"(1 + quad) : "memory");
+        if (half == 0) {
+            const int py = y0 + row / TW, px = x0 + row % TW;
+            if (py < p.Hm && px < p.Wm)
+                p.head_out[(static_cast<size_t>(img) * p.Hm + py) * p.Wm + px] = (head_acc + *slot) + p.head_b;
+        }
+    }
+}
+
 template <int BN, int STAGES>
 struct SmemPlan {
     static constexpr int B_BYTES = BN * BK * 2;
@@ -338,135 +477,183 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
             const int ty = (m_tile / p.tiles_x) % p.tiles_y;
             const int img = m_tile / tiles_per_img;
             const int x0 = tx * TILE_W, y0 = ty * TILE_H, n0 = n_tile * BN;
-            const int buf = lt & 1;
-            mbar_wait(tfull_bar(buf), (lt >> 1) & 1);
-            tcgen05_fence_after();
-            float head_acc = 0.0f;
-#pragma unroll 1
-            for (int c = half * (BN / 2); c < (half + 1) * (BN / 2); c += 32) {
-                uint32_t r[32];
-                tmem_ld32(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(buf * BN + c), r);
-                const int col = n0 + c;
-                int q = 0, co = col;
-                if (p.mode == MBS_CONVT2X2_S2) {
-                    q = col / p.Cout;
-                    co = col - q * p.Cout;
-                }
-                const float4 *pb = reinterpret_cast<const float4 *>(s_par + co);
-                const float4 *psc = reinterpret_cast<const float4 *>(s_par + p.Cout + co);
-                const float4 *psh = reinterpret_cast<const float4 *>(s_par + 2 * p.Cout + co);
-                float v[32];
+            epilogue_tile<BN, TILE_W>(p, s_par, s_epi, s_head, tmem_base, tfull_bar(lt & 1), tempty_bar(lt & 1), lt, quad, half,
+                                      lane, x0, y0, img, n0, has_head);
+        }
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tcgen05_fence_after();
+        tmem_dealloc(tmem_base, 2 * BN);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Full-resolution variant for Cout = 64, Cin = 64 (+64): halo tiles + smem-resident weights.
+//
+// At full resolution (M = H*W pixels, N = 64) the generic kernel is bound by L2 -> smem traffic:
+// every tap re-reads the A patch (9x) and every tile re-reads all weights.  Here
+//   * a tile is 8 wide x 16 tall, so UMMA row group g (8 rows) is image row g of the tile;
+//   * per 64-channel source chunk ONE TMA box load brings the (16+2)x(8+2) pixel halo patch
+//     (128 B per pixel, SWIZZLE_128B); the A operand of tap (ky,kx) is the same smem with the
+//     descriptor start address advanced by (ky*10+kx)*128 B and stride-byte-offset 10*128 B
+//     (the swizzle is a function of the absolute smem address, so shifted starts stay consistent
+//     with what TMA wrote);
+//   * all 9 x chunks weight tiles (8 KiB each) are loaded once per CTA and stay in smem.
+// L2 -> smem traffic per tile drops from 9*16 KiB + 72 KiB to 22.5 KiB per source chunk.
+// ------------------------------------------------------------------------------------------
+constexpr int HT_W = 8, HT_H = 16;
+constexpr int HALO_W = HT_W + 2, HALO_H = HT_H + 2;
+constexpr int HALO_BYTES = HALO_W * HALO_H * 128;              // 23040
+constexpr int HALO_SLOT = (HALO_BYTES + 1023) / 1024 * 1024;   // 23552
+constexpr int W_TILE_BYTES = 64 * 128;                         // one (tap, chunk) weight tile, N = 64
+
+template <int CHUNKS, int STAGES>
+struct HaloPlan {
+    static constexpr int OFF_W = 0;
+    static constexpr int OFF_A = 9 * CHUNKS * W_TILE_BYTES;
+    static constexpr int OFF_EPI = OFF_A + STAGES * HALO_SLOT;
+    static constexpr int EPI_BYTES = EPI_WARPS * 1024 + 2 * 128 * 4;
+    static constexpr int OFF_BAR = OFF_EPI + EPI_BYTES;        // full[S], empty[S], tfull[2], tempty[2], wbar
+    static constexpr int OFF_TMEM = OFF_BAR + 8 * (2 * STAGES + 5);
+    static constexpr int OFF_PAR = (OFF_TMEM + 8 + 15) / 16 * 16;
+    static constexpr int DYN_BYTES = OFF_PAR + 4 * 64 * 4 + 1024;
+};
+
+__device__ __forceinline__ uint64_t make_sw128_desc_sbo(uint32_t saddr, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= static_cast<uint64_t>((saddr & 0x3FFFFu) >> 4);
+    d |= static_cast<uint64_t>(1) << 16;
+    d |= static_cast<uint64_t>(sbo_bytes >> 4) << 32;
+    d |= static_cast<uint64_t>(1) << 46;
+    d |= static_cast<uint64_t>(2) << 61;
+    return d;
+}
+
+template <int CHUNKS, int STAGES>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+conv_halo64_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
+                   const __grid_constant__ CUtensorMap tmB, const ConvKParams p) {
+    using Plan = HaloPlan<CHUNKS, STAGES>;
+    constexpr int BN = 64;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t base = (raw + 1023u) & ~1023u;
+    uint8_t *gbase = smem_raw + (base - raw);
+    const uint32_t sW = base + Plan::OFF_W;
+    const uint32_t sA = base + Plan::OFF_A;
+    const uint32_t sBar = base + Plan::OFF_BAR;
+    auto full_bar = [&](int s) { return sBar + 8u * s; };
+    auto empty_bar = [&](int s) { return sBar + 8u * (STAGES + s); };
+    auto tfull_bar = [&](int b) { return sBar + 8u * (2 * STAGES + b); };
+    auto tempty_bar = [&](int b) { return sBar + 8u * (2 * STAGES + 2 + b); };
+    const uint32_t w_bar = sBar + 8u * (2 * STAGES + 4);
+    volatile uint32_t *tmem_ptr = reinterpret_cast<volatile uint32_t *>(gbase + Plan::OFF_TMEM);
+    float *s_par = reinterpret_cast<float *>(gbase + Plan::OFF_PAR);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int tiles_per_img = p.tiles_x * p.tiles_y;
+
+    if (threadIdx.x == 0) {
+        prefetch_tmap(&tmA0);
+        if (CHUNKS > 1) prefetch_tmap(&tmA1);
+        prefetch_tmap(&tmB);
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(full_bar(s), 1);
+            mbar_init(empty_bar(s), 1);
+        }
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(tfull_bar(b), 1);
+            mbar_init(tempty_bar(b), EPI_WARPS);
+        }
+        mbar_init(w_bar, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(smem_u32(const_cast<uint32_t *>(tmem_ptr)), 2 * BN);
+    if (warp >= 2) {
+        for (int j = threadIdx.x - 64; j < 64; j += NUM_THREADS - 64) {
+            s_par[j] = p.bias[j];
+            s_par[64 + j] = p.scale[j];
+            s_par[128 + j] = p.shift[j];
+            s_par[192 + j] = p.head_w ? p.head_w[j] : 0.0f;
+        }
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ===== TMA producer: resident weights once, then one halo patch per (tile, source chunk) =====
+            mbar_expect_tx(w_bar, 9 * CHUNKS * W_TILE_BYTES);
+            for (int t = 0; t < 9 * CHUNKS; ++t) tma_load_2d(sW + t * W_TILE_BYTES, &tmB, w_bar, t * BK, 0);
+            int it_g = 0;
+            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+                const int tx = tile % p.tiles_x;
+                const int ty = (tile / p.tiles_x) % p.tiles_y;
+                const int img = tile / tiles_per_img;
+                const int x0 = tx * HT_W, y0 = ty * HT_H;
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const float4 b4 = pb[j];
-                    v[4 * j + 0] = __uint_as_float(r[4 * j + 0]) + b4.x;
-                    v[4 * j + 1] = __uint_as_float(r[4 * j + 1]) + b4.y;
-                    v[4 * j + 2] = __uint_as_float(r[4 * j + 2]) + b4.z;
-                    v[4 * j + 3] = __uint_as_float(r[4 * j + 3]) + b4.w;
-                }
-                // one uniform branch per chunk (a per-element switch costs an indirect branch each)
-                switch (p.act) {
-                    case MBS_ACT_RELU:
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.0f);
-                        break;
-                    case MBS_ACT_LEAKYRELU:
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) v[j] = v[j] > 0.0f ? v[j] : 0.01f * v[j];
-                        break;
-                    case MBS_ACT_ELU:
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) v[j] = v[j] > 0.0f ? v[j] : expm1f(v[j]);
-                        break;
-                    case MBS_ACT_MISH:
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], MBS_ACT_MISH);
-                        break;
-                    default: break;
-                }
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const float4 s4 = psc[j], t4 = psh[j];
-                    v[4 * j + 0] = fmaf(v[4 * j + 0], s4.x, t4.x);
-                    v[4 * j + 1] = fmaf(v[4 * j + 1], s4.y, t4.y);
-                    v[4 * j + 2] = fmaf(v[4 * j + 2], s4.z, t4.z);
-                    v[4 * j + 3] = fmaf(v[4 * j + 3], s4.w, t4.w);
-                }
-                if (has_head) {
-                    const float4 *phw = reinterpret_cast<const float4 *>(s_par + 3 * p.Cout + co);
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const float4 w4 = phw[j];
-                        head_acc = fmaf(v[4 * j + 0], w4.x, head_acc);
-                        head_acc = fmaf(v[4 * j + 1], w4.y, head_acc);
-                        head_acc = fmaf(v[4 * j + 2], w4.z, head_acc);
-                        head_acc = fmaf(v[4 * j + 3], w4.w, head_acc);
-                    }
-                }
-                if (p.dst) {
-                    uint32_t packed[16];
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        __nv_bfloat162 h2 = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
-                        packed[j] = *reinterpret_cast<uint32_t *>(&h2);
-                    }
-                    // two passes of 16 columns: stage 32 rows x 32 B (16-byte chunks XOR-swizzled, conflict free),
-                    // then 2 lanes write one pixel's 32 contiguous bytes (a full sector), 16 pixels per instruction
-#pragma unroll
-                    for (int hh = 0; hh < 2; ++hh) {
-#pragma unroll
-                        for (int ch = 0; ch < 2; ++ch) {
-                            const uint32_t a = s_epi + lane * 32u + static_cast<uint32_t>((ch ^ ((lane >> 2) & 1)) * 16);
-                            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a),
-                                         "r"(packed[8 * hh + 4 * ch]), "r"(packed[8 * hh + 4 * ch + 1]),
-                                         "r"(packed[8 * hh + 4 * ch + 2]), "r"(packed[8 * hh + 4 * ch + 3])
-                                         : "memory");
-                        }
-                        __syncwarp();
-#pragma unroll
-                        for (int i = 0; i < 2; ++i) {
-                            const int rr = i * 16 + (lane >> 1);          // row inside this warp's 32
-                            const int ch = lane & 1;
-                            const int trow = quad * 32 + rr;
-                            const int qy = y0 + trow / TILE_W, qx = x0 + trow % TILE_W;
-                            uint32_t v0, v1, v2, v3;
-                            const uint32_t a = s_epi + rr * 32u + static_cast<uint32_t>((ch ^ ((rr >> 2) & 1)) * 16);
-                            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
-                                         : "=r"(v0), "=r"(v1), "=r"(v2), "=r"(v3)
-                                         : "r"(a)
-                                         : "memory");
-                            if (qy < p.Hm && qx < p.Wm) {
-                                size_t off;
-                                if (p.mode == MBS_CONVT2X2_S2) {
-                                    const int oy = 2 * qy + (q >> 1), ox = 2 * qx + (q & 1);
-                                    off = ((static_cast<size_t>(img) * p.Hd + oy) * p.Wd + ox) * p.ldd + p.coffd + co;
-                                } else {
-                                    off = ((static_cast<size_t>(img) * p.Hd + qy) * p.Wd + qx) * p.ldd + p.coffd + col;
-                                }
-                                *reinterpret_cast<uint4 *>(p.dst + off + hh * 16 + ch * 8) = make_uint4(v0, v1, v2, v3);
-                            }
-                        }
-                        __syncwarp();
-                    }
+                for (int cc = 0; cc < CHUNKS; ++cc, ++it_g) {
+                    const int s = it_g % STAGES;
+                    const uint32_t ph = (it_g / STAGES) & 1;
+                    mbar_wait(empty_bar(s), ph ^ 1u);
+                    mbar_expect_tx(full_bar(s), HALO_BYTES);
+                    tma_load_4d(sA + s * HALO_SLOT, cc == 0 ? &tmA0 : &tmA1, full_bar(s), 0, x0 - 1, y0 - 1, img);
                 }
             }
-            // all TMEM reads of this tile are complete (tcgen05.wait::ld inside tmem_ld32)
-            tcgen05_fence_before();
-            __syncwarp();
-            if (lane == 0) {
-                asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tempty_bar(buf)) : "memory");
-            }
-            if (has_head) {
-                // the two column-half warps of a quadrant combine their partial dot products through smem
-                float *slot = s_head + (lt & 1) * 128 + row;
-                if (half == 1) *slot = head_acc;
-                asm volatile("bar.sync %0, 64;" ::"r"(1 + quad) : "memory");
-                if (half == 0) {
-                    const int py = y0 + row / TILE_W, px = x0 + row % TILE_W;
-                    if (py < p.Hm && px < p.Wm)
-                        p.head_out[(static_cast<size_t>(img) * p.Hm + py) * p.Wm + px] = (head_acc + *slot) + p.head_b;
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc(BM, BN);
+            mbar_wait(w_bar, 0);
+            int it_g = 0, lt = 0;
+            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++lt) {
+                const int buf = lt & 1;
+                mbar_wait(tempty_bar(buf), ((lt >> 1) & 1) ^ 1u);
+                tcgen05_fence_after();
+                const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(buf * BN);
+#pragma unroll
+                for (int cc = 0; cc < CHUNKS; ++cc, ++it_g) {
+                    const int s = it_g % STAGES;
+                    const uint32_t ph = (it_g / STAGES) & 1;
+                    mbar_wait(full_bar(s), ph);
+                    tcgen05_fence_after();
+                    const uint32_t a_slot = sA + s * HALO_SLOT;
+#pragma unroll
+                    for (int tap = 0; tap < 9; ++tap) {
+                        const uint32_t a_tap = a_slot + static_cast<uint32_t>(((tap / 3) * HALO_W + (tap % 3)) * 128);
+                        const uint64_t adesc = make_sw128_desc_sbo(a_tap, HALO_W * 128);
+                        const uint64_t bdesc = make_sw128_desc(sW + (tap * CHUNKS + cc) * W_TILE_BYTES);
+#pragma unroll
+                        for (int k = 0; k < BK / 16; ++k)
+                            umma_f16(tmem_d, adesc + 2u * k, bdesc + 2u * k, idesc, (cc > 0 || tap > 0 || k > 0) ? 1u : 0u);
+                    }
+                    umma_commit(empty_bar(s));
                 }
+                umma_commit(tfull_bar(buf));
             }
+        }
+        __syncwarp();
+    } else {
+        const int e = warp - 2;
+        const int quad = warp & 3;
+        const int half = e >> 2;
+        const uint32_t s_epi = base + Plan::OFF_EPI + static_cast<uint32_t>(e) * 1024u;
+        float *s_head = reinterpret_cast<float *>(gbase + Plan::OFF_EPI + EPI_WARPS * 1024);
+        const bool has_head = p.head_out != nullptr;
+        int lt = 0;
+        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++lt) {
+            const int tx = tile % p.tiles_x;
+            const int ty = (tile / p.tiles_x) % p.tiles_y;
+            const int img = tile / tiles_per_img;
+            epilogue_tile<BN, HT_W>(p, s_par, s_epi, s_head, tmem_base, tfull_bar(lt & 1), tempty_bar(lt & 1), lt, quad, half,
+                                    lane, tx * HT_W, ty * HT_H, img, 0, has_head);
         }
     }
     tcgen05_fence_before();
@@ -624,7 +811,8 @@ EncodeTiledFn get_encode_fn() {
 }
 
 // NHWC bf16 activation view -> 4-D tensor map (C, W, H, N), box (64, bw, bh, 1), traversal stride es.
-int make_act_map(CUtensorMap *map, const void *base, int N, int H, int W, int C, int ld, int coff, int es) {
+int make_act_map(CUtensorMap *map, const void *base, int N, int H, int W, int C, int ld, int coff, int es,
+                 int box_w = TILE_W, int box_h = TILE_H) {
     EncodeTiledFn enc = get_encode_fn();
     MBS_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled entry point not available (no CUDA driver?)");
     const char *p = static_cast<const char *>(base) + static_cast<size_t>(coff) * 2;
@@ -634,8 +822,8 @@ int make_act_map(CUtensorMap *map, const void *base, int N, int H, int W, int C,
                           static_cast<cuuint64_t>(N)};
     cuuint64_t strides[3] = {static_cast<cuuint64_t>(ld) * 2, static_cast<cuuint64_t>(W) * ld * 2,
                              static_cast<cuuint64_t>(H) * W * ld * 2};
-    cuuint32_t box[4] = {static_cast<cuuint32_t>(BK), static_cast<cuuint32_t>(TILE_W * es),
-                         static_cast<cuuint32_t>(TILE_H * es), 1};
+    cuuint32_t box[4] = {static_cast<cuuint32_t>(BK), static_cast<cuuint32_t>(box_w * es),
+                         static_cast<cuuint32_t>(box_h * es), 1};
     cuuint32_t estr[4] = {1, static_cast<cuuint32_t>(es), static_cast<cuuint32_t>(es), 1};
     CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<char *>(p), dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -689,6 +877,31 @@ int launch_conv(const CUtensorMap &a0, const CUtensorMap &a1, const CUtensorMap 
     return 0;
 }
 
+template <int CHUNKS, int STAGES>
+int launch_halo(const CUtensorMap &a0, const CUtensorMap &a1, const CUtensorMap &b, const ConvKParams &kp,
+                cudaStream_t stream) {
+    using Plan = HaloPlan<CHUNKS, STAGES>;
+    static bool configured = false;
+    if (!configured) {
+        MBS_CHECK_CUDA(cudaFuncSetAttribute(conv_halo64_kernel<CHUNKS, STAGES>,
+                                            cudaFuncAttributeMaxDynamicSharedMemorySize, Plan::DYN_BYTES));
+        configured = true;
+    }
+    const int grid = kp.num_tiles < sm_count() ? kp.num_tiles : sm_count();
+    conv_halo64_kernel<CHUNKS, STAGES><<<grid, NUM_THREADS, Plan::DYN_BYTES, stream>>>(a0, a1, b, kp);
+    MBS_CHECK_LAUNCH();
+    return 0;
+}
+
+bool halo_enabled() {
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("MBS_NO_HALO");
+        v = (e && e[0] == '1') ? 0 : 1;
+    }
+    return v == 1;
+}
+
 }  // namespace
 
 extern "C" int mbs_conv_gemm(const mbs_conv_desc *d, void *stream_) {
@@ -733,6 +946,29 @@ extern "C" int mbs_conv_gemm(const mbs_conv_desc *d, void *stream_) {
     kp.head_w = d->head_out ? d->head_w : nullptr;
     kp.head_b = d->head_b;
     kp.head_out = d->head_out;
+
+    if (halo_enabled() && d->mode == MBS_CONV3X3_S1 && d->Cout == 64 && d->C0 == 64 && (d->C1 == 0 || d->C1 == 64)) {
+        // full-resolution layers: halo tiles + resident weights (see conv_halo64_kernel)
+        kp.tiles_x = mbs::cdiv(kp.Wm, HT_W);
+        kp.tiles_y = mbs::cdiv(kp.Hm, HT_H);
+        kp.n_tiles = 1;
+        const long long tiles_ll = static_cast<long long>(d->N) * kp.tiles_x * kp.tiles_y;
+        MBS_REQUIRE(tiles_ll > 0 && tiles_ll < (1ll << 31), "too many tiles");
+        kp.num_tiles = static_cast<int>(tiles_ll);
+        CUtensorMap a0, a1, b;
+        int rc = make_act_map(&a0, d->src0, d->N, d->H, d->W, d->C0, d->ld0, d->coff0, 1, HALO_W, HALO_H);
+        if (rc) return rc;
+        if (d->C1 > 0) {
+            rc = make_act_map(&a1, d->src1, d->N, d->H, d->W, d->C1, d->ld1, d->coff1, 1, HALO_W, HALO_H);
+            if (rc) return rc;
+        } else {
+            a1 = a0;
+        }
+        rc = make_weight_map(&b, d->weight, 64, 9 * (d->C0 + d->C1), 64);
+        if (rc) return rc;
+        if (d->C1 > 0) return launch_halo<2, 2>(a0, a1, b, kp, stream);
+        return launch_halo<1, 4>(a0, a1, b, kp, stream);
+    }
 
     const int ncols = d->mode == MBS_CONVT2X2_S2 ? 4 * d->Cout : d->Cout;
     const int K = kp.taps * (d->C0 + d->C1);
