@@ -667,64 +667,91 @@ conv_halo64_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
 // ------------------------------------------------------------------------------------------
 // first layer: normalise + pad + Conv2d(1,C,3,p=1) + act + BN(eval), CUDA cores (K = 9)
 // ------------------------------------------------------------------------------------------
+// Block = 32x8 output pixels.  The normalised (and padded) input patch incl. its 1-pixel halo is staged
+// once in shared memory (one IEEE division per input pixel instead of nine per output channel group);
+// thread (g, px) keeps the 72 weights of its 8 output channels in registers and walks 8 rows, so the
+// only smem traffic in the inner loop is the 9 input taps; a warp stores 4 pixels x 128 B contiguously.
+constexpr int FC_TW = 32, FC_TH = 8;
 template <typename T>
-__global__ void first_conv_kernel(const T *__restrict__ img, int H, int W, int pad_y, int pad_x, float lo, float hi,
-                                  const float *__restrict__ lohi_dev, const float *__restrict__ weight, const float *__restrict__ bias,
-                                  const float *__restrict__ scale, const float *__restrict__ shift, int C, int act,
-                                  __nv_bfloat16 *__restrict__ out, int ld, int coff) {
-    extern __shared__ float s_w[];  // [C*9] weights, [C] bias, [C] scale, [C] shift
+__global__ void __launch_bounds__(256)
+first_conv_kernel(const T *__restrict__ img, int H, int W, int pad_y, int pad_x, float lo, float hi,
+                  const float *__restrict__ lohi_dev, const float *__restrict__ weight, const float *__restrict__ bias,
+                  const float *__restrict__ scale, const float *__restrict__ shift, int C, int act,
+                  __nv_bfloat16 *__restrict__ out, int ld, int coff) {
+    __shared__ float s_in[FC_TH + 2][FC_TW + 2];
     if (lohi_dev) {                 // frame min / max computed on the device (mbs_frame_minmax)
         lo = lohi_dev[0];
         hi = lohi_dev[1];
     }
-    for (int i = threadIdx.x; i < C * 9; i += blockDim.x) s_w[i] = weight[i];
-    for (int i = threadIdx.x; i < C; i += blockDim.x) {
-        s_w[C * 9 + i] = bias[i];
-        s_w[C * 10 + i] = scale[i];
-        s_w[C * 11 + i] = shift[i];
-    }
-    __syncthreads();
     const int Hp = H + pad_y, Wp = W + pad_x;
-    const int groups = C / 8;
-    const long long gid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-    const long long pix = gid / groups;
-    const int cg = static_cast<int>(gid - pix * groups);
-    if (pix >= static_cast<long long>(Hp) * Wp) return;
-    const int Y = static_cast<int>(pix / Wp), X = static_cast<int>(pix - static_cast<long long>(Y) * Wp);
+    const int x0 = blockIdx.x * FC_TW, y0 = blockIdx.y * FC_TH;
     const float range = hi - lo;
-    float in[9];
-#pragma unroll
-    for (int t = 0; t < 9; ++t) {
-        const int yy = Y + t / 3 - 1, xx = X + t % 3 - 1;
+    for (int i = threadIdx.x; i < (FC_TH + 2) * (FC_TW + 2); i += 256) {
+        const int r = i / (FC_TW + 2), c = i - r * (FC_TW + 2);
+        const int yy = y0 + r - 1, xx = x0 + c - 1;
         float v = 0.0f;  // conv zero padding outside the (padded) model input
         if (yy >= 0 && yy < Hp && xx >= 0 && xx < Wp) {
             float raw = lo;  // zero_pad_model_input pad value = frame min (utils.py:124, infer.py:256)
             if (yy >= pad_y && xx >= pad_x) raw = static_cast<float>(img[static_cast<size_t>(yy - pad_y) * W + (xx - pad_x)]);
-            // 2 * (f32(img) - min) / (max - min) - 1, evaluated left to right in f32 (infer.py:346)
+            // 2 * (f32(img) - min) / (max - min) - 1, evaluated left to right in f32 (infer.py:346);
             // hi < lo: the caller already normalised the image (drop-in net(x) path) -> pass through
             v = hi < lo ? raw : __fsub_rn(__fdiv_rn(__fmul_rn(2.0f, __fsub_rn(raw, lo)), range), 1.0f);
         }
-        in[t] = v;
+        s_in[r][c] = v;
     }
-    uint32_t packed[4];
+    const int g = threadIdx.x & 7;           // channel group (8 channels) inside a 64-channel slab
+    const int px = threadIdx.x >> 3;         // pixel column inside the tile
+    __syncthreads();
+    for (int cbase = 0; cbase < C; cbase += 64) {
+        const int c0 = cbase + g * 8;
+        if (c0 >= C) break;
+        float w[8][9], b8[8], sc8[8], sh8[8];
 #pragma unroll
-    for (int j = 0; j < 8; j += 2) {
-        float o[2];
+        for (int u = 0; u < 8; ++u) {
 #pragma unroll
-        for (int u = 0; u < 2; ++u) {
-            const int c = cg * 8 + j + u;
-            float acc = 0.0f;
-#pragma unroll
-            for (int t = 0; t < 9; ++t) acc = fmaf(in[t], s_w[c * 9 + t], acc);
-            acc += s_w[C * 9 + c];
-            acc = apply_act(acc, act);
-            o[u] = fmaf(acc, s_w[C * 10 + c], s_w[C * 11 + c]);
+            for (int t = 0; t < 9; ++t) w[u][t] = weight[(c0 + u) * 9 + t];
+            b8[u] = bias[c0 + u];
+            sc8[u] = scale[c0 + u];
+            sh8[u] = shift[c0 + u];
         }
-        __nv_bfloat162 h = __floats2bfloat162_rn(o[0], o[1]);
-        packed[j >> 1] = *reinterpret_cast<uint32_t *>(&h);
+        const int X = x0 + px;
+#pragma unroll 2
+        for (int r = 0; r < FC_TH; ++r) {
+            const int Y = y0 + r;
+            float in[9];
+#pragma unroll
+            for (int t = 0; t < 9; ++t) in[t] = s_in[r + t / 3][px + t % 3];
+            float acc[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                float a = 0.0f;
+#pragma unroll
+                for (int t = 0; t < 9; ++t) a = fmaf(in[t], w[u][t], a);
+                acc[u] = a + b8[u];
+            }
+            switch (act) {      // one uniform branch per row, not per element
+                case MBS_ACT_RELU:
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) acc[u] = fmaxf(acc[u], 0.0f);
+                    break;
+                case MBS_ACT_NONE: break;
+                default:
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) acc[u] = apply_act(acc[u], act);
+                    break;
+            }
+            uint32_t packed[4];
+#pragma unroll
+            for (int u = 0; u < 8; u += 2) {
+                __nv_bfloat162 h2 = __floats2bfloat162_rn(fmaf(acc[u], sc8[u], sh8[u]), fmaf(acc[u + 1], sc8[u + 1], sh8[u + 1]));
+                packed[u >> 1] = *reinterpret_cast<uint32_t *>(&h2);
+            }
+            if (Y < Hp && X < Wp) {
+                uint4 *d = reinterpret_cast<uint4 *>(out + (static_cast<size_t>(Y) * Wp + X) * ld + coff + c0);
+                *d = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+            }
+        }
     }
-    uint4 *d = reinterpret_cast<uint4 *>(out + static_cast<size_t>(pix) * ld + coff + cg * 8);
-    *d = make_uint4(packed[0], packed[1], packed[2], packed[3]);
 }
 
 // frame min / max (np.min / np.max of the raw frame, infer_script_local.py:124) as ordered uint keys
@@ -1007,25 +1034,23 @@ extern "C" int mbs_first_conv(const void *img, int in_dtype, int H, int W, int p
     MBS_REQUIRE(((reinterpret_cast<uintptr_t>(out) + static_cast<size_t>(out_coff) * 2) & 15) == 0 &&
                     (out_ld * 2) % 16 == 0,
                 "first conv: destination view must be 16-byte aligned");
-    const long long total = static_cast<long long>(H + pad_y) * (W + pad_x) * (C / 8);
+    const dim3 fgrid(mbs::cdiv(W + pad_x, FC_TW), mbs::cdiv(H + pad_y, FC_TH));
     const int threads = 256;
-    const long long blocks = (total + threads - 1) / threads;
-    MBS_REQUIRE(blocks < (1ll << 31), "first conv: grid too large");
-    const size_t smem = static_cast<size_t>(C) * 12 * sizeof(float);
+    const size_t smem = 0;
     __nv_bfloat16 *o = static_cast<__nv_bfloat16 *>(out);
     switch (in_dtype) {
         case MBS_IN_U8:
-            first_conv_kernel<uint8_t><<<static_cast<int>(blocks), threads, smem, stream>>>(
+            first_conv_kernel<uint8_t><<<fgrid, threads, smem, stream>>>(
                 static_cast<const uint8_t *>(img), H, W, pad_y, pad_x, norm_lo, norm_hi, lohi_dev, weight, bias, scale, shift, C,
                 act, o, out_ld, out_coff);
             break;
         case MBS_IN_U16:
-            first_conv_kernel<uint16_t><<<static_cast<int>(blocks), threads, smem, stream>>>(
+            first_conv_kernel<uint16_t><<<fgrid, threads, smem, stream>>>(
                 static_cast<const uint16_t *>(img), H, W, pad_y, pad_x, norm_lo, norm_hi, lohi_dev, weight, bias, scale, shift, C,
                 act, o, out_ld, out_coff);
             break;
         case MBS_IN_F32:
-            first_conv_kernel<float><<<static_cast<int>(blocks), threads, smem, stream>>>(
+            first_conv_kernel<float><<<fgrid, threads, smem, stream>>>(
                 static_cast<const float *>(img), H, W, pad_y, pad_x, norm_lo, norm_hi, lohi_dev, weight, bias, scale, shift, C,
                 act, o, out_ld, out_coff);
             break;
