@@ -80,8 +80,13 @@ def cpu_reference_sample(size=1024, seed=1234, threads=None):
     from oracle import net as onet
     from oracle import postproc as op
     from microbeseg_b200 import synthetic as sy
-    if threads:
-        torch.set_num_threads(threads)
+    # all host cores the process may use (torchrun exports OMP_NUM_THREADS=1, which would throttle the reference)
+    if threads is None:
+        try:
+            threads = len(os.sched_getaffinity(0))
+        except AttributeError:
+            threads = os.cpu_count() or 1
+    torch.set_num_threads(max(1, threads))
     torch.set_grad_enabled(False)
     torch.manual_seed(0)
     sd = onet.seeded_state_dict(onet.reference_layout_template("DU", (64, 1024)), 0)
