@@ -122,6 +122,54 @@ class FrameSegmenter:
         return self.result(self.submit(frame, 0, min_val, max_val, crop))
 
 
+TILE_HALO = 128      # >= the network's 116-px receptive-field reach, multiple of 16
+
+
+def predict_maps_tiled(net, frame_dev, lo, hi, tile=1024, halo=TILE_HALO):
+    """Overlap-tiled network inference that is bit-identical to whole-frame inference.
+
+    The reference only has whole-frame inference (its ``sliding_window`` flag is a stub,
+    src/inference/infer.py:60,76) and refuses frames above 8192 px (src/utils/utils.py:154-155).
+    Tiles have 16-aligned origins and a ``halo``-pixel apron: every kept output pixel sees exactly the
+    inputs it sees in the whole frame (true zero padding only at real image borders), so stitching the
+    tile cores reproduces the whole-frame maps bit for bit.  ``frame_dev``: raw (H,W) CUDA frame whose
+    sides are multiples of 16 (already padded); returns (border, cell) float32 (H,W)."""
+    H, W = frame_dev.shape
+    if H % 16 or W % 16 or tile % 16 or halo % 16:
+        raise RuntimeError("tiled inference needs frame sides, tile and halo to be multiples of 16")
+    border = torch.empty((H, W), dtype=torch.float32, device=frame_dev.device)
+    cell = torch.empty((H, W), dtype=torch.float32, device=frame_dev.device)
+    for y0 in range(0, H, tile):
+        for x0 in range(0, W, tile):
+            y1, x1 = min(y0 + tile, H), min(x0 + tile, W)
+            wy0, wy1 = max(y0 - halo, 0), min(y1 + halo, H)
+            wx0, wx1 = max(x0 - halo, 0), min(x1 + halo, W)
+            win = frame_dev[wy0:wy1, wx0:wx1].contiguous()
+            b, c = net.forward_frame(win, [0, 0], float(lo), float(hi))
+            border[y0:y1, x0:x1] = b[0, 0, y0 - wy0:y1 - wy0, x0 - wx0:x1 - wx0]
+            cell[y0:y1, x0:x1] = c[0, 0, y0 - wy0:y1 - wy0, x0 - wx0:x1 - wx0]
+    return border, cell
+
+
+def segment_frame_tiled(net, frame, ths=(0.10, 0.45), tile=1024, device=None):
+    """Whole path for one large frame with overlap-tiled inference: min/max -> top/left padding with the
+    frame minimum -> tiled network -> crop -> distance post-processing."""
+    device = torch.device(device) if device is not None else next(net.parameters()).device
+    frame = FrameSegmenter._canon(frame)
+    H, W = frame.shape
+    lo, hi = frame.min(), frame.max()
+    pads = model_input_pads(H, W)
+    # same top/left padding as the reference while the frame fits its table (<= 8192); beyond it the
+    # reference raises ("Use sliding windows"), here the frame is padded to the next multiple of 16
+    py, px = (pads[0], pads[1]) if len(pads) == 2 else ((-H) % 16, (-W) % 16)
+    padded = np.pad(frame, ((py, 0), (px, 0)), mode="constant", constant_values=lo)
+    dev = torch.from_numpy(padded.view(np.int16) if padded.dtype == np.uint16 else padded).to(device)
+    with torch.cuda.device(device):
+        border, cell = predict_maps_tiled(net, dev, lo, hi, tile)
+        out = pp.distance_postprocessing_device(border[py:, px:], cell[py:, px:], float(ths[1]), float(ths[0]))
+    return out.cpu().numpy().view(np.uint16)
+
+
 def segment_stack(net, stack, ths=(0.10, 0.45), device=None, frames=None, out=None):
     """[T,H,W] stack -> [T,H,W] uint16 masks (infer_script_local.py:115-161).  ``frames`` selects the
     frame indices to process (frame sharding); other rows of ``out`` are left untouched."""

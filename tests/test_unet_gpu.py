@@ -220,3 +220,27 @@ def test_infer_worker_style_call_with_caller_padding(native_lib):
     padded, pads = zero_pad_model_input(img, pad_val=img.min())
     via_pads = seg.segment(padded, img.min(), img.max(), crop=pads)
     assert via_pads.shape == img.shape and np.array_equal(direct, via_pads)
+
+
+def test_tiled_inference_is_bit_identical_to_whole_frame(native_lib):
+    """Overlap tiling (north_star "overlapping-tile stitching"; new capability, the reference has a stub):
+    16-aligned tiles with a 128-px apron reproduce whole-frame inference exactly."""
+    from microbeseg_b200 import synthetic as sy
+    from microbeseg_b200.inference import predict_maps_tiled, segment_frame_tiled, FrameSegmenter
+    torch.set_grad_enabled(False)
+    net, _ = _build((64, 1024), "relu", 71)
+    img = sy.synth_frame(384, 512, 21)
+    dev = torch.from_numpy(img.view(np.int16)).cuda()
+    lo, hi = float(img.min()), float(img.max())
+    b0, c0 = net.forward_frame(dev, [0, 0], lo, hi)
+    b1, c1 = predict_maps_tiled(net, dev, lo, hi, tile=128)
+    assert torch.equal(b0[0, 0], b1) and torch.equal(c0[0, 0], c1)
+    b2, c2 = predict_maps_tiled(net, dev, lo, hi, tile=256, halo=112)
+    assert torch.equal(b0[0, 0], b2) and torch.equal(c0[0, 0], c2)
+    b3, _ = predict_maps_tiled(net, dev, lo, hi, tile=128, halo=64)      # too small an apron must differ
+    assert not torch.equal(b0[0, 0], b3)
+    # full path on a frame whose sides are not multiples of 16
+    odd = img[:300, :410]
+    whole = FrameSegmenter(net, (0.10, 0.45)).segment(odd)
+    tiled = segment_frame_tiled(net, odd, tile=128)
+    assert tiled.shape == odd.shape and np.array_equal(whole, tiled)
