@@ -88,8 +88,9 @@ typedef struct {
     int act;
     /* destination NHWC bf16 view (may be NULL when only the head output is wanted) */
     void *dst; int ldd, coffd;
-    /* optional fused 1x1 head (requires Cout == 64): head_out[n][y][x] = sum_c y_c*head_w[c] + head_b */
-    const float *head_w; float head_b; float *head_out;
+    /* optional fused 1x1 head(s) (requires Cout == 64, head_n <= 4):
+     * head_out[n][h][y][x] = sum_c y_c * head_w[h][c] + head_b[h]   (Conv2d(64, ch_out, 1), unets.py:347,460-461) */
+    const float *head_w; float head_b[4]; int head_n; float *head_out;
 } mbs_conv_desc;
 
 int mbs_conv_gemm(const mbs_conv_desc *d, void *stream);
@@ -110,6 +111,12 @@ size_t mbs_postproc_workspace_bytes(int H, int W);
  */
 int mbs_distance_postprocessing(const float *border, const float *cell, int H, int W, int ld,
                                 float th_seed, float th_cell, uint16_t *out, void *workspace,
+                                size_t workspace_bytes, int64_t *info_host, void *stream);
+
+/* boundary method (replaces src/inference/postprocessing.py:62-90): prediction = softmax probabilities
+ * (H,W,3) float32, channel-last as the reference passes them; the flood image is flat, so the result is
+ * pure FIFO order and is produced by the exact sequential flood whenever two markers share a mask region. */
+int mbs_boundary_postprocessing(const float *prediction_hwc, int H, int W, uint16_t *out, void *workspace,
                                 size_t workspace_bytes, int64_t *info_host, void *stream);
 
 /* individual stages, exposed for stage-level parity tests */

@@ -22,7 +22,7 @@ class ConvDesc(ctypes.Structure):
                 ("weight", c_void_p), ("Cout", c_int),
                 ("bias", c_void_p), ("scale", c_void_p), ("shift", c_void_p), ("act", c_int),
                 ("dst", c_void_p), ("ldd", c_int), ("coffd", c_int),
-                ("head_w", c_void_p), ("head_b", c_float), ("head_out", c_void_p)]
+                ("head_w", c_void_p), ("head_b", c_float * 4), ("head_n", c_int), ("head_out", c_void_p)]
 
 
 _SIGS = {
@@ -39,6 +39,7 @@ _SIGS = {
     "mbs_postproc_workspace_bytes": (c_size_t, [c_int, c_int]),
     "mbs_distance_postprocessing": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_float, c_void_p,
                                             c_void_p, c_size_t, c_void_p, c_void_p]),
+    "mbs_boundary_postprocessing": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_size_t, c_void_p, c_void_p]),
     "mbs_pp_front": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_float, c_void_p, c_void_p, c_void_p,
                              c_void_p]),
     "mbs_pp_label8": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),

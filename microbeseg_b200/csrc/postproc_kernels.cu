@@ -96,6 +96,23 @@ pp_front_kernel(const float *__restrict__ border, const float *__restrict__ cell
     }
 }
 
+// boundary_postprocessing front end (postprocessing.py:71-77): argmax over the 3 classes (first maximum wins,
+// as np.argmax), mask = class 1, seeds = p1 * (1 - p2) > 0.5; the flood image is the mask itself.
+__global__ void bp_front_kernel(const float *__restrict__ pred, int n, float *__restrict__ img, uint8_t *__restrict__ mask,
+                                uint8_t *__restrict__ seed) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float p0 = pred[3 * i], p1 = pred[3 * i + 1], p2 = pred[3 * i + 2];
+    int am = 0;
+    float best = p0;
+    if (p1 > best) { best = p1; am = 1; }
+    if (p2 > best) { am = 2; }
+    const bool m = am == 1;
+    mask[i] = m;
+    img[i] = m ? 1.0f : 0.0f;
+    seed[i] = __fmul_rn(p1, __fsub_rn(1.0f, p2)) > 0.5f;
+}
+
 // ------------------------------------------------------------------------------------------
 // union-find (root = minimum linear index = first pixel in raster order)
 // ------------------------------------------------------------------------------------------
@@ -853,6 +870,58 @@ extern "C" int mbs_distance_postprocessing(const float *border, const float *cel
     MBS_CHECK_LAUNCH();
     rc = run_watershed(cell_s, /*negate=*/1, markers, mask, H, W, lab, Lv, parent, uf, src, heap, st, tile_changed, 0,
                        stream);
+    if (rc) return rc;
+    to_u16_kernel<<<nb, 256, 0, stream>>>(lab, nn, out);
+    MBS_CHECK_LAUNCH();
+    if (info_host) {
+        MBS_CHECK_CUDA(cudaMemcpyAsync(hp, st, sizeof(Stats), cudaMemcpyDeviceToHost, stream));
+        MBS_CHECK_CUDA(cudaStreamSynchronize(stream));
+        memset(info_host, 0, 8 * sizeof(int64_t));
+        info_host[0] = hp->n_comp;
+        info_host[1] = hp->n_markers;
+        info_host[2] = hp->sweeps;
+        info_host[3] = hp->ambiguous ? 1 : 0;
+        info_host[4] = hp->ambiguous;
+    }
+    return 0;
+}
+
+extern "C" int mbs_boundary_postprocessing(const float *prediction_hwc, int H, int W, uint16_t *out, void *workspace,
+                                           size_t workspace_bytes, int64_t *info_host, void *stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    const size_t n = static_cast<size_t>(H) * W;
+    MBS_REQUIRE(H > 0 && W > 0 && n < (1ull << 31), "boundary_postprocessing: bad shape H=%d W=%d", H, W);
+    MBS_REQUIRE(workspace_bytes >= mbs_postproc_workspace_bytes(H, W), "boundary_postprocessing: workspace too small");
+    Carver cv{static_cast<char *>(workspace), workspace_bytes};
+    Stats *st = cv.take<Stats>(1);
+    float *img = cv.take<float>(n);
+    uint8_t *mask = cv.take<uint8_t>(n);
+    uint8_t *seed = cv.take<uint8_t>(n);
+    int *roots = cv.take<int>(n);
+    int *area = cv.take<int>(n);
+    int *rank = cv.take<int>(n);
+    int *tiles = cv.take<int>((n + SCAN_TILE - 1) / SCAN_TILE);
+    int *markers = cv.take<int>(n);
+    float *Lv = cv.take<float>(n);
+    int *parent = cv.take<int>(n);
+    int *uf = cv.take<int>(n);
+    int *src = cv.take<int>(n);
+    int *lab = cv.take<int>(n);
+    HeapItem *heap = cv.take<HeapItem>(n);
+    uint8_t *tile_changed = cv.take<uint8_t>(n / 64 + 4096);
+    MBS_REQUIRE(cv.ok, "boundary_postprocessing: workspace carve failed");
+    Stats *hp = pinned_stats();
+    MBS_REQUIRE(hp != nullptr, "boundary_postprocessing: cannot allocate pinned host memory");
+    const int nn = static_cast<int>(n);
+    const int nb = mbs::cdiv(nn, 256);
+    MBS_CHECK_CUDA(cudaMemsetAsync(st, 0, sizeof(Stats), stream));
+    bp_front_kernel<<<nb, 256, 0, stream>>>(prediction_hwc, nn, img, mask, seed);
+    MBS_CHECK_LAUNCH();
+    int rc = run_label_rank(seed, H, W, roots, area, rank, tiles, st, /*use_mean=*/0, 1, stream);   // drop area <= 4
+    if (rc) return rc;
+    markers_kernel<<<nb, 256, 0, stream>>>(roots, rank, mask, nn, markers);
+    MBS_CHECK_LAUNCH();
+    rc = run_watershed(img, /*negate=*/0, markers, mask, H, W, lab, Lv, parent, uf, src, heap, st, tile_changed, 0, stream);
     if (rc) return rc;
     to_u16_kernel<<<nb, 256, 0, stream>>>(lab, nn, out);
     MBS_CHECK_LAUNCH();

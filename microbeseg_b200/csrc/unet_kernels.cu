@@ -48,9 +48,10 @@ struct ConvKParams {
     const float *bias, *scale, *shift;
     __nv_bfloat16 *dst;
     int ldd, coffd, Hd, Wd;   // destination view
-    const float *head_w;
-    float head_b;
-    float *head_out;
+    const float *head_w;      // [head_n][Cout]
+    float head_b[4];
+    int head_n;               // number of fused 1x1 head outputs (<= 4)
+    float *head_out;          // [N][head_n][H][W]
 };
 
 // ------------------------------------------------------------------------------------------
@@ -196,7 +197,7 @@ __device__ __forceinline__ void epilogue_tile(const ConvKParams &p, const float 
     const int row = quad * 32 + lane;
     mbar_wait(tfull, (lt >> 1) & 1);
     tcgen05_fence_after();
-    float head_acc = 0.0f;
+    float head_acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
 #pragma unroll 1
     for (int c = half * (BN / 2); c < (half + 1) * (BN / 2); c += 32) {
         uint32_t r[32];
@@ -247,15 +248,20 @@ __device__ __forceinline__ void epilogue_tile(const ConvKParams &p, const float 
             v[4 * j + 2] = fmaf(v[4 * j + 2], s4.z, t4.z);
             v[4 * j + 3] = fmaf(v[4 * j + 3], s4.w, t4.w);
         }
-        if (has_head) {
-            const float4 *phw = reinterpret_cast<const float4 *>(s_par + 3 * p.Cout + co);
+        if (BN == 64 && has_head) {   // heads need Cout == 64, i.e. only the BN == 64 instantiations carry this code
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const float4 w4 = phw[j];
-                head_acc = fmaf(v[4 * j + 0], w4.x, head_acc);
-                head_acc = fmaf(v[4 * j + 1], w4.y, head_acc);
-                head_acc = fmaf(v[4 * j + 2], w4.z, head_acc);
-                head_acc = fmaf(v[4 * j + 3], w4.w, head_acc);
+            for (int h = 0; h < 4; ++h) {
+                if (h < p.head_n) {
+                    const float4 *phw = reinterpret_cast<const float4 *>(s_par + (3 + h) * p.Cout + co);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const float4 w4 = phw[j];
+                        head_acc[h] = fmaf(v[4 * j + 0], w4.x, head_acc[h]);
+                        head_acc[h] = fmaf(v[4 * j + 1], w4.y, head_acc[h]);
+                        head_acc[h] = fmaf(v[4 * j + 2], w4.z, head_acc[h]);
+                        head_acc[h] = fmaf(v[4 * j + 3], w4.w, head_acc[h]);
+                    }
+                }
             }
         }
         if (p.dst) {
@@ -311,15 +317,24 @@ __device__ __forceinline__ void epilogue_tile(const ConvKParams &p, const float 
     if (lane == 0) {
         asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tempty) : "memory");
     }
-    if (has_head) {
+    if (BN == 64 && has_head) {
         // the two column-half warps of a quadrant combine their partial dot products through smem
-        float *slot = s_head + (lt & 1) * 128 + row;
-        if (half == 1) *slot = head_acc;
+        float *slot = s_head + (lt & 1) * 512 + row;
+        if (half == 1) {
+#pragma unroll
+            for (int h = 0; h < 4; ++h)
+                if (h < p.head_n) slot[h * 128] = head_acc[h];
+        }
         asm volatile("bar.sync %0, 64;" ::"r"(1 + quad) : "memory");
         if (half == 0) {
             const int py = y0 + row / TW, px = x0 + row % TW;
-            if (py < p.Hm && px < p.Wm)
-                p.head_out[(static_cast<size_t>(img) * p.Hm + py) * p.Wm + px] = (head_acc + *slot) + p.head_b;
+            if (py < p.Hm && px < p.Wm) {
+#pragma unroll
+                for (int h = 0; h < 4; ++h)
+                    if (h < p.head_n)
+                        p.head_out[((static_cast<size_t>(img) * p.head_n + h) * p.Hm + py) * p.Wm + px] =
+                            (head_acc[h] + slot[h * 128]) + p.head_b[h];
+            }
         }
     }
 }
@@ -327,7 +342,7 @@ __device__ __forceinline__ void epilogue_tile(const ConvKParams &p, const float 
 template <int BN, int STAGES>
 struct SmemPlan {
     static constexpr int B_BYTES = BN * BK * 2;
-    static constexpr int EPI_BYTES = EPI_WARPS * 1024 + 2 * 128 * 4;   // per warp 32 rows x 16 bf16; + head partials
+    static constexpr int EPI_BYTES = EPI_WARPS * 1024 + 2 * 4 * 128 * 4;   // per warp 32 rows x 16 bf16; + head partials
     static constexpr int OFF_A = 0;
     static constexpr int OFF_B = STAGES * A_BYTES;
     static constexpr int OFF_EPI = OFF_B + STAGES * B_BYTES;
@@ -335,7 +350,7 @@ struct SmemPlan {
     static constexpr int OFF_TMEM = OFF_BAR + 8 * (2 * STAGES + 4);
     static constexpr int OFF_PAR = (OFF_TMEM + 8 + 15) / 16 * 16;  // bias/scale/shift/head_w, [4][Cout] floats (float4 reads)
     static constexpr int FIXED = OFF_PAR + 1024;                  // + slack for the manual 1024-B alignment
-    static int dyn_bytes(int cout) { return FIXED + 4 * cout * 4; }
+    static int dyn_bytes(int cout) { return FIXED + (3 * cout + (cout == 64 ? 4 * 64 : 0)) * 4; }   // heads only with Cout == 64
 };
 
 // Persistent, warp-specialised implicit-GEMM kernel.  Each CTA walks tiles t = blockIdx.x, +gridDim.x, ...
@@ -386,7 +401,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
             s_par[j] = p.bias[j];
             s_par[p.Cout + j] = p.scale[j];
             s_par[2 * p.Cout + j] = p.shift[j];
-            s_par[3 * p.Cout + j] = p.head_w ? p.head_w[j] : 0.0f;
+            for (int h = 0; h < p.head_n; ++h) s_par[(3 + h) * p.Cout + j] = p.head_w[h * p.Cout + j];
         }
     }
     tcgen05_fence_before();
@@ -514,11 +529,11 @@ struct HaloPlan {
     static constexpr int OFF_W = 0;
     static constexpr int OFF_A = 9 * CHUNKS * W_TILE_BYTES;
     static constexpr int OFF_EPI = OFF_A + STAGES * HALO_SLOT;
-    static constexpr int EPI_BYTES = EPI_WARPS * 1024 + 2 * 128 * 4;
+    static constexpr int EPI_BYTES = EPI_WARPS * 1024 + 2 * 4 * 128 * 4;
     static constexpr int OFF_BAR = OFF_EPI + EPI_BYTES;        // full[S], empty[S], tfull[2], tempty[2], wbar
     static constexpr int OFF_TMEM = OFF_BAR + 8 * (2 * STAGES + 5);
     static constexpr int OFF_PAR = (OFF_TMEM + 8 + 15) / 16 * 16;
-    static constexpr int DYN_BYTES = OFF_PAR + 4 * 64 * 4 + 1024;
+    static constexpr int DYN_BYTES = OFF_PAR + 7 * 64 * 4 + 1024;
 };
 
 __device__ __forceinline__ uint64_t make_sw128_desc_sbo(uint32_t saddr, uint32_t sbo_bytes) {
@@ -577,7 +592,7 @@ conv_halo64_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
             s_par[j] = p.bias[j];
             s_par[64 + j] = p.scale[j];
             s_par[128 + j] = p.shift[j];
-            s_par[192 + j] = p.head_w ? p.head_w[j] : 0.0f;
+            for (int h = 0; h < p.head_n; ++h) s_par[(3 + h) * 64 + j] = p.head_w[h * 64 + j];
         }
     }
     tcgen05_fence_before();
@@ -940,8 +955,9 @@ extern "C" int mbs_conv_gemm(const mbs_conv_desc *d, void *stream_) {
     MBS_REQUIRE(d->Cout > 0 && d->Cout % 64 == 0, "Cout must be a multiple of 64 (got %d)", d->Cout);
     MBS_REQUIRE(d->mode != MBS_CONVT2X2_S2 || d->C1 == 0, "transposed conv takes a single source");
     MBS_REQUIRE(d->mode != MBS_CONV3X3_S2 || (d->H % 2 == 0 && d->W % 2 == 0), "stride-2 conv needs even H, W");
-    MBS_REQUIRE(d->head_out == nullptr || (d->Cout == 64 && d->mode == MBS_CONV3X3_S1 && d->head_w),
-                "fused head needs Cout == 64, stride-1 conv and head weights");
+    MBS_REQUIRE(d->head_out == nullptr ||
+                    (d->Cout == 64 && d->mode == MBS_CONV3X3_S1 && d->head_w && d->head_n >= 1 && d->head_n <= 4),
+                "fused head needs Cout == 64, stride-1 conv, head weights and 1 <= head_n <= 4");
     MBS_REQUIRE(d->dst != nullptr || d->head_out != nullptr, "no output requested");
     if (d->dst) {
         MBS_REQUIRE(((reinterpret_cast<uintptr_t>(d->dst) + static_cast<size_t>(d->coffd) * 2) & 15) == 0 &&
@@ -971,7 +987,8 @@ extern "C" int mbs_conv_gemm(const mbs_conv_desc *d, void *stream_) {
     kp.Hd = d->mode == MBS_CONVT2X2_S2 ? 2 * d->H : kp.Hm;
     kp.Wd = d->mode == MBS_CONVT2X2_S2 ? 2 * d->W : kp.Wm;
     kp.head_w = d->head_out ? d->head_w : nullptr;
-    kp.head_b = d->head_b;
+    kp.head_n = d->head_out ? d->head_n : 0;
+    for (int h = 0; h < 4; ++h) kp.head_b[h] = d->head_b[h];
     kp.head_out = d->head_out;
 
     if (halo_enabled() && d->mode == MBS_CONV3X3_S1 && d->Cout == 64 && d->C0 == 64 && (d->C1 == 0 || d->C1 == 64)) {

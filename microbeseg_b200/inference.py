@@ -79,26 +79,34 @@ class FrameSegmenter:
                 st["ev_h2d"].record(self.h2d_stream)
             main.wait_event(st["ev_h2d"])
             main.wait_event(st["ev_out"])                          # read-back of this slot's previous mask is done
+            distance = len(getattr(self.net, "decoder_names", ())) == 2      # DU net = distance method, U net = boundary
             try:
                 if min_val is None or max_val is None:
                     # frame min / max before padding (infer_script_local.py:124), reduced on the device
                     lohi = frame_minmax(st["dev_in"], out=st["lohi"], scratch=st["scratch"])
-                    border, cell = self.net.forward_frame(st["dev_in"], pads, lohi_dev=lohi)
+                    maps = self.net.forward_frame(st["dev_in"], pads, lohi_dev=lohi)
                 else:
-                    border, cell = self.net.forward_frame(st["dev_in"], pads, float(min_val), float(max_val))
+                    maps = self.net.forward_frame(st["dev_in"], pads, float(min_val), float(max_val))
             except RuntimeError:
                 # same contract as infer.py:352-356: a RuntimeError during net() yields an empty mask
                 st["dev_out"].zero_()
                 st["view"] = (cy, cx) if (cy, cx) != (0, 0) else None
                 print('RuntimeError during inference (maybe not enough ram/vram?)')
             else:
-                b = border[0, 0, pads[0] + cy:, pads[1] + cx:]      # crop the pads (infer.py:358-359)
-                c = cell[0, 0, pads[0] + cy:, pads[1] + cx:]
+                if distance:
+                    border, cell = maps
+                    b = border[0, 0, pads[0] + cy:, pads[1] + cx:]      # crop the pads (infer.py:358-359)
+                    c = cell[0, 0, pads[0] + cy:, pads[1] + cx:]
+                    run = lambda dst: pp.distance_postprocessing_device(b, c, self.th_seed, self.th_cell, out=dst)
+                else:
+                    # boundary method: softmax over the 3 classes, channel-last crop (infer.py:371-374)
+                    prob = torch.softmax(maps, dim=1)[0, :, pads[0] + cy:, pads[1] + cx:].permute(1, 2, 0)
+                    run = lambda dst: pp.boundary_postprocessing_device(prob, out=dst)
                 if (cy, cx) == (0, 0):
-                    pp.distance_postprocessing_device(b, c, self.th_seed, self.th_cell, out=st["dev_out"])
+                    run(st["dev_out"])
                     st["view"] = None
                 else:
-                    small = pp.distance_postprocessing_device(b, c, self.th_seed, self.th_cell)
+                    small = run(None)
                     st["dev_out"].zero_()
                     st["dev_out"][cy:, cx:] = small
                     st["view"] = (cy, cx)
@@ -218,8 +226,6 @@ class InferWorker:
 
     def inference(self, img, min_val, max_val, pads):
         """``img`` is the already padded frame (infer.py:256-259); returns the uint16 mask without pads."""
-        if self.model_settings['label_type'] != 'distance':
-            raise NotImplementedError("boundary models are not built yet")
         torch.set_grad_enabled(False)
         if self._seg is None:
             self._seg = FrameSegmenter(self.net, self.ths, self.device)

@@ -92,3 +92,34 @@ def distance_postprocessing(border_prediction, cell_prediction, th_seed, th_cell
     out = distance_postprocessing_device(border, cell, th_seed, th_cell)
     # np.squeeze as in postprocessing.py:59 (a 1xW frame comes back 1-D, exactly like the reference)
     return np.squeeze(out.cpu().numpy().view(np.uint16))
+
+
+def boundary_postprocessing_device(pred, out=None):
+    """(H,W,3) float32 CUDA probabilities -> uint16-as-int16 CUDA mask (H,W)."""
+    if pred.dim() != 3 or pred.shape[-1] != 3:
+        raise ValueError(f"expected (H,W,3) class probabilities, got {tuple(pred.shape)}")
+    pred = pred.contiguous()
+    L = nat.lib()
+    H, W = pred.shape[:2]
+    device = pred.device
+    if out is None:
+        out = torch.empty((H, W), dtype=torch.int16, device=device)
+    ws = _workspace(device, L.mbs_postproc_workspace_bytes(H, W))
+    with torch.cuda.device(device):
+        rc = L.mbs_boundary_postprocessing(pred.data_ptr(), H, W, out.data_ptr(), ws.data_ptr(), ws.numel(), None,
+                                           nat.stream_ptr())
+    nat.check(rc, "boundary_postprocessing")
+    return out
+
+
+def boundary_postprocessing(prediction):
+    """Post-processing for boundary label prediction -> uint16 instance mask (postprocessing.py:62-90).
+
+    ``prediction``: (H,W,3) softmax probabilities (NumPy or CUDA tensor), channel-last as in the reference."""
+    device = _device_of(prediction)
+    if isinstance(prediction, torch.Tensor):
+        pred = prediction.to(device=device, dtype=torch.float32)
+    else:
+        pred = torch.from_numpy(np.ascontiguousarray(prediction, dtype=np.float32)).to(device)
+    out = boundary_postprocessing_device(pred)
+    return np.squeeze(out.cpu().numpy().view(np.uint16))

@@ -147,6 +147,15 @@ class _NetBase(nn.Module):
         n, _, h, w = x.shape
         return self.engine().run(x.reshape(n, h, w).contiguous().float(), 0, 0, 1.0, 0.0)  # hi < lo: pass through
 
+    def _forward_frame_maps(self, img, pads, lo, hi, lohi_dev):
+        """Fused entry used by the frame loop: raw (H,W) uint8/uint16/float32 CUDA frame -> head maps of the
+        padded size; normalisation ``2*(x-lo)/(hi-lo)-1`` and top/left padding with ``lo`` happen inside the
+        first kernel.  ``lohi_dev`` (float32[2] CUDA tensor from ``frame_minmax``) keeps min/max on the device."""
+        self._check_supported()
+        if self.training:
+            raise RuntimeError("microbeseg_b200: training-mode forward is not built yet (call net.eval())")
+        return self.engine().run(img[None], int(pads[0]), int(pads[1]), float(lo), float(hi), lohi_dev=lohi_dev)
+
 
 class DUNet(_NetBase):
     """U-net with two decoder paths; returns (x1 border/neighbour map, x2 cell map)  (unets.py:380-506)."""
@@ -160,14 +169,8 @@ class DUNet(_NetBase):
         return outs[0], outs[1]
 
     def forward_frame(self, img, pads, lo=0.0, hi=0.0, lohi_dev=None):
-        """Fused entry used by the frame loop: raw (H,W) uint8/uint16/float32 CUDA frame ->
-        (border, cell) float32 [1,1,Hp,Wp] of the padded size; normalisation
-        ``2*(x-lo)/(hi-lo)-1`` and top/left padding with ``lo`` happen inside the first kernel.
-        ``lohi_dev`` (float32[2] CUDA tensor from ``frame_minmax``) keeps min/max on the device."""
-        self._check_supported()
-        if self.training:
-            raise RuntimeError("microbeseg_b200: training-mode forward is not built yet (call net.eval())")
-        outs = self.engine().run(img[None], int(pads[0]), int(pads[1]), float(lo), float(hi), lohi_dev=lohi_dev)
+        """(border, cell) float32 [1,1,Hp,Wp] for one raw frame (see _forward_frame_maps)."""
+        outs = self._forward_frame_maps(img, pads, lo, hi, lohi_dev)
         return outs[0], outs[1]
 
 
@@ -179,9 +182,10 @@ class UNet(_NetBase):
         super().__init__(ch_in, ch_out, pool_method, act_fun, normalization, filters)
 
     def forward(self, x):
-        if self.ch_out != 1:
-            raise NotImplementedError("multi-channel heads (boundary method) are not built yet")
-        return self._forward_maps(x)[0]
+        return self._forward_maps(x)[0]        # [N, ch_out, H, W] linear outputs (softmax is applied by the caller)
+
+    def forward_frame(self, img, pads, lo=0.0, hi=0.0, lohi_dev=None):
+        return self._forward_frame_maps(img, pads, lo, hi, lohi_dev)[0]
 
 
 def frame_minmax(img, out=None, scratch=None):
@@ -254,10 +258,10 @@ class _Engine:
                 self._pack_conv(f"{name}c{i}a", convs[i].conv[0], convs[i].conv[2])
                 self._pack_conv(f"{name}c{i}b", convs[i].conv[3], convs[i].conv[5])
             head = convs[len(ups)]
-            if head.weight.shape[0] != 1:
-                raise NotImplementedError("multi-channel heads (boundary method) are not built yet")
-            self.p[name + "head"] = (head.weight.detach().float().reshape(-1).contiguous(),
-                                     float(head.bias.detach().float().item()))
+            if head.weight.shape[0] > 4:
+                raise NotImplementedError("the fused 1x1 head supports at most 4 output channels")
+            self.p[name + "head"] = (head.weight.detach().float().reshape(head.weight.shape[0], -1).contiguous(),
+                                     [float(b) for b in head.bias.detach().float().cpu()])
 
     # -- buffers -------------------------------------------------------------------------------
     def _buf(self, name, shape, dtype=torch.bfloat16):
@@ -289,9 +293,11 @@ class _Engine:
         else:
             d.dst, d.ldd, d.coffd = None, 0, 0
         if head is not None:
-            d.head_w, d.head_b, d.head_out = head[0].data_ptr(), head[1], head_out.data_ptr()
+            d.head_w, d.head_n, d.head_out = head[0].data_ptr(), len(head[1]), head_out.data_ptr()
+            for k, b in enumerate(head[1]):
+                d.head_b[k] = b
         else:
-            d.head_w, d.head_b, d.head_out = None, 0.0, None
+            d.head_w, d.head_n, d.head_out = None, 0, None
         nat.check(self.L.mbs_conv_gemm(ctypes.byref(d), nat.stream_ptr()), name)
         self.last_conv_launches += 1
 
@@ -336,7 +342,7 @@ class _Engine:
             outs = []
             for name in self.net.decoder_names:
                 x = skip[nl - 1]
-                out = torch.empty((n, 1, H, W), dtype=torch.float32, device=self.device)
+                out = torch.empty((n, len(self.p[name + "head"][1]), H, W), dtype=torch.float32, device=self.device)
                 for i in range(nl - 1):
                     l = nl - 2 - i
                     self._conv(2, f"{name}up{i}", n, H >> (l + 1), W >> (l + 1), x, None, t1[l], act=0)

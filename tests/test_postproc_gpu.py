@@ -227,3 +227,22 @@ def test_full_size_properties(pp):
     # oracle on a crop-independent sub-problem: full oracle run (takes a few seconds)
     ref = op.distance_postprocessing(border, cell, 0.45, 0.10)
     assert np.array_equal(out, ref)
+
+
+def test_boundary_postprocessing_vs_oracle(pp):
+    """Boundary method (postprocessing.py:62-90): flat flood image -> pure FIFO order incl. heap internals."""
+    for H, W, cells, seed in [(96, 96, 14, 1), (128, 160, 40, 2), (64, 64, 0, 3)]:
+        m = sy.synth_instance_mask(H, W, cells, seed)
+        inner = ndimage.binary_erosion(m > 0, iterations=2)
+        rng = np.random.default_rng(seed)
+        logits = rng.normal(0, 0.3, (H, W, 3)).astype(np.float32)
+        logits[..., 0] += np.where(m == 0, 3.0, 0.0)
+        logits[..., 1] += np.where(inner, 3.0, 0.0)
+        logits[..., 2] += np.where((m > 0) & ~inner, 2.0, 0.0)
+        e = np.exp(logits - logits.max(-1, keepdims=True))
+        prob = (e / e.sum(-1, keepdims=True)).astype(np.float32)
+        out = pp.boundary_postprocessing(prob)
+        ref = op.boundary_postprocessing(prob)
+        assert out.dtype == np.uint16 and np.array_equal(out, ref)
+        if cells:
+            assert out.max() >= cells // 2

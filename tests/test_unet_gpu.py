@@ -150,7 +150,7 @@ def test_conv_gemm_vs_torch(native_lib, mode, N, H, W, C0, C1, Cout):
     d.weight, d.Cout = packed.data_ptr(), Cout
     d.bias, d.scale, d.shift, d.act = bias.data_ptr(), scale.data_ptr(), shift.data_ptr(), 1
     d.dst, d.ldd, d.coffd = out.data_ptr(), Cout, 0
-    d.head_w, d.head_b, d.head_out = None, 0.0, None
+    d.head_w, d.head_n, d.head_out = None, 0, None
     nat.check(L.mbs_conv_gemm(ctypes.byref(d), nat.stream_ptr()))
     torch.cuda.synchronize()
     xin = (torch.cat([x0, x1], -1) if C1 else x0).float().permute(0, 3, 1, 2)
@@ -244,3 +244,44 @@ def test_tiled_inference_is_bit_identical_to_whole_frame(native_lib):
     whole = FrameSegmenter(net, (0.10, 0.45)).segment(odd)
     tiled = segment_frame_tiled(net, odd, tile=128)
     assert tiled.shape == odd.shape and np.array_equal(whole, tiled)
+
+
+def test_single_decoder_unet_with_three_channel_head(native_lib):
+    """'U' architecture with ch_out=3 (boundary method, unets.py:267-377): fused 3-output 1x1 head."""
+    from microbeseg_b200.unets import build_unet
+    torch.set_grad_enabled(False)
+    filters = (64, 256)
+    net = build_unet("U", "relu", "conv", "bn", torch.device("cuda:0"), 1, ch_in=1, ch_out=3, filters=list(filters))
+    sd = onet.seeded_state_dict(onet.reference_layout_template("U", filters, ch_out=3), 81)
+    net.load_state_dict(sd)
+    net.eval()
+    x = torch.from_numpy(np.random.default_rng(81).normal(0, 0.5, (2, 1, 64, 80)).astype(np.float32))
+    ref = onet.unet_forward(sd, x, "relu")
+    got = net(x.cuda())
+    assert got.shape == ref.shape == (2, 3, 64, 80)
+    _check(got.cpu().numpy(), ref.numpy(), "unet3")
+
+
+def test_boundary_model_frame_loop(native_lib):
+    """U net + softmax + boundary_postprocessing through the frame loop (infer.py:365-374)."""
+    from microbeseg_b200 import synthetic as sy
+    from microbeseg_b200.inference import segment_stack
+    from microbeseg_b200.unets import build_unet
+    from microbeseg_b200.utils import zero_pad_model_input
+    from oracle import postproc as op
+    torch.set_grad_enabled(False)
+    filters = (64, 128)
+    net = build_unet("U", "relu", "conv", "bn", torch.device("cuda:0"), 1, ch_in=1, ch_out=3, filters=list(filters)).eval()
+    sd = onet.seeded_state_dict(onet.reference_layout_template("U", filters, ch_out=3), 91)
+    net.load_state_dict(sd)
+    stack = sy.synth_stack(2, 60, 90, seed0=5, distinct=2)
+    out = segment_stack(net, stack)
+    assert out.shape == stack.shape and out.dtype == np.uint16
+    # same maps through the product net, then oracle post-processing: identical masks
+    for t in range(2):
+        img = stack[t]
+        padded, pads = zero_pad_model_input(img, pad_val=img.min())
+        x = 2 * (padded.astype(np.float32) - img.min()) / (img.max() - img.min()) - 1
+        logits = net(torch.from_numpy(x[None, None]).cuda())
+        prob = torch.softmax(logits, dim=1)[0, :, pads[0]:, pads[1]:].permute(1, 2, 0).cpu().numpy()
+        assert np.array_equal(out[t], op.boundary_postprocessing(prob))

@@ -43,7 +43,8 @@ def run_conv(mode, N, H, W, C0, C1, Cout, act=1, head=False, bench=0):
     d.weight, d.Cout = packed.data_ptr(), Cout
     d.bias, d.scale, d.shift, d.act = bias.data_ptr(), scale.data_ptr(), shift.data_ptr(), act
     d.dst, d.ldd, d.coffd = out.data_ptr(), Cout, 0
-    d.head_w, d.head_b, d.head_out = (hw.data_ptr() if head else None), 0.25, (hout.data_ptr() if head else None)
+    d.head_w, d.head_n, d.head_out = (hw.data_ptr() if head else None), (1 if head else 0), (hout.data_ptr() if head else None)
+    d.head_b[0] = 0.25
     nat.check(L.mbs_conv_gemm(ctypes.byref(d), nat.stream_ptr()), "conv_gemm")
     torch.cuda.synchronize()
     # reference
