@@ -301,7 +301,7 @@ class _Engine:
         nat.check(self.L.mbs_conv_gemm(ctypes.byref(d), nat.stream_ptr()), name)
         self.last_conv_launches += 1
 
-    def run(self, img, pad_y, pad_x, lo, hi, events=None, lohi_dev=None):
+    def run(self, img, pad_y, pad_x, lo, hi, events=None, lohi_dev=None, keep_features=None):
         """img: [N,H,W] CUDA tensor (uint8 / uint16-as-int16 / float32).  hi < lo -> the values are
         already normalised (reference callers pass the normalised float image)."""
         if img.dtype not in _IN_CODES:
@@ -351,7 +351,11 @@ class _Engine:
                         self._conv(0, f"{name}c{i}b", n, H >> l, W >> l, t2[l], None, t1[l])
                         x = t1[l]
                     else:
-                        self._conv(0, f"{name}c{i}b", n, H, W, t2[0], None, None, head=self.p[name + "head"],
+                        feat = None
+                        if keep_features is not None:      # calibration only: also write the last 64-channel map
+                            feat = torch.empty((n, H, W, ch[0]), dtype=torch.bfloat16, device=self.device)
+                            keep_features[name] = feat
+                        self._conv(0, f"{name}c{i}b", n, H, W, t2[0], None, feat, head=self.p[name + "head"],
                                    head_out=out)
                 outs.append(out)
             if events is not None:

@@ -285,3 +285,57 @@ def test_boundary_model_frame_loop(native_lib):
         logits = net(torch.from_numpy(x[None, None]).cuda())
         prob = torch.softmax(logits, dim=1)[0, :, pads[0]:, pads[1]:].permute(1, 2, 0).cpu().numpy()
         assert np.array_equal(out[t], op.boundary_postprocessing(prob))
+
+
+def _match_ap50(ref, got):
+    """Instance-level agreement: AP@IoU0.5 = TP / (TP + FP + FN) and mean IoU of matched pairs."""
+    ids_r, ids_g = np.unique(ref[ref > 0]), np.unique(got[got > 0])
+    if len(ids_r) == 0 and len(ids_g) == 0:
+        return 1.0, 1.0
+    pair = ref.astype(np.int64) * (int(got.max()) + 1) + got.astype(np.int64)
+    keys, cnt = np.unique(pair[(ref > 0) & (got > 0)], return_counts=True)
+    ar = np.bincount(ref.ravel(), minlength=int(ref.max()) + 1)
+    ag = np.bincount(got.ravel(), minlength=int(got.max()) + 1)
+    tp, ious = 0, []
+    for k, c in zip(keys, cnt):
+        r, g = divmod(int(k), int(got.max()) + 1)
+        iou = c / (ar[r] + ag[g] - c)
+        if iou > 0.5:
+            tp += 1
+            ious.append(iou)
+    fp, fn = len(ids_g) - tp, len(ids_r) - tp
+    return tp / max(tp + fp + fn, 1), float(np.mean(ious)) if ious else 0.0
+
+
+def test_instance_level_agreement_with_fp32_reference_path(native_lib):
+    """north_star: bf16 CUDA path vs fp32 reference path must agree at instance level.  The random-init net
+    gets its two 1x1 heads least-squares fitted to synthetic distance maps (calibrate.fit_heads) so that the
+    maps are cell-like; then  CUDA net + CUDA post-processing  is compared with  fp32 oracle net + oracle
+    post-processing  on unseen frames.  Stated thresholds: mean AP@0.5 over the frames >= 0.93, matched mean IoU >= 0.92 per frame,
+    map error within the bf16 tolerance.  (The fitted random-feature maps are low-contrast, so a few seeds sit
+    right at the thresholds; a trained model leaves far more margin.)"""
+    from microbeseg_b200 import calibrate
+    from microbeseg_b200.inference import FrameSegmenter
+    from oracle import postproc as op
+    torch.set_grad_enabled(False)
+    net, _ = _build((64, 256), "relu", 101)
+    train = [calibrate.synthetic_training_pair(256, 256, 3000 + 10 * k)[:3] for k in range(3)]
+    calibrate.fit_heads(net, train)
+    sd = {k: v.detach().cpu() for k, v in net.state_dict().items()}
+    seg = FrameSegmenter(net, (0.10, 0.45))
+    aps, n_obj = [], 0
+    for k in range(4):
+        frame, _, _, mask = calibrate.synthetic_training_pair(256, 256, 5000 + 10 * k)
+        got = seg.segment(frame)
+        lo, hi = frame.min(), frame.max()
+        x = 2 * (frame.astype(np.float32) - lo) / (hi - lo) - 1
+        ob, oc = onet.dunet_forward(sd, torch.from_numpy(x[None, None]), "relu")
+        b, c = net(torch.from_numpy(x[None, None]).cuda())
+        _check(c.cpu().numpy(), oc.numpy(), "cell(fitted)")
+        _check(b.cpu().numpy(), ob.numpy(), "border(fitted)")
+        ref = op.distance_postprocessing(ob[0, 0, :, :, None].numpy(), oc[0, 0, :, :, None].numpy(), 0.45, 0.10)
+        ap, miou = _match_ap50(ref, got)
+        aps.append((ap, miou))
+        n_obj += int(ref.max())
+    assert n_obj > 40, n_obj                       # the fitted heads do produce seeds / objects
+    assert float(np.mean([a for a, _ in aps])) >= 0.93 and min(m for _, m in aps) >= 0.92, aps
