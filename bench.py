@@ -147,6 +147,9 @@ def main():
     ap.add_argument("--warmup-ref", type=int, default=1)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--size", type=int, default=2048)
+    ap.add_argument("--heads", default="fitted", choices=["fitted", "random"],
+                    help="fitted: least-squares fit of the two 1x1 heads to synthetic distance maps (realistic "
+                         "post-processing load); random: pure random init (maps have no seeds)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -177,6 +180,9 @@ def main():
     # network: published architecture, random init (reference default init, seed 0), eval mode
     torch.manual_seed(0)
     net = build_unet("DU", "relu", "conv", "bn", device, 1, ch_in=1, ch_out=1, filters=[64, 1024]).eval()
+    if args.heads == "fitted":
+        from microbeseg_b200 import calibrate
+        calibrate.fit_heads(net, [calibrate.synthetic_training_pair(512, 512, 7000 + 10 * k)[:3] for k in range(3)])
 
     # synthetic stack: `distinct` rendered frames, cycled (per-rank seeds differ)
     distinct = 4
@@ -227,6 +233,9 @@ def main():
             ms = float(t.item())
         return ms, launches
 
+    frame_device(0)
+    torch.cuda.synchronize()
+    objects_per_frame = int(out_dev.cpu().numpy().view(np.uint16).max())
     sampler = ClockSampler(local_rank)
     sampler.start()
     ms_dev, launches = timed(step_device, args.steps, args.warmup)
@@ -261,7 +270,10 @@ def main():
     achieved = conv_flops / (conv_ms_frame / 1e3) / 1e12
     roofline = {"bound": "tensor", "kernel": "conv_gemm_kernel (tcgen05 implicit GEMM, all tensor-core launches of one frame)",
                 "achieved": achieved, "peak": peaks["tf_sustained"], "unit": "TFLOP/s", "frac": achieved / peaks["tf_sustained"],
-                "peak_source": peaks["src"] + " (sustained cuBLAS bf16)", "traffic": None,
+                "peak_source": peaks["src"] + " (sustained cuBLAS bf16)",
+                # dram__bytes_read+write per launch, averaged over the frame's tensor-core launches
+                # (ncu capture profiles/r01_conv_dram_traffic_frame.csv: 36 tensor-core launches, 13.245 GB)
+                "traffic": 13.245e9 / 36 if size == 2048 else None,
                 "launches_per_frame": n_conv_launch, "avg_launch_ms": conv_ms_frame / max(n_conv_launch, 1),
                 "algorithmic_flop_per_launch": conv_flops / max(n_conv_launch, 1)}
 
@@ -300,7 +312,10 @@ def main():
                                    "whole-frame inference (B200 fits 2048^2 without tiling)",
                        "parallelism": f"frame-sharded x{world}, no collective",
                        "l2": "inputs larger than L2 (0.5 GiB activations per layer at full resolution)",
-                       "weights": "random init (torch.manual_seed(0), reference default init)"},
+                       "weights": "random init (torch.manual_seed(0), reference default init)" + (
+                           "; the 2x65 parameters of the two 1x1 heads least-squares fitted to synthetic distance maps "
+                           "so that post-processing sees cell-like maps" if args.heads == "fitted" else ""),
+                       "objects_per_frame": objects_per_frame},
             "e2e": {"value": e2e_value, "unit": "Mpx/s", "h2d_bytes_per_step": int(F * size * size * 2),
                     "d2h_bytes_per_step": int(F * size * size * 2), "steps": e2e_steps,
                     "ms_per_step": ms_e2e / e2e_steps, "api": "microbeseg_b200.inference.segment_stack"},
