@@ -114,6 +114,20 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map
         "l"(map), "r"(bar), "r"(c0), "r"(c1)
         : "memory");
 }
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap *map, uint32_t src, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(map),
+                 "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_store_5d(const CUtensorMap *map, uint32_t src, int c0, int c1, int c2, int c3,
+                                             int c4) {
+    asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];" ::"l"(map),
+                 "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap *map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
@@ -339,16 +353,156 @@ __device__ __forceinline__ void epilogue_tile(const ConvKParams &p, const float 
     }
 }
 
-template <int BN, int STAGES>
+// TMA-store epilogue.  The 8 epilogue warps form two groups of 4 warps (one warp per TMEM lane quadrant).
+// Work items are (tile, 64-column chunk) pairs dealt round-robin to the groups; a group converts its
+// chunk (TMEM -> fp32 math -> bf16), writes the 128-row x 128-byte tile into its own 16 KiB staging buffer in
+// the 128B-swizzled layout, and one elected thread hands it to the TMA engine (cp.async.bulk.tensor store),
+// which writes full lines, clips at the tensor boundary and keeps the LSU free.  The transposed conv uses a
+// 5-D view (C, dx, x, dy, y) of the 2x up-sampled destination, so its pixel-shuffle scatter is one box too.
+constexpr int STAGE_TILE_BYTES = 128 * 128;
+template <int BN, int TW>
+__device__ __forceinline__ void epilogue_tile_tma(const ConvKParams &p, const CUtensorMap *tmD, const float *s_par,
+                                                  uint32_t s_stage, uint32_t tmem_base, uint32_t tfull,
+                                                  uint32_t tempty, int lt, int group, int quad, int lane, bool leader,
+                                                  int x0, int y0, int img, int n0, bool has_head, bool &pending) {
+    constexpr int CHUNKS = BN / 64;
+    if (CHUNKS == 1 && (lt & 1) != group) return;       // BN == 64: whole tiles alternate between the groups
+    const int buf = lt & 1;
+    const int row = quad * 32 + lane;
+    mbar_wait(tfull, (lt >> 1) & 1);
+    tcgen05_fence_after();
+    float head_acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+#pragma unroll 1
+    for (int chn = (CHUNKS == 1 ? 0 : group); chn < CHUNKS; chn += (CHUNKS == 1 ? 1 : 2)) {
+        const int col0 = n0 + chn * 64;
+        int q = 0, co0 = col0;
+        if (p.mode == MBS_CONVT2X2_S2) {
+            q = col0 / p.Cout;
+            co0 = col0 - q * p.Cout;
+        }
+        if (p.dst && pending) {      // the previous store out of this staging buffer must have been read
+            if (leader) tma_store_wait_read();
+            asm volatile("bar.sync %0, 128;" ::"r"(1 + group) : "memory");
+            pending = false;
+        }
+#pragma unroll 1
+        for (int k = 0; k < 2; ++k) {
+            uint32_t r[32];
+            tmem_ld32(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(buf * BN + chn * 64 + k * 32), r);
+            const int co = co0 + k * 32;
+            const float4 *pb = reinterpret_cast<const float4 *>(s_par + co);
+            const float4 *psc = reinterpret_cast<const float4 *>(s_par + p.Cout + co);
+            const float4 *psh = reinterpret_cast<const float4 *>(s_par + 2 * p.Cout + co);
+            float v[32];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float4 b4 = pb[j];
+                v[4 * j + 0] = __uint_as_float(r[4 * j + 0]) + b4.x;
+                v[4 * j + 1] = __uint_as_float(r[4 * j + 1]) + b4.y;
+                v[4 * j + 2] = __uint_as_float(r[4 * j + 2]) + b4.z;
+                v[4 * j + 3] = __uint_as_float(r[4 * j + 3]) + b4.w;
+            }
+            switch (p.act) {      // one uniform branch per 32 columns
+                case MBS_ACT_RELU:
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.0f);
+                    break;
+                case MBS_ACT_LEAKYRELU:
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = v[j] > 0.0f ? v[j] : 0.01f * v[j];
+                    break;
+                case MBS_ACT_ELU:
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = v[j] > 0.0f ? v[j] : expm1f(v[j]);
+                    break;
+                case MBS_ACT_MISH:
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], MBS_ACT_MISH);
+                    break;
+                default: break;
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float4 s4 = psc[j], t4 = psh[j];
+                v[4 * j + 0] = fmaf(v[4 * j + 0], s4.x, t4.x);
+                v[4 * j + 1] = fmaf(v[4 * j + 1], s4.y, t4.y);
+                v[4 * j + 2] = fmaf(v[4 * j + 2], s4.z, t4.z);
+                v[4 * j + 3] = fmaf(v[4 * j + 3], s4.w, t4.w);
+            }
+            if (BN == 64 && has_head) {
+#pragma unroll
+                for (int h = 0; h < 4; ++h) {
+                    if (h < p.head_n) {
+                        const float4 *phw = reinterpret_cast<const float4 *>(s_par + (3 + h) * p.Cout + co);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const float4 w4 = phw[j];
+                            head_acc[h] = fmaf(v[4 * j + 0], w4.x, head_acc[h]);
+                            head_acc[h] = fmaf(v[4 * j + 1], w4.y, head_acc[h]);
+                            head_acc[h] = fmaf(v[4 * j + 2], w4.z, head_acc[h]);
+                            head_acc[h] = fmaf(v[4 * j + 3], w4.w, head_acc[h]);
+                        }
+                    }
+                }
+            }
+            if (p.dst) {
+                // row r of the staging tile = pixel r of the patch; 16-byte chunk c lives at c ^ (r & 7) (SWIZZLE_128B)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    __nv_bfloat162 h0 = __floats2bfloat162_rn(v[8 * j + 0], v[8 * j + 1]);
+                    __nv_bfloat162 h1 = __floats2bfloat162_rn(v[8 * j + 2], v[8 * j + 3]);
+                    __nv_bfloat162 h2 = __floats2bfloat162_rn(v[8 * j + 4], v[8 * j + 5]);
+                    __nv_bfloat162 h3 = __floats2bfloat162_rn(v[8 * j + 6], v[8 * j + 7]);
+                    const uint32_t a = s_stage + row * 128u + static_cast<uint32_t>(((k * 4 + j) ^ (row & 7)) * 16);
+                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a),
+                                 "r"(*reinterpret_cast<uint32_t *>(&h0)), "r"(*reinterpret_cast<uint32_t *>(&h1)),
+                                 "r"(*reinterpret_cast<uint32_t *>(&h2)), "r"(*reinterpret_cast<uint32_t *>(&h3))
+                                 : "memory");
+                }
+            }
+        }
+        if (p.dst) {
+            fence_proxy_async();                         // generic-proxy smem writes -> visible to the TMA engine
+            asm volatile("bar.sync %0, 128;" ::"r"(1 + group) : "memory");
+            if (leader) {
+                if (p.mode == MBS_CONVT2X2_S2)
+                    tma_store_5d(tmD, s_stage, co0, q & 1, x0, q >> 1, img * p.Hm + y0);
+                else
+                    tma_store_4d(tmD, s_stage, col0, x0, y0, img);
+                tma_store_commit();
+            }
+            pending = true;
+        }
+    }
+    // all TMEM reads of this tile are complete (tcgen05.wait::ld inside tmem_ld32)
+    tcgen05_fence_before();
+    __syncwarp();
+    if (lane == 0) {
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tempty) : "memory");
+    }
+    if (BN == 64 && has_head) {
+        const int py = y0 + row / TW, px = x0 + row % TW;
+        if (py < p.Hm && px < p.Wm) {
+#pragma unroll
+            for (int h = 0; h < 4; ++h)
+                if (h < p.head_n)
+                    p.head_out[((static_cast<size_t>(img) * p.head_n + h) * p.Hm + py) * p.Wm + px] = head_acc[h] + p.head_b[h];
+        }
+    }
+}
+
+template <int BN, int STAGES, bool TMA_EPI>
 struct SmemPlan {
     static constexpr int B_BYTES = BN * BK * 2;
-    static constexpr int EPI_BYTES = EPI_WARPS * 1024 + 2 * 4 * 128 * 4;   // per warp 32 rows x 16 bf16; + head partials
+    // TMA epilogue: two 16 KiB staging tiles (one per epilogue group); direct epilogue: per warp 32 rows x 16 bf16
+    // plus the head partial sums
+    static constexpr int EPI_BYTES = TMA_EPI ? 2 * STAGE_TILE_BYTES : EPI_WARPS * 1024 + 2 * 4 * 128 * 4;
     static constexpr int OFF_A = 0;
     static constexpr int OFF_B = STAGES * A_BYTES;
     static constexpr int OFF_EPI = OFF_B + STAGES * B_BYTES;
     static constexpr int OFF_BAR = OFF_EPI + EPI_BYTES;           // full[S], empty[S], tmem_full[2], tmem_empty[2]
     static constexpr int OFF_TMEM = OFF_BAR + 8 * (2 * STAGES + 4);
-    static constexpr int OFF_PAR = (OFF_TMEM + 8 + 15) / 16 * 16;  // bias/scale/shift/head_w, [4][Cout] floats (float4 reads)
+    static constexpr int OFF_PAR = (OFF_TMEM + 8 + 15) / 16 * 16;  // bias/scale/shift(/head_w) floats (float4 reads)
     static constexpr int FIXED = OFF_PAR + 1024;                  // + slack for the manual 1024-B alignment
     static int dyn_bytes(int cout) { return FIXED + (3 * cout + (cout == 64 ? 4 * 64 : 0)) * 4; }   // heads only with Cout == 64
 };
@@ -356,11 +510,11 @@ struct SmemPlan {
 // Persistent, warp-specialised implicit-GEMM kernel.  Each CTA walks tiles t = blockIdx.x, +gridDim.x, ...
 // The smem ring (TMA <-> MMA) runs continuously across tiles; the accumulator is double buffered in
 // TMEM so that the epilogue of tile i overlaps the MMAs of tile i+1.
-template <int BN, int STAGES, int MIN_CTAS>
+template <int BN, int STAGES, int MIN_CTAS, bool TMA_EPI>
 __global__ void __launch_bounds__(NUM_THREADS, MIN_CTAS)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
-                 const __grid_constant__ CUtensorMap tmB, const ConvKParams p) {
-    using Plan = SmemPlan<BN, STAGES>;
+                 const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmD, const ConvKParams p) {
+    using Plan = SmemPlan<BN, STAGES, TMA_EPI>;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;
@@ -391,7 +545,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         }
         for (int b = 0; b < 2; ++b) {
             mbar_init(tfull_bar(b), 1);
-            mbar_init(tempty_bar(b), EPI_WARPS);   // one arrive per epilogue warp
+            mbar_init(tempty_bar(b), (TMA_EPI && BN == 64) ? 4 : EPI_WARPS);   // one arrive per participating epilogue warp
         }
         fence_barrier_init();
     }
@@ -479,11 +633,13 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         // ===== epilogue: TMEM -> registers -> bias/act/BN -> bf16 -> smem transpose -> coalesced global =====
         const int e = warp - 2;
         const int quad = warp & 3;                 // TMEM lane quadrant this warp may access
-        const int half = e >> 2;                   // which half of the BN columns this warp converts
-        const int row = quad * 32 + lane;          // tile row == pixel index inside the 8x16 patch
-        const uint32_t s_epi = base + Plan::OFF_EPI + static_cast<uint32_t>(e) * 1024u;
-        float *s_head = reinterpret_cast<float *>(gbase + Plan::OFF_EPI + EPI_WARPS * 1024);
+        const int half = e >> 2;                   // epilogue group / which half of the BN columns this warp converts
         const bool has_head = p.head_out != nullptr;
+        const uint32_t s_epi = base + Plan::OFF_EPI + static_cast<uint32_t>(e) * 1024u;
+        const uint32_t s_stage = base + Plan::OFF_EPI + static_cast<uint32_t>(half) * STAGE_TILE_BYTES;
+        float *s_head = reinterpret_cast<float *>(gbase + Plan::OFF_EPI + EPI_WARPS * 1024);
+        const bool leader = (e & 3) == 0 && lane == 0;
+        bool pending = false;
         int lt = 0;
         for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++lt) {
             const int n_tile = tile % p.n_tiles;
@@ -492,9 +648,14 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
             const int ty = (m_tile / p.tiles_x) % p.tiles_y;
             const int img = m_tile / tiles_per_img;
             const int x0 = tx * TILE_W, y0 = ty * TILE_H, n0 = n_tile * BN;
-            epilogue_tile<BN, TILE_W>(p, s_par, s_epi, s_head, tmem_base, tfull_bar(lt & 1), tempty_bar(lt & 1), lt, quad, half,
-                                      lane, x0, y0, img, n0, has_head);
+            if (TMA_EPI)
+                epilogue_tile_tma<BN, TILE_W>(p, &tmD, s_par, s_stage, tmem_base, tfull_bar(lt & 1), tempty_bar(lt & 1), lt,
+                                              half, quad, lane, leader, x0, y0, img, n0, has_head, pending);
+            else
+                epilogue_tile<BN, TILE_W>(p, s_par, s_epi, s_head, tmem_base, tfull_bar(lt & 1), tempty_bar(lt & 1), lt,
+                                          quad, half, lane, x0, y0, img, n0, has_head);
         }
+        if (TMA_EPI && leader && pending) tma_store_wait_all();
     }
     tcgen05_fence_before();
     __syncthreads();
@@ -529,7 +690,7 @@ struct HaloPlan {
     static constexpr int OFF_W = 0;
     static constexpr int OFF_A = 9 * CHUNKS * W_TILE_BYTES;
     static constexpr int OFF_EPI = OFF_A + STAGES * HALO_SLOT;
-    static constexpr int EPI_BYTES = EPI_WARPS * 1024 + 2 * 4 * 128 * 4;
+    static constexpr int EPI_BYTES = 2 * STAGE_TILE_BYTES;     // TMA-store staging, one tile per epilogue group
     static constexpr int OFF_BAR = OFF_EPI + EPI_BYTES;        // full[S], empty[S], tfull[2], tempty[2], wbar
     static constexpr int OFF_TMEM = OFF_BAR + 8 * (2 * STAGES + 5);
     static constexpr int OFF_PAR = (OFF_TMEM + 8 + 15) / 16 * 16;
@@ -549,7 +710,8 @@ __device__ __forceinline__ uint64_t make_sw128_desc_sbo(uint32_t saddr, uint32_t
 template <int CHUNKS, int STAGES>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_halo64_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
-                   const __grid_constant__ CUtensorMap tmB, const ConvKParams p) {
+                   const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmD,
+                   const ConvKParams p) {
     using Plan = HaloPlan<CHUNKS, STAGES>;
     constexpr int BN = 64;
     extern __shared__ uint8_t smem_raw[];
@@ -581,7 +743,7 @@ conv_halo64_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
         }
         for (int b = 0; b < 2; ++b) {
             mbar_init(tfull_bar(b), 1);
-            mbar_init(tempty_bar(b), EPI_WARPS);
+            mbar_init(tempty_bar(b), 4);     // BN == 64: tiles alternate between the two epilogue groups
         }
         mbar_init(w_bar, 1);
         fence_barrier_init();
@@ -658,18 +820,20 @@ conv_halo64_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
     } else {
         const int e = warp - 2;
         const int quad = warp & 3;
-        const int half = e >> 2;
-        const uint32_t s_epi = base + Plan::OFF_EPI + static_cast<uint32_t>(e) * 1024u;
-        float *s_head = reinterpret_cast<float *>(gbase + Plan::OFF_EPI + EPI_WARPS * 1024);
+        const int group = e >> 2;
+        const uint32_t s_stage = base + Plan::OFF_EPI + static_cast<uint32_t>(group) * STAGE_TILE_BYTES;
         const bool has_head = p.head_out != nullptr;
+        const bool leader = (e & 3) == 0 && lane == 0;
+        bool pending = false;
         int lt = 0;
         for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++lt) {
             const int tx = tile % p.tiles_x;
             const int ty = (tile / p.tiles_x) % p.tiles_y;
             const int img = tile / tiles_per_img;
-            epilogue_tile<BN, HT_W>(p, s_par, s_epi, s_head, tmem_base, tfull_bar(lt & 1), tempty_bar(lt & 1), lt, quad, half,
-                                    lane, tx * HT_W, ty * HT_H, img, 0, has_head);
+            epilogue_tile_tma<BN, HT_W>(p, &tmD, s_par, s_stage, tmem_base, tfull_bar(lt & 1), tempty_bar(lt & 1), lt, group,
+                                        quad, lane, leader, tx * HT_W, ty * HT_H, img, 0, has_head, pending);
         }
+        if (leader && pending) tma_store_wait_all();
     }
     tcgen05_fence_before();
     __syncthreads();
@@ -902,26 +1066,46 @@ int sm_count() {
     return n;
 }
 
-template <int BN, int STAGES, int CTAS_PER_SM>
-int launch_conv(const CUtensorMap &a0, const CUtensorMap &a1, const CUtensorMap &b, const ConvKParams &kp,
-                cudaStream_t stream) {
-    using Plan = SmemPlan<BN, STAGES>;
+// destination of a transposed conv as a 5-D tensor (C, dx, x, dy, y'): pixel (2y+dy, 2x+dx) of image n is
+// element (c, dx, x, dy, n*H_in + y); one store box = the (dy,dx) quadrant of an 8x16 input patch.
+int make_convT_store_map(CUtensorMap *map, const void *base, int N, int H_in, int W_in, int C, int ld, int coff) {
+    EncodeTiledFn enc = get_encode_fn();
+    MBS_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled entry point not available (no CUDA driver?)");
+    const char *p = static_cast<const char *>(base) + static_cast<size_t>(coff) * 2;
+    const cuuint64_t px = static_cast<cuuint64_t>(ld) * 2;          // bytes per output pixel
+    const cuuint64_t Wd = 2ull * W_in;
+    cuuint64_t dims[5] = {static_cast<cuuint64_t>(C), 2, static_cast<cuuint64_t>(W_in), 2,
+                          static_cast<cuuint64_t>(N) * H_in};
+    cuuint64_t strides[4] = {px, 2 * px, Wd * px, 2 * Wd * px};
+    cuuint32_t box[5] = {static_cast<cuuint32_t>(BK), 1, static_cast<cuuint32_t>(TILE_W), 1, static_cast<cuuint32_t>(TILE_H)};
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<char *>(p), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    MBS_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(convT destination) failed: %d", static_cast<int>(r));
+    return 0;
+}
+
+template <int BN, int STAGES, int CTAS_PER_SM, bool TMA_EPI>
+int launch_conv(const CUtensorMap &a0, const CUtensorMap &a1, const CUtensorMap &b, const CUtensorMap &dmap,
+                const ConvKParams &kp, cudaStream_t stream) {
+    using Plan = SmemPlan<BN, STAGES, TMA_EPI>;
     static int configured_bytes = 0;
     const int dyn = Plan::dyn_bytes(kp.Cout);
     if (dyn > configured_bytes) {
-        MBS_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<BN, STAGES, CTAS_PER_SM>,
+        MBS_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<BN, STAGES, CTAS_PER_SM, TMA_EPI>,
                                             cudaFuncAttributeMaxDynamicSharedMemorySize, dyn));
         configured_bytes = dyn;
     }
     const int grid = kp.num_tiles < sm_count() * CTAS_PER_SM ? kp.num_tiles : sm_count() * CTAS_PER_SM;
-    conv_gemm_kernel<BN, STAGES, CTAS_PER_SM><<<grid, NUM_THREADS, dyn, stream>>>(a0, a1, b, kp);
+    conv_gemm_kernel<BN, STAGES, CTAS_PER_SM, TMA_EPI><<<grid, NUM_THREADS, dyn, stream>>>(a0, a1, b, dmap, kp);
     MBS_CHECK_LAUNCH();
     return 0;
 }
 
 template <int CHUNKS, int STAGES>
-int launch_halo(const CUtensorMap &a0, const CUtensorMap &a1, const CUtensorMap &b, const ConvKParams &kp,
-                cudaStream_t stream) {
+int launch_halo(const CUtensorMap &a0, const CUtensorMap &a1, const CUtensorMap &b, const CUtensorMap &dmap,
+                const ConvKParams &kp, cudaStream_t stream) {
     using Plan = HaloPlan<CHUNKS, STAGES>;
     static bool configured = false;
     if (!configured) {
@@ -930,7 +1114,7 @@ int launch_halo(const CUtensorMap &a0, const CUtensorMap &a1, const CUtensorMap 
         configured = true;
     }
     const int grid = kp.num_tiles < sm_count() ? kp.num_tiles : sm_count();
-    conv_halo64_kernel<CHUNKS, STAGES><<<grid, NUM_THREADS, Plan::DYN_BYTES, stream>>>(a0, a1, b, kp);
+    conv_halo64_kernel<CHUNKS, STAGES><<<grid, NUM_THREADS, Plan::DYN_BYTES, stream>>>(a0, a1, b, dmap, kp);
     MBS_CHECK_LAUNCH();
     return 0;
 }
@@ -1010,15 +1194,21 @@ extern "C" int mbs_conv_gemm(const mbs_conv_desc *d, void *stream_) {
         }
         rc = make_weight_map(&b, d->weight, 64, 9 * (d->C0 + d->C1), 64);
         if (rc) return rc;
-        if (d->C1 > 0) return launch_halo<2, 2>(a0, a1, b, kp, stream);
-        return launch_halo<1, 4>(a0, a1, b, kp, stream);
+        CUtensorMap dm = a0;
+        if (d->dst) {
+            rc = make_act_map(&dm, d->dst, d->N, kp.Hd, kp.Wd, d->Cout, d->ldd, d->coffd, 1, HT_W, HT_H);
+            if (rc) return rc;
+        }
+        if (d->C1 > 0) return launch_halo<2, 2>(a0, a1, b, dm, kp, stream);
+        return launch_halo<1, 4>(a0, a1, b, dm, kp, stream);
     }
 
     const int ncols = d->mode == MBS_CONVT2X2_S2 ? 4 * d->Cout : d->Cout;
     const int K = kp.taps * (d->C0 + d->C1);
     int bn = ncols % 256 == 0 ? 256 : (ncols % 128 == 0 ? 128 : 64);
     // transposed convs have a short K loop and are epilogue/bandwidth bound: prefer two resident CTAs
-    if (d->mode == MBS_CONVT2X2_S2 && d->C0 <= 256) bn = 128;
+    // (the TMA-store path of the transposed conv needs whole patches per image in its folded (N*H) dimension)
+    if (d->mode == MBS_CONVT2X2_S2 && d->C0 <= 256 && (d->N == 1 || d->H % TILE_H == 0)) bn = 128;
     kp.n_tiles = ncols / bn;
 
     CUtensorMap a0, a1, b;
@@ -1037,9 +1227,20 @@ extern "C" int mbs_conv_gemm(const mbs_conv_desc *d, void *stream_) {
     MBS_REQUIRE(tiles_ll > 0 && tiles_ll < (1ll << 31), "too many tiles");
     kp.num_tiles = static_cast<int>(tiles_ll);
     MBS_REQUIRE(d->Cout <= 1024, "Cout > 1024 is not supported by the epilogue parameter staging");
-    if (bn == 256) return launch_conv<256, 4, 1>(a0, a1, b, kp, stream);
-    if (bn == 128) return launch_conv<128, 3, 2>(a0, a1, b, kp, stream);
-    return launch_conv<64, 4, 2>(a0, a1, b, kp, stream);
+    if (bn == 256) return launch_conv<256, 4, 1, false>(a0, a1, b, a0, kp, stream);
+    if (d->mode == MBS_CONVT2X2_S2) {
+        // short-K transposed conv: TMA-store epilogue (5-D pixel-shuffle view of the destination), one CTA per SM
+        CUtensorMap dm = a0;
+        if (d->dst) {
+            rc = make_convT_store_map(&dm, d->dst, d->N, d->H, d->W, d->Cout, d->ldd, d->coffd);
+            if (rc) return rc;
+        }
+        return launch_conv<128, 5, 1, true>(a0, a1, b, dm, kp, stream);
+    }
+    // measured on B200: for the generic BN <= 128 convs two resident CTAs with the direct epilogue beat one CTA
+    // with the TMA-store epilogue (128->128 @1024^2: 0.295 vs 0.378 ms)
+    if (bn == 128) return launch_conv<128, 3, 2, false>(a0, a1, b, a0, kp, stream);
+    return launch_conv<64, 4, 2, false>(a0, a1, b, a0, kp, stream);
 }
 
 extern "C" int mbs_first_conv(const void *img, int in_dtype, int H, int W, int pad_y, int pad_x, float norm_lo,
