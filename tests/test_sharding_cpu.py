@@ -70,3 +70,18 @@ def test_zero_pad_model_input_matches_reference_semantics():
     assert model_input_pads(9000, 100) == [28]          # reference quirk: one pad only, no exception
     x = min_max_normalization(np.array([[0, 5, 10]], np.uint16))
     assert x.dtype == np.float32 and x.tolist() == [[-1.0, 0.0, 1.0]]
+
+
+def test_tiff_roundtrip_and_cli_surface(tmp_path):
+    from microbeseg_b200 import tiffio
+    rng = np.random.default_rng(0)
+    for arr in (rng.integers(0, 65535, (3, 20, 31)).astype(np.uint16), rng.integers(0, 255, (17, 9)).astype(np.uint8),
+                rng.normal(size=(2, 8, 8)).astype(np.float32)):
+        f = tmp_path / "a.tif"
+        tiffio.imwrite(f, arr)
+        back = tiffio.imread(f)
+        assert back.dtype == arr.dtype and np.array_equal(back, arr)
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "infer_script_local.py"), "--help"], capture_output=True, text=True)
+    assert out.returncode == 0
+    for flag in ("--img_dir", "--model", "--thresholds", "--result_path", "--channel", "--device", "--overwrite"):
+        assert flag in out.stdout

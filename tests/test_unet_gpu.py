@@ -339,3 +339,25 @@ def test_instance_level_agreement_with_fp32_reference_path(native_lib):
         n_obj += int(ref.max())
     assert n_obj > 40, n_obj                       # the fitted heads do produce seeds / objects
     assert float(np.mean([a for a, _ in aps])) >= 0.93 and min(m for _, m in aps) >= 0.92, aps
+
+
+def test_cli_infer_script_local(native_lib, tmp_path):
+    """infer_script_local.py end to end: model dir (.pth + .json), .tif stack in, mask_<stem>_channel0.tif out."""
+    import json
+    import infer_script_local
+    from microbeseg_b200 import synthetic as sy, tiffio
+    from microbeseg_b200.inference import segment_stack
+    torch.set_grad_enabled(False)
+    filters = [64, 128]
+    net, sd = _build(tuple(filters), "relu", 111)
+    mdir, idir, rdir = tmp_path / "models", tmp_path / "imgs", tmp_path / "res"
+    for d in (mdir, idir, rdir):
+        d.mkdir()
+    torch.save(sd, mdir / "m1.pth")
+    json.dump({"architecture": ["DU", "conv", "relu", "bn", filters], "label_type": "distance"}, open(mdir / "m1.json", "w"))
+    stack = sy.synth_stack(2, 70, 90, seed0=9, distinct=2)
+    tiffio.imwrite(idir / "movie.tif", stack)
+    infer_script_local.main(["-i", str(idir), "-m", str(mdir / "m1"), "-r", str(rdir), "-d", "cuda:0"])
+    out = tiffio.imread(rdir / "mask_movie_channel0.tif")
+    assert out.dtype == np.uint16 and out.shape == stack.shape
+    assert np.array_equal(out, segment_stack(net, stack))
