@@ -60,7 +60,8 @@ constexpr int FT = 32;  // front-end tile edge
 // rounded, as scipy stores the intermediate in the float32 output array); phase 2: x-pass + maps.
 __global__ void __launch_bounds__(256)
 pp_front_kernel(const float *__restrict__ border, const float *__restrict__ cell, int H, int W, int ld, float th_seed,
-                float th_cell, float *__restrict__ cell_s, uint8_t *__restrict__ mask, uint8_t *__restrict__ seed) {
+                float th_cell, float *__restrict__ cell_s, uint8_t *__restrict__ mask, uint8_t *__restrict__ seed,
+                int *__restrict__ ccl_init) {
     __shared__ float s_in[FT + 4][FT + 4];
     __shared__ float s_y[FT][FT + 4];
     const int x0 = blockIdx.x * FT, y0 = blockIdx.y * FT;
@@ -92,7 +93,9 @@ pp_front_kernel(const float *__restrict__ border, const float *__restrict__ cell
         const size_t o = static_cast<size_t>(y) * W + x;
         cell_s[o] = cs;
         mask[o] = cs > th_cell ? 1 : 0;
-        seed[o] = cleaned > th_seed ? 1 : 0;
+        const bool sd = cleaned > th_seed;
+        seed[o] = sd ? 1 : 0;
+        if (ccl_init) ccl_init[o] = sd ? static_cast<int>(o) : -1;     // union-find initial state (saves a pass)
     }
 }
 
@@ -155,21 +158,28 @@ __global__ void ccl_init_kernel(const uint8_t *__restrict__ fg, int n, int *__re
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) L[i] = fg[i] ? i : -1;
 }
-// 8-connectivity: unite with W, NW, N, NE
+// 8-connectivity.  A pixel only issues the unions that are not implied by its left neighbour's:
+//   W  : always (cheap: the roots usually coincide already after the first pixels of a run)
+//   N  : unless both left neighbours (W and NW) are foreground -- then pixel W already joined the two runs
+//   NW : only if N is background and W is background (else W's own N union covers it)
+//   NE : only if N is background and E is background (else E's N union covers it)
 __global__ void ccl_merge8_kernel(const uint8_t *__restrict__ fg, int H, int W, int *L) {
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
     const int y = blockIdx.y * blockDim.y + threadIdx.y;
     if (x >= W || y >= H) return;
     const int i = y * W + x;
     if (!fg[i]) return;
-    if (x > 0 && fg[i - 1]) uf_union(L, i, i - 1);
+    const bool w = x > 0 && fg[i - 1];
+    if (w) uf_union(L, i, i - 1);
     if (y > 0) {
         const int u = i - W;
-        if (fg[u]) {
-            uf_union(L, i, u);  // N connects NW and NE as well
+        const bool n = fg[u] != 0;
+        const bool nw = x > 0 && fg[u - 1];
+        if (n) {
+            if (!(w && nw)) uf_union(L, i, u);
         } else {
-            if (x > 0 && fg[u - 1]) uf_union(L, i, u - 1);
-            if (x + 1 < W && fg[u + 1]) uf_union(L, i, u + 1);
+            if (nw && !w) uf_union(L, i, u - 1);
+            if (x + 1 < W && fg[u + 1] && !fg[i + 1]) uf_union(L, i, u + 1);
         }
     }
 }
@@ -187,11 +197,15 @@ struct Stats {
     unsigned int sweeps;
 };
 
-__global__ void area_kernel(const int *__restrict__ L, int n, int *__restrict__ area, Stats *st) {
+// path compression + component areas + component / pixel counts in one pass
+__global__ void compress_area_kernel(int *L, int n, int *__restrict__ area, Stats *st) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     int r = -1;
-    if (i < n) r = L[i];
-    if (r >= 0) atomicAdd(&area[r], 1);
+    if (i < n && L[i] >= 0) {
+        r = uf_find(L, i);
+        L[i] = r;
+        atomicAdd(&area[r], 1);
+    }
     const int cnt = __syncthreads_count(r >= 0);
     const int roots = __syncthreads_count(r >= 0 && r == i);
     if (threadIdx.x == 0) {
@@ -292,12 +306,19 @@ rank_assign_kernel(const int *__restrict__ L, const int *__restrict__ area, int 
     }
 }
 
+// markers = relabelled seeds * mask (_validate_inputs) and the initial flood level (markers: v, else +inf)
 __global__ void markers_kernel(const int *__restrict__ L, const int *__restrict__ rank, const uint8_t *__restrict__ mask,
-                               int n, int *__restrict__ markers) {
+                               int n, int *__restrict__ markers, const float *__restrict__ img, int negate,
+                               float *__restrict__ Lv) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const int r = L[i];
-    markers[i] = (r >= 0 && mask[i]) ? rank[r] : 0;  // _validate_inputs: markers * mask
+    const int m = (r >= 0 && mask[i]) ? rank[r] : 0;
+    markers[i] = m;
+    if (Lv) {
+        const float v = img[i];
+        Lv[i] = m > 0 ? (negate ? -v : v) : __builtin_huge_valf();
+    }
 }
 __global__ void labels_from_roots_kernel(const int *__restrict__ L, const int *__restrict__ rank, int n,
                                          int *__restrict__ out) {
@@ -382,8 +403,10 @@ ws_relax_coop_kernel(const float *__restrict__ img, int negate, const int *__res
             if (__syncthreads_or(any_act)) {
                 for (;;) {
                     bool changed = false;
+                    // down then up over this thread's 4-pixel column strip: levels travel the whole strip per iteration
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) {
+                    for (int kk = 0; kk < 7; ++kk) {
+                        const int k = kk < 4 ? kk : 6 - kk;
                         if (!act[k]) continue;
                         const int r = ty * 4 + k + 1, c = tx + 1;
                         const float m = fminf(fminf(sL[r - 1][c], sL[r + 1][c]), fminf(sL[r][c - 1], sL[r][c + 1]));
@@ -503,13 +526,14 @@ __global__ void ws_label_kernel(const int *__restrict__ parent, const int *__res
 }
 // order-independence check (see file header)
 __global__ void ws_check_kernel(const float *__restrict__ Lv, const int *__restrict__ parent,
-                                const int *__restrict__ lab, int H, int W, Stats *st) {
+                                const int *__restrict__ lab, int H, int W, Stats *st, uint16_t *__restrict__ out16) {
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
     const int y = blockIdx.y * blockDim.y + threadIdx.y;
     bool bad = false;
     if (x < W && y < H) {
         const int i = y * W + x;
         const int pr = parent[i];
+        if (out16) out16[i] = static_cast<uint16_t>(static_cast<unsigned int>(lab[i]));   // astype(uint16) wraps
         if (pr != P_NONE && pr != i) {
             const int me = lab[i];
             // level of the neighbours that may have labelled this pixel
@@ -575,7 +599,7 @@ __device__ void heap_pop(HeapItem *h, int &n, HeapItem &dst) {
 }
 __global__ void ws_sequential_kernel(const float *__restrict__ img, int negate, const int *__restrict__ markers,
                                      const uint8_t *__restrict__ mask, int H, int W, int *lab, HeapItem *heap,
-                                     const Stats *st, int force) {
+                                     const Stats *st, int force, uint16_t *out16) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     if (!force && st->ambiguous == 0) return;
     const int n = H * W;
@@ -614,11 +638,8 @@ __global__ void ws_sequential_kernel(const float *__restrict__ img, int negate, 
             heap_push(heap, hn, ne);
         }
     }
-}
-
-__global__ void to_u16_kernel(const int *__restrict__ lab, int n, uint16_t *__restrict__ out) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) out[i] = static_cast<uint16_t>(static_cast<unsigned int>(lab[i]));  // astype(uint16) wraps
+    if (out16)
+        for (int i = 0; i < n; ++i) out16[i] = static_cast<uint16_t>(static_cast<unsigned int>(lab[i]));
 }
 
 // ------------------------------------------------------------------------------------------
@@ -653,20 +674,19 @@ size_t watershed_ws_bytes(size_t n) {
 
 // label + filter + rank.  roots: [n] int scratch/out (component root per pixel, -1 background)
 int run_label_rank(const uint8_t *fg, int H, int W, int *roots, int *area, int *rank, int *tile_cnt, Stats *st,
-                   int use_mean, int filter, cudaStream_t stream) {
+                   int use_mean, int roots_initialised, cudaStream_t stream) {
     const int n = H * W;
     const int nb = mbs::cdiv(n, 256);
     dim3 b2(32, 8), g2(mbs::cdiv(W, 32), mbs::cdiv(H, 8));
-    ccl_init_kernel<<<nb, 256, 0, stream>>>(fg, n, roots);
-    MBS_CHECK_LAUNCH();
+    if (!roots_initialised) {
+        ccl_init_kernel<<<nb, 256, 0, stream>>>(fg, n, roots);
+        MBS_CHECK_LAUNCH();
+    }
     ccl_merge8_kernel<<<g2, b2, 0, stream>>>(fg, H, W, roots);
     MBS_CHECK_LAUNCH();
-    ccl_compress_kernel<<<nb, 256, 0, stream>>>(n, roots);
-    MBS_CHECK_LAUNCH();
     MBS_CHECK_CUDA(cudaMemsetAsync(area, 0, static_cast<size_t>(n) * 4, stream));
-    area_kernel<<<nb, 256, 0, stream>>>(roots, n, area, st);
+    compress_area_kernel<<<nb, 256, 0, stream>>>(roots, n, area, st);
     MBS_CHECK_LAUNCH();
-    (void)filter;
     const int tiles = mbs::cdiv(n, SCAN_TILE);
     rank_count_kernel<<<tiles, SCAN_THREADS, 0, stream>>>(roots, area, n, st, use_mean, tile_cnt);
     MBS_CHECK_LAUNCH();
@@ -679,14 +699,16 @@ int run_label_rank(const uint8_t *fg, int H, int W, int *roots, int *area, int *
 
 int run_watershed(const float *img, int negate, const int *markers, const uint8_t *mask, int H, int W, int *lab,
                   float *Lv, int *parent, int *uf, int *src, HeapItem *heap, Stats *st, uint8_t *tile_changed,
-                  int force_sequential, cudaStream_t stream) {
+                  int force_sequential, int lv_initialised, uint16_t *out16, cudaStream_t stream) {
     const int n = H * W;
     const int nb = mbs::cdiv(n, 256);
     dim3 b2(32, 8), g2(mbs::cdiv(W, 32), mbs::cdiv(H, 8));
     dim3 gr(mbs::cdiv(W, RT), mbs::cdiv(H, RT));
     if (!force_sequential) {
-        ws_init_kernel<<<nb, 256, 0, stream>>>(img, negate, markers, mask, n, Lv);
-        MBS_CHECK_LAUNCH();
+        if (!lv_initialised) {
+            ws_init_kernel<<<nb, 256, 0, stream>>>(img, negate, markers, mask, n, Lv);
+            MBS_CHECK_LAUNCH();
+        }
         // all sweeps in one cooperative launch; convergence is detected on the device
         {
             static int coop_blocks = 0;
@@ -713,10 +735,10 @@ int run_watershed(const float *img, int negate, const int *markers, const uint8_
         MBS_CHECK_LAUNCH();
         ws_label_kernel<<<nb, 256, 0, stream>>>(parent, uf, src, markers, n, lab);
         MBS_CHECK_LAUNCH();
-        ws_check_kernel<<<g2, b2, 0, stream>>>(Lv, parent, lab, H, W, st);
+        ws_check_kernel<<<g2, b2, 0, stream>>>(Lv, parent, lab, H, W, st, out16);
         MBS_CHECK_LAUNCH();
     }
-    ws_sequential_kernel<<<1, 32, 0, stream>>>(img, negate, markers, mask, H, W, lab, heap, st, force_sequential);
+    ws_sequential_kernel<<<1, 32, 0, stream>>>(img, negate, markers, mask, H, W, lab, heap, st, force_sequential, out16);
     MBS_CHECK_LAUNCH();
     return 0;
 }
@@ -744,7 +766,7 @@ extern "C" int mbs_pp_front(const float *border, const float *cell, int H, int W
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     MBS_REQUIRE(H > 0 && W > 0 && ld >= W, "pp_front: bad shape H=%d W=%d ld=%d", H, W, ld);
     dim3 grid(mbs::cdiv(W, FT), mbs::cdiv(H, FT));
-    pp_front_kernel<<<grid, 256, 0, stream>>>(border, cell, H, W, ld, th_seed, th_cell, cell_smooth, mask, seed);
+    pp_front_kernel<<<grid, 256, 0, stream>>>(border, cell, H, W, ld, th_seed, th_cell, cell_smooth, mask, seed, nullptr);
     MBS_CHECK_LAUNCH();
     return 0;
 }
@@ -814,7 +836,7 @@ extern "C" int mbs_pp_watershed(const float *image, const int32_t *markers, cons
     MBS_REQUIRE(hp != nullptr, "watershed: cannot allocate pinned host memory");
     MBS_CHECK_CUDA(cudaMemsetAsync(st, 0, sizeof(Stats), stream));
     int rc = run_watershed(image, 0, markers, mask, H, W, labels_out, Lv, parent, uf, src, heap, st, tile_changed,
-                           force_sequential, stream);
+                           force_sequential, /*lv_initialised=*/0, nullptr, stream);
     if (rc) return rc;
     if (info_host) {
         MBS_CHECK_CUDA(cudaMemcpyAsync(hp, st, sizeof(Stats), cudaMemcpyDeviceToHost, stream));
@@ -862,17 +884,15 @@ extern "C" int mbs_distance_postprocessing(const float *border, const float *cel
 
     MBS_CHECK_CUDA(cudaMemsetAsync(st, 0, sizeof(Stats), stream));
     dim3 grid(mbs::cdiv(W, FT), mbs::cdiv(H, FT));
-    pp_front_kernel<<<grid, 256, 0, stream>>>(border, cell, H, W, ld, th_seed, th_cell, cell_s, mask, seed);
+    pp_front_kernel<<<grid, 256, 0, stream>>>(border, cell, H, W, ld, th_seed, th_cell, cell_s, mask, seed, roots);
     MBS_CHECK_LAUNCH();
-    int rc = run_label_rank(seed, H, W, roots, area, rank, tiles, st, /*use_mean=*/1, 1, stream);
+    int rc = run_label_rank(seed, H, W, roots, area, rank, tiles, st, /*use_mean=*/1, /*roots_initialised=*/1, stream);
     if (rc) return rc;
-    markers_kernel<<<nb, 256, 0, stream>>>(roots, rank, mask, nn, markers);
+    markers_kernel<<<nb, 256, 0, stream>>>(roots, rank, mask, nn, markers, cell_s, 1, Lv);
     MBS_CHECK_LAUNCH();
     rc = run_watershed(cell_s, /*negate=*/1, markers, mask, H, W, lab, Lv, parent, uf, src, heap, st, tile_changed, 0,
-                       stream);
+                       /*lv_initialised=*/1, out, stream);
     if (rc) return rc;
-    to_u16_kernel<<<nb, 256, 0, stream>>>(lab, nn, out);
-    MBS_CHECK_LAUNCH();
     if (info_host) {
         MBS_CHECK_CUDA(cudaMemcpyAsync(hp, st, sizeof(Stats), cudaMemcpyDeviceToHost, stream));
         MBS_CHECK_CUDA(cudaStreamSynchronize(stream));
@@ -917,14 +937,13 @@ extern "C" int mbs_boundary_postprocessing(const float *prediction_hwc, int H, i
     MBS_CHECK_CUDA(cudaMemsetAsync(st, 0, sizeof(Stats), stream));
     bp_front_kernel<<<nb, 256, 0, stream>>>(prediction_hwc, nn, img, mask, seed);
     MBS_CHECK_LAUNCH();
-    int rc = run_label_rank(seed, H, W, roots, area, rank, tiles, st, /*use_mean=*/0, 1, stream);   // drop area <= 4
+    int rc = run_label_rank(seed, H, W, roots, area, rank, tiles, st, /*use_mean=*/0, /*roots_initialised=*/0, stream);   // drop area <= 4
     if (rc) return rc;
-    markers_kernel<<<nb, 256, 0, stream>>>(roots, rank, mask, nn, markers);
+    markers_kernel<<<nb, 256, 0, stream>>>(roots, rank, mask, nn, markers, img, 0, Lv);
     MBS_CHECK_LAUNCH();
-    rc = run_watershed(img, /*negate=*/0, markers, mask, H, W, lab, Lv, parent, uf, src, heap, st, tile_changed, 0, stream);
+    rc = run_watershed(img, /*negate=*/0, markers, mask, H, W, lab, Lv, parent, uf, src, heap, st, tile_changed, 0,
+                       /*lv_initialised=*/1, out, stream);
     if (rc) return rc;
-    to_u16_kernel<<<nb, 256, 0, stream>>>(lab, nn, out);
-    MBS_CHECK_LAUNCH();
     if (info_host) {
         MBS_CHECK_CUDA(cudaMemcpyAsync(hp, st, sizeof(Stats), cudaMemcpyDeviceToHost, stream));
         MBS_CHECK_CUDA(cudaStreamSynchronize(stream));
