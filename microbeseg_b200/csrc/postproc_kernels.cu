@@ -300,9 +300,10 @@ rank_assign_kernel(const int *__restrict__ L, const int *__restrict__ area, int 
     int woff = 0;
     for (int w = 0; w < (threadIdx.x >> 5); ++w) woff += s_w[w];
     int run = tile_off[blockIdx.x] + woff + inc - c;
+    // ranks are only ever read at component roots: write the survivors' ranks and zero the dropped roots
     for (int k = 0; k < SCAN_ITEMS; ++k) {
         const int i = base + k;
-        if (i < n) rank[i] = (flags >> k) & 1u ? ++run : 0;
+        if (i < n && L[i] == i) rank[i] = (flags >> k) & 1u ? ++run : 0;
     }
 }
 

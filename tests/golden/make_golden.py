@@ -2,6 +2,7 @@
 
   python tests/golden/make_golden.py postproc     # oracle/postproc.py on seeded synthetic maps
   python tests/golden/make_golden.py net          # the REAL reference DUNet (/root/reference) on CPU
+  python tests/golden/make_golden.py labels       # oracle/labels.py on seeded synthetic instance masks
 
 The post-processing goldens are produced by the oracle restatement (scikit-image cannot run in
 this image -> "parity unpinned" for the skimage pieces, see oracle/postproc.py); the network
@@ -59,9 +60,22 @@ def make_net():
         print("net", tag, float(border.abs().max()), float(cell.abs().max()))
 
 
+def make_labels():
+    from microbeseg_b200 import synthetic as sy
+    from oracle import labels as ol
+    for H, W, n, seed in [(128, 128, 22, 31), (96, 160, 30, 32)]:
+        m = sy.synth_instance_mask(H, W, n, seed, (9.0, 16.0), (7.0, 12.0)).astype(np.uint16)
+        (cd, nd), mal = ol.create_labels(m)
+        np.savez_compressed(os.path.join(HERE, f"labels_{H}x{W}_s{seed}.npz"), mask=m, cell_dist=cd, neighbor_dist=nd,
+                            max_mal=mal)
+        print("labels", H, W, seed, "max_mal", mal, "cells", int(m.max()))
+
+
 if __name__ == "__main__":
-    what = sys.argv[1:] or ["postproc", "net"]
+    what = sys.argv[1:] or ["postproc", "net", "labels"]
     if "postproc" in what:
         make_postproc()
     if "net" in what:
         make_net()
+    if "labels" in what:
+        make_labels()

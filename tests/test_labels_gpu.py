@@ -77,3 +77,13 @@ def test_batch_create_labels_matches_per_crop(lab):
         (rc, rn), mal = ol.create_labels(masks[i])
         assert int(mals[i]) == mal
         _check((cells[i], neighs[i]), (rc, rn), f"crop {i}")
+
+
+def test_golden_fixtures(lab):
+    import glob
+    import os
+    for f in sorted(glob.glob(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "labels_*.npz"))):
+        g = np.load(f)
+        cells, neighs, mals = lab.create_labels(g["mask"])
+        assert int(mals[0]) == int(g["max_mal"])
+        _check((cells[0], neighs[0]), (g["cell_dist"], g["neighbor_dist"]), f)
