@@ -41,7 +41,8 @@ int mbs_debug_flags(int reset);
 /* ---------------------------------------------------------------------------------------- */
 enum { MBS_ACT_NONE = 0, MBS_ACT_RELU = 1, MBS_ACT_LEAKYRELU = 2, MBS_ACT_ELU = 3, MBS_ACT_MISH = 4 };
 enum { MBS_IN_U8 = 0, MBS_IN_U16 = 1, MBS_IN_F32 = 2 };
-enum { MBS_CONV3X3_S1 = 0, MBS_CONV3X3_S2 = 1, MBS_CONVT2X2_S2 = 2 };
+enum { MBS_CONV3X3_S1 = 0, MBS_CONV3X3_S2 = 1, MBS_CONVT2X2_S2 = 2, MBS_CONV2X2_S2 = 3 /* 2x2 stride-2 conv: data
+       gradient of the transposed conv; weights packed [Cout][4][Cin] */ };
 
 /*
  * First encoder conv fused with min-max normalisation and top/left padding.
@@ -127,6 +128,43 @@ int mbs_pp_label8(const uint8_t *binary, int H, int W, int32_t *labels, int32_t 
 int mbs_pp_watershed(const float *image, const int32_t *markers, const uint8_t *mask, int H, int W,
                      int32_t *labels_out, void *workspace, size_t workspace_bytes,
                      int64_t *info_host, int force_sequential, void *stream);
+
+/* ---------------------------------------------------------------------------------------- */
+/* training step (replaces torch autograd + cuDNN/ATen in src/training/train.py:460-493)     */
+/* activations / activation gradients NHWC bf16; statistics and parameter gradients fp32      */
+/* ---------------------------------------------------------------------------------------- */
+/* BatchNorm2d, training mode (unets.py:128,153,206,246): batch mean / biased variance over the M = N*H*W rows of
+ * a [M][C]; y = gamma*(a-mean)*invstd + beta.  sums_scratch: 2*C floats; var_unbiased (optional) feeds running_var. */
+int mbs_bn_train_fwd(const void *a, long long M, int C, const float *gamma, const float *beta, float eps, void *y,
+                     float *sums_scratch, float *mean, float *invstd, float *var_unbiased, void *stream);
+/* backward of  y = BN(act(z)):  dz = act'(a) * gamma*invstd*(dy - dbeta/M - xhat*dgamma/M);  dgamma_dbeta: [2*C]
+ * (dgamma then dbeta), dbias[c] = sum dz (gradient of the conv bias).  act: MBS_ACT_RELU or MBS_ACT_NONE. */
+int mbs_bn_train_bwd(const void *dy, const void *a, long long M, int C, const float *mean, const float *invstd,
+                     const float *gamma, int act, void *dz, float *dgamma_dbeta, float *dbias, void *stream);
+/* Conv2d(C,1,1) head, SmoothL1Loss(beta=1,'mean') (losses.py:30-32) and their gradients */
+int mbs_head_fwd(const void *y, long long M, int C, const float *w, float b, float *pred, void *stream);
+int mbs_smoothl1(const float *pred, const float *target, long long M, float *loss_accum, float *grad, void *stream);
+int mbs_head_bwd(const float *g, const void *y, long long M, int C, const float *w, void *dy, float *dw_db, void *stream);
+/* layout / glue kernels of the backward pass */
+/* dst[n][c][y][x] = src[n][y][x*step_x + shift_x][c] (0 outside), dst row pitch `pitch` elements: TMA row starts must
+ * be 16-byte aligned and a swizzled box row is at most 128 bytes, so the horizontal tap shifts (and the column
+ * decimation of stride-2 layers) of the weight gradient are baked into channel-major copies */
+int mbs_nhwc_to_chw(const void *src, int N, int H, int W, int C, int pitch, int shift_x, int step_x, void *dst,
+                    void *stream);
+int mbs_zero_insert_up2(const void *src, int N, int H, int W, int C, void *dst, void *stream);
+int mbs_add3_bf16(const void *a, const void *b, const void *c, long long n, void *out, void *stream);
+int mbs_first_conv_wgrad(const float *x, const void *dz, int N, int H, int W, int C, float *dw, void *stream);
+/* weight gradient on the tensor cores: out[m][tap][out_coff + n] += sum_pixels At[m][..] * Bt[n][..]; operands are
+ * channel-major bf16 copies [N][C][H][pitch] (mbs_nhwc_to_chw).  kind 0/1: conv3x3 stride 1/2 (At = dz^T on the
+ * Ho x Wo output grid, Bt = x^T, three x-shifts); kind 2: transposed conv 2x2 (At = d(up)^T on the 2Ho x 2Wo grid,
+ * shifts 0 / +1, Bt = x^T). */
+typedef struct {
+    int kind, N, Ho, Wo;
+    const void *At[3]; int Cm, pitchA;     /* x-shifted copies: [0] shift -1, [1] shift 0, [2] shift +1 (NULL if unused) */
+    const void *Bt[3]; int Cn, pitchB;
+    float *out; int out_ld, out_coff;
+} mbs_wgrad_desc;
+int mbs_conv_wgrad(const mbs_wgrad_desc *d, void *stream);
 
 /* ---------------------------------------------------------------------------------------- */
 /* training-label generation, distance method (replaces src/training/train_data_representations */

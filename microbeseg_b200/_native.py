@@ -25,6 +25,14 @@ class ConvDesc(ctypes.Structure):
                 ("head_w", c_void_p), ("head_b", c_float * 4), ("head_n", c_int), ("head_out", c_void_p)]
 
 
+class WgradDesc(ctypes.Structure):
+    """mirror of mbs_wgrad_desc (include/mbseg.h)"""
+    _fields_ = [("kind", c_int), ("N", c_int), ("Ho", c_int), ("Wo", c_int),
+                ("At", c_void_p * 3), ("Cm", c_int), ("pitchA", c_int),
+                ("Bt", c_void_p * 3), ("Cn", c_int), ("pitchB", c_int),
+                ("out", c_void_p), ("out_ld", c_int), ("out_coff", c_int)]
+
+
 _SIGS = {
     "mbs_last_error": (ctypes.c_char_p, []),
     "mbs_version": (c_int, []),
@@ -47,6 +55,18 @@ _SIGS = {
     "mbs_labels_max_mal": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
     "mbs_distance_labels": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
                                     c_void_p, c_void_p, c_size_t, c_void_p]),
+    "mbs_bn_train_fwd": (c_int, [c_void_p, ctypes.c_longlong, c_int, c_void_p, c_void_p, c_float, c_void_p, c_void_p,
+                                 c_void_p, c_void_p, c_void_p, c_void_p]),
+    "mbs_bn_train_bwd": (c_int, [c_void_p, c_void_p, ctypes.c_longlong, c_int, c_void_p, c_void_p, c_void_p, c_int,
+                                 c_void_p, c_void_p, c_void_p, c_void_p]),
+    "mbs_head_fwd": (c_int, [c_void_p, ctypes.c_longlong, c_int, c_void_p, c_float, c_void_p, c_void_p]),
+    "mbs_smoothl1": (c_int, [c_void_p, c_void_p, ctypes.c_longlong, c_void_p, c_void_p, c_void_p]),
+    "mbs_head_bwd": (c_int, [c_void_p, c_void_p, ctypes.c_longlong, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "mbs_nhwc_to_chw": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "mbs_zero_insert_up2": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "mbs_add3_bf16": (c_int, [c_void_p, c_void_p, c_void_p, ctypes.c_longlong, c_void_p, c_void_p]),
+    "mbs_first_conv_wgrad": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "mbs_conv_wgrad": (c_int, [ctypes.POINTER(WgradDesc), c_void_p]),
     "mbs_pp_watershed": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_size_t, c_void_p,
                                  c_int, c_void_p]),
 }

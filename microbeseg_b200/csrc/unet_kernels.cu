@@ -588,6 +588,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                     } else if (p.mode == MBS_CONV3X3_S2) {
                         cx = 2 * x0 + (tap % 3) - 1;
                         cy = 2 * y0 + (tap / 3) - 1;
+                    } else if (p.mode == MBS_CONV2X2_S2) {
+                        cx = 2 * x0 + (tap & 1);
+                        cy = 2 * y0 + (tap >> 1);
                     } else {
                         cx = x0;
                         cy = y0;
@@ -840,6 +843,141 @@ conv_halo64_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
     if (warp == 1) {
         tcgen05_fence_after();
         tmem_dealloc(tmem_base, 2 * BN);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Weight gradient: G[m][tap][n] += sum over pixels of At[img][m][sA*o + offA(tap)] * Bt[img][n][sB*o + offB(tap)].
+//
+// Both operands are channel-major ("NCHW", row pitch padded to 16 B) bf16 copies, so the contraction
+// index (pixels along an image row) is contiguous and the SAME K-major SWIZZLE_128B UMMA descriptors as in
+// the forward kernel apply: A tile = 128 channels x 64 pixels, B tile = BN channels x 64 pixels, each one 4-D
+// TMA box whose out-of-bounds pixels are zero-filled (= the conv's zero padding; also the row tails).
+// conv3x3:  A = dz^T (stride 1, no offset), B = x^T (stride s, offset tap-1);  convT2x2: A = dup^T (stride 2,
+// offset (dy,dx)), B = x^T.  One CTA = one (m-tile, n-tile, tap, K-split) and adds its fp32 tile into G with
+// atomics (split-K over image rows fills the machine for the thin full-resolution layers).
+// ------------------------------------------------------------------------------------------
+struct WgradParams {
+    int N, Ho, Wo;
+    int sA, sB;
+    int offAy[9], offBy[9];    // row offsets per tap
+    int selA[9], selB[9];      // which x-shifted copy (0: -1, 1: 0, 2: +1) per tap -- TMA needs 16-byte aligned row starts,
+                               // so horizontal shifts are baked into pre-shifted channel-major copies
+    int taps;
+    int M_total, N_total;
+    int m_tiles, n_tiles, splits;
+    float *out;
+    int out_ld, out_coff;      // G row = m, then tap, then out_ld columns; this call fills columns [out_coff, out_coff+N_total)
+};
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+wgrad_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
+             const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB0,
+             const __grid_constant__ CUtensorMap tmB1, const __grid_constant__ CUtensorMap tmB2, const WgradParams p) {
+    constexpr int B_BYTES = BN * BK * 2;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t base = (raw + 1023u) & ~1023u;
+    uint8_t *gbase = smem_raw + (base - raw);
+    const uint32_t sA = base;
+    const uint32_t sB = base + STAGES * A_BYTES;
+    const uint32_t sBar = sB + STAGES * B_BYTES;
+    auto full_bar = [&](int s) { return sBar + 8u * s; };
+    auto empty_bar = [&](int s) { return sBar + 8u * (STAGES + s); };
+    const uint32_t tfull_bar = sBar + 8u * (2 * STAGES);
+    volatile uint32_t *tmem_ptr = reinterpret_cast<volatile uint32_t *>(gbase + STAGES * (A_BYTES + B_BYTES) + 8 * (2 * STAGES + 1));
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    int t = blockIdx.x;
+    const int split = t % p.splits; t /= p.splits;
+    const int tap = t % p.taps; t /= p.taps;
+    const int n_tile = t % p.n_tiles;
+    const int m_tile = t / p.n_tiles;
+    const int m0 = m_tile * BM, n0 = n_tile * BN;
+    const int rows_total = p.N * p.Ho;
+    const int rows_per = (rows_total + p.splits - 1) / p.splits;
+    const int r0 = split * rows_per;
+    const int r1 = min(rows_total, r0 + rows_per);
+    const int xchunks = (p.Wo + BK - 1) / BK;
+    const int num_k_iters = max(0, r1 - r0) * xchunks;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(full_bar(s), 1);
+            mbar_init(empty_bar(s), 1);
+        }
+        mbar_init(tfull_bar, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(smem_u32(const_cast<uint32_t *>(tmem_ptr)), BN);
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    if (num_k_iters > 0) {
+        if (warp == 0) {
+            if (lane == 0) {
+                const CUtensorMap *mapA = p.selA[tap] == 0 ? &tmA0 : (p.selA[tap] == 1 ? &tmA1 : &tmA2);
+                const CUtensorMap *mapB = p.selB[tap] == 0 ? &tmB0 : (p.selB[tap] == 1 ? &tmB1 : &tmB2);
+                int it = 0;
+                for (int r = r0; r < r1; ++r) {
+                    const int img = r / p.Ho, oy = r - img * p.Ho;
+                    for (int xc = 0; xc < xchunks; ++xc, ++it) {
+                        const int s = it % STAGES;
+                        const uint32_t ph = (it / STAGES) & 1;
+                        mbar_wait(empty_bar(s), ph ^ 1u);
+                        mbar_expect_tx(full_bar(s), A_BYTES + B_BYTES);
+                        const int ox0 = xc * BK;
+                        // columns are pre-shifted / pre-decimated in the channel-major copies; rows use the coordinate
+                        tma_load_4d(sA + s * A_BYTES, mapA, full_bar(s), ox0, p.sA * oy + p.offAy[tap], m0, img);
+                        tma_load_4d(sB + s * B_BYTES, mapB, full_bar(s), ox0, p.sB * oy + p.offBy[tap], n0, img);
+                    }
+                }
+            }
+            __syncwarp();
+        } else if (warp == 1) {
+            if (lane == 0) {
+                constexpr uint32_t idesc = make_idesc(BM, BN);
+                for (int it = 0; it < num_k_iters; ++it) {
+                    const int s = it % STAGES;
+                    const uint32_t ph = (it / STAGES) & 1;
+                    mbar_wait(full_bar(s), ph);
+                    tcgen05_fence_after();
+                    const uint64_t adesc = make_sw128_desc(sA + s * A_BYTES);
+                    const uint64_t bdesc = make_sw128_desc(sB + s * B_BYTES);
+#pragma unroll
+                    for (int k = 0; k < BK / 16; ++k)
+                        umma_f16(tmem_base, adesc + 2u * k, bdesc + 2u * k, idesc, (it > 0 || k > 0) ? 1u : 0u);
+                    umma_commit(empty_bar(s));
+                }
+                umma_commit(tfull_bar);
+            }
+            __syncwarp();
+        } else {
+            const int e = warp - 2, quad = warp & 3, half = e >> 2;
+            const int m = m0 + quad * 32 + lane;
+            mbar_wait(tfull_bar, 0);
+            tcgen05_fence_after();
+#pragma unroll 1
+            for (int c = half * (BN / 2); c < (half + 1) * (BN / 2); c += 32) {
+                uint32_t r[32];
+                tmem_ld32(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(c), r);
+                if (m < p.M_total) {
+                    float *dst = p.out + (static_cast<size_t>(m) * p.taps + tap) * p.out_ld + p.out_coff + n0 + c;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        if (n0 + c + j < p.N_total) atomicAdd(dst + j, __uint_as_float(r[j]));
+                }
+            }
+            tcgen05_fence_before();
+        }
+    }
+    __syncthreads();
+    if (warp == 1) {
+        tcgen05_fence_after();
+        tmem_dealloc(tmem_base, BN);
     }
 }
 
@@ -1103,6 +1241,39 @@ int launch_conv(const CUtensorMap &a0, const CUtensorMap &a1, const CUtensorMap 
     return 0;
 }
 
+// channel-major ("NCHW", padded row pitch) bf16 tensor -> 4-D map (W, H, C, N), box (64*es, 1, rows, 1)
+int make_chw_map(CUtensorMap *map, const void *base, int N, int C, int H, int W, int pitch, int es, int rows) {
+    EncodeTiledFn enc = get_encode_fn();
+    MBS_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled entry point not available (no CUDA driver?)");
+    MBS_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0 && (pitch * 2) % 16 == 0 && pitch >= W,
+                "channel-major tensor needs 16-byte aligned base and row pitch");
+    cuuint64_t dims[4] = {static_cast<cuuint64_t>(W), static_cast<cuuint64_t>(H), static_cast<cuuint64_t>(C),
+                          static_cast<cuuint64_t>(N)};
+    cuuint64_t strides[3] = {static_cast<cuuint64_t>(pitch) * 2, static_cast<cuuint64_t>(H) * pitch * 2,
+                             static_cast<cuuint64_t>(C) * H * pitch * 2};
+    cuuint32_t box[4] = {static_cast<cuuint32_t>(BK * es), 1, static_cast<cuuint32_t>(rows), 1};
+    cuuint32_t estr[4] = {static_cast<cuuint32_t>(es), 1, 1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void *>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    MBS_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(channel-major N=%d C=%d H=%d W=%d pitch=%d es=%d) failed: %d", N, C,
+                H, W, pitch, es, static_cast<int>(r));
+    return 0;
+}
+
+template <int BN, int STAGES>
+int launch_wgrad(const CUtensorMap *a, const CUtensorMap *b, const WgradParams &wp, int grid, cudaStream_t stream) {
+    constexpr int dyn = STAGES * (A_BYTES + BN * BK * 2) + 8 * (2 * STAGES + 1) + 16 + 1024;
+    static bool configured = false;
+    if (!configured) {
+        MBS_CHECK_CUDA(cudaFuncSetAttribute(wgrad_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn));
+        configured = true;
+    }
+    wgrad_kernel<BN, STAGES><<<grid, NUM_THREADS, dyn, stream>>>(a[0], a[1], a[2], b[0], b[1], b[2], wp);
+    MBS_CHECK_LAUNCH();
+    return 0;
+}
+
 template <int CHUNKS, int STAGES>
 int launch_halo(const CUtensorMap &a0, const CUtensorMap &a1, const CUtensorMap &b, const CUtensorMap &dmap,
                 const ConvKParams &kp, cudaStream_t stream) {
@@ -1133,12 +1304,13 @@ bool halo_enabled() {
 extern "C" int mbs_conv_gemm(const mbs_conv_desc *d, void *stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     MBS_REQUIRE(d != nullptr, "null descriptor");
-    MBS_REQUIRE(d->mode >= 0 && d->mode <= 2, "bad conv mode %d", d->mode);
+    MBS_REQUIRE(d->mode >= 0 && d->mode <= 3, "bad conv mode %d", d->mode);
     MBS_REQUIRE(d->C0 > 0 && d->C0 % BK == 0 && d->C1 >= 0 && d->C1 % BK == 0,
                 "input channels must be multiples of %d (got %d + %d)", BK, d->C0, d->C1);
     MBS_REQUIRE(d->Cout > 0 && d->Cout % 64 == 0, "Cout must be a multiple of 64 (got %d)", d->Cout);
     MBS_REQUIRE(d->mode != MBS_CONVT2X2_S2 || d->C1 == 0, "transposed conv takes a single source");
-    MBS_REQUIRE(d->mode != MBS_CONV3X3_S2 || (d->H % 2 == 0 && d->W % 2 == 0), "stride-2 conv needs even H, W");
+    const bool strided = d->mode == MBS_CONV3X3_S2 || d->mode == MBS_CONV2X2_S2;
+    MBS_REQUIRE(!strided || (d->H % 2 == 0 && d->W % 2 == 0), "stride-2 conv needs even H, W");
     MBS_REQUIRE(d->head_out == nullptr ||
                     (d->Cout == 64 && d->mode == MBS_CONV3X3_S1 && d->head_w && d->head_n >= 1 && d->head_n <= 4),
                 "fused head needs Cout == 64, stride-1 conv, head weights and 1 <= head_n <= 4");
@@ -1153,14 +1325,14 @@ extern "C" int mbs_conv_gemm(const mbs_conv_desc *d, void *stream_) {
     memset(&kp, 0, sizeof(kp));
     kp.mode = d->mode;
     kp.act = d->act;
-    const int es = d->mode == MBS_CONV3X3_S2 ? 2 : 1;
-    kp.Hm = d->mode == MBS_CONV3X3_S2 ? d->H / 2 : d->H;
-    kp.Wm = d->mode == MBS_CONV3X3_S2 ? d->W / 2 : d->W;
+    const int es = strided ? 2 : 1;
+    kp.Hm = strided ? d->H / 2 : d->H;
+    kp.Wm = strided ? d->W / 2 : d->W;
     kp.tiles_x = mbs::cdiv(kp.Wm, TILE_W);
     kp.tiles_y = mbs::cdiv(kp.Hm, TILE_H);
     kp.chunks0 = d->C0 / BK;
     kp.chunks1 = d->C1 / BK;
-    kp.taps = d->mode == MBS_CONVT2X2_S2 ? 1 : 9;
+    kp.taps = d->mode == MBS_CONVT2X2_S2 ? 1 : (d->mode == MBS_CONV2X2_S2 ? 4 : 9);
     kp.Cout = d->Cout;
     kp.bias = d->bias;
     kp.scale = d->scale;
@@ -1241,6 +1413,60 @@ extern "C" int mbs_conv_gemm(const mbs_conv_desc *d, void *stream_) {
     // with the TMA-store epilogue (128->128 @1024^2: 0.295 vs 0.378 ms)
     if (bn == 128) return launch_conv<128, 3, 2, false>(a0, a1, b, a0, kp, stream);
     return launch_conv<64, 4, 2, false>(a0, a1, b, a0, kp, stream);
+}
+
+extern "C" int mbs_conv_wgrad(const mbs_wgrad_desc *d, void *stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    MBS_REQUIRE(d != nullptr && d->kind >= 0 && d->kind <= 2, "wgrad: bad descriptor");
+    MBS_REQUIRE(d->Cm > 0 && d->Cn > 0 && d->N > 0 && d->Ho > 0 && d->Wo > 0, "wgrad: bad shape");
+    WgradParams wp;
+    memset(&wp, 0, sizeof(wp));
+    wp.N = d->N;
+    wp.Ho = d->Ho;
+    wp.Wo = d->Wo;
+    wp.M_total = d->Cm;
+    wp.N_total = d->Cn;
+    wp.out = d->out;
+    wp.out_ld = d->out_ld;
+    wp.out_coff = d->out_coff;
+    int Ha, Wa, Hb, Wb;          // spatial dims of the two channel-major operands
+    if (d->kind == 2) {          // transposed conv 2x2 s2: A = d(up)^T sampled at (2y+dy, 2x+dx), B = x^T
+        wp.taps = 4;
+        wp.sA = 2;
+        wp.sB = 1;
+        for (int q = 0; q < 4; ++q) { wp.offAy[q] = q >> 1; wp.selA[q] = 1 + (q & 1); wp.selB[q] = 1; }
+        Ha = 2 * d->Ho; Wa = d->Wo; Hb = d->Ho; Wb = d->Wo;       // A copies are column-decimated (x' = 2x + dx)
+        MBS_REQUIRE(d->At[1] && d->At[2] && d->Bt[1], "wgrad(convT): needs At shift 0 / +1 and Bt shift 0");
+    } else {                     // conv 3x3, stride 1 or 2, padding 1: A = dz^T, B = x^T shifted by the tap
+        wp.taps = 9;
+        wp.sA = 1;
+        wp.sB = d->kind == 1 ? 2 : 1;
+        for (int t = 0; t < 9; ++t) { wp.offBy[t] = t / 3 - 1; wp.selB[t] = t % 3; wp.selA[t] = 1; }
+        Ha = d->Ho; Wa = d->Wo; Hb = wp.sB * d->Ho; Wb = d->Wo;   // stride 2: B copies are column-decimated (2x + kx - 1)
+        MBS_REQUIRE(d->At[1] && d->Bt[0] && d->Bt[1] && d->Bt[2], "wgrad(conv): needs At shift 0 and Bt shifts -1 / 0 / +1");
+    }
+    const int bn = d->Cn % 256 == 0 ? 256 : (d->Cn % 128 == 0 ? 128 : 64);
+    wp.m_tiles = mbs::cdiv(d->Cm, BM);
+    wp.n_tiles = mbs::cdiv(d->Cn, bn);
+    const int tiles = wp.m_tiles * wp.n_tiles * wp.taps;
+    const int rows_total = d->N * d->Ho;
+    int splits = mbs::cdiv(3 * sm_count(), tiles);
+    if (splits > rows_total) splits = rows_total;
+    if (splits < 1) splits = 1;
+    wp.splits = splits;
+    CUtensorMap a[3], b[3];
+    for (int k = 0; k < 3; ++k) {
+        const void *pa = d->At[k] ? d->At[k] : d->At[1];
+        const void *pb = d->Bt[k] ? d->Bt[k] : d->Bt[1];
+        int rc = make_chw_map(&a[k], pa, d->N, d->Cm, Ha, Wa, d->pitchA, 1, BM);
+        if (rc) return rc;
+        rc = make_chw_map(&b[k], pb, d->N, d->Cn, Hb, Wb, d->pitchB, 1, bn);
+        if (rc) return rc;
+    }
+    const int grid = tiles * splits;
+    if (bn == 256) return launch_wgrad<256, 4>(a, b, wp, grid, stream);
+    if (bn == 128) return launch_wgrad<128, 6>(a, b, wp, grid, stream);
+    return launch_wgrad<64, 8>(a, b, wp, grid, stream);
 }
 
 extern "C" int mbs_first_conv(const void *img, int in_dtype, int H, int W, int pad_y, int pad_x, float norm_lo,

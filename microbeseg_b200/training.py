@@ -1,0 +1,380 @@
+"""Training step of the distance U-Net on the CUDA path (no autograd, no cuDNN).
+
+Mirrors the numerical part of the reference's inner loop (src/training/train.py:460-493):
+``zero_grad -> net(img) -> SmoothL1(border) + SmoothL1(cell) -> backward -> optimizer.step`` for the published
+configuration (DU net, conv pooling, BatchNorm, ReLU, ``smooth_l1``).  Forward and backward convolutions run on
+the tcgen05 kernels of libmbseg (forward / data-gradient: ``mbs_conv_gemm``; weight-gradient: ``mbs_conv_wgrad``);
+BatchNorm (batch statistics), ReLU', the 1x1 heads and the loss are the kernels of ``train_kernels.cu``.
+Activations and activation gradients are bf16 (fp32 accumulation), parameters / parameter gradients fp32
+("bf16 autocast with fp32 master weights").  The optimizer is the reference's own ``torch.optim.Adam`` and the
+gradient exchange is one NCCL all-reduce over a flat fp32 buffer (replaces nn.DataParallel, unets.py:51-52);
+BatchNorm statistics stay per rank, as with DataParallel.
+"""
+import ctypes
+
+import torch
+
+from . import _native as nat
+
+BN_EPS = 1e-5
+BN_MOMENTUM = 0.1
+ACT_NONE, ACT_RELU = 0, 1
+
+
+def _pitch(w):
+    return (w + 7) // 8 * 8
+
+
+class _Layer:
+    __slots__ = ("name", "kind", "conv", "bn", "act", "srcs", "a", "y", "mean", "invstd", "geom", "x_f32")
+
+
+class TrainEngine:
+    """Forward + backward of one DUNet on one GPU; fills ``param.grad`` (fp32) for every parameter."""
+
+    def __init__(self, net):
+        from .unets import DUNet
+        if not isinstance(net, DUNet):
+            raise NotImplementedError("training is built for the DU (distance) network")
+        net._check_supported()
+        if net.act_fun != "relu":
+            raise NotImplementedError("training on the CUDA path supports act_fun='relu' (Adam recipe, train.py:174)")
+        self.net = net
+        self.L = nat.lib()
+        self.dev = next(net.parameters()).device
+        if self.dev.type != "cuda":
+            raise RuntimeError("microbeseg_b200.training needs a CUDA device (no CPU fallback)")
+        self.chans = net._chans
+        self._const = {}
+        self._scratch = torch.empty(4 * 2048, dtype=torch.float32, device=self.dev)
+
+    # ---- small helpers ------------------------------------------------------------------------
+    def _ones(self, c):
+        k = ("1", c)
+        if k not in self._const:
+            self._const[k] = torch.ones(c, dtype=torch.float32, device=self.dev)
+        return self._const[k]
+
+    def _zeros(self, c):
+        k = ("0", c)
+        if k not in self._const:
+            self._const[k] = torch.zeros(c, dtype=torch.float32, device=self.dev)
+        return self._const[k]
+
+    def _sp(self):
+        return nat.stream_ptr()
+
+    def _pack3x3(self, w):
+        cout, cin = w.shape[0], w.shape[1]
+        out = torch.empty((cout, 9, cin), dtype=torch.bfloat16, device=self.dev)
+        nat.check(self.L.mbs_pack_conv3x3_weight(w.data_ptr(), cout, cin, out.data_ptr(), self._sp()))
+        return out
+
+    def _conv(self, mode, n, h, w, srcs, packed, cout, bias, act, dst):
+        d = nat.ConvDesc()
+        d.mode, d.N, d.H, d.W = mode, n, h, w
+        s0 = srcs[0]
+        d.src0, d.C0, d.ld0, d.coff0 = s0.data_ptr(), s0.shape[-1], s0.shape[-1], 0
+        if len(srcs) > 1:
+            s1 = srcs[1]
+            d.src1, d.C1, d.ld1, d.coff1 = s1.data_ptr(), s1.shape[-1], s1.shape[-1], 0
+        else:
+            d.src1, d.C1, d.ld1, d.coff1 = None, 0, 0, 0
+        d.weight, d.Cout = packed.data_ptr(), cout
+        d.bias, d.scale, d.shift = bias.data_ptr(), self._ones(cout).data_ptr(), self._zeros(cout).data_ptr()
+        d.act = act
+        d.dst, d.ldd, d.coffd = dst.data_ptr(), dst.shape[-1], 0
+        d.head_w, d.head_n, d.head_out = None, 0, None
+        nat.check(self.L.mbs_conv_gemm(ctypes.byref(d), self._sp()), "conv_gemm(train)")
+
+    def _bn_fwd(self, lay):
+        a, bn = lay.a, lay.bn
+        c = a.shape[-1]
+        m = a.numel() // c
+        lay.y = torch.empty_like(a)
+        lay.mean = torch.empty(c, dtype=torch.float32, device=self.dev)
+        lay.invstd = torch.empty(c, dtype=torch.float32, device=self.dev)
+        var_u = torch.empty(c, dtype=torch.float32, device=self.dev)
+        nat.check(self.L.mbs_bn_train_fwd(a.data_ptr(), m, c, bn.weight.data_ptr(), bn.bias.data_ptr(), BN_EPS,
+                                          lay.y.data_ptr(), self._scratch.data_ptr(), lay.mean.data_ptr(),
+                                          lay.invstd.data_ptr(), var_u.data_ptr(), self._sp()), "bn_train_fwd")
+        with torch.no_grad():      # running statistics, torch defaults (momentum 0.1, unbiased variance)
+            bn.running_mean.mul_(1 - BN_MOMENTUM).add_(lay.mean, alpha=BN_MOMENTUM)
+            bn.running_var.mul_(1 - BN_MOMENTUM).add_(var_u, alpha=BN_MOMENTUM)
+            bn.num_batches_tracked += 1
+
+    def _chw(self, t, shift=0, step=1):
+        """channel-major bf16 copy [N][C][H][pitch] of an NHWC tensor, columns shifted by ``shift`` (operand layout of the
+        weight gradient; TMA row starts must be 16-byte aligned, so horizontal tap shifts are pre-applied)."""
+        n, h, w, c = t.shape
+        p = _pitch((w + step - 1) // step)
+        out = torch.empty((n, c, h, p), dtype=torch.bfloat16, device=self.dev)
+        nat.check(self.L.mbs_nhwc_to_chw(t.data_ptr(), n, h, w, c, p, shift, step, out.data_ptr(), self._sp()), "nhwc_to_chw")
+        return out
+
+    def _chw_cached(self, t, shift=0, step=1):
+        k = (t.data_ptr(), shift, step)
+        if k not in self._chw_cache:
+            self._chw_cache[k] = (self._chw(t, shift, step), t)    # keep ``t`` alive: the key is its address
+        return self._chw_cache[k][0]
+
+    def _wgrad(self, kind, n, ho, wo, ats, cm, bts, cn, out, out_ld, out_coff):
+        """ats / bts: dicts shift -> channel-major tensor."""
+        d = nat.WgradDesc()
+        d.kind, d.N, d.Ho, d.Wo = kind, n, ho, wo
+        for sh in (-1, 0, 1):
+            d.At[sh + 1] = ats[sh].data_ptr() if sh in ats else None
+            d.Bt[sh + 1] = bts[sh].data_ptr() if sh in bts else None
+        d.Cm, d.pitchA = cm, ats[0].shape[-1]
+        d.Cn, d.pitchB = cn, bts[0].shape[-1]
+        d.out, d.out_ld, d.out_coff = out.data_ptr(), out_ld, out_coff
+        nat.check(self.L.mbs_conv_wgrad(ctypes.byref(d), self._sp()), "conv_wgrad")
+
+    # ---- forward ------------------------------------------------------------------------------
+    def _fwd_conv(self, name, conv, bn, srcs, stride=1):
+        lay = _Layer()
+        lay.name, lay.kind, lay.conv, lay.bn, lay.act, lay.srcs = name, ("s2" if stride == 2 else "s1"), conv, bn, ACT_RELU, srcs
+        n, h, w = srcs[0].shape[:3]
+        cout = conv.weight.shape[0]
+        ho, wo = (h // 2, w // 2) if stride == 2 else (h, w)
+        lay.a = torch.empty((n, ho, wo, cout), dtype=torch.bfloat16, device=self.dev)
+        self._conv(1 if stride == 2 else 0, n, h, w, srcs, self._pack3x3(conv.weight.detach().float().contiguous()), cout,
+                   conv.bias.detach().float(), ACT_RELU, lay.a)
+        self._bn_fwd(lay)
+        self.tape.append(lay)
+        return lay
+
+    def _fwd_first(self, conv, bn, x):
+        lay = _Layer()
+        lay.name, lay.kind, lay.conv, lay.bn, lay.act, lay.srcs, lay.x_f32 = "enc0a", "first", conv, bn, ACT_RELU, [], x
+        n, h, w = x.shape
+        c = conv.weight.shape[0]
+        lay.a = torch.empty((n, h, w, c), dtype=torch.bfloat16, device=self.dev)
+        wt = conv.weight.detach().float().reshape(c, 9).contiguous()
+        b = conv.bias.detach().float().contiguous()
+        for i in range(n):
+            nat.check(self.L.mbs_first_conv(x[i].data_ptr(), 2, h, w, 0, 0, 1.0, 0.0, None, wt.data_ptr(), b.data_ptr(),
+                                            self._ones(c).data_ptr(), self._zeros(c).data_ptr(), c, ACT_RELU,
+                                            lay.a[i].data_ptr(), c, 0, self._sp()), "first_conv(train)")
+        self._bn_fwd(lay)
+        self.tape.append(lay)
+        return lay
+
+    def _fwd_up(self, name, block, x):
+        lay = _Layer()
+        conv = block.up[0]
+        lay.name, lay.kind, lay.conv, lay.bn, lay.act, lay.srcs = name, "up", conv, block.norm, ACT_NONE, [x]
+        n, h, w, cin = x.shape
+        cout = conv.weight.shape[1]
+        packed = torch.empty((4 * cout, cin), dtype=torch.bfloat16, device=self.dev)
+        wt = conv.weight.detach().float().contiguous()
+        nat.check(self.L.mbs_pack_convT2x2_weight(wt.data_ptr(), cin, cout, packed.data_ptr(), self._sp()))
+        lay.a = torch.empty((n, 2 * h, 2 * w, cout), dtype=torch.bfloat16, device=self.dev)
+        self._conv(2, n, h, w, [x], packed, cout, conv.bias.detach().float(), ACT_NONE, lay.a)
+        self._bn_fwd(lay)
+        self.tape.append(lay)
+        return lay
+
+    def forward_backward(self, img, border_label, cell_label):
+        """img / labels: [N,1,H,W] float32 CUDA tensors (img normalised to [-1,1] as the reference's ToTensor does).
+        Returns the loss (0-d tensor) and leaves the gradients in ``param.grad``."""
+        net = self.net
+        if not net.training:
+            raise RuntimeError("call net.train() before a training step")
+        n, _, H, W = img.shape
+        nl = len(self.chans)
+        if H % (1 << (nl - 1)) or W % (1 << (nl - 1)):
+            raise RuntimeError(f"training crops must be divisible by {1 << (nl - 1)}")
+        self.tape, self._chw_cache = [], {}
+        with torch.cuda.device(self.dev), torch.no_grad():
+            x = img.reshape(n, H, W).contiguous().float()
+            # ---------------- forward ----------------
+            enc_a, enc_b, pools = [], [], []
+            cur = None
+            for l in range(nl):
+                blk = net.encoderConv[l]
+                la = self._fwd_first(blk.conv[0], blk.conv[2], x) if l == 0 else \
+                    self._fwd_conv(f"enc{l}a", blk.conv[0], blk.conv[2], [cur])
+                lb = self._fwd_conv(f"enc{l}b", blk.conv[3], blk.conv[5], [la.y])
+                enc_a.append(la)
+                enc_b.append(lb)
+                if l < nl - 1:
+                    pl = net.pooling[l]
+                    lp = self._fwd_conv(f"pool{l}", pl.conv_pool[0], pl.conv_pool[2], [lb.y], stride=2)
+                    pools.append(lp)
+                    cur = lp.y
+            dec = {}
+            preds, heads, last = [], [], []
+            targets = [border_label, cell_label]
+            for name in net.decoder_names:
+                ups, convs = getattr(net, name + "Upconv"), getattr(net, name + "Conv")
+                xcur = enc_b[nl - 1].y
+                chain = []
+                for i in range(nl - 1):
+                    l = nl - 2 - i
+                    lu = self._fwd_up(f"{name}up{i}", ups[i], xcur)
+                    la = self._fwd_conv(f"{name}c{i}a", convs[i].conv[0], convs[i].conv[2], [lu.y, enc_b[l].y])
+                    lb = self._fwd_conv(f"{name}c{i}b", convs[i].conv[3], convs[i].conv[5], [la.y])
+                    chain.append((lu, la, lb, l))
+                    xcur = lb.y
+                dec[name] = chain
+                head = convs[nl - 1]
+                pred = torch.empty((n, H, W), dtype=torch.float32, device=self.dev)
+                hw = head.weight.detach().float().reshape(-1).contiguous()
+                nat.check(self.L.mbs_head_fwd(xcur.data_ptr(), n * H * W, hw.numel(), hw.data_ptr(), float(head.bias.item()),
+                                              pred.data_ptr(), self._sp()), "head_fwd")
+                preds.append(pred)
+                heads.append((head, hw))
+                last.append(xcur)
+            # ---------------- loss ----------------
+            loss = torch.zeros(1, dtype=torch.float32, device=self.dev)
+            gpred = []
+            for pred, tgt in zip(preds, targets):
+                g = torch.empty_like(pred)
+                t = tgt.reshape(n, H, W).contiguous().float()
+                nat.check(self.L.mbs_smoothl1(pred.data_ptr(), t.data_ptr(), n * H * W, loss.data_ptr(), g.data_ptr(), self._sp()),
+                          "smoothl1")
+                gpred.append(g)
+            # ---------------- backward ----------------
+            skip_grads = [[] for _ in range(nl)]          # contributions to d(skip_l)
+            bott_grads = []
+            for di, name in enumerate(net.decoder_names):
+                head, hw = heads[di]
+                y_last = last[di]
+                c0 = hw.numel()
+                dy = torch.empty_like(y_last)
+                dwdb = torch.empty(c0 + 1, dtype=torch.float32, device=self.dev)
+                nat.check(self.L.mbs_head_bwd(gpred[di].data_ptr(), y_last.data_ptr(), n * H * W, c0, hw.data_ptr(),
+                                              dy.data_ptr(), dwdb.data_ptr(), self._sp()), "head_bwd")
+                head.weight.grad = dwdb[:c0].reshape(head.weight.shape).clone()
+                head.bias.grad = dwdb[c0:].clone()
+                for (lu, la, lb, l) in reversed(dec[name]):
+                    dy = self._bwd_conv(lb, dy)[0]
+                    dup, dskip = self._bwd_conv(la, dy)
+                    skip_grads[l].append(dskip)
+                    dy = self._bwd_up(lu, dup)
+                bott_grads.append(dy)
+            dy = self._sum(bott_grads)
+            for l in range(nl - 1, -1, -1):
+                dy = self._bwd_conv(enc_b[l], dy)[0]
+                if l == 0:
+                    self._bwd_first(enc_a[0], dy)
+                    break
+                dy = self._bwd_conv(enc_a[l], dy)[0]          # gradient w.r.t. pool_{l-1}.y
+                dsk = self._bwd_conv(pools[l - 1], dy)[0]      # ... w.r.t. skip_{l-1}
+                dy = self._sum(skip_grads[l - 1] + [dsk])
+        self.tape, self._chw_cache = [], {}
+        return loss[0]
+
+    # ---- backward pieces ----------------------------------------------------------------------
+    def _sum(self, ts):
+        if len(ts) == 1:
+            return ts[0]
+        out = torch.empty_like(ts[0])
+        c = ts[2] if len(ts) > 2 else None
+        nat.check(self.L.mbs_add3_bf16(ts[0].data_ptr(), ts[1].data_ptr(), c.data_ptr() if c is not None else None,
+                                       ts[0].numel(), out.data_ptr(), self._sp()), "add3")
+        assert len(ts) <= 3
+        return out
+
+    def _bn_bwd(self, lay, dy):
+        a, bn = lay.a, lay.bn
+        c = a.shape[-1]
+        m = a.numel() // c
+        dy = dy.contiguous()
+        dz = torch.empty_like(a)
+        dgb = torch.empty(2 * c, dtype=torch.float32, device=self.dev)
+        dbias = torch.empty(c, dtype=torch.float32, device=self.dev)
+        nat.check(self.L.mbs_bn_train_bwd(dy.data_ptr(), a.data_ptr(), m, c, lay.mean.data_ptr(), lay.invstd.data_ptr(),
+                                          bn.weight.data_ptr(), lay.act, dz.data_ptr(), dgb.data_ptr(), dbias.data_ptr(),
+                                          self._sp()), "bn_train_bwd")
+        bn.weight.grad = dgb[:c].clone()
+        bn.bias.grad = dgb[c:].clone()
+        lay.conv.bias.grad = dbias
+        return dz
+
+    def _bwd_conv(self, lay, dy):
+        """conv3x3 (stride 1 or 2) + ReLU + BN.  Returns the input gradients, one per source."""
+        conv = lay.conv
+        dz = self._bn_bwd(lay, dy)
+        n, ho, wo, cout = dz.shape
+        cins = [s.shape[-1] for s in lay.srcs]
+        cin = sum(cins)
+        stride2 = lay.kind == "s2"
+        # weight gradient: dW[co][tap][ci] (GEMM-packed layout) -> reference layout [Cout,Cin,3,3]
+        dzt = {0: self._chw(dz)}
+        dwp = torch.zeros((cout, 9, cin), dtype=torch.float32, device=self.dev)
+        off = 0
+        for s, cs in zip(lay.srcs, cins):
+            xts = {sh: self._chw_cached(s, sh, 2 if stride2 else 1) for sh in (-1, 0, 1)}
+            self._wgrad(1 if stride2 else 0, n, ho, wo, dzt, cout, xts, cs, dwp, cin, off)
+            off += cs
+        conv.weight.grad = dwp.view(cout, 3, 3, cin).permute(0, 3, 1, 2).contiguous()
+        # data gradient: full-resolution stride-1 conv with the flipped, transposed filter
+        wflip = conv.weight.detach().float().flip(2, 3).transpose(0, 1).contiguous()      # [Cin, Cout, 3, 3]
+        packed = self._pack3x3(wflip)                                                     # [Cin][9][Cout]
+        src = dz
+        h, w = ho, wo
+        if stride2:
+            src = torch.empty((n, 2 * ho, 2 * wo, cout), dtype=torch.bfloat16, device=self.dev)
+            nat.check(self.L.mbs_zero_insert_up2(dz.data_ptr(), n, ho, wo, cout, src.data_ptr(), self._sp()), "zero_insert")
+            h, w = 2 * ho, 2 * wo
+        dx = torch.empty((n, h, w, cin), dtype=torch.bfloat16, device=self.dev)
+        self._conv(0, n, h, w, [src], packed, cin, self._zeros(cin), ACT_NONE, dx)
+        if len(cins) == 1:
+            return [dx]
+        return [dx[..., :cins[0]].contiguous(), dx[..., cins[0]:].contiguous()]
+
+    def _bwd_first(self, lay, dy):
+        conv = lay.conv
+        dz = self._bn_bwd(lay, dy)
+        n, h, w, c = dz.shape
+        dw = torch.empty((c, 9), dtype=torch.float32, device=self.dev)
+        nat.check(self.L.mbs_first_conv_wgrad(lay.x_f32.data_ptr(), dz.data_ptr(), n, h, w, c, dw.data_ptr(), self._sp()),
+                  "first_conv_wgrad")
+        conv.weight.grad = dw.view(conv.weight.shape).clone()
+
+    def _bwd_up(self, lay, dy):
+        """ConvTranspose2d(2,2) + BN (no activation): returns the gradient w.r.t. its input."""
+        conv = lay.conv
+        dup = self._bn_bwd(lay, dy)                        # [N, 2H, 2W, Cout]
+        x = lay.srcs[0]
+        n, h, w, cin = x.shape
+        cout = dup.shape[-1]
+        g = torch.zeros((cout, 4, cin), dtype=torch.float32, device=self.dev)
+        self._wgrad(2, n, h, w, {0: self._chw(dup, 0, 2), 1: self._chw(dup, 1, 2)}, cout, {0: self._chw_cached(x)}, cin, g, cin, 0)
+        conv.weight.grad = g.permute(2, 0, 1).reshape(cin, cout, 2, 2).contiguous()
+        # data gradient = 2x2 stride-2 convolution of d(up) with W[ci][co][q]
+        packed = conv.weight.detach().float().permute(0, 2, 3, 1).reshape(cin, 4, cout).to(torch.bfloat16).contiguous()
+        dx = torch.empty((n, h, w, cin), dtype=torch.bfloat16, device=self.dev)
+        self._conv(3, n, 2 * h, 2 * w, [dup], packed, cin, self._zeros(cin), ACT_NONE, dx)
+        return dx
+
+
+def flat_grads(net):
+    return [p for p in net.parameters() if p.grad is not None]
+
+
+def allreduce_gradients(net, world_size):
+    """Data-parallel gradient exchange: ONE all-reduce over a flat fp32 buffer, then the mean (NCCL over NVLink)."""
+    import torch.distributed as dist
+    params = flat_grads(net)
+    flat = torch.cat([p.grad.reshape(-1) for p in params])
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+    flat.div_(world_size)
+    off = 0
+    for p in params:
+        k = p.grad.numel()
+        p.grad.copy_(flat[off:off + k].view_as(p.grad))
+        off += k
+    return flat.numel()
+
+
+def train_step(engine, optimizer, img, border_label, cell_label, world_size=1):
+    """One optimisation step as in train.py:473-493 (zero_grad, forward, loss, backward, step)."""
+    optimizer.zero_grad(set_to_none=True)
+    loss = engine.forward_backward(img, border_label, cell_label)
+    if world_size > 1:
+        allreduce_gradients(engine.net, world_size)
+    optimizer.step()
+    return loss

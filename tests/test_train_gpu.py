@@ -1,0 +1,91 @@
+"""GPU parity tests for the training step (forward + backward on the CUDA path, no autograd / cuDNN).
+
+Checker: a plain PyTorch fp32 reference of the same graph with autograd (oracle/net.py::dunet_train_loss; this is a
+floating-point kernel family, so the reference is torch fp32 on the same seeded inputs).  Tolerance (stated): the
+CUDA path keeps activations and activation gradients in bf16 with fp32 accumulation, so the loss must agree within
+2e-2 relative and every parameter gradient at least as close to the fp32 reference as torch's own bf16 autocast of the same graph is
+(relative L2 error <= max(1.5 x autocast error, 0.05), median error <= 1.25 x autocast median), gradient norms (20 %) within
+5 %, cosine similarity > min(0.97, autocast's - 0.05); the transposed-conv bias gradient is exactly zero in theory (BatchNorm follows directly)
+and is compared absolutely.  The seeded random labels make the gradients cancellation-heavy, i.e. a hard case."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import net as onet
+
+pytestmark = pytest.mark.gpu
+
+
+def _setup(filters, seed, n, h, w):
+    from microbeseg_b200.unets import build_unet
+    from microbeseg_b200.training import TrainEngine
+    net = build_unet("DU", "relu", "conv", "bn", torch.device("cuda:0"), 1, filters=list(filters))
+    sd = onet.seeded_state_dict(onet.reference_layout_template("DU", filters), seed)
+    net.load_state_dict(sd)
+    net.train()
+    rng = np.random.default_rng(seed)
+    img = torch.from_numpy(rng.uniform(-1, 1, (n, 1, h, w)).astype(np.float32)).cuda()
+    bl = torch.from_numpy(rng.uniform(0, 1, (n, 1, h, w)).astype(np.float32)).cuda()
+    cl = torch.from_numpy(rng.uniform(0, 1, (n, 1, h, w)).astype(np.float32)).cuda()
+    return net, sd, TrainEngine(net), img, bl, cl
+
+
+def _reference(sd, img, bl, cl, autocast=False):
+    params = {k: v.clone().cuda().requires_grad_(v.dtype.is_floating_point and "running" not in k) for k, v in sd.items()
+              if v.dtype.is_floating_point}
+    with torch.autocast("cuda", dtype=torch.bfloat16, enabled=autocast):
+        loss = onet.dunet_train_loss(params, img, bl, cl)
+    loss.backward()
+    return float(loss.detach()), {k: p.grad for k, p in params.items() if p.grad is not None}
+
+
+@pytest.mark.parametrize("filters,n,h,w", [((64, 128), 2, 32, 48), ((64, 256), 3, 64, 64), ((64, 1024), 2, 128, 96)])
+def test_loss_and_gradients_vs_torch_autograd(native_lib, filters, n, h, w):
+    net, sd, eng, img, bl, cl = _setup(filters, 7, n, h, w)
+    loss = float(eng.forward_backward(img, bl, cl))
+    ref_loss, ref_grads = _reference(sd, img, bl, cl)
+    assert native_lib.mbs_debug_flags(1) == 0
+    assert abs(loss - ref_loss) <= 2e-2 * abs(ref_loss), (loss, ref_loss)
+    # yardstick: the same graph under torch's own bf16 autocast (the standard mixed-precision policy)
+    _, amp_grads = _reference(sd, img, bl, cl, autocast=True)
+    rows = []
+    for name, p in net.named_parameters():
+        assert p.grad is not None, name
+        g, r, a = p.grad.float(), ref_grads[name].float(), amp_grads[name].float()
+        assert g.shape == r.shape and torch.isfinite(g).all(), name
+        rel = float((g - r).norm() / (r.norm() + 1e-12))
+        rel_amp = float((a - r).norm() / (r.norm() + 1e-12))
+        cos = float((g * r).sum() / (g.norm() * r.norm() + 1e-20))
+        cos_amp = float((a * r).sum() / (a.norm() * r.norm() + 1e-20))
+        rows.append((rel, cos, name, float(r.norm()), float(g.norm()), rel_amp, cos_amp))
+    if os.environ.get("MBS_PRINT_GRADS"):
+        for row in sorted(rows, reverse=True)[:40]:
+            print("GRAD %-42s rel=%.4f (torch autocast %.4f) cos=%.5f |ref|=%.3e |got|=%.3e" % (row[2], row[0], row[5], row[1], row[3], row[4]))
+    # a bias in front of a BatchNorm without activation (transposed-conv bias) has an exactly zero gradient: BN
+    # removes the mean.  Both sides then hold rounding noise only -> compare absolutely, against the weight scale.
+    wscale = max(r[3] for r in rows)
+    for rel, cos, name, rn, gn, rel_amp, cos_amp in rows:
+        if ".up.0.bias" in name:
+            assert gn < 1e-3 * wscale and rn < 1e-3 * wscale, (name, rn, gn)
+            continue
+        assert abs(gn - rn) <= max(0.2, 1.5 * rel_amp) * rn + 1e-6 * wscale, (name, rn, gn, rel_amp)   # magnitudes agree
+        assert rel <= max(1.5 * rel_amp, 0.05), (name, rel, rel_amp, cos)         # as accurate as torch bf16 autocast
+        assert cos > min(0.97, cos_amp - 0.05), (name, rel, cos, cos_amp)
+    assert float(np.median([r[0] for r in rows])) <= 1.25 * float(np.median([r[5] for r in rows])) + 0.01
+
+
+def test_running_statistics_and_optimizer_step(native_lib):
+    from microbeseg_b200.training import train_step
+    net, sd, eng, img, bl, cl = _setup((64, 128), 11, 2, 32, 32)
+    opt = torch.optim.Adam(net.parameters(), lr=8e-4, betas=(0.9, 0.999), eps=1e-08, weight_decay=0, amsgrad=True)  # train.py:380-385
+    rm0 = net.encoderConv[0].conv[2].running_mean.clone()
+    losses = [float(train_step(eng, opt, img, bl, cl)) for _ in range(8)]
+    assert losses[-1] < losses[0]                                   # the step descends on a fixed batch
+    assert not torch.equal(rm0, net.encoderConv[0].conv[2].running_mean)
+    assert int(net.encoderConv[0].conv[2].num_batches_tracked) == 100 + 8       # seeded state dict starts at 100
+    net.eval()                                                      # and the trained weights run on the inference path
+    with torch.no_grad():
+        b, c = net(img)
+    assert torch.isfinite(b).all() and torch.isfinite(c).all()
