@@ -142,7 +142,7 @@ int mbs_bn_train_fwd(const void *a, long long M, int C, const float *gamma, cons
 int mbs_bn_train_bwd(const void *dy, const void *a, long long M, int C, const float *mean, const float *invstd,
                      const float *gamma, int act, void *dz, float *dgamma_dbeta, float *dbias, void *stream);
 /* Conv2d(C,1,1) head, SmoothL1Loss(beta=1,'mean') (losses.py:30-32) and their gradients */
-int mbs_head_fwd(const void *y, long long M, int C, const float *w, float b, float *pred, void *stream);
+int mbs_head_fwd(const void *y, long long M, int C, const float *w, const float *b_dev, float *pred, void *stream);
 int mbs_smoothl1(const float *pred, const float *target, long long M, float *loss_accum, float *grad, void *stream);
 int mbs_head_bwd(const float *g, const void *y, long long M, int C, const float *w, void *dy, float *dw_db, void *stream);
 /* layout / glue kernels of the backward pass */
@@ -151,6 +151,9 @@ int mbs_head_bwd(const float *g, const void *y, long long M, int C, const float 
  * decimation of stride-2 layers) of the weight gradient are baked into channel-major copies */
 int mbs_nhwc_to_chw(const void *src, int N, int H, int W, int C, int pitch, int shift_x, int step_x, void *dst,
                     void *stream);
+/* unit-step variant writing the copies shifted by -1 / 0 / +1 in one pass (any of the three may be NULL) */
+int mbs_nhwc_to_chw3(const void *src, int N, int H, int W, int C, int pitch, void *dst_m1, void *dst_0, void *dst_p1,
+                     void *stream);
 int mbs_zero_insert_up2(const void *src, int N, int H, int W, int C, void *dst, void *stream);
 int mbs_add3_bf16(const void *a, const void *b, const void *c, long long n, void *out, void *stream);
 int mbs_first_conv_wgrad(const float *x, const void *dz, int N, int H, int W, int C, float *dw, void *stream);

@@ -19,46 +19,67 @@ __device__ __forceinline__ float warp_sum(float v) {
     return v;
 }
 
-// Per-channel reductions over an [M][C] bf16 matrix.  Block = 256 threads = 8 "pixel lanes" x 32 "channel lanes";
-// a thread owns channels c0 + 32*j (j < C/32 handled in chunks of 8 channel groups to bound registers).
-// Generic helper: F(pixel, channel, value) -> up to 2 accumulators.
-template <int NACC, typename F>
-__device__ __forceinline__ void channel_reduce(long long M, int C, float *out, F f) {
-    __shared__ float s_red[8][32][2];
-    const int cl = threadIdx.x & 31, pl = threadIdx.x >> 5;
-    for (int cbase = 0; cbase < C; cbase += 32) {
-        const int c = cbase + cl;
-        float acc[2] = {0.0f, 0.0f};
-        if (c < C) {
-            for (long long p = static_cast<long long>(blockIdx.x) * 8 + pl; p < M; p += static_cast<long long>(gridDim.x) * 8) {
-                float v[2];
-                f(p, c, v);
-                acc[0] += v[0];
-                if (NACC > 1) acc[1] += v[1];
-            }
+// Per-channel reductions over an [M][C] bf16 matrix with fully coalesced 16-byte accesses: C/8 consecutive threads
+// cover one pixel row (8 channels each), a 256-thread block covers 2048/C pixels per iteration, every thread keeps
+// its 8 channels' partial sums in registers; partials are combined through shared memory and one atomicAdd per
+// (block, channel).  F(p, c0, vals_in..., acc) is supplied per kernel.  Requires C % 8 == 0 and C <= 2048.
+struct Bf16x8 {
+    uint4 raw;
+    __device__ __forceinline__ void unpack(float (&f)[8]) const {
+        const __nv_bfloat162 *h = reinterpret_cast<const __nv_bfloat162 *>(&raw);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            f[2 * i] = __bfloat162float(h[i].x);
+            f[2 * i + 1] = __bfloat162float(h[i].y);
         }
-        s_red[pl][cl][0] = acc[0];
-        s_red[pl][cl][1] = acc[1];
-        __syncthreads();
-        if (pl == 0 && c < C) {
-            float a0 = 0.0f, a1 = 0.0f;
-            for (int k = 0; k < 8; ++k) {
-                a0 += s_red[k][cl][0];
-                a1 += s_red[k][cl][1];
-            }
-            atomicAdd(&out[c], a0);
-            if (NACC > 1) atomicAdd(&out[C + c], a1);
-        }
-        __syncthreads();
     }
+    __device__ __forceinline__ static uint4 pack(const float (&f)[8]) {
+        uint4 r;
+        __nv_bfloat162 *h = reinterpret_cast<__nv_bfloat162 *>(&r);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+        return r;
+    }
+};
+
+template <int NACC>
+__device__ __forceinline__ void block_channel_atomic(float (&acc)[NACC][8], int C, int c0, float *out) {
+    // threads with the same c0 (same threadIdx.x % (C/8)) hold partials of the same channels
+    __shared__ float s_acc[NACC][2048];
+    const int tpp = C / 8;                        // threads per pixel
+    for (int i = threadIdx.x; i < NACC * C; i += blockDim.x) (&s_acc[0][0])[(i / C) * 2048 + i % C] = 0.0f;
+    __syncthreads();
+    if (c0 < C) {
+#pragma unroll
+        for (int a = 0; a < NACC; ++a)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) atomicAdd(&s_acc[a][c0 + j], acc[a][j]);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < NACC * C; i += blockDim.x) {
+        const int a = i / C, c = i % C;
+        atomicAdd(&out[a * C + c], s_acc[a][c]);
+    }
+    (void)tpp;
 }
 
 __global__ void __launch_bounds__(256) bn_stats_kernel(const __nv_bfloat16 *__restrict__ a, long long M, int C, float *sums) {
-    channel_reduce<2>(M, C, sums, [&](long long p, int c, float *v) {
-        const float x = __bfloat162float(a[p * C + c]);
-        v[0] = x;
-        v[1] = x * x;
-    });
+    const int tpp = C / 8, c0 = (threadIdx.x % tpp) * 8, ppb = 256 / tpp;
+    float acc[2][8] = {};
+    if (threadIdx.x < ppb * tpp) {
+        for (long long p = static_cast<long long>(blockIdx.x) * ppb + threadIdx.x / tpp; p < M; p += static_cast<long long>(gridDim.x) * ppb) {
+            Bf16x8 v;
+            v.raw = *reinterpret_cast<const uint4 *>(a + p * C + c0);
+            float f[8];
+            v.unpack(f);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                acc[0][j] += f[j];
+                acc[1][j] = fmaf(f[j], f[j], acc[1][j]);
+            }
+        }
+    }
+    block_channel_atomic<2>(acc, C, threadIdx.x < ppb * tpp ? c0 : C, sums);
 }
 
 __global__ void bn_finalize_kernel(const float *__restrict__ sums, long long M, int C, float eps, float *mean, float *invstd,
@@ -76,24 +97,42 @@ __global__ void bn_finalize_kernel(const float *__restrict__ sums, long long M, 
 __global__ void bn_apply_kernel(const __nv_bfloat16 *__restrict__ a, long long total, int C, const float *__restrict__ mean,
                                 const float *__restrict__ invstd, const float *__restrict__ gamma,
                                 const float *__restrict__ beta, __nv_bfloat16 *__restrict__ y) {
-    const long long i = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) * 2;
+    const long long i = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) * 8;
     if (i >= total) return;
     const int c = static_cast<int>(i % C);
-    const __nv_bfloat162 v = *reinterpret_cast<const __nv_bfloat162 *>(a + i);
-    const float x0 = (__bfloat162float(v.x) - mean[c]) * invstd[c] * gamma[c] + beta[c];
-    const float x1 = (__bfloat162float(v.y) - mean[c + 1]) * invstd[c + 1] * gamma[c + 1] + beta[c + 1];
-    *reinterpret_cast<__nv_bfloat162 *>(y + i) = __floats2bfloat162_rn(x0, x1);
+    Bf16x8 v;
+    v.raw = *reinterpret_cast<const uint4 *>(a + i);
+    float f[8];
+    v.unpack(f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f[j] = (f[j] - mean[c + j]) * invstd[c + j] * gamma[c + j] + beta[c + j];
+    *reinterpret_cast<uint4 *>(y + i) = Bf16x8::pack(f);
 }
 
 __global__ void __launch_bounds__(256)
 bn_bwd_reduce_kernel(const __nv_bfloat16 *__restrict__ dy, const __nv_bfloat16 *__restrict__ a, long long M, int C,
                      const float *__restrict__ mean, const float *__restrict__ invstd, float *dgamma_dbeta) {
-    channel_reduce<2>(M, C, dgamma_dbeta, [&](long long p, int c, float *v) {
-        const float g = __bfloat162float(dy[p * C + c]);
-        const float xh = (__bfloat162float(a[p * C + c]) - mean[c]) * invstd[c];
-        v[0] = g * xh;
-        v[1] = g;
-    });
+    const int tpp = C / 8, c0 = (threadIdx.x % tpp) * 8, ppb = 256 / tpp;
+    float acc[2][8] = {};
+    if (threadIdx.x < ppb * tpp) {
+        float mu[8], is[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { mu[j] = mean[c0 + j]; is[j] = invstd[c0 + j]; }
+        for (long long p = static_cast<long long>(blockIdx.x) * ppb + threadIdx.x / tpp; p < M; p += static_cast<long long>(gridDim.x) * ppb) {
+            Bf16x8 vg, va;
+            vg.raw = *reinterpret_cast<const uint4 *>(dy + p * C + c0);
+            va.raw = *reinterpret_cast<const uint4 *>(a + p * C + c0);
+            float g[8], x[8];
+            vg.unpack(g);
+            va.unpack(x);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                acc[0][j] = fmaf(g[j], (x[j] - mu[j]) * is[j], acc[0][j]);
+                acc[1][j] += g[j];
+            }
+        }
+    }
+    block_channel_atomic<2>(acc, C, threadIdx.x < ppb * tpp ? c0 : C, dgamma_dbeta);
 }
 
 // dz = act'(a) * gamma * invstd * (dy - dbeta/M - xhat * dgamma/M);  dbias[c] += sum_p dz
@@ -101,21 +140,48 @@ __global__ void __launch_bounds__(256)
 bn_bwd_apply_kernel(const __nv_bfloat16 *__restrict__ dy, const __nv_bfloat16 *__restrict__ a, long long M, int C,
                     const float *__restrict__ mean, const float *__restrict__ invstd, const float *__restrict__ gamma,
                     const float *__restrict__ dgamma_dbeta, int act, __nv_bfloat16 *__restrict__ dz, float *dbias) {
+    const int tpp = C / 8, c0 = (threadIdx.x % tpp) * 8, ppb = 256 / tpp;
     const float invM = 1.0f / static_cast<float>(M);
-    channel_reduce<1>(M, C, dbias, [&](long long p, int c, float *v) {
-        const float av = __bfloat162float(a[p * C + c]);
-        const float xh = (av - mean[c]) * invstd[c];
-        float g = gamma[c] * invstd[c] * (__bfloat162float(dy[p * C + c]) - dgamma_dbeta[C + c] * invM - xh * dgamma_dbeta[c] * invM);
-        if (act == MBS_ACT_RELU && !(av > 0.0f)) g = 0.0f;
-        const __nv_bfloat16 gb = __float2bfloat16_rn(g);
-        dz[p * C + c] = gb;
-        v[0] = __bfloat162float(gb);
-    });
+    float acc[1][8] = {};
+    if (threadIdx.x < ppb * tpp) {
+        float mu[8], is[8], k1[8], k2[8], k3[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            mu[j] = mean[c0 + j];
+            is[j] = invstd[c0 + j];
+            k1[j] = gamma[c0 + j] * is[j];
+            k2[j] = dgamma_dbeta[C + c0 + j] * invM;
+            k3[j] = dgamma_dbeta[c0 + j] * invM;
+        }
+        for (long long p = static_cast<long long>(blockIdx.x) * ppb + threadIdx.x / tpp; p < M; p += static_cast<long long>(gridDim.x) * ppb) {
+            Bf16x8 vg, va;
+            vg.raw = *reinterpret_cast<const uint4 *>(dy + p * C + c0);
+            va.raw = *reinterpret_cast<const uint4 *>(a + p * C + c0);
+            float g[8], x[8], o[8];
+            vg.unpack(g);
+            va.unpack(x);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                float v = k1[j] * (g[j] - k2[j] - (x[j] - mu[j]) * is[j] * k3[j]);
+                if (act == MBS_ACT_RELU && !(x[j] > 0.0f)) v = 0.0f;
+                o[j] = v;
+            }
+            const uint4 packed = Bf16x8::pack(o);
+            *reinterpret_cast<uint4 *>(dz + p * C + c0) = packed;
+            Bf16x8 back;
+            back.raw = packed;
+            float r[8];
+            back.unpack(r);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[0][j] += r[j];
+        }
+    }
+    block_channel_atomic<1>(acc, C, threadIdx.x < ppb * tpp ? c0 : C, dbias);
 }
 
 // 1x1 head forward: pred[p] = sum_c y[p][c] * w[c] + b
-__global__ void head_fwd_kernel(const __nv_bfloat16 *__restrict__ y, long long M, int C, const float *__restrict__ w, float b,
-                                float *__restrict__ pred) {
+__global__ void head_fwd_kernel(const __nv_bfloat16 *__restrict__ y, long long M, int C, const float *__restrict__ w,
+                                const float *__restrict__ b, float *__restrict__ pred) {
     const long long p = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (p >= M) return;
     float acc = 0.0f;
@@ -125,7 +191,7 @@ __global__ void head_fwd_kernel(const __nv_bfloat16 *__restrict__ y, long long M
         acc = fmaf(__bfloat162float(v.x), w[2 * c], acc);
         acc = fmaf(__bfloat162float(v.y), w[2 * c + 1], acc);
     }
-    pred[p] = acc + b;
+    pred[p] = acc + b[0];
 }
 
 // SmoothL1Loss(beta = 1, reduction = 'mean'): loss += sum / M;  g = clamp(pred - target, -1, 1) / M
@@ -155,25 +221,31 @@ smoothl1_kernel(const float *__restrict__ pred, const float *__restrict__ target
 __global__ void __launch_bounds__(256)
 head_bwd_kernel(const float *__restrict__ g, const __nv_bfloat16 *__restrict__ y, long long M, int C, const float *__restrict__ w,
                 __nv_bfloat16 *__restrict__ dy, float *dw_db) {
-    channel_reduce<1>(M, C, dw_db, [&](long long p, int c, float *v) {
-        const float gp = g[p];
-        dy[p * C + c] = __float2bfloat16_rn(gp * w[c]);
-        v[0] = gp * __bfloat162float(y[p * C + c]);
-    });
-    // bias gradient: one extra pass over g by block 0 .. gridDim (cheap: M floats)
-    __shared__ float s_b[8];
-    float acc = 0.0f;
-    for (long long p = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; p < M;
-         p += static_cast<long long>(gridDim.x) * blockDim.x)
-        acc += g[p];
-    acc = warp_sum(acc);
-    if ((threadIdx.x & 31) == 0) s_b[threadIdx.x >> 5] = acc;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        float t = 0.0f;
-        for (int k = 0; k < 8; ++k) t += s_b[k];
-        atomicAdd(&dw_db[C], t);
+    const int tpp = C / 8, c0 = (threadIdx.x % tpp) * 8, ppb = 256 / tpp;
+    float acc[1][8] = {};
+    float gsum = 0.0f;
+    if (threadIdx.x < ppb * tpp) {
+        float wv[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) wv[j] = w[c0 + j];
+        for (long long p = static_cast<long long>(blockIdx.x) * ppb + threadIdx.x / tpp; p < M; p += static_cast<long long>(gridDim.x) * ppb) {
+            const float gp = g[p];
+            Bf16x8 vy;
+            vy.raw = *reinterpret_cast<const uint4 *>(y + p * C + c0);
+            float yv[8], o[8];
+            vy.unpack(yv);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                o[j] = gp * wv[j];
+                acc[0][j] = fmaf(gp, yv[j], acc[0][j]);
+            }
+            *reinterpret_cast<uint4 *>(dy + p * C + c0) = Bf16x8::pack(o);
+            if (c0 == 0) gsum += gp;
+        }
     }
+    block_channel_atomic<1>(acc, C, threadIdx.x < ppb * tpp ? c0 : C, dw_db);
+    gsum = warp_sum(gsum);
+    if ((threadIdx.x & 31) == 0 && gsum != 0.0f) atomicAdd(&dw_db[C], gsum);
 }
 
 // [N][H][W][C] -> channel-major [N][C][H][pitch] (bf16, pitch >= W, padding columns zero), 32x32 tiles via smem.
@@ -193,6 +265,44 @@ __global__ void nhwc_to_chw_kernel(const __nv_bfloat16 *__restrict__ src, int H,
     for (int r = threadIdx.y; r < 32; r += blockDim.y) {
         const int c = c0 + r, x = x0 + threadIdx.x;
         if (c < C && x < pitch) d[static_cast<size_t>(c) * H * pitch + x] = tile[threadIdx.x][r];
+    }
+}
+
+// Unit-step variant producing the shifted copies (-1, 0, +1) in ONE pass: a block stages 64 pixels (+1 halo pixel
+// each side) x 64 channels of one image row in shared memory (16-byte coalesced reads) and writes 64-pixel rows of
+// each requested copy (128-byte coalesced writes).  dsts[k] may be null.
+__global__ void __launch_bounds__(256)
+nhwc_to_chw3_kernel(const __nv_bfloat16 *__restrict__ src, int H, int W, int C, int pitch, __nv_bfloat16 *__restrict__ d0,
+                    __nv_bfloat16 *__restrict__ d1, __nv_bfloat16 *__restrict__ d2) {
+    __shared__ __nv_bfloat16 tile[66][72];           // [pixel + 1][channel], padded row (144 B) to spread banks
+    const int n = blockIdx.z / H, y = blockIdx.z % H;
+    const int x0 = blockIdx.x * 64, c0 = blockIdx.y * 64;
+    const __nv_bfloat16 *s = src + (static_cast<size_t>(n) * H + y) * W * C;
+    // 66 pixels x 64 channels = 66 x 8 chunks of 16 bytes
+    for (int i = threadIdx.x; i < 66 * 8; i += 256) {
+        const int px = i >> 3, ch = (i & 7) * 8;
+        const int x = x0 + px - 1;
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (x >= 0 && x < W && c0 + ch < C) v = *reinterpret_cast<const uint4 *>(s + static_cast<size_t>(x) * C + c0 + ch);
+        *reinterpret_cast<uint4 *>(&tile[px][ch]) = v;
+    }
+    __syncthreads();
+    __nv_bfloat16 *dsts[3] = {d0, d1, d2};
+    const size_t plane = static_cast<size_t>(H) * pitch;
+    // each thread writes 8 consecutive pixels (16 bytes) of one channel row: 64 channels x 8 chunks = 512 items
+    for (int i = threadIdx.x; i < 64 * 8; i += 256) {
+        const int c = i >> 3, xo = (i & 7) * 8;
+        if (c0 + c >= C || x0 + xo >= pitch) continue;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            if (!dsts[k]) continue;
+            __nv_bfloat16 v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = tile[xo + j + k][c];       // copy k holds src column x + (k - 1)
+            __nv_bfloat16 *d = dsts[k] + static_cast<size_t>(n) * C * plane + static_cast<size_t>(c0 + c) * plane +
+                               static_cast<size_t>(y) * pitch + x0 + xo;
+            *reinterpret_cast<uint4 *>(d) = *reinterpret_cast<uint4 *>(v);
+        }
     }
 }
 
@@ -255,6 +365,12 @@ first_conv_wgrad_kernel(const float *__restrict__ x, const __nv_bfloat16 *__rest
     for (int i = threadIdx.x; i < C * 9; i += blockDim.x) atomicAdd(&dw[i], s_acc[i]);
 }
 
+inline int grid_rows(long long M, int C) {          // blocks for the row-vectorised reductions: ~8 rows per thread
+    const long long ppb = 256 / (C / 8);
+    long long b = (M + ppb * 8 - 1) / (ppb * 8);
+    if (b < 1) b = 1;
+    return static_cast<int>(b > 148 * 8 ? 148 * 8 : b);
+}
 inline int grid_for(long long work, int per_block, int cap) {
     long long b = (work + per_block - 1) / per_block;
     if (b < 1) b = 1;
@@ -266,14 +382,14 @@ inline int grid_for(long long work, int per_block, int cap) {
 extern "C" int mbs_bn_train_fwd(const void *a, long long M, int C, const float *gamma, const float *beta, float eps, void *y,
                                 float *sums_scratch, float *mean, float *invstd, float *var_unbiased, void *stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-    MBS_REQUIRE(M > 0 && C > 0 && C % 2 == 0, "bn_train_fwd: bad shape");
+    MBS_REQUIRE(M > 0 && C >= 8 && C % 8 == 0 && C <= 2048 && 256 % (C / 8) == 0, "bn_train_fwd: bad shape (C must be 8*2^k <= 2048)");
     MBS_CHECK_CUDA(cudaMemsetAsync(sums_scratch, 0, 2 * C * sizeof(float), stream));
-    bn_stats_kernel<<<grid_for(M, 8 * 16, 148 * 8), 256, 0, stream>>>(static_cast<const __nv_bfloat16 *>(a), M, C, sums_scratch);
+    bn_stats_kernel<<<grid_rows(M, C), 256, 0, stream>>>(static_cast<const __nv_bfloat16 *>(a), M, C, sums_scratch);
     MBS_CHECK_LAUNCH();
     bn_finalize_kernel<<<mbs::cdiv(C, 128), 128, 0, stream>>>(sums_scratch, M, C, eps, mean, invstd, var_unbiased);
     MBS_CHECK_LAUNCH();
     const long long total = M * C;
-    bn_apply_kernel<<<static_cast<int>((total / 2 + 255) / 256), 256, 0, stream>>>(
+    bn_apply_kernel<<<static_cast<int>((total / 8 + 255) / 256), 256, 0, stream>>>(
         static_cast<const __nv_bfloat16 *>(a), total, C, mean, invstd, gamma, beta, static_cast<__nv_bfloat16 *>(y));
     MBS_CHECK_LAUNCH();
     return 0;
@@ -282,11 +398,11 @@ extern "C" int mbs_bn_train_fwd(const void *a, long long M, int C, const float *
 extern "C" int mbs_bn_train_bwd(const void *dy, const void *a, long long M, int C, const float *mean, const float *invstd,
                                 const float *gamma, int act, void *dz, float *dgamma_dbeta, float *dbias, void *stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-    MBS_REQUIRE(M > 0 && C > 0, "bn_train_bwd: bad shape");
+    MBS_REQUIRE(M > 0 && C >= 8 && C % 8 == 0 && C <= 2048 && 256 % (C / 8) == 0, "bn_train_bwd: bad shape");
     MBS_REQUIRE(act == MBS_ACT_NONE || act == MBS_ACT_RELU, "bn_train_bwd: only relu / none are supported in training");
     MBS_CHECK_CUDA(cudaMemsetAsync(dgamma_dbeta, 0, 2 * C * sizeof(float), stream));
     MBS_CHECK_CUDA(cudaMemsetAsync(dbias, 0, C * sizeof(float), stream));
-    const int grid = grid_for(M, 8 * 16, 148 * 8);
+    const int grid = grid_rows(M, C);
     bn_bwd_reduce_kernel<<<grid, 256, 0, stream>>>(static_cast<const __nv_bfloat16 *>(dy), static_cast<const __nv_bfloat16 *>(a), M,
                                                    C, mean, invstd, dgamma_dbeta);
     MBS_CHECK_LAUNCH();
@@ -297,10 +413,10 @@ extern "C" int mbs_bn_train_bwd(const void *dy, const void *a, long long M, int 
     return 0;
 }
 
-extern "C" int mbs_head_fwd(const void *y, long long M, int C, const float *w, float b, float *pred, void *stream_) {
+extern "C" int mbs_head_fwd(const void *y, long long M, int C, const float *w, const float *b_dev, float *pred, void *stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     MBS_REQUIRE(M > 0 && C > 0 && C % 2 == 0, "head_fwd: bad shape");
-    head_fwd_kernel<<<static_cast<int>((M + 255) / 256), 256, 0, stream>>>(static_cast<const __nv_bfloat16 *>(y), M, C, w, b, pred);
+    head_fwd_kernel<<<static_cast<int>((M + 255) / 256), 256, 0, stream>>>(static_cast<const __nv_bfloat16 *>(y), M, C, w, b_dev, pred);
     MBS_CHECK_LAUNCH();
     return 0;
 }
@@ -316,9 +432,9 @@ extern "C" int mbs_smoothl1(const float *pred, const float *target, long long M,
 extern "C" int mbs_head_bwd(const float *g, const void *y, long long M, int C, const float *w, void *dy, float *dw_db,
                             void *stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-    MBS_REQUIRE(M > 0 && C > 0, "head_bwd: bad shape");
+    MBS_REQUIRE(M > 0 && C >= 8 && C % 8 == 0 && C <= 2048 && 256 % (C / 8) == 0, "head_bwd: bad shape");
     MBS_CHECK_CUDA(cudaMemsetAsync(dw_db, 0, (C + 1) * sizeof(float), stream));
-    head_bwd_kernel<<<grid_for(M, 8 * 16, 148 * 8), 256, 0, stream>>>(g, static_cast<const __nv_bfloat16 *>(y), M, C, w,
+    head_bwd_kernel<<<grid_rows(M, C), 256, 0, stream>>>(g, static_cast<const __nv_bfloat16 *>(y), M, C, w,
                                                                       static_cast<__nv_bfloat16 *>(dy), dw_db);
     MBS_CHECK_LAUNCH();
     return 0;
@@ -333,6 +449,19 @@ extern "C" int mbs_nhwc_to_chw(const void *src, int N, int H, int W, int C, int 
     dim3 grid(mbs::cdiv(pitch, 32), mbs::cdiv(C, 32), N * H), block(32, 8);
     nhwc_to_chw_kernel<<<grid, block, 0, stream>>>(static_cast<const __nv_bfloat16 *>(src), H, W, C, pitch, shift_x, step_x,
                                                    static_cast<__nv_bfloat16 *>(dst));
+    MBS_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int mbs_nhwc_to_chw3(const void *src, int N, int H, int W, int C, int pitch, void *dst_m1, void *dst_0,
+                                void *dst_p1, void *stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    MBS_REQUIRE(N > 0 && H > 0 && W > 0 && C > 0 && C % 8 == 0 && pitch >= W && pitch % 8 == 0, "nhwc_to_chw3: bad shape / pitch");
+    MBS_REQUIRE(static_cast<long long>(N) * H <= 65535, "nhwc_to_chw3: N*H too large for one launch");
+    dim3 grid(mbs::cdiv(pitch, 64), mbs::cdiv(C, 64), N * H);
+    nhwc_to_chw3_kernel<<<grid, 256, 0, stream>>>(static_cast<const __nv_bfloat16 *>(src), H, W, C, pitch,
+                                                  static_cast<__nv_bfloat16 *>(dst_m1), static_cast<__nv_bfloat16 *>(dst_0),
+                                                  static_cast<__nv_bfloat16 *>(dst_p1));
     MBS_CHECK_LAUNCH();
     return 0;
 }

@@ -32,7 +32,7 @@ class _Layer:
 class TrainEngine:
     """Forward + backward of one DUNet on one GPU; fills ``param.grad`` (fp32) for every parameter."""
 
-    def __init__(self, net):
+    def __init__(self, net, use_graph=True):
         from .unets import DUNet
         if not isinstance(net, DUNet):
             raise NotImplementedError("training is built for the DU (distance) network")
@@ -47,6 +47,8 @@ class TrainEngine:
         self.chans = net._chans
         self._const = {}
         self._scratch = torch.empty(4 * 2048, dtype=torch.float32, device=self.dev)
+        self.use_graph = use_graph
+        self._graphs = {}
 
     # ---- small helpers ------------------------------------------------------------------------
     def _ones(self, c):
@@ -111,6 +113,21 @@ class TrainEngine:
         out = torch.empty((n, c, h, p), dtype=torch.bfloat16, device=self.dev)
         nat.check(self.L.mbs_nhwc_to_chw(t.data_ptr(), n, h, w, c, p, shift, step, out.data_ptr(), self._sp()), "nhwc_to_chw")
         return out
+
+    def _chw3(self, t, shifts=(-1, 0, 1)):
+        """the unit-step copies for ``shifts`` in one pass -> dict shift -> tensor"""
+        n, h, w, c = t.shape
+        p = _pitch(w)
+        outs = {sh: torch.empty((n, c, h, p), dtype=torch.bfloat16, device=self.dev) for sh in shifts}
+        ptr = lambda sh: outs[sh].data_ptr() if sh in outs else None
+        nat.check(self.L.mbs_nhwc_to_chw3(t.data_ptr(), n, h, w, c, p, ptr(-1), ptr(0), ptr(1), self._sp()), "nhwc_to_chw3")
+        return outs
+
+    def _chw3_cached(self, t):
+        k = (t.data_ptr(), "x3")
+        if k not in self._chw_cache:
+            self._chw_cache[k] = (self._chw3(t), t)
+        return self._chw_cache[k][0]
 
     def _chw_cached(self, t, shift=0, step=1):
         k = (t.data_ptr(), shift, step)
@@ -177,7 +194,41 @@ class TrainEngine:
 
     def forward_backward(self, img, border_label, cell_label):
         """img / labels: [N,1,H,W] float32 CUDA tensors (img normalised to [-1,1] as the reference's ToTensor does).
-        Returns the loss (0-d tensor) and leaves the gradients in ``param.grad``."""
+        Returns the loss (0-d tensor) and leaves the gradients in ``param.grad``.
+
+        With ``use_graph`` (default) the first call of a given batch shape runs eagerly (it also warms up every kernel
+        configuration), the second call captures the whole step -- ~600 kernel launches plus the torch glue -- into ONE
+        CUDA graph, and later calls only copy the batch into the static inputs and replay it."""
+        if not self.use_graph:
+            return self._forward_backward(img, border_label, cell_label)
+        key = (tuple(img.shape), img.dtype)
+        st = self._graphs.get(key)
+        if st is None:                                   # eager warm-up call
+            self._graphs[key] = {"calls": 1}
+            return self._forward_backward(img, border_label, cell_label)
+        if "graph" not in st:
+            st["in"] = [torch.empty_like(t, dtype=torch.float32) for t in (img, border_label, cell_label)]
+            for d, s_ in zip(st["in"], (img, border_label, cell_label)):
+                d.copy_(s_)
+            torch.cuda.synchronize(self.dev)
+            g = torch.cuda.CUDAGraph()
+            self.L.mbs_launch_count(1)
+            with torch.cuda.graph(g):
+                st["loss"] = self._forward_backward(*st["in"])
+            st["graph"] = g
+            st["launches"] = int(self.L.mbs_launch_count(0))     # kernels of this library inside one replay
+            # the capture does not execute the step; the gradient tensors it created are re-attached after every
+            # replay (optimizer.zero_grad(set_to_none=True) detaches them)
+            st["grads"] = [(p, p.grad) for p in self.net.parameters()]
+        for d, s_ in zip(st["in"], (img, border_label, cell_label)):
+            d.copy_(s_)
+        st["graph"].replay()
+        for p, gr in st["grads"]:
+            p.grad = gr
+        self.launches_last_step = st["launches"]
+        return st["loss"]
+
+    def _forward_backward(self, img, border_label, cell_label):
         net = self.net
         if not net.training:
             raise RuntimeError("call net.train() before a training step")
@@ -221,7 +272,7 @@ class TrainEngine:
                 head = convs[nl - 1]
                 pred = torch.empty((n, H, W), dtype=torch.float32, device=self.dev)
                 hw = head.weight.detach().float().reshape(-1).contiguous()
-                nat.check(self.L.mbs_head_fwd(xcur.data_ptr(), n * H * W, hw.numel(), hw.data_ptr(), float(head.bias.item()),
+                nat.check(self.L.mbs_head_fwd(xcur.data_ptr(), n * H * W, hw.numel(), hw.data_ptr(), head.bias.data_ptr(),
                                               pred.data_ptr(), self._sp()), "head_fwd")
                 preds.append(pred)
                 heads.append((head, hw))
@@ -302,11 +353,11 @@ class TrainEngine:
         cin = sum(cins)
         stride2 = lay.kind == "s2"
         # weight gradient: dW[co][tap][ci] (GEMM-packed layout) -> reference layout [Cout,Cin,3,3]
-        dzt = {0: self._chw(dz)}
+        dzt = self._chw3(dz, shifts=(0,))
         dwp = torch.zeros((cout, 9, cin), dtype=torch.float32, device=self.dev)
         off = 0
         for s, cs in zip(lay.srcs, cins):
-            xts = {sh: self._chw_cached(s, sh, 2 if stride2 else 1) for sh in (-1, 0, 1)}
+            xts = {sh: self._chw_cached(s, sh, 2) for sh in (-1, 0, 1)} if stride2 else self._chw3_cached(s)
             self._wgrad(1 if stride2 else 0, n, ho, wo, dzt, cout, xts, cs, dwp, cin, off)
             off += cs
         conv.weight.grad = dwp.view(cout, 3, 3, cin).permute(0, 3, 1, 2).contiguous()
@@ -342,7 +393,7 @@ class TrainEngine:
         n, h, w, cin = x.shape
         cout = dup.shape[-1]
         g = torch.zeros((cout, 4, cin), dtype=torch.float32, device=self.dev)
-        self._wgrad(2, n, h, w, {0: self._chw(dup, 0, 2), 1: self._chw(dup, 1, 2)}, cout, {0: self._chw_cached(x)}, cin, g, cin, 0)
+        self._wgrad(2, n, h, w, {0: self._chw(dup, 0, 2), 1: self._chw(dup, 1, 2)}, cout, {0: self._chw3_cached(x)[0]}, cin, g, cin, 0)
         conv.weight.grad = g.permute(2, 0, 1).reshape(cin, cout, 2, 2).contiguous()
         # data gradient = 2x2 stride-2 convolution of d(up) with W[ci][co][q]
         packed = conv.weight.detach().float().permute(0, 2, 3, 1).reshape(cin, 4, cout).to(torch.bfloat16).contiguous()

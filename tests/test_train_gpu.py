@@ -18,7 +18,7 @@ from oracle import net as onet
 pytestmark = pytest.mark.gpu
 
 
-def _setup(filters, seed, n, h, w):
+def _setup(filters, seed, n, h, w, graph=False):
     from microbeseg_b200.unets import build_unet
     from microbeseg_b200.training import TrainEngine
     net = build_unet("DU", "relu", "conv", "bn", torch.device("cuda:0"), 1, filters=list(filters))
@@ -29,7 +29,7 @@ def _setup(filters, seed, n, h, w):
     img = torch.from_numpy(rng.uniform(-1, 1, (n, 1, h, w)).astype(np.float32)).cuda()
     bl = torch.from_numpy(rng.uniform(0, 1, (n, 1, h, w)).astype(np.float32)).cuda()
     cl = torch.from_numpy(rng.uniform(0, 1, (n, 1, h, w)).astype(np.float32)).cuda()
-    return net, sd, TrainEngine(net), img, bl, cl
+    return net, sd, TrainEngine(net, use_graph=graph), img, bl, cl
 
 
 def _reference(sd, img, bl, cl, autocast=False):
@@ -89,3 +89,19 @@ def test_running_statistics_and_optimizer_step(native_lib):
     with torch.no_grad():
         b, c = net(img)
     assert torch.isfinite(b).all() and torch.isfinite(c).all()
+
+
+def test_cuda_graph_replay_matches_eager(native_lib):
+    """The captured step (one CUDA graph) must produce the same loss and gradients as the eager step."""
+    net, sd, eng, img, bl, cl = _setup((64, 128), 13, 2, 32, 32, graph=True)
+    net2, _, eng2, _, _, _ = _setup((64, 128), 13, 2, 32, 32, graph=False)
+    for it in range(3):                       # call 0 eager, call 1 captures + replays, call 2 replays
+        la = float(eng.forward_backward(img, bl, cl))
+        lb = float(eng2.forward_backward(img, bl, cl))
+        assert abs(la - lb) <= 2e-3 * abs(lb) + 1e-7, (it, la, lb)          # run-to-run atomics reorder -> ~3e-4 relative
+        for (n1, p1), (_, p2) in zip(net.named_parameters(), net2.named_parameters()):
+            if ".up.0.bias" in n1:
+                continue                      # exactly-zero gradient (BatchNorm follows): rounding noise only
+            # fp32 atomics reorder run to run -> bf16 roundings flip; the steps agree to a few % in L2 on this tiny batch, not bitwise
+            rel = float((p1.grad - p2.grad).norm() / (p2.grad.norm() + 1e-12))
+            assert rel < 0.15, (it, n1, rel)
