@@ -85,3 +85,35 @@ def test_tiff_roundtrip_and_cli_surface(tmp_path):
     assert out.returncode == 0
     for flag in ("--img_dir", "--model", "--thresholds", "--result_path", "--channel", "--device", "--overwrite"):
         assert flag in out.stdout
+
+
+def _ddp_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    sys.path.insert(0, ROOT)
+    from microbeseg_b200.training import allreduce_gradients
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.Conv2d(1, 4, 3), torch.nn.BatchNorm2d(4), torch.nn.Conv2d(4, 1, 1))
+    for i, p in enumerate(net.parameters()):
+        p.grad = torch.full_like(p, float(rank + 1) * (i + 1))
+    n = allreduce_gradients(net, world)
+    ok = all(torch.allclose(p.grad, torch.full_like(p, 1.5 * (i + 1))) for i, p in enumerate(net.parameters()))
+    if rank == 0:
+        q.put((ok, n, sum(p.numel() for p in net.parameters())))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_gradient_allreduce_two_ranks_gloo():
+    """Data-parallel exchange of the training step: one flat all-reduce, mean over ranks (replaces DataParallel)."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_ddp_worker, args=(r, 2, 29617, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    ok, n, total = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert ok and n == total

@@ -7,7 +7,7 @@ from microbeseg_b200.training import TrainEngine, train_step
 torch.manual_seed(0)
 dev = torch.device("cuda:0")
 net = build_unet("DU", "relu", "conv", "bn", dev, 1, filters=[64, 1024]).train()
-eng = TrainEngine(net)
+eng = TrainEngine(net, use_graph=False)
 opt = torch.optim.Adam(net.parameters(), lr=8e-4, amsgrad=True)
 B, S = 8, 320
 g = torch.Generator(device="cpu").manual_seed(0)
