@@ -197,16 +197,30 @@ def main():
 
     conv_ms = []
 
+    pp_stream = torch.cuda.Stream(device)
+    ev_net = [torch.cuda.Event() for _ in range(2)]
+    ev_pp = [torch.cuda.Event() for _ in range(2)]
+
     def frame_device(i, timed_events=None):
+        # same schedule as FrameSegmenter: post-processing of frame i on its own stream beside the network of frame i+1
         lo, hi = lohi[i % distinct]
+        main = torch.cuda.current_stream(device)
         border, cell = net.forward_frame(dev_frames[i % distinct], pads, lo, hi)
-        b = border[0, 0, pads[0]:, pads[1]:]
-        c = cell[0, 0, pads[0]:, pads[1]:]
-        pp.distance_postprocessing_device(b, c, th_seed, th_cell, out=out_dev)
+        ev_net[i & 1].record(main)
+        with torch.cuda.stream(pp_stream):
+            pp_stream.wait_event(ev_net[i & 1])
+            border.record_stream(pp_stream)
+            cell.record_stream(pp_stream)
+            b = border[0, 0, pads[0]:, pads[1]:]
+            c = cell[0, 0, pads[0]:, pads[1]:]
+            pp.distance_postprocessing_device(b, c, th_seed, th_cell, out=out_dev)
+            ev_pp[i & 1].record(pp_stream)
+        main.wait_event(ev_pp[(i + 1) & 1])        # keep at most one frame of post-processing in flight
 
     def step_device():
         for i in range(F):
             frame_device(i)
+        torch.cuda.current_stream(device).wait_stream(pp_stream)     # the step ends when its last mask exists
 
     def barrier():
         if world > 1:

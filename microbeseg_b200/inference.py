@@ -21,9 +21,10 @@ def shard_frames(num_frames, rank, world_size):
 
 
 class FrameSegmenter:
-    """Reusable pinned/device staging for one frame size, double buffered.  H2D, compute and D2H run on
-    three streams chained by events, so the copy of frame k+1 and the read-back of frame k-1 overlap
-    the network of frame k; frame min/max are reduced on the GPU (no host pass over the pixels)."""
+    """Reusable pinned/device staging for one frame size, double buffered.  H2D, network, post-processing and
+    D2H run on four streams chained by events: the copy of frame k+1, the post-processing of frame k-1 (small
+    latency-bound kernels that fit beside the persistent conv CTAs) and the read-back of frame k-2 overlap the
+    network of frame k; frame min/max are reduced on the GPU (no host pass over the pixels)."""
 
     def __init__(self, net, ths, device=None):
         self.net = net
@@ -34,6 +35,7 @@ class FrameSegmenter:
         self._stage = {}
         self.h2d_stream = torch.cuda.Stream(self.device)
         self.d2h_stream = torch.cuda.Stream(self.device)
+        self.pp_stream = torch.cuda.Stream(self.device)      # post-processing of frame k overlaps the network of frame k+1
 
     def _staging(self, shape, dtype, slot):
         key = (tuple(shape), np.dtype(dtype).str, slot)
@@ -47,7 +49,8 @@ class FrameSegmenter:
                       pin_out=torch.empty(shape, dtype=torch.int16).pin_memory(),
                       lohi=torch.empty(2, dtype=torch.float32, device=self.device),
                       scratch=torch.empty(2, dtype=torch.int32, device=self.device),
-                      ev_h2d=torch.cuda.Event(), ev_done=torch.cuda.Event(), ev_out=torch.cuda.Event())
+                      ev_h2d=torch.cuda.Event(), ev_net=torch.cuda.Event(), ev_done=torch.cuda.Event(),
+                      ev_out=torch.cuda.Event())
             self._stage[key] = st
         return st
 
@@ -74,11 +77,10 @@ class FrameSegmenter:
         main = torch.cuda.current_stream(self.device)
         with torch.cuda.device(self.device):
             with torch.cuda.stream(self.h2d_stream):
-                self.h2d_stream.wait_event(st["ev_done"])          # compute that read dev_in (2 frames ago) is done
+                self.h2d_stream.wait_event(st["ev_net"])           # the network that read dev_in (2 frames ago) is done
                 st["dev_in"].copy_(st["pin_in"], non_blocking=True)
                 st["ev_h2d"].record(self.h2d_stream)
             main.wait_event(st["ev_h2d"])
-            main.wait_event(st["ev_out"])                          # read-back of this slot's previous mask is done
             distance = len(getattr(self.net, "decoder_names", ())) == 2      # DU net = distance method, U net = boundary
             try:
                 if min_val is None or max_val is None:
@@ -89,28 +91,37 @@ class FrameSegmenter:
                     maps = self.net.forward_frame(st["dev_in"], pads, float(min_val), float(max_val))
             except RuntimeError:
                 # same contract as infer.py:352-356: a RuntimeError during net() yields an empty mask
-                st["dev_out"].zero_()
-                st["view"] = (cy, cx) if (cy, cx) != (0, 0) else None
+                maps = None
                 print('RuntimeError during inference (maybe not enough ram/vram?)')
-            else:
-                if distance:
-                    border, cell = maps
-                    b = border[0, 0, pads[0] + cy:, pads[1] + cx:]      # crop the pads (infer.py:358-359)
-                    c = cell[0, 0, pads[0] + cy:, pads[1] + cx:]
-                    run = lambda dst: pp.distance_postprocessing_device(b, c, self.th_seed, self.th_cell, out=dst)
-                else:
-                    # boundary method: softmax over the 3 classes, channel-last crop (infer.py:371-374)
-                    prob = torch.softmax(maps, dim=1)[0, :, pads[0] + cy:, pads[1] + cx:].permute(1, 2, 0)
-                    run = lambda dst: pp.boundary_postprocessing_device(prob, out=dst)
-                if (cy, cx) == (0, 0):
-                    run(st["dev_out"])
-                    st["view"] = None
-                else:
-                    small = run(None)
+            st["ev_net"].record(main)
+            with torch.cuda.stream(self.pp_stream):
+                self.pp_stream.wait_event(st["ev_net"])
+                self.pp_stream.wait_event(st["ev_out"])            # read-back of this slot's previous mask is done
+                if maps is None:
                     st["dev_out"].zero_()
-                    st["dev_out"][cy:, cx:] = small
-                    st["view"] = (cy, cx)
-            st["ev_done"].record(main)
+                    st["view"] = (cy, cx) if (cy, cx) != (0, 0) else None
+                else:
+                    if distance:
+                        border, cell = maps
+                        border.record_stream(self.pp_stream)
+                        cell.record_stream(self.pp_stream)
+                        b = border[0, 0, pads[0] + cy:, pads[1] + cx:]      # crop the pads (infer.py:358-359)
+                        c = cell[0, 0, pads[0] + cy:, pads[1] + cx:]
+                        run = lambda dst: pp.distance_postprocessing_device(b, c, self.th_seed, self.th_cell, out=dst)
+                    else:
+                        # boundary method: softmax over the 3 classes, channel-last crop (infer.py:371-374)
+                        maps.record_stream(self.pp_stream)
+                        prob = torch.softmax(maps, dim=1)[0, :, pads[0] + cy:, pads[1] + cx:].permute(1, 2, 0)
+                        run = lambda dst: pp.boundary_postprocessing_device(prob, out=dst)
+                    if (cy, cx) == (0, 0):
+                        run(st["dev_out"])
+                        st["view"] = None
+                    else:
+                        small = run(None)
+                        st["dev_out"].zero_()
+                        st["dev_out"][cy:, cx:] = small
+                        st["view"] = (cy, cx)
+                st["ev_done"].record(self.pp_stream)
             with torch.cuda.stream(self.d2h_stream):
                 self.d2h_stream.wait_event(st["ev_done"])
                 st["pin_out"].copy_(st["dev_out"], non_blocking=True)
