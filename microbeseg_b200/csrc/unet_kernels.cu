@@ -35,6 +35,7 @@ constexpr int BK = 64;   // bf16 elements per K chunk = 128 bytes = one swizzle 
 constexpr int A_BYTES = BM * BK * 2;
 constexpr int EPI_WARPS = 8;                     // 2 per TMEM lane quadrant (column halves)
 constexpr int NUM_THREADS = 64 + 32 * EPI_WARPS;  // warp0 TMA, warp1 MMA, then the epilogue warps
+__host__ __device__ constexpr int threads_for_groups(int ng) { return 64 + 128 * ng; }   // NG epilogue groups of 4 warps (one per TMEM lane quadrant)
 
 struct ConvKParams {
     int mode, act;
@@ -206,16 +207,16 @@ __device__ __forceinline__ float apply_act(float v, int act) {
 template <int BN, int TW>
 __device__ __forceinline__ void epilogue_tile(const ConvKParams &p, const float *s_par, uint32_t s_epi, float *s_head,
                                               uint32_t tmem_base, uint32_t tfull, uint32_t tempty, int lt, int quad,
-                                              int half, int lane, int x0, int y0, int img, int n0, bool has_head) {
-    const int buf = lt & 1;
+                                              int half, int lane, int x0, int y0, int img, int n0, bool has_head,
+                                              int acc_col, bool first_sub, bool last_sub) {
     const int row = quad * 32 + lane;
-    mbar_wait(tfull, (lt >> 1) & 1);
+    if (first_sub) mbar_wait(tfull, (lt >> 1) & 1);
     tcgen05_fence_after();
     float head_acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
 #pragma unroll 1
     for (int c = half * (BN / 2); c < (half + 1) * (BN / 2); c += 32) {
         uint32_t r[32];
-        tmem_ld32(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(buf * BN + c), r);
+        tmem_ld32(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(acc_col + c), r);
         const int col = n0 + c;
         int q = 0, co = col;
         if (p.mode == MBS_CONVT2X2_S2) {
@@ -328,7 +329,7 @@ __device__ __forceinline__ void epilogue_tile(const ConvKParams &p, const float 
     // all TMEM reads of this tile are complete (tcgen05.wait::ld inside tmem_ld32)
     tcgen05_fence_before();
     __syncwarp();
-    if (lane == 0) {
+    if (last_sub && lane == 0) {
         asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tempty) : "memory");
     }
     if (BN == 64 && has_head) {
@@ -353,27 +354,33 @@ __device__ __forceinline__ void epilogue_tile(const ConvKParams &p, const float 
     }
 }
 
-// TMA-store epilogue.  The 8 epilogue warps form two groups of 4 warps (one warp per TMEM lane quadrant).
+// TMA-store epilogue.  The epilogue warps form NG groups of 4 warps (one warp per TMEM lane quadrant); a single
+// warp converts ~1 column per 55 cycles (dependent TMEM load -> math -> smem store chains), so short-K layers
+// (transposed convs, K = 576 full-resolution convs) need 4 groups to keep up with the tensor pipe.
 // Work items are (tile, 64-column chunk) pairs dealt round-robin to the groups; a group converts its
 // chunk (TMEM -> fp32 math -> bf16), writes the 128-row x 128-byte tile into its own 16 KiB staging buffer in
 // the 128B-swizzled layout, and one elected thread hands it to the TMA engine (cp.async.bulk.tensor store),
 // which writes full lines, clips at the tensor boundary and keeps the LSU free.  The transposed conv uses a
 // 5-D view (C, dx, x, dy, y) of the 2x up-sampled destination, so its pixel-shuffle scatter is one box too.
 constexpr int STAGE_TILE_BYTES = 128 * 128;
-template <int BN, int TW>
+template <int BN, int TW, int NG>
 __device__ __forceinline__ void epilogue_tile_tma(const ConvKParams &p, const CUtensorMap *tmD, const float *s_par,
-                                                  uint32_t s_stage, uint32_t tmem_base, uint32_t tfull,
-                                                  uint32_t tempty, int lt, int group, int quad, int lane, bool leader,
+                                                  uint32_t s_stage, uint32_t tmem_base, uint32_t tfull0,
+                                                  uint32_t tempty0, int lt, int group, int quad, int lane, bool leader,
                                                   int x0, int y0, int img, int n0, bool has_head, bool &pending) {
     constexpr int CHUNKS = BN / 64;
-    if (CHUNKS == 1 && (lt & 1) != group) return;       // BN == 64: whole tiles alternate between the groups
-    const int buf = lt & 1;
+    // BN == 64: whole tiles are dealt round-robin to the groups, each group owning one TMEM accumulator
+    // (a group may run ahead of the others, so it must not share an mbarrier phase sequence with them)
+    constexpr int NBUF = CHUNKS == 1 ? NG : 2;
+    if (CHUNKS == 1 && (lt % NG) != group) return;
+    const int buf = lt % NBUF;
+    const uint32_t tfull = tfull0 + 8u * buf, tempty = tempty0 + 8u * buf;
     const int row = quad * 32 + lane;
-    mbar_wait(tfull, (lt >> 1) & 1);
+    mbar_wait(tfull, (lt / NBUF) & 1);
     tcgen05_fence_after();
     float head_acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
 #pragma unroll 1
-    for (int chn = (CHUNKS == 1 ? 0 : group); chn < CHUNKS; chn += (CHUNKS == 1 ? 1 : 2)) {
+    for (int chn = (CHUNKS == 1 ? 0 : group); chn < CHUNKS; chn += (CHUNKS == 1 ? 1 : NG)) {
         const int col0 = n0 + chn * 64;
         int q = 0, co0 = col0;
         if (p.mode == MBS_CONVT2X2_S2) {
@@ -491,14 +498,17 @@ __device__ __forceinline__ void epilogue_tile_tma(const ConvKParams &p, const CU
     }
 }
 
-template <int BN, int STAGES, bool TMA_EPI>
+// MT = pixel tiles (8 rows x 16 columns each, stacked in y) per work item: MT = 2 halves the weight
+// traffic L2 -> smem per MMA (one B tile feeds two accumulators), which is what bounds the Cout = 128 layers.
+template <int BN, int STAGES, bool TMA_EPI, int MT = 1, int NG = 2>
 struct SmemPlan {
     static constexpr int B_BYTES = BN * BK * 2;
+    static constexpr int A_STAGE = MT * A_BYTES;
     // TMA epilogue: two 16 KiB staging tiles (one per epilogue group); direct epilogue: per warp 32 rows x 16 bf16
     // plus the head partial sums
-    static constexpr int EPI_BYTES = TMA_EPI ? 2 * STAGE_TILE_BYTES : EPI_WARPS * 1024 + 2 * 4 * 128 * 4;
+    static constexpr int EPI_BYTES = TMA_EPI ? NG * STAGE_TILE_BYTES : EPI_WARPS * 1024 + 2 * 4 * 128 * 4;
     static constexpr int OFF_A = 0;
-    static constexpr int OFF_B = STAGES * A_BYTES;
+    static constexpr int OFF_B = STAGES * A_STAGE;
     static constexpr int OFF_EPI = OFF_B + STAGES * B_BYTES;
     static constexpr int OFF_BAR = OFF_EPI + EPI_BYTES;           // full[S], empty[S], tmem_full[2], tmem_empty[2]
     static constexpr int OFF_TMEM = OFF_BAR + 8 * (2 * STAGES + 4);
@@ -510,11 +520,15 @@ struct SmemPlan {
 // Persistent, warp-specialised implicit-GEMM kernel.  Each CTA walks tiles t = blockIdx.x, +gridDim.x, ...
 // The smem ring (TMA <-> MMA) runs continuously across tiles; the accumulator is double buffered in
 // TMEM so that the epilogue of tile i overlaps the MMAs of tile i+1.
-template <int BN, int STAGES, int MIN_CTAS, bool TMA_EPI>
-__global__ void __launch_bounds__(NUM_THREADS, MIN_CTAS)
+template <int BN, int STAGES, int MIN_CTAS, bool TMA_EPI, int MT = 1, int NG = 2>
+__global__ void __launch_bounds__(threads_for_groups(NG), MIN_CTAS)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                  const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmD, const ConvKParams p) {
-    using Plan = SmemPlan<BN, STAGES, TMA_EPI>;
+    using Plan = SmemPlan<BN, STAGES, TMA_EPI, MT, NG>;
+    static_assert(NG == 2 || (TMA_EPI && BN >= 128), "extra epilogue groups only with the TMA-store epilogue of wide tiles");
+    static_assert(MT == 1 || !TMA_EPI, "the TMA-store epilogue handles one pixel tile per work item");
+    static_assert(2 * MT * BN <= 512, "accumulators exceed TMEM");
+    constexpr int A_STAGE = Plan::A_STAGE;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;
@@ -545,13 +559,13 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         }
         for (int b = 0; b < 2; ++b) {
             mbar_init(tfull_bar(b), 1);
-            mbar_init(tempty_bar(b), (TMA_EPI && BN == 64) ? 4 : EPI_WARPS);   // one arrive per participating epilogue warp
+            mbar_init(tempty_bar(b), (TMA_EPI && BN == 64) ? 4 : 4 * NG);   // one arrive per participating epilogue warp
         }
         fence_barrier_init();
     }
-    if (warp == 1) tmem_alloc(smem_u32(const_cast<uint32_t *>(tmem_ptr)), 2 * BN);
+    if (warp == 1) tmem_alloc(smem_u32(const_cast<uint32_t *>(tmem_ptr)), 2 * MT * BN);
     if (warp >= 2) {
-        for (int j = threadIdx.x - 64; j < p.Cout; j += NUM_THREADS - 64) {
+        for (int j = threadIdx.x - 64; j < p.Cout; j += threads_for_groups(NG) - 64) {
             s_par[j] = p.bias[j];
             s_par[p.Cout + j] = p.scale[j];
             s_par[2 * p.Cout + j] = p.shift[j];
@@ -573,12 +587,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                 const int tx = m_tile % p.tiles_x;
                 const int ty = (m_tile / p.tiles_x) % p.tiles_y;
                 const int img = m_tile / tiles_per_img;
-                const int x0 = tx * TILE_W, y0 = ty * TILE_H, n0 = n_tile * BN;
+                const int x0 = tx * TILE_W, y0 = ty * (TILE_H * MT), n0 = n_tile * BN;
                 for (int it = 0; it < num_k_iters; ++it, ++it_g) {
                     const int s = it_g % STAGES;
                     const uint32_t ph = (it_g / STAGES) & 1;
                     mbar_wait(empty_bar(s), ph ^ 1u);
-                    mbar_expect_tx(full_bar(s), A_BYTES + Plan::B_BYTES);
+                    mbar_expect_tx(full_bar(s), A_STAGE + Plan::B_BYTES);
                     const int tap = it / chunks;
                     const int cc = it - tap * chunks;
                     int cx, cy;
@@ -596,9 +610,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                         cy = y0;
                     }
                     if (cc < p.chunks0)
-                        tma_load_4d(sA + s * A_BYTES, &tmA0, full_bar(s), cc * BK, cx, cy, img);
+                        tma_load_4d(sA + s * A_STAGE, &tmA0, full_bar(s), cc * BK, cx, cy, img);
                     else
-                        tma_load_4d(sA + s * A_BYTES, &tmA1, full_bar(s), (cc - p.chunks0) * BK, cx, cy, img);
+                        tma_load_4d(sA + s * A_STAGE, &tmA1, full_bar(s), (cc - p.chunks0) * BK, cx, cy, img);
                     tma_load_2d(sB + s * Plan::B_BYTES, &tmB, full_bar(s), it * BK, n0);
                 }
             }
@@ -613,22 +627,26 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                 const int buf = lt & 1;
                 mbar_wait(tempty_bar(buf), ((lt >> 1) & 1) ^ 1u);   // epilogue drained this accumulator
                 tcgen05_fence_after();
-                const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(buf * BN);
+                const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(buf * MT * BN);
                 for (int it = 0; it < num_k_iters; ++it, ++it_g) {
                     const int s = it_g % STAGES;
                     const uint32_t ph = (it_g / STAGES) & 1;
                     mbar_wait(full_bar(s), ph);
                     tcgen05_fence_after();
-                    const uint64_t adesc = make_sw128_desc(sA + s * A_BYTES);
+                    const uint64_t adesc = make_sw128_desc(sA + s * A_STAGE);
                     const uint64_t bdesc = make_sw128_desc(sB + s * Plan::B_BYTES);
 #pragma unroll
-                    for (int k = 0; k < BK / 16; ++k) {
-                        // advance 32 bytes (16 bf16) inside the 128-byte swizzle row: +2 in the >>4 encoding
-                        umma_f16(tmem_d, adesc + 2u * k, bdesc + 2u * k, idesc, (it > 0 || k > 0) ? 1u : 0u);
+                    for (int mt = 0; mt < MT; ++mt) {
+#pragma unroll
+                        for (int k = 0; k < BK / 16; ++k) {
+                            // advance 32 bytes (16 bf16) inside the 128-byte swizzle row: +2 in the >>4 encoding
+                            umma_f16(tmem_d + static_cast<uint32_t>(mt * BN), adesc + (mt * (A_BYTES >> 4)) + 2u * k,
+                                     bdesc + 2u * k, idesc, (it > 0 || k > 0) ? 1u : 0u);
+                        }
                     }
                     umma_commit(empty_bar(s));  // frees the smem slot when these MMAs retire
                 }
-                umma_commit(tfull_bar(buf));     // accumulator of this tile complete
+                umma_commit(tfull_bar(buf));     // accumulators of this work item complete
             }
         }
         __syncwarp();
@@ -650,13 +668,17 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
             const int tx = m_tile % p.tiles_x;
             const int ty = (m_tile / p.tiles_x) % p.tiles_y;
             const int img = m_tile / tiles_per_img;
-            const int x0 = tx * TILE_W, y0 = ty * TILE_H, n0 = n_tile * BN;
-            if (TMA_EPI)
-                epilogue_tile_tma<BN, TILE_W>(p, &tmD, s_par, s_stage, tmem_base, tfull_bar(lt & 1), tempty_bar(lt & 1), lt,
-                                              half, quad, lane, leader, x0, y0, img, n0, has_head, pending);
-            else
-                epilogue_tile<BN, TILE_W>(p, s_par, s_epi, s_head, tmem_base, tfull_bar(lt & 1), tempty_bar(lt & 1), lt,
-                                          quad, half, lane, x0, y0, img, n0, has_head);
+            const int x0 = tx * TILE_W, y0 = ty * (TILE_H * MT), n0 = n_tile * BN;
+            if (TMA_EPI) {
+                epilogue_tile_tma<BN, TILE_W, NG>(p, &tmD, s_par, s_stage, tmem_base, tfull_bar(0), tempty_bar(0), lt,
+                                                  half, quad, lane, leader, x0, y0, img, n0, has_head, pending);
+            } else {
+#pragma unroll
+                for (int mt = 0; mt < MT; ++mt)
+                    epilogue_tile<BN, TILE_W>(p, s_par, s_epi, s_head, tmem_base, tfull_bar(lt & 1), tempty_bar(lt & 1), lt,
+                                              quad, half, lane, x0, y0 + mt * TILE_H, img, n0, has_head,
+                                              (lt & 1) * MT * BN + mt * BN, mt == 0, mt == MT - 1);
+            }
         }
         if (TMA_EPI && leader && pending) tma_store_wait_all();
     }
@@ -664,7 +686,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     __syncthreads();
     if (warp == 1) {
         tcgen05_fence_after();
-        tmem_dealloc(tmem_base, 2 * BN);
+        tmem_dealloc(tmem_base, 2 * MT * BN);
     }
 }
 
@@ -688,14 +710,14 @@ constexpr int HALO_BYTES = HALO_W * HALO_H * 128;              // 23040
 constexpr int HALO_SLOT = (HALO_BYTES + 1023) / 1024 * 1024;   // 23552
 constexpr int W_TILE_BYTES = 64 * 128;                         // one (tap, chunk) weight tile, N = 64
 
-template <int CHUNKS, int STAGES>
+template <int CHUNKS, int STAGES, int NG>
 struct HaloPlan {
     static constexpr int OFF_W = 0;
     static constexpr int OFF_A = 9 * CHUNKS * W_TILE_BYTES;
     static constexpr int OFF_EPI = OFF_A + STAGES * HALO_SLOT;
-    static constexpr int EPI_BYTES = 2 * STAGE_TILE_BYTES;     // TMA-store staging, one tile per epilogue group
-    static constexpr int OFF_BAR = OFF_EPI + EPI_BYTES;        // full[S], empty[S], tfull[2], tempty[2], wbar
-    static constexpr int OFF_TMEM = OFF_BAR + 8 * (2 * STAGES + 5);
+    static constexpr int EPI_BYTES = NG * STAGE_TILE_BYTES;    // TMA-store staging, one tile per epilogue group
+    static constexpr int OFF_BAR = OFF_EPI + EPI_BYTES;        // full[S], empty[S], tfull[NG], tempty[NG], wbar
+    static constexpr int OFF_TMEM = OFF_BAR + 8 * (2 * STAGES + 2 * NG + 1);
     static constexpr int OFF_PAR = (OFF_TMEM + 8 + 15) / 16 * 16;
     static constexpr int DYN_BYTES = OFF_PAR + 7 * 64 * 4 + 1024;
 };
@@ -710,13 +732,14 @@ __device__ __forceinline__ uint64_t make_sw128_desc_sbo(uint32_t saddr, uint32_t
     return d;
 }
 
-template <int CHUNKS, int STAGES>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+template <int CHUNKS, int STAGES, int NG>
+__global__ void __launch_bounds__(threads_for_groups(NG), 1)
 conv_halo64_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                    const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmD,
                    const ConvKParams p) {
-    using Plan = HaloPlan<CHUNKS, STAGES>;
+    using Plan = HaloPlan<CHUNKS, STAGES, NG>;
     constexpr int BN = 64;
+    static_assert(NG == 2 || NG == 4, "TMEM allocations are powers of two");
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;
@@ -727,8 +750,8 @@ conv_halo64_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
     auto full_bar = [&](int s) { return sBar + 8u * s; };
     auto empty_bar = [&](int s) { return sBar + 8u * (STAGES + s); };
     auto tfull_bar = [&](int b) { return sBar + 8u * (2 * STAGES + b); };
-    auto tempty_bar = [&](int b) { return sBar + 8u * (2 * STAGES + 2 + b); };
-    const uint32_t w_bar = sBar + 8u * (2 * STAGES + 4);
+    auto tempty_bar = [&](int b) { return sBar + 8u * (2 * STAGES + NG + b); };
+    const uint32_t w_bar = sBar + 8u * (2 * STAGES + 2 * NG);
     volatile uint32_t *tmem_ptr = reinterpret_cast<volatile uint32_t *>(gbase + Plan::OFF_TMEM);
     float *s_par = reinterpret_cast<float *>(gbase + Plan::OFF_PAR);
 
@@ -744,16 +767,16 @@ conv_halo64_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
             mbar_init(full_bar(s), 1);
             mbar_init(empty_bar(s), 1);
         }
-        for (int b = 0; b < 2; ++b) {
+        for (int b = 0; b < NG; ++b) {
             mbar_init(tfull_bar(b), 1);
-            mbar_init(tempty_bar(b), 4);     // BN == 64: tiles alternate between the two epilogue groups
+            mbar_init(tempty_bar(b), 4);     // BN == 64: tiles are dealt round-robin to the epilogue groups
         }
         mbar_init(w_bar, 1);
         fence_barrier_init();
     }
-    if (warp == 1) tmem_alloc(smem_u32(const_cast<uint32_t *>(tmem_ptr)), 2 * BN);
+    if (warp == 1) tmem_alloc(smem_u32(const_cast<uint32_t *>(tmem_ptr)), NG * BN);
     if (warp >= 2) {
-        for (int j = threadIdx.x - 64; j < 64; j += NUM_THREADS - 64) {
+        for (int j = threadIdx.x - 64; j < 64; j += threads_for_groups(NG) - 64) {
             s_par[j] = p.bias[j];
             s_par[64 + j] = p.scale[j];
             s_par[128 + j] = p.shift[j];
@@ -794,8 +817,8 @@ conv_halo64_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
             mbar_wait(w_bar, 0);
             int it_g = 0, lt = 0;
             for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++lt) {
-                const int buf = lt & 1;
-                mbar_wait(tempty_bar(buf), ((lt >> 1) & 1) ^ 1u);
+                const int buf = lt % NG;
+                mbar_wait(tempty_bar(buf), ((lt / NG) & 1) ^ 1u);
                 tcgen05_fence_after();
                 const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(buf * BN);
 #pragma unroll
@@ -833,8 +856,8 @@ conv_halo64_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
             const int tx = tile % p.tiles_x;
             const int ty = (tile / p.tiles_x) % p.tiles_y;
             const int img = tile / tiles_per_img;
-            epilogue_tile_tma<BN, HT_W>(p, &tmD, s_par, s_stage, tmem_base, tfull_bar(lt & 1), tempty_bar(lt & 1), lt, group,
-                                        quad, lane, leader, tx * HT_W, ty * HT_H, img, 0, has_head, pending);
+            epilogue_tile_tma<BN, HT_W, NG>(p, &tmD, s_par, s_stage, tmem_base, tfull_bar(0), tempty_bar(0), lt, group,
+                                            quad, lane, leader, tx * HT_W, ty * HT_H, img, 0, has_head, pending);
         }
         if (leader && pending) tma_store_wait_all();
     }
@@ -842,7 +865,7 @@ conv_halo64_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
     __syncthreads();
     if (warp == 1) {
         tcgen05_fence_after();
-        tmem_dealloc(tmem_base, 2 * BN);
+        tmem_dealloc(tmem_base, NG * BN);
     }
 }
 
@@ -988,84 +1011,127 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
 // once in shared memory (one IEEE division per input pixel instead of nine per output channel group);
 // thread (g, px) keeps the 72 weights of its 8 output channels in registers and walks 8 rows, so the
 // only smem traffic in the inner loop is the 9 input taps; a warp stores 4 pixels x 128 B contiguously.
-constexpr int FC_TW = 32, FC_TH = 8;
-template <typename T>
-__global__ void __launch_bounds__(256)
+constexpr int FC_TW = 32, FC_TH = 36;   // tall tiles (a multiple of 3 rows): the 96 per-thread weight/affine loads amortise over 36 rows
+static_assert(FC_TH % 3 == 0, "the row loop rotates three register rows");
+
+__device__ __forceinline__ uint64_t pack_f32x2(float a, float b) {
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+    return r;
+}
+__device__ __forceinline__ void unpack_f32x2(uint64_t v, float &a, float &b) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+}
+__device__ __forceinline__ uint64_t fma_f32x2(uint64_t a, uint64_t b, uint64_t c) {   // sm_100 FFMA2
+    uint64_t d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+// Persistent: each CTA keeps its 8-channel slice of the weights / affine in registers and walks 32x36-pixel tiles.
+template <typename T, bool RELU>
+__global__ void __launch_bounds__(256, 2)
 first_conv_kernel(const T *__restrict__ img, int H, int W, int pad_y, int pad_x, float lo, float hi,
                   const float *__restrict__ lohi_dev, const float *__restrict__ weight, const float *__restrict__ bias,
                   const float *__restrict__ scale, const float *__restrict__ shift, int C, int act,
-                  __nv_bfloat16 *__restrict__ out, int ld, int coff) {
+                  __nv_bfloat16 *__restrict__ out, int ld, int coff, int tiles_x, int num_tiles) {
     __shared__ float s_in[FC_TH + 2][FC_TW + 2];
     if (lohi_dev) {                 // frame min / max computed on the device (mbs_frame_minmax)
         lo = lohi_dev[0];
         hi = lohi_dev[1];
     }
     const int Hp = H + pad_y, Wp = W + pad_x;
-    const int x0 = blockIdx.x * FC_TW, y0 = blockIdx.y * FC_TH;
     const float range = hi - lo;
-    for (int i = threadIdx.x; i < (FC_TH + 2) * (FC_TW + 2); i += 256) {
-        const int r = i / (FC_TW + 2), c = i - r * (FC_TW + 2);
-        const int yy = y0 + r - 1, xx = x0 + c - 1;
-        float v = 0.0f;  // conv zero padding outside the (padded) model input
-        if (yy >= 0 && yy < Hp && xx >= 0 && xx < Wp) {
-            float raw = lo;  // zero_pad_model_input pad value = frame min (utils.py:124, infer.py:256)
-            if (yy >= pad_y && xx >= pad_x) raw = static_cast<float>(img[static_cast<size_t>(yy - pad_y) * W + (xx - pad_x)]);
-            // 2 * (f32(img) - min) / (max - min) - 1, evaluated left to right in f32 (infer.py:346);
-            // hi < lo: the caller already normalised the image (drop-in net(x) path) -> pass through
-            v = hi < lo ? raw : __fsub_rn(__fdiv_rn(__fmul_rn(2.0f, __fsub_rn(raw, lo)), range), 1.0f);
-        }
-        s_in[r][c] = v;
-    }
     const int g = threadIdx.x & 7;           // channel group (8 channels) inside a 64-channel slab
     const int px = threadIdx.x >> 3;         // pixel column inside the tile
-    __syncthreads();
+    const size_t row_stride = static_cast<size_t>(Wp) * ld;
     for (int cbase = 0; cbase < C; cbase += 64) {
         const int c0 = cbase + g * 8;
-        if (c0 >= C) break;
-        float w[8][9], b8[8], sc8[8], sh8[8];
+        const bool live = c0 < C;
+        // channel pairs in 64-bit registers: one FFMA2 (fma.rn.f32x2, each half an IEEE fma) per tap and pair
+        uint64_t w2[4][9], b2[4], sc2[4], sh2[4];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
+        for (int u = 0; u < 4; ++u) {
+            const int ca = live ? c0 + 2 * u : 0, cb = live ? c0 + 2 * u + 1 : 0;
 #pragma unroll
-            for (int t = 0; t < 9; ++t) w[u][t] = weight[(c0 + u) * 9 + t];
-            b8[u] = bias[c0 + u];
-            sc8[u] = scale[c0 + u];
-            sh8[u] = shift[c0 + u];
+            for (int t = 0; t < 9; ++t) w2[u][t] = pack_f32x2(weight[ca * 9 + t], weight[cb * 9 + t]);
+            b2[u] = pack_f32x2(bias[ca], bias[cb]);
+            sc2[u] = pack_f32x2(scale[ca], scale[cb]);
+            sh2[u] = pack_f32x2(shift[ca], shift[cb]);
         }
-        const int X = x0 + px;
-#pragma unroll 2
-        for (int r = 0; r < FC_TH; ++r) {
-            const int Y = y0 + r;
-            float in[9];
-#pragma unroll
-            for (int t = 0; t < 9; ++t) in[t] = s_in[r + t / 3][px + t % 3];
-            float acc[8];
-#pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                float a = 0.0f;
-#pragma unroll
-                for (int t = 0; t < 9; ++t) a = fmaf(in[t], w[u][t], a);
-                acc[u] = a + b8[u];
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            const int x0 = (tile % tiles_x) * FC_TW, y0 = (tile / tiles_x) * FC_TH;
+            __syncthreads();         // everyone is done with the previous tile's patch
+            // (prefetching the next patch into registers during the FMA loop was measured: no gain, more spills)
+            for (int i = threadIdx.x; i < (FC_TH + 2) * (FC_TW + 2); i += 256) {
+                const int r = i / (FC_TW + 2), c = i - r * (FC_TW + 2);
+                const int yy = y0 + r - 1, xx = x0 + c - 1;
+                float v = 0.0f;  // conv zero padding outside the (padded) model input
+                if (yy >= 0 && yy < Hp && xx >= 0 && xx < Wp) {
+                    float raw = lo;  // zero_pad_model_input pad value = frame min (utils.py:124, infer.py:256)
+                    if (yy >= pad_y && xx >= pad_x) raw = static_cast<float>(img[static_cast<size_t>(yy - pad_y) * W + (xx - pad_x)]);
+                    // 2 * (f32(img) - min) / (max - min) - 1, evaluated left to right in f32 (infer.py:346);
+                    // hi < lo: the caller already normalised the image (drop-in net(x) path) -> pass through
+                    v = hi < lo ? raw : __fsub_rn(__fdiv_rn(__fmul_rn(2.0f, __fsub_rn(raw, lo)), range), 1.0f);
+                }
+                s_in[r][c] = v;
             }
-            switch (act) {      // one uniform branch per row, not per element
-                case MBS_ACT_RELU:
+            __syncthreads();
+            if (!live) continue;
+            const int X = x0 + px;
+            __nv_bfloat16 *drow = out + (static_cast<size_t>(y0) * Wp + X) * ld + coff + c0;
+            // one output row from the three input rows top / mid / bot (3 floats each)
+            auto do_row = [&](int r, const float (&top)[3], const float (&mid)[3], const float (&bot)[3]) {
+                uint64_t acc2[4];
 #pragma unroll
-                    for (int u = 0; u < 8; ++u) acc[u] = fmaxf(acc[u], 0.0f);
-                    break;
-                case MBS_ACT_NONE: break;
-                default:
+                for (int u = 0; u < 4; ++u) {
+                    uint64_t a = b2[u];
 #pragma unroll
-                    for (int u = 0; u < 8; ++u) acc[u] = apply_act(acc[u], act);
-                    break;
+                    for (int t = 0; t < 3; ++t) a = fma_f32x2(pack_f32x2(top[t], top[t]), w2[u][t], a);
+#pragma unroll
+                    for (int t = 0; t < 3; ++t) a = fma_f32x2(pack_f32x2(mid[t], mid[t]), w2[u][3 + t], a);
+#pragma unroll
+                    for (int t = 0; t < 3; ++t) a = fma_f32x2(pack_f32x2(bot[t], bot[t]), w2[u][6 + t], a);
+                    acc2[u] = a;
+                }
+                float v[8];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) unpack_f32x2(acc2[u], v[2 * u], v[2 * u + 1]);
+                if (RELU) {
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) v[u] = fmaxf(v[u], 0.0f);
+                } else if (act != MBS_ACT_NONE) {        // one uniform branch per row
+#pragma unroll 1
+                    for (int u = 0; u < 8; ++u) v[u] = apply_act(v[u], act);
+                }
+                uint32_t packed[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    float a0, a1;
+                    unpack_f32x2(fma_f32x2(pack_f32x2(v[2 * u], v[2 * u + 1]), sc2[u], sh2[u]), a0, a1);
+                    __nv_bfloat162 h2 = __floats2bfloat162_rn(a0, a1);
+                    packed[u] = *reinterpret_cast<uint32_t *>(&h2);
+                }
+                if (y0 + r < Hp && X < Wp)
+                    *reinterpret_cast<uint4 *>(drow + r * row_stride) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+            };
+            float ra[3], rb[3], rc[3];
+#pragma unroll
+            for (int t = 0; t < 3; ++t) {
+                ra[t] = s_in[0][px + t];
+                rb[t] = s_in[1][px + t];
             }
-            uint32_t packed[4];
+            // rows in groups of three with rotating register names: 3 new smem reads per output row, no moves
+#pragma unroll 1
+            for (int r = 0; r < FC_TH; r += 3) {
 #pragma unroll
-            for (int u = 0; u < 8; u += 2) {
-                __nv_bfloat162 h2 = __floats2bfloat162_rn(fmaf(acc[u], sc8[u], sh8[u]), fmaf(acc[u + 1], sc8[u + 1], sh8[u + 1]));
-                packed[u >> 1] = *reinterpret_cast<uint32_t *>(&h2);
-            }
-            if (Y < Hp && X < Wp) {
-                uint4 *d = reinterpret_cast<uint4 *>(out + (static_cast<size_t>(Y) * Wp + X) * ld + coff + c0);
-                *d = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+                for (int t = 0; t < 3; ++t) rc[t] = s_in[r + 2][px + t];
+                do_row(r, ra, rb, rc);
+#pragma unroll
+                for (int t = 0; t < 3; ++t) ra[t] = s_in[r + 3][px + t];
+                do_row(r + 1, rb, rc, ra);
+#pragma unroll
+                for (int t = 0; t < 3; ++t) rb[t] = s_in[r + 4][px + t];
+                do_row(r + 2, rc, ra, rb);
             }
         }
     }
@@ -1224,19 +1290,19 @@ int make_convT_store_map(CUtensorMap *map, const void *base, int N, int H_in, in
     return 0;
 }
 
-template <int BN, int STAGES, int CTAS_PER_SM, bool TMA_EPI>
+template <int BN, int STAGES, int CTAS_PER_SM, bool TMA_EPI, int MT = 1, int NG = 2>
 int launch_conv(const CUtensorMap &a0, const CUtensorMap &a1, const CUtensorMap &b, const CUtensorMap &dmap,
                 const ConvKParams &kp, cudaStream_t stream) {
-    using Plan = SmemPlan<BN, STAGES, TMA_EPI>;
+    using Plan = SmemPlan<BN, STAGES, TMA_EPI, MT, NG>;
     static int configured_bytes = 0;
     const int dyn = Plan::dyn_bytes(kp.Cout);
     if (dyn > configured_bytes) {
-        MBS_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<BN, STAGES, CTAS_PER_SM, TMA_EPI>,
+        MBS_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<BN, STAGES, CTAS_PER_SM, TMA_EPI, MT, NG>,
                                             cudaFuncAttributeMaxDynamicSharedMemorySize, dyn));
         configured_bytes = dyn;
     }
     const int grid = kp.num_tiles < sm_count() * CTAS_PER_SM ? kp.num_tiles : sm_count() * CTAS_PER_SM;
-    conv_gemm_kernel<BN, STAGES, CTAS_PER_SM, TMA_EPI><<<grid, NUM_THREADS, dyn, stream>>>(a0, a1, b, dmap, kp);
+    conv_gemm_kernel<BN, STAGES, CTAS_PER_SM, TMA_EPI, MT, NG><<<grid, threads_for_groups(NG), dyn, stream>>>(a0, a1, b, dmap, kp);
     MBS_CHECK_LAUNCH();
     return 0;
 }
@@ -1274,20 +1340,38 @@ int launch_wgrad(const CUtensorMap *a, const CUtensorMap *b, const WgradParams &
     return 0;
 }
 
-template <int CHUNKS, int STAGES>
+template <int CHUNKS, int STAGES, int NG>
 int launch_halo(const CUtensorMap &a0, const CUtensorMap &a1, const CUtensorMap &b, const CUtensorMap &dmap,
                 const ConvKParams &kp, cudaStream_t stream) {
-    using Plan = HaloPlan<CHUNKS, STAGES>;
+    using Plan = HaloPlan<CHUNKS, STAGES, NG>;
     static bool configured = false;
     if (!configured) {
-        MBS_CHECK_CUDA(cudaFuncSetAttribute(conv_halo64_kernel<CHUNKS, STAGES>,
+        MBS_CHECK_CUDA(cudaFuncSetAttribute(conv_halo64_kernel<CHUNKS, STAGES, NG>,
                                             cudaFuncAttributeMaxDynamicSharedMemorySize, Plan::DYN_BYTES));
         configured = true;
     }
     const int grid = kp.num_tiles < sm_count() ? kp.num_tiles : sm_count();
-    conv_halo64_kernel<CHUNKS, STAGES><<<grid, NUM_THREADS, Plan::DYN_BYTES, stream>>>(a0, a1, b, dmap, kp);
+    conv_halo64_kernel<CHUNKS, STAGES, NG><<<grid, threads_for_groups(NG), Plan::DYN_BYTES, stream>>>(a0, a1, b, dmap, kp);
     MBS_CHECK_LAUNCH();
     return 0;
+}
+
+int epi_variant() {     // MBS_EPI_VARIANT (A/B runs): 0 default; 1 = transposed convs on 128-column tiles; 3 = 4 epilogue groups in the halo kernel
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("MBS_EPI_VARIANT");
+        v = e ? atoi(e) : 0;
+    }
+    return v;
+}
+
+bool pair_enabled() {
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("MBS_NO_PAIR");
+        v = (e && e[0] == '1') ? 0 : 1;
+    }
+    return v == 1;
 }
 
 bool halo_enabled() {
@@ -1371,23 +1455,35 @@ extern "C" int mbs_conv_gemm(const mbs_conv_desc *d, void *stream_) {
             rc = make_act_map(&dm, d->dst, d->N, kp.Hd, kp.Wd, d->Cout, d->ldd, d->coffd, 1, HT_W, HT_H);
             if (rc) return rc;
         }
-        if (d->C1 > 0) return launch_halo<2, 2>(a0, a1, b, dm, kp, stream);
-        return launch_halo<1, 4>(a0, a1, b, dm, kp, stream);
+        if (d->C1 > 0) return launch_halo<2, 2, 2>(a0, a1, b, dm, kp, stream);
+        // measured: 4 epilogue groups do not help here (64->64 @2048^2: 0.333 vs 0.324 ms) -- the MMAs' own smem
+        // reads bound this layer, and more epilogue warps compete for the same smem bandwidth
+        if (epi_variant() == 3) return launch_halo<1, 3, 4>(a0, a1, b, dm, kp, stream);
+        return launch_halo<1, 4, 2>(a0, a1, b, dm, kp, stream);
     }
 
     const int ncols = d->mode == MBS_CONVT2X2_S2 ? 4 * d->Cout : d->Cout;
     const int K = kp.taps * (d->C0 + d->C1);
     int bn = ncols % 256 == 0 ? 256 : (ncols % 128 == 0 ? 128 : 64);
-    // transposed convs have a short K loop and are epilogue/bandwidth bound: prefer two resident CTAs
-    // (the TMA-store path of the transposed conv needs whole patches per image in its folded (N*H) dimension)
-    if (d->mode == MBS_CONVT2X2_S2 && d->C0 <= 256 && (d->N == 1 || d->H % TILE_H == 0)) bn = 128;
+    // transposed convs have a short K loop and are epilogue/bandwidth bound.  Up to 256 input channels: all four
+    // (dy,dx) taps of 64 output channels in one 256-column tile (A read once), TMA-store epilogue with 4 groups
+    // (measured 128->64 @1024^2: 0.146 ms vs 0.202 with 2 groups on 128-column tiles; 256->128 @512^2: 0.102 vs
+    // 0.122).  Deeper ones keep the direct epilogue (512->256 @256^2: 0.083 both; 1024->512 @128^2: 0.064 vs 0.072).
+    // (the TMA-store path needs whole patches per image in its folded (N*H) dimension)
+    const bool convT_tma = d->mode == MBS_CONVT2X2_S2 && d->C0 <= 256 && (d->N == 1 || d->H % TILE_H == 0);
+    if (convT_tma) bn = (epi_variant() != 1 && ncols % 256 == 0) ? 256 : 128;
     kp.n_tiles = ncols / bn;
+    // Cout = 128 layers: two stacked pixel tiles per work item share each weight tile (see SmemPlan)
+    const bool pair = pair_enabled() && bn == 128 && d->mode != MBS_CONVT2X2_S2 &&
+                      static_cast<long long>(d->N) * kp.tiles_x * mbs::cdiv(kp.Hm, 2 * TILE_H) >= sm_count();
+    const int mt = pair ? 2 : 1;
+    kp.tiles_y = mbs::cdiv(kp.Hm, TILE_H * mt);
 
     CUtensorMap a0, a1, b;
-    int rc = make_act_map(&a0, d->src0, d->N, d->H, d->W, d->C0, d->ld0, d->coff0, es);
+    int rc = make_act_map(&a0, d->src0, d->N, d->H, d->W, d->C0, d->ld0, d->coff0, es, TILE_W, TILE_H * mt);
     if (rc) return rc;
     if (d->C1 > 0) {
-        rc = make_act_map(&a1, d->src1, d->N, d->H, d->W, d->C1, d->ld1, d->coff1, es);
+        rc = make_act_map(&a1, d->src1, d->N, d->H, d->W, d->C1, d->ld1, d->coff1, es, TILE_W, TILE_H * mt);
         if (rc) return rc;
     } else {
         a1 = a0;
@@ -1399,18 +1495,20 @@ extern "C" int mbs_conv_gemm(const mbs_conv_desc *d, void *stream_) {
     MBS_REQUIRE(tiles_ll > 0 && tiles_ll < (1ll << 31), "too many tiles");
     kp.num_tiles = static_cast<int>(tiles_ll);
     MBS_REQUIRE(d->Cout <= 1024, "Cout > 1024 is not supported by the epilogue parameter staging");
-    if (bn == 256) return launch_conv<256, 4, 1, false>(a0, a1, b, a0, kp, stream);
-    if (d->mode == MBS_CONVT2X2_S2) {
-        // short-K transposed conv: TMA-store epilogue (5-D pixel-shuffle view of the destination), one CTA per SM
+    if (convT_tma) {
+        // short-K transposed conv: TMA-store epilogue (5-D pixel-shuffle view of the destination), 4 epilogue groups
         CUtensorMap dm = a0;
         if (d->dst) {
             rc = make_convT_store_map(&dm, d->dst, d->N, d->H, d->W, d->Cout, d->ldd, d->coffd);
             if (rc) return rc;
         }
+        if (bn == 256) return launch_conv<256, 3, 1, true, 1, 4>(a0, a1, b, dm, kp, stream);
         return launch_conv<128, 5, 1, true>(a0, a1, b, dm, kp, stream);
     }
+    if (bn == 256) return launch_conv<256, 4, 1, false>(a0, a1, b, a0, kp, stream);
     // measured on B200: for the generic BN <= 128 convs two resident CTAs with the direct epilogue beat one CTA
     // with the TMA-store epilogue (128->128 @1024^2: 0.295 vs 0.378 ms)
+    if (pair) return launch_conv<128, 4, 1, false, 2>(a0, a1, b, a0, kp, stream);
     if (bn == 128) return launch_conv<128, 3, 2, false>(a0, a1, b, a0, kp, stream);
     return launch_conv<64, 4, 2, false>(a0, a1, b, a0, kp, stream);
 }
@@ -1478,28 +1576,29 @@ extern "C" int mbs_first_conv(const void *img, int in_dtype, int H, int W, int p
     MBS_REQUIRE(((reinterpret_cast<uintptr_t>(out) + static_cast<size_t>(out_coff) * 2) & 15) == 0 &&
                     (out_ld * 2) % 16 == 0,
                 "first conv: destination view must be 16-byte aligned");
-    const dim3 fgrid(mbs::cdiv(W + pad_x, FC_TW), mbs::cdiv(H + pad_y, FC_TH));
+    const int tiles_x = mbs::cdiv(W + pad_x, FC_TW);
+    const int num_tiles = tiles_x * mbs::cdiv(H + pad_y, FC_TH);
+    const int fgrid = num_tiles < 2 * sm_count() ? num_tiles : 2 * sm_count();
     const int threads = 256;
-    const size_t smem = 0;
     __nv_bfloat16 *o = static_cast<__nv_bfloat16 *>(out);
+#define MBS_FIRST_CONV(T, RELU)                                                                                        \
+    first_conv_kernel<T, RELU><<<fgrid, threads, 0, stream>>>(static_cast<const T *>(img), H, W, pad_y, pad_x, norm_lo, \
+                                                              norm_hi, lohi_dev, weight, bias, scale, shift, C, act, o, \
+                                                              out_ld, out_coff, tiles_x, num_tiles)
+    const bool relu = act == MBS_ACT_RELU;
     switch (in_dtype) {
         case MBS_IN_U8:
-            first_conv_kernel<uint8_t><<<fgrid, threads, smem, stream>>>(
-                static_cast<const uint8_t *>(img), H, W, pad_y, pad_x, norm_lo, norm_hi, lohi_dev, weight, bias, scale, shift, C,
-                act, o, out_ld, out_coff);
+            if (relu) MBS_FIRST_CONV(uint8_t, true); else MBS_FIRST_CONV(uint8_t, false);
             break;
         case MBS_IN_U16:
-            first_conv_kernel<uint16_t><<<fgrid, threads, smem, stream>>>(
-                static_cast<const uint16_t *>(img), H, W, pad_y, pad_x, norm_lo, norm_hi, lohi_dev, weight, bias, scale, shift, C,
-                act, o, out_ld, out_coff);
+            if (relu) MBS_FIRST_CONV(uint16_t, true); else MBS_FIRST_CONV(uint16_t, false);
             break;
         case MBS_IN_F32:
-            first_conv_kernel<float><<<fgrid, threads, smem, stream>>>(
-                static_cast<const float *>(img), H, W, pad_y, pad_x, norm_lo, norm_hi, lohi_dev, weight, bias, scale, shift, C,
-                act, o, out_ld, out_coff);
+            if (relu) MBS_FIRST_CONV(float, true); else MBS_FIRST_CONV(float, false);
             break;
         default: MBS_REQUIRE(false, "first conv: unknown input dtype %d", in_dtype);
     }
+#undef MBS_FIRST_CONV
     MBS_CHECK_LAUNCH();
     return 0;
 }

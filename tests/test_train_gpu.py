@@ -35,9 +35,10 @@ def _setup(filters, seed, n, h, w, graph=False):
 def _reference(sd, img, bl, cl, autocast=False):
     params = {k: v.clone().cuda().requires_grad_(v.dtype.is_floating_point and "running" not in k) for k, v in sd.items()
               if v.dtype.is_floating_point}
-    with torch.autocast("cuda", dtype=torch.bfloat16, enabled=autocast):
-        loss = onet.dunet_train_loss(params, img, bl, cl)
-    loss.backward()
+    with torch.enable_grad():      # the inference tests (like the reference, infer.py:343) switch grad off globally
+        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=autocast):
+            loss = onet.dunet_train_loss(params, img, bl, cl)
+        loss.backward()
     return float(loss.detach()), {k: p.grad for k, p in params.items() if p.grad is not None}
 
 

@@ -102,7 +102,16 @@ cases = [
     (2, 1, 16, 16, 128, 0, 64),
     (2, 1, 8, 24, 1024, 0, 512),
     (0, 1, 4, 4, 1024, 0, 1024),
+    # large enough for the paired-tile (MT = 2) path, ragged edges
+    (0, 1, 200, 200, 128, 0, 128),
+    (1, 1, 400, 416, 128, 0, 128),
+    (0, 1, 208, 200, 128, 128, 128),
+    (0, 2, 168, 160, 64, 0, 128),
 ]
+if os.environ.get("PROBE_ONLY"):       # e.g. PROBE_ONLY=2,1,1024,1024,128,0,64 : one shape (for ncu captures)
+    c = tuple(int(v) for v in os.environ["PROBE_ONLY"].split(","))
+    run_conv(*c, bench=int(os.environ.get("PROBE_REPS", "3")))
+    sys.exit(0)
 allok = True
 for c in cases:
     try:
@@ -118,7 +127,7 @@ except Exception as e:
     P("EXC head", repr(e)); allok = False
 P("ALL_OK", allok)
 if allok or os.environ.get("FORCE_BENCH"):
-    for c in [(0, 1, 2048, 2048, 64, 0, 64), (0, 1, 2048, 2048, 64, 64, 64), (0, 1, 1024, 1024, 128, 0, 128),
+    for c in [(0, 1, 2048, 2048, 64, 0, 64), (0, 1, 2048, 2048, 64, 64, 64), (0, 1, 1024, 1024, 128, 0, 128), (0, 1, 1024, 1024, 128, 128, 128), (0, 1, 1024, 1024, 64, 0, 128), (1, 1, 1024, 1024, 128, 0, 128),
               (0, 1, 512, 512, 256, 0, 256), (0, 1, 256, 256, 512, 0, 512), (0, 1, 256, 256, 512, 512, 512),
               (0, 1, 128, 128, 1024, 0, 1024), (1, 1, 2048, 2048, 64, 0, 64), (2, 1, 1024, 1024, 128, 0, 64),
               (2, 1, 128, 128, 1024, 0, 512)]:
