@@ -146,25 +146,18 @@ int mbs_head_fwd(const void *y, long long M, int C, const float *w, const float 
 int mbs_smoothl1(const float *pred, const float *target, long long M, float *loss_accum, float *grad, void *stream);
 int mbs_head_bwd(const float *g, const void *y, long long M, int C, const float *w, void *dy, float *dw_db, void *stream);
 /* layout / glue kernels of the backward pass */
-/* dst[n][c][y][x] = src[n][y][x*step_x + shift_x][c] (0 outside), dst row pitch `pitch` elements: TMA row starts must
- * be 16-byte aligned and a swizzled box row is at most 128 bytes, so the horizontal tap shifts (and the column
- * decimation of stride-2 layers) of the weight gradient are baked into channel-major copies */
-int mbs_nhwc_to_chw(const void *src, int N, int H, int W, int C, int pitch, int shift_x, int step_x, void *dst,
-                    void *stream);
-/* unit-step variant writing the copies shifted by -1 / 0 / +1 in one pass (any of the three may be NULL) */
-int mbs_nhwc_to_chw3(const void *src, int N, int H, int W, int C, int pitch, void *dst_m1, void *dst_0, void *dst_p1,
-                     void *stream);
 int mbs_zero_insert_up2(const void *src, int N, int H, int W, int C, void *dst, void *stream);
 int mbs_add3_bf16(const void *a, const void *b, const void *c, long long n, void *out, void *stream);
 int mbs_first_conv_wgrad(const float *x, const void *dz, int N, int H, int W, int C, float *dw, void *stream);
-/* weight gradient on the tensor cores: out[m][tap][out_coff + n] += sum_pixels At[m][..] * Bt[n][..]; operands are
- * channel-major bf16 copies [N][C][H][pitch] (mbs_nhwc_to_chw).  kind 0/1: conv3x3 stride 1/2 (At = dz^T on the
- * Ho x Wo output grid, Bt = x^T, three x-shifts); kind 2: transposed conv 2x2 (At = d(up)^T on the 2Ho x 2Wo grid,
- * shifts 0 / +1, Bt = x^T). */
+/* weight gradient on the tensor cores, straight from the NHWC bf16 activations (no layout copies):
+ *   out[m][tap][out_coff + n] += sum over pixels o of a[sA*o + offA(tap)][m] * b[sB*o + offB(tap)][n]
+ * kind 0/1: conv3x3 stride 1/2 -- a = dz [N,Ho,Wo,Cm], b = x [N,s*Ho,s*Wo,Cn] (autograd of unets.py:112-134,
+ * 196-199); kind 2: transposed conv 2x2 -- a = d(up) [N,2Ho,2Wo,Cm], b = x [N,Ho,Wo,Cn] (unets.py:245).
+ * ld / coff: pixel stride and channel offset (elements) of the views; out is fp32, zeroed by the caller. */
 typedef struct {
     int kind, N, Ho, Wo;
-    const void *At[3]; int Cm, pitchA;     /* x-shifted copies: [0] shift -1, [1] shift 0, [2] shift +1 (NULL if unused) */
-    const void *Bt[3]; int Cn, pitchB;
+    const void *a; int Cm, lda, coffa;
+    const void *b; int Cn, ldb, coffb;
     float *out; int out_ld, out_coff;
 } mbs_wgrad_desc;
 int mbs_conv_wgrad(const mbs_wgrad_desc *d, void *stream);

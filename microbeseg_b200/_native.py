@@ -28,8 +28,8 @@ class ConvDesc(ctypes.Structure):
 class WgradDesc(ctypes.Structure):
     """mirror of mbs_wgrad_desc (include/mbseg.h)"""
     _fields_ = [("kind", c_int), ("N", c_int), ("Ho", c_int), ("Wo", c_int),
-                ("At", c_void_p * 3), ("Cm", c_int), ("pitchA", c_int),
-                ("Bt", c_void_p * 3), ("Cn", c_int), ("pitchB", c_int),
+                ("a", c_void_p), ("Cm", c_int), ("lda", c_int), ("coffa", c_int),
+                ("b", c_void_p), ("Cn", c_int), ("ldb", c_int), ("coffb", c_int),
                 ("out", c_void_p), ("out_ld", c_int), ("out_coff", c_int)]
 
 
@@ -62,8 +62,6 @@ _SIGS = {
     "mbs_head_fwd": (c_int, [c_void_p, ctypes.c_longlong, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "mbs_smoothl1": (c_int, [c_void_p, c_void_p, ctypes.c_longlong, c_void_p, c_void_p, c_void_p]),
     "mbs_head_bwd": (c_int, [c_void_p, c_void_p, ctypes.c_longlong, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
-    "mbs_nhwc_to_chw": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
-    "mbs_nhwc_to_chw3": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "mbs_zero_insert_up2": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "mbs_add3_bf16": (c_int, [c_void_p, c_void_p, c_void_p, ctypes.c_longlong, c_void_p, c_void_p]),
     "mbs_first_conv_wgrad": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),

@@ -248,64 +248,6 @@ head_bwd_kernel(const float *__restrict__ g, const __nv_bfloat16 *__restrict__ y
     if ((threadIdx.x & 31) == 0 && gsum != 0.0f) atomicAdd(&dw_db[C], gsum);
 }
 
-// [N][H][W][C] -> channel-major [N][C][H][pitch] (bf16, pitch >= W, padding columns zero), 32x32 tiles via smem.
-// One block row = 32 pixels of ONE image row (so that the padded pitch is simple).
-__global__ void nhwc_to_chw_kernel(const __nv_bfloat16 *__restrict__ src, int H, int W, int C, int pitch, int shift,
-                                   int step, __nv_bfloat16 *__restrict__ dst) {
-    __shared__ __nv_bfloat16 tile[32][33];
-    const int n = blockIdx.z / H, y = blockIdx.z % H;
-    const int x0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
-    const __nv_bfloat16 *s = src + (static_cast<size_t>(n) * H + y) * W * C;
-    __nv_bfloat16 *d = dst + static_cast<size_t>(n) * C * H * pitch + static_cast<size_t>(y) * pitch;
-    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
-        const int x = (x0 + r) * step + shift, c = c0 + threadIdx.x;   // destination column x0 + r reads source column x
-        tile[r][threadIdx.x] = (x >= 0 && x < W && c < C) ? s[static_cast<size_t>(x) * C + c] : __float2bfloat16(0.0f);
-    }
-    __syncthreads();
-    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
-        const int c = c0 + r, x = x0 + threadIdx.x;
-        if (c < C && x < pitch) d[static_cast<size_t>(c) * H * pitch + x] = tile[threadIdx.x][r];
-    }
-}
-
-// Unit-step variant producing the shifted copies (-1, 0, +1) in ONE pass: a block stages 64 pixels (+1 halo pixel
-// each side) x 64 channels of one image row in shared memory (16-byte coalesced reads) and writes 64-pixel rows of
-// each requested copy (128-byte coalesced writes).  dsts[k] may be null.
-__global__ void __launch_bounds__(256)
-nhwc_to_chw3_kernel(const __nv_bfloat16 *__restrict__ src, int H, int W, int C, int pitch, __nv_bfloat16 *__restrict__ d0,
-                    __nv_bfloat16 *__restrict__ d1, __nv_bfloat16 *__restrict__ d2) {
-    __shared__ __nv_bfloat16 tile[66][72];           // [pixel + 1][channel], padded row (144 B) to spread banks
-    const int n = blockIdx.z / H, y = blockIdx.z % H;
-    const int x0 = blockIdx.x * 64, c0 = blockIdx.y * 64;
-    const __nv_bfloat16 *s = src + (static_cast<size_t>(n) * H + y) * W * C;
-    // 66 pixels x 64 channels = 66 x 8 chunks of 16 bytes
-    for (int i = threadIdx.x; i < 66 * 8; i += 256) {
-        const int px = i >> 3, ch = (i & 7) * 8;
-        const int x = x0 + px - 1;
-        uint4 v = make_uint4(0, 0, 0, 0);
-        if (x >= 0 && x < W && c0 + ch < C) v = *reinterpret_cast<const uint4 *>(s + static_cast<size_t>(x) * C + c0 + ch);
-        *reinterpret_cast<uint4 *>(&tile[px][ch]) = v;
-    }
-    __syncthreads();
-    __nv_bfloat16 *dsts[3] = {d0, d1, d2};
-    const size_t plane = static_cast<size_t>(H) * pitch;
-    // each thread writes 8 consecutive pixels (16 bytes) of one channel row: 64 channels x 8 chunks = 512 items
-    for (int i = threadIdx.x; i < 64 * 8; i += 256) {
-        const int c = i >> 3, xo = (i & 7) * 8;
-        if (c0 + c >= C || x0 + xo >= pitch) continue;
-#pragma unroll
-        for (int k = 0; k < 3; ++k) {
-            if (!dsts[k]) continue;
-            __nv_bfloat16 v[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) v[j] = tile[xo + j + k][c];       // copy k holds src column x + (k - 1)
-            __nv_bfloat16 *d = dsts[k] + static_cast<size_t>(n) * C * plane + static_cast<size_t>(c0 + c) * plane +
-                               static_cast<size_t>(y) * pitch + x0 + xo;
-            *reinterpret_cast<uint4 *>(d) = *reinterpret_cast<uint4 *>(v);
-        }
-    }
-}
-
 // U[n][2y][2x][c] = src[n][y][x][c], zeros elsewhere (input of the stride-2 conv's data gradient)
 __global__ void zero_insert_kernel(const __nv_bfloat16 *__restrict__ src, int N, int H, int W, int C, __nv_bfloat16 *__restrict__ dst) {
     const long long i = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) * 8;   // 8 channels (16 B) per thread
@@ -436,32 +378,6 @@ extern "C" int mbs_head_bwd(const float *g, const void *y, long long M, int C, c
     MBS_CHECK_CUDA(cudaMemsetAsync(dw_db, 0, (C + 1) * sizeof(float), stream));
     head_bwd_kernel<<<grid_rows(M, C), 256, 0, stream>>>(g, static_cast<const __nv_bfloat16 *>(y), M, C, w,
                                                                       static_cast<__nv_bfloat16 *>(dy), dw_db);
-    MBS_CHECK_LAUNCH();
-    return 0;
-}
-
-extern "C" int mbs_nhwc_to_chw(const void *src, int N, int H, int W, int C, int pitch, int shift_x, int step_x, void *dst,
-                               void *stream_) {
-    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-    MBS_REQUIRE(N > 0 && H > 0 && W > 0 && C > 0 && (step_x == 1 || step_x == 2) && pitch * step_x >= W && pitch % 8 == 0,
-                "nhwc_to_chw: bad shape / pitch");
-    MBS_REQUIRE(static_cast<long long>(N) * H <= 65535, "nhwc_to_chw: N*H too large for one launch");
-    dim3 grid(mbs::cdiv(pitch, 32), mbs::cdiv(C, 32), N * H), block(32, 8);
-    nhwc_to_chw_kernel<<<grid, block, 0, stream>>>(static_cast<const __nv_bfloat16 *>(src), H, W, C, pitch, shift_x, step_x,
-                                                   static_cast<__nv_bfloat16 *>(dst));
-    MBS_CHECK_LAUNCH();
-    return 0;
-}
-
-extern "C" int mbs_nhwc_to_chw3(const void *src, int N, int H, int W, int C, int pitch, void *dst_m1, void *dst_0,
-                                void *dst_p1, void *stream_) {
-    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-    MBS_REQUIRE(N > 0 && H > 0 && W > 0 && C > 0 && C % 8 == 0 && pitch >= W && pitch % 8 == 0, "nhwc_to_chw3: bad shape / pitch");
-    MBS_REQUIRE(static_cast<long long>(N) * H <= 65535, "nhwc_to_chw3: N*H too large for one launch");
-    dim3 grid(mbs::cdiv(pitch, 64), mbs::cdiv(C, 64), N * H);
-    nhwc_to_chw3_kernel<<<grid, 256, 0, stream>>>(static_cast<const __nv_bfloat16 *>(src), H, W, C, pitch,
-                                                  static_cast<__nv_bfloat16 *>(dst_m1), static_cast<__nv_bfloat16 *>(dst_0),
-                                                  static_cast<__nv_bfloat16 *>(dst_p1));
     MBS_CHECK_LAUNCH();
     return 0;
 }

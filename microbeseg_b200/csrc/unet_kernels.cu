@@ -870,62 +870,101 @@ conv_halo64_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
 }
 
 // ------------------------------------------------------------------------------------------
-// Weight gradient: G[m][tap][n] += sum over pixels of At[img][m][sA*o + offA(tap)] * Bt[img][n][sB*o + offB(tap)].
+// Weight gradient straight from the NHWC activations (no channel-major copies).
 //
-// Both operands are channel-major ("NCHW", row pitch padded to 16 B) bf16 copies, so the contraction
-// index (pixels along an image row) is contiguous and the SAME K-major SWIZZLE_128B UMMA descriptors as in
-// the forward kernel apply: A tile = 128 channels x 64 pixels, B tile = BN channels x 64 pixels, each one 4-D
-// TMA box whose out-of-bounds pixels are zero-filled (= the conv's zero padding; also the row tails).
-// conv3x3:  A = dz^T (stride 1, no offset), B = x^T (stride s, offset tap-1);  convT2x2: A = dup^T (stride 2,
-// offset (dy,dx)), B = x^T.  One CTA = one (m-tile, n-tile, tap, K-split) and adds its fp32 tile into G with
-// atomics (split-K over image rows fills the machine for the thin full-resolution layers).
+//   G[m][tap][n] += sum over pixels o of  A[sA*o + offA(tap)][m] * B[sB*o + offB(tap)][n]
+//
+// The contraction index (pixels) is the SLOW dimension of both NHWC operands, i.e. both are "MN-major" UMMA
+// operands: one TMA box = an 8x8 (or 4x16 ...) pixel patch x 64 channels = 64 rows of 128 B (SWIZZLE_128B), which is
+// exactly the canonical MN-major SW128 layout ((64 ch contiguous, LBO between 64-channel blocks), (8 pixel rows of
+// 128 B, SBO = 1024 B between 8-pixel groups)).  A K = 16 MMA step consumes 16 consecutive pixels (2 KiB).
+// Tap shifts are pixel coordinates of the box (never the innermost dimension), so there is no alignment constraint;
+// out-of-image pixels are zero-filled by TMA = the conv's zero padding (and the ragged patch edges).
+//   conv3x3 s1/s2: A = dz (pixel o), B = x (pixel s*o + tap - 1);  convT2x2: A = d(up) (pixel 2o + (dy,dx)), B = x.
+//   Cm == 64, stride 1: the 128 accumulator rows hold TWO taps x 64 output channels: the shift is moved onto dz
+//   (sum_o dz[o] x[o+t] = sum_p dz[p-t] x[p]) so the two 64-row A blocks use different shifts and B is unshifted.
+// One CTA = one (m-tile, n-tile, tap item, K split) and adds its fp32 tile into G with vector reductions.
 // ------------------------------------------------------------------------------------------
-struct WgradParams {
+struct WgradNhwcParams {
     int N, Ho, Wo;
-    int sA, sB;
-    int offAy[9], offBy[9];    // row offsets per tap
-    int selA[9], selB[9];      // which x-shifted copy (0: -1, 1: 0, 2: +1) per tap -- TMA needs 16-byte aligned row starts,
-                               // so horizontal shifts are baked into pre-shifted channel-major copies
-    int taps;
-    int M_total, N_total;
+    int pw, ph;                // pixel patch of one K chunk (pw * ph = 64)
+    int ptx, pty;              // patches per image
+    int sA, sB;                // pixel stride of the two operands
+    int kind;                  // 0 conv s1, 1 conv s2, 2 convT
+    int pair;                  // 1: rows 0-63 / 64-127 of the tile are two taps of the same 64 output channels
+    int taps, tap_items;
+    int Cm, Cn;
     int m_tiles, n_tiles, splits;
     float *out;
-    int out_ld, out_coff;      // G row = m, then tap, then out_ld columns; this call fills columns [out_coff, out_coff+N_total)
+    int out_ld, out_coff;
 };
+
+__device__ __forceinline__ uint64_t make_sw128_mn_desc(uint32_t saddr, uint32_t lbo_bytes) {
+    uint64_t d = 0;
+    d |= static_cast<uint64_t>((saddr & 0x3FFFFu) >> 4);
+    d |= static_cast<uint64_t>(lbo_bytes >> 4) << 16;      // between 64-element blocks along M / N
+    d |= static_cast<uint64_t>(1024 >> 4) << 32;            // between 8-row groups along K
+    d |= static_cast<uint64_t>(1) << 46;
+    d |= static_cast<uint64_t>(2) << 61;
+    return d;
+}
+__device__ __forceinline__ void red_add_v4(float *addr, float a, float b, float c, float d) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+constexpr int WG_BLOCK = 64 * 128;     // one 64-pixel x 64-channel box
 
 template <int BN, int STAGES>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-wgrad_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
-             const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB0,
-             const __grid_constant__ CUtensorMap tmB1, const __grid_constant__ CUtensorMap tmB2, const WgradParams p) {
-    constexpr int B_BYTES = BN * BK * 2;
+wgrad_nhwc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const WgradNhwcParams p) {
+    constexpr int A_TILE = 2 * WG_BLOCK;
+    constexpr int B_TILE = (BN / 64) * WG_BLOCK;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;
     uint8_t *gbase = smem_raw + (base - raw);
     const uint32_t sA = base;
-    const uint32_t sB = base + STAGES * A_BYTES;
-    const uint32_t sBar = sB + STAGES * B_BYTES;
+    const uint32_t sB = base + STAGES * A_TILE;
+    const uint32_t sBar = sB + STAGES * B_TILE;
     auto full_bar = [&](int s) { return sBar + 8u * s; };
     auto empty_bar = [&](int s) { return sBar + 8u * (STAGES + s); };
     const uint32_t tfull_bar = sBar + 8u * (2 * STAGES);
-    volatile uint32_t *tmem_ptr = reinterpret_cast<volatile uint32_t *>(gbase + STAGES * (A_BYTES + B_BYTES) + 8 * (2 * STAGES + 1));
+    volatile uint32_t *tmem_ptr = reinterpret_cast<volatile uint32_t *>(gbase + STAGES * (A_TILE + B_TILE) + 8 * (2 * STAGES + 1));
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     int t = blockIdx.x;
     const int split = t % p.splits; t /= p.splits;
-    const int tap = t % p.taps; t /= p.taps;
+    const int item = t % p.tap_items; t /= p.tap_items;
     const int n_tile = t % p.n_tiles;
     const int m_tile = t / p.n_tiles;
-    const int m0 = m_tile * BM, n0 = n_tile * BN;
-    const int rows_total = p.N * p.Ho;
-    const int rows_per = (rows_total + p.splits - 1) / p.splits;
-    const int r0 = split * rows_per;
-    const int r1 = min(rows_total, r0 + rows_per);
-    const int xchunks = (p.Wo + BK - 1) / BK;
-    const int num_k_iters = max(0, r1 - r0) * xchunks;
+    const int n0 = n_tile * BN;
+    // the two 64-row blocks of the A tile: channel offset, tap, validity
+    int blk_c[2], blk_tap[2];
+    bool blk_ok[2];
+    if (p.pair) {
+        blk_c[0] = blk_c[1] = 0;
+        blk_tap[0] = 2 * item;
+        blk_tap[1] = 2 * item + 1;
+        blk_ok[0] = true;
+        blk_ok[1] = blk_tap[1] < p.taps;
+        if (!blk_ok[1]) blk_tap[1] = blk_tap[0];
+    } else {
+        blk_c[0] = m_tile * 128;
+        blk_c[1] = m_tile * 128 + 64;
+        blk_tap[0] = blk_tap[1] = item;
+        blk_ok[0] = true;
+        blk_ok[1] = blk_c[1] < p.Cm;
+        if (!blk_ok[1]) blk_c[1] = blk_c[0];
+    }
+    const int patches = p.N * p.ptx * p.pty;
+    const int per = (patches + p.splits - 1) / p.splits;
+    const int k0 = split * per;
+    const int k1 = min(patches, k0 + per);
+    const int num_k_iters = max(0, k1 - k0);
 
     if (threadIdx.x == 0) {
+        prefetch_tmap(&tmA);
+        prefetch_tmap(&tmB);
         for (int s = 0; s < STAGES; ++s) {
             mbar_init(full_bar(s), 1);
             mbar_init(empty_bar(s), 1);
@@ -942,37 +981,61 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
     if (num_k_iters > 0) {
         if (warp == 0) {
             if (lane == 0) {
-                const CUtensorMap *mapA = p.selA[tap] == 0 ? &tmA0 : (p.selA[tap] == 1 ? &tmA1 : &tmA2);
-                const CUtensorMap *mapB = p.selB[tap] == 0 ? &tmB0 : (p.selB[tap] == 1 ? &tmB1 : &tmB2);
-                int it = 0;
-                for (int r = r0; r < r1; ++r) {
-                    const int img = r / p.Ho, oy = r - img * p.Ho;
-                    for (int xc = 0; xc < xchunks; ++xc, ++it) {
-                        const int s = it % STAGES;
-                        const uint32_t ph = (it / STAGES) & 1;
-                        mbar_wait(empty_bar(s), ph ^ 1u);
-                        mbar_expect_tx(full_bar(s), A_BYTES + B_BYTES);
-                        const int ox0 = xc * BK;
-                        // columns are pre-shifted / pre-decimated in the channel-major copies; rows use the coordinate
-                        tma_load_4d(sA + s * A_BYTES, mapA, full_bar(s), ox0, p.sA * oy + p.offAy[tap], m0, img);
-                        tma_load_4d(sB + s * B_BYTES, mapB, full_bar(s), ox0, p.sB * oy + p.offBy[tap], n0, img);
+                // pixel offsets of the boxes for this item
+                int ax[2], ay[2], bx, by;
+                for (int b = 0; b < 2; ++b) {
+                    const int tp = blk_tap[b];
+                    if (p.kind == 2) {            // convT: A = d(up) at 2o + (dy, dx)
+                        ax[b] = tp & 1;
+                        ay[b] = tp >> 1;
+                    } else if (p.pair) {          // shift moved onto dz
+                        ax[b] = -(tp % 3 - 1);
+                        ay[b] = -(tp / 3 - 1);
+                    } else {
+                        ax[b] = ay[b] = 0;
                     }
+                }
+                if (p.kind == 2 || p.pair) {
+                    bx = by = 0;
+                } else {
+                    bx = blk_tap[0] % 3 - 1;
+                    by = blk_tap[0] / 3 - 1;
+                }
+                const int ppi = p.ptx * p.pty;
+                int it = 0;
+                for (int k = k0; k < k1; ++k, ++it) {
+                    const int img = k / ppi;
+                    const int r = k - img * ppi;
+                    const int oy0 = (r / p.ptx) * p.ph, ox0 = (r % p.ptx) * p.pw;
+                    const int s = it % STAGES;
+                    const uint32_t ph = (it / STAGES) & 1;
+                    mbar_wait(empty_bar(s), ph ^ 1u);
+                    mbar_expect_tx(full_bar(s), A_TILE + B_TILE);
+                    for (int b = 0; b < 2; ++b)
+                        tma_load_4d(sA + s * A_TILE + b * WG_BLOCK, &tmA, full_bar(s), blk_c[b], p.sA * ox0 + ax[b],
+                                    p.sA * oy0 + ay[b], img);
+#pragma unroll
+                    for (int j = 0; j < BN / 64; ++j)
+                        tma_load_4d(sB + s * B_TILE + j * WG_BLOCK, &tmB, full_bar(s), n0 + 64 * j, p.sB * ox0 + bx,
+                                    p.sB * oy0 + by, img);
                 }
             }
             __syncwarp();
         } else if (warp == 1) {
             if (lane == 0) {
-                constexpr uint32_t idesc = make_idesc(BM, BN);
+                // both operands MN-major: bits 15 / 16 of the instruction descriptor
+                constexpr uint32_t idesc = make_idesc(BM, BN) | (1u << 15) | (1u << 16);
                 for (int it = 0; it < num_k_iters; ++it) {
                     const int s = it % STAGES;
                     const uint32_t ph = (it / STAGES) & 1;
                     mbar_wait(full_bar(s), ph);
                     tcgen05_fence_after();
-                    const uint64_t adesc = make_sw128_desc(sA + s * A_BYTES);
-                    const uint64_t bdesc = make_sw128_desc(sB + s * B_BYTES);
 #pragma unroll
-                    for (int k = 0; k < BK / 16; ++k)
-                        umma_f16(tmem_base, adesc + 2u * k, bdesc + 2u * k, idesc, (it > 0 || k > 0) ? 1u : 0u);
+                    for (int k = 0; k < 4; ++k) {      // 16 pixels (2 KiB) per MMA
+                        const uint64_t adesc = make_sw128_mn_desc(sA + s * A_TILE + k * 2048, WG_BLOCK);
+                        const uint64_t bdesc = make_sw128_mn_desc(sB + s * B_TILE + k * 2048, WG_BLOCK);
+                        umma_f16(tmem_base, adesc, bdesc, idesc, (it > 0 || k > 0) ? 1u : 0u);
+                    }
                     umma_commit(empty_bar(s));
                 }
                 umma_commit(tfull_bar);
@@ -980,18 +1043,20 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
             __syncwarp();
         } else {
             const int e = warp - 2, quad = warp & 3, half = e >> 2;
-            const int m = m0 + quad * 32 + lane;
+            const int b = quad >> 1;                              // which 64-row block this TMEM lane quadrant holds
+            const int m = blk_c[b] + (quad & 1) * 32 + lane;      // output channel (G row)
             mbar_wait(tfull_bar, 0);
             tcgen05_fence_after();
 #pragma unroll 1
             for (int c = half * (BN / 2); c < (half + 1) * (BN / 2); c += 32) {
                 uint32_t r[32];
                 tmem_ld32(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(c), r);
-                if (m < p.M_total) {
-                    float *dst = p.out + (static_cast<size_t>(m) * p.taps + tap) * p.out_ld + p.out_coff + n0 + c;
+                if (blk_ok[b] && m < p.Cm && n0 + c < p.Cn) {
+                    float *dst = p.out + (static_cast<size_t>(m) * p.taps + blk_tap[b]) * p.out_ld + p.out_coff + n0 + c;
 #pragma unroll
-                    for (int j = 0; j < 32; ++j)
-                        if (n0 + c + j < p.N_total) atomicAdd(dst + j, __uint_as_float(r[j]));
+                    for (int j = 0; j < 32; j += 4)
+                        red_add_v4(dst + j, __uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
+                                   __uint_as_float(r[j + 3]));
                 }
             }
             tcgen05_fence_before();
@@ -1307,39 +1372,6 @@ int launch_conv(const CUtensorMap &a0, const CUtensorMap &a1, const CUtensorMap 
     return 0;
 }
 
-// channel-major ("NCHW", padded row pitch) bf16 tensor -> 4-D map (W, H, C, N), box (64*es, 1, rows, 1)
-int make_chw_map(CUtensorMap *map, const void *base, int N, int C, int H, int W, int pitch, int es, int rows) {
-    EncodeTiledFn enc = get_encode_fn();
-    MBS_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled entry point not available (no CUDA driver?)");
-    MBS_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0 && (pitch * 2) % 16 == 0 && pitch >= W,
-                "channel-major tensor needs 16-byte aligned base and row pitch");
-    cuuint64_t dims[4] = {static_cast<cuuint64_t>(W), static_cast<cuuint64_t>(H), static_cast<cuuint64_t>(C),
-                          static_cast<cuuint64_t>(N)};
-    cuuint64_t strides[3] = {static_cast<cuuint64_t>(pitch) * 2, static_cast<cuuint64_t>(H) * pitch * 2,
-                             static_cast<cuuint64_t>(C) * H * pitch * 2};
-    cuuint32_t box[4] = {static_cast<cuuint32_t>(BK * es), 1, static_cast<cuuint32_t>(rows), 1};
-    cuuint32_t estr[4] = {static_cast<cuuint32_t>(es), 1, 1, 1};
-    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void *>(base), dims, strides, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    MBS_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(channel-major N=%d C=%d H=%d W=%d pitch=%d es=%d) failed: %d", N, C,
-                H, W, pitch, es, static_cast<int>(r));
-    return 0;
-}
-
-template <int BN, int STAGES>
-int launch_wgrad(const CUtensorMap *a, const CUtensorMap *b, const WgradParams &wp, int grid, cudaStream_t stream) {
-    constexpr int dyn = STAGES * (A_BYTES + BN * BK * 2) + 8 * (2 * STAGES + 1) + 16 + 1024;
-    static bool configured = false;
-    if (!configured) {
-        MBS_CHECK_CUDA(cudaFuncSetAttribute(wgrad_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn));
-        configured = true;
-    }
-    wgrad_kernel<BN, STAGES><<<grid, NUM_THREADS, dyn, stream>>>(a[0], a[1], a[2], b[0], b[1], b[2], wp);
-    MBS_CHECK_LAUNCH();
-    return 0;
-}
-
 template <int CHUNKS, int STAGES, int NG>
 int launch_halo(const CUtensorMap &a0, const CUtensorMap &a1, const CUtensorMap &b, const CUtensorMap &dmap,
                 const ConvKParams &kp, cudaStream_t stream) {
@@ -1513,58 +1545,65 @@ extern "C" int mbs_conv_gemm(const mbs_conv_desc *d, void *stream_) {
     return launch_conv<64, 4, 2, false>(a0, a1, b, a0, kp, stream);
 }
 
+template <int BN, int STAGES>
+int launch_wgrad_nhwc(const CUtensorMap &a, const CUtensorMap &b, const WgradNhwcParams &wp, int grid, cudaStream_t stream) {
+    constexpr int dyn = STAGES * (2 * WG_BLOCK + (BN / 64) * WG_BLOCK) + 8 * (2 * STAGES + 1) + 16 + 1024;
+    static bool configured = false;
+    if (!configured) {
+        MBS_CHECK_CUDA(cudaFuncSetAttribute(wgrad_nhwc_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn));
+        configured = true;
+    }
+    wgrad_nhwc_kernel<BN, STAGES><<<grid, NUM_THREADS, dyn, stream>>>(a, b, wp);
+    MBS_CHECK_LAUNCH();
+    return 0;
+}
+
 extern "C" int mbs_conv_wgrad(const mbs_wgrad_desc *d, void *stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     MBS_REQUIRE(d != nullptr && d->kind >= 0 && d->kind <= 2, "wgrad: bad descriptor");
-    MBS_REQUIRE(d->Cm > 0 && d->Cn > 0 && d->N > 0 && d->Ho > 0 && d->Wo > 0, "wgrad: bad shape");
-    WgradParams wp;
+    MBS_REQUIRE(d->Cm > 0 && d->Cm % 64 == 0 && d->Cn > 0 && d->Cn % 64 == 0, "wgrad: channel counts must be multiples of 64 (got %d, %d)", d->Cm, d->Cn);
+    MBS_REQUIRE(d->N > 0 && d->Ho > 0 && d->Wo > 0 && d->a && d->b && d->out, "wgrad: bad shape / null operand");
+    MBS_REQUIRE(d->out_ld % 4 == 0 && d->out_coff % 4 == 0 && (reinterpret_cast<uintptr_t>(d->out) & 15) == 0,
+                "wgrad: the gradient buffer must allow 16-byte vector reductions");
+    WgradNhwcParams wp;
     memset(&wp, 0, sizeof(wp));
     wp.N = d->N;
     wp.Ho = d->Ho;
     wp.Wo = d->Wo;
-    wp.M_total = d->Cm;
-    wp.N_total = d->Cn;
+    wp.kind = d->kind;
+    wp.Cm = d->Cm;
+    wp.Cn = d->Cn;
     wp.out = d->out;
     wp.out_ld = d->out_ld;
     wp.out_coff = d->out_coff;
-    int Ha, Wa, Hb, Wb;          // spatial dims of the two channel-major operands
-    if (d->kind == 2) {          // transposed conv 2x2 s2: A = d(up)^T sampled at (2y+dy, 2x+dx), B = x^T
-        wp.taps = 4;
-        wp.sA = 2;
-        wp.sB = 1;
-        for (int q = 0; q < 4; ++q) { wp.offAy[q] = q >> 1; wp.selA[q] = 1 + (q & 1); wp.selB[q] = 1; }
-        Ha = 2 * d->Ho; Wa = d->Wo; Hb = d->Ho; Wb = d->Wo;       // A copies are column-decimated (x' = 2x + dx)
-        MBS_REQUIRE(d->At[1] && d->At[2] && d->Bt[1], "wgrad(convT): needs At shift 0 / +1 and Bt shift 0");
-    } else {                     // conv 3x3, stride 1 or 2, padding 1: A = dz^T, B = x^T shifted by the tap
-        wp.taps = 9;
-        wp.sA = 1;
-        wp.sB = d->kind == 1 ? 2 : 1;
-        for (int t = 0; t < 9; ++t) { wp.offBy[t] = t / 3 - 1; wp.selB[t] = t % 3; wp.selA[t] = 1; }
-        Ha = d->Ho; Wa = d->Wo; Hb = wp.sB * d->Ho; Wb = d->Wo;   // stride 2: B copies are column-decimated (2x + kx - 1)
-        MBS_REQUIRE(d->At[1] && d->Bt[0] && d->Bt[1] && d->Bt[2], "wgrad(conv): needs At shift 0 and Bt shifts -1 / 0 / +1");
-    }
+    wp.taps = d->kind == 2 ? 4 : 9;
+    wp.sA = d->kind == 2 ? 2 : 1;
+    wp.sB = d->kind == 1 ? 2 : 1;
+    wp.pair = (d->kind == 0 && d->Cm == 64) ? 1 : 0;
+    wp.tap_items = wp.pair ? (wp.taps + 1) / 2 : wp.taps;
+    // K chunk = 64 pixels: 8x8 patches; narrow grids use taller patches
+    wp.pw = d->Wo >= 8 ? 8 : (d->Wo >= 4 ? 4 : 2);
+    wp.ph = 64 / wp.pw;
+    wp.ptx = mbs::cdiv(d->Wo, wp.pw);
+    wp.pty = mbs::cdiv(d->Ho, wp.ph);
     const int bn = d->Cn % 256 == 0 ? 256 : (d->Cn % 128 == 0 ? 128 : 64);
-    wp.m_tiles = mbs::cdiv(d->Cm, BM);
-    wp.n_tiles = mbs::cdiv(d->Cn, bn);
-    const int tiles = wp.m_tiles * wp.n_tiles * wp.taps;
-    const int rows_total = d->N * d->Ho;
-    int splits = mbs::cdiv(3 * sm_count(), tiles);
-    if (splits > rows_total) splits = rows_total;
+    wp.m_tiles = wp.pair ? 1 : mbs::cdiv(d->Cm, 128);
+    wp.n_tiles = d->Cn / bn;
+    const int tiles = wp.m_tiles * wp.n_tiles * wp.tap_items;
+    const int patches = d->N * wp.ptx * wp.pty;
+    int splits = mbs::cdiv(2 * sm_count(), tiles);
+    if (splits > patches) splits = patches;
     if (splits < 1) splits = 1;
     wp.splits = splits;
-    CUtensorMap a[3], b[3];
-    for (int k = 0; k < 3; ++k) {
-        const void *pa = d->At[k] ? d->At[k] : d->At[1];
-        const void *pb = d->Bt[k] ? d->Bt[k] : d->Bt[1];
-        int rc = make_chw_map(&a[k], pa, d->N, d->Cm, Ha, Wa, d->pitchA, 1, BM);
-        if (rc) return rc;
-        rc = make_chw_map(&b[k], pb, d->N, d->Cn, Hb, Wb, d->pitchB, 1, bn);
-        if (rc) return rc;
-    }
+    CUtensorMap a, b;
+    int rc = make_act_map(&a, d->a, d->N, wp.sA * d->Ho, wp.sA * d->Wo, d->Cm, d->lda, d->coffa, wp.sA, wp.pw, wp.ph);
+    if (rc) return rc;
+    rc = make_act_map(&b, d->b, d->N, wp.sB * d->Ho, wp.sB * d->Wo, d->Cn, d->ldb, d->coffb, wp.sB, wp.pw, wp.ph);
+    if (rc) return rc;
     const int grid = tiles * splits;
-    if (bn == 256) return launch_wgrad<256, 4>(a, b, wp, grid, stream);
-    if (bn == 128) return launch_wgrad<128, 6>(a, b, wp, grid, stream);
-    return launch_wgrad<64, 8>(a, b, wp, grid, stream);
+    if (bn == 256) return launch_wgrad_nhwc<256, 4>(a, b, wp, grid, stream);
+    if (bn == 128) return launch_wgrad_nhwc<128, 6>(a, b, wp, grid, stream);
+    return launch_wgrad_nhwc<64, 8>(a, b, wp, grid, stream);
 }
 
 extern "C" int mbs_first_conv(const void *img, int in_dtype, int H, int W, int pad_y, int pad_x, float norm_lo,

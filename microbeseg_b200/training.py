@@ -21,10 +21,6 @@ BN_MOMENTUM = 0.1
 ACT_NONE, ACT_RELU = 0, 1
 
 
-def _pitch(w):
-    return (w + 7) // 8 * 8
-
-
 class _Layer:
     __slots__ = ("name", "kind", "conv", "bn", "act", "srcs", "a", "y", "mean", "invstd", "geom", "x_f32")
 
@@ -105,45 +101,13 @@ class TrainEngine:
             bn.running_var.mul_(1 - BN_MOMENTUM).add_(var_u, alpha=BN_MOMENTUM)
             bn.num_batches_tracked += 1
 
-    def _chw(self, t, shift=0, step=1):
-        """channel-major bf16 copy [N][C][H][pitch] of an NHWC tensor, columns shifted by ``shift`` (operand layout of the
-        weight gradient; TMA row starts must be 16-byte aligned, so horizontal tap shifts are pre-applied)."""
-        n, h, w, c = t.shape
-        p = _pitch((w + step - 1) // step)
-        out = torch.empty((n, c, h, p), dtype=torch.bfloat16, device=self.dev)
-        nat.check(self.L.mbs_nhwc_to_chw(t.data_ptr(), n, h, w, c, p, shift, step, out.data_ptr(), self._sp()), "nhwc_to_chw")
-        return out
-
-    def _chw3(self, t, shifts=(-1, 0, 1)):
-        """the unit-step copies for ``shifts`` in one pass -> dict shift -> tensor"""
-        n, h, w, c = t.shape
-        p = _pitch(w)
-        outs = {sh: torch.empty((n, c, h, p), dtype=torch.bfloat16, device=self.dev) for sh in shifts}
-        ptr = lambda sh: outs[sh].data_ptr() if sh in outs else None
-        nat.check(self.L.mbs_nhwc_to_chw3(t.data_ptr(), n, h, w, c, p, ptr(-1), ptr(0), ptr(1), self._sp()), "nhwc_to_chw3")
-        return outs
-
-    def _chw3_cached(self, t):
-        k = (t.data_ptr(), "x3")
-        if k not in self._chw_cache:
-            self._chw_cache[k] = (self._chw3(t), t)
-        return self._chw_cache[k][0]
-
-    def _chw_cached(self, t, shift=0, step=1):
-        k = (t.data_ptr(), shift, step)
-        if k not in self._chw_cache:
-            self._chw_cache[k] = (self._chw(t, shift, step), t)    # keep ``t`` alive: the key is its address
-        return self._chw_cache[k][0]
-
-    def _wgrad(self, kind, n, ho, wo, ats, cm, bts, cn, out, out_ld, out_coff):
-        """ats / bts: dicts shift -> channel-major tensor."""
+    def _wgrad(self, kind, n, ho, wo, a, cm, b, cn, out, out_ld, out_coff):
+        """weight gradient on the tensor cores straight from the NHWC bf16 activations: ``a`` = dz (conv) / d(up)
+        (transposed conv), ``b`` = the layer input; accumulates into out[m][tap][out_coff + n] (fp32)."""
         d = nat.WgradDesc()
         d.kind, d.N, d.Ho, d.Wo = kind, n, ho, wo
-        for sh in (-1, 0, 1):
-            d.At[sh + 1] = ats[sh].data_ptr() if sh in ats else None
-            d.Bt[sh + 1] = bts[sh].data_ptr() if sh in bts else None
-        d.Cm, d.pitchA = cm, ats[0].shape[-1]
-        d.Cn, d.pitchB = cn, bts[0].shape[-1]
+        d.a, d.Cm, d.lda, d.coffa = a.data_ptr(), cm, a.shape[-1], 0
+        d.b, d.Cn, d.ldb, d.coffb = b.data_ptr(), cn, b.shape[-1], 0
         d.out, d.out_ld, d.out_coff = out.data_ptr(), out_ld, out_coff
         nat.check(self.L.mbs_conv_wgrad(ctypes.byref(d), self._sp()), "conv_wgrad")
 
@@ -236,7 +200,7 @@ class TrainEngine:
         nl = len(self.chans)
         if H % (1 << (nl - 1)) or W % (1 << (nl - 1)):
             raise RuntimeError(f"training crops must be divisible by {1 << (nl - 1)}")
-        self.tape, self._chw_cache = [], {}
+        self.tape = []
         with torch.cuda.device(self.dev), torch.no_grad():
             x = img.reshape(n, H, W).contiguous().float()
             # ---------------- forward ----------------
@@ -314,7 +278,7 @@ class TrainEngine:
                 dy = self._bwd_conv(enc_a[l], dy)[0]          # gradient w.r.t. pool_{l-1}.y
                 dsk = self._bwd_conv(pools[l - 1], dy)[0]      # ... w.r.t. skip_{l-1}
                 dy = self._sum(skip_grads[l - 1] + [dsk])
-        self.tape, self._chw_cache = [], {}
+        self.tape = []
         return loss[0]
 
     # ---- backward pieces ----------------------------------------------------------------------
@@ -353,12 +317,10 @@ class TrainEngine:
         cin = sum(cins)
         stride2 = lay.kind == "s2"
         # weight gradient: dW[co][tap][ci] (GEMM-packed layout) -> reference layout [Cout,Cin,3,3]
-        dzt = self._chw3(dz, shifts=(0,))
         dwp = torch.zeros((cout, 9, cin), dtype=torch.float32, device=self.dev)
         off = 0
         for s, cs in zip(lay.srcs, cins):
-            xts = {sh: self._chw_cached(s, sh, 2) for sh in (-1, 0, 1)} if stride2 else self._chw3_cached(s)
-            self._wgrad(1 if stride2 else 0, n, ho, wo, dzt, cout, xts, cs, dwp, cin, off)
+            self._wgrad(1 if stride2 else 0, n, ho, wo, dz, cout, s, cs, dwp, cin, off)
             off += cs
         conv.weight.grad = dwp.view(cout, 3, 3, cin).permute(0, 3, 1, 2).contiguous()
         # data gradient: full-resolution stride-1 conv with the flipped, transposed filter
@@ -393,7 +355,7 @@ class TrainEngine:
         n, h, w, cin = x.shape
         cout = dup.shape[-1]
         g = torch.zeros((cout, 4, cin), dtype=torch.float32, device=self.dev)
-        self._wgrad(2, n, h, w, {0: self._chw(dup, 0, 2), 1: self._chw(dup, 1, 2)}, cout, {0: self._chw3_cached(x)[0]}, cin, g, cin, 0)
+        self._wgrad(2, n, h, w, dup, cout, x, cin, g, cin, 0)
         conv.weight.grad = g.permute(2, 0, 1).reshape(cin, cout, 2, 2).contiguous()
         # data gradient = 2x2 stride-2 convolution of d(up) with W[ci][co][q]
         packed = conv.weight.detach().float().permute(0, 2, 3, 1).reshape(cin, 4, cout).to(torch.bfloat16).contiguous()
