@@ -134,13 +134,16 @@ int mbs_pp_watershed(const float *image, const int32_t *markers, const uint8_t *
 /* activations / activation gradients NHWC bf16; statistics and parameter gradients fp32      */
 /* ---------------------------------------------------------------------------------------- */
 /* BatchNorm2d, training mode (unets.py:128,153,206,246): batch mean / biased variance over the M = N*H*W rows of
- * a [M][C]; y = gamma*(a-mean)*invstd + beta.  sums_scratch: 2*C floats; var_unbiased (optional) feeds running_var. */
+ * a [M][C]; y = gamma*(a-mean)*invstd + beta.  sums_scratch: mbs_bn_scratch_floats(C) floats (per-block partial sums,
+ * reduced without atomics: the statistics are deterministic); var_unbiased (optional) feeds running_var. */
+size_t mbs_bn_scratch_floats(int C);
 int mbs_bn_train_fwd(const void *a, long long M, int C, const float *gamma, const float *beta, float eps, void *y,
                      float *sums_scratch, float *mean, float *invstd, float *var_unbiased, void *stream);
 /* backward of  y = BN(act(z)):  dz = act'(a) * gamma*invstd*(dy - dbeta/M - xhat*dgamma/M);  dgamma_dbeta: [2*C]
- * (dgamma then dbeta), dbias[c] = sum dz (gradient of the conv bias).  act: MBS_ACT_RELU or MBS_ACT_NONE. */
+ * (dgamma then dbeta), dbias[c] = sum dz (gradient of the conv bias).  act: MBS_ACT_RELU or MBS_ACT_NONE.
+ * scratch: mbs_bn_scratch_floats(C) floats. */
 int mbs_bn_train_bwd(const void *dy, const void *a, long long M, int C, const float *mean, const float *invstd,
-                     const float *gamma, int act, void *dz, float *dgamma_dbeta, float *dbias, void *stream);
+                     const float *gamma, int act, void *dz, float *dgamma_dbeta, float *dbias, float *scratch, void *stream);
 /* Conv2d(C,1,1) head, SmoothL1Loss(beta=1,'mean') (losses.py:30-32) and their gradients */
 int mbs_head_fwd(const void *y, long long M, int C, const float *w, const float *b_dev, float *pred, void *stream);
 int mbs_smoothl1(const float *pred, const float *target, long long M, float *loss_accum, float *grad, void *stream);

@@ -8,6 +8,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdint>
+#include <cstdlib>
 
 #include "../../include/mbseg.h"
 #include "common.cuh"
@@ -42,7 +43,44 @@ struct Bf16x8 {
     }
 };
 
-template <int NACC>
+__device__ __forceinline__ uint4 ldg16(const __nv_bfloat16 *p) { return __ldg(reinterpret_cast<const uint4 *>(p)); }
+
+// Walk the pixels p = p0, p0 + stride, ... < M four at a time: the four 16-byte loads (per operand) are issued
+// before any of them is consumed, so each thread keeps 64-128 bytes in flight (these kernels are HBM bound).
+template <typename F>
+__device__ __forceinline__ void for_rows4(const __nv_bfloat16 *a, long long p0, long long stride, long long M, int C, int c0, F f) {
+    long long p = p0;
+    for (; p + 3 * stride < M; p += 4 * stride) {
+        const uint4 r0 = ldg16(a + p * C + c0), r1 = ldg16(a + (p + stride) * C + c0);
+        const uint4 r2 = ldg16(a + (p + 2 * stride) * C + c0), r3 = ldg16(a + (p + 3 * stride) * C + c0);
+        f(p, r0);
+        f(p + stride, r1);
+        f(p + 2 * stride, r2);
+        f(p + 3 * stride, r3);
+    }
+    for (; p < M; p += stride) f(p, ldg16(a + p * C + c0));
+}
+template <typename F>
+__device__ __forceinline__ void for_rows4x2(const __nv_bfloat16 *a, const __nv_bfloat16 *b, long long p0, long long stride,
+                                            long long M, int C, int c0, F f) {
+    long long p = p0;
+    for (; p + 3 * stride < M; p += 4 * stride) {
+        const uint4 a0 = ldg16(a + p * C + c0), a1 = ldg16(a + (p + stride) * C + c0);
+        const uint4 a2 = ldg16(a + (p + 2 * stride) * C + c0), a3 = ldg16(a + (p + 3 * stride) * C + c0);
+        const uint4 b0 = ldg16(b + p * C + c0), b1 = ldg16(b + (p + stride) * C + c0);
+        const uint4 b2 = ldg16(b + (p + 2 * stride) * C + c0), b3 = ldg16(b + (p + 3 * stride) * C + c0);
+        f(p, a0, b0);
+        f(p + stride, a1, b1);
+        f(p + 2 * stride, a2, b2);
+        f(p + 3 * stride, a3, b3);
+    }
+    for (; p < M; p += stride) f(p, ldg16(a + p * C + c0), ldg16(b + p * C + c0));
+}
+
+// PARTIAL = true: the block's sums are stored to out[blockIdx.x][NACC][C] (summed later by reduce_partials_kernel:
+// deterministic, and no same-address atomics from a thousand blocks -- those serialise in L2 and cost 10-25 us per
+// BatchNorm layer); PARTIAL = false: atomicAdd into out[NACC][C].
+template <int NACC, bool PARTIAL = false>
 __device__ __forceinline__ void block_channel_atomic(float (&acc)[NACC][8], int C, int c0, float *out) {
     // threads with the same c0 (same threadIdx.x % (C/8)) hold partials of the same channels
     __shared__ float s_acc[NACC][2048];
@@ -58,7 +96,10 @@ __device__ __forceinline__ void block_channel_atomic(float (&acc)[NACC][8], int 
     __syncthreads();
     for (int i = threadIdx.x; i < NACC * C; i += blockDim.x) {
         const int a = i / C, c = i % C;
-        atomicAdd(&out[a * C + c], s_acc[a][c]);
+        if (PARTIAL)
+            out[static_cast<size_t>(blockIdx.x) * NACC * C + i] = s_acc[a][c];
+        else
+            atomicAdd(&out[a * C + c], s_acc[a][c]);
     }
     (void)tpp;
 }
@@ -67,23 +108,41 @@ __global__ void __launch_bounds__(256) bn_stats_kernel(const __nv_bfloat16 *__re
     const int tpp = C / 8, c0 = (threadIdx.x % tpp) * 8, ppb = 256 / tpp;
     float acc[2][8] = {};
     if (threadIdx.x < ppb * tpp) {
-        for (long long p = static_cast<long long>(blockIdx.x) * ppb + threadIdx.x / tpp; p < M; p += static_cast<long long>(gridDim.x) * ppb) {
-            Bf16x8 v;
-            v.raw = *reinterpret_cast<const uint4 *>(a + p * C + c0);
-            float f[8];
-            v.unpack(f);
+        for_rows4(a, static_cast<long long>(blockIdx.x) * ppb + threadIdx.x / tpp, static_cast<long long>(gridDim.x) * ppb, M, C, c0,
+                  [&](long long, const uint4 &raw) {
+                      Bf16x8 v;
+                      v.raw = raw;
+                      float f[8];
+                      v.unpack(f);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                acc[0][j] += f[j];
-                acc[1][j] = fmaf(f[j], f[j], acc[1][j]);
-            }
-        }
+                      for (int j = 0; j < 8; ++j) {
+                          acc[0][j] += f[j];
+                          acc[1][j] = fmaf(f[j], f[j], acc[1][j]);
+                      }
+                  });
     }
-    block_channel_atomic<2>(acc, C, threadIdx.x < ppb * tpp ? c0 : C, sums);
+    block_channel_atomic<2, true>(acc, C, threadIdx.x < ppb * tpp ? c0 : C, sums);
 }
 
-__global__ void bn_finalize_kernel(const float *__restrict__ sums, long long M, int C, float eps, float *mean, float *invstd,
-                                   float *var_unbiased) {
+// out[i] = sum over blocks of part[b][i]
+__global__ void reduce_partials_kernel(const float *__restrict__ part, int nblocks, int n, float *__restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float s0 = 0.0f, s1 = 0.0f, s2 = 0.0f, s3 = 0.0f;
+    int b = 0;
+    for (; b + 3 < nblocks; b += 4) {
+        s0 += part[static_cast<size_t>(b) * n + i];
+        s1 += part[static_cast<size_t>(b + 1) * n + i];
+        s2 += part[static_cast<size_t>(b + 2) * n + i];
+        s3 += part[static_cast<size_t>(b + 3) * n + i];
+    }
+    for (; b < nblocks; ++b) s0 += part[static_cast<size_t>(b) * n + i];
+    out[i] = (s0 + s1) + (s2 + s3);
+}
+
+// also turns the sums scratch into the affine of the apply pass: sums[c] = gamma*invstd, sums[C+c] = beta - mean*gamma*invstd
+__global__ void bn_finalize_kernel(float *sums, long long M, int C, float eps, const float *__restrict__ gamma,
+                                   const float *__restrict__ beta, float *mean, float *invstd, float *var_unbiased) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= C) return;
     const double m = static_cast<double>(sums[c]) / static_cast<double>(M);
@@ -92,21 +151,33 @@ __global__ void bn_finalize_kernel(const float *__restrict__ sums, long long M, 
     mean[c] = static_cast<float>(m);
     invstd[c] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
     if (var_unbiased) var_unbiased[c] = static_cast<float>(M > 1 ? var * static_cast<double>(M) / static_cast<double>(M - 1) : var);
+    const float k = gamma[c] * invstd[c];
+    sums[c] = k;
+    sums[C + c] = fmaf(-mean[c], k, beta[c]);
 }
 
-__global__ void bn_apply_kernel(const __nv_bfloat16 *__restrict__ a, long long total, int C, const float *__restrict__ mean,
-                                const float *__restrict__ invstd, const float *__restrict__ gamma,
-                                const float *__restrict__ beta, __nv_bfloat16 *__restrict__ y) {
-    const long long i = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) * 8;
-    if (i >= total) return;
-    const int c = static_cast<int>(i % C);
-    Bf16x8 v;
-    v.raw = *reinterpret_cast<const uint4 *>(a + i);
-    float f[8];
-    v.unpack(f);
+// y = a * scale + shift with the row-vectorised mapping (8 channels per thread, affine in registers)
+__global__ void __launch_bounds__(256)
+bn_apply_kernel(const __nv_bfloat16 *__restrict__ a, long long M, int C, const float *__restrict__ scale_shift,
+                __nv_bfloat16 *__restrict__ y) {
+    const int tpp = C / 8, c0 = (threadIdx.x % tpp) * 8, ppb = 256 / tpp;
+    if (threadIdx.x >= ppb * tpp) return;
+    float k[8], b[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) f[j] = (f[j] - mean[c + j]) * invstd[c + j] * gamma[c + j] + beta[c + j];
-    *reinterpret_cast<uint4 *>(y + i) = Bf16x8::pack(f);
+    for (int j = 0; j < 8; ++j) {
+        k[j] = scale_shift[c0 + j];
+        b[j] = scale_shift[C + c0 + j];
+    }
+    for_rows4(a, static_cast<long long>(blockIdx.x) * ppb + threadIdx.x / tpp, static_cast<long long>(gridDim.x) * ppb, M, C, c0,
+              [&](long long p, const uint4 &raw) {
+                  Bf16x8 v;
+                  v.raw = raw;
+                  float f[8];
+                  v.unpack(f);
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) f[j] = fmaf(f[j], k[j], b[j]);
+                  *reinterpret_cast<uint4 *>(y + p * C + c0) = Bf16x8::pack(f);
+              });
 }
 
 __global__ void __launch_bounds__(256)
@@ -118,21 +189,22 @@ bn_bwd_reduce_kernel(const __nv_bfloat16 *__restrict__ dy, const __nv_bfloat16 *
         float mu[8], is[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) { mu[j] = mean[c0 + j]; is[j] = invstd[c0 + j]; }
-        for (long long p = static_cast<long long>(blockIdx.x) * ppb + threadIdx.x / tpp; p < M; p += static_cast<long long>(gridDim.x) * ppb) {
-            Bf16x8 vg, va;
-            vg.raw = *reinterpret_cast<const uint4 *>(dy + p * C + c0);
-            va.raw = *reinterpret_cast<const uint4 *>(a + p * C + c0);
-            float g[8], x[8];
-            vg.unpack(g);
-            va.unpack(x);
+        for_rows4x2(dy, a, static_cast<long long>(blockIdx.x) * ppb + threadIdx.x / tpp, static_cast<long long>(gridDim.x) * ppb, M, C,
+                    c0, [&](long long, const uint4 &rg, const uint4 &ra) {
+                        Bf16x8 vg, va;
+                        vg.raw = rg;
+                        va.raw = ra;
+                        float g[8], x[8];
+                        vg.unpack(g);
+                        va.unpack(x);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                acc[0][j] = fmaf(g[j], (x[j] - mu[j]) * is[j], acc[0][j]);
-                acc[1][j] += g[j];
-            }
-        }
+                        for (int j = 0; j < 8; ++j) {
+                            acc[0][j] = fmaf(g[j], (x[j] - mu[j]) * is[j], acc[0][j]);
+                            acc[1][j] += g[j];
+                        }
+                    });
     }
-    block_channel_atomic<2>(acc, C, threadIdx.x < ppb * tpp ? c0 : C, dgamma_dbeta);
+    block_channel_atomic<2, true>(acc, C, threadIdx.x < ppb * tpp ? c0 : C, dgamma_dbeta);
 }
 
 // dz = act'(a) * gamma * invstd * (dy - dbeta/M - xhat * dgamma/M);  dbias[c] += sum_p dz
@@ -153,30 +225,31 @@ bn_bwd_apply_kernel(const __nv_bfloat16 *__restrict__ dy, const __nv_bfloat16 *_
             k2[j] = dgamma_dbeta[C + c0 + j] * invM;
             k3[j] = dgamma_dbeta[c0 + j] * invM;
         }
-        for (long long p = static_cast<long long>(blockIdx.x) * ppb + threadIdx.x / tpp; p < M; p += static_cast<long long>(gridDim.x) * ppb) {
-            Bf16x8 vg, va;
-            vg.raw = *reinterpret_cast<const uint4 *>(dy + p * C + c0);
-            va.raw = *reinterpret_cast<const uint4 *>(a + p * C + c0);
-            float g[8], x[8], o[8];
-            vg.unpack(g);
-            va.unpack(x);
+        for_rows4x2(dy, a, static_cast<long long>(blockIdx.x) * ppb + threadIdx.x / tpp, static_cast<long long>(gridDim.x) * ppb, M, C,
+                    c0, [&](long long p, const uint4 &rg, const uint4 &ra) {
+                        Bf16x8 vg, va;
+                        vg.raw = rg;
+                        va.raw = ra;
+                        float g[8], x[8], o[8];
+                        vg.unpack(g);
+                        va.unpack(x);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                float v = k1[j] * (g[j] - k2[j] - (x[j] - mu[j]) * is[j] * k3[j]);
-                if (act == MBS_ACT_RELU && !(x[j] > 0.0f)) v = 0.0f;
-                o[j] = v;
-            }
-            const uint4 packed = Bf16x8::pack(o);
-            *reinterpret_cast<uint4 *>(dz + p * C + c0) = packed;
-            Bf16x8 back;
-            back.raw = packed;
-            float r[8];
-            back.unpack(r);
+                        for (int j = 0; j < 8; ++j) {
+                            float v = k1[j] * (g[j] - k2[j] - (x[j] - mu[j]) * is[j] * k3[j]);
+                            if (act == MBS_ACT_RELU && !(x[j] > 0.0f)) v = 0.0f;
+                            o[j] = v;
+                        }
+                        const uint4 packed = Bf16x8::pack(o);
+                        *reinterpret_cast<uint4 *>(dz + p * C + c0) = packed;
+                        Bf16x8 back;
+                        back.raw = packed;
+                        float r[8];
+                        back.unpack(r);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) acc[0][j] += r[j];
-        }
+                        for (int j = 0; j < 8; ++j) acc[0][j] += r[j];
+                    });
     }
-    block_channel_atomic<1>(acc, C, threadIdx.x < ppb * tpp ? c0 : C, dbias);
+    block_channel_atomic<1, true>(acc, C, threadIdx.x < ppb * tpp ? c0 : C, dbias);
 }
 
 // 1x1 head forward: pred[p] = sum_c y[p][c] * w[c] + b
@@ -307,11 +380,18 @@ first_conv_wgrad_kernel(const float *__restrict__ x, const __nv_bfloat16 *__rest
     for (int i = threadIdx.x; i < C * 9; i += blockDim.x) atomicAdd(&dw[i], s_acc[i]);
 }
 
-inline int grid_rows(long long M, int C) {          // blocks for the row-vectorised reductions: ~8 rows per thread
+constexpr int BN_MAX_BLOCKS = 148 * 4;
+inline int grid_rows(long long M, int C) {          // blocks for the row-vectorised reductions: >= 8 rows per thread
     const long long ppb = 256 / (C / 8);
     long long b = (M + ppb * 8 - 1) / (ppb * 8);
     if (b < 1) b = 1;
-    return static_cast<int>(b > 148 * 8 ? 148 * 8 : b);
+    static int cap = 0;
+    if (cap == 0) {
+        const char *e = getenv("MBS_BN_BLOCKS");       // A/B knob, <= BN_MAX_BLOCKS
+        cap = e ? atoi(e) : 2 * 148;                   // one resident wave at 2 blocks / SM (measured: 296 beats 148 and 592)
+        if (cap < 1 || cap > BN_MAX_BLOCKS) cap = BN_MAX_BLOCKS;
+    }
+    return static_cast<int>(b > cap ? cap : b);
 }
 inline int grid_for(long long work, int per_block, int cap) {
     long long b = (work + per_block - 1) / per_block;
@@ -325,32 +405,40 @@ extern "C" int mbs_bn_train_fwd(const void *a, long long M, int C, const float *
                                 float *sums_scratch, float *mean, float *invstd, float *var_unbiased, void *stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     MBS_REQUIRE(M > 0 && C >= 8 && C % 8 == 0 && C <= 2048 && 256 % (C / 8) == 0, "bn_train_fwd: bad shape (C must be 8*2^k <= 2048)");
-    MBS_CHECK_CUDA(cudaMemsetAsync(sums_scratch, 0, 2 * C * sizeof(float), stream));
-    bn_stats_kernel<<<grid_rows(M, C), 256, 0, stream>>>(static_cast<const __nv_bfloat16 *>(a), M, C, sums_scratch);
+    const int grid = grid_rows(M, C);
+    float *part = sums_scratch + 2 * C;          // [grid][2][C] per-block partial sums
+    bn_stats_kernel<<<grid, 256, 0, stream>>>(static_cast<const __nv_bfloat16 *>(a), M, C, part);
     MBS_CHECK_LAUNCH();
-    bn_finalize_kernel<<<mbs::cdiv(C, 128), 128, 0, stream>>>(sums_scratch, M, C, eps, mean, invstd, var_unbiased);
+    reduce_partials_kernel<<<mbs::cdiv(2 * C, 128), 128, 0, stream>>>(part, grid, 2 * C, sums_scratch);
     MBS_CHECK_LAUNCH();
-    const long long total = M * C;
-    bn_apply_kernel<<<static_cast<int>((total / 8 + 255) / 256), 256, 0, stream>>>(
-        static_cast<const __nv_bfloat16 *>(a), total, C, mean, invstd, gamma, beta, static_cast<__nv_bfloat16 *>(y));
+    bn_finalize_kernel<<<mbs::cdiv(C, 128), 128, 0, stream>>>(sums_scratch, M, C, eps, gamma, beta, mean, invstd, var_unbiased);
+    MBS_CHECK_LAUNCH();
+    bn_apply_kernel<<<grid, 256, 0, stream>>>(static_cast<const __nv_bfloat16 *>(a), M, C, sums_scratch,
+                                                         static_cast<__nv_bfloat16 *>(y));
     MBS_CHECK_LAUNCH();
     return 0;
 }
 
+extern "C" size_t mbs_bn_scratch_floats(int C) { return static_cast<size_t>(C) * (2 + 2 * BN_MAX_BLOCKS); }
+
 extern "C" int mbs_bn_train_bwd(const void *dy, const void *a, long long M, int C, const float *mean, const float *invstd,
-                                const float *gamma, int act, void *dz, float *dgamma_dbeta, float *dbias, void *stream_) {
+                                const float *gamma, int act, void *dz, float *dgamma_dbeta, float *dbias, float *scratch,
+                                void *stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     MBS_REQUIRE(M > 0 && C >= 8 && C % 8 == 0 && C <= 2048 && 256 % (C / 8) == 0, "bn_train_bwd: bad shape");
     MBS_REQUIRE(act == MBS_ACT_NONE || act == MBS_ACT_RELU, "bn_train_bwd: only relu / none are supported in training");
-    MBS_CHECK_CUDA(cudaMemsetAsync(dgamma_dbeta, 0, 2 * C * sizeof(float), stream));
-    MBS_CHECK_CUDA(cudaMemsetAsync(dbias, 0, C * sizeof(float), stream));
     const int grid = grid_rows(M, C);
+    float *part = scratch + 2 * C;               // [grid][2][C], then reused as [grid][C]
     bn_bwd_reduce_kernel<<<grid, 256, 0, stream>>>(static_cast<const __nv_bfloat16 *>(dy), static_cast<const __nv_bfloat16 *>(a), M,
-                                                   C, mean, invstd, dgamma_dbeta);
+                                                   C, mean, invstd, part);
+    MBS_CHECK_LAUNCH();
+    reduce_partials_kernel<<<mbs::cdiv(2 * C, 128), 128, 0, stream>>>(part, grid, 2 * C, dgamma_dbeta);
     MBS_CHECK_LAUNCH();
     bn_bwd_apply_kernel<<<grid, 256, 0, stream>>>(static_cast<const __nv_bfloat16 *>(dy), static_cast<const __nv_bfloat16 *>(a), M,
                                                   C, mean, invstd, gamma, dgamma_dbeta, act, static_cast<__nv_bfloat16 *>(dz),
-                                                  dbias);
+                                                  part);
+    MBS_CHECK_LAUNCH();
+    reduce_partials_kernel<<<mbs::cdiv(C, 128), 128, 0, stream>>>(part, grid, C, dbias);
     MBS_CHECK_LAUNCH();
     return 0;
 }

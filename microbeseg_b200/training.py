@@ -42,7 +42,7 @@ class TrainEngine:
             raise RuntimeError("microbeseg_b200.training needs a CUDA device (no CPU fallback)")
         self.chans = net._chans
         self._const = {}
-        self._scratch = torch.empty(4 * 2048, dtype=torch.float32, device=self.dev)
+        self._scratch = torch.empty(int(self.L.mbs_bn_scratch_floats(2048)), dtype=torch.float32, device=self.dev)
         self.use_graph = use_graph
         self._graphs = {}
 
@@ -302,7 +302,7 @@ class TrainEngine:
         dbias = torch.empty(c, dtype=torch.float32, device=self.dev)
         nat.check(self.L.mbs_bn_train_bwd(dy.data_ptr(), a.data_ptr(), m, c, lay.mean.data_ptr(), lay.invstd.data_ptr(),
                                           bn.weight.data_ptr(), lay.act, dz.data_ptr(), dgb.data_ptr(), dbias.data_ptr(),
-                                          self._sp()), "bn_train_bwd")
+                                          self._scratch.data_ptr(), self._sp()), "bn_train_bwd")
         bn.weight.grad = dgb[:c].clone()
         bn.bias.grad = dgb[c:].clone()
         lay.conv.bias.grad = dbias
