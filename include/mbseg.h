@@ -135,10 +135,12 @@ int mbs_pp_watershed(const float *image, const int32_t *markers, const uint8_t *
 /* ---------------------------------------------------------------------------------------- */
 /* BatchNorm2d, training mode (unets.py:128,153,206,246): batch mean / biased variance over the M = N*H*W rows of
  * a [M][C]; y = gamma*(a-mean)*invstd + beta.  sums_scratch: mbs_bn_scratch_floats(C) floats (per-block partial sums,
- * reduced without atomics: the statistics are deterministic); var_unbiased (optional) feeds running_var. */
+ * reduced without atomics: the statistics are deterministic).  running_mean / running_var / num_batches_tracked
+ * (optional, NULL to skip) are updated like nn.BatchNorm2d in training mode (momentum, unbiased variance). */
 size_t mbs_bn_scratch_floats(int C);
 int mbs_bn_train_fwd(const void *a, long long M, int C, const float *gamma, const float *beta, float eps, void *y,
-                     float *sums_scratch, float *mean, float *invstd, float *var_unbiased, void *stream);
+                     float *sums_scratch, float *mean, float *invstd, float momentum, float *running_mean,
+                     float *running_var, long long *num_batches_tracked, void *stream);
 /* backward of  y = BN(act(z)):  dz = act'(a) * gamma*invstd*(dy - dbeta/M - xhat*dgamma/M);  dgamma_dbeta: [2*C]
  * (dgamma then dbeta), dbias[c] = sum dz (gradient of the conv bias).  act: MBS_ACT_RELU or MBS_ACT_NONE.
  * scratch: mbs_bn_scratch_floats(C) floats. */
@@ -149,6 +151,10 @@ int mbs_head_fwd(const void *y, long long M, int C, const float *w, const float 
 int mbs_smoothl1(const float *pred, const float *target, long long M, float *loss_accum, float *grad, void *stream);
 int mbs_head_bwd(const float *g, const void *y, long long M, int C, const float *w, void *dy, float *dw_db, void *stream);
 /* layout / glue kernels of the backward pass */
+/* data-gradient filter of a 3x3 conv: packed[ci][tap][co] = bf16(w[co][ci][8 - tap]) from the reference-layout weight */
+int mbs_pack_conv3x3_dgrad(const float *w, int Cout, int Cin, void *packed, void *stream);
+/* weight gradient g[co][tap][ci] (mbs_conv_wgrad layout) -> reference layout out[co][ci][3][3] */
+int mbs_unpack_conv3x3_grad(const float *g, int Cout, int Cin, float *out, void *stream);
 int mbs_zero_insert_up2(const void *src, int N, int H, int W, int C, void *dst, void *stream);
 int mbs_add3_bf16(const void *a, const void *b, const void *c, long long n, void *out, void *stream);
 int mbs_first_conv_wgrad(const float *x, const void *dz, int N, int H, int W, int C, float *dw, void *stream);

@@ -141,8 +141,10 @@ __global__ void reduce_partials_kernel(const float *__restrict__ part, int nbloc
 }
 
 // also turns the sums scratch into the affine of the apply pass: sums[c] = gamma*invstd, sums[C+c] = beta - mean*gamma*invstd
+// and updates the running statistics like nn.BatchNorm2d.forward in training mode (unbiased variance, momentum).
 __global__ void bn_finalize_kernel(float *sums, long long M, int C, float eps, const float *__restrict__ gamma,
-                                   const float *__restrict__ beta, float *mean, float *invstd, float *var_unbiased) {
+                                   const float *__restrict__ beta, float *mean, float *invstd, float momentum,
+                                   float *running_mean, float *running_var, long long *num_batches_tracked) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= C) return;
     const double m = static_cast<double>(sums[c]) / static_cast<double>(M);
@@ -150,7 +152,13 @@ __global__ void bn_finalize_kernel(float *sums, long long M, int C, float eps, c
     if (var < 0.0) var = 0.0;
     mean[c] = static_cast<float>(m);
     invstd[c] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
-    if (var_unbiased) var_unbiased[c] = static_cast<float>(M > 1 ? var * static_cast<double>(M) / static_cast<double>(M - 1) : var);
+    if (running_mean) {
+        const float var_u = static_cast<float>(M > 1 ? var * static_cast<double>(M) / static_cast<double>(M - 1) : var);
+        // the two-step form of running.mul_(1 - momentum).add_(stat, alpha=momentum)
+        running_mean[c] = running_mean[c] * (1.0f - momentum) + mean[c] * momentum;
+        running_var[c] = running_var[c] * (1.0f - momentum) + var_u * momentum;
+        if (c == 0 && num_batches_tracked) *num_batches_tracked += 1;
+    }
     const float k = gamma[c] * invstd[c];
     sums[c] = k;
     sums[C + c] = fmaf(-mean[c], k, beta[c]);
@@ -321,6 +329,37 @@ head_bwd_kernel(const float *__restrict__ g, const __nv_bfloat16 *__restrict__ y
     if ((threadIdx.x & 31) == 0 && gsum != 0.0f) atomicAdd(&dw_db[C], gsum);
 }
 
+// Data-gradient filter of a 3x3 conv in GEMM-packed form: out[ci][t][co] = bf16(w[co][ci][8 - t]) (spatially flipped,
+// in/out channels swapped) straight from the reference-layout fp32 weight [Cout][Cin][3][3].  32x32 (co, ci) tiles
+// through shared memory: reads are 288-float runs, writes 64-byte runs.
+__global__ void __launch_bounds__(256) pack_dgrad3x3_kernel(const float *__restrict__ w, int Cout, int Cin, __nv_bfloat16 *__restrict__ out) {
+    __shared__ float tile[32][32 * 9 + 1];
+    const int co0 = blockIdx.x * 32, ci0 = blockIdx.y * 32;
+    for (int i = threadIdx.x; i < 32 * 288; i += 256) {
+        const int r = i / 288, k = i - r * 288;
+        tile[r][k] = (co0 + r < Cout && ci0 + k / 9 < Cin) ? w[(static_cast<size_t>(co0 + r) * Cin + ci0) * 9 + k] : 0.0f;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 32 * 9 * 32; i += 256) {
+        const int co = i & 31, t = (i >> 5) % 9, ci = i / 288;
+        if (co0 + co < Cout && ci0 + ci < Cin)
+            out[(static_cast<size_t>(ci0 + ci) * 9 + t) * Cout + co0 + co] = __float2bfloat16_rn(tile[co][ci * 9 + (8 - t)]);
+    }
+}
+
+// Weight gradient from the GEMM layout g[co][t][ci] to the reference layout out[co][ci][3][3] (fp32)
+__global__ void __launch_bounds__(256) unpack_grad3x3_kernel(const float *__restrict__ g, int Cin, float *__restrict__ out) {
+    __shared__ float tile[9][256 + 1];
+    const int co = blockIdx.x, ci0 = blockIdx.y * 256;
+    const int n = min(256, Cin - ci0);
+    for (int i = threadIdx.x; i < 9 * 256; i += 256) {
+        const int t = i >> 8, c = i & 255;
+        if (c < n) tile[t][c] = g[(static_cast<size_t>(co) * 9 + t) * Cin + ci0 + c];
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < n * 9; i += 256) out[(static_cast<size_t>(co) * Cin + ci0) * 9 + i] = tile[i % 9][i / 9];
+}
+
 // U[n][2y][2x][c] = src[n][y][x][c], zeros elsewhere (input of the stride-2 conv's data gradient)
 __global__ void zero_insert_kernel(const __nv_bfloat16 *__restrict__ src, int N, int H, int W, int C, __nv_bfloat16 *__restrict__ dst) {
     const long long i = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) * 8;   // 8 channels (16 B) per thread
@@ -402,7 +441,8 @@ inline int grid_for(long long work, int per_block, int cap) {
 }  // namespace
 
 extern "C" int mbs_bn_train_fwd(const void *a, long long M, int C, const float *gamma, const float *beta, float eps, void *y,
-                                float *sums_scratch, float *mean, float *invstd, float *var_unbiased, void *stream_) {
+                                float *sums_scratch, float *mean, float *invstd, float momentum, float *running_mean,
+                                float *running_var, long long *num_batches_tracked, void *stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     MBS_REQUIRE(M > 0 && C >= 8 && C % 8 == 0 && C <= 2048 && 256 % (C / 8) == 0, "bn_train_fwd: bad shape (C must be 8*2^k <= 2048)");
     const int grid = grid_rows(M, C);
@@ -411,7 +451,8 @@ extern "C" int mbs_bn_train_fwd(const void *a, long long M, int C, const float *
     MBS_CHECK_LAUNCH();
     reduce_partials_kernel<<<mbs::cdiv(2 * C, 128), 128, 0, stream>>>(part, grid, 2 * C, sums_scratch);
     MBS_CHECK_LAUNCH();
-    bn_finalize_kernel<<<mbs::cdiv(C, 128), 128, 0, stream>>>(sums_scratch, M, C, eps, gamma, beta, mean, invstd, var_unbiased);
+    bn_finalize_kernel<<<mbs::cdiv(C, 128), 128, 0, stream>>>(sums_scratch, M, C, eps, gamma, beta, mean, invstd, momentum,
+                                                              running_mean, running_var, num_batches_tracked);
     MBS_CHECK_LAUNCH();
     bn_apply_kernel<<<grid, 256, 0, stream>>>(static_cast<const __nv_bfloat16 *>(a), M, C, sums_scratch,
                                                          static_cast<__nv_bfloat16 *>(y));
@@ -466,6 +507,23 @@ extern "C" int mbs_head_bwd(const float *g, const void *y, long long M, int C, c
     MBS_CHECK_CUDA(cudaMemsetAsync(dw_db, 0, (C + 1) * sizeof(float), stream));
     head_bwd_kernel<<<grid_rows(M, C), 256, 0, stream>>>(g, static_cast<const __nv_bfloat16 *>(y), M, C, w,
                                                                       static_cast<__nv_bfloat16 *>(dy), dw_db);
+    MBS_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int mbs_pack_conv3x3_dgrad(const float *w, int Cout, int Cin, void *packed, void *stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    MBS_REQUIRE(w && packed && Cout > 0 && Cin > 0, "pack_conv3x3_dgrad: bad arguments");
+    pack_dgrad3x3_kernel<<<dim3(mbs::cdiv(Cout, 32), mbs::cdiv(Cin, 32)), 256, 0, stream>>>(w, Cout, Cin,
+                                                                                          static_cast<__nv_bfloat16 *>(packed));
+    MBS_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int mbs_unpack_conv3x3_grad(const float *g, int Cout, int Cin, float *out, void *stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    MBS_REQUIRE(g && out && Cout > 0 && Cin > 0, "unpack_conv3x3_grad: bad arguments");
+    unpack_grad3x3_kernel<<<dim3(Cout, mbs::cdiv(Cin, 256)), 256, 0, stream>>>(g, Cin, out);
     MBS_CHECK_LAUNCH();
     return 0;
 }

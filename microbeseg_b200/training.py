@@ -92,14 +92,12 @@ class TrainEngine:
         lay.y = torch.empty_like(a)
         lay.mean = torch.empty(c, dtype=torch.float32, device=self.dev)
         lay.invstd = torch.empty(c, dtype=torch.float32, device=self.dev)
-        var_u = torch.empty(c, dtype=torch.float32, device=self.dev)
+        # batch statistics, y = BN(a), and the running statistics (torch defaults: momentum 0.1, unbiased variance)
         nat.check(self.L.mbs_bn_train_fwd(a.data_ptr(), m, c, bn.weight.data_ptr(), bn.bias.data_ptr(), BN_EPS,
                                           lay.y.data_ptr(), self._scratch.data_ptr(), lay.mean.data_ptr(),
-                                          lay.invstd.data_ptr(), var_u.data_ptr(), self._sp()), "bn_train_fwd")
-        with torch.no_grad():      # running statistics, torch defaults (momentum 0.1, unbiased variance)
-            bn.running_mean.mul_(1 - BN_MOMENTUM).add_(lay.mean, alpha=BN_MOMENTUM)
-            bn.running_var.mul_(1 - BN_MOMENTUM).add_(var_u, alpha=BN_MOMENTUM)
-            bn.num_batches_tracked += 1
+                                          lay.invstd.data_ptr(), BN_MOMENTUM, bn.running_mean.data_ptr(),
+                                          bn.running_var.data_ptr(), bn.num_batches_tracked.data_ptr(), self._sp()),
+                  "bn_train_fwd")
 
     def _wgrad(self, kind, n, ho, wo, a, cm, b, cn, out, out_ld, out_coff):
         """weight gradient on the tensor cores straight from the NHWC bf16 activations: ``a`` = dz (conv) / d(up)
@@ -322,21 +320,28 @@ class TrainEngine:
         for s, cs in zip(lay.srcs, cins):
             self._wgrad(1 if stride2 else 0, n, ho, wo, dz, cout, s, cs, dwp, cin, off)
             off += cs
-        conv.weight.grad = dwp.view(cout, 3, 3, cin).permute(0, 3, 1, 2).contiguous()
-        # data gradient: full-resolution stride-1 conv with the flipped, transposed filter
-        wflip = conv.weight.detach().float().flip(2, 3).transpose(0, 1).contiguous()      # [Cin, Cout, 3, 3]
-        packed = self._pack3x3(wflip)                                                     # [Cin][9][Cout]
+        dw = torch.empty((cout, cin, 3, 3), dtype=torch.float32, device=self.dev)
+        nat.check(self.L.mbs_unpack_conv3x3_grad(dwp.data_ptr(), cout, cin, dw.data_ptr(), self._sp()), "unpack_grad")
+        conv.weight.grad = dw
+        # data gradient: full-resolution stride-1 conv with the flipped, transposed filter [Cin][9][Cout]
+        packed = torch.empty((cin, 9, cout), dtype=torch.bfloat16, device=self.dev)
+        nat.check(self.L.mbs_pack_conv3x3_dgrad(conv.weight.detach().float().contiguous().data_ptr(), cout, cin,
+                                                packed.data_ptr(), self._sp()), "pack_dgrad")
         src = dz
         h, w = ho, wo
         if stride2:
             src = torch.empty((n, 2 * ho, 2 * wo, cout), dtype=torch.bfloat16, device=self.dev)
             nat.check(self.L.mbs_zero_insert_up2(dz.data_ptr(), n, ho, wo, cout, src.data_ptr(), self._sp()), "zero_insert")
             h, w = 2 * ho, 2 * wo
-        dx = torch.empty((n, h, w, cin), dtype=torch.bfloat16, device=self.dev)
-        self._conv(0, n, h, w, [src], packed, cin, self._zeros(cin), ACT_NONE, dx)
-        if len(cins) == 1:
-            return [dx]
-        return [dx[..., :cins[0]].contiguous(), dx[..., cins[0]:].contiguous()]
+        # one conv per source of a concatenated input: the rows [off, off+cs) of the packed filter are that source's
+        # gradient, written contiguously (no strided split copies)
+        dxs, off = [], 0
+        for cs in cins:
+            dx = torch.empty((n, h, w, cs), dtype=torch.bfloat16, device=self.dev)
+            self._conv(0, n, h, w, [src], packed[off:off + cs], cs, self._zeros(cs), ACT_NONE, dx)
+            dxs.append(dx)
+            off += cs
+        return dxs
 
     def _bwd_first(self, lay, dy):
         conv = lay.conv
