@@ -106,3 +106,51 @@ def test_cuda_graph_replay_matches_eager(native_lib):
             # fp32 atomics reorder run to run -> bf16 roundings flip; the steps agree to a few % in L2 on this tiny batch, not bitwise
             rel = float((p1.grad - p2.grad).norm() / (p2.grad.norm() + 1e-12))
             assert rel < 0.15, (it, n1, rel)
+
+
+WGRAD_CASES = [(0, 1, 8, 64, 64, 64), (0, 2, 32, 48, 64, 64), (0, 2, 16, 20, 128, 128), (0, 1, 8, 64, 256, 512), (0, 2, 20, 20, 128, 64),
+               (0, 1, 6, 4, 64, 64), (1, 2, 16, 24, 64, 64), (1, 2, 20, 20, 128, 128), (2, 2, 8, 24, 64, 128), (2, 2, 20, 20, 256, 512),
+               (0, 1, 160, 160, 64, 128)]
+
+
+@pytest.mark.parametrize("kind,N,Ho,Wo,Cm,Cn", WGRAD_CASES)
+def test_conv_wgrad_vs_torch(native_lib, kind, N, Ho, Wo, Cm, Cn):
+    """mbs_conv_wgrad (MN-major tcgen05 GEMM straight from NHWC) vs torch autograd in float64 on the same bf16-rounded
+    operands: conv3x3 stride 1 (incl. the two-taps-per-tile path for Cm == 64), stride 2, transposed conv; ragged patches."""
+    import ctypes
+    from microbeseg_b200 import _native as nat
+    import torch.nn.functional as F
+    L = native_lib
+    dev = torch.device("cuda:0")
+    torch.manual_seed(Ho * Wo + Cm)
+    s = 2 if kind == 1 else 1
+    if kind == 2:
+        dz = torch.randn(N, 2 * Ho, 2 * Wo, Cm, device=dev).bfloat16()
+        x = torch.randn(N, Ho, Wo, Cn, device=dev).bfloat16()
+        taps = 4
+    else:
+        dz = torch.randn(N, Ho, Wo, Cm, device=dev).bfloat16()
+        x = torch.randn(N, s * Ho, s * Wo, Cn, device=dev).bfloat16()
+        taps = 9
+    out = torch.zeros(Cm, taps, Cn, device=dev)
+    d = nat.WgradDesc()
+    d.kind, d.N, d.Ho, d.Wo = kind, N, Ho, Wo
+    d.a, d.Cm, d.lda, d.coffa = dz.data_ptr(), Cm, Cm, 0
+    d.b, d.Cn, d.ldb, d.coffb = x.data_ptr(), Cn, Cn, 0
+    d.out, d.out_ld, d.out_coff = out.data_ptr(), Cn, 0
+    nat.check(L.mbs_conv_wgrad(ctypes.byref(d), nat.stream_ptr()), "wgrad")
+    torch.cuda.synchronize()
+    with torch.enable_grad():
+        xf, gf = x.double().permute(0, 3, 1, 2), dz.double().permute(0, 3, 1, 2)
+        if kind == 2:
+            w = torch.zeros(Cn, Cm, 2, 2, device=dev, dtype=torch.float64, requires_grad=True)
+            F.conv_transpose2d(xf, w, stride=2).backward(gf)
+            ref = w.grad.permute(1, 2, 3, 0).reshape(Cm, 4, Cn)
+        else:
+            w = torch.zeros(Cm, Cn, 3, 3, device=dev, dtype=torch.float64, requires_grad=True)
+            F.conv2d(xf, w, stride=s, padding=1).backward(gf)
+            ref = w.grad.permute(0, 2, 3, 1).reshape(Cm, 9, Cn)
+    err = (out.double() - ref).abs().max().item()
+    # exact bf16 products, fp32 accumulation in a different order: tolerance = a few fp32 ulps of the sum of magnitudes
+    assert err <= 2e-5 * (N * Ho * Wo) ** 0.5 * 4 + 1e-4 * ref.abs().max().item(), err
+    assert L.mbs_debug_flags(1) == 0

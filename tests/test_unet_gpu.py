@@ -118,6 +118,12 @@ CONV_CASES = [
     (0, 1, 8, 16, 64, 0, 64), (0, 1, 24, 40, 64, 0, 64), (0, 2, 32, 32, 128, 0, 128), (0, 1, 32, 32, 64, 64, 64),
     (0, 1, 16, 16, 512, 512, 512), (1, 1, 48, 80, 128, 0, 128), (2, 1, 8, 24, 1024, 0, 512), (0, 1, 4, 4, 1024, 0, 1024),
     (1, 3, 16, 16, 256, 0, 256), (2, 2, 16, 16, 128, 0, 64),
+    # large enough (>= 148 work items) for the paired-tile (MT = 2) path of the Cout = 128 layers, ragged edges
+    (0, 1, 200, 200, 128, 0, 128), (1, 1, 400, 416, 128, 0, 128), (0, 1, 208, 200, 128, 128, 128), (0, 2, 168, 160, 64, 0, 128),
+    # transposed convs on 256-column tiles with 4 epilogue groups (ragged patch edges) and the 128-column fallback (N > 1, H % 8 != 0)
+    (2, 1, 40, 56, 128, 0, 64), (2, 1, 24, 40, 256, 0, 128), (2, 2, 12, 16, 128, 0, 64),
+    # full-resolution halo kernel: single and dual source, ragged
+    (0, 1, 72, 100, 64, 0, 64), (0, 1, 48, 36, 64, 64, 64),
 ]
 
 
