@@ -125,6 +125,11 @@ int mbs_pp_front(const float *border, const float *cell, int H, int W, int ld, f
                  float th_cell, float *cell_smooth, uint8_t *mask, uint8_t *seed, void *stream);
 int mbs_pp_label8(const uint8_t *binary, int H, int W, int32_t *labels, int32_t *n_out,
                   void *workspace, size_t workspace_bytes, void *stream);
+/* skimage.measure.label of an INTEGER instance image (8-connectivity, equal non-zero values; labels 1..n in raster
+ * order of each component's first pixel) -- what eval.py:261,313 apply to ground truth and prediction before AJI+.
+ * workspace: mbs_postproc_workspace_bytes(H, W). */
+int mbs_label8_instances(const uint16_t *image, int H, int W, int32_t *labels, int32_t *n_out,
+                         void *workspace, size_t workspace_bytes, void *stream);
 int mbs_pp_watershed(const float *image, const int32_t *markers, const uint8_t *mask, int H, int W,
                      int32_t *labels_out, void *workspace, size_t workspace_bytes,
                      int64_t *info_host, int force_sequential, void *stream);

@@ -183,6 +183,27 @@ __global__ void ccl_merge8_kernel(const uint8_t *__restrict__ fg, int H, int W, 
         }
     }
 }
+// measure.label on an INTEGER image (eval.py:261,313 label the ground truth and the prediction before AJI+):
+// 8-connected pixels belong to one component iff they carry the same non-zero value.
+__global__ void ccl_init_values_kernel(const uint16_t *__restrict__ v, int n, int *__restrict__ L) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) L[i] = v[i] ? i : -1;
+}
+__global__ void ccl_merge8_values_kernel(const uint16_t *__restrict__ v, int H, int W, int *L) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= W || y >= H) return;
+    const int i = y * W + x;
+    const uint16_t me = v[i];
+    if (!me) return;
+    if (x > 0 && v[i - 1] == me) uf_union(L, i, i - 1);
+    if (y > 0) {
+        const int u = i - W;
+        if (v[u] == me) uf_union(L, i, u);
+        if (x > 0 && v[u - 1] == me) uf_union(L, i, u - 1);
+        if (x + 1 < W && v[u + 1] == me) uf_union(L, i, u + 1);
+    }
+}
 __global__ void ccl_compress_kernel(int n, int *L) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n && L[i] >= 0) L[i] = uf_find(L, i);
@@ -801,6 +822,46 @@ extern "C" int mbs_pp_label8(const uint8_t *binary, int H, int W, int32_t *label
     MBS_CHECK_LAUNCH();
     // areas := large constant at roots so that every component survives keep_root()
     MBS_CHECK_CUDA(cudaMemsetAsync(area, 0x3f, n * 4, stream));
+    const int tl = mbs::cdiv(nn, SCAN_TILE);
+    rank_count_kernel<<<tl, SCAN_THREADS, 0, stream>>>(roots, area, nn, st, 0, tiles);
+    MBS_CHECK_LAUNCH();
+    rank_scan_kernel<<<1, 1024, 0, stream>>>(tiles, tl, st);
+    MBS_CHECK_LAUNCH();
+    rank_assign_kernel<<<tl, SCAN_THREADS, 0, stream>>>(roots, area, nn, st, 0, tiles, rank);
+    MBS_CHECK_LAUNCH();
+    labels_from_roots_kernel<<<nb, 256, 0, stream>>>(roots, rank, nn, labels);
+    MBS_CHECK_LAUNCH();
+    if (n_out) {
+        MBS_CHECK_CUDA(cudaMemcpyAsync(n_out, &st->n_markers, sizeof(int), cudaMemcpyDeviceToDevice, stream));
+    }
+    return 0;
+}
+
+extern "C" int mbs_label8_instances(const uint16_t *image, int H, int W, int32_t *labels, int32_t *n_out, void *workspace,
+                                    size_t workspace_bytes, void *stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    const size_t n = static_cast<size_t>(H) * W;
+    MBS_REQUIRE(H > 0 && W > 0 && n < (1ull << 31), "label8_instances: bad shape");
+    MBS_REQUIRE(workspace_bytes >= label_ws_bytes(n), "label8_instances: workspace too small (%zu < %zu)", workspace_bytes,
+                label_ws_bytes(n));
+    Carver cv{static_cast<char *>(workspace), workspace_bytes};
+    Stats *st = cv.take<Stats>(1);
+    int *area = cv.take<int>(n);
+    int *rank = cv.take<int>(n);
+    int *tiles = cv.take<int>((n + SCAN_TILE - 1) / SCAN_TILE);
+    int *roots = cv.take<int>(n);
+    MBS_REQUIRE(cv.ok, "label8_instances: workspace carve failed");
+    MBS_CHECK_CUDA(cudaMemsetAsync(st, 0, sizeof(Stats), stream));
+    const int nn = static_cast<int>(n);
+    const int nb = mbs::cdiv(nn, 256);
+    dim3 b2(32, 8), g2(mbs::cdiv(W, 32), mbs::cdiv(H, 8));
+    ccl_init_values_kernel<<<nb, 256, 0, stream>>>(image, nn, roots);
+    MBS_CHECK_LAUNCH();
+    ccl_merge8_values_kernel<<<g2, b2, 0, stream>>>(image, H, W, roots);
+    MBS_CHECK_LAUNCH();
+    ccl_compress_kernel<<<nb, 256, 0, stream>>>(nn, roots);
+    MBS_CHECK_LAUNCH();
+    MBS_CHECK_CUDA(cudaMemsetAsync(area, 0x3f, n * 4, stream));      // every component survives the area filter
     const int tl = mbs::cdiv(nn, SCAN_TILE);
     rank_count_kernel<<<tl, SCAN_THREADS, 0, stream>>>(roots, area, nn, st, 0, tiles);
     MBS_CHECK_LAUNCH();
