@@ -172,6 +172,7 @@ def main():
     device = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # keep NCCL's version / debug lines off stdout (one JSON line)
         dist.init_process_group("nccl", device_id=device)
     torch.set_grad_enabled(False)
     size = args.size

@@ -20,6 +20,7 @@ torch.cuda.set_device(local)
 dev = torch.device("cuda", local)
 if world > 1:
     os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # keep NCCL's version / debug lines off stdout (one JSON line)
     dist.init_process_group("nccl", device_id=dev)
 from microbeseg_b200 import _native as nat, synthetic as sy, labels as lab
 from microbeseg_b200.unets import build_unet
