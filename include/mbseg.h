@@ -177,6 +177,21 @@ typedef struct {
 int mbs_conv_wgrad(const mbs_wgrad_desc *d, void *stream);
 
 /* ---------------------------------------------------------------------------------------- */
+/* Ranger optimizer step (RAdam + gradient centralisation + lookahead), replaces the per-tensor loop of    */
+/* src/training/ranger2020.py:101-208 (the reference's default --optimizer) with one launch over a table   */
+/* of all parameter tensors.  Rows: output-channel slices of dim>1 tensors (gc = 1: the gradient mean over  */
+/* the row is subtracted first, :30-40) or 1024-element chunks of 1-D tensors (gc = 0); row_start = prefix  */
+/* sum of `rows`.  step_lr = step_size*lr, use_denom = (N_sma > threshold) from the host schedule (:165-180)*/
+/* ---------------------------------------------------------------------------------------- */
+typedef struct {
+    float *p, *g, *exp_avg, *exp_avg_sq, *slow;   /* fp32 device tensors of identical shape */
+    long long numel;
+    int rows, row_len, gc, row_start;
+} mbs_ranger_tensor;
+int mbs_ranger_step(const mbs_ranger_tensor *tensors_dev, int n_tensors, int total_rows, float beta1, float beta2,
+                    float eps, float weight_decay, float step_lr, int use_denom, int lookahead, float alpha, void *stream);
+
+/* ---------------------------------------------------------------------------------------- */
 /* training-label generation, distance method (replaces src/training/train_data_representations */
 /* .py:261-361 distance_label + :102-126 border_label + :40-72 bottom_hat_closing, and the     */
 /* max_mal of src/training/train.py:74-79); batched over crops                                 */

@@ -25,6 +25,12 @@ class ConvDesc(ctypes.Structure):
                 ("head_w", c_void_p), ("head_b", c_float * 4), ("head_n", c_int), ("head_out", c_void_p)]
 
 
+class RangerTensor(ctypes.Structure):
+    """mirror of mbs_ranger_tensor (include/mbseg.h)"""
+    _fields_ = [("p", c_void_p), ("g", c_void_p), ("exp_avg", c_void_p), ("exp_avg_sq", c_void_p), ("slow", c_void_p),
+                ("numel", ctypes.c_longlong), ("rows", c_int), ("row_len", c_int), ("gc", c_int), ("row_start", c_int)]
+
+
 class WgradDesc(ctypes.Structure):
     """mirror of mbs_wgrad_desc (include/mbseg.h)"""
     _fields_ = [("kind", c_int), ("N", c_int), ("Ho", c_int), ("Wo", c_int),
@@ -69,6 +75,8 @@ _SIGS = {
     "mbs_add3_bf16": (c_int, [c_void_p, c_void_p, c_void_p, ctypes.c_longlong, c_void_p, c_void_p]),
     "mbs_first_conv_wgrad": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "mbs_conv_wgrad": (c_int, [ctypes.POINTER(WgradDesc), c_void_p]),
+    "mbs_ranger_step": (c_int, [c_void_p, c_int, c_int, c_float, c_float, c_float, c_float, c_float, c_int, c_int, c_float,
+                                c_void_p]),
     "mbs_label8_instances": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "mbs_pp_watershed": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_size_t, c_void_p,
                                  c_int, c_void_p]),

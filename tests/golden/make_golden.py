@@ -3,6 +3,7 @@
   python tests/golden/make_golden.py postproc     # oracle/postproc.py on seeded synthetic maps
   python tests/golden/make_golden.py net          # the REAL reference DUNet (/root/reference) on CPU
   python tests/golden/make_golden.py labels       # oracle/labels.py on seeded synthetic instance masks
+  python tests/golden/make_golden.py ranger       # the REAL reference Ranger optimizer (/root/reference) on CPU
 
 The post-processing goldens are produced by the oracle restatement (scikit-image cannot run in
 this image -> "parity unpinned" for the skimage pieces, see oracle/postproc.py); the network
@@ -71,8 +72,55 @@ def make_labels():
         print("labels", H, W, seed, "max_mal", mal, "cells", int(m.max()))
 
 
+RANGER_SHAPES = [(8, 4, 3, 3), (8,), (6, 8, 2, 2), (5, 7), (3,), (2, 1100)]
+RANGER_CASES = {"default": dict(lr=0.05), "wd_convonly": dict(lr=0.02, weight_decay=0.01, gc_conv_only=True, k=4),
+                "nogc": dict(lr=0.05, use_gc=False, betas=(0.9, 0.99))}
+RANGER_STEPS = 14
+RANGER_SNAPSHOTS = (1, 5, 6, 7, 12, 14)
+
+
+def ranger_inputs(case_idx):
+    """seeded initial parameters and per-step gradients (regenerated identically by the tests)"""
+    rng = np.random.default_rng(7000 + case_idx)
+    params = [rng.standard_normal(s).astype(np.float32) for s in RANGER_SHAPES]
+    grads = [[(rng.standard_normal(s) * 0.3 + 0.05).astype(np.float32) for s in RANGER_SHAPES] for _ in range(RANGER_STEPS)]
+    return params, grads
+
+
+def make_ranger():
+    import contextlib
+    import importlib.util
+    import io
+    import torch
+    spec = importlib.util.spec_from_file_location("reference_ranger", "/root/reference/src/training/ranger2020.py")
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    for ci, (name, kw) in enumerate(RANGER_CASES.items()):
+        p0, grads = ranger_inputs(ci)
+        params = [torch.nn.Parameter(torch.from_numpy(a.copy())) for a in p0]
+        with contextlib.redirect_stdout(io.StringIO()):
+            opt = mod.Ranger(params, **kw)
+        out = {}
+        for step in range(1, RANGER_STEPS + 1):
+            for p, g in zip(params, grads[step - 1]):
+                p.grad = torch.from_numpy(g.copy())
+            opt.step()
+            if step in RANGER_SNAPSHOTS:
+                for i, p in enumerate(params):
+                    st = opt.state[p]
+                    out[f"s{step}_p{i}"] = p.detach().numpy().copy()
+                    out[f"s{step}_m{i}"] = st["exp_avg"].numpy().copy()
+                    out[f"s{step}_v{i}"] = st["exp_avg_sq"].numpy().copy()
+                    out[f"s{step}_slow{i}"] = st["slow_buffer"].numpy().copy()
+                    out[f"s{step}_g{i}"] = p.grad.numpy().copy()      # the reference centralises p.grad in place
+        np.savez_compressed(os.path.join(HERE, f"ranger_{name}.npz"), **out)
+        print("ranger", name, "final |p0|", float(np.abs(out[f"s{RANGER_STEPS}_p0"]).mean()))
+
+
 if __name__ == "__main__":
-    what = sys.argv[1:] or ["postproc", "net", "labels"]
+    what = sys.argv[1:] or ["postproc", "net", "labels", "ranger"]
+    if "ranger" in what:
+        make_ranger()
     if "postproc" in what:
         make_postproc()
     if "net" in what:
