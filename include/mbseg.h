@@ -141,13 +141,16 @@ int mbs_pp_watershed(const float *image, const int32_t *markers, const uint8_t *
 /* BatchNorm2d, training mode (unets.py:128,153,206,246): batch mean / biased variance over the M = N*H*W rows of
  * a [M][C]; y = gamma*(a-mean)*invstd + beta.  sums_scratch: mbs_bn_scratch_floats(C) floats (per-block partial sums,
  * reduced without atomics: the statistics are deterministic).  running_mean / running_var / num_batches_tracked
- * (optional, NULL to skip) are updated like nn.BatchNorm2d in training mode (momentum, unbiased variance). */
+ * (optional, NULL to skip) are updated like nn.BatchNorm2d in training mode (momentum, unbiased variance).
+ * act = MBS_ACT_NONE: `a` is the post-activation tensor; MBS_ACT_MISH: `a` holds the PRE-activation z and mish(z)
+ * (unets.py:81-89) is applied on load (training keeps one tensor per layer; mish' needs z). */
 size_t mbs_bn_scratch_floats(int C);
 int mbs_bn_train_fwd(const void *a, long long M, int C, const float *gamma, const float *beta, float eps, void *y,
                      float *sums_scratch, float *mean, float *invstd, float momentum, float *running_mean,
-                     float *running_var, long long *num_batches_tracked, void *stream);
+                     float *running_var, long long *num_batches_tracked, int act, void *stream);
 /* backward of  y = BN(act(z)):  dz = act'(a) * gamma*invstd*(dy - dbeta/M - xhat*dgamma/M);  dgamma_dbeta: [2*C]
- * (dgamma then dbeta), dbias[c] = sum dz (gradient of the conv bias).  act: MBS_ACT_RELU or MBS_ACT_NONE.
+ * (dgamma then dbeta), dbias[c] = sum dz (gradient of the conv bias).  act: MBS_ACT_RELU (a = post-activation),
+ * MBS_ACT_MISH (a = pre-activation z) or MBS_ACT_NONE.
  * scratch: mbs_bn_scratch_floats(C) floats. */
 int mbs_bn_train_bwd(const void *dy, const void *a, long long M, int C, const float *mean, const float *invstd,
                      const float *gamma, int act, void *dz, float *dgamma_dbeta, float *dbias, float *scratch, void *stream);

@@ -62,7 +62,7 @@ _SIGS = {
     "mbs_distance_labels": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
                                     c_void_p, c_void_p, c_size_t, c_void_p]),
     "mbs_bn_train_fwd": (c_int, [c_void_p, ctypes.c_longlong, c_int, c_void_p, c_void_p, c_float, c_void_p, c_void_p,
-                                 c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_void_p, c_void_p]),
+                                 c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     "mbs_pack_conv3x3_dgrad": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "mbs_unpack_conv3x3_grad": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "mbs_bn_train_bwd": (c_int, [c_void_p, c_void_p, ctypes.c_longlong, c_int, c_void_p, c_void_p, c_void_p, c_int,

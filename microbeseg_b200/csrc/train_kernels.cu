@@ -20,6 +20,34 @@ __device__ __forceinline__ float warp_sum(float v) {
     return v;
 }
 
+// Mish (unets.py:81-89: x * tanh(softplus(x)), softplus threshold 20) with ONE exponential:
+//   tanh(log(1 + e)) = ((1+e)^2 - 1) / ((1+e)^2 + 1) = n / (n + 2),  n = e * (e + 2),  e = exp(x)
+// (these passes are HBM bound only if the special-function unit is not asked for exp + log + tanh per element).
+__device__ __forceinline__ float mish_f(float x) {
+    if (x > 20.0f) return x;
+    const float e = __expf(x);
+    const float n = e * (e + 2.0f);
+    return x * __fdividef(n, n + 2.0f);
+}
+// d/dx mish = tanh(sp) + x * (1 - tanh(sp)^2) * sigmoid(x)
+__device__ __forceinline__ float mish_grad_f(float x) {
+    if (x > 20.0f) return 1.0f;
+    const float e = __expf(x);
+    const float n = e * (e + 2.0f);
+    const float t = __fdividef(n, n + 2.0f);
+    const float sg = __fdividef(e, e + 1.0f);
+    return fmaf(x * (1.0f - t * t), sg, t);
+}
+// Training keeps ONE activation-sized tensor per layer.  act == MBS_ACT_MISH: it is the pre-activation z (needed by
+// the derivative) and a = mish(z) is recomputed on load; otherwise it is the post-activation a itself.
+template <bool MISH>
+__device__ __forceinline__ void act_on_load(float (&f)[8]) {
+    if (MISH) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] = mish_f(f[j]);
+    }
+}
+
 // Per-channel reductions over an [M][C] bf16 matrix with fully coalesced 16-byte accesses: C/8 consecutive threads
 // cover one pixel row (8 channels each), a 256-thread block covers 2048/C pixels per iteration, every thread keeps
 // its 8 channels' partial sums in registers; partials are combined through shared memory and one atomicAdd per
@@ -104,6 +132,7 @@ __device__ __forceinline__ void block_channel_atomic(float (&acc)[NACC][8], int 
     (void)tpp;
 }
 
+template <bool MISH>
 __global__ void __launch_bounds__(256) bn_stats_kernel(const __nv_bfloat16 *__restrict__ a, long long M, int C, float *sums) {
     const int tpp = C / 8, c0 = (threadIdx.x % tpp) * 8, ppb = 256 / tpp;
     float acc[2][8] = {};
@@ -114,6 +143,7 @@ __global__ void __launch_bounds__(256) bn_stats_kernel(const __nv_bfloat16 *__re
                       v.raw = raw;
                       float f[8];
                       v.unpack(f);
+                      act_on_load<MISH>(f);
 #pragma unroll
                       for (int j = 0; j < 8; ++j) {
                           acc[0][j] += f[j];
@@ -165,6 +195,7 @@ __global__ void bn_finalize_kernel(float *sums, long long M, int C, float eps, c
 }
 
 // y = a * scale + shift with the row-vectorised mapping (8 channels per thread, affine in registers)
+template <bool MISH>
 __global__ void __launch_bounds__(256)
 bn_apply_kernel(const __nv_bfloat16 *__restrict__ a, long long M, int C, const float *__restrict__ scale_shift,
                 __nv_bfloat16 *__restrict__ y) {
@@ -182,12 +213,14 @@ bn_apply_kernel(const __nv_bfloat16 *__restrict__ a, long long M, int C, const f
                   v.raw = raw;
                   float f[8];
                   v.unpack(f);
+                  act_on_load<MISH>(f);
 #pragma unroll
                   for (int j = 0; j < 8; ++j) f[j] = fmaf(f[j], k[j], b[j]);
                   *reinterpret_cast<uint4 *>(y + p * C + c0) = Bf16x8::pack(f);
               });
 }
 
+template <bool MISH>
 __global__ void __launch_bounds__(256)
 bn_bwd_reduce_kernel(const __nv_bfloat16 *__restrict__ dy, const __nv_bfloat16 *__restrict__ a, long long M, int C,
                      const float *__restrict__ mean, const float *__restrict__ invstd, float *dgamma_dbeta) {
@@ -205,6 +238,7 @@ bn_bwd_reduce_kernel(const __nv_bfloat16 *__restrict__ dy, const __nv_bfloat16 *
                         float g[8], x[8];
                         vg.unpack(g);
                         va.unpack(x);
+                        act_on_load<MISH>(x);
 #pragma unroll
                         for (int j = 0; j < 8; ++j) {
                             acc[0][j] = fmaf(g[j], (x[j] - mu[j]) * is[j], acc[0][j]);
@@ -243,8 +277,10 @@ bn_bwd_apply_kernel(const __nv_bfloat16 *__restrict__ dy, const __nv_bfloat16 *_
                         va.unpack(x);
 #pragma unroll
                         for (int j = 0; j < 8; ++j) {
-                            float v = k1[j] * (g[j] - k2[j] - (x[j] - mu[j]) * is[j] * k3[j]);
+                            const float xa = act == MBS_ACT_MISH ? mish_f(x[j]) : x[j];      // post-activation value
+                            float v = k1[j] * (g[j] - k2[j] - (xa - mu[j]) * is[j] * k3[j]);
                             if (act == MBS_ACT_RELU && !(x[j] > 0.0f)) v = 0.0f;
+                            if (act == MBS_ACT_MISH) v *= mish_grad_f(x[j]);
                             o[j] = v;
                         }
                         const uint4 packed = Bf16x8::pack(o);
@@ -442,19 +478,27 @@ inline int grid_for(long long work, int per_block, int cap) {
 
 extern "C" int mbs_bn_train_fwd(const void *a, long long M, int C, const float *gamma, const float *beta, float eps, void *y,
                                 float *sums_scratch, float *mean, float *invstd, float momentum, float *running_mean,
-                                float *running_var, long long *num_batches_tracked, void *stream_) {
+                                float *running_var, long long *num_batches_tracked, int act, void *stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     MBS_REQUIRE(M > 0 && C >= 8 && C % 8 == 0 && C <= 2048 && 256 % (C / 8) == 0, "bn_train_fwd: bad shape (C must be 8*2^k <= 2048)");
     const int grid = grid_rows(M, C);
     float *part = sums_scratch + 2 * C;          // [grid][2][C] per-block partial sums
-    bn_stats_kernel<<<grid, 256, 0, stream>>>(static_cast<const __nv_bfloat16 *>(a), M, C, part);
+    MBS_REQUIRE(act == MBS_ACT_NONE || act == MBS_ACT_MISH, "bn_train_fwd: act must be NONE (tensor is post-activation) or MISH (pre-activation)");
+    if (act == MBS_ACT_MISH)
+        bn_stats_kernel<true><<<grid, 256, 0, stream>>>(static_cast<const __nv_bfloat16 *>(a), M, C, part);
+    else
+        bn_stats_kernel<false><<<grid, 256, 0, stream>>>(static_cast<const __nv_bfloat16 *>(a), M, C, part);
     MBS_CHECK_LAUNCH();
     reduce_partials_kernel<<<mbs::cdiv(2 * C, 128), 128, 0, stream>>>(part, grid, 2 * C, sums_scratch);
     MBS_CHECK_LAUNCH();
     bn_finalize_kernel<<<mbs::cdiv(C, 128), 128, 0, stream>>>(sums_scratch, M, C, eps, gamma, beta, mean, invstd, momentum,
                                                               running_mean, running_var, num_batches_tracked);
     MBS_CHECK_LAUNCH();
-    bn_apply_kernel<<<grid, 256, 0, stream>>>(static_cast<const __nv_bfloat16 *>(a), M, C, sums_scratch,
+    if (act == MBS_ACT_MISH)
+        bn_apply_kernel<true><<<grid, 256, 0, stream>>>(static_cast<const __nv_bfloat16 *>(a), M, C, sums_scratch,
+                                                        static_cast<__nv_bfloat16 *>(y));
+    else
+        bn_apply_kernel<false><<<grid, 256, 0, stream>>>(static_cast<const __nv_bfloat16 *>(a), M, C, sums_scratch,
                                                          static_cast<__nv_bfloat16 *>(y));
     MBS_CHECK_LAUNCH();
     return 0;
@@ -467,11 +511,16 @@ extern "C" int mbs_bn_train_bwd(const void *dy, const void *a, long long M, int 
                                 void *stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     MBS_REQUIRE(M > 0 && C >= 8 && C % 8 == 0 && C <= 2048 && 256 % (C / 8) == 0, "bn_train_bwd: bad shape");
-    MBS_REQUIRE(act == MBS_ACT_NONE || act == MBS_ACT_RELU, "bn_train_bwd: only relu / none are supported in training");
+    MBS_REQUIRE(act == MBS_ACT_NONE || act == MBS_ACT_RELU || act == MBS_ACT_MISH,
+                "bn_train_bwd: training supports relu (tensor = post-activation), mish (tensor = pre-activation) or none");
     const int grid = grid_rows(M, C);
     float *part = scratch + 2 * C;               // [grid][2][C], then reused as [grid][C]
-    bn_bwd_reduce_kernel<<<grid, 256, 0, stream>>>(static_cast<const __nv_bfloat16 *>(dy), static_cast<const __nv_bfloat16 *>(a), M,
-                                                   C, mean, invstd, part);
+    if (act == MBS_ACT_MISH)
+        bn_bwd_reduce_kernel<true><<<grid, 256, 0, stream>>>(static_cast<const __nv_bfloat16 *>(dy),
+                                                             static_cast<const __nv_bfloat16 *>(a), M, C, mean, invstd, part);
+    else
+        bn_bwd_reduce_kernel<false><<<grid, 256, 0, stream>>>(static_cast<const __nv_bfloat16 *>(dy),
+                                                              static_cast<const __nv_bfloat16 *>(a), M, C, mean, invstd, part);
     MBS_CHECK_LAUNCH();
     reduce_partials_kernel<<<mbs::cdiv(2 * C, 128), 128, 0, stream>>>(part, grid, 2 * C, dgamma_dbeta);
     MBS_CHECK_LAUNCH();

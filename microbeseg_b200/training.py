@@ -18,7 +18,7 @@ from . import _native as nat
 
 BN_EPS = 1e-5
 BN_MOMENTUM = 0.1
-ACT_NONE, ACT_RELU = 0, 1
+ACT_NONE, ACT_RELU, ACT_MISH = 0, 1, 4
 
 
 class _Layer:
@@ -33,8 +33,14 @@ class TrainEngine:
         if not isinstance(net, DUNet):
             raise NotImplementedError("training is built for the DU (distance) network")
         net._check_supported()
-        if net.act_fun != "relu":
-            raise NotImplementedError("training on the CUDA path supports act_fun='relu' (Adam recipe, train.py:174)")
+        if net.act_fun not in ("relu", "mish"):
+            raise NotImplementedError("training on the CUDA path supports act_fun='relu' (Adam recipe) and 'mish' "
+                                      "(Ranger recipe), the two the reference trains with (train.py:174)")
+        # relu: the conv epilogue applies it and the stored tensor is post-activation (its sign is the derivative mask);
+        # mish: the conv writes the PRE-activation z, the BatchNorm passes apply mish on load and the backward pass
+        # evaluates mish'(z) -- still one activation-sized tensor per layer
+        self.act = ACT_RELU if net.act_fun == "relu" else ACT_MISH
+        self.conv_act = ACT_RELU if net.act_fun == "relu" else ACT_NONE
         self.net = net
         self.L = nat.lib()
         self.dev = next(net.parameters()).device
@@ -96,7 +102,8 @@ class TrainEngine:
         nat.check(self.L.mbs_bn_train_fwd(a.data_ptr(), m, c, bn.weight.data_ptr(), bn.bias.data_ptr(), BN_EPS,
                                           lay.y.data_ptr(), self._scratch.data_ptr(), lay.mean.data_ptr(),
                                           lay.invstd.data_ptr(), BN_MOMENTUM, bn.running_mean.data_ptr(),
-                                          bn.running_var.data_ptr(), bn.num_batches_tracked.data_ptr(), self._sp()),
+                                          bn.running_var.data_ptr(), bn.num_batches_tracked.data_ptr(),
+                                          ACT_MISH if lay.act == ACT_MISH else ACT_NONE, self._sp()),
                   "bn_train_fwd")
 
     def _wgrad(self, kind, n, ho, wo, a, cm, b, cn, out, out_ld, out_coff):
@@ -112,20 +119,20 @@ class TrainEngine:
     # ---- forward ------------------------------------------------------------------------------
     def _fwd_conv(self, name, conv, bn, srcs, stride=1):
         lay = _Layer()
-        lay.name, lay.kind, lay.conv, lay.bn, lay.act, lay.srcs = name, ("s2" if stride == 2 else "s1"), conv, bn, ACT_RELU, srcs
+        lay.name, lay.kind, lay.conv, lay.bn, lay.act, lay.srcs = name, ("s2" if stride == 2 else "s1"), conv, bn, self.act, srcs
         n, h, w = srcs[0].shape[:3]
         cout = conv.weight.shape[0]
         ho, wo = (h // 2, w // 2) if stride == 2 else (h, w)
         lay.a = torch.empty((n, ho, wo, cout), dtype=torch.bfloat16, device=self.dev)
         self._conv(1 if stride == 2 else 0, n, h, w, srcs, self._pack3x3(conv.weight.detach().float().contiguous()), cout,
-                   conv.bias.detach().float(), ACT_RELU, lay.a)
+                   conv.bias.detach().float(), self.conv_act, lay.a)
         self._bn_fwd(lay)
         self.tape.append(lay)
         return lay
 
     def _fwd_first(self, conv, bn, x):
         lay = _Layer()
-        lay.name, lay.kind, lay.conv, lay.bn, lay.act, lay.srcs, lay.x_f32 = "enc0a", "first", conv, bn, ACT_RELU, [], x
+        lay.name, lay.kind, lay.conv, lay.bn, lay.act, lay.srcs, lay.x_f32 = "enc0a", "first", conv, bn, self.act, [], x
         n, h, w = x.shape
         c = conv.weight.shape[0]
         lay.a = torch.empty((n, h, w, c), dtype=torch.bfloat16, device=self.dev)
@@ -133,7 +140,7 @@ class TrainEngine:
         b = conv.bias.detach().float().contiguous()
         for i in range(n):
             nat.check(self.L.mbs_first_conv(x[i].data_ptr(), 2, h, w, 0, 0, 1.0, 0.0, None, wt.data_ptr(), b.data_ptr(),
-                                            self._ones(c).data_ptr(), self._zeros(c).data_ptr(), c, ACT_RELU,
+                                            self._ones(c).data_ptr(), self._zeros(c).data_ptr(), c, self.conv_act,
                                             lay.a[i].data_ptr(), c, 0, self._sp()), "first_conv(train)")
         self._bn_fwd(lay)
         self.tape.append(lay)

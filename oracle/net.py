@@ -171,21 +171,21 @@ def _bn_train(x, sd, prefix):
     return F.batch_norm(x, None, None, sd[prefix + ".weight"], sd[prefix + ".bias"], training=True, eps=1e-5)
 
 
-def _conv_block_train(x, sd, prefix):
-    x = _bn_train(F.relu(F.conv2d(x, sd[prefix + ".conv.0.weight"], sd[prefix + ".conv.0.bias"], padding=1)), sd, prefix + ".conv.2")
-    return _bn_train(F.relu(F.conv2d(x, sd[prefix + ".conv.3.weight"], sd[prefix + ".conv.3.bias"], padding=1)), sd, prefix + ".conv.5")
+def _conv_block_train(x, sd, prefix, act="relu"):
+    x = _bn_train(_act(F.conv2d(x, sd[prefix + ".conv.0.weight"], sd[prefix + ".conv.0.bias"], padding=1), act), sd, prefix + ".conv.2")
+    return _bn_train(_act(F.conv2d(x, sd[prefix + ".conv.3.weight"], sd[prefix + ".conv.3.bias"], padding=1), act), sd, prefix + ".conv.5")
 
 
-def dunet_train_loss(params, x, border_label, cell_label):
-    """params: dict name -> tensor (requires_grad where wanted), relu activations.  Returns the scalar loss."""
+def dunet_train_loss(params, x, border_label, cell_label, act="relu"):
+    """params: dict name -> tensor (requires_grad where wanted).  Returns the scalar loss."""
     nl = n_levels(params)
     skips = []
     for i in range(nl - 1):
-        x = _conv_block_train(x, params, f"encoderConv.{i}")
+        x = _conv_block_train(x, params, f"encoderConv.{i}", act)
         skips.append(x)
         x = F.conv2d(x, params[f"pooling.{i}.conv_pool.0.weight"], params[f"pooling.{i}.conv_pool.0.bias"], stride=2, padding=1)
-        x = _bn_train(F.relu(x), params, f"pooling.{i}.conv_pool.2")
-    b = _conv_block_train(x, params, f"encoderConv.{nl - 1}")
+        x = _bn_train(_act(x, act), params, f"pooling.{i}.conv_pool.2")
+    b = _conv_block_train(x, params, f"encoderConv.{nl - 1}", act)
     skips = skips[::-1]
     outs = []
     for name in ("decoder1", "decoder2"):
@@ -193,7 +193,7 @@ def dunet_train_loss(params, x, border_label, cell_label):
         for i, s in enumerate(skips):
             y = F.conv_transpose2d(y, params[f"{name}Upconv.{i}.up.0.weight"], params[f"{name}Upconv.{i}.up.0.bias"], stride=2)
             y = _bn_train(y, params, f"{name}Upconv.{i}.norm")
-            y = _conv_block_train(torch.cat([y, s], 1), params, f"{name}Conv.{i}")
+            y = _conv_block_train(torch.cat([y, s], 1), params, f"{name}Conv.{i}", act)
         k = len(skips)
         outs.append(F.conv2d(y, params[f"{name}Conv.{k}.weight"], params[f"{name}Conv.{k}.bias"]))
     crit = torch.nn.SmoothL1Loss()

@@ -18,10 +18,10 @@ from oracle import net as onet
 pytestmark = pytest.mark.gpu
 
 
-def _setup(filters, seed, n, h, w, graph=False):
+def _setup(filters, seed, n, h, w, graph=False, act="relu"):
     from microbeseg_b200.unets import build_unet
     from microbeseg_b200.training import TrainEngine
-    net = build_unet("DU", "relu", "conv", "bn", torch.device("cuda:0"), 1, filters=list(filters))
+    net = build_unet("DU", act, "conv", "bn", torch.device("cuda:0"), 1, filters=list(filters))
     sd = onet.seeded_state_dict(onet.reference_layout_template("DU", filters), seed)
     net.load_state_dict(sd)
     net.train()
@@ -32,25 +32,28 @@ def _setup(filters, seed, n, h, w, graph=False):
     return net, sd, TrainEngine(net, use_graph=graph), img, bl, cl
 
 
-def _reference(sd, img, bl, cl, autocast=False):
+def _reference(sd, img, bl, cl, autocast=False, act="relu"):
     params = {k: v.clone().cuda().requires_grad_(v.dtype.is_floating_point and "running" not in k) for k, v in sd.items()
               if v.dtype.is_floating_point}
     with torch.enable_grad():      # the inference tests (like the reference, infer.py:343) switch grad off globally
         with torch.autocast("cuda", dtype=torch.bfloat16, enabled=autocast):
-            loss = onet.dunet_train_loss(params, img, bl, cl)
+            loss = onet.dunet_train_loss(params, img, bl, cl, act)
         loss.backward()
     return float(loss.detach()), {k: p.grad for k, p in params.items() if p.grad is not None}
 
 
-@pytest.mark.parametrize("filters,n,h,w", [((64, 128), 2, 32, 48), ((64, 256), 3, 64, 64), ((64, 1024), 2, 128, 96)])
-def test_loss_and_gradients_vs_torch_autograd(native_lib, filters, n, h, w):
-    net, sd, eng, img, bl, cl = _setup(filters, 7, n, h, w)
+@pytest.mark.parametrize("filters,n,h,w,act", [((64, 128), 2, 32, 48, "relu"), ((64, 256), 3, 64, 64, "relu"),
+                                               ((64, 1024), 2, 128, 96, "relu"), ((64, 256), 2, 64, 48, "mish"),
+                                               ((64, 1024), 2, 96, 128, "mish")])
+def test_loss_and_gradients_vs_torch_autograd(native_lib, filters, n, h, w, act):
+    """relu = the Adam recipe, mish = the Ranger recipe (train.py:174)"""
+    net, sd, eng, img, bl, cl = _setup(filters, 7, n, h, w, act=act)
     loss = float(eng.forward_backward(img, bl, cl))
-    ref_loss, ref_grads = _reference(sd, img, bl, cl)
+    ref_loss, ref_grads = _reference(sd, img, bl, cl, act=act)
     assert native_lib.mbs_debug_flags(1) == 0
     assert abs(loss - ref_loss) <= 2e-2 * abs(ref_loss), (loss, ref_loss)
     # yardstick: the same graph under torch's own bf16 autocast (the standard mixed-precision policy)
-    _, amp_grads = _reference(sd, img, bl, cl, autocast=True)
+    _, amp_grads = _reference(sd, img, bl, cl, autocast=True, act=act)
     rows = []
     for name, p in net.named_parameters():
         assert p.grad is not None, name
@@ -154,3 +157,17 @@ def test_conv_wgrad_vs_torch(native_lib, kind, N, Ho, Wo, Cm, Cn):
     # exact bf16 products, fp32 accumulation in a different order: tolerance = a few fp32 ulps of the sum of magnitudes
     assert err <= 2e-5 * (N * Ho * Wo) ** 0.5 * 4 + 1e-4 * ref.abs().max().item(), err
     assert L.mbs_debug_flags(1) == 0
+
+
+def test_ranger_mish_recipe_reduces_the_loss(native_lib):
+    """the reference's default recipe (train_script.py --optimizer ranger => mish, train.py:174,399-404): fused Ranger
+    step + CUDA training step, a few iterations on one batch must reduce the loss"""
+    from microbeseg_b200.ranger import Ranger
+    from microbeseg_b200.training import train_step
+    net, sd, eng, img, bl, cl = _setup((64, 128), 3, 2, 64, 64, graph=True, act="mish")
+    opt = Ranger(net.parameters(), lr=6e-3, alpha=0.5, k=6, N_sma_threshhold=5, betas=(.95, 0.999), eps=1e-6, weight_decay=0,
+                 use_gc=True, gc_conv_only=False, gc_loc=True)
+    losses = [float(train_step(eng, opt, img, bl, cl)) for _ in range(14)]
+    assert all(np.isfinite(losses)) and losses[-1] < 0.7 * losses[0], losses
+    assert opt.launches_last_step == 1
+    assert native_lib.mbs_debug_flags(1) == 0

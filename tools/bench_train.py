@@ -14,6 +14,8 @@ ap.add_argument("--warmup", type=int, default=3)
 ap.add_argument("--per-gpu-batch", type=int, default=8)
 ap.add_argument("--size", type=int, default=320)
 ap.add_argument("--no-torch-baseline", action="store_true")
+ap.add_argument("--optimizer", default="adam", choices=["adam", "ranger"],
+                help="adam: relu + torch Adam(amsgrad); ranger: mish + the fused Ranger step (train.py:174,380-404)")
 args = ap.parse_args()
 rank, local, world = int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
 torch.cuda.set_device(local)
@@ -28,12 +30,18 @@ from microbeseg_b200.training import TrainEngine, train_step
 from oracle import net as onet
 
 torch.manual_seed(0)
-net = build_unet("DU", "relu", "conv", "bn", dev, 1, filters=[64, 1024]).train()
+ACT = "relu" if args.optimizer == "adam" else "mish"
+net = build_unet("DU", ACT, "conv", "bn", dev, 1, filters=[64, 1024]).train()
 if world > 1:                       # replicas start identical (rank 0's init), like DataParallel's replicate
     for t in list(net.parameters()) + list(net.buffers()):
         dist.broadcast(t.data, 0)
 eng = TrainEngine(net)
-opt = torch.optim.Adam(net.parameters(), lr=8e-4, betas=(0.9, 0.999), eps=1e-08, weight_decay=0, amsgrad=True)
+if args.optimizer == "adam":
+    opt = torch.optim.Adam(net.parameters(), lr=8e-4, betas=(0.9, 0.999), eps=1e-08, weight_decay=0, amsgrad=True)
+else:
+    from microbeseg_b200.ranger import Ranger
+    opt = Ranger(net.parameters(), lr=6e-3, alpha=0.5, k=6, N_sma_threshhold=5, betas=(.95, 0.999), eps=1e-6, weight_decay=0,
+                 use_gc=True, gc_conv_only=False, gc_loc=True)
 B, S = args.per_gpu_batch, args.size
 # synthetic crops: rendered frames + labels from the label-generation path (config 4 -> config 5)
 masks = np.stack([sy.synth_instance_mask(S, S, 40 + 5 * i, 320 + 100 * rank + i, (9.0, 16.0), (7.0, 12.0)).astype(np.uint16) for i in range(B)])
@@ -70,16 +78,57 @@ if world > 1:
     ms = float(t.item())
 losses.append(float(loss))
 
+class _PerTensorRanger:
+    """baseline only: the reference's per-tensor loop (ranger2020.py:101-210) in the same ATen calls"""
+    def __init__(self, params, lr=6e-3, alpha=0.5, k=6, thr=5, betas=(.95, 0.999), eps=1e-6):
+        self.params, self.lr, self.alpha, self.k, self.thr, self.betas, self.eps = list(params), lr, alpha, k, thr, betas, eps
+        self.state, self.t = {}, 0
+    def zero_grad(self, set_to_none=True):
+        for p in self.params:
+            p.grad = None
+    def step(self):
+        import math
+        self.t += 1
+        b1, b2 = self.betas
+        b2t = b2 ** self.t
+        nmax = 2 / (1 - b2) - 1
+        nsma = nmax - 2 * self.t * b2t / (1 - b2t)
+        if nsma > self.thr:
+            ss = math.sqrt((1 - b2t) * (nsma - 4) / (nmax - 4) * (nsma - 2) / nsma * nmax / (nmax - 2)) / (1 - b1 ** self.t)
+        else:
+            ss = 1.0 / (1 - b1 ** self.t)
+        with torch.no_grad():
+            for p in self.params:
+                if p.grad is None:
+                    continue
+                g = p.grad
+                st = self.state.setdefault(p, None)
+                if st is None:
+                    st = self.state[p] = dict(m=torch.zeros_like(p), v=torch.zeros_like(p), slow=p.detach().clone())
+                if g.dim() > 1:
+                    g.add_(-g.mean(dim=tuple(range(1, g.dim())), keepdim=True))
+                st["v"].mul_(b2).addcmul_(g, g, value=1 - b2)
+                st["m"].mul_(b1).add_(g, alpha=1 - b1)
+                G = st["m"] / st["v"].sqrt().add_(self.eps) if nsma > self.thr else st["m"]
+                p.add_(G, alpha=-ss * self.lr)
+                if self.t % self.k == 0:
+                    st["slow"].add_(p - st["slow"], alpha=self.alpha)
+                    p.copy_(st["slow"])
+
+
 base = {}
 if rank == 0 and not args.no_torch_baseline:
     sd = {k: v.detach().clone() for k, v in net.state_dict().items()}
     for tag, amp in (("torch_cudnn_fp32", False), ("torch_cudnn_bf16_autocast", True)):
         params = {k: v.clone().float().requires_grad_("running" not in k) for k, v in sd.items() if v.dtype.is_floating_point}
-        o2 = torch.optim.Adam([p for p in params.values() if p.requires_grad], lr=8e-4, amsgrad=True)
+        if args.optimizer == "adam":
+            o2 = torch.optim.Adam([p for p in params.values() if p.requires_grad], lr=8e-4, amsgrad=True)
+        else:
+            o2 = _PerTensorRanger([p for p in params.values() if p.requires_grad])
         def step():
             o2.zero_grad(set_to_none=True)
             with torch.autocast("cuda", dtype=torch.bfloat16, enabled=amp):
-                l = onet.dunet_train_loss(params, img, bl, cl)
+                l = onet.dunet_train_loss(params, img, bl, cl, ACT)
             l.backward()
             o2.step()
         for _ in range(3):
@@ -96,7 +145,7 @@ if rank == 0:
     ach = FLOP_PER_PX_TRAIN * px / world / (ms / 1e3) / 1e12
     print(json.dumps({"metric": "training img/s", "value": world * B / (ms / 1e3), "unit": "img/s", "n_gpus": world,
                       "ms_per_step": ms, "steps": args.steps, "warmup": args.warmup, "dtype": "bf16 (fp32 master weights)",
-                      "config": {"workload": f"config 5: DUNet[64,1024] training step (fwd, SmoothL1 x2, bwd, Adam amsgrad), {S}x{S} crops, "
+                      "config": {"workload": f"config 5: DUNet[64,1024] training step (fwd, SmoothL1 x2, bwd, {'Adam amsgrad, relu' if args.optimizer == 'adam' else 'fused Ranger, mish'}), {S}x{S} crops, "
                                              f"{B} per GPU, global batch {world * B}", "parallelism": f"dp{world}, one flat NCCL all-reduce per step"},
                       "loss_first_last": [losses[0], losses[-1]], "gpu_launches": launches,
                       "roofline": {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
