@@ -200,6 +200,9 @@ int mbs_ranger_step(const mbs_ranger_tensor *tensors_dev, int n_tensors, int tot
 /* max_mal of src/training/train.py:74-79); batched over crops                                 */
 /* ---------------------------------------------------------------------------------------- */
 size_t mbs_labels_workspace_bytes(int n_crops, int H, int W, int max_id);
+/* label types 'boundary' (mode 0, train_data_representations.py:75-99) and 'border' (mode 1, :102-126) of the
+ * baseline boundary method: uint8 [n_crops][H][W], 0 background / 1 nucleus / 2 boundary resp. touching border */
+int mbs_boundary_border_labels(const uint16_t *masks, int n_crops, int H, int W, int mode, uint8_t *out, void *stream);
 /* masks: uint16 [n_crops][H][W] instance ids (0 = background, ids <= max_id).
  * max_mal_out: int32 [n_crops] = int(ceil(max regionprops.major_axis_length)) per crop. */
 int mbs_labels_max_mal(const uint16_t *masks, int n_crops, int H, int W, int max_id, int32_t *max_mal_out,

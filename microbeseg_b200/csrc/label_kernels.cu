@@ -497,6 +497,49 @@ constexpr int kMaxGaps = 4096;
 
 }  // namespace
 
+namespace {
+// boundary_label / border_label (train_data_representations.py:75-99 / :102-126) as ONE stencil pass instead of a
+// full-image binary_dilation per nucleus: `boundary` = pixels with an 8-neighbour inside a nucleus they do not belong to
+// (dilation(nucleus) ^ nucleus, OR-ed over the ids; binary_dilation's border_value = 0: outside the image is empty);
+// border = boundary ^ (dilation(label > 0) ^ (label > 0)) = nucleus pixels touching a DIFFERENT nucleus.
+// out = max(label > 0, 2 * boundary | border) as uint8.
+__global__ void simple_label_kernel(const uint16_t *__restrict__ masks, int H, int W, int mode, uint8_t *__restrict__ out) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= W || y >= H) return;
+    const size_t base = static_cast<size_t>(blockIdx.z) * H * W;
+    const uint16_t me = masks[base + static_cast<size_t>(y) * W + x];
+    bool other = false;                 // an 8-neighbour belongs to a nucleus that is not mine
+    for (int dy = -1; dy <= 1; ++dy) {
+        const int yy = y + dy;
+        if (yy < 0 || yy >= H) continue;
+        for (int dx = -1; dx <= 1; ++dx) {
+            const int xx = x + dx;
+            if (xx < 0 || xx >= W) continue;
+            const uint16_t q = masks[base + static_cast<size_t>(yy) * W + xx];
+            other |= (q != 0 && q != me);
+        }
+    }
+    uint8_t v = me ? 1 : 0;
+    if (mode == 0) {                    // boundary: background pixels next to a nucleus count too
+        if (other) v = 2;
+    } else {                            // border: only nucleus pixels (the outer ring dilation(bin) ^ bin cancels)
+        if (other && me) v = 2;
+    }
+    out[base + static_cast<size_t>(y) * W + x] = v;
+}
+}  // namespace
+
+extern "C" int mbs_boundary_border_labels(const uint16_t *masks, int n_crops, int H, int W, int mode, uint8_t *out,
+                                          void *stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    MBS_REQUIRE(masks && out && n_crops > 0 && n_crops <= 65535 && H > 0 && W > 0 && (mode == 0 || mode == 1),
+                "boundary_border_labels: bad arguments");
+    dim3 block(32, 8), grid((W + 31) / 32, (H + 7) / 8, n_crops);
+    simple_label_kernel<<<grid, block, 0, stream>>>(masks, H, W, mode, out);
+    MBS_CHECK_LAUNCH();
+    return 0;
+}
+
 extern "C" size_t mbs_labels_workspace_bytes(int n_crops, int H, int W, int max_id) {
     const size_t px = static_cast<size_t>(n_crops) * H * W;
     const size_t ids = static_cast<size_t>(max_id) + 1;

@@ -71,12 +71,43 @@ def distance_label(label, search_radius):
     return cell[0].cpu().numpy(), neigh[0].cpu().numpy()
 
 
+def _simple_label(label, mode):
+    L = nat.lib()
+    dev, _ = _masks_to_device(label, _device())
+    n, H, W = dev.shape
+    out = torch.empty((n, H, W), dtype=torch.uint8, device=dev.device)
+    with torch.cuda.device(dev.device):
+        nat.check(L.mbs_boundary_border_labels(dev.data_ptr(), n, H, W, mode, out.data_ptr(), nat.stream_ptr()),
+                  "boundary_border_labels")
+    res = out.cpu().numpy()
+    return res[0] if np.asarray(label).ndim == 2 else res
+
+
+def boundary_label(label):
+    """Boundary label image (train_data_representations.py:75-99): uint8, 1 nucleus, 2 boundary."""
+    return _simple_label(label, 0)
+
+
+def border_label(label):
+    """Border label image (train_data_representations.py:102-126): uint8, 1 nucleus, 2 border between touching nuclei."""
+    return _simple_label(label, 1)
+
+
 def get_label(mask, label_type, max_mal):
     """Calculate training data representation / label (train_data_representations.py:11-37)."""
     if label_type == 'distance':
         return distance_label(mask, search_radius=int(np.ceil(0.75 * max_mal)))
-    if label_type in ('boundary', 'border', 'adapted_border', 'j4', 'cell_dist', 'cell_dist_clipped'):
-        raise NotImplementedError(f"label type {label_type!r} is not built on the CUDA path (only 'distance')")
+    if label_type == 'boundary':
+        return boundary_label(mask)
+    if label_type == 'border':
+        return border_label(mask)
+    if label_type == 'cell_dist':
+        # cell_distance_label(apply_clipping=False) (:220-258) is the cell half of distance_label: same windows, same
+        # normalised EDTs, same `+=` (cells whose EDT is all zero add zeros there and are skipped here)
+        return distance_label(mask, search_radius=int(np.ceil(0.75 * max_mal)))[0]
+    if label_type in ('adapted_border', 'j4', 'cell_dist_clipped'):
+        raise NotImplementedError(f"label type {label_type!r} is not built on the CUDA path "
+                                  "('distance', 'cell_dist', 'boundary', 'border' are)")
     raise Exception('Label type not known')
 
 

@@ -94,6 +94,30 @@ def max_major_axis_length(mask):
     return int(np.ceil(np.max(np.array([p.major_axis_length for p in props]))))
 
 
+def boundary_label(label):
+    """train_data_representations.py:75-99"""
+    label_bin = label > 0
+    kernel = np.ones((3, 3), np.uint8)
+    boundary = np.zeros(label.shape, bool)
+    for nucleus_id in get_nucleus_ids(label):
+        nucleus = label == nucleus_id
+        boundary |= ndimage.binary_dilation(nucleus, kernel) ^ nucleus
+    return np.maximum(label_bin, 2 * boundary).astype(np.uint8)
+
+
+def cell_distance_label(label, search_radius):
+    """train_data_representations.py:220-258 with apply_clipping=False"""
+    label_dist = np.zeros(label.shape, np.float64)
+    for prop in regionprops(label):
+        nucleus = label == prop.label
+        ys, xs = _window(prop.centroid, search_radius, label.shape)
+        d = distance_transform_edt(nucleus[ys, xs])
+        if d.max() > 0:
+            d = d / d.max()
+        label_dist[ys, xs] += d
+    return label_dist.astype(np.float32)
+
+
 def border_label(label):
     """train_data_representations.py:102-126"""
     label_bin = label > 0
@@ -185,7 +209,13 @@ def distance_label(label, search_radius, return_intermediates=False):
 
 
 def get_label(mask, label_type, max_mal):
-    """train_data_representations.py:11-37 (distance method only)"""
+    """train_data_representations.py:11-37 (the label types the CUDA path builds)"""
+    if label_type == 'boundary':
+        return boundary_label(mask)
+    if label_type == 'border':
+        return border_label(mask)
+    if label_type == 'cell_dist':
+        return cell_distance_label(mask, search_radius=int(np.ceil(0.75 * max_mal)))
     if label_type != 'distance':
         raise Exception('Label type not known')
     return distance_label(mask, search_radius=int(np.ceil(0.75 * max_mal)))

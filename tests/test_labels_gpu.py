@@ -87,3 +87,24 @@ def test_golden_fixtures(lab):
         cells, neighs, mals = lab.create_labels(g["mask"])
         assert int(mals[0]) == int(g["max_mal"])
         _check((cells[0], neighs[0]), (g["cell_dist"], g["neighbor_dist"]), f)
+
+
+def test_boundary_border_and_cell_dist_label_types():
+    """the other label types of get_label (train_data_representations.py:11-37) that are built: bit-exact vs the oracle"""
+    from microbeseg_b200 import labels as lab, synthetic as sy
+    from oracle import labels as ol
+    for seed, (H, W, n) in enumerate([(96, 128, 30), (64, 64, 12), (80, 50, 0)]):
+        m = sy.synth_instance_mask(H, W, n, 50 + seed, (7.0, 12.0), (5.0, 9.0)).astype(np.uint16)
+        if n:
+            m[0:5, 0:6] = 900            # touches the image corner
+            m[0:5, 6:11] = 901           # and a neighbour
+        for lt in ("boundary", "border"):
+            got, want = lab.get_label(m, lt, 0), ol.get_label(m, lt, 0)
+            assert got.dtype == np.uint8 and got.shape == m.shape and np.array_equal(got, want), lt
+        mal = ol.max_major_axis_length(m) if n else 1
+        got, want = lab.get_label(m, "cell_dist", mal), ol.get_label(m, "cell_dist", mal)
+        assert got.dtype == np.float32 and np.array_equal(got, want)
+    with pytest.raises(NotImplementedError):
+        lab.get_label(m, "j4", 10)
+    with pytest.raises(Exception):
+        lab.get_label(m, "nonsense", 10)

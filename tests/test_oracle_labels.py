@@ -45,3 +45,18 @@ def test_border_label_and_window_semantics():
     # scipy's EDT of an all-foreground array measures the distance to (-1, 0): relied upon by the GPU path
     e = ndimage.distance_transform_edt(np.ones((3, 4), bool))
     assert np.allclose(e[0], np.sqrt(1 + np.arange(4) ** 2)) and np.isclose(e[2, 0], 3.0)
+
+
+def test_boundary_and_border_label_semantics():
+    from oracle import labels as ol
+    m = np.zeros((8, 10), np.uint16)
+    m[2:5, 1:4] = 3
+    m[2:5, 4:7] = 5               # touches nucleus 3
+    m[6:8, 8:10] = 9              # isolated, at the image corner
+    b = ol.boundary_label(m)
+    assert b[1, 1] == 2 and b[3, 3] == 2 and b[3, 4] == 2 and b[3, 2] == 1 and b[0, 9] == 0 and b[5, 8] == 2
+    r = ol.border_label(m)
+    assert r[1, 1] == 0 and r[3, 3] == 2 and r[3, 4] == 2 and r[3, 2] == 1 and r[7, 9] == 1 and r[5, 8] == 0
+    assert (r == 2).sum() == 6
+    cd = ol.cell_distance_label(m, 6)
+    assert cd.dtype == np.float32 and cd.max() == 1.0 and np.array_equal(cd, ol.distance_label(m, 6)[0])
