@@ -252,6 +252,31 @@ def test_tiled_inference_is_bit_identical_to_whole_frame(native_lib):
     assert tiled.shape == odd.shape and np.array_equal(whole, tiled)
 
 
+def test_full_size_frame_is_consistent_across_kernel_paths(native_lib):
+    """BASELINE config-2 frame size (2048^2): size-independent properties.  (1) 1024-px tiles with a 128-px apron -- which
+    run through differently shaped launches (other tile counts, ragged edges) -- reproduce the whole-frame maps bit for
+    bit; (2) so does the mask; (3) the fused raw-frame path equals the drop-in net(x) path on the normalised frame."""
+    from microbeseg_b200 import synthetic as sy
+    from microbeseg_b200.inference import predict_maps_tiled, FrameSegmenter
+    torch.set_grad_enabled(False)
+    net, _ = _build((64, 1024), "relu", 72)
+    img = sy.synth_frame(2048, 2048, 2001)
+    dev = torch.from_numpy(img.view(np.int16)).cuda()
+    lo, hi = float(img.min()), float(img.max())
+    b0, c0 = net.forward_frame(dev, [0, 0], lo, hi)
+    b1, c1 = predict_maps_tiled(net, dev, lo, hi, tile=1024)
+    assert torch.equal(b0[0, 0], b1) and torch.equal(c0[0, 0], c1)
+    assert torch.isfinite(b0).all() and torch.isfinite(c0).all()
+    x = torch.from_numpy((2 * (img.astype(np.float32) - np.float32(lo)) / (np.float32(hi) - np.float32(lo)) - 1)[None, None]).cuda()
+    b2, c2 = net(x)
+    assert torch.equal(b0, b2) and torch.equal(c0, c2)
+    seg = FrameSegmenter(net, (0.10, 0.45))
+    m0 = seg.segment(img)
+    assert m0.shape == (2048, 2048) and m0.dtype == np.uint16
+    assert np.array_equal(m0, seg.segment(img))               # deterministic
+    assert native_lib.mbs_debug_flags(1) == 0
+
+
 def test_single_decoder_unet_with_three_channel_head(native_lib):
     """'U' architecture with ch_out=3 (boundary method, unets.py:267-377): fused 3-output 1x1 head."""
     from microbeseg_b200.unets import build_unet
