@@ -1070,6 +1070,148 @@ wgrad_nhwc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 }
 
 // ------------------------------------------------------------------------------------------
+// Weight gradient of the full-resolution layers (conv3x3 stride 1, Cout = 64): halo variant.
+//
+// With one (tap pair, 64-pixel chunk) per MMA group the generic kernel moves 24 KiB of operands per 4 MMAs and is
+// L2 -> smem bound (250-440 TFLOP/s).  Here one CTA owns ALL nine taps of a 64-input-channel slice: per 8x8 pixel
+// patch it loads the x patch once (8 KiB) and the dz patch with a 1-pixel halo once (10x10 pixels, 12.5 KiB), and the
+// five tap pairs are five accumulators (5 x 64 TMEM columns).  sum_o dz[o] x[o+t] = sum_p dz[p-t] x[p]: the A operand
+// of tap t is the halo patch read from pixel offset off(t) = (2-ky)*10 + (2-kx); its 8-pixel K groups are 10 pixels
+// (1280 B) apart = the descriptor's stride byte offset, and the second tap of a pair is the "second 64-row block" of
+// the MN-major A tile at leading byte offset (off(t2) - off(t1)) * 128 B.  (The 128B swizzle is a function of the
+// absolute smem address, so shifted starts read what TMA wrote -- same property the forward halo kernel relies on.)
+// ------------------------------------------------------------------------------------------
+constexpr int WH_A_SLOT = 13 * 1024;          // 10 x 10 pixels x 128 B = 12800 B, slot rounded to the 1 KiB swizzle period
+constexpr int WH_B_SLOT = 8 * 1024;
+constexpr int WH_STAGES = 6;
+constexpr int WH_DYN = WH_STAGES * (WH_A_SLOT + WH_B_SLOT) + 8 * (2 * WH_STAGES + 1) + 16 + 1024;
+
+__device__ __forceinline__ uint64_t make_sw128_mn_desc2(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= static_cast<uint64_t>((saddr & 0x3FFFFu) >> 4);
+    d |= static_cast<uint64_t>(lbo_bytes >> 4) << 16;
+    d |= static_cast<uint64_t>(sbo_bytes >> 4) << 32;
+    d |= static_cast<uint64_t>(1) << 46;
+    d |= static_cast<uint64_t>(2) << 61;
+    return d;
+}
+
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+wgrad_halo64_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const WgradNhwcParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t base = (raw + 1023u) & ~1023u;
+    uint8_t *gbase = smem_raw + (base - raw);
+    const uint32_t sA = base;
+    const uint32_t sB = base + WH_STAGES * WH_A_SLOT;
+    const uint32_t sBar = sB + WH_STAGES * WH_B_SLOT;
+    auto full_bar = [&](int s) { return sBar + 8u * s; };
+    auto empty_bar = [&](int s) { return sBar + 8u * (WH_STAGES + s); };
+    const uint32_t tfull_bar = sBar + 8u * (2 * WH_STAGES);
+    volatile uint32_t *tmem_ptr = reinterpret_cast<volatile uint32_t *>(gbase + WH_STAGES * (WH_A_SLOT + WH_B_SLOT) + 8 * (2 * WH_STAGES + 1));
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    const int split = blockIdx.x % p.splits;
+    const int n_chunk = blockIdx.x / p.splits;
+    const int n0 = n_chunk * 64;
+    const int patches = p.N * p.ptx * p.pty;
+    const int per = (patches + p.splits - 1) / p.splits;
+    const int k0 = split * per;
+    const int k1 = min(patches, k0 + per);
+    const int num_k_iters = max(0, k1 - k0);
+
+    if (threadIdx.x == 0) {
+        prefetch_tmap(&tmA);
+        prefetch_tmap(&tmB);
+        for (int s = 0; s < WH_STAGES; ++s) {
+            mbar_init(full_bar(s), 1);
+            mbar_init(empty_bar(s), 1);
+        }
+        mbar_init(tfull_bar, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(smem_u32(const_cast<uint32_t *>(tmem_ptr)), 512);
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    if (num_k_iters > 0) {
+        if (warp == 0) {
+            if (lane == 0) {
+                const int ppi = p.ptx * p.pty;
+                int it = 0;
+                for (int k = k0; k < k1; ++k, ++it) {
+                    const int img = k / ppi;
+                    const int r = k - img * ppi;
+                    const int oy0 = (r / p.ptx) * 8, ox0 = (r % p.ptx) * 8;
+                    const int s = it % WH_STAGES;
+                    const uint32_t ph = (it / WH_STAGES) & 1;
+                    mbar_wait(empty_bar(s), ph ^ 1u);
+                    mbar_expect_tx(full_bar(s), 100 * 128 + 64 * 128);
+                    tma_load_4d(sA + s * WH_A_SLOT, &tmA, full_bar(s), 0, ox0 - 1, oy0 - 1, img);     // dz, 10 x 10 halo box
+                    tma_load_4d(sB + s * WH_B_SLOT, &tmB, full_bar(s), n0, ox0, oy0, img);           // x, 8 x 8 box
+                }
+            }
+            __syncwarp();
+        } else if (warp == 1) {
+            if (lane == 0) {
+                constexpr uint32_t idesc = make_idesc(BM, 64) | (1u << 15) | (1u << 16);
+                for (int it = 0; it < num_k_iters; ++it) {
+                    const int s = it % WH_STAGES;
+                    const uint32_t ph = (it / WH_STAGES) & 1;
+                    mbar_wait(full_bar(s), ph);
+                    tcgen05_fence_after();
+                    const uint32_t a_slot = sA + s * WH_A_SLOT, b_slot = sB + s * WH_B_SLOT;
+#pragma unroll
+                    for (int pr = 0; pr < 5; ++pr) {
+                        // pair pr = taps (8 - 2pr, 7 - 2pr); halo pixel offset of tap t: (2 - t/3) * 10 + (2 - t%3)
+                        const int t1 = 8 - 2 * pr, t2 = pr < 4 ? 7 - 2 * pr : t1;
+                        const int o1 = (2 - t1 / 3) * 10 + (2 - t1 % 3), o2 = (2 - t2 / 3) * 10 + (2 - t2 % 3);
+                        const uint32_t lbo = pr < 4 ? static_cast<uint32_t>(o2 - o1) * 128u : 128u;
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {      // 16 pixels = two 8-pixel patch rows per MMA
+                            const uint64_t adesc = make_sw128_mn_desc2(a_slot + o1 * 128 + k * 2 * 1280, lbo, 1280);
+                            const uint64_t bdesc = make_sw128_mn_desc2(b_slot + k * 2048, 8192, 1024);
+                            umma_f16(tmem_base + static_cast<uint32_t>(pr * 64), adesc, bdesc, idesc, (it > 0 || k > 0) ? 1u : 0u);
+                        }
+                    }
+                    umma_commit(empty_bar(s));
+                }
+                umma_commit(tfull_bar);
+            }
+            __syncwarp();
+        } else {
+            const int e = warp - 2, quad = warp & 3, half = e >> 2;
+            const int blk = quad >> 1;                               // first / second tap of the pair
+            const int m = (quad & 1) * 32 + lane;                    // output channel
+            mbar_wait(tfull_bar, 0);
+            tcgen05_fence_after();
+#pragma unroll 1
+            for (int c = half * 160; c < (half + 1) * 160; c += 32) {
+                uint32_t r[32];
+                tmem_ld32(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(c), r);
+                const int pr = c >> 6;
+                const int tap = 8 - 2 * pr - blk;
+                if (tap >= 0) {
+                    float *dst = p.out + (static_cast<size_t>(m) * 9 + tap) * p.out_ld + p.out_coff + n0 + (c & 63);
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4)
+                        red_add_v4(dst + j, __uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
+                                   __uint_as_float(r[j + 3]));
+                }
+            }
+            tcgen05_fence_before();
+        }
+    }
+    __syncthreads();
+    if (warp == 1) {
+        tcgen05_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // first layer: normalise + pad + Conv2d(1,C,3,p=1) + act + BN(eval), CUDA cores (K = 9)
 // ------------------------------------------------------------------------------------------
 // Block = 32x8 output pixels.  The normalised (and padded) input patch incl. its 1-pixel halo is staged
@@ -1397,6 +1539,15 @@ int epi_variant() {     // MBS_EPI_VARIANT (A/B runs): 0 default; 1 = transposed
     return v;
 }
 
+bool wgrad_halo_enabled() {
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("MBS_NO_WGRAD_HALO");
+        v = (e && e[0] == '1') ? 0 : 1;
+    }
+    return v == 1;
+}
+
 bool pair_enabled() {
     static int v = -1;
     if (v < 0) {
@@ -1586,6 +1737,30 @@ extern "C" int mbs_conv_wgrad(const mbs_wgrad_desc *d, void *stream_) {
     wp.ph = 64 / wp.pw;
     wp.ptx = mbs::cdiv(d->Wo, wp.pw);
     wp.pty = mbs::cdiv(d->Ho, wp.ph);
+    if (d->kind == 0 && d->Cm == 64 && d->Wo >= 8 && d->Ho >= 8 && wgrad_halo_enabled()) {
+        // full-resolution layers: all nine taps per CTA from one halo patch (see wgrad_halo64_kernel)
+        wp.pw = wp.ph = 8;
+        wp.ptx = mbs::cdiv(d->Wo, 8);
+        wp.pty = mbs::cdiv(d->Ho, 8);
+        const int chunks = d->Cn / 64;
+        const int patches = d->N * wp.ptx * wp.pty;
+        int splits = mbs::cdiv(sm_count(), chunks);      // one resident CTA per SM: one wave, fewest partial-tile reductions
+        if (splits > patches) splits = patches;
+        wp.splits = splits;
+        CUtensorMap a, b;
+        int rc = make_act_map(&a, d->a, d->N, d->Ho, d->Wo, d->Cm, d->lda, d->coffa, 1, 10, 10);
+        if (rc) return rc;
+        rc = make_act_map(&b, d->b, d->N, d->Ho, d->Wo, d->Cn, d->ldb, d->coffb, 1, 8, 8);
+        if (rc) return rc;
+        static bool configured = false;
+        if (!configured) {
+            MBS_CHECK_CUDA(cudaFuncSetAttribute(wgrad_halo64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WH_DYN));
+            configured = true;
+        }
+        wgrad_halo64_kernel<<<chunks * splits, NUM_THREADS, WH_DYN, stream>>>(a, b, wp);
+        MBS_CHECK_LAUNCH();
+        return 0;
+    }
     const int bn = d->Cn % 256 == 0 ? 256 : (d->Cn % 128 == 0 ? 128 : 64);
     wp.m_tiles = wp.pair ? 1 : mbs::cdiv(d->Cm, 128);
     wp.n_tiles = d->Cn / bn;
