@@ -386,10 +386,19 @@ __global__ void __launch_bounds__(256) pack_dgrad3x3_kernel(const float *__restr
         tile[r][k] = (co0 + r < Cout && ci0 + k / 9 < Cin) ? w[(static_cast<size_t>(co0 + r) * Cin + ci0) * 9 + k] : 0.0f;
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < 32 * 9 * 32; i += 256) {
-        const int co = i & 31, t = (i >> 5) % 9, ci = i / 288;
-        if (co0 + co < Cout && ci0 + ci < Cin)
-            out[(static_cast<size_t>(ci0 + ci) * 9 + t) * Cout + co0 + co] = __float2bfloat16_rn(tile[co][ci * 9 + (8 - t)]);
+    // 8 consecutive output channels (16 bytes) per thread
+    for (int i = threadIdx.x; i < 32 * 9 * 4; i += 256) {
+        const int c8 = (i & 3) * 8, t = (i >> 2) % 9, ci = i / 36;
+        if (ci0 + ci >= Cin) continue;
+        __nv_bfloat16 *dst = out + (static_cast<size_t>(ci0 + ci) * 9 + t) * Cout + co0 + c8;
+        if (co0 + c8 + 8 <= Cout && (Cout & 7) == 0) {
+            float f[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) f[j] = tile[c8 + j][ci * 9 + (8 - t)];
+            *reinterpret_cast<uint4 *>(dst) = Bf16x8::pack(f);
+        } else {
+            for (int j = 0; j < 8 && co0 + c8 + j < Cout; ++j) dst[j] = __float2bfloat16_rn(tile[c8 + j][ci * 9 + (8 - t)]);
+        }
     }
 }
 
