@@ -287,8 +287,9 @@ def main():
                 "achieved": achieved, "peak": peaks["tf_sustained"], "unit": "TFLOP/s", "frac": achieved / peaks["tf_sustained"],
                 "peak_source": peaks["src"] + " (sustained cuBLAS bf16)",
                 # dram__bytes_read+write per launch, averaged over the frame's tensor-core launches
-                # (ncu capture profiles/r01_conv_dram_traffic_frame.csv: 36 tensor-core launches, 13.245 GB)
-                "traffic": 13.245e9 / 36 if size == 2048 else None,
+                # (ncu capture profiles/r01_conv_dram_traffic_frame_v3.csv: 37 tensor-core launches of one frame,
+                #  dram__bytes_read.sum + dram__bytes_write.sum = 9.450 + 5.339 GB)
+                "traffic": 14.789e9 / 37 if size == 2048 else None,
                 "launches_per_frame": n_conv_launch, "avg_launch_ms": conv_ms_frame / max(n_conv_launch, 1),
                 "algorithmic_flop_per_launch": conv_flops / max(n_conv_launch, 1)}
 
