@@ -52,21 +52,44 @@ __global__ void lab_init_stats_kernel(CellStats *cs, int total) {
     cs[i] = z;
 }
 
+// Per-instance integer statistics.  All pixels of an instance hit the same ten addresses, so plain atomics
+// serialise; a warp (32 consecutive pixels of one row) first groups its lanes by instance id and reduces each
+// group with REDUX (__reduce_*_sync), then ONE lane per group issues the atomics.
 __global__ void lab_accum_kernel(const uint16_t *__restrict__ masks, int H, int W, int ids, CellStats *cs) {
     const int crop = blockIdx.z;
     const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
-    if (x >= W || y >= H) return;
-    const int id = masks[(static_cast<size_t>(crop) * H + y) * W + x];
-    if (id == 0 || id >= ids) return;
-    CellStats *s = cs + static_cast<size_t>(crop) * ids + id;
-    atomicAdd(&s->cnt, 1ull);
-    atomicAdd(&s->sy, static_cast<unsigned long long>(y));
-    atomicAdd(&s->sx, static_cast<unsigned long long>(x));
-    atomicAdd(&s->syy, static_cast<unsigned long long>(y) * y);
-    atomicAdd(&s->sxx, static_cast<unsigned long long>(x) * x);
-    atomicAdd(&s->sxy, static_cast<unsigned long long>(x) * y);
-    atomicMin(&s->y0, y); atomicMax(&s->y1, y);
-    atomicMin(&s->x0, x); atomicMax(&s->x1, x);
+    const int lane = threadIdx.x & 31;
+    int id = 0;
+    if (x < W && y < H) id = masks[(static_cast<size_t>(crop) * H + y) * W + x];
+    const bool valid = id != 0 && id < ids;
+    unsigned remaining = __ballot_sync(0xffffffffu, valid);
+    while (remaining) {
+        const int leader = __ffs(remaining) - 1;
+        const int cur = __shfl_sync(0xffffffffu, id, leader);
+        const bool mine = valid && id == cur;
+        const unsigned grp = __ballot_sync(0xffffffffu, mine);
+        if (mine) {
+            const unsigned ux = static_cast<unsigned>(x), uy = static_cast<unsigned>(y);
+            const unsigned c = __popc(grp);
+            const unsigned sy = __reduce_add_sync(grp, uy), sx = __reduce_add_sync(grp, ux);
+            const unsigned syy = __reduce_add_sync(grp, uy * uy), sxx = __reduce_add_sync(grp, ux * ux);
+            const unsigned sxy = __reduce_add_sync(grp, ux * uy);
+            const int y0 = __reduce_min_sync(grp, y), y1 = __reduce_max_sync(grp, y);
+            const int x0 = __reduce_min_sync(grp, x), x1 = __reduce_max_sync(grp, x);
+            if (lane == leader) {
+                CellStats *s = cs + static_cast<size_t>(crop) * ids + cur;
+                atomicAdd(&s->cnt, static_cast<unsigned long long>(c));
+                atomicAdd(&s->sy, static_cast<unsigned long long>(sy));
+                atomicAdd(&s->sx, static_cast<unsigned long long>(sx));
+                atomicAdd(&s->syy, static_cast<unsigned long long>(syy));
+                atomicAdd(&s->sxx, static_cast<unsigned long long>(sxx));
+                atomicAdd(&s->sxy, static_cast<unsigned long long>(sxy));
+                atomicMin(&s->y0, y0); atomicMax(&s->y1, y1);
+                atomicMin(&s->x0, x0); atomicMax(&s->x1, x1);
+            }
+        }
+        remaining &= ~grp;
+    }
 }
 
 // 4*sqrt(eigenvalue) of the inertia tensor [[mu02, -mu11], [-mu11, mu20]] / n  (skimage regionprops)
@@ -143,29 +166,26 @@ lab_cell_kernel(const uint16_t *__restrict__ masks, int H, int W, int ids, const
     }
     __syncthreads();
     // column scans (one thread per column): nearest site above / below
-    for (int x = threadIdx.x; x < ww; x += blockDim.x) {
-        int d1 = -1, d2 = -1;                 // distance to the last site seen going down (-1: none yet)
-        bool bg = false, other = false, own = false;
+    for (int t = threadIdx.x; t < 2 * ww; t += blockDim.x) {
+        const int x = t >> 1, which = t & 1;  // which = 0: sites are "not my id", 1: sites are other instances
+        unsigned short *g = which ? g2 : g1;
+        int d = -1;                           // distance to the last site seen going down (-1: none yet)
+        bool any_site = false, own = false;
         for (int y = 0; y < wh; ++y) {
             const int l = lab[y * ww + x];
-            const bool site1 = l != id, site2 = l != 0 && l != id;
-            bg |= site1; other |= site2; own |= !site1;
-            d1 = site1 ? 0 : (d1 < 0 ? -1 : d1 + 1);
-            d2 = site2 ? 0 : (d2 < 0 ? -1 : d2 + 1);
-            g1[y * ww + x] = d1 < 0 ? kInf16 : static_cast<unsigned short>(d1);
-            g2[y * ww + x] = d2 < 0 ? kInf16 : static_cast<unsigned short>(d2);
+            const bool site = which ? (l != 0 && l != id) : (l != id);
+            any_site |= site; own |= (l == id);
+            d = site ? 0 : (d < 0 ? -1 : d + 1);
+            g[y * ww + x] = d < 0 ? kInf16 : static_cast<unsigned short>(d);
         }
-        d1 = -1; d2 = -1;
+        d = -1;
         for (int y = wh - 1; y >= 0; --y) {
             const int l = lab[y * ww + x];
-            const bool site1 = l != id, site2 = l != 0 && l != id;
-            d1 = site1 ? 0 : (d1 < 0 ? -1 : d1 + 1);
-            d2 = site2 ? 0 : (d2 < 0 ? -1 : d2 + 1);
-            if (d1 >= 0 && d1 < g1[y * ww + x]) g1[y * ww + x] = static_cast<unsigned short>(d1);
-            if (d2 >= 0 && d2 < g2[y * ww + x]) g2[y * ww + x] = static_cast<unsigned short>(d2);
+            const bool site = which ? (l != 0 && l != id) : (l != id);
+            d = site ? 0 : (d < 0 ? -1 : d + 1);
+            if (d >= 0 && d < g[y * ww + x]) g[y * ww + x] = static_cast<unsigned short>(d);
         }
-        if (bg) s_any_bg = 1;
-        if (other) s_any_other = 1;
+        if (any_site) { if (which) s_any_other = 1; else s_any_bg = 1; }
         if (own) s_any_own = 1;
     }
     __syncthreads();
@@ -177,25 +197,40 @@ lab_cell_kernel(const uint16_t *__restrict__ masks, int H, int W, int ids, const
         if (lab[i] != id) continue;
         const int y = i / ww, x = i - y * ww;
         unsigned int b1 = 0xFFFFFFFFu, b2 = 0xFFFFFFFFu;
+        // exact minimum over all columns, visited outwards from x: once dx^2 alone reaches the best squared distance
+        // no farther column can improve it
+        const unsigned short *r1 = g1 + y * ww, *r2 = g2 + y * ww;
         if (any_bg) {
-            for (int xx = 0; xx < ww; ++xx) {
-                const unsigned int g = g1[y * ww + xx];
-                if (g == kInf16) continue;
-                const unsigned int dx = static_cast<unsigned int>(xx > x ? xx - x : x - xx);
-                const unsigned int d = dx * dx + g * g;
-                b1 = d < b1 ? d : b1;
+            const int kmax = x > ww - 1 - x ? x : ww - 1 - x;
+            for (int k = 0; k <= kmax; ++k) {
+                const unsigned int dx2 = static_cast<unsigned int>(k * k);
+                if (dx2 >= b1) break;
+                if (x - k >= 0) {
+                    const unsigned int g = r1[x - k];
+                    if (g != kInf16) { const unsigned int d = dx2 + g * g; b1 = d < b1 ? d : b1; }
+                }
+                if (k && x + k < ww) {
+                    const unsigned int g = r1[x + k];
+                    if (g != kInf16) { const unsigned int d = dx2 + g * g; b1 = d < b1 ? d : b1; }
+                }
             }
         } else {
             // scipy's feature transform of an all-foreground array points at (-1, 0)
             b1 = static_cast<unsigned int>((y + 1) * (y + 1) + x * x);
         }
         if (any_other) {
-            for (int xx = 0; xx < ww; ++xx) {
-                const unsigned int g = g2[y * ww + xx];
-                if (g == kInf16) continue;
-                const unsigned int dx = static_cast<unsigned int>(xx > x ? xx - x : x - xx);
-                const unsigned int d = dx * dx + g * g;
-                b2 = d < b2 ? d : b2;
+            const int kmax = x > ww - 1 - x ? x : ww - 1 - x;
+            for (int k = 0; k <= kmax; ++k) {
+                const unsigned int dx2 = static_cast<unsigned int>(k * k);
+                if (dx2 >= b2) break;
+                if (x - k >= 0) {
+                    const unsigned int g = r2[x - k];
+                    if (g != kInf16) { const unsigned int d = dx2 + g * g; b2 = d < b2 ? d : b2; }
+                }
+                if (k && x + k < ww) {
+                    const unsigned int g = r2[x + k];
+                    if (g != kInf16) { const unsigned int d = dx2 + g * g; b2 = d < b2 ? d : b2; }
+                }
             }
         }
         lmax1 = b1 > lmax1 ? b1 : lmax1;
@@ -229,23 +264,27 @@ lab_cell_kernel(const uint16_t *__restrict__ masks, int H, int W, int ids, const
     }
 }
 
-// per-instance binary_closing(nucleus, disk(3)) OR-ed into label_bin (bottom_hat_closing :50-55);
+constexpr int CB_MAX_ROWS = 96;      // window rows (bbox + 6) handled by the warp-per-instance bit-parallel closing
+
+// per-instance binary_closing(nucleus, disk(3)) OR-ed into the label_bin bit image (bottom_hat_closing :50-55) for
+// instances too large for lab_close_cell_bits_kernel;
 // scipy's erosion uses border_value=0, i.e. pixels whose disk leaves the image are removed.
 __device__ __forceinline__ bool in_disk3(int dy, int dx) { return dy * dy + dx * dx <= 9; }
 
 __global__ void __launch_bounds__(256)
-lab_close_cell_kernel(const uint16_t *__restrict__ masks, int H, int W, int ids, const CellStats *cs, CropInfo *info,
-                      uint8_t *__restrict__ label_bin, int smem_cap_bytes) {
-    const int crop = blockIdx.y;
-    const int id = blockIdx.x + 1;
-    if (id >= ids) return;
-    const CellStats s = cs[static_cast<size_t>(crop) * ids + id];
-    if (s.cnt == 0) return;
+lab_close_cell_kernel(const uint16_t *__restrict__ masks, int H, int W, int WW, int ids, const CellStats *cs, CropInfo *info,
+                      unsigned long long *__restrict__ lbits, int smem_cap_bytes, const int *__restrict__ big_list) {
+  // big_list[0] = number of oversized instances, then their (crop * ids + id) keys (appended by lab_close_cell_bits_kernel)
+  for (int k = blockIdx.x; k < big_list[0]; k += gridDim.x) {
+    __syncthreads();                                    // smem reuse between instances
+    const int key = big_list[1 + k];
+    const int crop = key / ids, id = key - crop * ids;
+    const CellStats s = cs[key];
     const int bh = s.y1 - s.y0 + 1, bw = s.x1 - s.x0 + 1;
     const int dh = bh + 6, dw = bw + 6;
     if (bh * bw + dh * dw > smem_cap_bytes) {
         if (threadIdx.x == 0) atomicOr(&info[crop].error, 1);
-        return;
+        continue;
     }
     extern __shared__ unsigned short sm[];
     uint8_t *X = reinterpret_cast<uint8_t *>(sm);      // [bh][bw]
@@ -271,7 +310,7 @@ lab_close_cell_kernel(const uint16_t *__restrict__ masks, int H, int W, int ids,
         D[i] = v;
     }
     __syncthreads();
-    uint8_t *out = label_bin + static_cast<size_t>(crop) * H * W;
+    unsigned long long *out = lbits + static_cast<size_t>(crop) * H * WW;
     for (int i = threadIdx.x; i < bh * bw; i += blockDim.x) {
         const int y = i / bw, x = i - y * bw;
         bool v = true;
@@ -281,7 +320,176 @@ lab_close_cell_kernel(const uint16_t *__restrict__ masks, int H, int W, int ids,
                 const int gy = s.y0 + y + dy, gx = s.x0 + x + dx;
                 if (gy < 0 || gy >= H || gx < 0 || gx >= W || !D[(y + dy + 3) * dw + (x + dx + 3)]) { v = false; break; }
             }
-        if (v) out[static_cast<size_t>(s.y0 + y) * W + s.x0 + x] = 1;
+        if (v) atomicOr(out + static_cast<size_t>(s.y0 + y) * WW + ((s.x0 + x) >> 6), 1ull << ((s.x0 + x) & 63));
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Bit-parallel morphology with disk(3) = {|dx|<=3, dy=0} U {|dx|<=2, |dy|<=2} U {dx=0, |dy|=3} (x^2+y^2 <= 9):
+// image rows are 64-bit words (bit b of word w = pixel x = 64w+b), a dilation / erosion of 64 pixels is ~40 word
+// operations instead of 64 x 29 byte tests.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long or_spread(unsigned long long c, int k) {       // single-word window
+    unsigned long long r = c;
+    for (int s = 1; s <= k; ++s) r |= (c << s) | (c >> s);
+    return r;
+}
+__device__ __forceinline__ unsigned long long and_spread(unsigned long long c, int k) {      // zeros shift in at the ends
+    unsigned long long r = c;
+    for (int s = 1; s <= k; ++s) r &= (c << s) & (c >> s);
+    return r;
+}
+// OR / AND over horizontal shifts -k..k of a row given as (left word, centre word, right word)
+__device__ __forceinline__ unsigned long long or_spread3(unsigned long long l, unsigned long long c, unsigned long long r, int k) {
+    unsigned long long o = c;
+    for (int s = 1; s <= k; ++s) o |= ((c << s) | (l >> (64 - s))) | ((c >> s) | (r << (64 - s)));
+    return o;
+}
+__device__ __forceinline__ unsigned long long and_spread3(unsigned long long l, unsigned long long c, unsigned long long r, int k) {
+    unsigned long long o = c;
+    for (int s = 1; s <= k; ++s) o &= ((c << s) | (l >> (64 - s))) & ((c >> s) | (r << (64 - s)));
+    return o;
+}
+
+
+// per-instance binary_closing(nucleus, disk(3)) OR-ed into the label_bin BIT image (bottom_hat_closing :50-55); one
+// warp per instance, the window (bbox + 3 px) is at most 64 columns x 96 rows (larger instances: lab_close_cell_kernel).
+// Window bit b = image column x0 - 3 + b.  scipy's erosion uses border_value = 0.
+__global__ void __launch_bounds__(256)
+lab_close_cell_bits_kernel(const uint16_t *__restrict__ masks, int H, int W, int WW, int ids, const CellStats *cs,
+                           unsigned long long *__restrict__ lbits, int *__restrict__ big_list) {
+    __shared__ unsigned long long sX[8][CB_MAX_ROWS + 6], sD[8][CB_MAX_ROWS + 6];
+    const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int crop = blockIdx.y;
+    const int id = blockIdx.x * 8 + wib + 1;
+    if (id >= ids) return;
+    const CellStats s = cs[static_cast<size_t>(crop) * ids + id];
+    if (s.cnt == 0) return;
+    const int bh = s.y1 - s.y0 + 1, bw = s.x1 - s.x0 + 1;
+    const int dh = bh + 6, dw = bw + 6;
+    if (dw > 64 || dh > CB_MAX_ROWS) {                  // queue for the byte-wise kernel
+        if (lane == 0) big_list[1 + atomicAdd(&big_list[0], 1)] = crop * ids + id;
+        return;
+    }
+    unsigned long long *X = sX[wib] + 3, *D = sD[wib] + 3;       // rows -3 .. dh+2 addressable
+    const uint16_t *m = masks + static_cast<size_t>(crop) * H * W;
+    const int gx0 = s.x0 - 3, gy0 = s.y0 - 3;
+    // columns of the window that lie inside the image
+    unsigned long long colmask = 0;
+    for (int b = 0; b < dw; ++b)
+        if (gx0 + b >= 0 && gx0 + b < W) colmask |= 1ull << b;
+    if (lane < 3) { X[-1 - lane] = 0; X[dh + lane] = 0; D[-1 - lane] = 0; D[dh + lane] = 0; }
+    // rows as ballots: lane = column (two halves)
+    for (int r = 0; r < dh; ++r) {
+        const int gy = gy0 + r;
+        unsigned lo = 0, hi = 0;
+        if (gy >= 0 && gy < H) {             // warp-uniform
+            const int xa = gx0 + lane, xb = gx0 + 32 + lane;
+            const bool a = lane < dw && xa >= 0 && xa < W && m[static_cast<size_t>(gy) * W + xa] == id;
+            const bool b = 32 + lane < dw && xb >= 0 && xb < W && m[static_cast<size_t>(gy) * W + xb] == id;
+            lo = __ballot_sync(0xffffffffu, a);
+            hi = __ballot_sync(0xffffffffu, b);
+        }
+        if (lane == 0) X[r] = (static_cast<unsigned long long>(hi) << 32) | lo;
+    }
+    __syncwarp();
+    for (int r = lane; r < dh; r += 32) {    // dilation, defined inside the image only
+        const int gy = gy0 + r;
+        unsigned long long d = 0;
+        if (gy >= 0 && gy < H)
+            d = (or_spread(X[r], 3) | or_spread(X[r - 1] | X[r + 1] | X[r - 2] | X[r + 2], 2) | X[r - 3] | X[r + 3]) & colmask;
+        D[r] = d;
+    }
+    __syncwarp();
+    unsigned long long *out = lbits + static_cast<size_t>(crop) * H * WW;
+    for (int r = 3 + lane; r < 3 + bh; r += 32) {      // erosion at the bounding-box rows
+        unsigned long long e = and_spread(D[r], 3) & and_spread(D[r - 1] & D[r + 1] & D[r - 2] & D[r + 2], 2) & D[r - 3] & D[r + 3];
+        if (!e) continue;
+        const int gy = gy0 + r;
+        int gx = gx0;
+        if (gx < 0) { e >>= -gx; gx = 0; }
+        const int w = gx >> 6, sh = gx & 63;
+        unsigned long long *row = out + static_cast<size_t>(gy) * WW;
+        atomicOr(row + w, e << sh);
+        if (sh && w + 1 < WW && (e >> (64 - sh))) atomicOr(row + w + 1, e >> (64 - sh));
+    }
+}
+
+__device__ __forceinline__ void load3(const unsigned long long *img, int H, int WW, int y, int w, unsigned long long &l,
+                                      unsigned long long &c, unsigned long long &r) {
+    l = c = r = 0;
+    if (y < 0 || y >= H) return;
+    const unsigned long long *row = img + static_cast<size_t>(y) * WW;
+    c = row[w];
+    if (w > 0) l = row[w - 1];
+    if (w + 1 < WW) r = row[w + 1];
+}
+// dil = binary_dilation(label_bin, disk(3)) on bit images (bottom_hat_closing :58)
+__global__ void lab_dilate_bits_kernel(const unsigned long long *__restrict__ in, int H, int W, int WW, int n_crops,
+                                       unsigned long long *__restrict__ out) {
+    const long long t = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (t >= static_cast<long long>(n_crops) * H * WW) return;
+    const int w = static_cast<int>(t % WW), y = static_cast<int>((t / WW) % H);
+    const unsigned long long *img = in + (t / (static_cast<long long>(WW) * H)) * H * WW;
+    unsigned long long d = 0, l, c, r;
+    load3(img, H, WW, y, w, l, c, r);
+    d |= or_spread3(l, c, r, 3);
+#pragma unroll
+    for (int dy = 1; dy <= 2; ++dy) {
+        load3(img, H, WW, y - dy, w, l, c, r);
+        d |= or_spread3(l, c, r, 2);
+        load3(img, H, WW, y + dy, w, l, c, r);
+        d |= or_spread3(l, c, r, 2);
+    }
+    load3(img, H, WW, y - 3, w, l, c, r);
+    d |= c;
+    load3(img, H, WW, y + 3, w, l, c, r);
+    d |= c;
+    const int valid = W - 64 * w;                      // columns of this word inside the image
+    if (valid < 64) d &= (1ull << valid) - 1;
+    out[t] = d;
+}
+// gap = ~label_bin & (erode(dil) ^ label_bin) as BYTES for the component labelling (bottom_hat_closing :58-59)
+__global__ void lab_erode_gap_bits_kernel(const unsigned long long *__restrict__ dil, const unsigned long long *__restrict__ lbits,
+                                          int H, int W, int WW, int n_crops, uint8_t *__restrict__ gap) {
+    const long long t = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (t >= static_cast<long long>(n_crops) * H * WW) return;
+    const int w = static_cast<int>(t % WW), y = static_cast<int>((t / WW) % H);
+    const long long crop = t / (static_cast<long long>(WW) * H);
+    const unsigned long long *img = dil + crop * H * WW;
+    unsigned long long l, c, r;
+    load3(img, H, WW, y, w, l, c, r);
+    unsigned long long e = and_spread3(l, c, r, 3);
+#pragma unroll
+    for (int dy = 1; dy <= 2; ++dy) {
+        load3(img, H, WW, y - dy, w, l, c, r);
+        e &= and_spread3(l, c, r, 2);
+        load3(img, H, WW, y + dy, w, l, c, r);
+        e &= and_spread3(l, c, r, 2);
+    }
+    load3(img, H, WW, y - 3, w, l, c, r);
+    e &= c;
+    load3(img, H, WW, y + 3, w, l, c, r);
+    e &= c;
+    const unsigned long long lb = lbits[t];
+    const unsigned long long g = ~lb & (e ^ lb);
+    const int valid = min(64, W - 64 * w);
+    uint8_t *dst = gap + (crop * H + y) * W + 64 * w;
+    if (valid == 64 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+        // 8 bits -> 8 bytes: isolate bit i in byte i, then normalise every non-zero byte to 1
+        auto expand8 = [](unsigned long long x) {
+            unsigned long long v = (x * 0x0101010101010101ull) & 0x8040201008040201ull;
+            return ((v + 0x7F7F7F7F7F7F7F7Full) >> 7) & 0x0101010101010101ull;
+        };
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const unsigned long long a = expand8((g >> (16 * q)) & 0xFFull), b = expand8((g >> (16 * q + 8)) & 0xFFull);
+            *reinterpret_cast<uint4 *>(dst + 16 * q) = make_uint4(static_cast<unsigned>(a), static_cast<unsigned>(a >> 32),
+                                                                 static_cast<unsigned>(b), static_cast<unsigned>(b >> 32));
+        }
+    } else {
+        for (int b = 0; b < valid; ++b) dst[b] = static_cast<uint8_t>((g >> b) & 1ull);
     }
 }
 
@@ -303,39 +511,6 @@ __global__ void lab_border_kernel(const uint16_t *__restrict__ masks, int H, int
             }
     }
     border[(static_cast<size_t>(crop) * H + y) * W + x] = b;
-}
-
-__global__ void lab_dilate_kernel(const uint8_t *__restrict__ in, int H, int W, uint8_t *__restrict__ out) {
-    const int crop = blockIdx.z;
-    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
-    if (x >= W || y >= H) return;
-    const uint8_t *p = in + static_cast<size_t>(crop) * H * W;
-    bool v = false;
-    for (int dy = -3; dy <= 3 && !v; ++dy)
-        for (int dx = -3; dx <= 3; ++dx) {
-            if (!in_disk3(dy, dx)) continue;
-            const int yy = y + dy, xx = x + dx;
-            if (yy >= 0 && yy < H && xx >= 0 && xx < W && p[yy * W + xx]) { v = true; break; }
-        }
-    out[(static_cast<size_t>(crop) * H + y) * W + x] = v;
-}
-// gap = ~label_bin & (erode(dilated) ^ label_bin)   (bottom_hat_closing :58-59)
-__global__ void lab_erode_gap_kernel(const uint8_t *__restrict__ dil, const uint8_t *__restrict__ label_bin, int H, int W,
-                                     uint8_t *__restrict__ gap) {
-    const int crop = blockIdx.z;
-    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
-    if (x >= W || y >= H) return;
-    const uint8_t *p = dil + static_cast<size_t>(crop) * H * W;
-    bool v = true;
-    for (int dy = -3; dy <= 3 && v; ++dy)
-        for (int dx = -3; dx <= 3; ++dx) {
-            if (!in_disk3(dy, dx)) continue;
-            const int yy = y + dy, xx = x + dx;
-            if (yy < 0 || yy >= H || xx < 0 || xx >= W || !p[yy * W + xx]) { v = false; break; }
-        }
-    const size_t o = (static_cast<size_t>(crop) * H + y) * W + x;
-    const bool lb = label_bin[o] != 0;
-    gap[o] = (!lb) && (v != lb);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -545,7 +720,9 @@ extern "C" size_t mbs_labels_workspace_bytes(int n_crops, int H, int W, int max_
     const size_t ids = static_cast<size_t>(max_id) + 1;
     return r256(n_crops * ids * sizeof(CellStats)) + r256(n_crops * sizeof(CropInfo)) +
            r256(static_cast<size_t>(n_crops) * kMaxGaps * sizeof(GapStats)) + 2 * r256(px * 8) /*nraw, scaled*/ +
-           4 * r256(px) /*label_bin, dil, gap, border*/ + 2 * r256(px * 4) /*L, gid*/ + 4096;
+           4 * r256(px) /*label_bin, dil, gap, border*/ + 2 * r256(px * 4) /*L, gid*/ +
+           2 * r256(static_cast<size_t>(n_crops) * H * ((W + 63) / 64) * 8) /*label_bin, dil as bit images*/ +
+           r256((n_crops * ids + 1) * sizeof(int)) /*oversized-instance list*/ + 4096;
 }
 
 extern "C" int mbs_labels_max_mal(const uint16_t *masks, int n_crops, int H, int W, int max_id, int32_t *max_mal_out,
@@ -594,6 +771,13 @@ extern "C" int mbs_distance_labels(const uint16_t *masks, int n_crops, int H, in
     uint8_t *border = reinterpret_cast<uint8_t *>(take(px));
     int *L = reinterpret_cast<int *>(take(px * 4));
     int *gid = reinterpret_cast<int *>(take(px * 4));
+    const int WW = (W + 63) / 64;
+    const size_t bit_bytes = static_cast<size_t>(n_crops) * H * WW * 8;
+    unsigned long long *lbits = reinterpret_cast<unsigned long long *>(take(bit_bytes));
+    unsigned long long *dbits = reinterpret_cast<unsigned long long *>(take(bit_bytes));
+    int *big_list = reinterpret_cast<int *>(take((static_cast<size_t>(n_crops) * ids + 1) * sizeof(int)));
+    (void)label_bin;
+    (void)dil;
 
     const int total = n_crops * ids;
     dim3 b2(32, 8), g3(mbs::cdiv(W, 32), mbs::cdiv(H, 8), n_crops);
@@ -602,7 +786,8 @@ extern "C" int mbs_distance_labels(const uint16_t *masks, int n_crops, int H, in
     MBS_CHECK_CUDA(cudaMemsetAsync(gs, 0, static_cast<size_t>(n_crops) * kMaxGaps * sizeof(GapStats), stream));
     MBS_CHECK_CUDA(cudaMemsetAsync(nraw, 0, px * 8, stream));
     MBS_CHECK_CUDA(cudaMemsetAsync(cell_dist, 0, px * 4, stream));
-    MBS_CHECK_CUDA(cudaMemsetAsync(label_bin, 0, px, stream));
+    MBS_CHECK_CUDA(cudaMemsetAsync(lbits, 0, bit_bytes, stream));
+    MBS_CHECK_CUDA(cudaMemsetAsync(big_list, 0, sizeof(int), stream));
     lab_init_stats_kernel<<<mbs::cdiv(total, 256), 256, 0, stream>>>(cs, total);
     MBS_CHECK_LAUNCH();
     lab_accum_kernel<<<g3, b2, 0, stream>>>(masks, H, W, ids, cs);
@@ -634,14 +819,18 @@ extern "C" int mbs_distance_labels(const uint16_t *masks, int n_crops, int H, in
         MBS_CHECK_LAUNCH();
         long long wantc = 2ll * (static_cast<long long>(H) + 6) * (W + 6);
         int smemc = wantc > smem_opt ? smem_opt : static_cast<int>(wantc);
-        lab_close_cell_kernel<<<gc, 256, smemc, stream>>>(masks, H, W, ids, cs, info, label_bin, smemc);
+        lab_close_cell_bits_kernel<<<dim3(mbs::cdiv(max_id, 8), n_crops), 256, 0, stream>>>(masks, H, W, WW, ids, cs, lbits, big_list);
+        MBS_CHECK_LAUNCH();
+        // oversized instances only: a small persistent grid walks the queue (usually empty)
+        lab_close_cell_kernel<<<2 * 148, 256, smemc, stream>>>(masks, H, W, WW, ids, cs, info, lbits, smemc, big_list);
         MBS_CHECK_LAUNCH();
     }
     lab_border_kernel<<<g3, b2, 0, stream>>>(masks, H, W, border);
     MBS_CHECK_LAUNCH();
-    lab_dilate_kernel<<<g3, b2, 0, stream>>>(label_bin, H, W, dil);
+    const int nwords = static_cast<int>((static_cast<long long>(n_crops) * H * WW + 255) / 256);
+    lab_dilate_bits_kernel<<<nwords, 256, 0, stream>>>(lbits, H, W, WW, n_crops, dbits);
     MBS_CHECK_LAUNCH();
-    lab_erode_gap_kernel<<<g3, b2, 0, stream>>>(dil, label_bin, H, W, gap);
+    lab_erode_gap_bits_kernel<<<nwords, 256, 0, stream>>>(dbits, lbits, H, W, WW, n_crops, gap);
     MBS_CHECK_LAUNCH();
     gap_init_kernel<<<nb, 256, 0, stream>>>(gap, static_cast<long long>(px), L);
     MBS_CHECK_LAUNCH();

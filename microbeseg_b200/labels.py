@@ -123,13 +123,30 @@ def create_labels(masks):
     if masks.ndim == 2:
         masks = masks[None]
     n, H, W = masks.shape
-    per = max(1, min(n, _MAX_BATCH_PIXELS // (H * W)))
-    cells, neighs, mals = [], [], []
+    per = max(1, min(n, (_MAX_BATCH_PIXELS // 4) // (H * W)))      # <= 64 Mpx per batch: 2 x 256 MiB of pinned staging
+    L = nat.lib()
+    device = _device()
+    cells = np.empty((n, H, W), np.float32)
+    neighs = np.empty((n, H, W), np.float32)
+    mals = np.empty(n, np.int32)
+    # pinned staging for the read-back of one batch (two float32 maps per pixel dominate the host traffic)
+    pin_c = torch.empty((per, H, W), dtype=torch.float32, pin_memory=True)
+    pin_n = torch.empty((per, H, W), dtype=torch.float32, pin_memory=True)
     for s in range(0, n, per):
-        dev, max_id = _masks_to_device(masks[s:s + per], _device())
-        hint = int(np.ceil(0.75 * int(max_major_axis_lengths(masks[s:s + per]).max()))) if max_id > 0 else 0
+        dev, max_id = _masks_to_device(masks[s:s + per], device)       # one upload per batch
+        k = dev.shape[0]
+        hint = 0
+        if max_id > 0:       # radius hint from the batch's own max_mal, computed on the uploaded masks
+            mal_dev = torch.zeros(k, dtype=torch.int32, device=device)
+            ws = torch.empty(L.mbs_labels_workspace_bytes(k, H, W, max_id), dtype=torch.uint8, device=device)
+            with torch.cuda.device(device):
+                nat.check(L.mbs_labels_max_mal(dev.data_ptr(), k, H, W, max_id, mal_dev.data_ptr(), ws.data_ptr(), ws.numel(),
+                                               nat.stream_ptr()), "labels_max_mal")
+            hint = int(np.ceil(0.75 * int(mal_dev.max().item())))
         c, nb, mal = _run(dev, max_id, -1, hint)
-        cells.append(c.cpu().numpy())
-        neighs.append(nb.cpu().numpy())
-        mals.append(mal.cpu().numpy())
-    return np.concatenate(cells), np.concatenate(neighs), np.concatenate(mals)
+        pin_c[:k].copy_(c, non_blocking=True)
+        pin_n[:k].copy_(nb, non_blocking=True)
+        mals[s:s + k] = mal.cpu().numpy()                               # synchronises the stream
+        cells[s:s + k] = pin_c[:k].numpy()
+        neighs[s:s + k] = pin_n[:k].numpy()
+    return cells, neighs, mals

@@ -50,6 +50,24 @@ def test_touching_cells_gaps_and_borders(lab):
     _check(lab.distance_label(m, 20), ref, "dense")
 
 
+def test_large_and_word_crossing_instances(lab):
+    """instances wider than the 64-column bit window (byte-wise closing fallback OR-ing into the bit image), instances
+    straddling the 64-pixel word boundaries of the bit rows, cells at the image border, width not a multiple of 64"""
+    H, W = 200, 330
+    yy, xx = np.mgrid[0:H, 0:W]
+    m = np.zeros((H, W), np.uint16)
+    m[((yy - 100) / 45.0) ** 2 + ((xx - 120) / 75.0) ** 2 <= 1] = 3          # 150 px wide
+    m[((yy - 30) / 12.0) ** 2 + ((xx - 64) / 9.0) ** 2 <= 1] = 7             # straddles the word boundary x = 64
+    m[((yy - 170) / 10.0) ** 2 + ((xx - 256) / 14.0) ** 2 <= 1] = 8          # straddles x = 256
+    m[((yy - 186) / 14.0) ** 2 + ((xx - 205) / 11.0) ** 2 <= 1] = 9          # touches the bottom edge
+    m[90:112, 318:330] = 11                                                  # touches the right edge (last partial word)
+    m[((yy - 60) / 9.0) ** 2 + ((xx - 215) / 16.0) ** 2 <= 1] = 12           # close to the big one: gaps
+    m[((yy - 100) / 12.0) ** 2 + ((xx - 206) / 8.0) ** 2 <= 1] = 13          # touching the big one
+    ref, im = ol.distance_label(m, 40, return_intermediates=True)
+    _check(lab.distance_label(m, 40), ref, "large / word crossing")
+    assert (ref[1] > 0).sum() > 10 and im["gaps"].max() >= 1
+
+
 def test_edge_cases(lab):
     z = np.zeros((64, 80), np.uint16)
     _check(lab.distance_label(z, 10), ol.distance_label(z, 10), "empty")
