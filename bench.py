@@ -198,7 +198,8 @@ def main():
 
     conv_ms = []
 
-    pp_stream = torch.cuda.Stream(device)
+    # MBS_PP_STREAM=0: post-processing on the network's stream (A/B knob)
+    pp_stream = torch.cuda.current_stream(device) if os.environ.get("MBS_PP_STREAM") == "0" else torch.cuda.Stream(device)
     ev_net = [torch.cuda.Event() for _ in range(2)]
     ev_pp = [torch.cuda.Event() for _ in range(2)]
 

@@ -8,6 +8,8 @@ normalisation + padding are fused into the first conv kernel, the distance maps 
 GPU, and only the uint16 mask comes back.  Frames of a 2D+t stack are independent (per-frame
 min/max), so multi-GPU runs shard frames over ranks with no collective.
 """
+import os
+
 import numpy as np
 import torch
 
@@ -35,7 +37,9 @@ class FrameSegmenter:
         self._stage = {}
         self.h2d_stream = torch.cuda.Stream(self.device)
         self.d2h_stream = torch.cuda.Stream(self.device)
-        self.pp_stream = torch.cuda.Stream(self.device)      # post-processing of frame k overlaps the network of frame k+1
+        # post-processing of frame k overlaps the network of frame k+1 (MBS_PP_STREAM=0: same stream, A/B knob)
+        self.pp_stream = (torch.cuda.current_stream(self.device) if os.environ.get("MBS_PP_STREAM") == "0"
+                          else torch.cuda.Stream(self.device))
 
     def _staging(self, shape, dtype, slot):
         key = (tuple(shape), np.dtype(dtype).str, slot)
