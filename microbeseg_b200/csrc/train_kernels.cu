@@ -455,17 +455,30 @@ first_conv_wgrad_kernel(const float *__restrict__ x, const __nv_bfloat16 *__rest
     __syncthreads();
     const int c = threadIdx.x % C, pl = threadIdx.x / C, lanes = blockDim.x / C;
     float acc[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-    const long long P = static_cast<long long>(N) * H * W;
-    for (long long p = static_cast<long long>(blockIdx.x) * lanes + pl; p < P; p += static_cast<long long>(gridDim.x) * lanes) {
-        const int xx = static_cast<int>(p % W);
-        const int yy = static_cast<int>((p / W) % H);
-        const long long n = p / (static_cast<long long>(W) * H);
-        const float g = __bfloat162float(dz[p * C + c]);
-        if (g == 0.0f) continue;
-#pragma unroll
-        for (int t = 0; t < 9; ++t) {
-            const int y2 = yy + t / 3 - 1, x2 = xx + t % 3 - 1;
-            if (y2 >= 0 && y2 < H && x2 >= 0 && x2 < W) acc[t] = fmaf(g, x[(n * H + y2) * W + x2], acc[t]);
+    // a block walks whole image rows (no per-pixel 64-bit div / mod: that arithmetic used to dominate this kernel)
+    const int rows = N * H;
+    for (int row = blockIdx.x; row < rows; row += gridDim.x) {
+        const int yy = row % H;
+        const float *xr = x + static_cast<size_t>(row) * W;                 // x is [N][H][W]: same row index
+        const __nv_bfloat16 *gr = dz + static_cast<size_t>(row) * W * C + c;
+        const bool up = yy > 0, down = yy + 1 < H;
+        for (int xx = pl; xx < W; xx += lanes) {
+            const float g = __bfloat162float(gr[static_cast<size_t>(xx) * C]);
+            if (g == 0.0f) continue;
+            const bool left = xx > 0, right = xx + 1 < W;
+            if (up) {
+                if (left) acc[0] = fmaf(g, xr[xx - W - 1], acc[0]);
+                acc[1] = fmaf(g, xr[xx - W], acc[1]);
+                if (right) acc[2] = fmaf(g, xr[xx - W + 1], acc[2]);
+            }
+            if (left) acc[3] = fmaf(g, xr[xx - 1], acc[3]);
+            acc[4] = fmaf(g, xr[xx], acc[4]);
+            if (right) acc[5] = fmaf(g, xr[xx + 1], acc[5]);
+            if (down) {
+                if (left) acc[6] = fmaf(g, xr[xx + W - 1], acc[6]);
+                acc[7] = fmaf(g, xr[xx + W], acc[7]);
+                if (right) acc[8] = fmaf(g, xr[xx + W + 1], acc[8]);
+            }
         }
     }
 #pragma unroll
