@@ -35,7 +35,7 @@ def fit_heads(net, pairs, ridge=1e-3):
         eng.run(d[None], 0, 0, float(frame.min()), float(frame.max()), keep_features=feats)
         targets = {names[0]: border_t, names[-1]: cell_t}
         for n in names:
-            F = feats[n][0].reshape(-1, C).double()
+            F = feats[n][0][..., :C].reshape(-1, C).double()      # narrow nets run zero-padded to 64 channels
             F1 = torch.cat([F, torch.ones((F.shape[0], 1), dtype=torch.float64, device=dev)], 1)
             y = torch.from_numpy(np.ascontiguousarray(targets[n], dtype=np.float64)).to(dev).reshape(-1)
             A[n] += F1.T @ F1

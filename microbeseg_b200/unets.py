@@ -133,8 +133,8 @@ class _NetBase(nn.Module):
             raise NotImplementedError(
                 "the CUDA path covers the published configuration (pool 'conv', normalization 'bn'); got "
                 f"pool_method={self.pool_method!r}, normalization={self.normalization!r}")
-        if self.ch_in != 1 or self._chans[0] % 64 != 0:
-            raise NotImplementedError("the CUDA path needs ch_in == 1 and filters[0] a multiple of 64")
+        if self.ch_in != 1 or self._chans[0] % 8 != 0:
+            raise NotImplementedError("the CUDA path needs ch_in == 1 and filters[0] a multiple of 8")
 
     def _forward_maps(self, x):
         if self.training:
@@ -203,13 +203,21 @@ def frame_minmax(img, out=None, scratch=None):
     return out
 
 
+def _pad64(c):
+    return (int(c) + 63) // 64 * 64
+
+
 class _Engine:
     """Flat list of kernel launches for one network instance (eval mode)."""
 
     def __init__(self, net):
         self.L = nat.lib()
         self.net = net
-        self.chans = net._chans
+        # the tensor-core kernels work on 64-channel groups: narrower levels (the reference's low-memory fallbacks
+        # filters = [32, 512] / [32, 256], train.py:283-288) run zero-padded to 64 channels -- padded output channels
+        # get zero weights / bias / shift (act(0) = 0 for every supported activation) and padded input channels zero
+        # weight columns, so the real channels are unchanged
+        self.chans = [_pad64(c) for c in net._chans]
         self.act = _ACT_CODES[net.act_fun]
         self.device = next(net.parameters()).device
         if self.device.type != "cuda":
@@ -225,24 +233,53 @@ class _Engine:
         shift = (bn.bias.float() - bn.running_mean.float() * scale).contiguous()
         return scale, shift
 
-    def _pack_conv(self, name, conv, bn):
-        w = conv.weight.detach().float().contiguous()
-        cout, cin = w.shape[0], w.shape[1]
+    def _pad_vec(self, v, n, fill):
+        v = v.detach().float()
+        if v.numel() == n:
+            return v.contiguous()
+        out = torch.full((n,), float(fill), dtype=torch.float32, device=self.device)
+        out[:v.numel()] = v
+        return out
+
+    def _pack_conv(self, name, conv, bn, in_parts=None):
+        """in_parts: real channel counts of the concatenated sources (each is padded to 64 separately)"""
+        w = conv.weight.detach().float()
+        cout_r, cin_r = w.shape[0], w.shape[1]
+        in_parts = in_parts or [cin_r]
+        cout = _pad64(cout_r)
+        cin = cin_r if cin_r == 1 else sum(_pad64(c) for c in in_parts)
+        if cout != cout_r or cin != cin_r:
+            wp = torch.zeros((cout, cin, 3, 3), dtype=torch.float32, device=self.device)
+            src = dst = 0
+            for c in in_parts:
+                wp[:cout_r, dst:dst + c] = w[:, src:src + c]
+                src += c
+                dst += c if cin_r == 1 else _pad64(c)
+            w = wp
+        w = w.contiguous()
         if cin == 1:
             packed = w.reshape(cout, 9).contiguous()
         else:
             packed = torch.empty((cout, 9, cin), dtype=torch.bfloat16, device=self.device)
             nat.check(self.L.mbs_pack_conv3x3_weight(w.data_ptr(), cout, cin, packed.data_ptr(), nat.stream_ptr()))
         scale, shift = self._affine(bn)
-        self.p[name] = (packed, conv.bias.detach().float().contiguous(), scale, shift, cin, cout)
+        self.p[name] = (packed, self._pad_vec(conv.bias, cout, 0.0), self._pad_vec(scale, cout, 1.0),
+                        self._pad_vec(shift, cout, 0.0), cin, cout)
 
     def _pack_convT(self, name, block):
-        w = block.up[0].weight.detach().float().contiguous()   # [Cin, Cout, 2, 2]
-        cin, cout = w.shape[0], w.shape[1]
+        w = block.up[0].weight.detach().float()   # [Cin, Cout, 2, 2]
+        cin_r, cout_r = w.shape[0], w.shape[1]
+        cin, cout = _pad64(cin_r), _pad64(cout_r)
+        if cin != cin_r or cout != cout_r:
+            wp = torch.zeros((cin, cout, 2, 2), dtype=torch.float32, device=self.device)
+            wp[:cin_r, :cout_r] = w
+            w = wp
+        w = w.contiguous()
         packed = torch.empty((4 * cout, cin), dtype=torch.bfloat16, device=self.device)
         nat.check(self.L.mbs_pack_convT2x2_weight(w.data_ptr(), cin, cout, packed.data_ptr(), nat.stream_ptr()))
         scale, shift = self._affine(block.norm)
-        self.p[name] = (packed, block.up[0].bias.detach().float().contiguous(), scale, shift, cin, cout)
+        self.p[name] = (packed, self._pad_vec(block.up[0].bias, cout, 0.0), self._pad_vec(scale, cout, 1.0),
+                        self._pad_vec(shift, cout, 0.0), cin, cout)
 
     def _pack(self):
         net = self.net
@@ -255,13 +292,18 @@ class _Engine:
             ups, convs = getattr(net, name + "Upconv"), getattr(net, name + "Conv")
             for i, up in enumerate(ups):
                 self._pack_convT(f"{name}up{i}", up)
-                self._pack_conv(f"{name}c{i}a", convs[i].conv[0], convs[i].conv[2])
+                half = convs[i].conv[0].weight.shape[1] // 2             # cat([up, skip], 1): two equal parts
+                self._pack_conv(f"{name}c{i}a", convs[i].conv[0], convs[i].conv[2], in_parts=[half, half])
                 self._pack_conv(f"{name}c{i}b", convs[i].conv[3], convs[i].conv[5])
             head = convs[len(ups)]
             if head.weight.shape[0] > 4:
                 raise NotImplementedError("the fused 1x1 head supports at most 4 output channels")
-            self.p[name + "head"] = (head.weight.detach().float().reshape(head.weight.shape[0], -1).contiguous(),
-                                     [float(b) for b in head.bias.detach().float().cpu()])
+            hw = head.weight.detach().float().reshape(head.weight.shape[0], -1)
+            if hw.shape[1] != self.chans[0]:
+                hp = torch.zeros((hw.shape[0], self.chans[0]), dtype=torch.float32, device=self.device)
+                hp[:, :hw.shape[1]] = hw
+                hw = hp
+            self.p[name + "head"] = (hw.contiguous(), [float(b) for b in head.bias.detach().float().cpu()])
 
     # -- buffers -------------------------------------------------------------------------------
     def _buf(self, name, shape, dtype=torch.bfloat16):

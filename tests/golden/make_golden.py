@@ -34,7 +34,7 @@ def make_postproc():
         print("postproc", H, W, seed, "objects", int(out.max()))
 
 
-def make_net():
+def make_net(only=None):
     import importlib.util
     import torch
     # the real reference module, loaded by path (this repo also has a drop-in `src` package)
@@ -46,7 +46,11 @@ def make_net():
     torch.set_grad_enabled(False)
     for tag, filters, act, H, W, seed in [("f64-128_relu", (64, 128), "relu", 64, 64, 21),
                                           ("f64-256_mish", (64, 256), "mish", 48, 80, 22),
-                                          ("f64-1024_relu", (64, 1024), "relu", 64, 64, 23)]:
+                                          ("f64-1024_relu", (64, 1024), "relu", 64, 64, 23),
+                                          # the reference's low-memory fallback architecture (train.py:283-285)
+                                          ("f32-512_relu", (32, 512), "relu", 64, 96, 24)]:
+        if only and tag not in only:
+            continue
         ref = build_unet("DU", act, "conv", "bn", torch.device("cpu"), 1, ch_in=1, ch_out=1, filters=list(filters))
         sd = onet.seeded_state_dict(ref.state_dict(), seed)
         ref.load_state_dict(sd)
@@ -124,6 +128,6 @@ if __name__ == "__main__":
     if "postproc" in what:
         make_postproc()
     if "net" in what:
-        make_net()
+        make_net([a[4:] for a in what if a.startswith("net:")] or None)
     if "labels" in what:
         make_labels()

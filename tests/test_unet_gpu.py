@@ -277,6 +277,28 @@ def test_full_size_frame_is_consistent_across_kernel_paths(native_lib):
     assert native_lib.mbs_debug_flags(1) == 0
 
 
+def test_narrow_fallback_architectures_run_zero_padded(native_lib):
+    """filters = [32, 512] / [32, 256] (the reference's out-of-memory fallbacks, train.py:283-288): 32-channel levels
+    run zero-padded to 64 channels; results vs the fp32 oracle, frame path == drop-in path, bad filters rejected"""
+    from microbeseg_b200.unets import build_unet
+    torch.set_grad_enabled(False)
+    for filters, act, seed in (((32, 256), "mish", 91), ((32, 512), "relu", 92)):
+        net, sd = _build(filters, act, seed)
+        rng = np.random.default_rng(seed)
+        img = rng.integers(0, 60000, (48, 64)).astype(np.uint16)
+        x = torch.from_numpy(_norm(img)[None, None])
+        ob, oc = onet.dunet_forward(sd, x, act)
+        b, c = net(x.cuda())
+        _check(b[0, 0].cpu().numpy(), ob[0, 0].numpy(), f"{filters} border")
+        _check(c[0, 0].cpu().numpy(), oc[0, 0].numpy(), f"{filters} cell")
+        dev = torch.from_numpy(img.view(np.int16)).cuda()
+        b2, c2 = net.forward_frame(dev, [0, 0], float(img.min()), float(img.max()))
+        assert torch.equal(b, b2) and torch.equal(c, c2)
+    with pytest.raises(NotImplementedError):
+        build_unet("DU", "relu", "conv", "bn", torch.device("cuda:0"), 1, filters=[20, 80]).eval()(x.cuda())
+    assert native_lib.mbs_debug_flags(1) == 0
+
+
 def test_single_decoder_unet_with_three_channel_head(native_lib):
     """'U' architecture with ch_out=3 (boundary method, unets.py:267-377): fused 3-output 1x1 head."""
     from microbeseg_b200.unets import build_unet
