@@ -720,7 +720,7 @@ extern "C" size_t mbs_labels_workspace_bytes(int n_crops, int H, int W, int max_
     const size_t ids = static_cast<size_t>(max_id) + 1;
     return r256(n_crops * ids * sizeof(CellStats)) + r256(n_crops * sizeof(CropInfo)) +
            r256(static_cast<size_t>(n_crops) * kMaxGaps * sizeof(GapStats)) + 2 * r256(px * 8) /*nraw, scaled*/ +
-           4 * r256(px) /*label_bin, dil, gap, border*/ + 2 * r256(px * 4) /*L, gid*/ +
+           2 * r256(px) /*gap, border*/ + 2 * r256(px * 4) /*L, gid*/ +
            2 * r256(static_cast<size_t>(n_crops) * H * ((W + 63) / 64) * 8) /*label_bin, dil as bit images*/ +
            r256((n_crops * ids + 1) * sizeof(int)) /*oversized-instance list*/ + 4096;
 }
@@ -765,8 +765,6 @@ extern "C" int mbs_distance_labels(const uint16_t *masks, int n_crops, int H, in
     GapStats *gs = reinterpret_cast<GapStats *>(take(static_cast<size_t>(n_crops) * kMaxGaps * sizeof(GapStats)));
     double *nraw = reinterpret_cast<double *>(take(px * 8));
     double *scaled = reinterpret_cast<double *>(take(px * 8));
-    uint8_t *label_bin = reinterpret_cast<uint8_t *>(take(px));
-    uint8_t *dil = reinterpret_cast<uint8_t *>(take(px));
     uint8_t *gap = reinterpret_cast<uint8_t *>(take(px));
     uint8_t *border = reinterpret_cast<uint8_t *>(take(px));
     int *L = reinterpret_cast<int *>(take(px * 4));
@@ -776,8 +774,6 @@ extern "C" int mbs_distance_labels(const uint16_t *masks, int n_crops, int H, in
     unsigned long long *lbits = reinterpret_cast<unsigned long long *>(take(bit_bytes));
     unsigned long long *dbits = reinterpret_cast<unsigned long long *>(take(bit_bytes));
     int *big_list = reinterpret_cast<int *>(take((static_cast<size_t>(n_crops) * ids + 1) * sizeof(int)));
-    (void)label_bin;
-    (void)dil;
 
     const int total = n_crops * ids;
     dim3 b2(32, 8), g3(mbs::cdiv(W, 32), mbs::cdiv(H, 8), n_crops);
