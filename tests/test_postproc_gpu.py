@@ -246,3 +246,42 @@ def test_boundary_postprocessing_vs_oracle(pp):
         assert out.dtype == np.uint16 and np.array_equal(out, ref)
         if cells:
             assert out.max() >= cells // 2
+
+
+def test_operators_run_from_worker_threads(native_lib):
+    """the reference calls the operators from Qt worker threads (one inference at a time per process,
+    microbe_seg_gui.py:1566-1596) -- no thread-local CUDA state may be assumed.  Two Python threads alternate calls to
+    the network and the post-processing; every result must equal the main-thread result."""
+    import threading
+    from microbeseg_b200 import postprocessing as pp, synthetic as sy
+    from microbeseg_b200.unets import build_unet
+    torch.set_grad_enabled(False)
+    torch.manual_seed(0)
+    net = build_unet("DU", "relu", "conv", "bn", torch.device("cuda:0"), 1, filters=[64, 128]).eval()
+    x = torch.rand(1, 1, 64, 64).cuda() * 2 - 1
+    ref_maps = [t.clone() for t in net(x)]
+    m = sy.synth_instance_mask(128, 128, 30, 77)
+    border, cell = sy.synth_distance_maps(m, 78)
+    ref_mask = pp.distance_postprocessing(border, cell, 0.45, 0.10)
+    errors = []
+    lock = threading.Lock()           # the reference runs one worker at a time (is_ready() gate); calls alternate
+
+    def worker(k):
+        try:
+            torch.set_grad_enabled(False)          # grad mode is thread-local in torch
+            for _ in range(3):
+                with lock:
+                    b, c = net(x)
+                    got = pp.distance_postprocessing(border_prediction=border, cell_prediction=cell, th_seed=0.45, th_cell=0.10)
+                    ok = torch.equal(b, ref_maps[0]) and torch.equal(c, ref_maps[1]) and np.array_equal(got, ref_mask)
+                if not ok:
+                    errors.append(k)
+        except Exception as e:                     # noqa: BLE001
+            errors.append(repr(e))
+
+    threads = [threading.Thread(target=worker, args=(k,)) for k in range(2)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
