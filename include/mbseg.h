@@ -157,6 +157,10 @@ int mbs_bn_train_bwd(const void *dy, const void *a, long long M, int C, const fl
 /* Conv2d(C,1,1) head, SmoothL1Loss(beta=1,'mean') (losses.py:30-32) and their gradients */
 int mbs_head_fwd(const void *y, long long M, int C, const float *w, const float *b_dev, float *pred, void *stream);
 int mbs_smoothl1(const float *pred, const float *target, long long M, float *loss_accum, float *grad, void *stream);
+/* the three distance-method criteria of get_loss (losses.py:24-35), reduction 'mean': kind 0 smooth_l1, 1 l1, 2 l2;
+ * *loss_accum += loss (zeroed by the caller), grad = dloss/dpred */
+int mbs_regression_loss(const float *pred, const float *target, long long M, int kind, float *loss_accum, float *grad,
+                        void *stream);
 int mbs_head_bwd(const float *g, const void *y, long long M, int C, const float *w, void *dy, float *dw_db, void *stream);
 /* layout / glue kernels of the backward pass */
 /* data-gradient filter of a 3x3 conv: packed[ci][tap][co] = bf16(w[co][ci][8 - tap]) from the reference-layout weight */

@@ -321,9 +321,11 @@ __global__ void head_fwd_kernel(const __nv_bfloat16 *__restrict__ y, long long M
     pred[p] = acc + b[0];
 }
 
-// SmoothL1Loss(beta = 1, reduction = 'mean'): loss += sum / M;  g = clamp(pred - target, -1, 1) / M
+// The distance-method criteria of losses.py:24-35 with reduction 'mean': loss += sum / M and g = dloss/dpred.
+//   kind 0 SmoothL1Loss (beta = 1): g = clamp(d, -1, 1) / M;  1 L1Loss: g = sign(d) / M;  2 MSELoss: g = 2 d / M
 __global__ void __launch_bounds__(256)
-smoothl1_kernel(const float *__restrict__ pred, const float *__restrict__ target, long long M, float *loss, float *__restrict__ g) {
+smoothl1_kernel(const float *__restrict__ pred, const float *__restrict__ target, long long M, float *loss, float *__restrict__ g,
+                int kind) {
     __shared__ float s_part[8];
     float acc = 0.0f;
     const float invM = 1.0f / static_cast<float>(M);
@@ -331,8 +333,16 @@ smoothl1_kernel(const float *__restrict__ pred, const float *__restrict__ target
          p += static_cast<long long>(gridDim.x) * blockDim.x) {
         const float d = pred[p] - target[p];
         const float ad = fabsf(d);
-        acc += ad < 1.0f ? 0.5f * d * d : ad - 0.5f;
-        g[p] = fminf(fmaxf(d, -1.0f), 1.0f) * invM;
+        if (kind == 0) {
+            acc += ad < 1.0f ? 0.5f * d * d : ad - 0.5f;
+            g[p] = fminf(fmaxf(d, -1.0f), 1.0f) * invM;
+        } else if (kind == 1) {
+            acc += ad;
+            g[p] = (d > 0.0f ? 1.0f : (d < 0.0f ? -1.0f : 0.0f)) * invM;       // torch: sign(0) = 0
+        } else {
+            acc += d * d;
+            g[p] = 2.0f * d * invM;
+        }
     }
     acc = warp_sum(acc);
     if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = acc;
@@ -574,9 +584,14 @@ extern "C" int mbs_head_fwd(const void *y, long long M, int C, const float *w, c
 }
 
 extern "C" int mbs_smoothl1(const float *pred, const float *target, long long M, float *loss_accum, float *grad, void *stream_) {
+    return mbs_regression_loss(pred, target, M, 0, loss_accum, grad, stream_);
+}
+
+extern "C" int mbs_regression_loss(const float *pred, const float *target, long long M, int kind, float *loss_accum, float *grad,
+                                   void *stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-    MBS_REQUIRE(M > 0, "smoothl1: bad shape");
-    smoothl1_kernel<<<grid_for(M, 256 * 8, 148 * 8), 256, 0, stream>>>(pred, target, M, loss_accum, grad);
+    MBS_REQUIRE(M > 0 && kind >= 0 && kind <= 2, "regression_loss: bad shape / kind");
+    smoothl1_kernel<<<grid_for(M, 256 * 8, 148 * 8), 256, 0, stream>>>(pred, target, M, loss_accum, grad, kind);
     MBS_CHECK_LAUNCH();
     return 0;
 }

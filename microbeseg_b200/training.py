@@ -19,6 +19,7 @@ from . import _native as nat
 BN_EPS = 1e-5
 BN_MOMENTUM = 0.1
 ACT_NONE, ACT_RELU, ACT_MISH = 0, 1, 4
+_LOSS_KINDS = {'smooth_l1': 0, 'l1': 1, 'l2': 2}      # get_loss(loss_function, 'distance'), losses.py:24-35
 
 
 class _Layer:
@@ -28,7 +29,7 @@ class _Layer:
 class TrainEngine:
     """Forward + backward of one DUNet on one GPU; fills ``param.grad`` (fp32) for every parameter."""
 
-    def __init__(self, net, use_graph=True):
+    def __init__(self, net, use_graph=True, loss='smooth_l1'):
         from .unets import DUNet
         if not isinstance(net, DUNet):
             raise NotImplementedError("training is built for the DU (distance) network")
@@ -43,6 +44,9 @@ class TrainEngine:
         # evaluates mish'(z) -- still one activation-sized tensor per layer
         self.act = ACT_RELU if net.act_fun == "relu" else ACT_MISH
         self.conv_act = ACT_RELU if net.act_fun == "relu" else ACT_NONE
+        if loss not in _LOSS_KINDS:
+            raise Exception('Loss unknown')                 # get_loss, losses.py:33-34
+        self.loss_kind = _LOSS_KINDS[loss]
         self.net = net
         self.L = nat.lib()
         self.dev = next(net.parameters()).device
@@ -254,8 +258,8 @@ class TrainEngine:
             for pred, tgt in zip(preds, targets):
                 g = torch.empty_like(pred)
                 t = tgt.reshape(n, H, W).contiguous().float()
-                nat.check(self.L.mbs_smoothl1(pred.data_ptr(), t.data_ptr(), n * H * W, loss.data_ptr(), g.data_ptr(), self._sp()),
-                          "smoothl1")
+                nat.check(self.L.mbs_regression_loss(pred.data_ptr(), t.data_ptr(), n * H * W, self.loss_kind, loss.data_ptr(),
+                                                     g.data_ptr(), self._sp()), "regression_loss")
                 gpred.append(g)
             # ---------------- backward ----------------
             skip_grads = [[] for _ in range(nl)]          # contributions to d(skip_l)

@@ -176,7 +176,7 @@ def _conv_block_train(x, sd, prefix, act="relu"):
     return _bn_train(_act(F.conv2d(x, sd[prefix + ".conv.3.weight"], sd[prefix + ".conv.3.bias"], padding=1), act), sd, prefix + ".conv.5")
 
 
-def dunet_train_loss(params, x, border_label, cell_label, act="relu"):
+def dunet_train_loss(params, x, border_label, cell_label, act="relu", loss="smooth_l1"):
     """params: dict name -> tensor (requires_grad where wanted).  Returns the scalar loss."""
     nl = n_levels(params)
     skips = []
@@ -196,5 +196,5 @@ def dunet_train_loss(params, x, border_label, cell_label, act="relu"):
             y = _conv_block_train(torch.cat([y, s], 1), params, f"{name}Conv.{i}", act)
         k = len(skips)
         outs.append(F.conv2d(y, params[f"{name}Conv.{k}.weight"], params[f"{name}Conv.{k}.bias"]))
-    crit = torch.nn.SmoothL1Loss()
+    crit = {'smooth_l1': torch.nn.SmoothL1Loss, 'l1': torch.nn.L1Loss, 'l2': torch.nn.MSELoss}[loss]()      # losses.py:24-35
     return crit(outs[0], border_label) + crit(outs[1], cell_label)

@@ -171,3 +171,24 @@ def test_ranger_mish_recipe_reduces_the_loss(native_lib):
     assert all(np.isfinite(losses)) and losses[-1] < 0.7 * losses[0], losses
     assert opt.launches_last_step == 1
     assert native_lib.mbs_debug_flags(1) == 0
+
+
+@pytest.mark.parametrize("loss", ["l1", "l2"])
+def test_other_distance_criteria(native_lib, loss):
+    """get_loss(loss_function, 'distance') also offers l1 / l2 (losses.py:24-29): loss value and head-bias gradients"""
+    from microbeseg_b200.training import TrainEngine
+    net, sd, _, img, bl, cl = _setup((64, 128), 11, 2, 32, 32)
+    eng = TrainEngine(net, use_graph=False, loss=loss)
+    got = float(eng.forward_backward(img, bl, cl))
+    params = {k: v.clone().cuda().requires_grad_(v.dtype.is_floating_point and "running" not in k) for k, v in sd.items()
+              if v.dtype.is_floating_point}
+    with torch.enable_grad():
+        ref = onet.dunet_train_loss(params, img, bl, cl, "relu", loss)
+        ref.backward()
+    assert abs(got - float(ref.detach())) <= 2e-2 * abs(float(ref.detach())), (got, float(ref.detach()))
+    for name, p in net.named_parameters():
+        if name.endswith("Conv.2.bias"):            # the two 1x1 heads: gradient = sum of dloss/dpred
+            r = params[name].grad
+            assert torch.allclose(p.grad, r, rtol=0.1, atol=0.05 * float(r.abs().max()) + 1e-4), (name, p.grad, r)
+    with pytest.raises(Exception):
+        TrainEngine(net, loss="ce")
