@@ -167,6 +167,8 @@ int mbs_head_bwd(const float *g, const void *y, long long M, int C, const float 
 int mbs_pack_conv3x3_dgrad(const float *w, int Cout, int Cin, void *packed, void *stream);
 /* weight gradient g[co][tap][ci] (mbs_conv_wgrad layout) -> reference layout out[co][ci][3][3] */
 int mbs_unpack_conv3x3_grad(const float *g, int Cout, int Cin, float *out, void *stream);
+/* nn.MaxPool2d(2, 2) on contiguous NHWC bf16 (build_unet pool_method = 'max', unets.py:306-307,363-364) */
+int mbs_maxpool2x2(const void *src, int N, int H, int W, int C, void *dst, void *stream);
 int mbs_zero_insert_up2(const void *src, int N, int H, int W, int C, void *dst, void *stream);
 int mbs_add3_bf16(const void *a, const void *b, const void *c, long long n, void *out, void *stream);
 int mbs_first_conv_wgrad(const float *x, const void *dz, int N, int H, int W, int C, float *dw, void *stream);

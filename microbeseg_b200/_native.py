@@ -73,6 +73,7 @@ _SIGS = {
     "mbs_smoothl1": (c_int, [c_void_p, c_void_p, ctypes.c_longlong, c_void_p, c_void_p, c_void_p]),
     "mbs_regression_loss": (c_int, [c_void_p, c_void_p, ctypes.c_longlong, c_int, c_void_p, c_void_p, c_void_p]),
     "mbs_head_bwd": (c_int, [c_void_p, c_void_p, ctypes.c_longlong, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "mbs_maxpool2x2": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "mbs_zero_insert_up2": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "mbs_add3_bf16": (c_int, [c_void_p, c_void_p, c_void_p, ctypes.c_longlong, c_void_p, c_void_p]),
     "mbs_first_conv_wgrad": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),

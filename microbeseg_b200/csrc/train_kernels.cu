@@ -425,6 +425,30 @@ __global__ void __launch_bounds__(256) unpack_grad3x3_kernel(const float *__rest
     for (int i = threadIdx.x; i < n * 9; i += 256) out[(static_cast<size_t>(co) * Cin + ci0) * 9 + i] = tile[i % 9][i / 9];
 }
 
+// nn.MaxPool2d(kernel_size=2, stride=2) on NHWC bf16 (pool_method = 'max', unets.py:306-307,363-364): 8 channels per thread
+__global__ void maxpool2x2_kernel(const __nv_bfloat16 *__restrict__ src, int N, int H, int W, int C, __nv_bfloat16 *__restrict__ dst) {
+    const long long i = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) * 8;
+    const int Ho = H / 2, Wo = W / 2;
+    const long long total = static_cast<long long>(N) * Ho * Wo * C;
+    if (i >= total) return;
+    const int c = static_cast<int>(i % C);
+    long long t = i / C;
+    const int x = static_cast<int>(t % Wo);
+    t /= Wo;
+    const int y = static_cast<int>(t % Ho);
+    const int n = static_cast<int>(t / Ho);
+    const __nv_bfloat16 *p = src + ((static_cast<size_t>(n) * H + 2 * y) * W + 2 * x) * C + c;
+    const uint4 a = *reinterpret_cast<const uint4 *>(p), b = *reinterpret_cast<const uint4 *>(p + C);
+    const uint4 d = *reinterpret_cast<const uint4 *>(p + static_cast<size_t>(W) * C), e = *reinterpret_cast<const uint4 *>(p + static_cast<size_t>(W) * C + C);
+    uint4 o;
+    const __nv_bfloat162 *pa = reinterpret_cast<const __nv_bfloat162 *>(&a), *pb = reinterpret_cast<const __nv_bfloat162 *>(&b);
+    const __nv_bfloat162 *pd = reinterpret_cast<const __nv_bfloat162 *>(&d), *pe = reinterpret_cast<const __nv_bfloat162 *>(&e);
+    __nv_bfloat162 *po = reinterpret_cast<__nv_bfloat162 *>(&o);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) po[j] = __hmax2_nan(__hmax2_nan(pa[j], pb[j]), __hmax2_nan(pd[j], pe[j]));     // NaN propagates like torch
+    *reinterpret_cast<uint4 *>(dst + i) = o;
+}
+
 // U[n][2y][2x][c] = src[n][y][x][c], zeros elsewhere (input of the stride-2 conv's data gradient)
 __global__ void zero_insert_kernel(const __nv_bfloat16 *__restrict__ src, int N, int H, int W, int C, __nv_bfloat16 *__restrict__ dst) {
     const long long i = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) * 8;   // 8 channels (16 B) per thread
@@ -620,6 +644,16 @@ extern "C" int mbs_unpack_conv3x3_grad(const float *g, int Cout, int Cin, float 
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     MBS_REQUIRE(g && out && Cout > 0 && Cin > 0, "unpack_conv3x3_grad: bad arguments");
     unpack_grad3x3_kernel<<<dim3(Cout, mbs::cdiv(Cin, 256)), 256, 0, stream>>>(g, Cin, out);
+    MBS_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int mbs_maxpool2x2(const void *src, int N, int H, int W, int C, void *dst, void *stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    MBS_REQUIRE(src && dst && N > 0 && H > 0 && W > 0 && H % 2 == 0 && W % 2 == 0 && C > 0 && C % 8 == 0, "maxpool2x2: bad shape");
+    const long long total = static_cast<long long>(N) * (H / 2) * (W / 2) * C;
+    maxpool2x2_kernel<<<static_cast<int>((total / 8 + 255) / 256), 256, 0, stream>>>(static_cast<const __nv_bfloat16 *>(src), N, H, W, C,
+                                                                                    static_cast<__nv_bfloat16 *>(dst));
     MBS_CHECK_LAUNCH();
     return 0;
 }

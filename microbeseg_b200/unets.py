@@ -129,9 +129,9 @@ class _NetBase(nn.Module):
         return self._engine
 
     def _check_supported(self):
-        if self.pool_method != 'conv' or self.normalization != 'bn':
+        if self.pool_method not in ('conv', 'max') or self.normalization != 'bn':
             raise NotImplementedError(
-                "the CUDA path covers the published configuration (pool 'conv', normalization 'bn'); got "
+                "the CUDA path covers pool_method 'conv' (published) / 'max' and normalization 'bn'; got "
                 f"pool_method={self.pool_method!r}, normalization={self.normalization!r}")
         if self.ch_in != 1 or self._chans[0] % 8 != 0:
             raise NotImplementedError("the CUDA path needs ch_in == 1 and filters[0] a multiple of 8")
@@ -286,8 +286,9 @@ class _Engine:
         for i, blk in enumerate(net.encoderConv):
             self._pack_conv(f"enc{i}a", blk.conv[0], blk.conv[2])
             self._pack_conv(f"enc{i}b", blk.conv[3], blk.conv[5])
-        for i, pl in enumerate(net.pooling):
-            self._pack_conv(f"pool{i}", pl.conv_pool[0], pl.conv_pool[2])
+        if net.pool_method == 'conv':
+            for i, pl in enumerate(net.pooling):
+                self._pack_conv(f"pool{i}", pl.conv_pool[0], pl.conv_pool[2])
         for name in net.decoder_names:
             ups, convs = getattr(net, name + "Upconv"), getattr(net, name + "Conv")
             for i, up in enumerate(ups):
@@ -380,7 +381,11 @@ class _Engine:
                     self._conv(0, f"enc{l}a", n, H >> l, W >> l, pool[l - 1], None, t1[l])
                 self._conv(0, f"enc{l}b", n, H >> l, W >> l, t1[l], None, skip[l])
                 if l < nl - 1:
-                    self._conv(1, f"pool{l}", n, H >> l, W >> l, skip[l], None, pool[l])
+                    if self.net.pool_method == 'max':          # nn.MaxPool2d(2, 2), unets.py:363-364
+                        nat.check(self.L.mbs_maxpool2x2(skip[l].data_ptr(), n, H >> l, W >> l, ch[l], pool[l].data_ptr(),
+                                                        nat.stream_ptr()), "maxpool2x2")
+                    else:
+                        self._conv(1, f"pool{l}", n, H >> l, W >> l, skip[l], None, pool[l])
             outs = []
             for name in self.net.decoder_names:
                 x = skip[nl - 1]

@@ -61,7 +61,10 @@ def encoder(sd, x, act):
     for i in range(nl - 1):
         x = _conv_block(x, sd, f"encoderConv.{i}", act)
         skips.append(x)
-        x = _conv_pool(x, sd, f"pooling.{i}", act)
+        if f"pooling.{i}.conv_pool.0.weight" in sd:
+            x = _conv_pool(x, sd, f"pooling.{i}", act)
+        else:                                      # pool_method 'max': nn.MaxPool2d(2, 2) has no parameters (unets.py:306-307)
+            x = F.max_pool2d(x, kernel_size=2, stride=2)
     x = _conv_block(x, sd, f"encoderConv.{nl - 1}", act)
     return x, skips[::-1]
 
@@ -121,7 +124,7 @@ def seeded_state_dict(template, seed):
     return out
 
 
-def reference_layout_template(unet_type="DU", filters=(64, 1024), ch_in=1, ch_out=1):
+def reference_layout_template(unet_type="DU", filters=(64, 1024), ch_in=1, ch_out=1, pool_method="conv"):
     """Shapes of a reference state dict without importing the reference."""
     t = {}
 
@@ -146,8 +149,9 @@ def reference_layout_template(unet_type="DU", filters=(64, 1024), ch_in=1, ch_ou
     for i, c in enumerate(chans):
         block(f"encoderConv.{i}", ch_in if i == 0 else chans[i - 1], c)
     for i, c in enumerate(chans[:-1]):
-        conv(f"pooling.{i}.conv_pool.0", c, c, 3)
-        bn(f"pooling.{i}.conv_pool.2", c)
+        if pool_method == "conv":                  # nn.MaxPool2d has no parameters
+            conv(f"pooling.{i}.conv_pool.0", c, c, 3)
+            bn(f"pooling.{i}.conv_pool.2", c)
     names = ["decoder1", "decoder2"] if unet_type == "DU" else ["decoder"]
     for name in names:
         rc = chans[::-1]

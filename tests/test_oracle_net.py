@@ -27,7 +27,8 @@ def test_oracle_matches_reference_goldens():
     for f in files:
         g = np.load(f)
         filters, act, seed = tuple(int(v) for v in g["filters"]), str(g["act"]), int(g["seed"])
-        sd = onet.seeded_state_dict(onet.reference_layout_template("DU", filters), seed)
+        pool = str(g["pool"]) if "pool" in g.files else "conv"
+        sd = onet.seeded_state_dict(onet.reference_layout_template("DU", filters, pool_method=pool), seed)
         x = torch.from_numpy(normalise(g["img"])[None, None])
         border, cell = onet.dunet_forward(sd, x, act)
         # same math, same library (CPU fp32 conv) -> agreement to rounding noise

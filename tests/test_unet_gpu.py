@@ -21,10 +21,10 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 REL_MAX, REL_MEAN = 2.5e-2, 4e-3
 
 
-def _build(filters, act, seed):
+def _build(filters, act, seed, pool="conv"):
     from microbeseg_b200.unets import build_unet
-    net = build_unet("DU", act, "conv", "bn", torch.device("cuda:0"), 1, filters=list(filters))
-    sd = onet.seeded_state_dict(onet.reference_layout_template("DU", filters), seed)
+    net = build_unet("DU", act, pool, "bn", torch.device("cuda:0"), 1, filters=list(filters))
+    sd = onet.seeded_state_dict(onet.reference_layout_template("DU", filters, pool_method=pool), seed)
     net.load_state_dict(sd)
     return net.eval(), sd
 
@@ -49,7 +49,7 @@ def test_against_reference_goldens(native_lib):
     for f in files:
         g = np.load(f)
         filters, act, seed = tuple(int(v) for v in g["filters"]), str(g["act"]), int(g["seed"])
-        net, _ = _build(filters, act, seed)
+        net, _ = _build(filters, act, seed, str(g["pool"]) if "pool" in g.files else "conv")
         x = torch.from_numpy(_norm(g["img"])[None, None]).cuda()
         border, cell = net(x)
         assert border.shape == cell.shape == (1, 1) + g["img"].shape and border.dtype == torch.float32
