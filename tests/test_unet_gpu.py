@@ -124,6 +124,8 @@ CONV_CASES = [
     (2, 1, 40, 56, 128, 0, 64), (2, 1, 24, 40, 256, 0, 128), (2, 2, 12, 16, 128, 0, 64),
     # full-resolution halo kernel: single and dual source, ragged
     (0, 1, 72, 100, 64, 0, 64), (0, 1, 48, 36, 64, 64, 64),
+    # many small images: paired tiles whose 16-row box is taller than the image, batch > 1 through the halo kernel
+    (0, 64, 8, 48, 128, 0, 128), (0, 40, 8, 24, 64, 0, 64), (1, 48, 16, 32, 128, 0, 128),
 ]
 
 
