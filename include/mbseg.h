@@ -154,6 +154,11 @@ int mbs_bn_train_fwd(const void *a, long long M, int C, const float *gamma, cons
  * scratch: mbs_bn_scratch_floats(C) floats. */
 int mbs_bn_train_bwd(const void *dy, const void *a, long long M, int C, const float *mean, const float *invstd,
                      const float *gamma, int act, void *dz, float *dgamma_dbeta, float *dbias, float *scratch, void *stream);
+/* nn.GroupNorm(groups, C) (normalization 'gn', groups = 8) / nn.InstanceNorm2d(C) ('in', groups = C, gamma = beta = NULL)
+ * of ONE sample in eval mode (unets.py:129-132,155-158,207-210,247-250): a, y = [M = H*W][C] bf16 (y may alias a),
+ * statistics over the sample's own pixels, biased variance.  scratch: mbs_bn_scratch_floats(C) floats. */
+int mbs_sample_group_norm(const void *a, long long M, int C, int groups, const float *gamma, const float *beta, float eps,
+                          void *y, float *scratch, void *stream);
 /* Conv2d(C,1,1) head, SmoothL1Loss(beta=1,'mean') (losses.py:30-32) and their gradients */
 int mbs_head_fwd(const void *y, long long M, int C, const float *w, const float *b_dev, float *pred, void *stream);
 int mbs_smoothl1(const float *pred, const float *target, long long M, float *loss_accum, float *grad, void *stream);

@@ -69,6 +69,8 @@ _SIGS = {
     "mbs_bn_train_bwd": (c_int, [c_void_p, c_void_p, ctypes.c_longlong, c_int, c_void_p, c_void_p, c_void_p, c_int,
                                  c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "mbs_bn_scratch_floats": (c_size_t, [c_int]),
+    "mbs_sample_group_norm": (c_int, [c_void_p, ctypes.c_longlong, c_int, c_int, c_void_p, c_void_p, c_float, c_void_p, c_void_p,
+                                      c_void_p]),
     "mbs_head_fwd": (c_int, [c_void_p, ctypes.c_longlong, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "mbs_smoothl1": (c_int, [c_void_p, c_void_p, ctypes.c_longlong, c_void_p, c_void_p, c_void_p]),
     "mbs_regression_loss": (c_int, [c_void_p, c_void_p, ctypes.c_longlong, c_int, c_void_p, c_void_p, c_void_p]),

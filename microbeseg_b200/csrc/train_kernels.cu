@@ -110,26 +110,29 @@ __device__ __forceinline__ void for_rows4x2(const __nv_bfloat16 *a, const __nv_b
 // BatchNorm layer); PARTIAL = false: atomicAdd into out[NACC][C].
 template <int NACC, bool PARTIAL = false>
 __device__ __forceinline__ void block_channel_atomic(float (&acc)[NACC][8], int C, int c0, float *out) {
-    // threads with the same c0 (same threadIdx.x % (C/8)) hold partials of the same channels
+    // threads with the same c0 (same threadIdx.x % (C/8)) hold partials of the same channels.  Every thread parks its
+    // partials in its own shared-memory row ([pixel slot][channel], 256 * 8 floats per accumulator) and the block sums
+    // the slots in a fixed order: no shared-memory atomics, so the result does not depend on warp scheduling.
     __shared__ float s_acc[NACC][2048];
     const int tpp = C / 8;                        // threads per pixel
-    for (int i = threadIdx.x; i < NACC * C; i += blockDim.x) (&s_acc[0][0])[(i / C) * 2048 + i % C] = 0.0f;
-    __syncthreads();
-    if (c0 < C) {
+    const int ppb = 256 / tpp;                    // pixel slots per block
+    const int slot = threadIdx.x / tpp;
+    __syncthreads();                              // callers may reuse this function's shared memory back to back
 #pragma unroll
-        for (int a = 0; a < NACC; ++a)
+    for (int a = 0; a < NACC; ++a)
 #pragma unroll
-            for (int j = 0; j < 8; ++j) atomicAdd(&s_acc[a][c0 + j], acc[a][j]);
-    }
+        for (int j = 0; j < 8; ++j)
+            if (slot < ppb) s_acc[a][slot * C + (c0 < C ? c0 : 0) + j] = c0 < C ? acc[a][j] : 0.0f;
     __syncthreads();
     for (int i = threadIdx.x; i < NACC * C; i += blockDim.x) {
         const int a = i / C, c = i % C;
+        float t = 0.0f;
+        for (int sl = 0; sl < ppb; ++sl) t += s_acc[a][sl * C + c];
         if (PARTIAL)
-            out[static_cast<size_t>(blockIdx.x) * NACC * C + i] = s_acc[a][c];
+            out[static_cast<size_t>(blockIdx.x) * NACC * C + i] = t;
         else
-            atomicAdd(&out[a * C + c], s_acc[a][c]);
+            atomicAdd(&out[a * C + c], t);
     }
-    (void)tpp;
 }
 
 template <bool MISH>
@@ -202,6 +205,36 @@ __global__ void bn_finalize_kernel(float *sums, long long M, int C, float eps, c
     const float k = gamma[c] * invstd[c];
     sums[c] = k;
     sums[C + c] = fmaf(-mean[c], k, beta[c]);
+}
+
+// GroupNorm(groups, C) / InstanceNorm2d(C) of ONE sample in eval mode (unets.py:129-132): statistics over the sample's own
+// M = H*W pixels and the C/groups channels of a group (groups == C: instance norm), biased variance, eps inside the
+// sqrt; gamma / beta optional (InstanceNorm2d's default has none).  Turns the per-channel sums into the affine of the
+// apply pass: sums[c] = gamma*invstd, sums[C+c] = beta - mean*gamma*invstd.
+__global__ void group_norm_finalize_kernel(float *sums, long long M, int C, int groups, float eps, const float *__restrict__ gamma,
+                                           const float *__restrict__ beta) {
+    extern __shared__ float s_grp[];          // [2][groups]
+    const int cpg = C / groups;
+    for (int g = threadIdx.x; g < groups; g += blockDim.x) {
+        double s1 = 0.0, s2 = 0.0;
+        for (int j = 0; j < cpg; ++j) {
+            s1 += static_cast<double>(sums[g * cpg + j]);
+            s2 += static_cast<double>(sums[C + g * cpg + j]);
+        }
+        const double cnt = static_cast<double>(M) * cpg;
+        const double m = s1 / cnt;
+        double var = s2 / cnt - m * m;
+        if (var < 0.0) var = 0.0;
+        s_grp[g] = static_cast<float>(m);
+        s_grp[groups + g] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        const int g = c / cpg;
+        const float k = (gamma ? gamma[c] : 1.0f) * s_grp[groups + g];
+        sums[c] = k;
+        sums[C + c] = fmaf(-s_grp[g], k, beta ? beta[c] : 0.0f);
+    }
 }
 
 // y = a * scale + shift with the row-vectorised mapping (8 channels per thread, affine in registers)
@@ -566,6 +599,24 @@ extern "C" int mbs_bn_train_fwd(const void *a, long long M, int C, const float *
     else
         bn_apply_kernel<false><<<grid, 256, 0, stream>>>(static_cast<const __nv_bfloat16 *>(a), M, C, sums_scratch,
                                                          static_cast<__nv_bfloat16 *>(y));
+    MBS_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int mbs_sample_group_norm(const void *a, long long M, int C, int groups, const float *gamma, const float *beta, float eps,
+                                     void *y, float *scratch, void *stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    MBS_REQUIRE(a && y && scratch && M > 0 && C >= 8 && C % 8 == 0 && C <= 2048 && 256 % (C / 8) == 0 && groups > 0 && C % groups == 0,
+                "sample_group_norm: bad shape (C must be 8*2^k <= 2048 and divisible by groups)");
+    const int grid = grid_rows(M, C);
+    float *part = scratch + 2 * C;
+    bn_stats_kernel<false><<<grid, 256, 0, stream>>>(static_cast<const __nv_bfloat16 *>(a), M, C, part);
+    MBS_CHECK_LAUNCH();
+    reduce_partials_kernel<<<mbs::cdiv(2 * C, 32), 256, 0, stream>>>(part, grid, 2 * C, scratch);
+    MBS_CHECK_LAUNCH();
+    group_norm_finalize_kernel<<<1, 256, 2 * groups * sizeof(float), stream>>>(scratch, M, C, groups, eps, gamma, beta);
+    MBS_CHECK_LAUNCH();
+    bn_apply_kernel<false><<<grid, 256, 0, stream>>>(static_cast<const __nv_bfloat16 *>(a), M, C, scratch, static_cast<__nv_bfloat16 *>(y));
     MBS_CHECK_LAUNCH();
     return 0;
 }

@@ -34,8 +34,9 @@ class TrainEngine:
         if not isinstance(net, DUNet):
             raise NotImplementedError("training is built for the DU (distance) network")
         net._check_supported()
-        if net._chans[0] % 64 != 0 or net.pool_method != 'conv':
-            raise NotImplementedError("the CUDA training step needs filters[0] % 64 == 0 and pool_method 'conv'")
+        if net._chans[0] % 64 != 0 or net.pool_method != 'conv' or net.normalization != 'bn':
+            raise NotImplementedError("the CUDA training step needs filters[0] % 64 == 0, pool_method 'conv' and normalization "
+                                      "'bn' (what the reference's TrainWorker builds, train.py:184-188)")
         if net.act_fun not in ("relu", "mish"):
             raise NotImplementedError("training on the CUDA path supports act_fun='relu' (Adam recipe) and 'mish' "
                                       "(Ranger recipe), the two the reference trains with (train.py:174)")

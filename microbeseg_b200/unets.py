@@ -129,12 +129,14 @@ class _NetBase(nn.Module):
         return self._engine
 
     def _check_supported(self):
-        if self.pool_method not in ('conv', 'max') or self.normalization != 'bn':
+        if self.pool_method not in ('conv', 'max') or self.normalization not in ('bn', 'gn', 'in'):
             raise NotImplementedError(
-                "the CUDA path covers pool_method 'conv' (published) / 'max' and normalization 'bn'; got "
+                "the CUDA path covers pool_method 'conv' / 'max' and normalization 'bn' / 'gn' / 'in'; got "
                 f"pool_method={self.pool_method!r}, normalization={self.normalization!r}")
         if self.ch_in != 1 or self._chans[0] % 8 != 0:
             raise NotImplementedError("the CUDA path needs ch_in == 1 and filters[0] a multiple of 8")
+        if self.normalization != 'bn' and self._chans[0] % 64 != 0:
+            raise NotImplementedError("group / instance normalisation needs filters[0] to be a multiple of 64")
 
     def _forward_maps(self, x):
         if self.training:
@@ -224,14 +226,41 @@ class _Engine:
             raise RuntimeError("microbeseg_b200: move the network to a CUDA device first (no CPU fallback)")
         self.bufs = {}
         self.p = {}
+        self.norms = {}        # layer name -> (groups, gamma, beta, eps) for the per-sample normalisations ('gn' / 'in')
+        self._norm_scratch = None
         with torch.no_grad(), torch.cuda.device(self.device):
             self._pack()
 
     # -- parameter packing ---------------------------------------------------------------------
-    def _affine(self, bn):
-        scale = (bn.weight.float() / torch.sqrt(bn.running_var.float() + BN_EPS)).contiguous()
-        shift = (bn.bias.float() - bn.running_mean.float() * scale).contiguous()
-        return scale, shift
+    def _affine(self, bn, name=None):
+        """eval-mode BatchNorm folds into the conv epilogue; GroupNorm / InstanceNorm2d need the sample's own
+        statistics, so the conv gets an identity affine and the layer is normalised in a second pass (_apply_norm)"""
+        if isinstance(bn, nn.BatchNorm2d):
+            scale = (bn.weight.float() / torch.sqrt(bn.running_var.float() + bn.eps)).contiguous()
+            shift = (bn.bias.float() - bn.running_mean.float() * scale).contiguous()
+            return scale, shift
+        if isinstance(bn, nn.GroupNorm):
+            c = bn.num_channels
+            self.norms[name] = (bn.num_groups, bn.weight.detach().float().contiguous(), bn.bias.detach().float().contiguous(), bn.eps)
+        elif isinstance(bn, nn.InstanceNorm2d):
+            c = bn.num_features
+            if bn.affine or bn.track_running_stats:
+                raise NotImplementedError("InstanceNorm2d with affine / running statistics is not what the reference builds")
+            self.norms[name] = (c, None, None, bn.eps)
+        else:
+            raise NotImplementedError(f"unsupported normalisation module {type(bn).__name__}")
+        return (torch.ones(c, dtype=torch.float32, device=self.device), torch.zeros(c, dtype=torch.float32, device=self.device))
+
+    def _apply_norm(self, name, t):
+        """in-place GroupNorm / InstanceNorm2d of every sample of the NHWC tensor ``t``"""
+        groups, gamma, beta, eps = self.norms[name]
+        n, h, w, c = t.shape
+        if self._norm_scratch is None:
+            self._norm_scratch = torch.empty(int(self.L.mbs_bn_scratch_floats(2048)), dtype=torch.float32, device=self.device)
+        for b in range(n):
+            nat.check(self.L.mbs_sample_group_norm(t[b].data_ptr(), h * w, c, groups, gamma.data_ptr() if gamma is not None else None,
+                                                   beta.data_ptr() if beta is not None else None, eps, t[b].data_ptr(),
+                                                   self._norm_scratch.data_ptr(), nat.stream_ptr()), "sample_group_norm")
 
     def _pad_vec(self, v, n, fill):
         v = v.detach().float()
@@ -262,7 +291,7 @@ class _Engine:
         else:
             packed = torch.empty((cout, 9, cin), dtype=torch.bfloat16, device=self.device)
             nat.check(self.L.mbs_pack_conv3x3_weight(w.data_ptr(), cout, cin, packed.data_ptr(), nat.stream_ptr()))
-        scale, shift = self._affine(bn)
+        scale, shift = self._affine(bn, name)
         self.p[name] = (packed, self._pad_vec(conv.bias, cout, 0.0), self._pad_vec(scale, cout, 1.0),
                         self._pad_vec(shift, cout, 0.0), cin, cout)
 
@@ -277,7 +306,7 @@ class _Engine:
         w = w.contiguous()
         packed = torch.empty((4 * cout, cin), dtype=torch.bfloat16, device=self.device)
         nat.check(self.L.mbs_pack_convT2x2_weight(w.data_ptr(), cin, cout, packed.data_ptr(), nat.stream_ptr()))
-        scale, shift = self._affine(block.norm)
+        scale, shift = self._affine(block.norm, name)
         self.p[name] = (packed, self._pad_vec(block.up[0].bias, cout, 0.0), self._pad_vec(scale, cout, 1.0),
                         self._pad_vec(shift, cout, 0.0), cin, cout)
 
@@ -304,7 +333,8 @@ class _Engine:
                 hp = torch.zeros((hw.shape[0], self.chans[0]), dtype=torch.float32, device=self.device)
                 hp[:, :hw.shape[1]] = hw
                 hw = hp
-            self.p[name + "head"] = (hw.contiguous(), [float(b) for b in head.bias.detach().float().cpu()])
+            self.p[name + "head"] = (hw.contiguous(), [float(b) for b in head.bias.detach().float().cpu()],
+                                     head.bias.detach().float().contiguous())
 
     # -- buffers -------------------------------------------------------------------------------
     def _buf(self, name, shape, dtype=torch.bfloat16):
@@ -343,6 +373,8 @@ class _Engine:
             d.head_w, d.head_n, d.head_out = None, 0, None
         nat.check(self.L.mbs_conv_gemm(ctypes.byref(d), nat.stream_ptr()), name)
         self.last_conv_launches += 1
+        if name in self.norms and dst is not None:
+            self._apply_norm(name, dst)
 
     def run(self, img, pad_y, pad_x, lo, hi, events=None, lohi_dev=None, keep_features=None):
         """img: [N,H,W] CUDA tensor (uint8 / uint16-as-int16 / float32).  hi < lo -> the values are
@@ -374,6 +406,8 @@ class _Engine:
                                                 packed.data_ptr(), bias.data_ptr(), scale.data_ptr(),
                                                 shift.data_ptr(), c0, self.act, t1[0][b].data_ptr(), c0, 0,
                                                 nat.stream_ptr()), "first_conv")
+            if "enc0a" in self.norms:
+                self._apply_norm("enc0a", t1[0])
             if events is not None:
                 events[1].record()
             for l in range(nl):
@@ -402,8 +436,20 @@ class _Engine:
                         if keep_features is not None:      # calibration only: also write the last 64-channel map
                             feat = torch.empty((n, H, W, ch[0]), dtype=torch.bfloat16, device=self.device)
                             keep_features[name] = feat
-                        self._conv(0, f"{name}c{i}b", n, H, W, t2[0], None, feat, head=self.p[name + "head"],
-                                   head_out=out)
+                        lname = f"{name}c{i}b"
+                        if lname in self.norms:
+                            # the normalisation sits between the last conv and the 1x1 head: no fused head
+                            if feat is None:
+                                feat = self._buf("feat_last", (n, H, W, ch[0]))
+                            self._conv(0, lname, n, H, W, t2[0], None, feat)
+                            hw, hb, hb_dev = self.p[name + "head"]
+                            for b in range(n):
+                                for k in range(len(hb)):
+                                    nat.check(self.L.mbs_head_fwd(feat[b].data_ptr(), H * W, ch[0], hw[k].data_ptr(),
+                                                                  hb_dev[k:k + 1].data_ptr(), out[b, k].data_ptr(),
+                                                                  nat.stream_ptr()), "head_fwd")
+                        else:
+                            self._conv(0, lname, n, H, W, t2[0], None, feat, head=self.p[name + "head"][:2], head_out=out)
                 outs.append(out)
             if events is not None:
                 events[2].record()

@@ -28,8 +28,14 @@ def _act(x, act):
 
 
 def _bn(x, sd, prefix):
-    return F.batch_norm(x, sd[prefix + ".running_mean"], sd[prefix + ".running_var"], sd[prefix + ".weight"],
-                        sd[prefix + ".bias"], training=False, eps=1e-5)
+    """the block's normalisation in eval mode (unets.py:127-132): BatchNorm2d if the state dict holds running statistics,
+    GroupNorm(8, C) if only weight / bias, InstanceNorm2d (no parameters, no buffers) otherwise"""
+    if prefix + ".running_mean" in sd:
+        return F.batch_norm(x, sd[prefix + ".running_mean"], sd[prefix + ".running_var"], sd[prefix + ".weight"],
+                            sd[prefix + ".bias"], training=False, eps=1e-5)
+    if prefix + ".weight" in sd:
+        return F.group_norm(x, 8, sd[prefix + ".weight"], sd[prefix + ".bias"], eps=1e-5)
+    return F.instance_norm(x, eps=1e-5)
 
 
 def _conv_block(x, sd, prefix, act):
@@ -124,7 +130,7 @@ def seeded_state_dict(template, seed):
     return out
 
 
-def reference_layout_template(unet_type="DU", filters=(64, 1024), ch_in=1, ch_out=1, pool_method="conv"):
+def reference_layout_template(unet_type="DU", filters=(64, 1024), ch_in=1, ch_out=1, pool_method="conv", normalization="bn"):
     """Shapes of a reference state dict without importing the reference."""
     t = {}
 
@@ -133,9 +139,13 @@ def reference_layout_template(unet_type="DU", filters=(64, 1024), ch_in=1, ch_ou
         t[prefix + ".bias"] = torch.empty(cout)
 
     def bn(prefix, c):
-        for n in ("weight", "bias", "running_mean", "running_var"):
+        if normalization == "in":                  # nn.InstanceNorm2d default: no parameters, no buffers
+            return
+        names = ("weight", "bias", "running_mean", "running_var") if normalization == "bn" else ("weight", "bias")
+        for n in names:
             t[f"{prefix}.{n}"] = torch.empty(c)
-        t[prefix + ".num_batches_tracked"] = torch.empty((), dtype=torch.int64)
+        if normalization == "bn":
+            t[prefix + ".num_batches_tracked"] = torch.empty((), dtype=torch.int64)
 
     def block(prefix, cin, cout):
         conv(prefix + ".conv.0", cin, cout, 3)

@@ -44,15 +44,17 @@ def make_net(only=None):
     build_unet = reference_unets.build_unet
     from oracle import net as onet
     torch.set_grad_enabled(False)
-    for tag, filters, act, H, W, seed, pool in [("f64-128_relu", (64, 128), "relu", 64, 64, 21, "conv"),
-                                                ("f64-256_mish", (64, 256), "mish", 48, 80, 22, "conv"),
-                                                ("f64-1024_relu", (64, 1024), "relu", 64, 64, 23, "conv"),
-                                                # the reference's low-memory fallback architecture (train.py:283-285)
-                                                ("f32-512_relu", (32, 512), "relu", 64, 96, 24, "conv"),
-                                                ("f64-256_elu_maxpool", (64, 256), "elu", 64, 48, 25, "max")]:
+    for tag, filters, act, H, W, seed, pool, norm in [("f64-128_relu", (64, 128), "relu", 64, 64, 21, "conv", "bn"),
+                                                      ("f64-256_mish", (64, 256), "mish", 48, 80, 22, "conv", "bn"),
+                                                      ("f64-1024_relu", (64, 1024), "relu", 64, 64, 23, "conv", "bn"),
+                                                      # the reference's low-memory fallback architecture (train.py:283-285)
+                                                      ("f32-512_relu", (32, 512), "relu", 64, 96, 24, "conv", "bn"),
+                                                      ("f64-256_elu_maxpool", (64, 256), "elu", 64, 48, 25, "max", "bn"),
+                                                      ("f64-256_relu_gn", (64, 256), "relu", 48, 64, 26, "conv", "gn"),
+                                                      ("f64-128_leakyrelu_in", (64, 128), "leakyrelu", 64, 48, 27, "conv", "in")]:
         if only and tag not in only:
             continue
-        ref = build_unet("DU", act, pool, "bn", torch.device("cpu"), 1, ch_in=1, ch_out=1, filters=list(filters))
+        ref = build_unet("DU", act, pool, norm, torch.device("cpu"), 1, ch_in=1, ch_out=1, filters=list(filters))
         sd = onet.seeded_state_dict(ref.state_dict(), seed)
         ref.load_state_dict(sd)
         ref.eval()
@@ -62,7 +64,7 @@ def make_net(only=None):
         x = 2 * (img.astype(np.float32) - lo) / (hi - lo) - 1
         border, cell = ref(torch.from_numpy(x[None, None]))
         np.savez_compressed(os.path.join(HERE, f"net_{tag}_{H}x{W}_s{seed}.npz"), img=img, filters=np.array(filters),
-                            act=act, seed=seed, pool=pool, border=border[0, 0].numpy(), cell=cell[0, 0].numpy())
+                            act=act, seed=seed, pool=pool, norm=norm, border=border[0, 0].numpy(), cell=cell[0, 0].numpy())
         print("net", tag, float(border.abs().max()), float(cell.abs().max()))
 
 

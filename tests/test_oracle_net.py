@@ -28,7 +28,8 @@ def test_oracle_matches_reference_goldens():
         g = np.load(f)
         filters, act, seed = tuple(int(v) for v in g["filters"]), str(g["act"]), int(g["seed"])
         pool = str(g["pool"]) if "pool" in g.files else "conv"
-        sd = onet.seeded_state_dict(onet.reference_layout_template("DU", filters, pool_method=pool), seed)
+        norm = str(g["norm"]) if "norm" in g.files else "bn"
+        sd = onet.seeded_state_dict(onet.reference_layout_template("DU", filters, pool_method=pool, normalization=norm), seed)
         x = torch.from_numpy(normalise(g["img"])[None, None])
         border, cell = onet.dunet_forward(sd, x, act)
         # same math, same library (CPU fp32 conv) -> agreement to rounding noise

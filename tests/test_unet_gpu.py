@@ -21,10 +21,10 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 REL_MAX, REL_MEAN = 2.5e-2, 4e-3
 
 
-def _build(filters, act, seed, pool="conv"):
+def _build(filters, act, seed, pool="conv", norm="bn"):
     from microbeseg_b200.unets import build_unet
-    net = build_unet("DU", act, pool, "bn", torch.device("cuda:0"), 1, filters=list(filters))
-    sd = onet.seeded_state_dict(onet.reference_layout_template("DU", filters, pool_method=pool), seed)
+    net = build_unet("DU", act, pool, norm, torch.device("cuda:0"), 1, filters=list(filters))
+    sd = onet.seeded_state_dict(onet.reference_layout_template("DU", filters, pool_method=pool, normalization=norm), seed)
     net.load_state_dict(sd)
     return net.eval(), sd
 
@@ -34,12 +34,12 @@ def _norm(img):
     return 2 * (img.astype(np.float32) - lo) / (hi - lo) - 1
 
 
-def _check(got, ref, what):
+def _check(got, ref, what, loose=1.0):
     scale = max(1.0, float(np.abs(ref).max()))
     err = np.abs(got - ref)
     assert np.isfinite(got).all(), what
-    assert err.max() <= REL_MAX * scale, (what, err.max(), scale)
-    assert err.mean() <= REL_MEAN * scale, (what, err.mean(), scale)
+    assert err.max() <= loose * REL_MAX * scale, (what, err.max(), scale)
+    assert err.mean() <= loose * REL_MEAN * scale, (what, err.mean(), scale)
 
 
 def test_against_reference_goldens(native_lib):
@@ -49,12 +49,18 @@ def test_against_reference_goldens(native_lib):
     for f in files:
         g = np.load(f)
         filters, act, seed = tuple(int(v) for v in g["filters"]), str(g["act"]), int(g["seed"])
-        net, _ = _build(filters, act, seed, str(g["pool"]) if "pool" in g.files else "conv")
+        net, _ = _build(filters, act, seed, str(g["pool"]) if "pool" in g.files else "conv",
+                        str(g["norm"]) if "norm" in g.files else "bn")
         x = torch.from_numpy(_norm(g["img"])[None, None]).cuda()
         border, cell = net(x)
         assert border.shape == cell.shape == (1, 1) + g["img"].shape and border.dtype == torch.float32
-        _check(border[0, 0].cpu().numpy(), g["border"], f + ":border")
-        _check(cell[0, 0].cpu().numpy(), g["cell"], f + ":cell")
+        # group / instance norm cannot be folded into the conv epilogue: the activation is rounded to bf16 once more
+        # (before AND after the normalisation), measured error 1.7x that of the BatchNorm nets -> 2x tolerance
+        loose = 2.0 if ("norm" in g.files and str(g["norm"]) != "bn") else 1.0
+        _check(border[0, 0].cpu().numpy(), g["border"], f + ":border", loose)
+        _check(cell[0, 0].cpu().numpy(), g["cell"], f + ":cell", loose)
+        b2, c2 = net(x)                                     # bitwise reproducible (no atomics in the statistics)
+        assert torch.equal(border, b2) and torch.equal(cell, c2)
         assert native_lib.mbs_debug_flags(1) == 0
 
 
