@@ -451,8 +451,10 @@ __global__ void lab_dilate_bits_kernel(const unsigned long long *__restrict__ in
     out[t] = d;
 }
 // gap = ~label_bin & (erode(dil) ^ label_bin) as BYTES for the component labelling (bottom_hat_closing :58-59)
+// ... and L[i] = i at the gap pixels: the union-find arrays are only ever touched where gap != 0 (gaps are ~1 % of the
+// pixels, so the labelling passes below read one byte per pixel instead of 4-byte ids).
 __global__ void lab_erode_gap_bits_kernel(const unsigned long long *__restrict__ dil, const unsigned long long *__restrict__ lbits,
-                                          int H, int W, int WW, int n_crops, uint8_t *__restrict__ gap) {
+                                          int H, int W, int WW, int n_crops, uint8_t *__restrict__ gap, int *__restrict__ L) {
     const long long t = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (t >= static_cast<long long>(n_crops) * H * WW) return;
     const int w = static_cast<int>(t % WW), y = static_cast<int>((t / WW) % H);
@@ -476,6 +478,15 @@ __global__ void lab_erode_gap_bits_kernel(const unsigned long long *__restrict__
     const unsigned long long g = ~lb & (e ^ lb);
     const int valid = min(64, W - 64 * w);
     uint8_t *dst = gap + (crop * H + y) * W + 64 * w;
+    {
+        const int pix0 = static_cast<int>((crop * H + y) * W + 64 * w);
+        unsigned long long rest = valid < 64 ? (g & ((1ull << valid) - 1)) : g;
+        while (rest) {
+            const int b = __ffsll(static_cast<long long>(rest)) - 1;
+            L[pix0 + b] = pix0 + b;
+            rest &= rest - 1;
+        }
+    }
     if (valid == 64 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
         // 8 bits -> 8 bytes: isolate bit i in byte i, then normalise every non-zero byte to 1
         auto expand8 = [](unsigned long long x) {
@@ -531,10 +542,6 @@ __device__ __forceinline__ void uf_union(int *L, int a, int b) {
         else done = true;
     } while (!done);
 }
-__global__ void gap_init_kernel(const uint8_t *__restrict__ gap, long long n, int *__restrict__ L) {
-    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (i < n) L[i] = gap[i] ? static_cast<int>(i) : -1;
-}
 __global__ void gap_merge_kernel(const uint8_t *__restrict__ gap, int H, int W, int *L) {
     const int crop = blockIdx.z;
     const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
@@ -552,10 +559,10 @@ __global__ void gap_merge_kernel(const uint8_t *__restrict__ gap, int H, int W, 
         }
     }
 }
-__global__ void gap_compress_ids_kernel(int *L, long long n, int HW, int max_gaps, CropInfo *info, int *gid) {
+__global__ void gap_compress_ids_kernel(const uint8_t *__restrict__ gap, int *L, long long n, int HW, int max_gaps, CropInfo *info,
+                                        int *gid) {
     const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    if (L[i] < 0) { gid[i] = -1; return; }
+    if (i >= n || !gap[i]) return;              // gid is only defined at gap pixels
     if (L[i] == i) {          // root claims a dense id inside its crop
         const int crop = static_cast<int>(i / HW);
         const int k = atomicAdd(&info[crop].n_gaps, 1);
@@ -563,26 +570,27 @@ __global__ void gap_compress_ids_kernel(int *L, long long n, int HW, int max_gap
         else gid[i] = k;
     }
 }
-__global__ void gap_resolve_kernel(int *L, long long n, int *gid) {
+__global__ void gap_resolve_kernel(const uint8_t *__restrict__ gap, int *L, long long n) {
     const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (i >= n || L[i] < 0) return;
+    if (i >= n || !gap[i]) return;
     const int r = uf_find(L, static_cast<int>(i));
     L[i] = r;
 }
-__global__ void gap_assign_kernel(const int *__restrict__ L, long long n, int *gid) {
+__global__ void gap_assign_kernel(const uint8_t *__restrict__ gap, const int *__restrict__ L, long long n, int *gid) {
     const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (i >= n || L[i] < 0 || L[i] == i) return;
+    if (i >= n || !gap[i] || L[i] == i) return;
     gid[i] = gid[L[i]];
 }
-__global__ void gap_stats_kernel(const int *__restrict__ gid, const double *__restrict__ nraw, int H, int W, int max_gaps,
-                                 GapStats *gs) {
+__global__ void gap_stats_kernel(const uint8_t *__restrict__ gap, const int *__restrict__ gid, const double *__restrict__ nraw, int H,
+                                 int W, int max_gaps, GapStats *gs) {
     const int crop = blockIdx.z;
     const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
     if (x >= W || y >= H) return;
     const size_t base = static_cast<size_t>(crop) * H * W;
     const int *g = gid + base;
+    const uint8_t *gp = gap + base;
     GapStats *S = gs + static_cast<size_t>(crop) * max_gaps;
-    const int me = g[y * W + x];
+    const int me = gp[y * W + x] ? g[y * W + x] : -1;
     if (me >= 0) {
         atomicAdd(&S[me].cnt, 1ull);
         atomicAdd(&S[me].sy, static_cast<unsigned long long>(y));
@@ -601,7 +609,7 @@ __global__ void gap_stats_kernel(const int *__restrict__ gid, const double *__re
             if (!dy && !dx) continue;
             const int yy = y + dy, xx = x + dx;
             if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
-            const int o = g[yy * W + xx];
+            const int o = gp[yy * W + xx] ? g[yy * W + xx] : -1;
             if (o < 0 || o == me) continue;
             bool dup = false;
             for (int k = 0; k < ns; ++k) dup |= (seen[k] == o);
@@ -610,14 +618,16 @@ __global__ void gap_stats_kernel(const int *__restrict__ gid, const double *__re
 }
 
 // gap map (label_closed_corr) + max with raw neighbour map and touching borders + rescale + clip (:352-358)
-__global__ void lab_compose_kernel(const int *__restrict__ gid, const GapStats *__restrict__ gs, const uint8_t *__restrict__ border,
-                                   const double *__restrict__ nraw, int H, int W, int max_gaps, double *__restrict__ scaled) {
+__global__ void lab_compose_kernel(const uint8_t *__restrict__ gap, const int *__restrict__ gid, const GapStats *__restrict__ gs,
+                                   const uint8_t *__restrict__ border, const double *__restrict__ nraw, int H, int W, int max_gaps,
+                                   double *__restrict__ scaled) {
     const int crop = blockIdx.z;
     const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
     if (x >= W || y >= H) return;
     const size_t base = static_cast<size_t>(crop) * H * W;
     const int *g = gid + base;
-    const int me = g[y * W + x];
+    const uint8_t *gp = gap + base;
+    const int me = gp[y * W + x] ? g[y * W + x] : -1;
     float corr = 0.0f;
     if (me >= 0) {
         const GapStats s = gs[static_cast<size_t>(crop) * max_gaps + me];
@@ -630,8 +640,9 @@ __global__ void lab_compose_kernel(const int *__restrict__ gid, const GapStats *
             axis_lengths(s.cnt, s.sy, s.sx, s.syy, s.sxx, s.sxy, &major, &minor);
             if (minor >= 3.0) {
                 // ring = gap ^ binary_erosion(gap, cross), border_value = 0
-                const bool inner = y > 0 && y + 1 < H && x > 0 && x + 1 < W && g[(y - 1) * W + x] == me &&
-                                   g[(y + 1) * W + x] == me && g[y * W + x - 1] == me && g[y * W + x + 1] == me;
+                auto same = [&](int i) { return gp[i] && g[i] == me; };
+                const bool inner = y > 0 && y + 1 < H && x > 0 && x + 1 < W && same((y - 1) * W + x) && same((y + 1) * W + x) &&
+                                   same(y * W + x - 1) && same(y * W + x + 1);
                 if (!inner) corr = 0.8f;
             }
         }
@@ -651,20 +662,46 @@ __device__ __forceinline__ int reflect_idx(int i, int n) {
     }
     return i;
 }
-// grey_closing(size=(3,3)) = 3x3 max filter then 3x3 min filter, mode 'reflect'
-template <bool IS_MAX, typename TOUT>
-__global__ void lab_grey_kernel(const double *__restrict__ in, int H, int W, TOUT *__restrict__ out) {
+// grey_closing(size=(3,3)) = 3x3 max filter then 3x3 min filter, mode 'reflect' (edge sample duplicated) -- both filters
+// in ONE pass.  S holds scaled[reflect(raw)] for the raw coordinates of the 32x8 tile with a 2-pixel apron; the dilated map
+// D at a raw position h (1-pixel apron) is the 3x3 maximum around q = reflect(h), i.e. the value the min filter would
+// read there; the output is the 3x3 minimum of D.
+__global__ void __launch_bounds__(256)
+lab_grey_closing_kernel(const double *__restrict__ in, int H, int W, float *__restrict__ out) {
+    __shared__ double S[12][36 + 1];
+    __shared__ double D[10][34 + 1];
     const int crop = blockIdx.z;
-    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
-    if (x >= W || y >= H) return;
+    const int x0 = blockIdx.x * 32, y0 = blockIdx.y * 8;
+    const int tid = threadIdx.y * 32 + threadIdx.x;
     const double *p = in + static_cast<size_t>(crop) * H * W;
-    double v = p[y * W + x];
-    for (int dy = -1; dy <= 1; ++dy)
-        for (int dx = -1; dx <= 1; ++dx) {
-            const double o = p[reflect_idx(y + dy, H) * W + reflect_idx(x + dx, W)];
-            v = IS_MAX ? fmax(v, o) : fmin(v, o);
+    for (int i = tid; i < 12 * 36; i += 256) {
+        const int r = i / 36, c = i - r * 36;
+        S[r][c] = p[reflect_idx(y0 - 2 + r, H) * W + reflect_idx(x0 - 2 + c, W)];
+    }
+    __syncthreads();
+    for (int i = tid; i < 10 * 34; i += 256) {
+        const int r = i / 34, c = i - r * 34;
+        if (y0 - 1 + r > H || x0 - 1 + c > W) {      // beyond the 1-pixel apron of the image (ragged last tiles): never read
+            D[r][c] = 0.0;
+            continue;
         }
-    out[(static_cast<size_t>(crop) * H + y) * W + x] = static_cast<TOUT>(v);
+        const int qy = reflect_idx(y0 - 1 + r, H) - (y0 - 2), qx = reflect_idx(x0 - 1 + c, W) - (x0 - 2);   // indices into S
+        double v = S[qy][qx];
+#pragma unroll
+        for (int dy = -1; dy <= 1; ++dy)
+#pragma unroll
+            for (int dx = -1; dx <= 1; ++dx) v = fmax(v, S[qy + dy][qx + dx]);
+        D[r][c] = v;
+    }
+    __syncthreads();
+    const int x = x0 + threadIdx.x, y = y0 + threadIdx.y;
+    if (x >= W || y >= H) return;
+    double v = D[threadIdx.y + 1][threadIdx.x + 1];
+#pragma unroll
+    for (int dy = 0; dy <= 2; ++dy)
+#pragma unroll
+        for (int dx = 0; dx <= 2; ++dx) v = fmin(v, D[threadIdx.y + dy][threadIdx.x + dx]);
+    out[(static_cast<size_t>(crop) * H + y) * W + x] = static_cast<float>(v);
 }
 
 inline size_t r256(size_t b) { return (b + 255) & ~static_cast<size_t>(255); }
@@ -826,25 +863,21 @@ extern "C" int mbs_distance_labels(const uint16_t *masks, int n_crops, int H, in
     const int nwords = static_cast<int>((static_cast<long long>(n_crops) * H * WW + 255) / 256);
     lab_dilate_bits_kernel<<<nwords, 256, 0, stream>>>(lbits, H, W, WW, n_crops, dbits);
     MBS_CHECK_LAUNCH();
-    lab_erode_gap_bits_kernel<<<nwords, 256, 0, stream>>>(dbits, lbits, H, W, WW, n_crops, gap);
-    MBS_CHECK_LAUNCH();
-    gap_init_kernel<<<nb, 256, 0, stream>>>(gap, static_cast<long long>(px), L);
+    lab_erode_gap_bits_kernel<<<nwords, 256, 0, stream>>>(dbits, lbits, H, W, WW, n_crops, gap, L);
     MBS_CHECK_LAUNCH();
     gap_merge_kernel<<<g3, b2, 0, stream>>>(gap, H, W, L);
     MBS_CHECK_LAUNCH();
-    gap_resolve_kernel<<<nb, 256, 0, stream>>>(L, static_cast<long long>(px), gid);
+    gap_resolve_kernel<<<nb, 256, 0, stream>>>(gap, L, static_cast<long long>(px));
     MBS_CHECK_LAUNCH();
-    gap_compress_ids_kernel<<<nb, 256, 0, stream>>>(L, static_cast<long long>(px), H * W, kMaxGaps, info, gid);
+    gap_compress_ids_kernel<<<nb, 256, 0, stream>>>(gap, L, static_cast<long long>(px), H * W, kMaxGaps, info, gid);
     MBS_CHECK_LAUNCH();
-    gap_assign_kernel<<<nb, 256, 0, stream>>>(L, static_cast<long long>(px), gid);
+    gap_assign_kernel<<<nb, 256, 0, stream>>>(gap, L, static_cast<long long>(px), gid);
     MBS_CHECK_LAUNCH();
-    gap_stats_kernel<<<g3, b2, 0, stream>>>(gid, nraw, H, W, kMaxGaps, gs);
+    gap_stats_kernel<<<g3, b2, 0, stream>>>(gap, gid, nraw, H, W, kMaxGaps, gs);
     MBS_CHECK_LAUNCH();
-    lab_compose_kernel<<<g3, b2, 0, stream>>>(gid, gs, border, nraw, H, W, kMaxGaps, scaled);
+    lab_compose_kernel<<<g3, b2, 0, stream>>>(gap, gid, gs, border, nraw, H, W, kMaxGaps, scaled);
     MBS_CHECK_LAUNCH();
-    lab_grey_kernel<true, double><<<g3, b2, 0, stream>>>(scaled, H, W, nraw);        // nraw reused as the dilated map
-    MBS_CHECK_LAUNCH();
-    lab_grey_kernel<false, float><<<g3, b2, 0, stream>>>(nraw, H, W, neighbor_dist);
+    lab_grey_closing_kernel<<<g3, b2, 0, stream>>>(scaled, H, W, neighbor_dist);
     MBS_CHECK_LAUNCH();
     if (max_mal_out)
         MBS_CHECK_CUDA(cudaMemcpy2DAsync(max_mal_out, sizeof(int), &info[0].max_mal, sizeof(CropInfo), sizeof(int), n_crops,
