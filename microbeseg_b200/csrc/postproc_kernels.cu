@@ -225,7 +225,16 @@ __global__ void compress_area_kernel(int *L, int n, int *__restrict__ area, Stat
     if (i < n && L[i] >= 0) {
         r = uf_find(L, i);
         L[i] = r;
-        atomicAdd(&area[r], 1);
+    }
+    // all pixels of a component add to the same counter: group the warp's lanes by root, one atomic per group
+    unsigned remaining = __ballot_sync(0xffffffffu, r >= 0);
+    const int lane = threadIdx.x & 31;
+    while (remaining) {
+        const int leader = __ffs(remaining) - 1;
+        const int cur = __shfl_sync(0xffffffffu, r, leader);
+        const unsigned grp = __ballot_sync(0xffffffffu, r == cur);
+        if (lane == leader) atomicAdd(&area[cur], __popc(grp));
+        remaining &= ~grp;
     }
     const int cnt = __syncthreads_count(r >= 0);
     const int roots = __syncthreads_count(r >= 0 && r == i);
