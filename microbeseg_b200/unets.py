@@ -140,7 +140,8 @@ class _NetBase(nn.Module):
 
     def _forward_maps(self, x):
         if self.training:
-            raise RuntimeError("microbeseg_b200: training-mode forward is not built yet (call net.eval())")
+            raise RuntimeError("microbeseg_b200: net(x) is the eval-mode forward (call net.eval()); the training step runs through "
+                               "microbeseg_b200.training.TrainEngine, not through autograd")
         if not x.is_cuda:
             raise RuntimeError("microbeseg_b200: the network runs on CUDA only (no CPU fallback); got a CPU tensor")
         if x.dim() != 4 or x.shape[1] != 1:
@@ -155,7 +156,8 @@ class _NetBase(nn.Module):
         first kernel.  ``lohi_dev`` (float32[2] CUDA tensor from ``frame_minmax``) keeps min/max on the device."""
         self._check_supported()
         if self.training:
-            raise RuntimeError("microbeseg_b200: training-mode forward is not built yet (call net.eval())")
+            raise RuntimeError("microbeseg_b200: net(x) is the eval-mode forward (call net.eval()); the training step runs through "
+                               "microbeseg_b200.training.TrainEngine, not through autograd")
         return self.engine().run(img[None], int(pads[0]), int(pads[1]), float(lo), float(hi), lohi_dev=lohi_dev)
 
 
