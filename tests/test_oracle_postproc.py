@@ -135,9 +135,27 @@ def test_synthetic_is_deterministic():
 def test_c_abi_exports_every_declared_symbol(native_lib):
     hdr = open(os.path.join(ROOT, "include", "mbseg.h")).read()
     hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
-    names = set(re.findall(r"\b(mbs_[a-z0-9_]+)\s*\(", hdr))
+    names = set(re.findall(r"\b(mbs_[A-Za-z0-9_]+)\s*\(", hdr))
     assert len(names) >= 12
     for n in names:
         assert hasattr(native_lib, n), f"libmbseg.so does not export {n}"
     assert native_lib.mbs_version() >= 1
     assert native_lib.mbs_postproc_workspace_bytes(64, 64) > 64 * 64 * 40
+
+
+def test_ctypes_signatures_match_the_header():
+    """every prototype in include/mbseg.h has a ctypes signature in the host mirror with the same number of parameters
+    (an ABI drift between header, library and mirror would otherwise corrupt the stack silently)"""
+    from microbeseg_b200 import _native as nat
+    hdr = open(os.path.join(ROOT, "include", "mbseg.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    protos = re.findall(r"\b(?:int|int64_t|size_t|long long|const char \*)\s*\*?\s*(mbs_[A-Za-z0-9_]+)\s*\(([^;{]*?)\)\s*;", hdr, flags=re.S)
+    assert len(protos) >= 30
+    seen = set()
+    for name, params in protos:
+        seen.add(name)
+        params = params.strip()
+        n = 0 if params in ("", "void") else params.count(",") + 1
+        assert name in nat._SIGS, f"no ctypes signature for {name}"
+        assert len(nat._SIGS[name][1]) == n, (name, n, len(nat._SIGS[name][1]))
+    assert set(nat._SIGS) <= seen, sorted(set(nat._SIGS) - seen)
