@@ -38,6 +38,28 @@ def load_peaks():
     return dict(hbm=6650.0, tf_burst=1590.0, tf_sustained=1400.0, src="fallback")
 
 
+CONV_TRAFFIC_CSV = "profiles/r01_conv_dram_traffic_frame_v3.csv"
+
+
+def conv_traffic_from_profile(path=None):
+    """Average DRAM bytes (read + write) per tensor-core conv launch of one 2048^2 frame, parsed from the committed
+    per-launch summary of an ncu capture (columns kernel, dram_read_MB, dram_write_MB, time_us; see profiles/README.md);
+    None if the file is missing."""
+    path = os.path.join(ROOT, path or CONV_TRAFFIC_CSV)
+    if not os.path.exists(path):
+        return None
+    tot, n = 0.0, 0
+    try:
+        for ln in open(path).read().splitlines()[1:]:
+            f = ln.rsplit(",", 3)            # the kernel name holds template commas: split the three numbers off the right
+            if len(f) == 4 and f[0].startswith(("conv_gemm_kernel", "conv_halo64_kernel")):
+                tot += (float(f[1]) + float(f[2])) * 1e6
+                n += 1
+    except Exception:
+        return None
+    return tot / n if n else None
+
+
 class ClockSampler(threading.Thread):
     """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
 
@@ -73,9 +95,10 @@ class ClockSampler(threading.Thread):
                 "samples": len(sm)}
 
 
-def cpu_reference_sample(size=1024, seed=1234, threads=None):
+def cpu_reference_sample(size=2048, seed=2000, threads=None):
     """The reference's CPU path on a bounded sample: fp32 DUNet on all host threads + single-threaded
-    post-processing (oracle port: oracle/net.py + oracle/postproc.py), one `size`^2 frame."""
+    post-processing (oracle port: oracle/net.py + oracle/postproc.py), one `size`^2 frame (2048^2 = one frame of
+    the config-2 stack, the same frame the CUDA arm processes first)."""
     import torch
     from oracle import net as onet
     from oracle import postproc as op
@@ -113,7 +136,7 @@ def run_reference(args, rank):
         return
     vals, last = [], None
     for i in range(args.warmup_ref + args.steps_ref):
-        r = cpu_reference_sample(args.ref_size)
+        r = cpu_reference_sample(args.ref_size, seed=2000 + i)
         if i >= args.warmup_ref:
             vals.append(r)
         last = r
@@ -124,7 +147,8 @@ def run_reference(args, rank):
         "ms_per_step": float(np.mean([(v["net_s"] + v["pp_s"]) * 1e3 for v in vals])), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "config 2 frame path (normalise + DUNet[64,1024] fp32 + distance post-processing), "
-                               f"bounded sample: one {args.ref_size}x{args.ref_size} frame per step on the host CPU"},
+                               f"bounded sample: one {args.ref_size}x{args.ref_size} frame of the stack per step on the host CPU",
+                   "same_config": args.ref_size == 2048},
         "cpu_baseline": {"value": value, "unit": "Mpx/s", "cores": last["cores"], "kind": "port",
                          "sample": f"one {args.ref_size}^2 synthetic frame: torch fp32 DUNet on {last['cores']} threads "
                                    f"({last['net_mpx_s']:.3f} Mpx/s) + oracle post-processing on 1 thread "
@@ -142,9 +166,12 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--frames-per-step", type=int, default=25)
-    ap.add_argument("--ref-size", type=int, default=1024)
+    ap.add_argument("--ref-size", type=int, default=2048)
     ap.add_argument("--steps-ref", type=int, default=2)
-    ap.add_argument("--warmup-ref", type=int, default=1)
+    ap.add_argument("--warmup-ref", type=int, default=0)
+    ap.add_argument("--no-extras", action="store_true", help="skip the config 3 / 4 / 5 sub-records and the same-GPU "
+                                                             "torch / cuDNN baseline (kernel A/B runs)")
+    ap.add_argument("--c4-crops", type=int, default=10000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--size", type=int, default=2048)
     ap.add_argument("--heads", default="fitted", choices=["fitted", "random"],
@@ -252,6 +279,17 @@ def main():
     frame_device(0)
     torch.cuda.synchronize()
     objects_per_frame = int(out_dev.cpu().numpy().view(np.uint16).max())
+    # tie statistics of the bench frames: how many pixels the order-free watershed flagged as order dependent and
+    # whether the exact sequential flood had to run (it must not on network-produced maps)
+    tie_info = []
+    for i in range(distinct):
+        lo_, hi_ = lohi[i]
+        border, cell = net.forward_frame(dev_frames[i], pads, lo_, hi_)
+        pp.distance_postprocessing_device(border[0, 0, pads[0]:, pads[1]:], cell[0, 0, pads[0]:, pads[1]:], th_seed, th_cell,
+                                          out=out_dev, want_info=True)
+        tie_info.append(dict(pp.last_info))
+    pp_frame_info = {"ambiguous_pixels": [t["ambiguous"] for t in tie_info], "sequential_fallback": [t["sequential"] for t in tie_info],
+                     "sweeps": [t["sweeps"] for t in tie_info], "markers": [t["n_markers"] for t in tie_info]}
     sampler = ClockSampler(local_rank)
     sampler.start()
     ms_dev, launches = timed(step_device, args.steps, args.warmup)
@@ -287,30 +325,28 @@ def main():
     roofline = {"bound": "tensor", "kernel": "conv_gemm_kernel (tcgen05 implicit GEMM, all tensor-core launches of one frame)",
                 "achieved": achieved, "peak": peaks["tf_sustained"], "unit": "TFLOP/s", "frac": achieved / peaks["tf_sustained"],
                 "peak_source": peaks["src"] + " (sustained cuBLAS bf16)",
-                # dram__bytes_read+write per launch, averaged over the frame's tensor-core launches
-                # (ncu capture profiles/r01_conv_dram_traffic_frame_v3.csv: 37 tensor-core launches of one frame,
-                #  dram__bytes_read.sum + dram__bytes_write.sum = 9.450 + 5.339 GB)
-                "traffic": 14.789e9 / 37 if size == 2048 else None,
+                # dram__bytes_read.sum + dram__bytes_write.sum per launch, read from the committed ncu capture of one
+                # 2048^2 frame (not measured in this run: ncu cannot run inside the timed process)
+                "traffic": conv_traffic_from_profile() if size == 2048 else None,
+                "traffic_source": CONV_TRAFFIC_CSV,
                 "launches_per_frame": n_conv_launch, "avg_launch_ms": conv_ms_frame / max(n_conv_launch, 1),
                 "algorithmic_flop_per_launch": conv_flops / max(n_conv_launch, 1)}
 
-    # post-processing alone on realistic maps (BASELINE config 3 style, same frame size) for the record
-    m = sy.synth_instance_mask(size, size, int(size * size * 0.4 / 330), 4096)
-    bm, cm = sy.synth_distance_maps(m, 4097)
-    bmd, cmd = torch.from_numpy(bm[..., 0]).to(device), torch.from_numpy(cm[..., 0]).to(device)
-    for _ in range(3):
-        pp.distance_postprocessing_device(bmd, cmd, th_seed, th_cell, out=out_dev)
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(10):
-        pp.distance_postprocessing_device(bmd, cmd, th_seed, th_cell, out=out_dev)
-    e1.record()
-    torch.cuda.synchronize()
-    pp_ms = e0.elapsed_time(e1) / 10
-    pp_mpx_s = size * size / 1e6 / (pp_ms / 1e3)
-    pp_roof = {"bound": "hbm", "achieved": 10.0 * size * size / (pp_ms / 1e3) / 1e9, "peak": peaks["hbm"], "unit": "GB/s"}
-    pp_roof["frac"] = pp_roof["achieved"] / pp_roof["peak"]
+    # secondary BASELINE configs as sub-records: config 5 (training, all ranks: data-parallel all-reduce), then on
+    # rank 0 config 3 (post-processing of 4096^2 maps), config 4 (label generation) and the same-GPU torch/cuDNN arm
+    extras = {}
+    if not args.no_extras:
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import bench_parts as parts
+        torch.cuda.empty_cache()
+        rec = parts.bench_c5(device, rank, world, peaks, steps=10, warmup=3, torch_baseline=(world == 1))
+        if rank == 0:
+            extras["train"] = rec
+            torch.cuda.empty_cache()
+            extras["postproc"] = parts.bench_c3(device, peaks, cpu=not args.no_cpu_baseline)
+            extras["labels"] = parts.bench_c4(device, peaks, n_crops=args.c4_crops, cpu=not args.no_cpu_baseline)
+            if world == 1:
+                extras["gpu_reference"] = parts.bench_gpu_reference(device, size=size)
 
     if rank == 0:
         cpu = None
@@ -338,12 +374,12 @@ def main():
                     "ms_per_step": ms_e2e / e2e_steps, "api": "microbeseg_b200.inference.segment_stack"},
             "gpu_launches": launches,
             "roofline": roofline,
-            "postproc": {"metric": "watershed postproc Mpx/s", "value": pp_mpx_s, "ms_per_frame": pp_ms,
-                         "workload": f"{size}x{size} synthetic distance maps, {int(m.max())} cells", "roofline": pp_roof},
+            "postproc_in_frame_loop": pp_frame_info,
             "cpu_baseline": cpu,
             "clocks": sampler.summary(),
             "timeout_flag": int(L.mbs_debug_flags(0)),
         }
+        line.update(extras)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -8,7 +8,8 @@ import numpy as np
 import torch
 
 from microbeseg_b200 import tiffio as tiff
-from microbeseg_b200.inference import segment_stack
+from microbeseg_b200 import sharding
+from microbeseg_b200.inference import segment_stack_sharded
 from src.utils.unets import build_unet, get_weights
 
 
@@ -39,11 +40,15 @@ def main(argv=None):
         raise ValueError('this build runs on CUDA devices only (no CPU path); use the reference for device "cpu"')
     if not torch.cuda.is_available():
         raise ValueError('No cuda capable gpu device detected')
-    device = torch.device(args.device)
+    # under torchrun (one process per GPU) the frames of every stack are sharded over the ranks, frame t -> rank
+    # t mod world; rank 0 gathers the masks and is the only writer; plain launch: one GPU as given
+    rank, world, local_rank = sharding.init_from_env()
+    device = torch.device('cuda', local_rank) if world > 1 else torch.device(args.device)
+    say = print if rank == 0 else (lambda *a, **k: None)
 
     file_ids = sorted(imgs_path.glob('*.tif*'))
     if len(file_ids) == 0:
-        print('No files found')
+        say('No files found')
         return
 
     arch = model_settings['architecture']
@@ -52,7 +57,7 @@ def main(argv=None):
     net = get_weights(net=net, weights=str(inference_model.parent / f"{inference_model.stem}.pth"), num_gpus=1, device=device)
     net.eval()
     torch.set_grad_enabled(False)
-    print('--- Start inference ---')
+    say('--- Start inference ---')
     for img_id in file_ids:
         img = tiff.imread(str(img_id))
         fname = result_path / img_id.stem
@@ -67,18 +72,23 @@ def main(argv=None):
         elif img.ndim == 4:
             img = img[:, args.channel, ...]
         elif img.ndim == 5:
-            print(f'Skip {fname.name} (not supported image shape)')
+            say(f'Skip {fname.name} (not supported image shape)')
             continue
         else:
             raise Exception('Adapt script for your data format!')
         out_file = result_path / f"mask_{fname.stem}_channel{args.channel}.tif"
         if out_file.is_file() and not args.overwrite:
-            print(f'Skip {fname.name} (already processed and overwriting not enabled)')
+            say(f'Skip {fname.name} (already processed and overwriting not enabled)')
             continue
-        print(f'Process {fname.name} (channel: {args.channel})')
-        results_array = segment_stack(net, img, ths=args.thresholds, device=device)
-        tiff.imwrite(str(out_file), np.squeeze(results_array))
-    print('--- Finished ---')
+        say(f'Process {fname.name} (channel: {args.channel})')
+        results_array = segment_stack_sharded(net, img, ths=args.thresholds, device=device)
+        if rank == 0:
+            tiff.imwrite(str(out_file), np.squeeze(results_array))
+    say('--- Finished ---')
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+        dist.destroy_process_group()
 
 
 if __name__ == "__main__":

@@ -10,6 +10,21 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libmbseg.so")
 _lib = None
 
+# Kernels of this library write parameters and BatchNorm buffers through raw pointers, which does not bump
+# torch's tensor version counters.  Every such writer (TrainEngine.forward_backward, Ranger.step, the fused Adam
+# step) calls note_raw_write(); caches keyed on parameter versions (the eval engine, unets._NetBase.engine)
+# include this epoch so they are rebuilt after training steps.
+_raw_write_epoch = 0
+
+
+def note_raw_write():
+    global _raw_write_epoch
+    _raw_write_epoch += 1
+
+
+def raw_write_epoch():
+    return _raw_write_epoch
+
 c_void_p, c_int, c_float, c_size_t, c_int64 = (ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_size_t,
                                                ctypes.c_int64)
 

@@ -48,3 +48,40 @@ def fit_heads(net, pairs, ridge=1e-3):
         head.weight.copy_(sol[:C].float().reshape(1, C, 1, 1))
         head.bias.copy_(sol[C:].float())
     return net
+
+
+def train_briefly(net, steps=400, crop=256, n_crops=48, batch=8, seed0=9000, lr=8e-4, log=None):
+    """Short CUDA training run on synthetic crops so that a random-init DU net predicts well-separated distance
+    maps (tests / bench calibration only; no checkpoint or dataset is reachable offline).  Everything runs on this
+    repo's own path: labels from ``labels.create_labels_device`` (the CUDA distance transforms), the step from
+    ``training.TrainEngine`` (tcgen05 forward / backward) with the reference's Adam settings (train.py:380-385).
+    Frames are normalised per frame to [-1, 1] exactly as the inference path does (infer.py:346).  Returns the
+    list of losses; the net is left in eval() mode with its trained weights and BatchNorm running statistics."""
+    from . import labels as lb
+    from .training import TrainEngine, train_step
+    dev = next(net.parameters()).device
+    frames, masks = [], []
+    for k in range(n_crops):
+        frame, _, _, mask = synthetic_training_pair(crop, crop, seed0 + 10 * k)
+        lo, hi = float(frame.min()), float(frame.max())
+        frames.append(2 * (frame.astype(np.float32) - lo) / (hi - lo) - 1)
+        masks.append(mask.astype(np.uint16))
+    with torch.cuda.device(dev):
+        md = torch.from_numpy(np.stack(masks).view(np.int16)).to(dev)
+        cell, neigh, _ = lb.create_labels_device(md, int(np.stack(masks).max()))
+        x = torch.from_numpy(np.stack(frames)[:, None]).to(dev)
+        cell, neigh = cell[:, None].contiguous(), neigh[:, None].contiguous()
+        net.train()
+        eng = TrainEngine(net)
+        opt = torch.optim.Adam(net.parameters(), lr=lr, betas=(0.9, 0.999), eps=1e-8, weight_decay=0, amsgrad=True)
+        g = torch.Generator(device="cpu").manual_seed(seed0)
+        losses = []
+        for it in range(steps):
+            idx = torch.randperm(n_crops, generator=g)[:batch].to(dev)
+            loss = train_step(eng, opt, x[idx].contiguous(), neigh[idx].contiguous(), cell[idx].contiguous())
+            if it % 50 == 0 or it == steps - 1:
+                losses.append(float(loss))
+                if log:
+                    log(f"train_briefly step {it}: loss {losses[-1]:.5f}")
+        net.eval()
+    return losses

@@ -41,4 +41,14 @@ void count_launch(int n = 1);
 
 static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 
+// Per-device caches: function attributes (opt-in shared memory), SM counts and occupancy are properties of ONE
+// device, so anything cached about them is indexed by the current device ordinal (a process may use cuda:0 and
+// then cuda:1).  Racing threads write the same value, so plain ints are enough.
+constexpr int kMaxDevices = 64;
+static inline int current_device() {
+    int d = 0;
+    if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= kMaxDevices) d = 0;
+    return d;
+}
+
 }  // namespace mbs

@@ -847,15 +847,17 @@ extern "C" int mbs_distance_labels(const uint16_t *masks, int n_crops, int H, in
     MBS_CHECK_LAUNCH();
     if (max_id > 0) {
         // dynamic shared memory: as much as the device allows (opt-in), the kernels flag windows that do not fit
-        static int smem_opt = 0;
-        if (!smem_opt) {
-            int dev = 0;
-            cudaGetDevice(&dev);
-            cudaDeviceGetAttribute(&smem_opt, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-            smem_opt -= 1024;
-            MBS_CHECK_CUDA(cudaFuncSetAttribute(lab_cell_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_opt));
-            MBS_CHECK_CUDA(cudaFuncSetAttribute(lab_close_cell_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_opt));
+        static int smem_opt_dev[mbs::kMaxDevices] = {0};
+        const int dev = mbs::current_device();
+        if (!smem_opt_dev[dev]) {
+            int v = 0;
+            cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+            v -= 1024;
+            MBS_CHECK_CUDA(cudaFuncSetAttribute(lab_cell_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, v));
+            MBS_CHECK_CUDA(cudaFuncSetAttribute(lab_close_cell_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, v));
+            smem_opt_dev[dev] = v;
         }
+        const int smem_opt = smem_opt_dev[dev];
         // size the launch for the largest window the radius can produce, capped by the device limit
         const int R = search_radius >= 0 ? search_radius : (radius_hint >= 0 ? radius_hint : (H > W ? H : W));
         long long want = 3ll * 2 * (2ll * R) * (2ll * R);

@@ -1468,13 +1468,14 @@ int make_weight_map(CUtensorMap *map, const void *base, int rows, int K, int bn)
 }
 
 int sm_count() {
-    static int n = 0;
-    if (n == 0) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    static int n[mbs::kMaxDevices] = {0};
+    const int dev = mbs::current_device();
+    if (n[dev] == 0) {
+        int v = 0;
+        if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = 148;
+        n[dev] = v;
     }
-    return n;
+    return n[dev];
 }
 
 // destination of a transposed conv as a 5-D tensor (C, dx, x, dy, y'): pixel (2y+dy, 2x+dx) of image n is
@@ -1501,12 +1502,13 @@ template <int BN, int STAGES, int CTAS_PER_SM, bool TMA_EPI, int MT = 1, int NG 
 int launch_conv(const CUtensorMap &a0, const CUtensorMap &a1, const CUtensorMap &b, const CUtensorMap &dmap,
                 const ConvKParams &kp, cudaStream_t stream) {
     using Plan = SmemPlan<BN, STAGES, TMA_EPI, MT, NG>;
-    static int configured_bytes = 0;
+    static int configured_bytes[mbs::kMaxDevices] = {0};
     const int dyn = Plan::dyn_bytes(kp.Cout);
-    if (dyn > configured_bytes) {
+    const int dev = mbs::current_device();
+    if (dyn > configured_bytes[dev]) {
         MBS_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<BN, STAGES, CTAS_PER_SM, TMA_EPI, MT, NG>,
                                             cudaFuncAttributeMaxDynamicSharedMemorySize, dyn));
-        configured_bytes = dyn;
+        configured_bytes[dev] = dyn;
     }
     const int grid = kp.num_tiles < sm_count() * CTAS_PER_SM ? kp.num_tiles : sm_count() * CTAS_PER_SM;
     conv_gemm_kernel<BN, STAGES, CTAS_PER_SM, TMA_EPI, MT, NG><<<grid, threads_for_groups(NG), dyn, stream>>>(a0, a1, b, dmap, kp);
@@ -1518,11 +1520,12 @@ template <int CHUNKS, int STAGES, int NG>
 int launch_halo(const CUtensorMap &a0, const CUtensorMap &a1, const CUtensorMap &b, const CUtensorMap &dmap,
                 const ConvKParams &kp, cudaStream_t stream) {
     using Plan = HaloPlan<CHUNKS, STAGES, NG>;
-    static bool configured = false;
-    if (!configured) {
+    static bool configured[mbs::kMaxDevices] = {false};
+    const int dev = mbs::current_device();
+    if (!configured[dev]) {
         MBS_CHECK_CUDA(cudaFuncSetAttribute(conv_halo64_kernel<CHUNKS, STAGES, NG>,
                                             cudaFuncAttributeMaxDynamicSharedMemorySize, Plan::DYN_BYTES));
-        configured = true;
+        configured[dev] = true;
     }
     const int grid = kp.num_tiles < sm_count() ? kp.num_tiles : sm_count();
     conv_halo64_kernel<CHUNKS, STAGES, NG><<<grid, threads_for_groups(NG), Plan::DYN_BYTES, stream>>>(a0, a1, b, dmap, kp);
@@ -1699,10 +1702,11 @@ extern "C" int mbs_conv_gemm(const mbs_conv_desc *d, void *stream_) {
 template <int BN, int STAGES>
 int launch_wgrad_nhwc(const CUtensorMap &a, const CUtensorMap &b, const WgradNhwcParams &wp, int grid, cudaStream_t stream) {
     constexpr int dyn = STAGES * (2 * WG_BLOCK + (BN / 64) * WG_BLOCK) + 8 * (2 * STAGES + 1) + 16 + 1024;
-    static bool configured = false;
-    if (!configured) {
+    static bool configured[mbs::kMaxDevices] = {false};
+    const int dev = mbs::current_device();
+    if (!configured[dev]) {
         MBS_CHECK_CUDA(cudaFuncSetAttribute(wgrad_nhwc_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn));
-        configured = true;
+        configured[dev] = true;
     }
     wgrad_nhwc_kernel<BN, STAGES><<<grid, NUM_THREADS, dyn, stream>>>(a, b, wp);
     MBS_CHECK_LAUNCH();
@@ -1752,10 +1756,11 @@ extern "C" int mbs_conv_wgrad(const mbs_wgrad_desc *d, void *stream_) {
         if (rc) return rc;
         rc = make_act_map(&b, d->b, d->N, d->Ho, d->Wo, d->Cn, d->ldb, d->coffb, 1, 8, 8);
         if (rc) return rc;
-        static bool configured = false;
-        if (!configured) {
+        static bool configured[mbs::kMaxDevices] = {false};
+        const int dev = mbs::current_device();
+        if (!configured[dev]) {
             MBS_CHECK_CUDA(cudaFuncSetAttribute(wgrad_halo64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WH_DYN));
-            configured = true;
+            configured[dev] = true;
         }
         wgrad_halo64_kernel<<<chunks * splits, NUM_THREADS, WH_DYN, stream>>>(a, b, wp);
         MBS_CHECK_LAUNCH();

@@ -215,6 +215,23 @@ def segment_stack(net, stack, ths=(0.10, 0.45), device=None, frames=None, out=No
     return out
 
 
+def segment_stack_sharded(net, stack, ths=(0.10, 0.45), device=None, transport="auto"):
+    """``segment_stack`` under a torchrun launch: frame t -> rank t mod world, every rank runs its frames on its own
+    GPU (weights replicated, no collective on the data path), rank 0 receives all masks and returns the full
+    [T,H,W] uint16 array (the other ranks return None).  Without a process group it is plain ``segment_stack``."""
+    from . import sharding
+    stack = np.asarray(stack)
+    if stack.ndim == 2:
+        stack = stack[None]
+    T, H, W = stack.shape
+
+    def work(indices, outs):
+        segment_stack(net, stack, ths=ths, device=device, frames=indices, out=outs[0])
+
+    res = sharding.run_sharded(work, T, [((H, W), np.uint16)], transport=transport)
+    return None if res is None else res[0]
+
+
 class InferWorker:
     """The numerical part of the reference's ``InferWorker`` (src/inference/infer.py:30-94, 328-376):
     same constructor argument order; OMERO transport / Qt signals are out of scope."""

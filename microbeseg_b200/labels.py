@@ -157,3 +157,24 @@ def create_labels(masks):
         cells[s:s + k] = pin_c[:k].numpy()
         neighs[s:s + k] = pin_n[:k].numpy()
     return cells, neighs, mals
+
+
+def create_labels_sharded(masks, transport="auto"):
+    """``create_labels`` under a torchrun launch: crop i -> rank i mod world, each rank runs its
+    crops on its own GPU, rank 0 returns (cell_dist, neighbor_dist, max_mal) for all crops, the other ranks None.
+    Mirrors the crop loop of CreateLabelsWorker.create_labels (train.py:63-96), whose iterations are independent."""
+    from . import sharding
+    masks = np.asarray(masks)
+    if masks.ndim == 2:
+        masks = masks[None]
+    n, H, W = masks.shape
+
+    def work(indices, outs):
+        if len(indices) == 0:
+            return
+        c, nb, mal = create_labels(masks[indices])
+        for j, t in enumerate(indices):
+            outs[0][t], outs[1][t], outs[2][t] = c[j], nb[j], mal[j]
+
+    res = sharding.run_sharded(work, n, [((H, W), np.float32), ((H, W), np.float32), ((), np.int32)], transport=transport)
+    return None if res is None else tuple(res)

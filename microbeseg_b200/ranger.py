@@ -129,4 +129,5 @@ class Ranger(Optimizer):
                                                 1 if step % group['k'] == 0 else 0, self.alpha, nat.stream_ptr()),
                               "ranger_step")
                 self.launches_last_step += 1
+        nat.note_raw_write()        # parameters changed behind torch's version counters: cached eval engines are stale
         return loss

@@ -175,9 +175,13 @@ class TrainEngine:
         With ``use_graph`` (default) the first call of a given batch shape runs eagerly (it also warms up every kernel
         configuration), the second call captures the whole step -- ~600 kernel launches plus the torch glue -- into ONE
         CUDA graph, and later calls only copy the batch into the static inputs and replay it."""
+        nat.note_raw_write()        # BatchNorm running statistics are updated through raw pointers
         if not self.use_graph:
             return self._forward_backward(img, border_label, cell_label)
-        key = (tuple(img.shape), img.dtype)
+        # the captured graph bakes in parameter / buffer storage and the loss kind: re-capture when any of them moves
+        # (net.to(), load_state_dict(assign=True), p.data rebinding)
+        key = (tuple(img.shape), img.dtype, self.loss_kind) + tuple(
+            t.data_ptr() for t in list(self.net.parameters()) + list(self.net.buffers()))
         st = self._graphs.get(key)
         if st is None:                                   # eager warm-up call
             self._graphs[key] = {"calls": 1}
@@ -202,7 +206,7 @@ class TrainEngine:
         for p, gr in st["grads"]:
             p.grad = gr
         self.launches_last_step = st["launches"]
-        return st["loss"]
+        return st["loss"].clone()       # the static loss tensor is overwritten by the next replay
 
     def _forward_backward(self, img, border_label, cell_label):
         net = self.net
@@ -402,6 +406,19 @@ def allreduce_gradients(net, world_size):
         off += k
     torch._foreach_copy_(grads, views)          # one multi-tensor launch instead of 270 small copies
     return flat.numel()
+
+
+DDP_DESCRIPTION = "one flat NCCL all-reduce per step (mean over ranks)"
+
+
+def broadcast_module_state(net, src=0):
+    """Replicas start from rank ``src``'s parameters and BatchNorm buffers, like nn.DataParallel's replicate
+    (unets.py:51-52).  During training every rank keeps its own batch statistics (DataParallel semantics); call this
+    again before evaluating / saving so that rank 0's running statistics are the ones that survive, as in the reference."""
+    import torch.distributed as dist
+    for t in list(net.parameters()) + list(net.buffers()):
+        dist.broadcast(t.data, src)
+    nat.note_raw_write()
 
 
 def train_step(engine, optimizer, img, border_label, cell_label, world_size=1):

@@ -117,8 +117,11 @@ class _NetBase(nn.Module):
 
     # -- CUDA engine ---------------------------------------------------------------------------
     def _param_version(self):
-        return tuple(int(t._version) for t in list(self.parameters()) + list(self.buffers())) + tuple(
-            t.data_ptr() for t in self.parameters())
+        # raw_write_epoch: the training kernels (BatchNorm running statistics, fused optimizer steps) write through
+        # raw pointers and do not bump torch's version counters
+        return (nat.raw_write_epoch(),) + tuple(
+            int(t._version) for t in list(self.parameters()) + list(self.buffers())) + tuple(
+            t.data_ptr() for t in list(self.parameters()) + list(self.buffers()))
 
     def engine(self):
         """Packed-weight execution plan; rebuilt when parameters change (load_state_dict, .to())."""

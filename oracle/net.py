@@ -38,23 +38,49 @@ def _bn(x, sd, prefix):
     return F.instance_norm(x, eps=1e-5)
 
 
-def _conv_block(x, sd, prefix, act):
+# Storage-policy emulation ("check mode").  The CUDA path stores every layer output and every tensor-core weight in
+# bf16 and accumulates in fp32.  With _POLICY["bf16"] the oracle rounds exactly those tensors to bf16 (values stay
+# fp32 tensors): the weights of every conv with more than one input channel, and every layer output except the last
+# 64-channel map, which the fused 1x1 head consumes unrounded.  What remains between this oracle and the CUDA path is
+# fp32 summation order (and the bf16 roundings that flip because of it), so a kernel bug shows up far above the
+# residual, while the plain fp32 oracle measures the precision policy itself.
+_POLICY = {"bf16": False, "keep_next": False}
+
+
+def _r(x):
+    return x.to(torch.bfloat16).float() if _POLICY["bf16"] else x
+
+
+def _w(w):
+    return w.to(torch.bfloat16).float() if (_POLICY["bf16"] and w.shape[1] > 1) else w
+
+
+def _out(x):
+    """a layer output as the CUDA path stores it"""
+    if _POLICY["keep_next"]:
+        _POLICY["keep_next"] = False
+        return x
+    return _r(x)
+
+
+def _conv_block(x, sd, prefix, act, last=False):
     # conv -> act -> norm -> conv -> act -> norm (unets.py:112-160; note: norm AFTER the activation)
-    x = _bn(_act(F.conv2d(x, sd[prefix + ".conv.0.weight"], sd[prefix + ".conv.0.bias"], padding=1), act), sd,
-            prefix + ".conv.2")
-    x = _bn(_act(F.conv2d(x, sd[prefix + ".conv.3.weight"], sd[prefix + ".conv.3.bias"], padding=1), act), sd,
-            prefix + ".conv.5")
+    x = _out(_bn(_act(F.conv2d(x, _w(sd[prefix + ".conv.0.weight"]), sd[prefix + ".conv.0.bias"], padding=1), act), sd,
+                 prefix + ".conv.2"))
+    _POLICY["keep_next"] = last
+    x = _out(_bn(_act(F.conv2d(x, _w(sd[prefix + ".conv.3.weight"]), sd[prefix + ".conv.3.bias"], padding=1), act), sd,
+                 prefix + ".conv.5"))
     return x
 
 
 def _conv_pool(x, sd, prefix, act):
-    x = F.conv2d(x, sd[prefix + ".conv_pool.0.weight"], sd[prefix + ".conv_pool.0.bias"], stride=2, padding=1)
-    return _bn(_act(x, act), sd, prefix + ".conv_pool.2")
+    x = F.conv2d(x, _w(sd[prefix + ".conv_pool.0.weight"]), sd[prefix + ".conv_pool.0.bias"], stride=2, padding=1)
+    return _out(_bn(_act(x, act), sd, prefix + ".conv_pool.2"))
 
 
 def _upconv(x, sd, prefix):
-    x = F.conv_transpose2d(x, sd[prefix + ".up.0.weight"], sd[prefix + ".up.0.bias"], stride=2)
-    return _bn(x, sd, prefix + ".norm")            # no activation (unets.py:261-262)
+    x = F.conv_transpose2d(x, _w(sd[prefix + ".up.0.weight"]), sd[prefix + ".up.0.bias"], stride=2)
+    return _out(_bn(x, sd, prefix + ".norm"))      # no activation (unets.py:261-262)
 
 
 def n_levels(sd):
@@ -79,17 +105,22 @@ def decoder(sd, x, skips, act, name):
     for i, s in enumerate(skips):
         x = _upconv(x, sd, f"{name}Upconv.{i}")
         x = torch.cat([x, s], 1)                   # up first, then skip (unets.py:492)
-        x = _conv_block(x, sd, f"{name}Conv.{i}", act)
+        x = _conv_block(x, sd, f"{name}Conv.{i}", act, last=(i == len(skips) - 1))
     k = len(skips)
     return F.conv2d(x, sd[f"{name}Conv.{k}.weight"], sd[f"{name}Conv.{k}.bias"])
 
 
 @torch.no_grad()
-def dunet_forward(sd, x, act="relu"):
-    """DUNet.forward (unets.py:463-506): returns (x1 = border/neighbour map, x2 = cell map)."""
+def dunet_forward(sd, x, act="relu", policy="fp32"):
+    """DUNet.forward (unets.py:463-506): returns (x1 = border/neighbour map, x2 = cell map).
+    ``policy='bf16'``: emulate the CUDA path's bf16 storage (see _POLICY); default = the reference's plain fp32."""
     sd = {k: v.float() for k, v in sd.items() if v.dtype.is_floating_point}
-    b, skips = encoder(sd, x.float(), act)
-    return decoder(sd, b, skips, act, "decoder1"), decoder(sd, b, skips, act, "decoder2")
+    _POLICY["bf16"], _POLICY["keep_next"] = (policy == "bf16"), False
+    try:
+        b, skips = encoder(sd, x.float(), act)
+        return decoder(sd, b, skips, act, "decoder1"), decoder(sd, b, skips, act, "decoder2")
+    finally:
+        _POLICY["bf16"], _POLICY["keep_next"] = False, False
 
 
 @torch.no_grad()

@@ -117,3 +117,60 @@ def test_gradient_allreduce_two_ranks_gloo():
         p.join(timeout=60)
         assert p.exitcode == 0
     assert ok and n == total
+
+
+def _sharded_worker(rank, world, port, transport, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    sys.path.insert(0, ROOT)
+    from microbeseg_b200 import sharding
+    T, H, W = 7, 3, 5
+    seen = []
+
+    def work(indices, outs):          # stand-in for the per-frame CUDA path: frame t -> mask full of t+1, score t/2
+        for t in indices:
+            seen.append(t)
+            outs[0][t] = np.full((H, W), t + 1, np.uint16)
+            outs[1][t] = np.float32(t / 2)
+
+    res = sharding.run_sharded(work, T, [((H, W), np.uint16), ((), np.float32)], transport=transport)
+    if rank == 0:
+        q.put((res[0].tolist(), res[1].tolist(), seen))
+    else:
+        assert res is None and seen == sharding.shard_indices(T, rank, world)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def _run_sharded_case(transport, port):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_sharded_worker, args=(r, 2, port, transport, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    masks, scores, seen0 = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    masks = np.array(masks)
+    assert masks.shape == (7, 3, 5) and all((masks[t] == t + 1).all() for t in range(7))      # every frame once, on rank 0
+    assert scores == [t / 2 for t in range(7)] and seen0 == [0, 2, 4, 6]
+
+
+def test_run_sharded_gathers_on_rank0_shared_memory():
+    """product multi-GPU path (infer_script_local.py under torchrun, labels.create_labels_sharded): rows computed by
+    each rank land on rank 0 through the /dev/shm array; world_size 2, gloo"""
+    _run_sharded_case("auto", 29621)
+    assert not [f for f in os.listdir("/dev/shm") if f.startswith("mbseg_")]        # the shared arrays are unlinked
+
+
+def test_run_sharded_gathers_on_rank0_point_to_point():
+    """same, ranks on different hosts: rows travel to rank 0 over the CPU backend"""
+    _run_sharded_case("p2p", 29623)
+
+
+def test_run_sharded_without_process_group():
+    from microbeseg_b200 import sharding
+    res = sharding.run_sharded(lambda idx, outs: [outs[0].__setitem__(t, t * 2) for t in idx], 5, [((), np.int64)])
+    assert res[0].tolist() == [0, 2, 4, 6, 8] and sharding.dist_info() == (0, 1)

@@ -2,8 +2,8 @@
 
 Tolerance policy (stated): activations and weights are bf16, accumulation fp32.
 Against the fp32 reference the distance maps must agree within
-    max |err| <= 2.5e-2 * max|ref|   and   mean |err| <= 4e-3 * max|ref|
-(for real models the maps are O(1), i.e. <= 2.5e-2 absolute), and the instance masks derived from
+    max |err| <= 2e-2 * max|ref|   and   mean |err| <= 4e-3 * max|ref|
+(for real models the maps are O(1), i.e. <= 2e-2 absolute), and the instance masks derived from
 both maps must agree (object count within 1 %, matched IoU > 0.9 for >= 99 % of objects)."""
 import ctypes
 import glob
@@ -18,7 +18,7 @@ from oracle import net as onet
 
 pytestmark = pytest.mark.gpu
 HERE = os.path.dirname(os.path.abspath(__file__))
-REL_MAX, REL_MEAN = 2.5e-2, 4e-3
+REL_MAX, REL_MEAN = 2e-2, 4e-3
 
 
 def _build(filters, act, seed, pool="conv", norm="bn"):
@@ -368,21 +368,64 @@ def _match_ap50(ref, got):
     return tp / max(tp + fp + fn, 1), float(np.mean(ious)) if ious else 0.0
 
 
+def _percentile_err(got, ref, q=99.99):
+    return float(np.percentile(np.abs(got - ref).ravel(), q))
+
+
+@pytest.mark.parametrize("size,seed,with_bf16_policy", [(1024, 1234, True), (2048, 2000, False)])
+def test_full_network_at_baseline_sizes_vs_fp32_oracle(native_lib, size, seed, with_bf16_policy):
+    """Whole DUNet[64,1024] on BASELINE config 1 (one 1024^2 frame, seed 1234) and one config-2 frame (2048^2,
+    seed 2000) against the fp32 oracle (SURVEY 8(c) policy).  Stated tolerance, relative to scale = max(1, max|ref|)
+    (the seeded He-init maps are O(5), real distance maps O(1)):  max |err| <= 2e-2 * scale, 99.99-percentile
+    <= 1e-2 * scale, mean <= 2e-3 * scale.  "Check mode" at 1024^2: against the oracle run with the CUDA path's
+    bf16 storage policy (oracle/net.py::_POLICY) the residual is only summation order and the bf16 roundings it
+    flips, so it must be several times smaller than the policy error itself: max <= 8e-3 * scale, mean <= 4e-4."""
+    from microbeseg_b200 import synthetic as sy
+    torch.set_grad_enabled(False)
+    net, sd = _build((64, 1024), "relu", 23)
+    img = sy.synth_frame(size, size, seed)
+    x = torch.from_numpy(_norm(img)[None, None])
+    ob, oc = onet.dunet_forward(sd, x, "relu")
+    dev = torch.from_numpy(img.view(np.int16)).cuda()
+    b, c = net.forward_frame(dev, [0, 0], float(img.min()), float(img.max()))
+    rows = []
+    for name, got, ref in (("border", b, ob), ("cell", c, oc)):
+        g, r = got[0, 0].cpu().numpy(), ref[0, 0].numpy()
+        scale = max(1.0, float(np.abs(r).max()))
+        e = np.abs(g - r)
+        rows.append((name, scale, float(e.max()), _percentile_err(g, r), float(e.mean())))
+        assert np.isfinite(g).all()
+        assert e.max() <= 2e-2 * scale and _percentile_err(g, r) <= 1e-2 * scale and e.mean() <= 2e-3 * scale, rows
+    print(f"\nfull-size parity {size}^2 vs fp32 oracle (name, scale, max, p99.99, mean): {rows}")
+    if with_bf16_policy:
+        pb, pc = onet.dunet_forward(sd, x, "relu", policy="bf16")
+        rows = []
+        for name, got, ref in (("border", b, pb), ("cell", c, pc)):
+            g, r = got[0, 0].cpu().numpy(), ref[0, 0].numpy()
+            scale = max(1.0, float(np.abs(r).max()))
+            e = np.abs(g - r)
+            rows.append((name, scale, float(e.max()), _percentile_err(g, r), float(e.mean())))
+            assert e.max() <= 8e-3 * scale and e.mean() <= 4e-4 * scale, rows
+        print(f"check mode {size}^2 vs bf16-storage oracle (name, scale, max, p99.99, mean): {rows}")
+    assert native_lib.mbs_debug_flags(1) == 0
+
+
 def test_instance_level_agreement_with_fp32_reference_path(native_lib):
-    """north_star: bf16 CUDA path vs fp32 reference path must agree at instance level.  The random-init net
-    gets its two 1x1 heads least-squares fitted to synthetic distance maps (calibrate.fit_heads) so that the
-    maps are cell-like; then  CUDA net + CUDA post-processing  is compared with  fp32 oracle net + oracle
-    post-processing  on unseen frames.  Stated thresholds: mean AP@0.5 over the frames >= 0.93, matched mean IoU >= 0.92 per frame,
-    map error within the bf16 tolerance.  (The fitted random-feature maps are low-contrast, so a few seeds sit
-    right at the thresholds; a trained model leaves far more margin.)"""
+    """north_star: the bf16 CUDA path and the fp32 reference path must agree at instance level (stated threshold:
+    mean AP@0.5 >= 0.99, matched mean IoU >= 0.95 per frame).  No checkpoint is reachable offline, so
+    the net is trained for a few hundred steps on synthetic crops with this repo's own CUDA training step
+    (calibrate.train_briefly) until its maps are cell-like; then  CUDA net + CUDA post-processing  is compared with
+    fp32 oracle net (same trained weights) + oracle post-processing  on unseen frames."""
     from microbeseg_b200 import calibrate
     from microbeseg_b200.inference import FrameSegmenter
     from oracle import postproc as op
-    torch.set_grad_enabled(False)
     net, _ = _build((64, 256), "relu", 101)
-    train = [calibrate.synthetic_training_pair(256, 256, 3000 + 10 * k)[:3] for k in range(3)]
-    calibrate.fit_heads(net, train)
-    sd = {k: v.detach().cpu() for k, v in net.state_dict().items()}
+    with torch.enable_grad():
+        losses = calibrate.train_briefly(net, steps=500, crop=256, n_crops=48, batch=8)
+    print("\ntrain_briefly losses:", [round(v, 4) for v in losses])
+    assert losses[-1] < 0.5 * losses[0], losses
+    torch.set_grad_enabled(False)
+    sd = {k: v.detach().cpu().clone() for k, v in net.state_dict().items()}
     seg = FrameSegmenter(net, (0.10, 0.45))
     aps, n_obj = [], 0
     for k in range(4):
@@ -392,14 +435,42 @@ def test_instance_level_agreement_with_fp32_reference_path(native_lib):
         x = 2 * (frame.astype(np.float32) - lo) / (hi - lo) - 1
         ob, oc = onet.dunet_forward(sd, torch.from_numpy(x[None, None]), "relu")
         b, c = net(torch.from_numpy(x[None, None]).cuda())
-        _check(c.cpu().numpy(), oc.numpy(), "cell(fitted)")
-        _check(b.cpu().numpy(), ob.numpy(), "border(fitted)")
+        _check(c.cpu().numpy(), oc.numpy(), "cell(trained)")
+        _check(b.cpu().numpy(), ob.numpy(), "border(trained)")
         ref = op.distance_postprocessing(ob[0, 0, :, :, None].numpy(), oc[0, 0, :, :, None].numpy(), 0.45, 0.10)
         ap, miou = _match_ap50(ref, got)
-        aps.append((ap, miou))
+        ap_gt, _ = _match_ap50(mask, got)
+        aps.append((round(ap, 4), round(miou, 4), round(ap_gt, 3), int(ref.max())))
         n_obj += int(ref.max())
-    assert n_obj > 40, n_obj                       # the fitted heads do produce seeds / objects
-    assert float(np.mean([a for a, _ in aps])) >= 0.93 and min(m for _, m in aps) >= 0.92, aps
+    print("instance agreement (AP@0.5 vs fp32 path, matched mIoU, AP@0.5 vs ground truth, objects):", aps)
+    assert n_obj > 150, n_obj                       # the trained net does segment cells
+    assert float(np.mean([a[0] for a in aps])) >= 0.99 and min(a[1] for a in aps) >= 0.95, aps
+
+
+def test_eval_after_raw_pointer_training_steps_uses_fresh_weights(native_lib):
+    """the fused Ranger step and the BatchNorm running-statistics update write through raw pointers
+    and do not bump tensor versions; net.eval()(x) after such steps must not reuse the engine packed before them."""
+    from microbeseg_b200.ranger import Ranger
+    from microbeseg_b200.training import TrainEngine, train_step
+    from microbeseg_b200.unets import _Engine
+    net, _ = _build((64, 128), "mish", 77)
+    rng = np.random.default_rng(77)
+    x = torch.from_numpy(rng.uniform(-1, 1, (2, 1, 32, 32)).astype(np.float32)).cuda()
+    t1 = torch.from_numpy(rng.uniform(0, 1, (2, 1, 32, 32)).astype(np.float32)).cuda()
+    t2 = torch.from_numpy(rng.uniform(0, 1, (2, 1, 32, 32)).astype(np.float32)).cuda()
+    with torch.no_grad():
+        before = [t.clone() for t in net(x)]
+    net.train()
+    eng, opt = TrainEngine(net), Ranger(net.parameters(), lr=1e-2)
+    with torch.enable_grad():
+        for _ in range(4):
+            train_step(eng, opt, x, t1, t2)
+    net.eval()
+    with torch.no_grad():
+        after = net(x)
+        fresh = _Engine(net).run(x.reshape(2, 32, 32).contiguous(), 0, 0, 1.0, 0.0)
+    assert not torch.equal(before[1], after[1])
+    assert torch.equal(after[0], fresh[0]) and torch.equal(after[1], fresh[1])
 
 
 def test_cli_infer_script_local(native_lib, tmp_path):
