@@ -228,6 +228,24 @@ int mbs_distance_labels(const uint16_t *masks, int n_crops, int H, int W, int ma
                         int radius_hint, float *cell_dist, float *neighbor_dist, int32_t *max_mal_out,
                         int32_t *error_out, void *workspace, size_t workspace_bytes, void *stream);
 
+/* ---------------------------------------------------------------------------------------- */
+/* mask -> polygon ROI encoding                                           */
+/* ---------------------------------------------------------------------------------------- */
+/*
+ * Outer contour of every instance of a uint16 mask, in the point order of
+ * cv2.findContours(RETR_TREE, CHAIN_APPROX_NONE) on the instance's own crop.
+ * Replaces: get_indices_pandas (src/utils/hull_polygon.py:8-42) + cv2_countour (:45-89), called once per cell from
+ *   src/inference/infer.py:273-289.  Scope: each id is one 8-connected component (watershed labels); for an
+ *   instance with holes the outer contour is returned (the reference's result when its shapely test holds, :61-75).
+ * mbs_contour_first: first[l] = linear index of the first raster pixel of id l+1 (INT32_MAX if absent), l < n_labels.
+ * mbs_contour_trace: offsets == NULL -> counting pass, counts[l] = number of contour points of id l+1;
+ *                    offsets != NULL -> writing pass, points_yx[2*(offsets[l]+k)] = y, [...+1] = x of point k.
+ * overflow (device int32, caller zeroes it): set if a walk hit its step guard (cannot happen for a valid mask).
+ */
+int mbs_contour_first(const uint16_t *mask, int H, int W, int n_labels, int32_t *first, void *stream);
+int mbs_contour_trace(const uint16_t *mask, int H, int W, int n_labels, const int32_t *first, const int64_t *offsets,
+                      int32_t *counts, int32_t *points_yx, int32_t *overflow, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -216,6 +216,11 @@ struct Stats {
     unsigned int changed[3];    // rotating "some tile changed in sweep s" flags (slot s % 3)
     unsigned int ambiguous;     // ambiguity counter
     unsigned int sweeps;
+    unsigned int n_roots;       // tiled path: entries of the tile-local root list
+    unsigned int overflow;      // tiled path: plateau hop counter saturated / root list full -> exact sequential flood
+    // instrumentation of flood_kernel (tools/time_pp.py): tiles visited per sweep, %globaltimer at the end of each sweep
+    unsigned int dbg_tiles[32];
+    unsigned long long dbg_t[36];
 };
 
 // path compression + component areas + component / pixel counts in one pass
@@ -632,7 +637,7 @@ __global__ void ws_sequential_kernel(const float *__restrict__ img, int negate, 
                                      const uint8_t *__restrict__ mask, int H, int W, int *lab, HeapItem *heap,
                                      const Stats *st, int force, uint16_t *out16) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    if (!force && st->ambiguous == 0) return;
+    if (!force && st->ambiguous == 0 && st->overflow == 0) return;
     const int n = H * W;
     int hn = 0;
     for (int i = 0; i < n; ++i) {
@@ -671,6 +676,707 @@ __global__ void ws_sequential_kernel(const float *__restrict__ img, int negate, 
     }
     if (out16)
         for (int i = 0; i < n; ++i) out16[i] = static_cast<uint16_t>(static_cast<unsigned int>(lab[i]));
+}
+
+
+// ==========================================================================================
+// Tiled pipeline (round 2): 3 kernels + a gated exact fallback instead of 13 streaming passes.
+//
+//   front_ccl_kernel   gaussian / clip / tan / thresholds, and the 8-connected labelling of the seed pixels of one
+//                      64x64 tile in SHARED memory (union-find with the smallest raster index as root).  Per pixel it
+//                      writes the smoothed cell value (f32) and ONE 16-bit word: mask bit, seed bit, index of the
+//                      tile-local root.  Global union-find state exists only at the tile-local roots (sparse).
+//   mid_kernel         one cooperative launch over compact lists: unions across tile seams, path compression and
+//                      component areas at the local roots, the area filter (float64, postprocessing.py:46-53), a bitmap
+//                      of the surviving component roots and its prefix popcount = the raster-order relabelling.
+//   flood_kernel       marker watershed, one cooperative launch.  State per pixel = 64 bits [level | hops | label]:
+//                      level L(p) = minimax path cost from the markers, hops = distance to the place where the path
+//                      reached that level (makes the "labelled by an earlier popped neighbour" relation well founded
+//                      on plateaus), label = label of the neighbour with the smallest (level, hops).  64x64 tiles are
+//                      relaxed to their fixed point in shared memory, sweeps are separated by grid barriers, only tiles
+//                      next to a change are revisited.  The last phase writes the uint16 mask and runs the
+//                      order-independence check of the file header (every neighbour at the minimal level must carry
+//                      the pixel's label); any violation triggers the exact sequential flood.
+// ==========================================================================================
+constexpr int CT = 64;                       // tile edge of the tiled pipeline
+constexpr unsigned L16_MASK = 0x8000u, L16_SEED = 0x4000u, L16_IDX = 0x0FFFu;
+constexpr unsigned ORD_INF = 0xFF800000u;    // ordered image of +inf
+constexpr unsigned long long ST_OUTSIDE = ~0ull;                                         // not in the mask: never updated
+constexpr unsigned long long ST_UNREACHED = (static_cast<unsigned long long>(ORD_INF) << 32) | (0xFFFEull << 16);
+constexpr unsigned HOP_MAX = 0x7FFEu;
+
+// float -> unsigned with the same order (finite values and infinities); -0.0 and +0.0 map to the same code
+__device__ __forceinline__ unsigned ord_f32(float v) {
+    v = v + 0.0f;
+    const unsigned b = __float_as_uint(v);
+    return b ^ ((static_cast<unsigned>(static_cast<int>(b) >> 31)) | 0x80000000u);
+}
+
+__device__ __forceinline__ int l16_root_index(unsigned v16, int y, int x, int W) {
+    const int idx = static_cast<int>(v16 & L16_IDX);
+    return ((y & ~(CT - 1)) + (idx >> 6)) * W + (x & ~(CT - 1)) + (idx & (CT - 1));
+}
+
+template <bool BOUNDARY>
+__global__ void __launch_bounds__(256)
+front_ccl_kernel(const float *__restrict__ border, const float *__restrict__ cell, int H, int W, int ld, float th_seed,
+                 float th_cell, float *__restrict__ cell_s, uint16_t *__restrict__ L16, int *G, int *area,
+                 int *__restrict__ roots_list, int list_cap, unsigned *bitmap, Stats *st) {
+    __shared__ float s_in[CT + 4][CT + 4];      // later: tile-local union-find (int[4096])
+    __shared__ float s_y[CT][CT + 4];           // later: tile-local component areas (int[4096])
+    int *s_uf = reinterpret_cast<int *>(&s_in[0][0]);
+    int *s_cnt = reinterpret_cast<int *>(&s_y[0][0]);
+    const int x0 = blockIdx.x * CT, y0 = blockIdx.y * CT;
+    const int tid = threadIdx.x;
+    const int c = tid & (CT - 1), rq = tid >> 6;            // pixel k of this thread: row k*4 + rq, column c
+
+    if (!BOUNDARY) {
+        for (int i = tid; i < (CT + 4) * (CT + 4); i += 256) {
+            const int r = i / (CT + 4), cc = i % (CT + 4);
+            const int yy = reflect_idx(y0 + r - 2, H), xx = reflect_idx(x0 + cc - 2, W);
+            s_in[r][cc] = cell[static_cast<size_t>(yy) * ld + xx];
+        }
+        __syncthreads();
+        for (int i = tid; i < CT * (CT + 4); i += 256) {
+            const int r = i / (CT + 4), cc = i % (CT + 4);
+            s_y[r][cc] = gauss5(s_in[r][cc], s_in[r + 1][cc], s_in[r + 2][cc], s_in[r + 3][cc], s_in[r + 4][cc]);
+        }
+        __syncthreads();
+    }
+    // the bitmap of surviving roots is filled by mid_kernel: clear the words this tile's pixels fall into
+    for (int r = tid; r < CT; r += 256) {
+        const int y = y0 + r;
+        if (y < H) {
+            const long long b0 = static_cast<long long>(y) * W + x0;
+            long long b1 = b0 + CT - 1;
+            const long long rowend = static_cast<long long>(y) * W + W - 1;
+            if (b1 > rowend) b1 = rowend;
+            for (long long w = b0 >> 5; w <= (b1 >> 5); ++w) bitmap[w] = 0u;
+        }
+    }
+    unsigned sdbits = 0, mkbits = 0;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+        const int r = k * 4 + rq;
+        const int y = y0 + r, x = x0 + c;
+        bool sd = false, mk = false;
+        if (y < H && x < W) {
+            const size_t o = static_cast<size_t>(y) * W + x;
+            if (BOUNDARY) {
+                // boundary_postprocessing front end (postprocessing.py:71-77): `border` holds the (H,W,3) probabilities
+                const float p0 = border[3 * o], p1 = border[3 * o + 1], p2 = border[3 * o + 2];
+                int am = 0;
+                float best = p0;
+                if (p1 > best) { best = p1; am = 1; }
+                if (p2 > best) { am = 2; }
+                mk = am == 1;
+                sd = __fmul_rn(p1, __fsub_rn(1.0f, p2)) > 0.5f;
+                cell_s[o] = mk ? 1.0f : 0.0f;
+            } else {
+                const float cs = gauss5(s_y[r][c], s_y[r][c + 1], s_y[r][c + 2], s_y[r][c + 3], s_y[r][c + 4]);
+                float b = border[static_cast<size_t>(y) * ld + x];
+                b = b < 0.0f ? 0.0f : (b > 1.0f ? 1.0f : b);                    // np.clip keeps NaN
+                const float sq = __fmul_rn(b, b);
+                // float32(tan_f64(x)); tan is increasing on [0,1] and tan(0.0499) = 0.04994 < 0.05, so
+                // every sq below 0.0499 lands in the `borders < 0.05 -> 0` branch without evaluating tan
+                float t = 0.0f;
+                if (!(sq < 0.0499f)) {
+                    t = static_cast<float>(tan(static_cast<double>(sq)));
+                    if (t < 0.05f) t = 0.0f;
+                    t = t < 0.0f ? 0.0f : (t > 1.0f ? 1.0f : t);
+                }
+                const float cleaned = __fsub_rn(cs, t);
+                cell_s[o] = cs;
+                mk = cs > th_cell;
+                sd = cleaned > th_seed;
+            }
+        }
+        sdbits |= (sd ? 1u : 0u) << k;
+        mkbits |= (mk ? 1u : 0u) << k;
+    }
+    __syncthreads();                      // s_in / s_y are dead: reuse them as s_uf / s_cnt
+    // ---- tile-local 8-connected labelling on RUNS: the seed pixels of a row are a 64-bit mask, a pixel finds the start
+    // of its horizontal run with two bit operations, and only run starts take part in the union-find (one union per
+    // pair of touching runs in consecutive rows instead of up to four per pixel)
+    __shared__ unsigned s_row32[CT][2];
+    const int lane = tid & 31;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+        const unsigned bal = __ballot_sync(0xffffffffu, (sdbits >> k) & 1u);
+        if (lane == 0) s_row32[k * 4 + rq][(tid >> 5) & 1] = bal;
+    }
+    __syncthreads();
+    auto row_mask = [&](int r) -> unsigned long long {
+        return static_cast<unsigned long long>(s_row32[r][0]) | (static_cast<unsigned long long>(s_row32[r][1]) << 32);
+    };
+    auto run_start = [](unsigned long long m, int col) -> int {       // first column of the run of ones that contains `col`
+        const unsigned long long below = (1ull << col) - 1ull;
+        const unsigned long long zeros = ~m & below;
+        return zeros ? 64 - __clzll(static_cast<long long>(zeros)) : 0;
+    };
+    auto run_mask = [](unsigned long long m, int start) -> unsigned long long {     // the run of ones that starts at `start`
+        const unsigned long long t = m >> start;
+        const int len = (~t) ? __ffsll(static_cast<long long>(~t)) - 1 : 64;
+        const unsigned long long ones = len >= 64 ? ~0ull : ((1ull << len) - 1ull);
+        return ones << start;
+    };
+    unsigned startbits = 0;               // pixel k is the first pixel of its run
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+        if (!((sdbits >> k) & 1u)) continue;
+        const int r = k * 4 + rq;
+        if (run_start(row_mask(r), c) == c) {
+            startbits |= 1u << k;
+            s_uf[r * CT + c] = r * CT + c;
+            s_cnt[r * CT + c] = 0;
+        }
+    }
+    __syncthreads();
+#pragma unroll 1
+    for (int k = 0; k < 16; ++k) {
+        if (!((startbits >> k) & 1u)) continue;
+        const int r = k * 4 + rq;
+        if (r == 0) continue;
+        const unsigned long long run = run_mask(row_mask(r), c);
+        const unsigned long long above = row_mask(r - 1);
+        unsigned long long touch = above & (run | (run << 1) | (run >> 1));
+        while (touch) {
+            const int bcol = __ffsll(static_cast<long long>(touch)) - 1;
+            const int sa = run_start(above, bcol);
+            uf_union(s_uf, r * CT + c, (r - 1) * CT + sa);
+            touch &= ~run_mask(above, sa);
+        }
+    }
+    __syncthreads();
+    // flatten the run starts, areas of the tile-local components
+#pragma unroll 1
+    for (int k = 0; k < 16; ++k) {
+        if (!((startbits >> k) & 1u)) continue;
+        const int i = (k * 4 + rq) * CT + c;
+        const int rt = uf_find_v(s_uf, i);
+        const unsigned long long run = run_mask(row_mask(k * 4 + rq), c);
+        atomicAdd(&s_cnt[rt], __popcll(run));
+        if (rt != i) *reinterpret_cast<volatile int *>(&s_uf[i]) = rt;      // chains stay valid: rt is a root
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+        const int r = k * 4 + rq;
+        const int y = y0 + r, x = x0 + c;
+        const bool sd = (sdbits >> k) & 1u;
+        int rt = 0;
+        if (sd) rt = uf_find_v(s_uf, r * CT + run_start(row_mask(r), c));
+        const bool isroot = sd && rt == r * CT + c;
+        if (y < H && x < W) {
+            const unsigned v = ((mkbits >> k) & 1u ? L16_MASK : 0u) | (sd ? (L16_SEED | static_cast<unsigned>(rt)) : 0u);
+            L16[static_cast<size_t>(y) * W + x] = static_cast<uint16_t>(v);
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, isroot);
+        if (m) {
+            int base = 0;
+            if (lane == __ffs(m) - 1) base = static_cast<int>(atomicAdd(&st->n_roots, static_cast<unsigned>(__popc(m))));
+            base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
+            if (isroot) {
+                const int g = y * W + x;
+                G[g] = g;
+                area[g] = s_cnt[r * CT + c];
+                const int slot = base + __popc(m & ((1u << lane) - 1u));
+                if (slot < list_cap) roots_list[slot] = g;
+                else atomicExch(&st->overflow, 1u);
+            }
+        }
+    }
+    // seed pixels of the tile -> st->total (one atomic per block)
+    int cnt = __popc(sdbits);
+    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_down_sync(0xffffffffu, cnt, o);
+    __shared__ int s_red[8];
+    if (lane == 0) s_red[tid >> 5] = cnt;
+    __syncthreads();
+    if (tid == 0) {
+        int t = 0;
+        for (int w = 0; w < 8; ++w) t += s_red[w];
+        if (t) atomicAdd(&st->total, static_cast<unsigned long long>(t));
+    }
+}
+
+__device__ __forceinline__ bool keep_area(int area, unsigned long long total, unsigned n_comp, int use_mean) {
+    // postprocessing.py:46-53: min_area = max(0.10 * mean(areas), 4); drop area <= min_area (float64)
+    double min_area = 0.0;
+    if (use_mean && n_comp > 0)
+        min_area = __dmul_rn(0.10, __ddiv_rn(static_cast<double>(total), static_cast<double>(n_comp)));
+    min_area = fmax(min_area, 4.0);
+    return !(static_cast<double>(area) <= min_area);
+}
+
+__global__ void __launch_bounds__(256)
+mid_kernel(const uint16_t *__restrict__ L16, int H, int W, int *G, int *area, const int *__restrict__ roots_list,
+           int list_cap, unsigned *bitmap, int *prefix, int *block_sums, Stats *st, int use_mean) {
+    namespace cg = cooperative_groups;
+    cg::grid_group grid = cg::this_grid();
+    const int gtid = blockIdx.x * blockDim.x + threadIdx.x;
+    const int gsz = gridDim.x * blockDim.x;
+    const int tiles_x = (W + CT - 1) / CT, tiles_y = (H + CT - 1) / CT;
+    __shared__ int s_red[8];
+    __shared__ int s_off;
+    // ---- phase 0: unions across tile seams (8-connectivity: three neighbours on the other side of the seam)
+    {
+        const long long nv = static_cast<long long>(tiles_x - 1) * H, nh = static_cast<long long>(tiles_y - 1) * W;
+        for (long long it = gtid; it < nv + nh; it += gsz) {
+            int ya, xa, yb0, xb0, dy, dx;
+            if (it < nv) {
+                const int k = static_cast<int>(it / H) + 1;
+                ya = static_cast<int>(it % H); xa = k * CT - 1; yb0 = ya; xb0 = k * CT; dy = 1; dx = 0;
+            } else {
+                const long long j = it - nv;
+                const int k = static_cast<int>(j / W) + 1;
+                xa = static_cast<int>(j % W); ya = k * CT - 1; yb0 = k * CT; xb0 = xa; dy = 0; dx = 1;
+            }
+            const unsigned va = L16[static_cast<size_t>(ya) * W + xa];
+            if (!(va & L16_SEED)) continue;
+            const int ra = l16_root_index(va, ya, xa, W);
+            for (int s = -1; s <= 1; ++s) {
+                const int yb = yb0 + s * dy, xb = xb0 + s * dx;
+                if (yb < 0 || yb >= H || xb < 0 || xb >= W) continue;
+                const unsigned vb = L16[static_cast<size_t>(yb) * W + xb];
+                if (vb & L16_SEED) uf_union(G, ra, l16_root_index(vb, yb, xb, W));
+            }
+        }
+    }
+    __threadfence();
+    grid.sync();
+    // ---- phase 1: compress the local roots, accumulate areas at the component roots, count components
+    int n_roots = static_cast<int>(*reinterpret_cast<volatile unsigned int *>(&st->n_roots));
+    if (n_roots > list_cap) n_roots = list_cap;
+    {
+        int comps = 0;
+        for (int i = gtid; i < n_roots; i += gsz) {
+            const int lr = roots_list[i];
+            const int r = uf_find_v(G, lr);
+            if (r != lr) {
+                G[lr] = r;
+                atomicAdd(&area[r], area[lr]);
+            } else {
+                ++comps;
+            }
+        }
+        int v = comps;
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+        if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = v;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int t = 0;
+            for (int w = 0; w < 8; ++w) t += s_red[w];
+            if (t) atomicAdd(&st->n_comp, static_cast<unsigned>(t));
+        }
+    }
+    __threadfence();
+    grid.sync();
+    // ---- phase 2: area filter -> bitmap of the surviving component roots
+    {
+        const unsigned long long total = *reinterpret_cast<volatile unsigned long long *>(&st->total);
+        const unsigned n_comp = *reinterpret_cast<volatile unsigned int *>(&st->n_comp);
+        for (int i = gtid; i < n_roots; i += gsz) {
+            const int lr = roots_list[i];
+            if (*reinterpret_cast<volatile int *>(&G[lr]) != lr) continue;
+            const int a = *reinterpret_cast<volatile int *>(&area[lr]);
+            if (keep_area(a, total, n_comp, use_mean)) atomicOr(&bitmap[lr >> 5], 1u << (lr & 31));
+        }
+    }
+    __threadfence();
+    grid.sync();
+    // ---- phase 3: prefix popcount over the bitmap words (rank of a root = 1 + number of surviving roots before it)
+    const int nwords = static_cast<int>((static_cast<long long>(H) * W + 31) >> 5);
+    const int per = (nwords + gridDim.x - 1) / gridDim.x;
+    const int w0 = blockIdx.x * per;
+    const int w1 = (w0 + per < nwords) ? w0 + per : nwords;
+    {
+        int v = 0;
+        for (int w = w0 + threadIdx.x; w < w1; w += blockDim.x) v += __popc(*reinterpret_cast<volatile unsigned *>(&bitmap[w]));
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+        __syncthreads();
+        if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = v;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int t = 0;
+            for (int w = 0; w < 8; ++w) t += s_red[w];
+            block_sums[blockIdx.x] = t;
+        }
+    }
+    __threadfence();
+    grid.sync();
+    {
+        int v = 0;
+        for (int b = threadIdx.x; b < static_cast<int>(blockIdx.x); b += blockDim.x) v += *reinterpret_cast<volatile int *>(&block_sums[b]);
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+        __syncthreads();
+        if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = v;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int t = 0;
+            for (int w = 0; w < 8; ++w) t += s_red[w];
+            s_off = t;
+        }
+        __syncthreads();
+        int running = s_off;
+        for (int base = w0; base < w1; base += blockDim.x) {
+            const int w = base + threadIdx.x;
+            const int pc = w < w1 ? __popc(*reinterpret_cast<volatile unsigned *>(&bitmap[w])) : 0;
+            int inc = pc;
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, inc, o);
+                if ((threadIdx.x & 31) >= o) inc += t;
+            }
+            __syncthreads();
+            if ((threadIdx.x & 31) == 31) s_red[threadIdx.x >> 5] = inc;
+            __syncthreads();
+            int woff = 0, tot = 0;
+            for (int q = 0; q < 8; ++q) {
+                if (q < (threadIdx.x >> 5)) woff += s_red[q];
+                tot += s_red[q];
+            }
+            if (w < w1) prefix[w] = running + woff + inc - pc;
+            running += tot;
+        }
+        if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) st->n_markers = static_cast<unsigned>(running);
+    }
+}
+
+// marker id (1-based raster rank of the surviving seed component) of a seed pixel, 0 if its component was dropped
+__device__ __forceinline__ int marker_of(unsigned v16, int y, int x, int W, const int *__restrict__ G,
+                                         const unsigned *__restrict__ bitmap, const int *__restrict__ prefix) {
+    const int lr = l16_root_index(v16, y, x, W);
+    const int r = G[lr];
+    const unsigned w = bitmap[r >> 5];
+    if (!((w >> (r & 31)) & 1u)) return 0;
+    return prefix[r >> 5] + __popc(w & ((1u << (r & 31)) - 1u)) + 1;
+}
+
+// generic entry (mbs_pp_watershed): state / labels from an explicit marker image
+__global__ void flood_init_kernel(const float *__restrict__ img, const int *__restrict__ markers, const uint8_t *__restrict__ mask,
+                                  int n, unsigned long long *__restrict__ state, int *__restrict__ lab32) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const bool m = mask[i] != 0;
+    const int mk = m ? markers[i] : 0;
+    unsigned long long s = ST_OUTSIDE;
+    if (m) s = mk != 0 ? ((static_cast<unsigned long long>(ord_f32(img[i])) << 32) | (1ull << 16)) : ST_UNREACHED;
+    state[i] = s;
+    lab32[i] = mk;
+}
+
+struct FloodParams {
+    const float *img;                // flood image (negate != 0: -img)
+    int negate;
+    const uint16_t *L16;             // fused mode: seeds / mask / local roots from front_ccl_kernel
+    const int *G;
+    const unsigned *bitmap;
+    const int *prefix;
+    unsigned long long *state;
+    int *lab32;                      // LAB32 only
+    int H, W;
+    Stats *st;
+    uint8_t *tile_changed;
+    uint16_t *out16;                 // fused mode
+    int *out32;                      // LAB32 mode
+};
+
+// shared memory of flood_kernel: state tile with a 1-pixel halo, flood values, two work queues, "queued" bits
+constexpr int FL_STATE_BYTES = (CT + 2) * (CT + 2) * 8;
+constexpr int FL_V_BYTES = CT * CT * 4;
+constexpr int FL_Q_BYTES = 2 * CT * CT * 2;
+constexpr int FL_FLAG_BYTES = (CT * CT / 32) * 4;
+constexpr int FL_MISC_BYTES = 64;
+constexpr int FL_LAB_BYTES = (CT + 2) * (CT + 2) * 4;
+constexpr int FLOOD_SMEM16 = FL_STATE_BYTES + FL_V_BYTES + FL_Q_BYTES + FL_FLAG_BYTES + FL_MISC_BYTES;
+constexpr int FLOOD_SMEM32 = FLOOD_SMEM16 + FL_LAB_BYTES;
+constexpr unsigned EDGE_TOP = 1u, EDGE_BOTTOM = 2u, EDGE_LEFT = 4u, EDGE_RIGHT = 8u;
+
+// The in-tile relaxation is EVENT DRIVEN: a pixel is (re)evaluated only when one of its 4-neighbours changed.  Work is
+// proportional to the number of floodable pixels (a few evaluations each) instead of tile area x wavefront depth.
+template <bool LAB32>
+__global__ void __launch_bounds__(256)
+flood_kernel(const FloodParams p) {
+    namespace cg = cooperative_groups;
+    cg::grid_group grid = cg::this_grid();
+    extern __shared__ unsigned long long smem_u64[];
+    unsigned char *smem = reinterpret_cast<unsigned char *>(smem_u64);
+    unsigned long long(*sS)[CT + 2] = reinterpret_cast<unsigned long long(*)[CT + 2]>(smem);
+    unsigned *sV = reinterpret_cast<unsigned *>(smem + FL_STATE_BYTES);
+    unsigned short *sQ = reinterpret_cast<unsigned short *>(smem + FL_STATE_BYTES + FL_V_BYTES);      // [2][4096]
+    unsigned *sFlag = reinterpret_cast<unsigned *>(smem + FL_STATE_BYTES + FL_V_BYTES + FL_Q_BYTES);
+    int *sMisc = reinterpret_cast<int *>(smem + FL_STATE_BYTES + FL_V_BYTES + FL_Q_BYTES + FL_FLAG_BYTES);   // [0],[1]: queue sizes, [2]: edge bits, [3]: any change
+    int(*sLab)[CT + 2] = reinterpret_cast<int(*)[CT + 2]>(smem + FLOOD_SMEM16);
+    const int H = p.H, W = p.W;
+    const int tiles_x = (W + CT - 1) / CT, tiles_y = (H + CT - 1) / CT;
+    const int ntiles = tiles_x * tiles_y;
+    const int tx = threadIdx.x & (CT - 1), tq = threadIdx.x >> 6;      // column, and rows k*4 + tq (k = 0..15)
+    const int lane = threadIdx.x & 31;
+    int sweep = 0;
+    bool overflow = false;
+    auto stamp = [&](int slot) {
+        if (blockIdx.x == 0 && threadIdx.x == 0 && slot < 36) {
+            unsigned long long t;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+            p.st->dbg_t[slot] = t;
+        }
+    };
+    stamp(0);
+    for (;;) {
+        const uint8_t *prev = p.tile_changed + ((sweep + 1) & 1) * ntiles;
+        uint8_t *cur = p.tile_changed + (sweep & 1) * ntiles;
+        bool block_changed = false;
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+            const int tyi = tile / tiles_x, txi = tile - tyi * tiles_x;
+            if (sweep > 0) {
+                // a tile is revisited only if a neighbour changed pixels on the edge that faces it
+                const bool need = (txi > 0 && (prev[tile - 1] & EDGE_RIGHT)) || (txi + 1 < tiles_x && (prev[tile + 1] & EDGE_LEFT)) ||
+                                  (tyi > 0 && (prev[tile - tiles_x] & EDGE_BOTTOM)) || (tyi + 1 < tiles_y && (prev[tile + tiles_x] & EDGE_TOP));
+                if (!need) {
+                    if (threadIdx.x == 0) cur[tile] = 0;
+                    continue;
+                }
+            }
+            const int x0 = txi * CT, y0 = tyi * CT;
+            __syncthreads();   // shared tile reuse
+            const bool fused_init = !LAB32 && sweep == 0;
+            if (threadIdx.x == 0 && sweep < 32) atomicAdd(&p.st->dbg_tiles[sweep], 1u);
+            if (threadIdx.x < CT * CT / 32) sFlag[threadIdx.x] = 0u;
+            if (threadIdx.x < 4) sMisc[threadIdx.x] = 0;
+            if (fused_init) {
+                // halo: the neighbouring tiles have no state yet; they are picked up in sweep 1
+                for (int i = threadIdx.x; i < 4 * (CT + 2); i += 256) {
+                    const int side = i / (CT + 2), j = i % (CT + 2);
+                    const int r = side == 0 ? 0 : (side == 1 ? CT + 1 : j);
+                    const int c = side <= 1 ? j : (side == 2 ? 0 : CT + 1);
+                    sS[r][c] = ST_OUTSIDE;
+                }
+#pragma unroll 4
+                for (int k = 0; k < 16; ++k) {
+                    const int r = k * 4 + tq;
+                    const int y = y0 + r, x = x0 + tx;
+                    unsigned long long s = ST_OUTSIDE;
+                    if (y < H && x < W) {
+                        const size_t i = static_cast<size_t>(y) * W + x;
+                        const unsigned v16 = p.L16[i];
+                        if (v16 & L16_MASK) {
+                            const float v = p.img[i];
+                            const unsigned vo = ord_f32(p.negate ? -v : v);
+                            sV[r * CT + tx] = vo;
+                            int mk = 0;
+                            if (v16 & L16_SEED) mk = marker_of(v16, y, x, W, p.G, p.bitmap, p.prefix);
+                            s = mk > 0 ? ((static_cast<unsigned long long>(vo) << 32) | (1ull << 16) | static_cast<unsigned>(mk & 0xFFFF))
+                                       : ST_UNREACHED;
+                        }
+                    }
+                    sS[r + 1][tx + 1] = s;
+                }
+            } else {
+                for (int i = threadIdx.x; i < (CT + 2) * (CT + 2); i += 256) {
+                    const int r = i / (CT + 2), c = i % (CT + 2);
+                    const int y = y0 + r - 1, x = x0 + c - 1;
+                    const bool in = y >= 0 && y < H && x >= 0 && x < W;
+                    const unsigned long long s = in ? p.state[static_cast<size_t>(y) * W + x] : ST_OUTSIDE;
+                    sS[r][c] = s;
+                    if (LAB32) sLab[r][c] = in ? p.lab32[static_cast<size_t>(y) * W + x] : 0;
+                    if (in && r >= 1 && r <= CT && c >= 1 && c <= CT && !((s >> 16) & 1ull)) {      // floodable: needs its value
+                        const float v = p.img[static_cast<size_t>(y) * W + x];
+                        sV[(r - 1) * CT + c - 1] = ord_f32(p.negate ? -v : v);
+                    }
+                }
+            }
+            __syncthreads();
+            // initial work list.  First visit: every floodable pixel next to a flooded one; later visits: the floodable
+            // pixels on the tile edges next to a flooded halo pixel (the inside is already at its fixed point)
+            const bool first_visit = sweep == 0;
+#pragma unroll 4
+            for (int k = 0; k < 16; ++k) {
+                const int r = k * 4 + tq, c = tx;
+                const unsigned long long s = sS[r + 1][c + 1];
+                bool want = false;
+                if (!((s >> 16) & 1ull)) {
+                    if (first_visit) {
+                        want = static_cast<unsigned>(sS[r][c + 1] >> 32) < ORD_INF || static_cast<unsigned>(sS[r + 2][c + 1] >> 32) < ORD_INF ||
+                               static_cast<unsigned>(sS[r + 1][c] >> 32) < ORD_INF || static_cast<unsigned>(sS[r + 1][c + 2] >> 32) < ORD_INF;
+                    } else {
+                        want = (r == 0 && static_cast<unsigned>(sS[0][c + 1] >> 32) < ORD_INF) ||
+                               (r == CT - 1 && static_cast<unsigned>(sS[CT + 1][c + 1] >> 32) < ORD_INF) ||
+                               (c == 0 && static_cast<unsigned>(sS[r + 1][0] >> 32) < ORD_INF) ||
+                               (c == CT - 1 && static_cast<unsigned>(sS[r + 1][CT + 1] >> 32) < ORD_INF);
+                    }
+                }
+                const unsigned m = __ballot_sync(0xffffffffu, want);
+                if (m) {
+                    int base = 0;
+                    if (lane == __ffs(m) - 1) base = atomicAdd(&sMisc[0], __popc(m));
+                    base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
+                    if (want) {
+                        const int idx = r * CT + c;
+                        sQ[base + __popc(m & ((1u << lane) - 1u))] = static_cast<unsigned short>(idx);
+                        atomicOr(&sFlag[idx >> 5], 1u << (idx & 31));
+                    }
+                }
+            }
+            __syncthreads();
+            int qc = 0;
+            for (;;) {
+                const int n = *reinterpret_cast<volatile int *>(&sMisc[qc]);
+                if (n == 0) break;
+                const unsigned short *qin = sQ + qc * CT * CT;
+                unsigned short *qout = sQ + (qc ^ 1) * CT * CT;
+                for (int i = threadIdx.x; i < n; i += 256) {
+                    const int idx = qin[i];
+                    const int r = (idx >> 6) + 1, c = (idx & (CT - 1)) + 1;
+                    atomicAnd(&sFlag[idx >> 5], ~(1u << (idx & 31)));      // dequeued before the neighbours are read
+                    __threadfence_block();
+                    // skimage's neighbour order: up, left, right, down; the first minimal (level, hops) wins
+                    unsigned long long best = *reinterpret_cast<volatile unsigned long long *>(&sS[r - 1][c]);
+                    int bi = 0;
+                    unsigned long long q = *reinterpret_cast<volatile unsigned long long *>(&sS[r][c - 1]);
+                    if ((q >> 16) < (best >> 16)) { best = q; bi = 1; }
+                    q = *reinterpret_cast<volatile unsigned long long *>(&sS[r][c + 1]);
+                    if ((q >> 16) < (best >> 16)) { best = q; bi = 2; }
+                    q = *reinterpret_cast<volatile unsigned long long *>(&sS[r + 1][c]);
+                    if ((q >> 16) < (best >> 16)) { best = q; bi = 3; }
+                    const unsigned Lq = static_cast<unsigned>(best >> 32);
+                    if (Lq >= ORD_INF) continue;                     // no flooded neighbour yet
+                    const unsigned vo = sV[idx];
+                    unsigned long long ns;
+                    if (vo > Lq) {
+                        ns = (static_cast<unsigned long long>(vo) << 32) | (best & 0xFFFFull);
+                    } else {
+                        unsigned h = ((static_cast<unsigned>(best >> 16) & 0xFFFFu) >> 1) + 1u;
+                        if (h > HOP_MAX) { h = HOP_MAX; overflow = true; }
+                        ns = (static_cast<unsigned long long>(Lq) << 32) | (static_cast<unsigned long long>(h << 1) << 16) | (best & 0xFFFFull);
+                    }
+                    bool ch = ns != *reinterpret_cast<volatile unsigned long long *>(&sS[r][c]);
+                    if (LAB32) {
+                        const int nl = bi == 0 ? sLab[r - 1][c] : (bi == 1 ? sLab[r][c - 1] : (bi == 2 ? sLab[r][c + 1] : sLab[r + 1][c]));
+                        if (nl != sLab[r][c]) { *reinterpret_cast<volatile int *>(&sLab[r][c]) = nl; ch = true; }
+                    }
+                    if (!ch) continue;
+                    *reinterpret_cast<volatile unsigned long long *>(&sS[r][c]) = ns;
+                    __threadfence_block();
+                    unsigned eb = (r == 1 ? EDGE_TOP : 0u) | (r == CT ? EDGE_BOTTOM : 0u) | (c == 1 ? EDGE_LEFT : 0u) | (c == CT ? EDGE_RIGHT : 0u);
+                    if (eb) atomicOr(reinterpret_cast<unsigned *>(&sMisc[2]), eb);
+                    sMisc[3] = 1;
+                    // wake the floodable 4-neighbours inside the tile
+#pragma unroll
+                    for (int d = 0; d < 4; ++d) {
+                        const int rr = r + (d == 0 ? -1 : (d == 3 ? 1 : 0)), cc = c + (d == 1 ? -1 : (d == 2 ? 1 : 0));
+                        if (rr < 1 || rr > CT || cc < 1 || cc > CT) continue;
+                        const unsigned long long sn = *reinterpret_cast<volatile unsigned long long *>(&sS[rr][cc]);
+                        if ((sn >> 16) & 1ull) continue;             // marker or outside the mask
+                        const int nidx = (rr - 1) * CT + (cc - 1);
+                        const unsigned bit = 1u << (nidx & 31);
+                        if (atomicOr(&sFlag[nidx >> 5], bit) & bit) continue;       // already queued
+                        qout[atomicAdd(&sMisc[qc ^ 1], 1)] = static_cast<unsigned short>(nidx);
+                    }
+                }
+                __syncthreads();
+                if (threadIdx.x == 0) sMisc[qc] = 0;
+                qc ^= 1;
+                __syncthreads();
+            }
+            const bool changed_any = *reinterpret_cast<volatile int *>(&sMisc[3]) != 0;
+            unsigned edge_bits = *reinterpret_cast<volatile unsigned *>(&sMisc[2]);
+            unsigned my_edges = 0;
+            if (changed_any || fused_init || (LAB32 && sweep == 0)) {
+#pragma unroll 4
+                for (int k = 0; k < 16; ++k) {
+                    const int r = k * 4 + tq;
+                    const int y = y0 + r, x = x0 + tx;
+                    if (y < H && x < W) {
+                        const unsigned long long s = sS[r + 1][tx + 1];
+                        if (fused_init || !((s >> 16) & 1ull)) {
+                            p.state[static_cast<size_t>(y) * W + x] = s;
+                            if (LAB32) p.lab32[static_cast<size_t>(y) * W + x] = sLab[r + 1][tx + 1];
+                        }
+                        // first visit: the neighbours have not seen this tile yet -- every flooded edge pixel counts
+                        if (sweep == 0 && static_cast<unsigned>(s >> 32) < ORD_INF)
+                            my_edges |= (r == 0 ? EDGE_TOP : 0u) | (r == CT - 1 ? EDGE_BOTTOM : 0u) | (tx == 0 ? EDGE_LEFT : 0u) |
+                                        (tx == CT - 1 ? EDGE_RIGHT : 0u);
+                    }
+                }
+            }
+            if (sweep == 0) {
+                for (int o = 16; o > 0; o >>= 1) my_edges |= __shfl_xor_sync(0xffffffffu, my_edges, o);
+                if (lane == 0 && my_edges) atomicOr(reinterpret_cast<unsigned *>(&sMisc[2]), my_edges);
+                __syncthreads();
+                edge_bits = *reinterpret_cast<volatile unsigned *>(&sMisc[2]);
+            }
+            if (threadIdx.x == 0) cur[tile] = static_cast<uint8_t>(edge_bits);
+            block_changed |= edge_bits != 0;
+        }
+        if (block_changed && threadIdx.x == 0) p.st->changed[sweep % 3] = 1;
+        __threadfence();
+        grid.sync();
+        const unsigned int flag = *reinterpret_cast<volatile unsigned int *>(&p.st->changed[sweep % 3]);
+        if (blockIdx.x == 0 && threadIdx.x == 0) p.st->changed[(sweep + 2) % 3] = 0;
+        ++sweep;
+        stamp(sweep < 34 ? sweep : 34);
+        if (!flag) break;
+    }
+    if (overflow) atomicExch(&p.st->overflow, 1u);
+    if (blockIdx.x == 0 && threadIdx.x == 0) p.st->sweeps = static_cast<unsigned int>(sweep);
+    // ---- final phase: labels out + order-independence check (see the file header)
+    int bad_total = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int tyi = tile / tiles_x, txi = tile - tyi * tiles_x;
+        const int x0 = txi * CT, y0 = tyi * CT;
+        __syncthreads();
+        for (int i = threadIdx.x; i < (CT + 2) * (CT + 2); i += 256) {
+            const int r = i / (CT + 2), c = i % (CT + 2);
+            const int y = y0 + r - 1, x = x0 + c - 1;
+            const bool in = y >= 0 && y < H && x >= 0 && x < W;
+            sS[r][c] = in ? p.state[static_cast<size_t>(y) * W + x] : ST_OUTSIDE;
+            if (LAB32) sLab[r][c] = in ? p.lab32[static_cast<size_t>(y) * W + x] : 0;
+        }
+        __syncthreads();
+#pragma unroll 4
+        for (int k = 0; k < 16; ++k) {
+            const int y = y0 + k * 4 + tq, x = x0 + tx;
+            if (y >= H || x >= W) continue;
+            const int r = k * 4 + tq + 1, c = tx + 1;
+            const unsigned long long s = sS[r][c];
+            const bool flooded = static_cast<unsigned>(s >> 32) < ORD_INF;
+            const int me = LAB32 ? sLab[r][c] : static_cast<int>(s & 0xFFFFull);
+            const size_t o = static_cast<size_t>(y) * W + x;
+            if (LAB32) p.out32[o] = flooded ? me : 0;
+            else p.out16[o] = flooded ? static_cast<uint16_t>(me) : static_cast<uint16_t>(0);
+            if (flooded && !((s >> 16) & 1ull)) {
+                const unsigned long long n0 = sS[r - 1][c], n1 = sS[r][c - 1], n2 = sS[r][c + 1], n3 = sS[r + 1][c];
+                unsigned lmin = static_cast<unsigned>(n0 >> 32);
+                lmin = min(lmin, static_cast<unsigned>(n1 >> 32));
+                lmin = min(lmin, static_cast<unsigned>(n2 >> 32));
+                lmin = min(lmin, static_cast<unsigned>(n3 >> 32));
+                bool bad = false;
+                if (static_cast<unsigned>(n0 >> 32) == lmin && (LAB32 ? sLab[r - 1][c] : static_cast<int>(n0 & 0xFFFFull)) != me) bad = true;
+                if (static_cast<unsigned>(n1 >> 32) == lmin && (LAB32 ? sLab[r][c - 1] : static_cast<int>(n1 & 0xFFFFull)) != me) bad = true;
+                if (static_cast<unsigned>(n2 >> 32) == lmin && (LAB32 ? sLab[r][c + 1] : static_cast<int>(n2 & 0xFFFFull)) != me) bad = true;
+                if (static_cast<unsigned>(n3 >> 32) == lmin && (LAB32 ? sLab[r + 1][c] : static_cast<int>(n3 & 0xFFFFull)) != me) bad = true;
+                if (bad) ++bad_total;
+            }
+        }
+    }
+    if (bad_total) atomicAdd(&p.st->ambiguous, static_cast<unsigned int>(bad_total));
+    __syncthreads();
+    stamp(35);          // block 0's end of the final phase
+}
+
+// exact fallback, part 1 (runs only when the tiled result is order dependent): explicit marker / mask images for
+// ws_sequential_kernel from the packed words of the tiled pipeline
+__global__ void expand_markers_kernel(const uint16_t *__restrict__ L16, const int *__restrict__ G, const unsigned *__restrict__ bitmap,
+                                      const int *__restrict__ prefix, int H, int W, const Stats *st, int *__restrict__ markers,
+                                      uint8_t *__restrict__ mask) {
+    if (st->ambiguous == 0 && st->overflow == 0) return;
+    const long long n = static_cast<long long>(H) * W;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n; i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int y = static_cast<int>(i / W), x = static_cast<int>(i - static_cast<long long>(y) * W);
+        const unsigned v16 = L16[i];
+        const bool m = (v16 & L16_MASK) != 0;
+        mask[i] = m ? 1 : 0;
+        markers[i] = (m && (v16 & L16_SEED)) ? marker_of(v16, y, x, W, G, bitmap, prefix) : 0;
+    }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -784,7 +1490,7 @@ Stats *pinned_stats() {
 
 }  // namespace
 
-extern "C" size_t mbs_postproc_workspace_bytes(int H, int W) {
+static size_t legacy_postproc_workspace_bytes(int H, int W) {
     const size_t n = static_cast<size_t>(H) * W;
     const size_t tiles = (n + SCAN_TILE - 1) / SCAN_TILE;
     // cell_s, mask, seed, roots, area, rank, tile counts, markers, Lv, parent, uf, src, lab, heap, stats
@@ -886,9 +1592,9 @@ extern "C" int mbs_label8_instances(const uint16_t *image, int H, int W, int32_t
     return 0;
 }
 
-extern "C" int mbs_pp_watershed(const float *image, const int32_t *markers, const uint8_t *mask, int H, int W,
-                                int32_t *labels_out, void *workspace, size_t workspace_bytes, int64_t *info_host,
-                                int force_sequential, void *stream_) {
+static int legacy_pp_watershed(const float *image, const int32_t *markers, const uint8_t *mask, int H, int W,
+                               int32_t *labels_out, void *workspace, size_t workspace_bytes, int64_t *info_host,
+                               int force_sequential, void *stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     const size_t n = static_cast<size_t>(H) * W;
     MBS_REQUIRE(H > 0 && W > 0 && n < (1ull << 31), "watershed: bad shape");
@@ -920,16 +1626,16 @@ extern "C" int mbs_pp_watershed(const float *image, const int32_t *markers, cons
     return 0;
 }
 
-extern "C" int mbs_distance_postprocessing(const float *border, const float *cell, int H, int W, int ld, float th_seed,
-                                           float th_cell, uint16_t *out, void *workspace, size_t workspace_bytes,
-                                           int64_t *info_host, void *stream_) {
+static int legacy_distance_postprocessing(const float *border, const float *cell, int H, int W, int ld, float th_seed,
+                                          float th_cell, uint16_t *out, void *workspace, size_t workspace_bytes,
+                                          int64_t *info_host, void *stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     const size_t n = static_cast<size_t>(H) * W;
     MBS_REQUIRE(H > 0 && W > 0 && ld >= W && n < (1ull << 31), "distance_postprocessing: bad shape H=%d W=%d ld=%d", H,
                 W, ld);
-    MBS_REQUIRE(workspace_bytes >= mbs_postproc_workspace_bytes(H, W),
+    MBS_REQUIRE(workspace_bytes >= legacy_postproc_workspace_bytes(H, W),
                 "distance_postprocessing: workspace too small (%zu < %zu)", workspace_bytes,
-                mbs_postproc_workspace_bytes(H, W));
+                legacy_postproc_workspace_bytes(H, W));
     Carver cv{static_cast<char *>(workspace), workspace_bytes};
     Stats *st = cv.take<Stats>(1);
     float *cell_s = cv.take<float>(n);
@@ -977,12 +1683,12 @@ extern "C" int mbs_distance_postprocessing(const float *border, const float *cel
     return 0;
 }
 
-extern "C" int mbs_boundary_postprocessing(const float *prediction_hwc, int H, int W, uint16_t *out, void *workspace,
-                                           size_t workspace_bytes, int64_t *info_host, void *stream_) {
+static int legacy_boundary_postprocessing(const float *prediction_hwc, int H, int W, uint16_t *out, void *workspace,
+                                          size_t workspace_bytes, int64_t *info_host, void *stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     const size_t n = static_cast<size_t>(H) * W;
     MBS_REQUIRE(H > 0 && W > 0 && n < (1ull << 31), "boundary_postprocessing: bad shape H=%d W=%d", H, W);
-    MBS_REQUIRE(workspace_bytes >= mbs_postproc_workspace_bytes(H, W), "boundary_postprocessing: workspace too small");
+    MBS_REQUIRE(workspace_bytes >= legacy_postproc_workspace_bytes(H, W), "boundary_postprocessing: workspace too small");
     Carver cv{static_cast<char *>(workspace), workspace_bytes};
     Stats *st = cv.take<Stats>(1);
     float *img = cv.take<float>(n);
@@ -1024,6 +1730,264 @@ extern "C" int mbs_boundary_postprocessing(const float *prediction_hwc, int H, i
         info_host[2] = hp->sweeps;
         info_host[3] = hp->ambiguous ? 1 : 0;
         info_host[4] = hp->ambiguous;
+    }
+    return 0;
+}
+
+
+// ==========================================================================================
+// Tiled pipeline: host side
+// ==========================================================================================
+namespace {
+
+bool legacy_path() {        // MBS_PP_LEGACY=1: the round-1 streaming pipeline (A/B runs)
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("MBS_PP_LEGACY");
+        v = (e && e[0] == '1') ? 1 : 0;
+    }
+    return v == 1;
+}
+
+struct TiledWs {
+    Stats *st;
+    float *cell_s;
+    uint16_t *L16;
+    int *G, *area, *list;
+    int list_cap;
+    unsigned *bitmap;
+    int *prefix, *block_sums;
+    unsigned long long *state;
+    uint8_t *tile_changed;
+    int *lab32;              // generic watershed only
+    // exact sequential fallback
+    int *markers;
+    uint8_t *mask8;
+    int *lab;
+    HeapItem *heap;
+};
+constexpr int MID_MAX_BLOCKS = 4096;
+
+size_t tiled_ws_bytes(size_t n, int H, int W, bool generic) {
+    const size_t tiles = static_cast<size_t>((H + CT - 1) / CT) * ((W + CT - 1) / CT);
+    size_t b = r256(sizeof(Stats)) + r256(n * 4) + r256(n * 2) + 2 * r256(n * 4) + r256((n / 4 + 1024) * 4) +
+               2 * r256((n / 32 + 2) * 4) + r256(MID_MAX_BLOCKS * 4) + r256(n * 8) + r256(2 * tiles + 256) +
+               r256(n * 4) /*markers*/ + r256(n) /*mask*/ + r256(n * 4) /*lab*/ + r256(n * sizeof(HeapItem));
+    if (generic) b += r256(n * 4);
+    return b + 4096;
+}
+
+bool carve_tiled(TiledWs &t, void *workspace, size_t bytes, size_t n, int H, int W, bool generic) {
+    const size_t tiles = static_cast<size_t>((H + CT - 1) / CT) * ((W + CT - 1) / CT);
+    Carver cv{static_cast<char *>(workspace), bytes};
+    t.st = cv.take<Stats>(1);
+    t.cell_s = cv.take<float>(n);
+    t.L16 = cv.take<uint16_t>(n);
+    t.G = cv.take<int>(n);
+    t.area = cv.take<int>(n);
+    t.list_cap = static_cast<int>(n / 4 + 1024);
+    t.list = cv.take<int>(t.list_cap);
+    t.bitmap = cv.take<unsigned>(n / 32 + 2);
+    t.prefix = cv.take<int>(n / 32 + 2);
+    t.block_sums = cv.take<int>(MID_MAX_BLOCKS);
+    t.state = cv.take<unsigned long long>(n);
+    t.tile_changed = cv.take<uint8_t>(2 * tiles + 256);
+    t.markers = cv.take<int>(n);
+    t.mask8 = cv.take<uint8_t>(n);
+    t.lab = cv.take<int>(n);
+    t.heap = cv.take<HeapItem>(n);
+    t.lab32 = generic ? cv.take<int>(n) : nullptr;
+    return cv.ok;
+}
+
+struct CoopCfg {
+    int mid_blocks, flood16_blocks, flood32_blocks;
+    bool ready;
+};
+
+int coop_config(CoopCfg **out) {
+    static CoopCfg cfg[mbs::kMaxDevices] = {};
+    const int dev = mbs::current_device();
+    CoopCfg &c = cfg[dev];
+    if (!c.ready) {
+        int sms = 0, per = 0;
+        MBS_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        MBS_CHECK_CUDA(cudaFuncSetAttribute(flood_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FLOOD_SMEM16));
+        MBS_CHECK_CUDA(cudaFuncSetAttribute(flood_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FLOOD_SMEM32));
+        MBS_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, mid_kernel, 256, 0));
+        c.mid_blocks = sms * (per > 0 ? per : 1);
+        if (c.mid_blocks > MID_MAX_BLOCKS) c.mid_blocks = MID_MAX_BLOCKS;
+        MBS_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, flood_kernel<false>, 256, FLOOD_SMEM16));
+        c.flood16_blocks = sms * (per > 0 ? per : 1);
+        MBS_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, flood_kernel<true>, 256, FLOOD_SMEM32));
+        c.flood32_blocks = sms * (per > 0 ? per : 1);
+        c.ready = true;
+    }
+    *out = &c;
+    return 0;
+}
+
+int read_info(const TiledWs &t, int64_t *info_host, cudaStream_t stream) {
+    Stats *hp = pinned_stats();
+    MBS_REQUIRE(hp != nullptr, "post-processing: cannot allocate pinned host memory");
+    MBS_CHECK_CUDA(cudaMemcpyAsync(hp, t.st, sizeof(Stats), cudaMemcpyDeviceToHost, stream));
+    MBS_CHECK_CUDA(cudaStreamSynchronize(stream));
+    memset(info_host, 0, 8 * sizeof(int64_t));
+    info_host[0] = hp->n_comp;
+    info_host[1] = hp->n_markers;
+    info_host[2] = hp->sweeps;
+    info_host[3] = (hp->ambiguous || hp->overflow) ? 1 : 0;
+    info_host[4] = hp->ambiguous;
+    info_host[5] = hp->overflow;
+    return 0;
+}
+
+// front end + labelling + flood for both methods; `a` / `b`: border + cell maps (distance) or the (H,W,3) probabilities
+template <bool BOUNDARY>
+int run_tiled(const float *a, const float *b, int H, int W, int ld, float th_seed, float th_cell, uint16_t *out,
+              void *workspace, size_t workspace_bytes, int64_t *info_host, cudaStream_t stream) {
+    const size_t n = static_cast<size_t>(H) * W;
+    TiledWs t;
+    MBS_REQUIRE(carve_tiled(t, workspace, workspace_bytes, n, H, W, false), "post-processing: workspace carve failed");
+    CoopCfg *cfg = nullptr;
+    int rc = coop_config(&cfg);
+    if (rc) return rc;
+    MBS_CHECK_CUDA(cudaMemsetAsync(t.st, 0, sizeof(Stats), stream));
+    dim3 tgrid(mbs::cdiv(W, CT), mbs::cdiv(H, CT));
+    front_ccl_kernel<BOUNDARY><<<tgrid, 256, 0, stream>>>(a, b, H, W, ld, th_seed, th_cell, t.cell_s, t.L16, t.G, t.area, t.list,
+                                                          t.list_cap, t.bitmap, t.st);
+    MBS_CHECK_LAUNCH();
+    {
+        const int use_mean = BOUNDARY ? 0 : 1;       // boundary method: drop area <= 4 only (postprocessing.py:79-84)
+        const uint16_t *L16 = t.L16;
+        const int *list = t.list;
+        void *args[] = {(void *)&L16, (void *)&H, (void *)&W, (void *)&t.G, (void *)&t.area, (void *)&list, (void *)&t.list_cap,
+                        (void *)&t.bitmap, (void *)&t.prefix, (void *)&t.block_sums, (void *)&t.st, (void *)&use_mean};
+        MBS_CHECK_CUDA(cudaLaunchCooperativeKernel((void *)mid_kernel, dim3(cfg->mid_blocks), dim3(256), args, 0, stream));
+        mbs::count_launch();
+    }
+    {
+        FloodParams fp;
+        fp.img = t.cell_s;
+        fp.negate = BOUNDARY ? 0 : 1;
+        fp.L16 = t.L16;
+        fp.G = t.G;
+        fp.bitmap = t.bitmap;
+        fp.prefix = t.prefix;
+        fp.state = t.state;
+        fp.lab32 = nullptr;
+        fp.H = H;
+        fp.W = W;
+        fp.st = t.st;
+        fp.tile_changed = t.tile_changed;
+        fp.out16 = out;
+        fp.out32 = nullptr;
+        const int ntiles = static_cast<int>(tgrid.x * tgrid.y);
+        const int blocks = ntiles < cfg->flood16_blocks ? ntiles : cfg->flood16_blocks;
+        void *args[] = {(void *)&fp};
+        MBS_CHECK_CUDA(cudaLaunchCooperativeKernel((void *)flood_kernel<false>, dim3(blocks), dim3(256), args, FLOOD_SMEM16, stream));
+        mbs::count_launch();
+    }
+    // exact fallback (both kernels return immediately unless the flood flagged an order-dependent pixel)
+    {
+        const int want = mbs::cdiv(static_cast<int>(n), 256);
+        expand_markers_kernel<<<want < 1184 ? want : 1184, 256, 0, stream>>>(t.L16, t.G, t.bitmap, t.prefix, H, W, t.st, t.markers, t.mask8);
+    }
+    MBS_CHECK_LAUNCH();
+    ws_sequential_kernel<<<1, 32, 0, stream>>>(t.cell_s, BOUNDARY ? 0 : 1, t.markers, t.mask8, H, W, t.lab, t.heap, t.st, 0, out);
+    MBS_CHECK_LAUNCH();
+    if (info_host) return read_info(t, info_host, stream);
+    return 0;
+}
+
+}  // namespace
+
+extern "C" size_t mbs_postproc_workspace_bytes(int H, int W) {
+    const size_t n = static_cast<size_t>(H) * W;
+    const size_t a = tiled_ws_bytes(n, H, W, true), b = legacy_postproc_workspace_bytes(H, W);
+    return a > b ? a : b;
+}
+
+extern "C" int mbs_distance_postprocessing(const float *border, const float *cell, int H, int W, int ld, float th_seed,
+                                           float th_cell, uint16_t *out, void *workspace, size_t workspace_bytes,
+                                           int64_t *info_host, void *stream_) {
+    if (legacy_path())
+        return legacy_distance_postprocessing(border, cell, H, W, ld, th_seed, th_cell, out, workspace, workspace_bytes, info_host, stream_);
+    const size_t n = static_cast<size_t>(H) * W;
+    MBS_REQUIRE(H > 0 && W > 0 && ld >= W && n < (1ull << 31), "distance_postprocessing: bad shape H=%d W=%d ld=%d", H, W, ld);
+    MBS_REQUIRE(workspace_bytes >= mbs_postproc_workspace_bytes(H, W), "distance_postprocessing: workspace too small (%zu < %zu)",
+                workspace_bytes, mbs_postproc_workspace_bytes(H, W));
+    return run_tiled<false>(border, cell, H, W, ld, th_seed, th_cell, out, workspace, workspace_bytes, info_host,
+                            static_cast<cudaStream_t>(stream_));
+}
+
+extern "C" int mbs_boundary_postprocessing(const float *prediction_hwc, int H, int W, uint16_t *out, void *workspace,
+                                           size_t workspace_bytes, int64_t *info_host, void *stream_) {
+    if (legacy_path()) return legacy_boundary_postprocessing(prediction_hwc, H, W, out, workspace, workspace_bytes, info_host, stream_);
+    const size_t n = static_cast<size_t>(H) * W;
+    MBS_REQUIRE(H > 0 && W > 0 && n < (1ull << 31), "boundary_postprocessing: bad shape H=%d W=%d", H, W);
+    MBS_REQUIRE(workspace_bytes >= mbs_postproc_workspace_bytes(H, W), "boundary_postprocessing: workspace too small");
+    return run_tiled<true>(prediction_hwc, nullptr, H, W, W, 0.0f, 0.0f, out, workspace, workspace_bytes, info_host,
+                           static_cast<cudaStream_t>(stream_));
+}
+
+extern "C" int mbs_pp_watershed(const float *image, const int32_t *markers, const uint8_t *mask, int H, int W,
+                                int32_t *labels_out, void *workspace, size_t workspace_bytes, int64_t *info_host,
+                                int force_sequential, void *stream_) {
+    if (legacy_path())
+        return legacy_pp_watershed(image, markers, mask, H, W, labels_out, workspace, workspace_bytes, info_host, force_sequential, stream_);
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    const size_t n = static_cast<size_t>(H) * W;
+    MBS_REQUIRE(H > 0 && W > 0 && n < (1ull << 31), "watershed: bad shape");
+    // own carve (a subset of the fused pipeline's workspace): stats, state, labels, tile flags, heap of the exact flood
+    const size_t tiles = static_cast<size_t>((H + CT - 1) / CT) * ((W + CT - 1) / CT);
+    const size_t need = r256(sizeof(Stats)) + r256(n * 8) + r256(n * 4) + r256(2 * tiles + 256) + r256(n * sizeof(HeapItem));
+    MBS_REQUIRE(workspace_bytes >= need, "watershed: workspace too small (%zu < %zu)", workspace_bytes, need);
+    TiledWs t;
+    {
+        Carver cv{static_cast<char *>(workspace), workspace_bytes};
+        t.st = cv.take<Stats>(1);
+        t.state = cv.take<unsigned long long>(n);
+        t.lab32 = cv.take<int>(n);
+        t.tile_changed = cv.take<uint8_t>(2 * tiles + 256);
+        t.heap = cv.take<HeapItem>(n);
+        MBS_REQUIRE(cv.ok, "watershed: workspace carve failed");
+    }
+    CoopCfg *cfg = nullptr;
+    int rc = coop_config(&cfg);
+    if (rc) return rc;
+    MBS_CHECK_CUDA(cudaMemsetAsync(t.st, 0, sizeof(Stats), stream));
+    const int nn = static_cast<int>(n);
+    if (!force_sequential) {
+        flood_init_kernel<<<mbs::cdiv(nn, 256), 256, 0, stream>>>(image, markers, mask, nn, t.state, t.lab32);
+        MBS_CHECK_LAUNCH();
+        FloodParams fp;
+        fp.img = image;
+        fp.negate = 0;
+        fp.L16 = nullptr;
+        fp.G = nullptr;
+        fp.bitmap = nullptr;
+        fp.prefix = nullptr;
+        fp.state = t.state;
+        fp.lab32 = t.lab32;
+        fp.H = H;
+        fp.W = W;
+        fp.st = t.st;
+        fp.tile_changed = t.tile_changed;
+        fp.out16 = nullptr;
+        fp.out32 = labels_out;
+        const int ntiles = mbs::cdiv(W, CT) * mbs::cdiv(H, CT);
+        const int blocks = ntiles < cfg->flood32_blocks ? ntiles : cfg->flood32_blocks;
+        void *args[] = {(void *)&fp};
+        MBS_CHECK_CUDA(cudaLaunchCooperativeKernel((void *)flood_kernel<true>, dim3(blocks), dim3(256), args, FLOOD_SMEM32, stream));
+        mbs::count_launch();
+    }
+    ws_sequential_kernel<<<1, 32, 0, stream>>>(image, 0, markers, mask, H, W, labels_out, t.heap, t.st, force_sequential, nullptr);
+    MBS_CHECK_LAUNCH();
+    if (info_host) {
+        rc = read_info(t, info_host, stream);
+        if (rc) return rc;
+        if (force_sequential) info_host[3] = 1;
     }
     return 0;
 }

@@ -14,18 +14,29 @@ import torch
 
 from . import _native as nat
 
-_WS = {}       # (device index, bytes) -> workspace tensor
-_INFO = (ctypes.c_int64 * 8)()
+_WS = {}       # (device index, stream handle) -> workspace tensor
 last_info = {}
 
 
 def _workspace(device, nbytes):
-    key = device.index if device.index is not None else torch.cuda.current_device()
+    """Scratch for one call, cached per (device, stream): kernels of two streams never share a buffer, and a buffer
+    is only ever reused by later work on the stream it was allocated on (stream order = reuse order), so neither the
+    caching allocator nor a concurrent caller can hand it to someone else while kernels still use it."""
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    key = (idx, torch.cuda.current_stream(device).cuda_stream)
     ws = _WS.get(key)
     if ws is None or ws.numel() < nbytes:
-        ws = torch.empty(int(nbytes), dtype=torch.uint8, device=device)
+        if len(_WS) > 16:                     # streams come and go (FrameSegmenter instances): keep the cache small
+            _WS.clear()
+        with torch.cuda.device(device):
+            ws = torch.empty(int(nbytes), dtype=torch.uint8, device=device)
         _WS[key] = ws
     return ws
+
+
+def _info_dict(info):
+    return dict(n_seed_components=int(info[0]), n_markers=int(info[1]), sweeps=int(info[2]), sequential=int(info[3]),
+                ambiguous=int(info[4]), overflow=int(info[5]))
 
 
 def _as_device_map(a, device):
@@ -68,17 +79,17 @@ def distance_postprocessing_device(border, cell, th_seed, th_cell, out=None, wan
     if out is None:
         out = torch.empty((H, W), dtype=torch.int16, device=device)  # uint16 payload
     nbytes = L.mbs_postproc_workspace_bytes(H, W)
-    ws = _workspace(device, nbytes)
+    info = (ctypes.c_int64 * 8)() if want_info else None
     with torch.cuda.device(device):
+        ws = _workspace(device, nbytes)
         rc = L.mbs_distance_postprocessing(border.data_ptr(), cell.data_ptr(), H, W, ld, float(th_seed),
                                            float(th_cell), out.data_ptr(), ws.data_ptr(), ws.numel(),
-                                           ctypes.cast(_INFO, ctypes.c_void_p) if want_info else None,
+                                           ctypes.cast(info, ctypes.c_void_p) if want_info else None,
                                            nat.stream_ptr())
     nat.check(rc, "distance_postprocessing")
     if want_info:
         last_info.clear()
-        last_info.update(n_seed_components=int(_INFO[0]), n_markers=int(_INFO[1]), sweeps=int(_INFO[2]),
-                         sequential=int(_INFO[3]), ambiguous=int(_INFO[4]))
+        last_info.update(_info_dict(info))
     return out
 
 
@@ -94,7 +105,7 @@ def distance_postprocessing(border_prediction, cell_prediction, th_seed, th_cell
     return np.squeeze(out.cpu().numpy().view(np.uint16))
 
 
-def boundary_postprocessing_device(pred, out=None):
+def boundary_postprocessing_device(pred, out=None, want_info=False):
     """(H,W,3) float32 CUDA probabilities -> uint16-as-int16 CUDA mask (H,W)."""
     if pred.dim() != 3 or pred.shape[-1] != 3:
         raise ValueError(f"expected (H,W,3) class probabilities, got {tuple(pred.shape)}")
@@ -104,11 +115,15 @@ def boundary_postprocessing_device(pred, out=None):
     device = pred.device
     if out is None:
         out = torch.empty((H, W), dtype=torch.int16, device=device)
-    ws = _workspace(device, L.mbs_postproc_workspace_bytes(H, W))
+    info = (ctypes.c_int64 * 8)() if want_info else None
     with torch.cuda.device(device):
-        rc = L.mbs_boundary_postprocessing(pred.data_ptr(), H, W, out.data_ptr(), ws.data_ptr(), ws.numel(), None,
-                                           nat.stream_ptr())
+        ws = _workspace(device, L.mbs_postproc_workspace_bytes(H, W))
+        rc = L.mbs_boundary_postprocessing(pred.data_ptr(), H, W, out.data_ptr(), ws.data_ptr(), ws.numel(),
+                                           ctypes.cast(info, ctypes.c_void_p) if want_info else None, nat.stream_ptr())
     nat.check(rc, "boundary_postprocessing")
+    if want_info:
+        last_info.clear()
+        last_info.update(_info_dict(info))
     return out
 
 
