@@ -731,10 +731,50 @@ front_ccl_kernel(const float *__restrict__ border, const float *__restrict__ cel
     const int c = tid & (CT - 1), rq = tid >> 6;            // pixel k of this thread: row k*4 + rq, column c
 
     if (!BOUNDARY) {
-        for (int i = tid; i < (CT + 4) * (CT + 4); i += 256) {
-            const int r = i / (CT + 4), cc = i % (CT + 4);
-            const int yy = reflect_idx(y0 + r - 2, H), xx = reflect_idx(x0 + cc - 2, W);
-            s_in[r][cc] = cell[static_cast<size_t>(yy) * ld + xx];
+        // tile + 2-pixel apron of the cell map.  Full tiles with 16-byte aligned rows: four independent float4 loads
+        // per thread for the interior and ~2 scalar loads for the apron ring, all in flight together (the plain loop
+        // serialises 18 load latencies per tile)
+        const bool vec = x0 + CT <= W && y0 + CT <= H && (ld & 3) == 0 && (reinterpret_cast<uintptr_t>(cell) & 15) == 0;
+        if (vec) {
+            const int row = tid >> 2, col0 = (tid & 3) * 16;
+            const float4 *src = reinterpret_cast<const float4 *>(cell + static_cast<size_t>(y0 + row) * ld + x0 + col0);
+            const float4 f0 = src[0], f1 = src[1], f2 = src[2], f3 = src[3];
+            float ring[3];
+            int rr[3], rc[3];
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+                const int h = tid + j * 256;
+                rr[j] = -1;
+                if (h < 4 * (CT + 4) + 4 * CT) {
+                    int r, cc;
+                    if (h < 4 * (CT + 4)) {                       // rows 0, 1, CT+2, CT+3 over the full width
+                        const int q = h / (CT + 4);
+                        r = q < 2 ? q : CT + q;
+                        cc = h % (CT + 4);
+                    } else {                                       // columns 0, 1, CT+2, CT+3 of the interior rows
+                        const int g = h - 4 * (CT + 4);
+                        r = 2 + (g >> 2);
+                        const int q = g & 3;
+                        cc = q < 2 ? q : CT + q;
+                    }
+                    rr[j] = r;
+                    rc[j] = cc;
+                    const int yy = reflect_idx(y0 + r - 2, H), xx = reflect_idx(x0 + cc - 2, W);
+                    ring[j] = cell[static_cast<size_t>(yy) * ld + xx];
+                }
+            }
+            float *d = &s_in[row + 2][col0 + 2];
+            d[0] = f0.x; d[1] = f0.y; d[2] = f0.z; d[3] = f0.w; d[4] = f1.x; d[5] = f1.y; d[6] = f1.z; d[7] = f1.w;
+            d[8] = f2.x; d[9] = f2.y; d[10] = f2.z; d[11] = f2.w; d[12] = f3.x; d[13] = f3.y; d[14] = f3.z; d[15] = f3.w;
+#pragma unroll
+            for (int j = 0; j < 3; ++j)
+                if (rr[j] >= 0) s_in[rr[j]][rc[j]] = ring[j];
+        } else {
+            for (int i = tid; i < (CT + 4) * (CT + 4); i += 256) {
+                const int r = i / (CT + 4), cc = i % (CT + 4);
+                const int yy = reflect_idx(y0 + r - 2, H), xx = reflect_idx(x0 + cc - 2, W);
+                s_in[r][cc] = cell[static_cast<size_t>(yy) * ld + xx];
+            }
         }
         __syncthreads();
         for (int i = tid; i < CT * (CT + 4); i += 256) {
@@ -1039,16 +1079,24 @@ mid_kernel(const uint16_t *__restrict__ L16, int H, int W, int *G, int *area, co
         }
         if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) st->n_markers = static_cast<unsigned>(running);
     }
+    __threadfence();
+    grid.sync();
+    // ---- phase 4: marker id (1-based raster rank of the surviving component, 0 = dropped) of every tile-local root,
+    // stored over its (no longer needed) area: the flood resolves a seed pixel with ONE gather instead of three
+    for (int i = gtid; i < n_roots; i += gsz) {
+        const int lr = roots_list[i];
+        const int r = *reinterpret_cast<volatile int *>(&G[lr]);
+        const unsigned w = *reinterpret_cast<volatile unsigned *>(&bitmap[r >> 5]);
+        int id = 0;
+        if ((w >> (r & 31)) & 1u) id = *reinterpret_cast<volatile int *>(&prefix[r >> 5]) + __popc(w & ((1u << (r & 31)) - 1u)) + 1;
+        area[lr] = id;
+    }
 }
 
-// marker id (1-based raster rank of the surviving seed component) of a seed pixel, 0 if its component was dropped
-__device__ __forceinline__ int marker_of(unsigned v16, int y, int x, int W, const int *__restrict__ G,
-                                         const unsigned *__restrict__ bitmap, const int *__restrict__ prefix) {
-    const int lr = l16_root_index(v16, y, x, W);
-    const int r = G[lr];
-    const unsigned w = bitmap[r >> 5];
-    if (!((w >> (r & 31)) & 1u)) return 0;
-    return prefix[r >> 5] + __popc(w & ((1u << (r & 31)) - 1u)) + 1;
+// marker id (1-based raster rank of the surviving seed component) of a seed pixel, 0 if its component was dropped:
+// mid_kernel phase 4 left it at the pixel's tile-local root
+__device__ __forceinline__ int marker_of(unsigned v16, int y, int x, int W, const int *__restrict__ marker_at_root) {
+    return marker_at_root[l16_root_index(v16, y, x, W)];
 }
 
 // generic entry (mbs_pp_watershed): state / labels from an explicit marker image
@@ -1068,9 +1116,7 @@ struct FloodParams {
     const float *img;                // flood image (negate != 0: -img)
     int negate;
     const uint16_t *L16;             // fused mode: seeds / mask / local roots from front_ccl_kernel
-    const int *G;
-    const unsigned *bitmap;
-    const int *prefix;
+    const int *marker_at_root;       // fused mode: marker id of every tile-local root (mid_kernel phase 4)
     unsigned long long *state;
     int *lab32;                      // LAB32 only
     int H, W;
@@ -1093,6 +1139,8 @@ constexpr unsigned EDGE_TOP = 1u, EDGE_BOTTOM = 2u, EDGE_LEFT = 4u, EDGE_RIGHT =
 
 // The in-tile relaxation is EVENT DRIVEN: a pixel is (re)evaluated only when one of its 4-neighbours changed.  Work is
 // proportional to the number of floodable pixels (a few evaluations each) instead of tile area x wavefront depth.
+// Tile loads / stores are bulk 16-byte accesses issued back to back (a tile visit used to cost ~20 us of serialised
+// load latency); thread t owns the 16 consecutive pixels (row t/4, columns (t%4)*16 ..) in those phases.
 template <bool LAB32>
 __global__ void __launch_bounds__(256)
 flood_kernel(const FloodParams p) {
@@ -1109,8 +1157,11 @@ flood_kernel(const FloodParams p) {
     const int H = p.H, W = p.W;
     const int tiles_x = (W + CT - 1) / CT, tiles_y = (H + CT - 1) / CT;
     const int ntiles = tiles_x * tiles_y;
-    const int tx = threadIdx.x & (CT - 1), tq = threadIdx.x >> 6;      // column, and rows k*4 + tq (k = 0..15)
+    const int row = threadIdx.x >> 2, col0 = (threadIdx.x & 3) * 16;      // this thread's 16 pixels
     const int lane = threadIdx.x & 31;
+    // 16-byte accesses need aligned bases (caller-provided outputs may be offset views)
+    const bool aligned = !LAB32 && ((reinterpret_cast<uintptr_t>(p.img) | reinterpret_cast<uintptr_t>(p.L16) |
+                                     reinterpret_cast<uintptr_t>(p.state) | reinterpret_cast<uintptr_t>(p.out16)) & 15) == 0;
     int sweep = 0;
     bool overflow = false;
     auto stamp = [&](int slot) {
@@ -1118,6 +1169,20 @@ flood_kernel(const FloodParams p) {
             unsigned long long t;
             asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
             p.st->dbg_t[slot] = t;
+        }
+    };
+    // halo ring of the tile at (y0, x0): 260 elements, element h of thread t = t and (t < 4) 256 + t
+    auto load_halo = [&](int x0, int y0) {
+        for (int h = threadIdx.x; h < 4 * CT + 4; h += 256) {
+            int r, c;
+            if (h < CT + 2) { r = 0; c = h; }
+            else if (h < 2 * (CT + 2)) { r = CT + 1; c = h - (CT + 2); }
+            else if (h < 2 * (CT + 2) + CT) { r = h - 2 * (CT + 2) + 1; c = 0; }
+            else { r = h - 2 * (CT + 2) - CT + 1; c = CT + 1; }
+            const int y = y0 + r - 1, x = x0 + c - 1;
+            const bool in = y >= 0 && y < H && x >= 0 && x < W;
+            sS[r][c] = in ? p.state[static_cast<size_t>(y) * W + x] : ST_OUTSIDE;
+            if (LAB32) sLab[r][c] = in ? p.lab32[static_cast<size_t>(y) * W + x] : 0;
         }
     };
     stamp(0);
@@ -1137,6 +1202,8 @@ flood_kernel(const FloodParams p) {
                 }
             }
             const int x0 = txi * CT, y0 = tyi * CT;
+            const bool fast = aligned && x0 + CT <= W && y0 + CT <= H && (W & 7) == 0;      // 16-byte rows, no ragged edge
+            const size_t rowbase = static_cast<size_t>(y0 + row) * W + x0 + col0;
             __syncthreads();   // shared tile reuse
             const bool fused_init = !LAB32 && sweep == 0;
             if (threadIdx.x == 0 && sweep < 32) atomicAdd(&p.st->dbg_tiles[sweep], 1u);
@@ -1150,37 +1217,84 @@ flood_kernel(const FloodParams p) {
                     const int c = side <= 1 ? j : (side == 2 ? 0 : CT + 1);
                     sS[r][c] = ST_OUTSIDE;
                 }
-#pragma unroll 4
-                for (int k = 0; k < 16; ++k) {
-                    const int r = k * 4 + tq;
-                    const int y = y0 + r, x = x0 + tx;
-                    unsigned long long s = ST_OUTSIDE;
-                    if (y < H && x < W) {
-                        const size_t i = static_cast<size_t>(y) * W + x;
-                        const unsigned v16 = p.L16[i];
-                        if (v16 & L16_MASK) {
-                            const float v = p.img[i];
-                            const unsigned vo = ord_f32(p.negate ? -v : v);
-                            sV[r * CT + tx] = vo;
-                            int mk = 0;
-                            if (v16 & L16_SEED) mk = marker_of(v16, y, x, W, p.G, p.bitmap, p.prefix);
-                            s = mk > 0 ? ((static_cast<unsigned long long>(vo) << 32) | (1ull << 16) | static_cast<unsigned>(mk & 0xFFFF))
-                                       : ST_UNREACHED;
-                        }
+                unsigned short v16[16];
+                float v[16];
+                if (fast) {
+                    const uint4 *lp = reinterpret_cast<const uint4 *>(p.L16 + rowbase);
+                    const float4 *vp = reinterpret_cast<const float4 *>(p.img + rowbase);
+                    const uint4 l0 = lp[0], l1 = lp[1];
+                    const float4 f0 = vp[0], f1 = vp[1], f2 = vp[2], f3 = vp[3];
+                    const unsigned lw[8] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w};
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        v16[2 * i] = static_cast<unsigned short>(lw[i] & 0xFFFFu);
+                        v16[2 * i + 1] = static_cast<unsigned short>(lw[i] >> 16);
                     }
-                    sS[r + 1][tx + 1] = s;
+                    const float fv[16] = {f0.x, f0.y, f0.z, f0.w, f1.x, f1.y, f1.z, f1.w, f2.x, f2.y, f2.z, f2.w, f3.x, f3.y, f3.z, f3.w};
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) v[i] = fv[i];
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        const int y = y0 + row, x = x0 + col0 + i;
+                        const bool in = y < H && x < W;
+                        v16[i] = in ? p.L16[static_cast<size_t>(y) * W + x] : static_cast<unsigned short>(0);
+                        v[i] = in ? p.img[static_cast<size_t>(y) * W + x] : 0.0f;
+                    }
+                }
+                int mk[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {          // independent gathers, all in flight together
+                    mk[i] = 0;
+                    if ((v16[i] & (L16_MASK | L16_SEED)) == (L16_MASK | L16_SEED))
+                        mk[i] = marker_of(v16[i], y0 + row, x0 + col0 + i, W, p.marker_at_root);
+                }
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    unsigned long long s = ST_OUTSIDE;
+                    if (v16[i] & L16_MASK) {
+                        const unsigned vo = ord_f32(p.negate ? -v[i] : v[i]);
+                        sV[row * CT + col0 + i] = vo;
+                        s = mk[i] > 0 ? ((static_cast<unsigned long long>(vo) << 32) | (1ull << 16) | static_cast<unsigned>(mk[i] & 0xFFFF))
+                                      : ST_UNREACHED;
+                    }
+                    sS[row + 1][col0 + i + 1] = s;
+                }
+            } else if (fast) {
+                const ulonglong2 *sp = reinterpret_cast<const ulonglong2 *>(p.state + rowbase);
+                const float4 *vp = reinterpret_cast<const float4 *>(p.img + rowbase);
+                ulonglong2 sv[8];
+                float4 fv[4];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) sv[j] = sp[j];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) fv[j] = vp[j];
+                load_halo(x0, y0);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    sS[row + 1][col0 + 2 * j + 1] = sv[j].x;
+                    sS[row + 1][col0 + 2 * j + 2] = sv[j].y;
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    unsigned *d = sV + row * CT + col0 + 4 * j;
+                    d[0] = ord_f32(p.negate ? -fv[j].x : fv[j].x);
+                    d[1] = ord_f32(p.negate ? -fv[j].y : fv[j].y);
+                    d[2] = ord_f32(p.negate ? -fv[j].z : fv[j].z);
+                    d[3] = ord_f32(p.negate ? -fv[j].w : fv[j].w);
                 }
             } else {
-                for (int i = threadIdx.x; i < (CT + 2) * (CT + 2); i += 256) {
-                    const int r = i / (CT + 2), c = i % (CT + 2);
-                    const int y = y0 + r - 1, x = x0 + c - 1;
-                    const bool in = y >= 0 && y < H && x >= 0 && x < W;
+                load_halo(x0, y0);
+#pragma unroll 4
+                for (int i = 0; i < 16; ++i) {
+                    const int y = y0 + row, x = x0 + col0 + i;
+                    const bool in = y < H && x < W;
                     const unsigned long long s = in ? p.state[static_cast<size_t>(y) * W + x] : ST_OUTSIDE;
-                    sS[r][c] = s;
-                    if (LAB32) sLab[r][c] = in ? p.lab32[static_cast<size_t>(y) * W + x] : 0;
-                    if (in && r >= 1 && r <= CT && c >= 1 && c <= CT && !((s >> 16) & 1ull)) {      // floodable: needs its value
+                    sS[row + 1][col0 + i + 1] = s;
+                    if (LAB32) sLab[row + 1][col0 + i + 1] = in ? p.lab32[static_cast<size_t>(y) * W + x] : 0;
+                    if (in && !((s >> 16) & 1ull)) {               // floodable: needs its value
                         const float v = p.img[static_cast<size_t>(y) * W + x];
-                        sV[(r - 1) * CT + c - 1] = ord_f32(p.negate ? -v : v);
+                        sV[row * CT + col0 + i] = ord_f32(p.negate ? -v : v);
                     }
                 }
             }
@@ -1189,8 +1303,8 @@ flood_kernel(const FloodParams p) {
             // pixels on the tile edges next to a flooded halo pixel (the inside is already at its fixed point)
             const bool first_visit = sweep == 0;
 #pragma unroll 4
-            for (int k = 0; k < 16; ++k) {
-                const int r = k * 4 + tq, c = tx;
+            for (int i = 0; i < 16; ++i) {
+                const int r = row, c = col0 + i;
                 const unsigned long long s = sS[r + 1][c + 1];
                 bool want = false;
                 if (!((s >> 16) & 1ull)) {
@@ -1229,17 +1343,19 @@ flood_kernel(const FloodParams p) {
                     atomicAnd(&sFlag[idx >> 5], ~(1u << (idx & 31)));      // dequeued before the neighbours are read
                     __threadfence_block();
                     // skimage's neighbour order: up, left, right, down; the first minimal (level, hops) wins
-                    unsigned long long best = *reinterpret_cast<volatile unsigned long long *>(&sS[r - 1][c]);
+                    const unsigned long long n0 = *reinterpret_cast<volatile unsigned long long *>(&sS[r - 1][c]);
+                    const unsigned long long n1 = *reinterpret_cast<volatile unsigned long long *>(&sS[r][c - 1]);
+                    const unsigned long long n2 = *reinterpret_cast<volatile unsigned long long *>(&sS[r][c + 1]);
+                    const unsigned long long n3 = *reinterpret_cast<volatile unsigned long long *>(&sS[r + 1][c]);
+                    const unsigned long long old = *reinterpret_cast<volatile unsigned long long *>(&sS[r][c]);
+                    const unsigned vo = sV[idx];
+                    unsigned long long best = n0;
                     int bi = 0;
-                    unsigned long long q = *reinterpret_cast<volatile unsigned long long *>(&sS[r][c - 1]);
-                    if ((q >> 16) < (best >> 16)) { best = q; bi = 1; }
-                    q = *reinterpret_cast<volatile unsigned long long *>(&sS[r][c + 1]);
-                    if ((q >> 16) < (best >> 16)) { best = q; bi = 2; }
-                    q = *reinterpret_cast<volatile unsigned long long *>(&sS[r + 1][c]);
-                    if ((q >> 16) < (best >> 16)) { best = q; bi = 3; }
+                    if ((n1 >> 16) < (best >> 16)) { best = n1; bi = 1; }
+                    if ((n2 >> 16) < (best >> 16)) { best = n2; bi = 2; }
+                    if ((n3 >> 16) < (best >> 16)) { best = n3; bi = 3; }
                     const unsigned Lq = static_cast<unsigned>(best >> 32);
                     if (Lq >= ORD_INF) continue;                     // no flooded neighbour yet
-                    const unsigned vo = sV[idx];
                     unsigned long long ns;
                     if (vo > Lq) {
                         ns = (static_cast<unsigned long long>(vo) << 32) | (best & 0xFFFFull);
@@ -1248,7 +1364,7 @@ flood_kernel(const FloodParams p) {
                         if (h > HOP_MAX) { h = HOP_MAX; overflow = true; }
                         ns = (static_cast<unsigned long long>(Lq) << 32) | (static_cast<unsigned long long>(h << 1) << 16) | (best & 0xFFFFull);
                     }
-                    bool ch = ns != *reinterpret_cast<volatile unsigned long long *>(&sS[r][c]);
+                    bool ch = ns != old;
                     if (LAB32) {
                         const int nl = bi == 0 ? sLab[r - 1][c] : (bi == 1 ? sLab[r][c - 1] : (bi == 2 ? sLab[r][c + 1] : sLab[r + 1][c]));
                         if (nl != sLab[r][c]) { *reinterpret_cast<volatile int *>(&sLab[r][c]) = nl; ch = true; }
@@ -1256,21 +1372,27 @@ flood_kernel(const FloodParams p) {
                     if (!ch) continue;
                     *reinterpret_cast<volatile unsigned long long *>(&sS[r][c]) = ns;
                     __threadfence_block();
-                    unsigned eb = (r == 1 ? EDGE_TOP : 0u) | (r == CT ? EDGE_BOTTOM : 0u) | (c == 1 ? EDGE_LEFT : 0u) | (c == CT ? EDGE_RIGHT : 0u);
+                    // wake the floodable 4-neighbours inside the tile (their "fixed" bit never changes: reuse n0..n3);
+                    // the four flag updates are independent, one queue reservation covers all new entries
+                    const bool w0 = r > 1 && !((n0 >> 16) & 1ull), w1 = c > 1 && !((n1 >> 16) & 1ull);
+                    const bool w2 = c < CT && !((n2 >> 16) & 1ull), w3 = r < CT && !((n3 >> 16) & 1ull);
+                    const int i0 = idx - CT, i1 = idx - 1, i2 = idx + 1, i3 = idx + CT;
+                    unsigned o0 = ~0u, o1 = ~0u, o2 = ~0u, o3 = ~0u;
+                    if (w0) o0 = atomicOr(&sFlag[i0 >> 5], 1u << (i0 & 31)) & (1u << (i0 & 31));
+                    if (w1) o1 = atomicOr(&sFlag[i1 >> 5], 1u << (i1 & 31)) & (1u << (i1 & 31));
+                    if (w2) o2 = atomicOr(&sFlag[i2 >> 5], 1u << (i2 & 31)) & (1u << (i2 & 31));
+                    if (w3) o3 = atomicOr(&sFlag[i3 >> 5], 1u << (i3 & 31)) & (1u << (i3 & 31));
+                    const int cnt = (o0 == 0) + (o1 == 0) + (o2 == 0) + (o3 == 0);
+                    if (cnt) {
+                        int pos = atomicAdd(&sMisc[qc ^ 1], cnt);
+                        if (o0 == 0) qout[pos++] = static_cast<unsigned short>(i0);
+                        if (o1 == 0) qout[pos++] = static_cast<unsigned short>(i1);
+                        if (o2 == 0) qout[pos++] = static_cast<unsigned short>(i2);
+                        if (o3 == 0) qout[pos++] = static_cast<unsigned short>(i3);
+                    }
+                    const unsigned eb = (r == 1 ? EDGE_TOP : 0u) | (r == CT ? EDGE_BOTTOM : 0u) | (c == 1 ? EDGE_LEFT : 0u) | (c == CT ? EDGE_RIGHT : 0u);
                     if (eb) atomicOr(reinterpret_cast<unsigned *>(&sMisc[2]), eb);
                     sMisc[3] = 1;
-                    // wake the floodable 4-neighbours inside the tile
-#pragma unroll
-                    for (int d = 0; d < 4; ++d) {
-                        const int rr = r + (d == 0 ? -1 : (d == 3 ? 1 : 0)), cc = c + (d == 1 ? -1 : (d == 2 ? 1 : 0));
-                        if (rr < 1 || rr > CT || cc < 1 || cc > CT) continue;
-                        const unsigned long long sn = *reinterpret_cast<volatile unsigned long long *>(&sS[rr][cc]);
-                        if ((sn >> 16) & 1ull) continue;             // marker or outside the mask
-                        const int nidx = (rr - 1) * CT + (cc - 1);
-                        const unsigned bit = 1u << (nidx & 31);
-                        if (atomicOr(&sFlag[nidx >> 5], bit) & bit) continue;       // already queued
-                        qout[atomicAdd(&sMisc[qc ^ 1], 1)] = static_cast<unsigned short>(nidx);
-                    }
                 }
                 __syncthreads();
                 if (threadIdx.x == 0) sMisc[qc] = 0;
@@ -1281,20 +1403,36 @@ flood_kernel(const FloodParams p) {
             unsigned edge_bits = *reinterpret_cast<volatile unsigned *>(&sMisc[2]);
             unsigned my_edges = 0;
             if (changed_any || fused_init || (LAB32 && sweep == 0)) {
-#pragma unroll 4
-                for (int k = 0; k < 16; ++k) {
-                    const int r = k * 4 + tq;
-                    const int y = y0 + r, x = x0 + tx;
-                    if (y < H && x < W) {
-                        const unsigned long long s = sS[r + 1][tx + 1];
-                        if (fused_init || !((s >> 16) & 1ull)) {
-                            p.state[static_cast<size_t>(y) * W + x] = s;
-                            if (LAB32) p.lab32[static_cast<size_t>(y) * W + x] = sLab[r + 1][tx + 1];
+                if (fast) {
+                    ulonglong2 *dp = reinterpret_cast<ulonglong2 *>(p.state + rowbase);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        ulonglong2 v;
+                        v.x = sS[row + 1][col0 + 2 * j + 1];
+                        v.y = sS[row + 1][col0 + 2 * j + 2];
+                        dp[j] = v;
+                        if (sweep == 0) {
+                            if (static_cast<unsigned>(v.x >> 32) < ORD_INF)
+                                my_edges |= (row == 0 ? EDGE_TOP : 0u) | (row == CT - 1 ? EDGE_BOTTOM : 0u) | (col0 + 2 * j == 0 ? EDGE_LEFT : 0u);
+                            if (static_cast<unsigned>(v.y >> 32) < ORD_INF)
+                                my_edges |= (row == 0 ? EDGE_TOP : 0u) | (row == CT - 1 ? EDGE_BOTTOM : 0u) | (col0 + 2 * j + 1 == CT - 1 ? EDGE_RIGHT : 0u);
                         }
-                        // first visit: the neighbours have not seen this tile yet -- every flooded edge pixel counts
-                        if (sweep == 0 && static_cast<unsigned>(s >> 32) < ORD_INF)
-                            my_edges |= (r == 0 ? EDGE_TOP : 0u) | (r == CT - 1 ? EDGE_BOTTOM : 0u) | (tx == 0 ? EDGE_LEFT : 0u) |
-                                        (tx == CT - 1 ? EDGE_RIGHT : 0u);
+                    }
+                } else {
+#pragma unroll 4
+                    for (int i = 0; i < 16; ++i) {
+                        const int y = y0 + row, x = x0 + col0 + i;
+                        if (y < H && x < W) {
+                            const unsigned long long s = sS[row + 1][col0 + i + 1];
+                            if (fused_init || !((s >> 16) & 1ull)) {
+                                p.state[static_cast<size_t>(y) * W + x] = s;
+                                if (LAB32) p.lab32[static_cast<size_t>(y) * W + x] = sLab[row + 1][col0 + i + 1];
+                            }
+                            // first visit: the neighbours have not seen this tile yet -- every flooded edge pixel counts
+                            if (sweep == 0 && static_cast<unsigned>(s >> 32) < ORD_INF)
+                                my_edges |= (row == 0 ? EDGE_TOP : 0u) | (row == CT - 1 ? EDGE_BOTTOM : 0u) | (col0 + i == 0 ? EDGE_LEFT : 0u) |
+                                            (col0 + i == CT - 1 ? EDGE_RIGHT : 0u);
+                        }
                     }
                 }
             }
@@ -1323,39 +1461,63 @@ flood_kernel(const FloodParams p) {
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int tyi = tile / tiles_x, txi = tile - tyi * tiles_x;
         const int x0 = txi * CT, y0 = tyi * CT;
+        const bool fast = aligned && x0 + CT <= W && y0 + CT <= H && (W & 7) == 0;
+        const size_t rowbase = static_cast<size_t>(y0 + row) * W + x0 + col0;
         __syncthreads();
-        for (int i = threadIdx.x; i < (CT + 2) * (CT + 2); i += 256) {
-            const int r = i / (CT + 2), c = i % (CT + 2);
-            const int y = y0 + r - 1, x = x0 + c - 1;
-            const bool in = y >= 0 && y < H && x >= 0 && x < W;
-            sS[r][c] = in ? p.state[static_cast<size_t>(y) * W + x] : ST_OUTSIDE;
-            if (LAB32) sLab[r][c] = in ? p.lab32[static_cast<size_t>(y) * W + x] : 0;
+        if (fast) {
+            const ulonglong2 *sp = reinterpret_cast<const ulonglong2 *>(p.state + rowbase);
+            ulonglong2 sv[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) sv[j] = sp[j];
+            load_halo(x0, y0);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                sS[row + 1][col0 + 2 * j + 1] = sv[j].x;
+                sS[row + 1][col0 + 2 * j + 2] = sv[j].y;
+            }
+        } else {
+            load_halo(x0, y0);
+#pragma unroll 4
+            for (int i = 0; i < 16; ++i) {
+                const int y = y0 + row, x = x0 + col0 + i;
+                const bool in = y < H && x < W;
+                sS[row + 1][col0 + i + 1] = in ? p.state[static_cast<size_t>(y) * W + x] : ST_OUTSIDE;
+                if (LAB32) sLab[row + 1][col0 + i + 1] = in ? p.lab32[static_cast<size_t>(y) * W + x] : 0;
+            }
         }
         __syncthreads();
-#pragma unroll 4
-        for (int k = 0; k < 16; ++k) {
-            const int y = y0 + k * 4 + tq, x = x0 + tx;
-            if (y >= H || x >= W) continue;
-            const int r = k * 4 + tq + 1, c = tx + 1;
+        unsigned outw[8];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const int y = y0 + row, x = x0 + col0 + i;
+            const int r = row + 1, c = col0 + i + 1;
             const unsigned long long s = sS[r][c];
             const bool flooded = static_cast<unsigned>(s >> 32) < ORD_INF;
             const int me = LAB32 ? sLab[r][c] : static_cast<int>(s & 0xFFFFull);
-            const size_t o = static_cast<size_t>(y) * W + x;
-            if (LAB32) p.out32[o] = flooded ? me : 0;
-            else p.out16[o] = flooded ? static_cast<uint16_t>(me) : static_cast<uint16_t>(0);
-            if (flooded && !((s >> 16) & 1ull)) {
-                const unsigned long long n0 = sS[r - 1][c], n1 = sS[r][c - 1], n2 = sS[r][c + 1], n3 = sS[r + 1][c];
-                unsigned lmin = static_cast<unsigned>(n0 >> 32);
-                lmin = min(lmin, static_cast<unsigned>(n1 >> 32));
-                lmin = min(lmin, static_cast<unsigned>(n2 >> 32));
-                lmin = min(lmin, static_cast<unsigned>(n3 >> 32));
-                bool bad = false;
-                if (static_cast<unsigned>(n0 >> 32) == lmin && (LAB32 ? sLab[r - 1][c] : static_cast<int>(n0 & 0xFFFFull)) != me) bad = true;
-                if (static_cast<unsigned>(n1 >> 32) == lmin && (LAB32 ? sLab[r][c - 1] : static_cast<int>(n1 & 0xFFFFull)) != me) bad = true;
-                if (static_cast<unsigned>(n2 >> 32) == lmin && (LAB32 ? sLab[r][c + 1] : static_cast<int>(n2 & 0xFFFFull)) != me) bad = true;
-                if (static_cast<unsigned>(n3 >> 32) == lmin && (LAB32 ? sLab[r + 1][c] : static_cast<int>(n3 & 0xFFFFull)) != me) bad = true;
-                if (bad) ++bad_total;
+            const unsigned o16 = flooded ? static_cast<unsigned>(me & 0xFFFF) : 0u;
+            if (i & 1) outw[i >> 1] |= o16 << 16; else outw[i >> 1] = o16;
+            if (y < H && x < W) {
+                if (LAB32) p.out32[static_cast<size_t>(y) * W + x] = flooded ? me : 0;
+                else if (!fast) p.out16[static_cast<size_t>(y) * W + x] = static_cast<uint16_t>(o16);
+                if (flooded && !((s >> 16) & 1ull)) {
+                    const unsigned long long n0 = sS[r - 1][c], n1 = sS[r][c - 1], n2 = sS[r][c + 1], n3 = sS[r + 1][c];
+                    unsigned lmin = static_cast<unsigned>(n0 >> 32);
+                    lmin = min(lmin, static_cast<unsigned>(n1 >> 32));
+                    lmin = min(lmin, static_cast<unsigned>(n2 >> 32));
+                    lmin = min(lmin, static_cast<unsigned>(n3 >> 32));
+                    bool bad = false;
+                    if (static_cast<unsigned>(n0 >> 32) == lmin && (LAB32 ? sLab[r - 1][c] : static_cast<int>(n0 & 0xFFFFull)) != me) bad = true;
+                    if (static_cast<unsigned>(n1 >> 32) == lmin && (LAB32 ? sLab[r][c - 1] : static_cast<int>(n1 & 0xFFFFull)) != me) bad = true;
+                    if (static_cast<unsigned>(n2 >> 32) == lmin && (LAB32 ? sLab[r][c + 1] : static_cast<int>(n2 & 0xFFFFull)) != me) bad = true;
+                    if (static_cast<unsigned>(n3 >> 32) == lmin && (LAB32 ? sLab[r + 1][c] : static_cast<int>(n3 & 0xFFFFull)) != me) bad = true;
+                    if (bad) ++bad_total;
+                }
             }
+        }
+        if (fast) {
+            uint4 *op = reinterpret_cast<uint4 *>(p.out16 + rowbase);
+            op[0] = make_uint4(outw[0], outw[1], outw[2], outw[3]);
+            op[1] = make_uint4(outw[4], outw[5], outw[6], outw[7]);
         }
     }
     if (bad_total) atomicAdd(&p.st->ambiguous, static_cast<unsigned int>(bad_total));
@@ -1365,9 +1527,8 @@ flood_kernel(const FloodParams p) {
 
 // exact fallback, part 1 (runs only when the tiled result is order dependent): explicit marker / mask images for
 // ws_sequential_kernel from the packed words of the tiled pipeline
-__global__ void expand_markers_kernel(const uint16_t *__restrict__ L16, const int *__restrict__ G, const unsigned *__restrict__ bitmap,
-                                      const int *__restrict__ prefix, int H, int W, const Stats *st, int *__restrict__ markers,
-                                      uint8_t *__restrict__ mask) {
+__global__ void expand_markers_kernel(const uint16_t *__restrict__ L16, const int *__restrict__ marker_at_root, int H, int W,
+                                      const Stats *st, int *__restrict__ markers, uint8_t *__restrict__ mask) {
     if (st->ambiguous == 0 && st->overflow == 0) return;
     const long long n = static_cast<long long>(H) * W;
     for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n; i += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -1375,7 +1536,7 @@ __global__ void expand_markers_kernel(const uint16_t *__restrict__ L16, const in
         const unsigned v16 = L16[i];
         const bool m = (v16 & L16_MASK) != 0;
         mask[i] = m ? 1 : 0;
-        markers[i] = (m && (v16 & L16_SEED)) ? marker_of(v16, y, x, W, G, bitmap, prefix) : 0;
+        markers[i] = (m && (v16 & L16_SEED)) ? marker_of(v16, y, x, W, marker_at_root) : 0;
     }
 }
 
@@ -1871,9 +2032,7 @@ int run_tiled(const float *a, const float *b, int H, int W, int ld, float th_see
         fp.img = t.cell_s;
         fp.negate = BOUNDARY ? 0 : 1;
         fp.L16 = t.L16;
-        fp.G = t.G;
-        fp.bitmap = t.bitmap;
-        fp.prefix = t.prefix;
+        fp.marker_at_root = t.area;
         fp.state = t.state;
         fp.lab32 = nullptr;
         fp.H = H;
@@ -1891,7 +2050,7 @@ int run_tiled(const float *a, const float *b, int H, int W, int ld, float th_see
     // exact fallback (both kernels return immediately unless the flood flagged an order-dependent pixel)
     {
         const int want = mbs::cdiv(static_cast<int>(n), 256);
-        expand_markers_kernel<<<want < 1184 ? want : 1184, 256, 0, stream>>>(t.L16, t.G, t.bitmap, t.prefix, H, W, t.st, t.markers, t.mask8);
+        expand_markers_kernel<<<want < 1184 ? want : 1184, 256, 0, stream>>>(t.L16, t.area, H, W, t.st, t.markers, t.mask8);
     }
     MBS_CHECK_LAUNCH();
     ws_sequential_kernel<<<1, 32, 0, stream>>>(t.cell_s, BOUNDARY ? 0 : 1, t.markers, t.mask8, H, W, t.lab, t.heap, t.st, 0, out);
@@ -1965,9 +2124,7 @@ extern "C" int mbs_pp_watershed(const float *image, const int32_t *markers, cons
         fp.img = image;
         fp.negate = 0;
         fp.L16 = nullptr;
-        fp.G = nullptr;
-        fp.bitmap = nullptr;
-        fp.prefix = nullptr;
+        fp.marker_at_root = nullptr;
         fp.state = t.state;
         fp.lab32 = t.lab32;
         fp.H = H;

@@ -33,23 +33,32 @@ def _device():
     return torch.device("cuda", torch.cuda.current_device())
 
 
-def _run(masks_dev, max_id, search_radius, radius_hint):
+def _check_err(err):
+    e = err.cpu().numpy()
+    if e.any():
+        raise RuntimeError(f"distance_labels: crops {np.flatnonzero(e).tolist()[:8]} exceeded a device limit "
+                           f"(bit0: instance window too large for shared memory, bit1: > 4096 gaps): {e[e != 0][:8]}")
+
+
+def _run(masks_dev, max_id, search_radius, radius_hint, err=None):
+    """``err``: int32 [n] device tensor that collects the per-crop limit flags (checked later by the caller, no
+    synchronisation here); None = check immediately."""
     L = nat.lib()
     n, H, W = masks_dev.shape
     device = masks_dev.device
     cell = torch.empty((n, H, W), dtype=torch.float32, device=device)
     neigh = torch.empty((n, H, W), dtype=torch.float32, device=device)
     mal = torch.zeros(n, dtype=torch.int32, device=device)
-    err = torch.zeros(n, dtype=torch.int32, device=device)
+    deferred = err is not None
+    if err is None:
+        err = torch.zeros(n, dtype=torch.int32, device=device)
     ws = torch.empty(L.mbs_labels_workspace_bytes(n, H, W, max_id), dtype=torch.uint8, device=device)
     with torch.cuda.device(device):
         nat.check(L.mbs_distance_labels(masks_dev.data_ptr(), n, H, W, max_id, int(search_radius), int(radius_hint),
                                         cell.data_ptr(), neigh.data_ptr(), mal.data_ptr(), err.data_ptr(),
                                         ws.data_ptr(), ws.numel(), nat.stream_ptr()), "distance_labels")
-    e = err.cpu().numpy()
-    if e.any():
-        raise RuntimeError(f"distance_labels: crops {np.flatnonzero(e).tolist()[:8]} exceeded a device limit "
-                           f"(bit0: instance window too large for shared memory, bit1: > 4096 gaps): {e[e != 0][:8]}")
+    if not deferred:
+        _check_err(err)
     return cell, neigh, mal
 
 
@@ -117,45 +126,101 @@ def create_labels_device(masks_dev, max_id, radius_hint=-1):
     return _run(masks_dev, max_id, -1, radius_hint)
 
 
-def create_labels(masks):
+def create_labels(masks, out=None):
     """Batch version of CreateLabelsWorker.create_labels (train.py:63-96) for [n,H,W] masks.
-    Returns (cell_dist [n,H,W] f32, neighbor_dist [n,H,W] f32, max_mal [n] int)."""
+    Returns (cell_dist [n,H,W] f32, neighbor_dist [n,H,W] f32, max_mal [n] int).
+
+    Host path: masks go up and maps come back through pinned, chunked, multi-threaded staging (``staging``), batch
+    k+1 is uploaded while batch k computes, and nothing synchronises per batch except the final read-back of a batch's
+    maps.  ``out=(cell, neigh)``: caller-provided float32 [n,H,W] destinations -- NumPy arrays, or PINNED torch tensors,
+    which are written by the copy engine directly (no host-side copy at all)."""
+    from . import staging
     masks = np.asarray(masks)
     if masks.ndim == 2:
         masks = masks[None]
+    if masks.dtype != np.uint16:
+        if masks.min() < 0 or masks.max() > 65535:
+            raise ValueError("instance ids must fit in uint16")
+        masks = masks.astype(np.uint16)
+    masks = np.ascontiguousarray(masks)
     n, H, W = masks.shape
-    # <= 16 Mpx per batch: 2 x 64 MiB of pinned staging (measured end to end on 4000 crops of 320^2: 473 Mpx/s with
-    # 16 Mpx batches, 284 with 64 Mpx, 161 with 256 Mpx -- allocation and first touch of large staging buffers dominate)
+    # <= 16 Mpx per batch (allocation and first touch of larger device / staging buffers dominate)
     per = max(1, min(n, (_MAX_BATCH_PIXELS // 16) // (H * W)))
     L = nat.lib()
     device = _device()
-    cells = np.empty((n, H, W), np.float32)
-    neighs = np.empty((n, H, W), np.float32)
-    mals = np.empty(n, np.int32)
-    # pinned staging for the read-back of one batch (two float32 maps per pixel dominate the host traffic)
-    key = (per, H, W)
-    if key not in _PINNED:
-        _PINNED.clear()                                # keep one staging pair
-        _PINNED[key] = (torch.empty((per, H, W), dtype=torch.float32, pin_memory=True),
-                        torch.empty((per, H, W), dtype=torch.float32, pin_memory=True))
-    pin_c, pin_n = _PINNED[key]
-    for s in range(0, n, per):
-        dev, max_id = _masks_to_device(masks[s:s + per], device)       # one upload per batch
-        k = dev.shape[0]
-        hint = 0
-        if max_id > 0:       # radius hint from the batch's own max_mal, computed on the uploaded masks
-            mal_dev = torch.zeros(k, dtype=torch.int32, device=device)
-            ws = torch.empty(L.mbs_labels_workspace_bytes(k, H, W, max_id), dtype=torch.uint8, device=device)
-            with torch.cuda.device(device):
-                nat.check(L.mbs_labels_max_mal(dev.data_ptr(), k, H, W, max_id, mal_dev.data_ptr(), ws.data_ptr(), ws.numel(),
-                                               nat.stream_ptr()), "labels_max_mal")
-            hint = int(np.ceil(0.75 * int(mal_dev.max().item())))
-        c, nb, mal = _run(dev, max_id, -1, hint)
-        pin_c[:k].copy_(c, non_blocking=True)
-        pin_n[:k].copy_(nb, non_blocking=True)
-        mals[s:s + k] = mal.cpu().numpy()                               # synchronises the stream
-        cells[s:s + k] = pin_c[:k].numpy()
-        neighs[s:s + k] = pin_n[:k].numpy()
+    pinned_out = out is not None and all(isinstance(o, torch.Tensor) and o.is_pinned() for o in out)
+    if out is None:
+        cells, neighs = np.empty((n, H, W), np.float32), np.empty((n, H, W), np.float32)
+    else:
+        cells, neighs = out
+        for o in (cells, neighs):
+            if tuple(o.shape) != (n, H, W) or (o.dtype not in (np.float32, torch.float32)):
+                raise ValueError("create_labels: out arrays must be float32 [n,H,W]")
+    mals_dev = torch.zeros(n, dtype=torch.int32, device=device)
+    err_dev = torch.zeros(n, dtype=torch.int32, device=device)
+    max_id_all = int(masks.max()) if n else 0
+    starts = list(range(0, n, per))
+    with torch.cuda.device(device):
+        main = torch.cuda.current_stream(device)
+        up, dn = torch.cuda.Stream(device), torch.cuda.Stream(device)
+        bufs = [torch.empty((per, H, W), dtype=torch.int16, device=device) for _ in range(2)]
+        hint_pin = torch.zeros(2, dtype=torch.int32).pin_memory()
+        ev_up = [torch.cuda.Event() for _ in range(2)]
+        ev_free = [torch.cuda.Event() for _ in range(2)]
+
+        def upload(bi):
+            """stream `up`: masks of batch bi -> device, and the batch's max major axis (sizes the EDT launch) -> pinned"""
+            s0 = starts[bi]
+            k = min(per, n - s0)
+            with torch.cuda.stream(up):
+                if bi >= 2:
+                    up.wait_event(ev_free[bi & 1])               # the batch that used this buffer has been computed
+                staging.upload(masks[s0:s0 + k].view(np.int16), bufs[bi & 1][:k])
+                if max_id_all > 0:
+                    mal_dev = torch.zeros(k, dtype=torch.int32, device=device)
+                    ws = torch.empty(L.mbs_labels_workspace_bytes(k, H, W, max_id_all), dtype=torch.uint8, device=device)
+                    nat.check(L.mbs_labels_max_mal(bufs[bi & 1][:k].data_ptr(), k, H, W, max_id_all, mal_dev.data_ptr(), ws.data_ptr(),
+                                                   ws.numel(), nat.stream_ptr()), "labels_max_mal")
+                    hint_pin[bi & 1:(bi & 1) + 1].copy_(mal_dev.max().reshape(1), non_blocking=True)
+                ev_up[bi & 1].record(up)
+
+        def read_back(item):
+            """stream `dn`: maps of a finished batch -> host (blocks the host, overlaps the next batch's kernels)"""
+            c, nb, s0, k, ev = item
+            with torch.cuda.stream(dn):
+                dn.wait_event(ev)
+                c.record_stream(dn)
+                nb.record_stream(dn)
+                if pinned_out:
+                    cells[s0:s0 + k].copy_(c, non_blocking=True)
+                    neighs[s0:s0 + k].copy_(nb, non_blocking=True)
+                else:
+                    staging.download(c, cells[s0:s0 + k] if isinstance(cells, np.ndarray) else cells[s0:s0 + k].numpy())
+                    staging.download(nb, neighs[s0:s0 + k] if isinstance(neighs, np.ndarray) else neighs[s0:s0 + k].numpy())
+
+        if starts:
+            upload(0)
+        pending = None
+        for bi, s0 in enumerate(starts):
+            k = min(per, n - s0)
+            if bi + 1 < len(starts):
+                upload(bi + 1)
+            ev_up[bi & 1].synchronize()                          # masks + hint of this batch are there (uploaded a batch ago)
+            main.wait_event(ev_up[bi & 1])
+            hint = int(np.ceil(0.75 * int(hint_pin[bi & 1]))) if max_id_all > 0 else 0
+            c, nb, mal = _run(bufs[bi & 1][:k], max_id_all, -1, hint, err=err_dev[s0:s0 + k])
+            ev_free[bi & 1].record(main)
+            mals_dev[s0:s0 + k] = mal
+            ev_done = torch.cuda.Event()
+            ev_done.record(main)
+            if pending is not None:
+                read_back(pending)
+            pending = (c, nb, s0, k, ev_done)
+        if pending is not None:
+            read_back(pending)
+        dn.synchronize()
+        mals = mals_dev.cpu().numpy()
+        _check_err(err_dev)
     return cells, neighs, mals
 
 

@@ -1,0 +1,121 @@
+"""Pinned, chunked, multi-threaded staging between caller-owned (pageable) NumPy arrays and device tensors.
+
+The reference's operators take and return plain NumPy arrays.  A pageable ``cudaMemcpy`` of such an
+array runs at 5-6 GB/s on this box (the driver stages it through its own small pinned buffer on one thread), which made
+the NumPy-in / NumPy-out operators 20-150x slower than their kernels (515 Mpx/s vs 10.9 Gpx/s for config
+3, 70 Mpx/s vs 11.5 Gpx/s for config 4).  Here the array is cut into row chunks; a few worker threads copy chunks into a
+ring of pinned buffers (NumPy releases the GIL for large copies) while the copy engine moves the previous chunks, so the
+transfer runs at host-memcpy x threads speed instead.  Callers that already hold pinned memory skip all of this
+(``is_pinned`` tensors are copied directly).
+"""
+import threading
+from concurrent.futures import ThreadPoolExecutor
+
+import numpy as np
+import torch
+
+_CHUNK_BYTES = 8 << 20
+_RING = 8
+_THREADS = 6
+_pool = None
+_rings = {}
+_lock = threading.Lock()
+
+
+def _executor():
+    global _pool
+    if _pool is None:
+        _pool = ThreadPoolExecutor(max_workers=_THREADS, thread_name_prefix="mbseg-stage")
+    return _pool
+
+
+def _ring(device):
+    """ring of pinned chunk buffers + one event per slot, per (device, thread)"""
+    key = (device.index, threading.get_ident())
+    with _lock:
+        r = _rings.get(key)
+        if r is None:
+            r = dict(bufs=[torch.empty(_CHUNK_BYTES, dtype=torch.uint8).pin_memory() for _ in range(_RING)],
+                     events=[torch.cuda.Event() for _ in range(_RING)], used=[False] * _RING)
+            _rings[key] = r
+    return r
+
+
+def _row_chunks(n_rows, row_bytes):
+    per = max(1, _CHUNK_BYTES // max(row_bytes, 1))
+    return [(s, min(s + per, n_rows)) for s in range(0, n_rows, per)]
+
+
+def upload(src, dst):
+    """``src``: C-contiguous NumPy array; ``dst``: contiguous CUDA tensor with the same number of bytes.  The copy is
+    enqueued on the current stream; the function returns when the last chunk has been handed to the copy engine
+    (``src`` may be modified afterwards)."""
+    src = np.ascontiguousarray(src)
+    nbytes = src.nbytes
+    if nbytes != dst.numel() * dst.element_size():
+        raise ValueError("staging.upload: size mismatch")
+    flat_src = src.reshape(-1).view(np.uint8)
+    flat_dst = dst.reshape(-1).view(torch.uint8)
+    if nbytes <= (1 << 20):                       # small: one pageable copy is as good
+        flat_dst.copy_(torch.from_numpy(flat_src))
+        return
+    ring = _ring(dst.device)
+    chunks = [(s, min(s + _CHUNK_BYTES, nbytes)) for s in range(0, nbytes, _CHUNK_BYTES)]
+    ex = _executor()
+
+    def fill(slot, s, e):
+        if ring["used"][slot]:
+            ring["events"][slot].synchronize()     # the previous transfer out of this pinned buffer is done
+        np.copyto(ring["bufs"][slot].numpy()[:e - s], flat_src[s:e])
+        return slot, s, e
+
+    futures = []
+    for k, (s, e) in enumerate(chunks):
+        if k >= _RING:                             # the slot is reused: its previous chunk must have been ENQUEUED first
+            slot, s0, e0 = futures[k - _RING].result()
+            flat_dst[s0:e0].copy_(ring["bufs"][slot][:e0 - s0], non_blocking=True)
+            ring["events"][slot].record()
+            ring["used"][slot] = True
+            futures[k - _RING] = None
+        futures.append(ex.submit(fill, k % _RING, s, e))
+    for f in futures:
+        if f is None:
+            continue
+        slot, s0, e0 = f.result()
+        flat_dst[s0:e0].copy_(ring["bufs"][slot][:e0 - s0], non_blocking=True)
+        ring["events"][slot].record()
+        ring["used"][slot] = True
+
+
+def download(src, dst):
+    """``src``: contiguous CUDA tensor; ``dst``: C-contiguous writable NumPy array of the same byte size.  Blocks until
+    ``dst`` holds the data (device-to-host into pinned chunks, worker threads copy them out)."""
+    nbytes = dst.nbytes
+    if nbytes != src.numel() * src.element_size() or not dst.flags.c_contiguous:
+        raise ValueError("staging.download: size mismatch / non-contiguous destination")
+    flat_src = src.reshape(-1).view(torch.uint8)
+    flat_dst = dst.reshape(-1).view(np.uint8)
+    if nbytes <= (1 << 20):
+        flat_dst[:] = flat_src.cpu().numpy()
+        return
+    ring = _ring(src.device)
+    chunks = [(s, min(s + _CHUNK_BYTES, nbytes)) for s in range(0, nbytes, _CHUNK_BYTES)]
+    ex = _executor()
+
+    def drain(slot, s, e):
+        ring["events"][slot].synchronize()
+        np.copyto(flat_dst[s:e], ring["bufs"][slot].numpy()[:e - s])
+
+    futures = []
+    for k, (s, e) in enumerate(chunks):
+        slot = k % _RING
+        if k >= _RING:
+            futures[k - _RING].result()            # the buffer has been emptied
+        elif ring["used"][slot]:
+            ring["events"][slot].synchronize()
+        ring["bufs"][slot][:e - s].copy_(flat_src[s:e], non_blocking=True)
+        ring["events"][slot].record()
+        ring["used"][slot] = True
+        futures.append(ex.submit(drain, slot, s, e))
+    for f in futures:
+        f.result()

@@ -126,3 +126,33 @@ def test_boundary_border_and_cell_dist_label_types():
         lab.get_label(m, "j4", 10)
     with pytest.raises(Exception):
         lab.get_label(m, "nonsense", 10)
+
+
+def test_create_labels_host_paths_agree(native_lib):
+    """host path of config 4: pipelined pinned staging into fresh arrays, into caller-provided NumPy arrays and straight
+    into caller-provided PINNED tensors (no host copy) all give the bytes of the device-resident entry"""
+    from microbeseg_b200 import labels as lab, synthetic as sy
+    masks = np.stack([sy.synth_instance_mask(160, 192, 18 + i, 900 + i).astype(np.uint16) for i in range(9)])
+    c0, n0, m0 = lab.create_labels(masks)
+    dev = torch.from_numpy(masks.view(np.int16)).cuda()
+    cd, nd, md = lab.create_labels_device(dev, int(masks.max()))
+    assert np.array_equal(c0, cd.cpu().numpy()) and np.array_equal(n0, nd.cpu().numpy()) and np.array_equal(m0, md.cpu().numpy())
+    c1, n1 = np.zeros_like(c0), np.zeros_like(n0)
+    lab.create_labels(masks, out=(c1, n1))
+    assert np.array_equal(c1, c0) and np.array_equal(n1, n0)
+    pc, pn = torch.zeros(c0.shape).pin_memory(), torch.zeros(n0.shape).pin_memory()
+    lab.create_labels(masks, out=(pc, pn))
+    assert np.array_equal(pc.numpy(), c0) and np.array_equal(pn.numpy(), n0)
+
+
+def test_staging_roundtrip(native_lib):
+    from microbeseg_b200 import staging
+    rng = np.random.default_rng(5)
+    for shape, dt in (((3000, 3001), np.float32), ((7, 5), np.uint16), ((2, 4096, 4096), np.uint16)):
+        a = (rng.random(shape) * 60000).astype(dt)
+        tdt = {np.dtype(np.float32): torch.float32, np.dtype(np.uint16): torch.int16}[np.dtype(dt)]
+        d = torch.empty(shape, dtype=tdt, device="cuda")
+        staging.upload(a.view(np.int16) if dt == np.uint16 else a, d)
+        back = np.zeros(shape, dt)
+        staging.download(d, back.view(np.int16) if dt == np.uint16 else back)
+        assert np.array_equal(a, back)
