@@ -246,6 +246,18 @@ int mbs_contour_first(const uint16_t *mask, int H, int W, int n_labels, int32_t 
 int mbs_contour_trace(const uint16_t *mask, int H, int W, int n_labels, const int32_t *first, const int64_t *offsets,
                       int32_t *counts, int32_t *points_yx, int32_t *overflow, void *stream);
 
+/* ---------------------------------------------------------------------------------------- */
+/* per-frame analysis                                                     */
+/* ---------------------------------------------------------------------------------------- */
+/*
+ * Area and major / minor axis length (skimage regionprops: 4*sqrt of the inertia tensor eigenvalues, float64) of every
+ * instance id of every frame.  Replaces the regionprops loop of src/inference/analysis.py:153-166 (per-frame counts,
+ * mean area, mean axis lengths of the analysis export).  Outputs are indexed [frame * (max_id+1) + id]; area 0 = id absent.
+ * Workspace: (max_id+1) * n_frames * 96 bytes (rounded up to 256).
+ */
+int mbs_instance_stats(const uint16_t *masks, int n_frames, int H, int W, int max_id, int32_t *area, double *major,
+                       double *minor, void *workspace, size_t workspace_bytes, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -100,6 +100,7 @@ _SIGS = {
     "mbs_label8_instances": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "mbs_pp_watershed": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_size_t, c_void_p,
                                  c_int, c_void_p]),
+    "mbs_instance_stats": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "mbs_contour_first": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     "mbs_contour_trace": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
 }

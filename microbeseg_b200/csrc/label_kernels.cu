@@ -803,6 +803,41 @@ extern "C" int mbs_labels_max_mal(const uint16_t *masks, int n_crops, int H, int
     return 0;
 }
 
+// per-frame analysis (src/inference/analysis.py:141-170): area and axis lengths of every instance
+namespace {
+__global__ void lab_export_stats_kernel(const CellStats *cs, int total, int32_t *area, double *major, double *minor) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const CellStats s = cs[i];
+    double ma = 0.0, mi = 0.0;
+    if (s.cnt) axis_lengths(s.cnt, s.sy, s.sx, s.syy, s.sxx, s.sxy, &ma, &mi);
+    area[i] = static_cast<int32_t>(s.cnt);
+    major[i] = ma;
+    minor[i] = mi;
+}
+}  // namespace
+
+extern "C" int mbs_instance_stats(const uint16_t *masks, int n_frames, int H, int W, int max_id, int32_t *area, double *major,
+                                  double *minor, void *workspace, size_t workspace_bytes, void *stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    MBS_REQUIRE(n_frames > 0 && H > 0 && W > 0 && max_id >= 0 && max_id <= 65535 && area && major && minor,
+                "instance_stats: bad arguments");
+    const int ids = max_id + 1;
+    const size_t need = r256(static_cast<size_t>(n_frames) * ids * sizeof(CellStats));
+    MBS_REQUIRE(workspace_bytes >= need, "instance_stats: workspace too small (%zu < %zu)", workspace_bytes, need);
+    MBS_REQUIRE(static_cast<long long>(n_frames) * ids < (1ll << 31), "instance_stats: too many (frame, id) pairs");
+    CellStats *cs = reinterpret_cast<CellStats *>(workspace);
+    const int total = n_frames * ids;
+    dim3 b2(32, 8), g3(mbs::cdiv(W, 32), mbs::cdiv(H, 8), n_frames);
+    lab_init_stats_kernel<<<mbs::cdiv(total, 256), 256, 0, stream>>>(cs, total);
+    MBS_CHECK_LAUNCH();
+    lab_accum_kernel<<<g3, b2, 0, stream>>>(masks, H, W, ids, cs);
+    MBS_CHECK_LAUNCH();
+    lab_export_stats_kernel<<<mbs::cdiv(total, 256), 256, 0, stream>>>(cs, total, area, major, minor);
+    MBS_CHECK_LAUNCH();
+    return 0;
+}
+
 extern "C" int mbs_distance_labels(const uint16_t *masks, int n_crops, int H, int W, int max_id, int search_radius,
                                    int radius_hint, float *cell_dist, float *neighbor_dist, int32_t *max_mal_out, int32_t *error_out,
                                    void *workspace, size_t workspace_bytes, void *stream_) {

@@ -1142,7 +1142,7 @@ constexpr unsigned EDGE_TOP = 1u, EDGE_BOTTOM = 2u, EDGE_LEFT = 4u, EDGE_RIGHT =
 // Tile loads / stores are bulk 16-byte accesses issued back to back (a tile visit used to cost ~20 us of serialised
 // load latency); thread t owns the 16 consecutive pixels (row t/4, columns (t%4)*16 ..) in those phases.
 template <bool LAB32>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 3)
 flood_kernel(const FloodParams p) {
     namespace cg = cooperative_groups;
     cg::grid_group grid = cg::this_grid();
@@ -1304,7 +1304,7 @@ flood_kernel(const FloodParams p) {
             const bool first_visit = sweep == 0;
 #pragma unroll 4
             for (int i = 0; i < 16; ++i) {
-                const int r = row, c = col0 + i;
+                const int r = i * 4 + (threadIdx.x >> 6), c = threadIdx.x & (CT - 1);     // a warp = 32 adjacent columns: no bank conflicts
                 const unsigned long long s = sS[r + 1][c + 1];
                 bool want = false;
                 if (!((s >> 16) & 1ull)) {
@@ -1338,61 +1338,75 @@ flood_kernel(const FloodParams p) {
                 const unsigned short *qin = sQ + qc * CT * CT;
                 unsigned short *qout = sQ + (qc ^ 1) * CT * CT;
                 for (int i = threadIdx.x; i < n; i += 256) {
-                    const int idx = qin[i];
-                    const int r = (idx >> 6) + 1, c = (idx & (CT - 1)) + 1;
+                    int idx = qin[i];
                     atomicAnd(&sFlag[idx >> 5], ~(1u << (idx & 31)));      // dequeued before the neighbours are read
                     __threadfence_block();
-                    // skimage's neighbour order: up, left, right, down; the first minimal (level, hops) wins
-                    const unsigned long long n0 = *reinterpret_cast<volatile unsigned long long *>(&sS[r - 1][c]);
-                    const unsigned long long n1 = *reinterpret_cast<volatile unsigned long long *>(&sS[r][c - 1]);
-                    const unsigned long long n2 = *reinterpret_cast<volatile unsigned long long *>(&sS[r][c + 1]);
-                    const unsigned long long n3 = *reinterpret_cast<volatile unsigned long long *>(&sS[r + 1][c]);
-                    const unsigned long long old = *reinterpret_cast<volatile unsigned long long *>(&sS[r][c]);
-                    const unsigned vo = sV[idx];
-                    unsigned long long best = n0;
-                    int bi = 0;
-                    if ((n1 >> 16) < (best >> 16)) { best = n1; bi = 1; }
-                    if ((n2 >> 16) < (best >> 16)) { best = n2; bi = 2; }
-                    if ((n3 >> 16) < (best >> 16)) { best = n3; bi = 3; }
-                    const unsigned Lq = static_cast<unsigned>(best >> 32);
-                    if (Lq >= ORD_INF) continue;                     // no flooded neighbour yet
-                    unsigned long long ns;
-                    if (vo > Lq) {
-                        ns = (static_cast<unsigned long long>(vo) << 32) | (best & 0xFFFFull);
-                    } else {
-                        unsigned h = ((static_cast<unsigned>(best >> 16) & 0xFFFFu) >> 1) + 1u;
-                        if (h > HOP_MAX) { h = HOP_MAX; overflow = true; }
-                        ns = (static_cast<unsigned long long>(Lq) << 32) | (static_cast<unsigned long long>(h << 1) << 16) | (best & 0xFFFFull);
+                    // One queue entry = one evaluation plus a CHASE: while a pixel changes, the thread carries on with
+                    // the neighbour straight ahead (away from the neighbour the new state came from), so a front crosses
+                    // up to CHASE pixels per round along rows / columns instead of one.
+                    constexpr int CHASE = 12;
+#pragma unroll 1
+                    for (int step = 0; step <= CHASE; ++step) {
+                        const int r = (idx >> 6) + 1, c = (idx & (CT - 1)) + 1;
+                        // skimage's neighbour order: up, left, right, down; the first minimal (level, hops) wins
+                        const unsigned long long n0 = *reinterpret_cast<volatile unsigned long long *>(&sS[r - 1][c]);
+                        const unsigned long long n1 = *reinterpret_cast<volatile unsigned long long *>(&sS[r][c - 1]);
+                        const unsigned long long n2 = *reinterpret_cast<volatile unsigned long long *>(&sS[r][c + 1]);
+                        const unsigned long long n3 = *reinterpret_cast<volatile unsigned long long *>(&sS[r + 1][c]);
+                        const unsigned long long old = *reinterpret_cast<volatile unsigned long long *>(&sS[r][c]);
+                        const unsigned vo = sV[idx];
+                        unsigned long long best = n0;
+                        int bi = 0;
+                        if ((n1 >> 16) < (best >> 16)) { best = n1; bi = 1; }
+                        if ((n2 >> 16) < (best >> 16)) { best = n2; bi = 2; }
+                        if ((n3 >> 16) < (best >> 16)) { best = n3; bi = 3; }
+                        const unsigned Lq = static_cast<unsigned>(best >> 32);
+                        if (Lq >= ORD_INF) break;                        // no flooded neighbour yet
+                        unsigned long long ns;
+                        if (vo > Lq) {
+                            ns = (static_cast<unsigned long long>(vo) << 32) | (best & 0xFFFFull);
+                        } else {
+                            unsigned h = ((static_cast<unsigned>(best >> 16) & 0xFFFFu) >> 1) + 1u;
+                            if (h > HOP_MAX) { h = HOP_MAX; overflow = true; }
+                            ns = (static_cast<unsigned long long>(Lq) << 32) | (static_cast<unsigned long long>(h << 1) << 16) | (best & 0xFFFFull);
+                        }
+                        bool ch = ns != old;
+                        if (LAB32) {
+                            const int nl = bi == 0 ? sLab[r - 1][c] : (bi == 1 ? sLab[r][c - 1] : (bi == 2 ? sLab[r][c + 1] : sLab[r + 1][c]));
+                            if (nl != sLab[r][c]) { *reinterpret_cast<volatile int *>(&sLab[r][c]) = nl; ch = true; }
+                        }
+                        if (!ch) break;
+                        *reinterpret_cast<volatile unsigned long long *>(&sS[r][c]) = ns;
+                        __threadfence_block();
+                        // the pixel straight ahead is handled by this thread in the next step; the other floodable
+                        // neighbours inside the tile are queued (their "fixed" bit never changes: reuse n0..n3)
+                        const int ahead = 3 - bi;                        // came from up -> go down, left -> right, ...
+                        bool w0 = r > 1 && !((n0 >> 16) & 1ull), w1 = c > 1 && !((n1 >> 16) & 1ull);
+                        bool w2 = c < CT && !((n2 >> 16) & 1ull), w3 = r < CT && !((n3 >> 16) & 1ull);
+                        const bool go = step < CHASE && (ahead == 0 ? w0 : (ahead == 1 ? w1 : (ahead == 2 ? w2 : w3)));
+                        if (go) {
+                            if (ahead == 0) w0 = false; else if (ahead == 1) w1 = false; else if (ahead == 2) w2 = false; else w3 = false;
+                        }
+                        const int i0 = idx - CT, i1 = idx - 1, i2 = idx + 1, i3 = idx + CT;
+                        unsigned o0 = ~0u, o1 = ~0u, o2 = ~0u, o3 = ~0u;
+                        if (w0) o0 = atomicOr(&sFlag[i0 >> 5], 1u << (i0 & 31)) & (1u << (i0 & 31));
+                        if (w1) o1 = atomicOr(&sFlag[i1 >> 5], 1u << (i1 & 31)) & (1u << (i1 & 31));
+                        if (w2) o2 = atomicOr(&sFlag[i2 >> 5], 1u << (i2 & 31)) & (1u << (i2 & 31));
+                        if (w3) o3 = atomicOr(&sFlag[i3 >> 5], 1u << (i3 & 31)) & (1u << (i3 & 31));
+                        const int cnt = (o0 == 0) + (o1 == 0) + (o2 == 0) + (o3 == 0);
+                        if (cnt) {
+                            int pos = atomicAdd(&sMisc[qc ^ 1], cnt);
+                            if (o0 == 0) qout[pos++] = static_cast<unsigned short>(i0);
+                            if (o1 == 0) qout[pos++] = static_cast<unsigned short>(i1);
+                            if (o2 == 0) qout[pos++] = static_cast<unsigned short>(i2);
+                            if (o3 == 0) qout[pos++] = static_cast<unsigned short>(i3);
+                        }
+                        const unsigned eb = (r == 1 ? EDGE_TOP : 0u) | (r == CT ? EDGE_BOTTOM : 0u) | (c == 1 ? EDGE_LEFT : 0u) | (c == CT ? EDGE_RIGHT : 0u);
+                        if (eb) atomicOr(reinterpret_cast<unsigned *>(&sMisc[2]), eb);
+                        sMisc[3] = 1;
+                        if (!go) break;
+                        idx = ahead == 0 ? i0 : (ahead == 1 ? i1 : (ahead == 2 ? i2 : i3));
                     }
-                    bool ch = ns != old;
-                    if (LAB32) {
-                        const int nl = bi == 0 ? sLab[r - 1][c] : (bi == 1 ? sLab[r][c - 1] : (bi == 2 ? sLab[r][c + 1] : sLab[r + 1][c]));
-                        if (nl != sLab[r][c]) { *reinterpret_cast<volatile int *>(&sLab[r][c]) = nl; ch = true; }
-                    }
-                    if (!ch) continue;
-                    *reinterpret_cast<volatile unsigned long long *>(&sS[r][c]) = ns;
-                    __threadfence_block();
-                    // wake the floodable 4-neighbours inside the tile (their "fixed" bit never changes: reuse n0..n3);
-                    // the four flag updates are independent, one queue reservation covers all new entries
-                    const bool w0 = r > 1 && !((n0 >> 16) & 1ull), w1 = c > 1 && !((n1 >> 16) & 1ull);
-                    const bool w2 = c < CT && !((n2 >> 16) & 1ull), w3 = r < CT && !((n3 >> 16) & 1ull);
-                    const int i0 = idx - CT, i1 = idx - 1, i2 = idx + 1, i3 = idx + CT;
-                    unsigned o0 = ~0u, o1 = ~0u, o2 = ~0u, o3 = ~0u;
-                    if (w0) o0 = atomicOr(&sFlag[i0 >> 5], 1u << (i0 & 31)) & (1u << (i0 & 31));
-                    if (w1) o1 = atomicOr(&sFlag[i1 >> 5], 1u << (i1 & 31)) & (1u << (i1 & 31));
-                    if (w2) o2 = atomicOr(&sFlag[i2 >> 5], 1u << (i2 & 31)) & (1u << (i2 & 31));
-                    if (w3) o3 = atomicOr(&sFlag[i3 >> 5], 1u << (i3 & 31)) & (1u << (i3 & 31));
-                    const int cnt = (o0 == 0) + (o1 == 0) + (o2 == 0) + (o3 == 0);
-                    if (cnt) {
-                        int pos = atomicAdd(&sMisc[qc ^ 1], cnt);
-                        if (o0 == 0) qout[pos++] = static_cast<unsigned short>(i0);
-                        if (o1 == 0) qout[pos++] = static_cast<unsigned short>(i1);
-                        if (o2 == 0) qout[pos++] = static_cast<unsigned short>(i2);
-                        if (o3 == 0) qout[pos++] = static_cast<unsigned short>(i3);
-                    }
-                    const unsigned eb = (r == 1 ? EDGE_TOP : 0u) | (r == CT ? EDGE_BOTTOM : 0u) | (c == 1 ? EDGE_LEFT : 0u) | (c == CT ? EDGE_RIGHT : 0u);
-                    if (eb) atomicOr(reinterpret_cast<unsigned *>(&sMisc[2]), eb);
-                    sMisc[3] = 1;
                 }
                 __syncthreads();
                 if (threadIdx.x == 0) sMisc[qc] = 0;
@@ -1486,38 +1500,31 @@ flood_kernel(const FloodParams p) {
             }
         }
         __syncthreads();
-        unsigned outw[8];
-#pragma unroll
+#pragma unroll 4
         for (int i = 0; i < 16; ++i) {
-            const int y = y0 + row, x = x0 + col0 + i;
-            const int r = row + 1, c = col0 + i + 1;
+            const int rr = i * 4 + (threadIdx.x >> 6), cc = threadIdx.x & (CT - 1);       // a warp = 32 adjacent columns
+            const int y = y0 + rr, x = x0 + cc;
+            if (y >= H || x >= W) continue;
+            const int r = rr + 1, c = cc + 1;
             const unsigned long long s = sS[r][c];
             const bool flooded = static_cast<unsigned>(s >> 32) < ORD_INF;
             const int me = LAB32 ? sLab[r][c] : static_cast<int>(s & 0xFFFFull);
-            const unsigned o16 = flooded ? static_cast<unsigned>(me & 0xFFFF) : 0u;
-            if (i & 1) outw[i >> 1] |= o16 << 16; else outw[i >> 1] = o16;
-            if (y < H && x < W) {
-                if (LAB32) p.out32[static_cast<size_t>(y) * W + x] = flooded ? me : 0;
-                else if (!fast) p.out16[static_cast<size_t>(y) * W + x] = static_cast<uint16_t>(o16);
-                if (flooded && !((s >> 16) & 1ull)) {
-                    const unsigned long long n0 = sS[r - 1][c], n1 = sS[r][c - 1], n2 = sS[r][c + 1], n3 = sS[r + 1][c];
-                    unsigned lmin = static_cast<unsigned>(n0 >> 32);
-                    lmin = min(lmin, static_cast<unsigned>(n1 >> 32));
-                    lmin = min(lmin, static_cast<unsigned>(n2 >> 32));
-                    lmin = min(lmin, static_cast<unsigned>(n3 >> 32));
-                    bool bad = false;
-                    if (static_cast<unsigned>(n0 >> 32) == lmin && (LAB32 ? sLab[r - 1][c] : static_cast<int>(n0 & 0xFFFFull)) != me) bad = true;
-                    if (static_cast<unsigned>(n1 >> 32) == lmin && (LAB32 ? sLab[r][c - 1] : static_cast<int>(n1 & 0xFFFFull)) != me) bad = true;
-                    if (static_cast<unsigned>(n2 >> 32) == lmin && (LAB32 ? sLab[r][c + 1] : static_cast<int>(n2 & 0xFFFFull)) != me) bad = true;
-                    if (static_cast<unsigned>(n3 >> 32) == lmin && (LAB32 ? sLab[r + 1][c] : static_cast<int>(n3 & 0xFFFFull)) != me) bad = true;
-                    if (bad) ++bad_total;
-                }
+            const size_t o = static_cast<size_t>(y) * W + x;
+            if (LAB32) p.out32[o] = flooded ? me : 0;
+            else p.out16[o] = flooded ? static_cast<uint16_t>(me) : static_cast<uint16_t>(0);
+            if (flooded && !((s >> 16) & 1ull)) {
+                const unsigned long long n0 = sS[r - 1][c], n1 = sS[r][c - 1], n2 = sS[r][c + 1], n3 = sS[r + 1][c];
+                unsigned lmin = static_cast<unsigned>(n0 >> 32);
+                lmin = min(lmin, static_cast<unsigned>(n1 >> 32));
+                lmin = min(lmin, static_cast<unsigned>(n2 >> 32));
+                lmin = min(lmin, static_cast<unsigned>(n3 >> 32));
+                bool bad = false;
+                if (static_cast<unsigned>(n0 >> 32) == lmin && (LAB32 ? sLab[r - 1][c] : static_cast<int>(n0 & 0xFFFFull)) != me) bad = true;
+                if (static_cast<unsigned>(n1 >> 32) == lmin && (LAB32 ? sLab[r][c - 1] : static_cast<int>(n1 & 0xFFFFull)) != me) bad = true;
+                if (static_cast<unsigned>(n2 >> 32) == lmin && (LAB32 ? sLab[r][c + 1] : static_cast<int>(n2 & 0xFFFFull)) != me) bad = true;
+                if (static_cast<unsigned>(n3 >> 32) == lmin && (LAB32 ? sLab[r + 1][c] : static_cast<int>(n3 & 0xFFFFull)) != me) bad = true;
+                if (bad) ++bad_total;
             }
-        }
-        if (fast) {
-            uint4 *op = reinterpret_cast<uint4 *>(p.out16 + rowbase);
-            op[0] = make_uint4(outw[0], outw[1], outw[2], outw[3]);
-            op[1] = make_uint4(outw[4], outw[5], outw[6], outw[7]);
         }
     }
     if (bad_total) atomicAdd(&p.st->ambiguous, static_cast<unsigned int>(bad_total));

@@ -5,6 +5,7 @@ neighbor_dist additionally goes through exp() (numpy's and CUDA's float64 exp ma
 bit) -> after the float32 cast at most 1 float32 ulp (tolerance 1.2e-7 absolute on [0,1] maps)."""
 import numpy as np
 import pytest
+import torch
 
 from oracle import labels as ol
 from microbeseg_b200 import synthetic as sy
