@@ -204,6 +204,12 @@ typedef struct {
 } mbs_ranger_tensor;
 int mbs_ranger_step(const mbs_ranger_tensor *tensors_dev, int n_tensors, int total_rows, float beta1, float beta2,
                     float eps, float weight_decay, float step_lr, int use_denom, int lookahead, float alpha, void *stream);
+/* Fused Adam / AMSGrad step for every parameter tensor in one launch: the reference's Adam recipe
+ * torch.optim.Adam(lr=8e-4, betas=(0.9,0.999), eps=1e-8, weight_decay=0, amsgrad=True) (src/training/train.py:380-385),
+ * arithmetic of torch/optim/adam.py::_single_tensor_adam.  Same table type as mbs_ranger_step (`slow` = max_exp_avg_sq,
+ * gc = 0, rows = 1024-element chunks); step_size = lr / (1 - beta1^step), bias_correction2_sqrt = sqrt(1 - beta2^step). */
+int mbs_adam_step(const mbs_ranger_tensor *tensors_dev, int n_tensors, int total_rows, float beta1, float beta2, float eps,
+                  float weight_decay, float step_size, float bias_correction2_sqrt, int amsgrad, void *stream);
 
 /* ---------------------------------------------------------------------------------------- */
 /* training-label generation, distance method (replaces src/training/train_data_representations */

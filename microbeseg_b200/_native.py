@@ -97,6 +97,7 @@ _SIGS = {
     "mbs_conv_wgrad": (c_int, [ctypes.POINTER(WgradDesc), c_void_p]),
     "mbs_ranger_step": (c_int, [c_void_p, c_int, c_int, c_float, c_float, c_float, c_float, c_float, c_int, c_int, c_float,
                                 c_void_p]),
+    "mbs_adam_step": (c_int, [c_void_p, c_int, c_int, c_float, c_float, c_float, c_float, c_float, c_float, c_int, c_void_p]),
     "mbs_label8_instances": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "mbs_pp_watershed": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_size_t, c_void_p,
                                  c_int, c_void_p]),

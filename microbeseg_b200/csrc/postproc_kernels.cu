@@ -221,6 +221,9 @@ struct Stats {
     // instrumentation of flood_kernel (tools/time_pp.py): tiles visited per sweep, %globaltimer at the end of each sweep
     unsigned int dbg_tiles[32];
     unsigned long long dbg_t[36];
+    unsigned int dbg_rounds[32];    // sum over the visited tiles of the number of event rounds, per sweep
+    unsigned int dbg_maxrounds[32];
+    unsigned int dbg_items[32];     // queue entries processed, per sweep
 };
 
 // path compression + component areas + component / pixel counts in one pass
@@ -1127,11 +1130,15 @@ struct FloodParams {
 };
 
 // shared memory of flood_kernel: state tile with a 1-pixel halo, flood values, two work queues, "queued" bits
+constexpr unsigned EDGE_DIRTY = 16u;          // a light revisit ran out of queue space: full block-wide visit next sweep
+constexpr int LQ = 1024;                      // queue entries of a warp-level ("light") revisit
+constexpr int LIGHT_WARP_BYTES = 2 * LQ * 2 + (CT * CT / 32) * 4 + 16;
+constexpr int FL_LIST_MAX = 256;              // light revisits a block can defer per sweep (more: handled block-wide)
 constexpr int FL_STATE_BYTES = (CT + 2) * (CT + 2) * 8;
 constexpr int FL_V_BYTES = CT * CT * 4;
 constexpr int FL_Q_BYTES = 2 * CT * CT * 2;
 constexpr int FL_FLAG_BYTES = (CT * CT / 32) * 4;
-constexpr int FL_MISC_BYTES = 64;
+constexpr int FL_MISC_BYTES = 64 + 4 * FL_LIST_MAX + 16;       // queue sizes / edge bits / flags, list of light revisits
 constexpr int FL_LAB_BYTES = (CT + 2) * (CT + 2) * 4;
 constexpr int FLOOD_SMEM16 = FL_STATE_BYTES + FL_V_BYTES + FL_Q_BYTES + FL_FLAG_BYTES + FL_MISC_BYTES;
 constexpr int FLOOD_SMEM32 = FLOOD_SMEM16 + FL_LAB_BYTES;
@@ -1154,6 +1161,7 @@ flood_kernel(const FloodParams p) {
     unsigned *sFlag = reinterpret_cast<unsigned *>(smem + FL_STATE_BYTES + FL_V_BYTES + FL_Q_BYTES);
     int *sMisc = reinterpret_cast<int *>(smem + FL_STATE_BYTES + FL_V_BYTES + FL_Q_BYTES + FL_FLAG_BYTES);   // [0],[1]: queue sizes, [2]: edge bits, [3]: any change
     int(*sLab)[CT + 2] = reinterpret_cast<int(*)[CT + 2]>(smem + FLOOD_SMEM16);
+    int *sList = sMisc + 16;                     // [0, FL_LIST_MAX): tiles deferred to a warp-level revisit, [FL_LIST_MAX]: "one of them changed"
     const int H = p.H, W = p.W;
     const int tiles_x = (W + CT - 1) / CT, tiles_y = (H + CT - 1) / CT;
     const int ntiles = tiles_x * tiles_y;
@@ -1190,16 +1198,29 @@ flood_kernel(const FloodParams p) {
         const uint8_t *prev = p.tile_changed + ((sweep + 1) & 1) * ntiles;
         uint8_t *cur = p.tile_changed + (sweep & 1) * ntiles;
         bool block_changed = false;
+        if (threadIdx.x == 0) sList[FL_LIST_MAX] = 0;
+        int n_light = 0;                              // uniform across the block
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
             const int tyi = tile / tiles_x, txi = tile - tyi * tiles_x;
+            bool full_scan = sweep == 0;
             if (sweep > 0) {
-                // a tile is revisited only if a neighbour changed pixels on the edge that faces it
+                // a tile is revisited only if a neighbour changed pixels on the edge that faces it ...
                 const bool need = (txi > 0 && (prev[tile - 1] & EDGE_RIGHT)) || (txi + 1 < tiles_x && (prev[tile + 1] & EDGE_LEFT)) ||
                                   (tyi > 0 && (prev[tile - tiles_x] & EDGE_BOTTOM)) || (tyi + 1 < tiles_y && (prev[tile + tiles_x] & EDGE_TOP));
-                if (!need) {
+                // ... or if its own light revisit overflowed in the previous sweep
+                const bool dirty = (prev[tile] & EDGE_DIRTY) != 0;
+                if (!need && !dirty) {
                     if (threadIdx.x == 0) cur[tile] = 0;
                     continue;
                 }
+                if (!LAB32 && !dirty && n_light < FL_LIST_MAX) {
+                    // a revisit changes a few dozen pixels next to an edge: one WARP handles it straight on the global
+                    // state (below) instead of the block staging the whole 48 KB tile in shared memory
+                    if (threadIdx.x == 0) sList[n_light] = tile;
+                    ++n_light;
+                    continue;
+                }
+                full_scan = dirty;
             }
             const int x0 = txi * CT, y0 = tyi * CT;
             const bool fast = aligned && x0 + CT <= W && y0 + CT <= H && (W & 7) == 0;      // 16-byte rows, no ragged edge
@@ -1301,7 +1322,7 @@ flood_kernel(const FloodParams p) {
             __syncthreads();
             // initial work list.  First visit: every floodable pixel next to a flooded one; later visits: the floodable
             // pixels on the tile edges next to a flooded halo pixel (the inside is already at its fixed point)
-            const bool first_visit = sweep == 0;
+            const bool first_visit = full_scan;
 #pragma unroll 4
             for (int i = 0; i < 16; ++i) {
                 const int r = i * 4 + (threadIdx.x >> 6), c = threadIdx.x & (CT - 1);     // a warp = 32 adjacent columns: no bank conflicts
@@ -1332,9 +1353,12 @@ flood_kernel(const FloodParams p) {
             }
             __syncthreads();
             int qc = 0;
+            unsigned n_rounds = 0, n_items = 0;
             for (;;) {
                 const int n = *reinterpret_cast<volatile int *>(&sMisc[qc]);
                 if (n == 0) break;
+                ++n_rounds;
+                n_items += static_cast<unsigned>(n);
                 const unsigned short *qin = sQ + qc * CT * CT;
                 unsigned short *qout = sQ + (qc ^ 1) * CT * CT;
                 for (int i = threadIdx.x; i < n; i += 256) {
@@ -1413,6 +1437,11 @@ flood_kernel(const FloodParams p) {
                 qc ^= 1;
                 __syncthreads();
             }
+            if (threadIdx.x == 0 && sweep < 32) {
+                atomicAdd(&p.st->dbg_rounds[sweep], n_rounds);
+                atomicMax(&p.st->dbg_maxrounds[sweep], n_rounds);
+                atomicAdd(&p.st->dbg_items[sweep], n_items);
+            }
             const bool changed_any = *reinterpret_cast<volatile int *>(&sMisc[3]) != 0;
             unsigned edge_bits = *reinterpret_cast<volatile unsigned *>(&sMisc[2]);
             unsigned my_edges = 0;
@@ -1458,6 +1487,130 @@ flood_kernel(const FloodParams p) {
             }
             if (threadIdx.x == 0) cur[tile] = static_cast<uint8_t>(edge_bits);
             block_changed |= edge_bits != 0;
+        }
+        if (n_light > 0) {
+            __syncthreads();                          // the block-wide tile (if any) is done: its shared memory is free
+            const int warp = threadIdx.x >> 5;
+            unsigned char *wbase = smem + warp * LIGHT_WARP_BYTES;
+            unsigned short *wq = reinterpret_cast<unsigned short *>(wbase);
+            unsigned *wflag = reinterpret_cast<unsigned *>(wbase + 2 * LQ * 2);
+            int *wc = reinterpret_cast<int *>(wbase + 2 * LQ * 2 + (CT * CT / 32) * 4);      // [0],[1] queue sizes, [2] edge bits, [3] overflow
+            auto gstate = [&](int y, int x) -> unsigned long long {
+                unsigned long long v = ~0ull;                  // ST_OUTSIDE
+                if (y >= 0 && y < H && x >= 0 && x < W) v = *reinterpret_cast<volatile unsigned long long *>(&p.state[static_cast<size_t>(y) * W + x]);
+                return v;
+            };
+            for (int li = warp; li < n_light; li += 8) {
+                const int tile = sList[li];
+                const int tyi = tile / tiles_x, txi = tile - tyi * tiles_x;
+                const int x0 = txi * CT, y0 = tyi * CT;
+                __syncwarp();
+                for (int i = lane; i < CT * CT / 32; i += 32) wflag[i] = 0u;
+                if (lane < 4) wc[lane] = 0;
+                __syncwarp();
+                if (lane == 0 && sweep < 32) atomicAdd(&p.st->dbg_tiles[sweep], 1u);
+                // work list: floodable edge pixels next to a flooded pixel of the neighbouring tile
+                for (int e = lane; e < 4 * CT; e += 32) {
+                    const int side = e >> 6, k = e & (CT - 1);
+                    const int r = side == 0 ? 0 : (side == 1 ? CT - 1 : k), c = side <= 1 ? k : (side == 2 ? 0 : CT - 1);
+                    const int hy = y0 + (side == 0 ? -1 : (side == 1 ? CT : k)), hx = x0 + (side <= 1 ? k : (side == 2 ? -1 : CT));
+                    const int y = y0 + r, x = x0 + c;
+                    if (y >= H || x >= W) continue;
+                    if ((gstate(y, x) >> 16) & 1ull) continue;
+                    if (static_cast<unsigned>(gstate(hy, hx) >> 32) >= ORD_INF) continue;
+                    const int idx = r * CT + c;
+                    const unsigned bit = 1u << (idx & 31);
+                    if (atomicOr(&wflag[idx >> 5], bit) & bit) continue;
+                    const int pos = atomicAdd(&wc[0], 1);
+                    if (pos < LQ) wq[pos] = static_cast<unsigned short>(idx); else wc[3] = 1;
+                }
+                __syncwarp();
+                int qc = 0;
+                for (;;) {
+                    int n = *reinterpret_cast<volatile int *>(&wc[qc]);
+                    if (n == 0) break;
+                    if (n > LQ) n = LQ;
+                    const unsigned short *qin = wq + qc * LQ;
+                    unsigned short *qout = wq + (qc ^ 1) * LQ;
+                    for (int i = lane; i < n; i += 32) {
+                        int idx = qin[i];
+                        atomicAnd(&wflag[idx >> 5], ~(1u << (idx & 31)));
+                        __threadfence_block();
+                        constexpr int CHASE = 6;
+#pragma unroll 1
+                        for (int step = 0; step <= CHASE; ++step) {
+                            const int r = idx >> 6, c = idx & (CT - 1);
+                            const int y = y0 + r, x = x0 + c;
+                            const unsigned long long n0 = gstate(y - 1, x), n1 = gstate(y, x - 1), n2 = gstate(y, x + 1), n3 = gstate(y + 1, x);
+                            const unsigned long long old = gstate(y, x);
+                            const float v = p.img[static_cast<size_t>(y) * W + x];
+                            const unsigned vo = ord_f32(p.negate ? -v : v);
+                            unsigned long long best = n0;
+                            int bi = 0;
+                            if ((n1 >> 16) < (best >> 16)) { best = n1; bi = 1; }
+                            if ((n2 >> 16) < (best >> 16)) { best = n2; bi = 2; }
+                            if ((n3 >> 16) < (best >> 16)) { best = n3; bi = 3; }
+                            const unsigned Lq = static_cast<unsigned>(best >> 32);
+                            if (Lq >= ORD_INF) break;
+                            unsigned long long ns;
+                            if (vo > Lq) {
+                                ns = (static_cast<unsigned long long>(vo) << 32) | (best & 0xFFFFull);
+                            } else {
+                                unsigned h = ((static_cast<unsigned>(best >> 16) & 0xFFFFu) >> 1) + 1u;
+                                if (h > HOP_MAX) { h = HOP_MAX; overflow = true; }
+                                ns = (static_cast<unsigned long long>(Lq) << 32) | (static_cast<unsigned long long>(h << 1) << 16) | (best & 0xFFFFull);
+                            }
+                            if (ns == old) break;
+                            *reinterpret_cast<volatile unsigned long long *>(&p.state[static_cast<size_t>(y) * W + x]) = ns;
+                            __threadfence_block();
+                            const int ahead = 3 - bi;
+                            bool w0 = r > 0 && !((n0 >> 16) & 1ull), w1 = c > 0 && !((n1 >> 16) & 1ull);
+                            bool w2 = c < CT - 1 && !((n2 >> 16) & 1ull), w3 = r < CT - 1 && !((n3 >> 16) & 1ull);
+                            const bool go = step < CHASE && (ahead == 0 ? w0 : (ahead == 1 ? w1 : (ahead == 2 ? w2 : w3)));
+                            if (go) {
+                                if (ahead == 0) w0 = false; else if (ahead == 1) w1 = false; else if (ahead == 2) w2 = false; else w3 = false;
+                            }
+                            const int i0 = idx - CT, i1 = idx - 1, i2 = idx + 1, i3 = idx + CT;
+                            unsigned o0 = ~0u, o1 = ~0u, o2 = ~0u, o3 = ~0u;
+                            if (w0) o0 = atomicOr(&wflag[i0 >> 5], 1u << (i0 & 31)) & (1u << (i0 & 31));
+                            if (w1) o1 = atomicOr(&wflag[i1 >> 5], 1u << (i1 & 31)) & (1u << (i1 & 31));
+                            if (w2) o2 = atomicOr(&wflag[i2 >> 5], 1u << (i2 & 31)) & (1u << (i2 & 31));
+                            if (w3) o3 = atomicOr(&wflag[i3 >> 5], 1u << (i3 & 31)) & (1u << (i3 & 31));
+                            const int cnt = (o0 == 0) + (o1 == 0) + (o2 == 0) + (o3 == 0);
+                            if (cnt) {
+                                // every reserved slot below LQ is written by its owner; slots beyond are dropped and the
+                                // tile gets a full block-wide visit next sweep
+                                int pos = atomicAdd(&wc[qc ^ 1], cnt);
+                                if (pos + cnt > LQ) wc[3] = 1;
+                                if (o0 == 0) { if (pos < LQ) qout[pos] = static_cast<unsigned short>(i0); ++pos; }
+                                if (o1 == 0) { if (pos < LQ) qout[pos] = static_cast<unsigned short>(i1); ++pos; }
+                                if (o2 == 0) { if (pos < LQ) qout[pos] = static_cast<unsigned short>(i2); ++pos; }
+                                if (o3 == 0) { if (pos < LQ) qout[pos] = static_cast<unsigned short>(i3); ++pos; }
+                            }
+                            const unsigned eb = (r == 0 ? EDGE_TOP : 0u) | (r == CT - 1 ? EDGE_BOTTOM : 0u) | (c == 0 ? EDGE_LEFT : 0u) |
+                                                (c == CT - 1 ? EDGE_RIGHT : 0u);
+                            if (eb) atomicOr(reinterpret_cast<unsigned *>(&wc[2]), eb);
+                            if (!go) break;
+                            idx = ahead == 0 ? i0 : (ahead == 1 ? i1 : (ahead == 2 ? i2 : i3));
+                        }
+                    }
+                    __syncwarp();
+                    if (lane == 0) {
+                        // entries beyond the queue were dropped (flagged): clamp so the next round reads valid slots only
+                        if (*reinterpret_cast<volatile int *>(&wc[qc ^ 1]) > LQ) wc[qc ^ 1] = LQ;
+                        wc[qc] = 0;
+                    }
+                    qc ^= 1;
+                    __syncwarp();
+                }
+                if (lane == 0) {
+                    const unsigned res = (static_cast<unsigned>(wc[2]) & 0xFu) | (wc[3] ? EDGE_DIRTY : 0u);
+                    cur[tile] = static_cast<uint8_t>(res);
+                    if (res) *reinterpret_cast<volatile int *>(&sList[FL_LIST_MAX]) = 1;
+                }
+            }
+            __syncthreads();
+            if (*reinterpret_cast<volatile int *>(&sList[FL_LIST_MAX]) != 0) block_changed = true;
         }
         if (block_changed && threadIdx.x == 0) p.st->changed[sweep % 3] = 1;
         __threadfence();

@@ -22,6 +22,65 @@ ACT_NONE, ACT_RELU, ACT_MISH = 0, 1, 4
 _LOSS_KINDS = {'smooth_l1': 0, 'l1': 1, 'l2': 2}      # get_loss(loss_function, 'distance'), losses.py:24-35
 
 
+class GradBuckets:
+    """Flat fp32 gradient buffer laid out in the order the backward pass PRODUCES the gradients, cut into buckets of
+    about ``bucket_bytes`` (~25 MB).  ``views[p]`` is the slice a parameter's gradient lives in (the
+    kernels write there directly, so there is no flatten / unflatten copy); bucket k can be all-reduced as soon as the
+    parameter ``closing[k]`` has its gradient, while the backward pass carries on with the earlier layers."""
+
+    def __init__(self, params_in_order, device, bucket_bytes=25 << 20):
+        self.params = list(params_in_order)
+        total = sum(p.numel() for p in self.params)
+        self.flat = torch.zeros(total, dtype=torch.float32, device=device)
+        self.views, self.closing, self.ranges = {}, {}, []
+        off = start = acc = 0
+        for p in self.params:
+            n = p.numel()
+            self.views[p] = self.flat[off:off + n].view(p.shape)
+            off += n
+            acc += 4 * n
+            if acc >= bucket_bytes:
+                self.closing[p] = len(self.ranges)
+                self.ranges.append((start, off))
+                start, acc = off, 0
+        if start < total:
+            self.closing[self.params[-1]] = len(self.ranges)
+            self.ranges.append((start, total))
+        self._works = []
+        self._comm = None
+
+    def allreduce(self, k, world_size):
+        """asynchronous mean over the ranks of bucket k, on a side stream that waits for the work enqueued so far"""
+        import torch.distributed as dist
+        s, e = self.ranges[k]
+        buf = self.flat[s:e]
+        if buf.is_cuda:
+            cur = torch.cuda.current_stream(buf.device)
+            if self._comm is None:
+                self._comm = torch.cuda.Stream(buf.device)
+            ev = torch.cuda.Event()
+            ev.record(cur)
+            with torch.cuda.stream(self._comm):
+                self._comm.wait_event(ev)
+                if dist.get_backend() == "nccl":
+                    w = dist.all_reduce(buf, op=dist.ReduceOp.AVG, async_op=True)
+                    self._works.append((w, None))
+                else:
+                    w = dist.all_reduce(buf, op=dist.ReduceOp.SUM, async_op=True)
+                    self._works.append((w, (buf, world_size)))
+        else:                                   # CPU tensors (gloo): tests of the host logic
+            w = dist.all_reduce(buf, op=dist.ReduceOp.SUM, async_op=True)
+            self._works.append((w, (buf, world_size)))
+
+    def finish(self):
+        """the current stream waits for every outstanding bucket (no host synchronisation on CUDA)"""
+        for w, post in self._works:
+            w.wait()
+            if post is not None:
+                post[0].div_(post[1])
+        self._works = []
+
+
 class _Layer:
     __slots__ = ("name", "kind", "conv", "bn", "act", "srcs", "a", "y", "mean", "invstd", "geom", "x_f32")
 
@@ -58,6 +117,10 @@ class TrainEngine:
         self._scratch = torch.empty(int(self.L.mbs_bn_scratch_floats(2048)), dtype=torch.float32, device=self.dev)
         self.use_graph = use_graph
         self._graphs = {}
+        # gradient buckets (built after the first step has shown the production order) and the data-parallel exchange
+        self._order, self._buckets = [], None
+        self.world_size = 1
+        self._capture = None
 
     # ---- small helpers ------------------------------------------------------------------------
     def _ones(self, c):
@@ -74,6 +137,42 @@ class TrainEngine:
 
     def _sp(self):
         return nat.stream_ptr()
+
+    # ---- gradient placement / data-parallel exchange ---------------------------------------------
+    def _grad_buf(self, param):
+        """where the kernel that produces ``param``'s gradient writes it: its slice of the flat bucket buffer"""
+        if self._buckets is not None:
+            return self._buckets.views[param]
+        return torch.empty(param.shape, dtype=torch.float32, device=self.dev)
+
+    def _set_grad(self, param, tensor):
+        if self._buckets is None:                       # first (eager) step: remember the production order
+            param.grad = tensor if tuple(tensor.shape) == tuple(param.shape) else tensor.reshape(param.shape)
+            self._order.append(param)
+            return
+        view = self._buckets.views[param]
+        if tensor.data_ptr() != view.data_ptr():
+            view.copy_(tensor.reshape(view.shape))
+        param.grad = view
+        k = self._buckets.closing.get(param)
+        if k is not None:
+            self._boundary(k)
+
+    def _boundary(self, k):
+        """bucket k is complete.  While capturing: close the current CUDA graph and open the next one (the all-reduce
+        is launched between the graph replays, never captured); otherwise launch the bucket's all-reduce now."""
+        cap = self._capture
+        if cap is not None:
+            cap["cur"].capture_end()
+            cap["graphs"].append((cap["cur"], k))
+            cap["cur"] = torch.cuda.CUDAGraph()
+            cap["cur"].capture_begin(pool=cap["pool"])
+        elif self.world_size > 1:
+            self._buckets.allreduce(k, self.world_size)
+
+    def finish_allreduce(self):
+        if self._buckets is not None:
+            self._buckets.finish()
 
     def _pack3x3(self, w):
         cout, cin = w.shape[0], w.shape[1]
@@ -168,41 +267,62 @@ class TrainEngine:
         self.tape.append(lay)
         return lay
 
-    def forward_backward(self, img, border_label, cell_label):
+    def forward_backward(self, img, border_label, cell_label, world_size=1):
         """img / labels: [N,1,H,W] float32 CUDA tensors (img normalised to [-1,1] as the reference's ToTensor does).
         Returns the loss (0-d tensor) and leaves the gradients in ``param.grad``.
 
-        With ``use_graph`` (default) the first call of a given batch shape runs eagerly (it also warms up every kernel
-        configuration), the second call captures the whole step -- ~600 kernel launches plus the torch glue -- into ONE
-        CUDA graph, and later calls only copy the batch into the static inputs and replay it."""
+        The first call of a given batch shape runs eagerly (it warms up every kernel configuration and records the
+        order in which the backward pass produces the gradients); gradients then live in one flat buffer cut into
+        ~25 MB buckets.  With ``use_graph`` the second call captures the step -- ~600 kernel launches plus the torch
+        glue -- into one CUDA graph PER BUCKET, and later calls replay them; with ``world_size`` > 1 the all-reduce of
+        bucket k is launched (on a side stream) right after graph k, so it overlaps the rest of the backward pass.
+        Call ``finish_allreduce()`` (``train_step`` does) before the optimizer reads the gradients."""
         nat.note_raw_write()        # BatchNorm running statistics are updated through raw pointers
-        if not self.use_graph:
-            return self._forward_backward(img, border_label, cell_label)
-        # the captured graph bakes in parameter / buffer storage and the loss kind: re-capture when any of them moves
+        self.world_size = int(world_size)
+        first = self._buckets is None
+        if first or not self.use_graph:
+            loss = self._forward_backward(img, border_label, cell_label)
+            if first:
+                self._buckets = GradBuckets(self._order, self.dev)
+                if self.world_size > 1:                 # this one step: gradients are not in the flat buffer yet
+                    allreduce_gradients(self.net, self.world_size)
+            return loss
+        # the captured graphs bake in parameter / buffer storage and the loss kind: re-capture when any of them moves
         # (net.to(), load_state_dict(assign=True), p.data rebinding)
         key = (tuple(img.shape), img.dtype, self.loss_kind) + tuple(
             t.data_ptr() for t in list(self.net.parameters()) + list(self.net.buffers()))
         st = self._graphs.get(key)
-        if st is None:                                   # eager warm-up call
-            self._graphs[key] = {"calls": 1}
-            return self._forward_backward(img, border_label, cell_label)
-        if "graph" not in st:
-            st["in"] = [torch.empty_like(t, dtype=torch.float32) for t in (img, border_label, cell_label)]
+        if st is None:
+            st = {"in": [torch.empty_like(t, dtype=torch.float32) for t in (img, border_label, cell_label)]}
             for d, s_ in zip(st["in"], (img, border_label, cell_label)):
                 d.copy_(s_)
             torch.cuda.synchronize(self.dev)
-            g = torch.cuda.CUDAGraph()
             self.L.mbs_launch_count(1)
-            with torch.cuda.graph(g):
-                st["loss"] = self._forward_backward(*st["in"])
-            st["graph"] = g
-            st["launches"] = int(self.L.mbs_launch_count(0))     # kernels of this library inside one replay
-            # the capture does not execute the step; the gradient tensors it created are re-attached after every
-            # replay (optimizer.zero_grad(set_to_none=True) detaches them)
-            st["grads"] = [(p, p.grad) for p in self.net.parameters()]
+            side = torch.cuda.Stream(self.dev)
+            side.wait_stream(torch.cuda.current_stream(self.dev))
+            cap = {"graphs": [], "pool": torch.cuda.graph_pool_handle(), "cur": torch.cuda.CUDAGraph()}
+            with torch.cuda.stream(side):
+                cap["cur"].capture_begin(pool=cap["pool"])
+                self._capture = cap
+                try:
+                    st["loss"] = self._forward_backward(*st["in"])
+                finally:
+                    self._capture = None
+                    cap["cur"].capture_end()
+                cap["graphs"].append((cap["cur"], None))
+            torch.cuda.current_stream(self.dev).wait_stream(side)
+            st["graphs"] = cap["graphs"]
+            st["launches"] = int(self.L.mbs_launch_count(0))     # kernels of this library inside one replay of all graphs
+            # the capture does not execute the step; the gradient views are re-attached after every replay
+            # (optimizer.zero_grad(set_to_none=True) detaches them)
+            st["grads"] = [(p, self._buckets.views[p]) for p in self.net.parameters()]
+            self._graphs = {key: st}                             # one live capture (its private pool holds every activation)
         for d, s_ in zip(st["in"], (img, border_label, cell_label)):
             d.copy_(s_)
-        st["graph"].replay()
+        for g, k in st["graphs"]:
+            g.replay()
+            if k is not None and self.world_size > 1:
+                self._buckets.allreduce(k, self.world_size)
         for p, gr in st["grads"]:
             p.grad = gr
         self.launches_last_step = st["launches"]
@@ -277,8 +397,8 @@ class TrainEngine:
                 dwdb = torch.empty(c0 + 1, dtype=torch.float32, device=self.dev)
                 nat.check(self.L.mbs_head_bwd(gpred[di].data_ptr(), y_last.data_ptr(), n * H * W, c0, hw.data_ptr(),
                                               dy.data_ptr(), dwdb.data_ptr(), self._sp()), "head_bwd")
-                head.weight.grad = dwdb[:c0].reshape(head.weight.shape).clone()
-                head.bias.grad = dwdb[c0:].clone()
+                self._set_grad(head.weight, dwdb[:c0])
+                self._set_grad(head.bias, dwdb[c0:])
                 for (lu, la, lb, l) in reversed(dec[name]):
                     dy = self._bwd_conv(lb, dy)[0]
                     dup, dskip = self._bwd_conv(la, dy)
@@ -319,9 +439,9 @@ class TrainEngine:
         nat.check(self.L.mbs_bn_train_bwd(dy.data_ptr(), a.data_ptr(), m, c, lay.mean.data_ptr(), lay.invstd.data_ptr(),
                                           bn.weight.data_ptr(), lay.act, dz.data_ptr(), dgb.data_ptr(), dbias.data_ptr(),
                                           self._scratch.data_ptr(), self._sp()), "bn_train_bwd")
-        bn.weight.grad = dgb[:c].clone()
-        bn.bias.grad = dgb[c:].clone()
-        lay.conv.bias.grad = dbias
+        self._set_grad(bn.weight, dgb[:c])
+        self._set_grad(bn.bias, dgb[c:])
+        self._set_grad(lay.conv.bias, dbias)
         return dz
 
     def _bwd_conv(self, lay, dy):
@@ -338,9 +458,9 @@ class TrainEngine:
         for s, cs in zip(lay.srcs, cins):
             self._wgrad(1 if stride2 else 0, n, ho, wo, dz, cout, s, cs, dwp, cin, off)
             off += cs
-        dw = torch.empty((cout, cin, 3, 3), dtype=torch.float32, device=self.dev)
+        dw = self._grad_buf(conv.weight)
         nat.check(self.L.mbs_unpack_conv3x3_grad(dwp.data_ptr(), cout, cin, dw.data_ptr(), self._sp()), "unpack_grad")
-        conv.weight.grad = dw
+        self._set_grad(conv.weight, dw)
         # data gradient: full-resolution stride-1 conv with the flipped, transposed filter [Cin][9][Cout]
         packed = torch.empty((cin, 9, cout), dtype=torch.bfloat16, device=self.dev)
         nat.check(self.L.mbs_pack_conv3x3_dgrad(conv.weight.detach().float().contiguous().data_ptr(), cout, cin,
@@ -368,7 +488,7 @@ class TrainEngine:
         dw = torch.empty((c, 9), dtype=torch.float32, device=self.dev)
         nat.check(self.L.mbs_first_conv_wgrad(lay.x_f32.data_ptr(), dz.data_ptr(), n, h, w, c, dw.data_ptr(), self._sp()),
                   "first_conv_wgrad")
-        conv.weight.grad = dw.view(conv.weight.shape).clone()
+        self._set_grad(conv.weight, dw)
 
     def _bwd_up(self, lay, dy):
         """ConvTranspose2d(2,2) + BN (no activation): returns the gradient w.r.t. its input."""
@@ -379,7 +499,7 @@ class TrainEngine:
         cout = dup.shape[-1]
         g = torch.zeros((cout, 4, cin), dtype=torch.float32, device=self.dev)
         self._wgrad(2, n, h, w, dup, cout, x, cin, g, cin, 0)
-        conv.weight.grad = g.permute(2, 0, 1).reshape(cin, cout, 2, 2).contiguous()
+        self._set_grad(conv.weight, g.permute(2, 0, 1).reshape(cin, cout, 2, 2))
         # data gradient = 2x2 stride-2 convolution of d(up) with W[ci][co][q]
         packed = conv.weight.detach().float().permute(0, 2, 3, 1).reshape(cin, 4, cout).to(torch.bfloat16).contiguous()
         dx = torch.empty((n, h, w, cin), dtype=torch.bfloat16, device=self.dev)
@@ -408,7 +528,8 @@ def allreduce_gradients(net, world_size):
     return flat.numel()
 
 
-DDP_DESCRIPTION = "one flat NCCL all-reduce per step (mean over ranks)"
+DDP_DESCRIPTION = ("gradients in one flat buffer in backward order, ~25 MB buckets, NCCL all-reduce (AVG) of bucket k launched "
+                   "after CUDA graph k on a side stream: overlaps the rest of the backward pass")
 
 
 def broadcast_module_state(net, src=0):
@@ -424,8 +545,7 @@ def broadcast_module_state(net, src=0):
 def train_step(engine, optimizer, img, border_label, cell_label, world_size=1):
     """One optimisation step as in train.py:473-493 (zero_grad, forward, loss, backward, step)."""
     optimizer.zero_grad(set_to_none=True)
-    loss = engine.forward_backward(img, border_label, cell_label)
-    if world_size > 1:
-        allreduce_gradients(engine.net, world_size)
+    loss = engine.forward_backward(img, border_label, cell_label, world_size)
+    engine.finish_allreduce()
     optimizer.step()
     return loss

@@ -129,7 +129,8 @@ def bench_c5(dev, rank, world, peaks, steps=10, warmup=3, per_gpu_batch=8, size=
     import torch
     import torch.distributed as dist
     from microbeseg_b200 import _native as nat, labels as lab, synthetic as sy
-    from microbeseg_b200.training import TrainEngine, broadcast_module_state, train_step
+    from microbeseg_b200.adam import Adam
+    from microbeseg_b200.training import DDP_DESCRIPTION, TrainEngine, broadcast_module_state, train_step
     from microbeseg_b200.unets import build_unet
     torch.manual_seed(0)
     with torch.enable_grad():
@@ -137,7 +138,7 @@ def bench_c5(dev, rank, world, peaks, steps=10, warmup=3, per_gpu_batch=8, size=
         if world > 1:                       # replicas start identical (rank 0's weights and BatchNorm buffers)
             broadcast_module_state(net)
         eng = TrainEngine(net)
-        opt = torch.optim.Adam(net.parameters(), lr=8e-4, betas=(0.9, 0.999), eps=1e-08, weight_decay=0, amsgrad=True)
+        opt = Adam(net.parameters(), lr=8e-4, betas=(0.9, 0.999), eps=1e-08, weight_decay=0, amsgrad=True)    # fused, one launch
         B, S = per_gpu_batch, size
         masks = np.stack([sy.synth_instance_mask(S, S, 40 + 5 * i, 320 + 100 * rank + i, (9.0, 16.0), (7.0, 12.0)).astype(np.uint16)
                           for i in range(B)])
@@ -224,9 +225,9 @@ def bench_c5(dev, rank, world, peaks, steps=10, warmup=3, per_gpu_batch=8, size=
     ach = FLOP_PER_PX_TRAIN * px / (ms / 1e3) / 1e12
     return {"metric": "training img/s", "value": world * B / (ms / 1e3), "unit": "img/s", "n_gpus": world, "ms_per_step": ms,
             "steps": steps, "warmup": warmup, "dtype": "bf16 activations / gradients, fp32 accumulation and master weights",
-            "workload": f"config 5: DUNet[64,1024] training step (forward, SmoothL1 x2, backward, Adam amsgrad), {S}x{S} crops, "
+            "workload": f"config 5: DUNet[64,1024] training step (forward, SmoothL1 x2, backward, fused Adam amsgrad), {S}x{S} crops, "
                         f"{B} per GPU, global batch {world * B}",
-            "parallelism": f"dp{world}: bucketed NCCL gradient all-reduce overlapped with the backward pass" if world > 1 else "single GPU",
+            "parallelism": f"dp{world}: {DDP_DESCRIPTION}" if world > 1 else "single GPU",
             "loss_first_last": [losses[0], losses[-1]], "gpu_launches": launches,
             "e2e": {"value": world * B / (e2e_ms / 1e3), "unit": "img/s", "h2d_bytes_per_step": int(3 * B * S * S * 4),
                     "d2h_bytes_per_step": 4, "api": "microbeseg_b200.training.train_step (pinned host batch in, loss out)"},

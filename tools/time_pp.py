@@ -25,15 +25,17 @@ def timeit(b, c, out, reps=20):
 def flood_profile():
     """per-sweep instrumentation written by flood_kernel into the Stats block at the head of the workspace"""
     ws = max(pp._WS.values(), key=lambda t: t.numel())
-    raw = ws[:464].cpu().numpy()
+    raw = ws[:848].cpu().numpy()
+    rounds, maxr, items = (raw[464 + 128 * k:592 + 128 * k].view(np.uint32) for k in range(3))
     tiles = raw[44:172].view(np.uint32)
     t = raw[176:464].view(np.uint64).astype(np.int64)
     sweeps = int(raw[32:36].view(np.uint32)[0])
     out = []
     for k in range(min(sweeps, 33)):
-        out.append((int(tiles[k]) if k < 32 else -1, round((t[k + 1] - t[k]) / 1e3, 1)))
-    fin = round((t[35] - t[min(sweeps, 34)]) / 1e3, 1)
-    return f"sweeps (tiles visited, us): {out}, final phase {fin} us, flood total {round((t[35] - t[0]) / 1e3, 1)} us"
+        out.append((int(tiles[k]) if k < 32 else -1, round(float(t[k + 1] - t[k]) / 1e3, 1),
+                    f"rounds avg {rounds[k] / max(tiles[k], 1):.1f} max {maxr[k]}, items/tile {items[k] / max(tiles[k], 1):.0f}" if k < 32 else ""))
+    fin = round(float(t[35] - t[min(sweeps, 34)]) / 1e3, 1)
+    return f"sweeps (tiles visited, us): {out}, final phase {fin} us, flood total {round(float(t[35] - t[0]) / 1e3, 1)} us"
 
 
 tag = "legacy" if os.environ.get("MBS_PP_LEGACY") == "1" else "tiled"
