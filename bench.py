@@ -339,6 +339,26 @@ def main():
         sys.path.insert(0, os.path.join(ROOT, "tools"))
         import bench_parts as parts
         torch.cuda.empty_cache()
+        if world > 1:
+            # the product's multi-GPU entry (what infer_script_local.py runs under torchrun): ONE 200-frame stack, frames
+            # sharded t -> rank t mod world, masks gathered on rank 0 through shared memory; strong scaling incl. the gather
+            stack200 = np.ascontiguousarray(base[np.arange(200) % distinct])
+            inference.segment_stack_sharded(net, stack200[:2 * world], ths=(th_cell, th_seed), device=device)
+            barrier()
+            t0 = time.perf_counter()
+            res200 = inference.segment_stack_sharded(net, stack200, ths=(th_cell, th_seed), device=device)
+            torch.cuda.synchronize()
+            dt = torch.tensor([time.perf_counter() - t0], device=device)
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+            if rank == 0:
+                extras["stack200_sharded"] = {
+                    "metric": "end-to-end segmentation Mpx/s", "value": 200 * size * size / 1e6 / float(dt.item()), "unit": "Mpx/s",
+                    "seconds": float(dt.item()), "scaling": "strong",
+                    "workload": f"one 200-frame {size}x{size} stack through microbeseg_b200.inference.segment_stack_sharded: frame t -> "
+                                f"rank t mod {world}, pinned H2D / D2H per frame, masks gathered on rank 0 via /dev/shm (host wall "
+                                "clock, max over ranks)",
+                    "objects_first_frame": int(res200[0].max())}
+            del stack200, res200
         rec = parts.bench_c5(device, rank, world, peaks, steps=10, warmup=3, torch_baseline=(world == 1))
         if rank == 0:
             extras["train"] = rec

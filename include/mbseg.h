@@ -234,6 +234,18 @@ int mbs_distance_labels(const uint16_t *masks, int n_crops, int H, int W, int ma
                         int radius_hint, float *cell_dist, float *neighbor_dist, int32_t *max_mal_out,
                         int32_t *error_out, void *workspace, size_t workspace_bytes, void *stream);
 
+/*
+ * Threshold sweep of the evaluation (src/evaluation/eval.py:128-129, 395-412: one prediction post-processed for every
+ * pair of product(th_cell, th_seed)).  Smoothing, seed image, 8-connected labelling and the area filter depend on
+ * th_seed only and run once per seed threshold; each cell threshold then costs one watershed.
+ * th_*_host: HOST float arrays; out: uint16 [n_seed][n_cell][H][W], each plane identical to
+ * mbs_distance_postprocessing(.., th_seeds[is], th_cells[ic], ..); info_host (optional): int64 [n_seed*n_cell*8].
+ * Workspace: mbs_postproc_workspace_bytes(H, W).
+ */
+int mbs_distance_postprocessing_sweep(const float *border, const float *cell, int H, int W, int ld, const float *th_seeds_host,
+                                      int n_seed, const float *th_cells_host, int n_cell, uint16_t *out, void *workspace,
+                                      size_t workspace_bytes, int64_t *info_host, void *stream);
+
 /* ---------------------------------------------------------------------------------------- */
 /* mask -> polygon ROI encoding                                           */
 /* ---------------------------------------------------------------------------------------- */

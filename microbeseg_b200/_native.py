@@ -68,6 +68,8 @@ _SIGS = {
     "mbs_postproc_workspace_bytes": (c_size_t, [c_int, c_int]),
     "mbs_distance_postprocessing": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_float, c_void_p,
                                             c_void_p, c_size_t, c_void_p, c_void_p]),
+    "mbs_distance_postprocessing_sweep": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p,
+                                                  c_void_p, c_size_t, c_void_p, c_void_p]),
     "mbs_boundary_postprocessing": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_size_t, c_void_p, c_void_p]),
     "mbs_pp_front": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_float, c_void_p, c_void_p, c_void_p,
                              c_void_p]),

@@ -224,6 +224,7 @@ struct Stats {
     unsigned int dbg_rounds[32];    // sum over the visited tiles of the number of event rounds, per sweep
     unsigned int dbg_maxrounds[32];
     unsigned int dbg_items[32];     // queue entries processed, per sweep
+    unsigned long long dbg_phase[5]; // block-wide visits in sweeps >= 3: clocks in load / queue build / rounds / store, count
 };
 
 // path compression + component areas + component / pixel counts in one pass
@@ -822,16 +823,30 @@ front_ccl_kernel(const float *__restrict__ border, const float *__restrict__ cel
                 const float sq = __fmul_rn(b, b);
                 // float32(tan_f64(x)); tan is increasing on [0,1] and tan(0.0499) = 0.04994 < 0.05, so
                 // every sq below 0.0499 lands in the `borders < 0.05 -> 0` branch without evaluating tan
-                float t = 0.0f;
-                if (!(sq < 0.0499f)) {
-                    t = static_cast<float>(tan(static_cast<double>(sq)));
-                    if (t < 0.05f) t = 0.0f;
-                    t = t < 0.0f ? 0.0f : (t > 1.0f ? 1.0f : t);
-                }
-                const float cleaned = __fsub_rn(cs, t);
                 cell_s[o] = cs;
                 mk = cs > th_cell;
-                sd = cleaned > th_seed;
+                if (sq < 0.0499f) {
+                    sd = cs > th_seed;                                          // borders == 0: cleaned = cs - 0
+                } else {
+                    // Only the DECISION (cs - borders) > th_seed is needed, not the value of tan.  tanf is within 4 ulp
+                    // (< 6e-7 on [0, 1.56]) of the exact tangent and so is float32(tan_f64); if the float32 estimate keeps
+                    // the three comparisons that use it (borders < 0.05, borders > 1, cleaned > th_seed) at least 1e-5
+                    // away from their thresholds, the exact evaluation cannot decide differently.  Otherwise (about one
+                    // pixel in 10^4) the float64 tangent is evaluated as before.  (The double-precision tan costs ~150
+                    // FP64 instructions per warp and was half of this kernel's time.)
+                    const float tf = tanf(sq);
+                    const float te = tf > 1.0f ? 1.0f : tf;
+                    const bool sure = fabsf(tf - 0.05f) > 1e-5f && fabsf(tf - 1.0f) > 1e-5f && fabsf((cs - te) - th_seed) > 1e-5f &&
+                                      tf >= 0.05f;
+                    if (sure) {
+                        sd = (cs - te) > th_seed;
+                    } else {
+                        float t = static_cast<float>(tan(static_cast<double>(sq)));
+                        if (t < 0.05f) t = 0.0f;
+                        t = t < 0.0f ? 0.0f : (t > 1.0f ? 1.0f : t);
+                        sd = __fsub_rn(cs, t) > th_seed;
+                    }
+                }
             }
         }
         sdbits |= (sd ? 1u : 0u) << k;
@@ -1120,6 +1135,11 @@ struct FloodParams {
     int negate;
     const uint16_t *L16;             // fused mode: seeds / mask / local roots from front_ccl_kernel
     const int *marker_at_root;       // fused mode: marker id of every tile-local root (mid_kernel phase 4)
+    int light_init_max, light_items_max;   // a warp-level revisit is abandoned (and finished block-wide) beyond these sizes
+    int light_min_tiles;                   // warp-level revisits only if the block has at least this many tiles to revisit
+    int chase_heavy, chase_light;          // pixels a thread follows straight ahead per queue entry (block-wide / warp-level visit)
+    float th_mask;                   // threshold sweeps: mask = img > th_mask instead of the mask bit stored by the front end
+    int use_th_mask;
     unsigned long long *state;
     int *lab32;                      // LAB32 only
     int H, W;
@@ -1138,7 +1158,7 @@ constexpr int FL_STATE_BYTES = (CT + 2) * (CT + 2) * 8;
 constexpr int FL_V_BYTES = CT * CT * 4;
 constexpr int FL_Q_BYTES = 2 * CT * CT * 2;
 constexpr int FL_FLAG_BYTES = (CT * CT / 32) * 4;
-constexpr int FL_MISC_BYTES = 64 + 4 * FL_LIST_MAX + 16;       // queue sizes / edge bits / flags, list of light revisits
+constexpr int FL_MISC_BYTES = 64 + 2 * (4 * FL_LIST_MAX + 16);       // queue sizes / edge bits / flags, list of light revisits
 constexpr int FL_LAB_BYTES = (CT + 2) * (CT + 2) * 4;
 constexpr int FLOOD_SMEM16 = FL_STATE_BYTES + FL_V_BYTES + FL_Q_BYTES + FL_FLAG_BYTES + FL_MISC_BYTES;
 constexpr int FLOOD_SMEM32 = FLOOD_SMEM16 + FL_LAB_BYTES;
@@ -1162,6 +1182,7 @@ flood_kernel(const FloodParams p) {
     int *sMisc = reinterpret_cast<int *>(smem + FL_STATE_BYTES + FL_V_BYTES + FL_Q_BYTES + FL_FLAG_BYTES);   // [0],[1]: queue sizes, [2]: edge bits, [3]: any change
     int(*sLab)[CT + 2] = reinterpret_cast<int(*)[CT + 2]>(smem + FLOOD_SMEM16);
     int *sList = sMisc + 16;                     // [0, FL_LIST_MAX): tiles deferred to a warp-level revisit, [FL_LIST_MAX]: "one of them changed"
+    int *sAbort = sList + FL_LIST_MAX + 4;       // [0, FL_LIST_MAX): abandoned light revisits, [FL_LIST_MAX]: their count
     const int H = p.H, W = p.W;
     const int tiles_x = (W + CT - 1) / CT, tiles_y = (H + CT - 1) / CT;
     const int ntiles = tiles_x * tiles_y;
@@ -1193,39 +1214,18 @@ flood_kernel(const FloodParams p) {
             if (LAB32) sLab[r][c] = in ? p.lab32[static_cast<size_t>(y) * W + x] : 0;
         }
     };
-    stamp(0);
-    for (;;) {
-        const uint8_t *prev = p.tile_changed + ((sweep + 1) & 1) * ntiles;
-        uint8_t *cur = p.tile_changed + (sweep & 1) * ntiles;
-        bool block_changed = false;
-        if (threadIdx.x == 0) sList[FL_LIST_MAX] = 0;
-        int n_light = 0;                              // uniform across the block
-        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    // ---- block-wide visit of one tile: stage it in shared memory, relax to the local fixed point, write it back
+    long long ph[5] = {0, 0, 0, 0, 0};          // clock64 spent in load / queue build / rounds / store, visits (sweeps >= 3)
+    const uint8_t *prev = nullptr;
+    uint8_t *cur = nullptr;
+    bool block_changed = false;
+    auto heavy_visit = [&](const int tile, const bool full_scan, const unsigned extra_edges) {
             const int tyi = tile / tiles_x, txi = tile - tyi * tiles_x;
-            bool full_scan = sweep == 0;
-            if (sweep > 0) {
-                // a tile is revisited only if a neighbour changed pixels on the edge that faces it ...
-                const bool need = (txi > 0 && (prev[tile - 1] & EDGE_RIGHT)) || (txi + 1 < tiles_x && (prev[tile + 1] & EDGE_LEFT)) ||
-                                  (tyi > 0 && (prev[tile - tiles_x] & EDGE_BOTTOM)) || (tyi + 1 < tiles_y && (prev[tile + tiles_x] & EDGE_TOP));
-                // ... or if its own light revisit overflowed in the previous sweep
-                const bool dirty = (prev[tile] & EDGE_DIRTY) != 0;
-                if (!need && !dirty) {
-                    if (threadIdx.x == 0) cur[tile] = 0;
-                    continue;
-                }
-                if (!LAB32 && !dirty && n_light < FL_LIST_MAX) {
-                    // a revisit changes a few dozen pixels next to an edge: one WARP handles it straight on the global
-                    // state (below) instead of the block staging the whole 48 KB tile in shared memory
-                    if (threadIdx.x == 0) sList[n_light] = tile;
-                    ++n_light;
-                    continue;
-                }
-                full_scan = dirty;
-            }
             const int x0 = txi * CT, y0 = tyi * CT;
             const bool fast = aligned && x0 + CT <= W && y0 + CT <= H && (W & 7) == 0;      // 16-byte rows, no ragged edge
             const size_t rowbase = static_cast<size_t>(y0 + row) * W + x0 + col0;
             __syncthreads();   // shared tile reuse
+            const long long tk0 = clock64();
             const bool fused_init = !LAB32 && sweep == 0;
             if (threadIdx.x == 0 && sweep < 32) atomicAdd(&p.st->dbg_tiles[sweep], 1u);
             if (threadIdx.x < CT * CT / 32) sFlag[threadIdx.x] = 0u;
@@ -1261,6 +1261,15 @@ flood_kernel(const FloodParams p) {
                         const bool in = y < H && x < W;
                         v16[i] = in ? p.L16[static_cast<size_t>(y) * W + x] : static_cast<unsigned short>(0);
                         v[i] = in ? p.img[static_cast<size_t>(y) * W + x] : 0.0f;
+                    }
+                }
+                if (p.use_th_mask) {
+                    // threshold sweep: one front end / labelling pass serves several cell thresholds (the seeds do not
+                    // depend on th_cell); mask = cell_s > th_cell is re-derived from the smoothed map
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        const bool in = y0 + row < H && x0 + col0 + i < W;
+                        v16[i] = static_cast<unsigned short>((v16[i] & ~L16_MASK) | ((in && v[i] > p.th_mask) ? L16_MASK : 0u));
                     }
                 }
                 int mk[16];
@@ -1320,6 +1329,7 @@ flood_kernel(const FloodParams p) {
                 }
             }
             __syncthreads();
+            const long long tk1 = clock64();
             // initial work list.  First visit: every floodable pixel next to a flooded one; later visits: the floodable
             // pixels on the tile edges next to a flooded halo pixel (the inside is already at its fixed point)
             const bool first_visit = full_scan;
@@ -1352,6 +1362,7 @@ flood_kernel(const FloodParams p) {
                 }
             }
             __syncthreads();
+            const long long tk2 = clock64();
             int qc = 0;
             unsigned n_rounds = 0, n_items = 0;
             for (;;) {
@@ -1368,7 +1379,7 @@ flood_kernel(const FloodParams p) {
                     // One queue entry = one evaluation plus a CHASE: while a pixel changes, the thread carries on with
                     // the neighbour straight ahead (away from the neighbour the new state came from), so a front crosses
                     // up to CHASE pixels per round along rows / columns instead of one.
-                    constexpr int CHASE = 12;
+                    const int CHASE = p.chase_heavy;
 #pragma unroll 1
                     for (int step = 0; step <= CHASE; ++step) {
                         const int r = (idx >> 6) + 1, c = (idx & (CT - 1)) + 1;
@@ -1437,6 +1448,7 @@ flood_kernel(const FloodParams p) {
                 qc ^= 1;
                 __syncthreads();
             }
+            const long long tk3 = clock64();
             if (threadIdx.x == 0 && sweep < 32) {
                 atomicAdd(&p.st->dbg_rounds[sweep], n_rounds);
                 atomicMax(&p.st->dbg_maxrounds[sweep], n_rounds);
@@ -1485,10 +1497,53 @@ flood_kernel(const FloodParams p) {
                 __syncthreads();
                 edge_bits = *reinterpret_cast<volatile unsigned *>(&sMisc[2]);
             }
+            edge_bits |= extra_edges;                 // changes an abandoned light revisit already made on the tile's edges
             if (threadIdx.x == 0) cur[tile] = static_cast<uint8_t>(edge_bits);
             block_changed |= edge_bits != 0;
+            if (sweep >= 3) {
+                const long long tk4 = clock64();
+                ph[0] += tk1 - tk0; ph[1] += tk2 - tk1; ph[2] += tk3 - tk2; ph[3] += tk4 - tk3; ph[4] += 1;
+            }
+    };
+    stamp(0);
+    for (;;) {
+        prev = p.tile_changed + ((sweep + 1) & 1) * ntiles;
+        cur = p.tile_changed + (sweep & 1) * ntiles;
+        block_changed = false;
+        if (threadIdx.x == 0) { sList[FL_LIST_MAX] = 0; sAbort[FL_LIST_MAX] = 0; }
+        int n_light = 0;                              // uniform across the block
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+            const int tyi = tile / tiles_x, txi = tile - tyi * tiles_x;
+            if (sweep == 0) {
+                heavy_visit(tile, true, 0u);
+                continue;
+            }
+            // a tile is revisited only if a neighbour changed pixels on the edge that faces it ...
+            const bool need = (txi > 0 && (prev[tile - 1] & EDGE_RIGHT)) || (txi + 1 < tiles_x && (prev[tile + 1] & EDGE_LEFT)) ||
+                              (tyi > 0 && (prev[tile - tiles_x] & EDGE_BOTTOM)) || (tyi + 1 < tiles_y && (prev[tile + tiles_x] & EDGE_TOP));
+            // ... or if its own light revisit ran out of queue space in the previous sweep
+            const bool dirty = (prev[tile] & EDGE_DIRTY) != 0;
+            if (!need && !dirty) {
+                if (threadIdx.x == 0) cur[tile] = 0;
+                continue;
+            }
+            if (!LAB32 && !dirty && n_light < FL_LIST_MAX) {
+                // a revisit usually changes a few dozen pixels next to an edge: one WARP handles it straight on the
+                // global state (below) instead of the block staging the whole 48 KB tile in shared memory
+                if (threadIdx.x == 0) sList[n_light] = tile;
+                ++n_light;
+                continue;
+            }
+            heavy_visit(tile, dirty, 0u);
+        }
+        if (n_light > 0 && n_light < p.light_min_tiles) {
+            // latency regime (the tail sweeps: a handful of tiles with long dependency chains): shared memory is faster
+            __syncthreads();
+            for (int li = 0; li < n_light; ++li) heavy_visit(sList[li], false, 0u);
+            n_light = 0;
         }
         if (n_light > 0) {
+            // throughput regime: many tiles with little work each, eight of them in flight per block
             __syncthreads();                          // the block-wide tile (if any) is done: its shared memory is free
             const int warp = threadIdx.x >> 5;
             unsigned char *wbase = smem + warp * LIGHT_WARP_BYTES;
@@ -1509,34 +1564,53 @@ flood_kernel(const FloodParams p) {
                 if (lane < 4) wc[lane] = 0;
                 __syncwarp();
                 if (lane == 0 && sweep < 32) atomicAdd(&p.st->dbg_tiles[sweep], 1u);
-                // work list: floodable edge pixels next to a flooded pixel of the neighbouring tile
-                for (int e = lane; e < 4 * CT; e += 32) {
-                    const int side = e >> 6, k = e & (CT - 1);
-                    const int r = side == 0 ? 0 : (side == 1 ? CT - 1 : k), c = side <= 1 ? k : (side == 2 ? 0 : CT - 1);
-                    const int hy = y0 + (side == 0 ? -1 : (side == 1 ? CT : k)), hx = x0 + (side <= 1 ? k : (side == 2 ? -1 : CT));
-                    const int y = y0 + r, x = x0 + c;
-                    if (y >= H || x >= W) continue;
-                    if ((gstate(y, x) >> 16) & 1ull) continue;
-                    if (static_cast<unsigned>(gstate(hy, hx) >> 32) >= ORD_INF) continue;
-                    const int idx = r * CT + c;
-                    const unsigned bit = 1u << (idx & 31);
-                    if (atomicOr(&wflag[idx >> 5], bit) & bit) continue;
-                    const int pos = atomicAdd(&wc[0], 1);
-                    if (pos < LQ) wq[pos] = static_cast<unsigned short>(idx); else wc[3] = 1;
+                // work list: floodable edge pixels next to a flooded pixel of the neighbouring tile (all sixteen loads of
+                // a lane are issued before the first one is used)
+                {
+                    unsigned long long own[8], halo[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const int e = lane + 32 * j;
+                        const int side = e >> 6, k = e & (CT - 1);
+                        const int r = side == 0 ? 0 : (side == 1 ? CT - 1 : k), c = side <= 1 ? k : (side == 2 ? 0 : CT - 1);
+                        const int hy = y0 + (side == 0 ? -1 : (side == 1 ? CT : k)), hx = x0 + (side <= 1 ? k : (side == 2 ? -1 : CT));
+                        own[j] = gstate(y0 + r, x0 + c);
+                        halo[j] = gstate(hy, hx);
+                    }
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const int e = lane + 32 * j;
+                        const int side = e >> 6, k = e & (CT - 1);
+                        const int r = side == 0 ? 0 : (side == 1 ? CT - 1 : k), c = side <= 1 ? k : (side == 2 ? 0 : CT - 1);
+                        if ((own[j] >> 16) & 1ull) continue;                       // marker, outside the mask or outside the image
+                        if (static_cast<unsigned>(halo[j] >> 32) >= ORD_INF) continue;
+                        const int idx = r * CT + c;
+                        const unsigned bit = 1u << (idx & 31);
+                        if (atomicOr(&wflag[idx >> 5], bit) & bit) continue;
+                        const int pos = atomicAdd(&wc[0], 1);
+                        if (pos < LQ) wq[pos] = static_cast<unsigned short>(idx); else wc[3] = 1;
+                    }
                 }
                 __syncwarp();
                 int qc = 0;
-                for (;;) {
+                int processed = 0;
+                bool abandon = *reinterpret_cast<volatile int *>(&wc[0]) > p.light_init_max;
+                for (; !abandon;) {
                     int n = *reinterpret_cast<volatile int *>(&wc[qc]);
                     if (n == 0) break;
                     if (n > LQ) n = LQ;
+                    processed += n;
+                    if (processed > p.light_items_max) {             // not a small revisit after all: finish it block-wide
+                        abandon = true;
+                        break;
+                    }
                     const unsigned short *qin = wq + qc * LQ;
                     unsigned short *qout = wq + (qc ^ 1) * LQ;
                     for (int i = lane; i < n; i += 32) {
                         int idx = qin[i];
                         atomicAnd(&wflag[idx >> 5], ~(1u << (idx & 31)));
                         __threadfence_block();
-                        constexpr int CHASE = 6;
+                        const int CHASE = p.chase_light;
 #pragma unroll 1
                         for (int step = 0; step <= CHASE; ++step) {
                             const int r = idx >> 6, c = idx & (CT - 1);
@@ -1604,13 +1678,25 @@ flood_kernel(const FloodParams p) {
                     __syncwarp();
                 }
                 if (lane == 0) {
-                    const unsigned res = (static_cast<unsigned>(wc[2]) & 0xFu) | (wc[3] ? EDGE_DIRTY : 0u);
-                    cur[tile] = static_cast<uint8_t>(res);
-                    if (res) *reinterpret_cast<volatile int *>(&sList[FL_LIST_MAX]) = 1;
+                    const unsigned edges = static_cast<unsigned>(*reinterpret_cast<volatile int *>(&wc[2])) & 0xFu;
+                    if (abandon || *reinterpret_cast<volatile int *>(&wc[3])) {
+                        // hand the tile to the block (this sweep): tile index + the edge bits already produced
+                        const int pos = atomicAdd(&sAbort[FL_LIST_MAX], 1);
+                        sAbort[pos] = tile | static_cast<int>(edges << 28);
+                    } else {
+                        cur[tile] = static_cast<uint8_t>(edges);
+                        if (edges) *reinterpret_cast<volatile int *>(&sList[FL_LIST_MAX]) = 1;
+                    }
                 }
             }
             __syncthreads();
             if (*reinterpret_cast<volatile int *>(&sList[FL_LIST_MAX]) != 0) block_changed = true;
+        }
+        {
+            // light revisits that turned out to be large were abandoned half way: finish them block-wide (full scan)
+            __syncthreads();
+            const int n_abort = *reinterpret_cast<volatile int *>(&sAbort[FL_LIST_MAX]);
+            for (int h = 0; h < n_abort; ++h) heavy_visit(sAbort[h] & 0x0FFFFFFF, true, static_cast<unsigned>(sAbort[h]) >> 28);
         }
         if (block_changed && threadIdx.x == 0) p.st->changed[sweep % 3] = 1;
         __threadfence();
@@ -1622,6 +1708,8 @@ flood_kernel(const FloodParams p) {
         if (!flag) break;
     }
     if (overflow) atomicExch(&p.st->overflow, 1u);
+    if (threadIdx.x == 0 && ph[4])
+        for (int k = 0; k < 5; ++k) atomicAdd(&p.st->dbg_phase[k], static_cast<unsigned long long>(ph[k]));
     if (blockIdx.x == 0 && threadIdx.x == 0) p.st->sweeps = static_cast<unsigned int>(sweep);
     // ---- final phase: labels out + order-independence check (see the file header)
     int bad_total = 0;
@@ -1688,13 +1776,14 @@ flood_kernel(const FloodParams p) {
 // exact fallback, part 1 (runs only when the tiled result is order dependent): explicit marker / mask images for
 // ws_sequential_kernel from the packed words of the tiled pipeline
 __global__ void expand_markers_kernel(const uint16_t *__restrict__ L16, const int *__restrict__ marker_at_root, int H, int W,
-                                      const Stats *st, int *__restrict__ markers, uint8_t *__restrict__ mask) {
+                                      const Stats *st, int *__restrict__ markers, uint8_t *__restrict__ mask,
+                                      const float *__restrict__ img, float th_mask, int use_th_mask) {
     if (st->ambiguous == 0 && st->overflow == 0) return;
     const long long n = static_cast<long long>(H) * W;
     for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n; i += static_cast<long long>(gridDim.x) * blockDim.x) {
         const int y = static_cast<int>(i / W), x = static_cast<int>(i - static_cast<long long>(y) * W);
         const unsigned v16 = L16[i];
-        const bool m = (v16 & L16_MASK) != 0;
+        const bool m = use_th_mask ? (img[i] > th_mask) : ((v16 & L16_MASK) != 0);
         mask[i] = m ? 1 : 0;
         markers[i] = (m && (v16 & L16_SEED)) ? marker_of(v16, y, x, W, marker_at_root) : 0;
     }
@@ -2070,6 +2159,21 @@ bool legacy_path() {        // MBS_PP_LEGACY=1: the round-1 streaming pipeline (
     return v == 1;
 }
 
+int light_limit(int which) {      // MBS_PP_LIGHT=init,items,chase_heavy,chase_light,min_tiles (A/B knob); 0,0 = no warp-level revisits
+    static int v[5] = {-1, -1, -1, -1, -1};
+    if (v[0] < 0) {
+        int a = 64, b = 256, c = 16, d = 8, m = 4;
+        const char *e = getenv("MBS_PP_LIGHT");
+        if (e) sscanf(e, "%d,%d,%d,%d,%d", &a, &b, &c, &d, &m);
+        v[1] = b;
+        v[2] = c;
+        v[3] = d;
+        v[4] = m;
+        v[0] = a;
+    }
+    return v[which];
+}
+
 struct TiledWs {
     Stats *st;
     float *cell_s;
@@ -2193,6 +2297,13 @@ int run_tiled(const float *a, const float *b, int H, int W, int ld, float th_see
         fp.negate = BOUNDARY ? 0 : 1;
         fp.L16 = t.L16;
         fp.marker_at_root = t.area;
+        fp.th_mask = 0.0f;
+        fp.use_th_mask = 0;
+        fp.light_init_max = light_limit(0);
+        fp.light_items_max = light_limit(1);
+        fp.chase_heavy = light_limit(2);
+        fp.chase_light = light_limit(3);
+        fp.light_min_tiles = light_limit(4);
         fp.state = t.state;
         fp.lab32 = nullptr;
         fp.H = H;
@@ -2210,7 +2321,7 @@ int run_tiled(const float *a, const float *b, int H, int W, int ld, float th_see
     // exact fallback (both kernels return immediately unless the flood flagged an order-dependent pixel)
     {
         const int want = mbs::cdiv(static_cast<int>(n), 256);
-        expand_markers_kernel<<<want < 1184 ? want : 1184, 256, 0, stream>>>(t.L16, t.area, H, W, t.st, t.markers, t.mask8);
+        expand_markers_kernel<<<want < 1184 ? want : 1184, 256, 0, stream>>>(t.L16, t.area, H, W, t.st, t.markers, t.mask8, t.cell_s, 0.0f, 0);
     }
     MBS_CHECK_LAUNCH();
     ws_sequential_kernel<<<1, 32, 0, stream>>>(t.cell_s, BOUNDARY ? 0 : 1, t.markers, t.mask8, H, W, t.lab, t.heap, t.st, 0, out);
@@ -2220,6 +2331,93 @@ int run_tiled(const float *a, const float *b, int H, int W, int ld, float th_see
 }
 
 }  // namespace
+
+namespace {
+__global__ void flood_reset_kernel(Stats *st) {
+    st->changed[0] = st->changed[1] = st->changed[2] = 0;
+    st->ambiguous = 0;
+    st->sweeps = 0;
+    st->overflow = 0;
+    for (int i = 0; i < 32; ++i) st->dbg_tiles[i] = st->dbg_rounds[i] = st->dbg_maxrounds[i] = st->dbg_items[i] = 0;
+}
+}  // namespace
+
+// Threshold sweep of the evaluation (src/evaluation/eval.py:128-129, 395-412): the reference post-processes ONE
+// prediction with every pair of product(th_cell, th_seed).  The smoothed map, the seed image, its labelling and the area
+// filter depend on th_seed only, so they run once per seed threshold; each cell threshold then costs one flood.
+extern "C" int mbs_distance_postprocessing_sweep(const float *border, const float *cell, int H, int W, int ld, const float *th_seeds_host,
+                                                 int n_seed, const float *th_cells_host, int n_cell, uint16_t *out, void *workspace,
+                                                 size_t workspace_bytes, int64_t *info_host, void *stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    const size_t n = static_cast<size_t>(H) * W;
+    MBS_REQUIRE(H > 0 && W > 0 && ld >= W && n < (1ull << 31) && n_seed > 0 && n_cell > 0 && th_seeds_host && th_cells_host,
+                "distance_postprocessing_sweep: bad arguments");
+    MBS_REQUIRE(workspace_bytes >= tiled_ws_bytes(n, H, W, false), "distance_postprocessing_sweep: workspace too small");
+    TiledWs t;
+    MBS_REQUIRE(carve_tiled(t, workspace, workspace_bytes, n, H, W, false), "distance_postprocessing_sweep: workspace carve failed");
+    CoopCfg *cfg = nullptr;
+    int rc = coop_config(&cfg);
+    if (rc) return rc;
+    dim3 tgrid(mbs::cdiv(W, CT), mbs::cdiv(H, CT));
+    const int ntiles = static_cast<int>(tgrid.x * tgrid.y);
+    for (int is = 0; is < n_seed; ++is) {
+        MBS_CHECK_CUDA(cudaMemsetAsync(t.st, 0, sizeof(Stats), stream));
+        front_ccl_kernel<false><<<tgrid, 256, 0, stream>>>(border, cell, H, W, ld, th_seeds_host[is], th_cells_host[0], t.cell_s, t.L16, t.G,
+                                                           t.area, t.list, t.list_cap, t.bitmap, t.st);
+        MBS_CHECK_LAUNCH();
+        {
+            const int use_mean = 1;
+            const uint16_t *L16 = t.L16;
+            const int *list = t.list;
+            void *args[] = {(void *)&L16, (void *)&H, (void *)&W, (void *)&t.G, (void *)&t.area, (void *)&list, (void *)&t.list_cap,
+                            (void *)&t.bitmap, (void *)&t.prefix, (void *)&t.block_sums, (void *)&t.st, (void *)&use_mean};
+            MBS_CHECK_CUDA(cudaLaunchCooperativeKernel((void *)mid_kernel, dim3(cfg->mid_blocks), dim3(256), args, 0, stream));
+            mbs::count_launch();
+        }
+        for (int ic = 0; ic < n_cell; ++ic) {
+            uint16_t *o = out + (static_cast<size_t>(is) * n_cell + ic) * n;
+            if (ic > 0) {
+                flood_reset_kernel<<<1, 1, 0, stream>>>(t.st);
+                MBS_CHECK_LAUNCH();
+            }
+            FloodParams fp;
+            fp.img = t.cell_s;
+            fp.negate = 1;
+            fp.L16 = t.L16;
+            fp.marker_at_root = t.area;
+            fp.th_mask = th_cells_host[ic];
+            fp.use_th_mask = 1;
+            fp.light_init_max = light_limit(0);
+            fp.light_items_max = light_limit(1);
+            fp.chase_heavy = light_limit(2);
+            fp.chase_light = light_limit(3);
+            fp.light_min_tiles = light_limit(4);
+            fp.state = t.state;
+            fp.lab32 = nullptr;
+            fp.H = H;
+            fp.W = W;
+            fp.st = t.st;
+            fp.tile_changed = t.tile_changed;
+            fp.out16 = o;
+            fp.out32 = nullptr;
+            const int blocks = ntiles < cfg->flood16_blocks ? ntiles : cfg->flood16_blocks;
+            void *args[] = {(void *)&fp};
+            MBS_CHECK_CUDA(cudaLaunchCooperativeKernel((void *)flood_kernel<false>, dim3(blocks), dim3(256), args, FLOOD_SMEM16, stream));
+            mbs::count_launch();
+            const int want = mbs::cdiv(static_cast<int>(n), 256);
+            expand_markers_kernel<<<want < 1184 ? want : 1184, 256, 0, stream>>>(t.L16, t.area, H, W, t.st, t.markers, t.mask8, t.cell_s,
+                                                                                th_cells_host[ic], 1);
+            MBS_CHECK_LAUNCH();
+            ws_sequential_kernel<<<1, 32, 0, stream>>>(t.cell_s, 1, t.markers, t.mask8, H, W, t.lab, t.heap, t.st, 0, o);
+            MBS_CHECK_LAUNCH();
+            if (info_host) {
+                rc = read_info(t, info_host + (static_cast<size_t>(is) * n_cell + ic) * 8, stream);
+                if (rc) return rc;
+            }
+        }
+    }
+    return 0;
+}
 
 extern "C" size_t mbs_postproc_workspace_bytes(int H, int W) {
     const size_t n = static_cast<size_t>(H) * W;
@@ -2285,6 +2483,13 @@ extern "C" int mbs_pp_watershed(const float *image, const int32_t *markers, cons
         fp.negate = 0;
         fp.L16 = nullptr;
         fp.marker_at_root = nullptr;
+        fp.th_mask = 0.0f;
+        fp.use_th_mask = 0;
+        fp.light_init_max = light_limit(0);
+        fp.light_items_max = light_limit(1);
+        fp.chase_heavy = light_limit(2);
+        fp.chase_light = light_limit(3);
+        fp.light_min_tiles = light_limit(4);
         fp.state = t.state;
         fp.lab32 = t.lab32;
         fp.H = H;

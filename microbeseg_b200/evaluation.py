@@ -32,18 +32,37 @@ def threshold_sweep(border, cell, ths=None):
     """border / cell: (H,W) or (H,W,1) float32 maps (NumPy or CUDA tensors, pads already cropped).
     Returns {(th_cell, th_seed): uint16 (H,W) NumPy mask}, each identical to
     ``distance_postprocessing(border, cell, th_seed=..., th_cell=...)`` (eval.py:401-404)."""
-    ths = default_thresholds() if ths is None else list(ths)
+    import ctypes
+    ths = default_thresholds() if ths is None else [tuple(t) for t in ths]
     dev = pp._device_of(border, cell)
     b = pp._as_device_map(border, dev)
     c = pp._as_device_map(cell, dev)
+    if b.stride(1) != 1 or c.stride(1) != 1 or b.stride(0) != c.stride(0):
+        b, c = b.contiguous(), c.contiguous()
+    H, W = c.shape
+    # the smoothed map, the seed labelling and the area filter depend on th_seed only: one front end per seed threshold,
+    # one flood per (seed, cell) pair (mbs_distance_postprocessing_sweep)
+    seeds = sorted({float(t[1]) for t in ths})
+    cells = sorted({float(t[0]) for t in ths})
+    L = nat.lib()
     outs = {}
     with torch.cuda.device(dev):
-        stage = torch.empty((len(ths),) + tuple(c.shape), dtype=torch.int16, device=dev)
-        for k, (th_cell, th_seed) in enumerate(ths):
-            pp.distance_postprocessing_device(b, c, th_seed, th_cell, out=stage[k])
-        host = stage.cpu().numpy().view(np.uint16)           # one read-back for the whole sweep
-    for k, th in enumerate(ths):
-        outs[tuple(th)] = host[k]
+        stage = torch.empty((len(seeds), len(cells), H, W), dtype=torch.int16, device=dev)
+        ws = pp._workspace(dev, int(L.mbs_postproc_workspace_bytes(H, W)))
+        a_s = (ctypes.c_float * len(seeds))(*seeds)
+        a_c = (ctypes.c_float * len(cells))(*cells)
+        nat.check(L.mbs_distance_postprocessing_sweep(b.data_ptr(), c.data_ptr(), H, W, c.stride(0) if H > 1 else W,
+                                                      ctypes.cast(a_s, ctypes.c_void_p), len(seeds), ctypes.cast(a_c, ctypes.c_void_p),
+                                                      len(cells), stage.data_ptr(), ws.data_ptr(), ws.numel(), None, nat.stream_ptr()),
+                  "distance_postprocessing_sweep")
+        want = sorted({(seeds.index(float(t[1])), cells.index(float(t[0]))) for t in ths})
+        if len(want) == len(seeds) * len(cells):
+            host = stage.cpu().numpy().view(np.uint16)           # one read-back for the whole sweep
+        else:
+            host = {k: stage[k[0], k[1]].cpu().numpy().view(np.uint16) for k in want}
+    for th in ths:
+        k = (seeds.index(float(th[1])), cells.index(float(th[0])))
+        outs[tuple(th)] = host[k[0], k[1]] if isinstance(host, np.ndarray) else host[k]
     return outs
 
 

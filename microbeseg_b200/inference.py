@@ -133,13 +133,18 @@ class FrameSegmenter:
         return st
 
     @staticmethod
-    def result(handle):
+    def result(handle, out=None):
+        """Mask of a submitted frame.  ``out``: caller-provided (H,W) uint16 array the mask is written into straight
+        from the pinned read-back buffer (one host copy instead of two); default: a fresh array."""
         handle["ev_out"].synchronize()
-        out = handle["pin_out"].numpy().view(np.uint16)
+        res = handle["pin_out"].numpy().view(np.uint16)
         v = handle.get("view")
         if isinstance(v, tuple):
-            out = out[v[0]:, v[1]:]
-        return out.copy()
+            res = res[v[0]:, v[1]:]
+        if out is None:
+            return res.copy()
+        np.copyto(out, res)
+        return out
 
     def segment(self, frame, min_val=None, max_val=None, crop=None):
         return self.result(self.submit(frame, 0, min_val, max_val, crop))
@@ -208,10 +213,10 @@ def segment_stack(net, stack, ths=(0.10, 0.45), device=None, frames=None, out=No
     for k, t in enumerate(todo):
         h = seg.submit(stack[t], slot=k & 1)
         if pending is not None:
-            out[pending[0]] = seg.result(pending[1])
+            seg.result(pending[1], out=out[pending[0]])
         pending = (t, h)
     if pending is not None:
-        out[pending[0]] = seg.result(pending[1])
+        seg.result(pending[1], out=out[pending[0]])
     return out
 
 

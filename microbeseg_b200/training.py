@@ -147,7 +147,7 @@ class TrainEngine:
 
     def _set_grad(self, param, tensor):
         if self._buckets is None:                       # first (eager) step: remember the production order
-            param.grad = tensor if tuple(tensor.shape) == tuple(param.shape) else tensor.reshape(param.shape)
+            param.grad = tensor.reshape(param.shape).contiguous()
             self._order.append(param)
             return
         view = self._buckets.views[param]

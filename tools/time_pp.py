@@ -25,7 +25,8 @@ def timeit(b, c, out, reps=20):
 def flood_profile():
     """per-sweep instrumentation written by flood_kernel into the Stats block at the head of the workspace"""
     ws = max(pp._WS.values(), key=lambda t: t.numel())
-    raw = ws[:848].cpu().numpy()
+    raw = ws[:888].cpu().numpy()
+    ph = raw[848:888].view(np.uint64).astype(np.float64)
     rounds, maxr, items = (raw[464 + 128 * k:592 + 128 * k].view(np.uint32) for k in range(3))
     tiles = raw[44:172].view(np.uint32)
     t = raw[176:464].view(np.uint64).astype(np.int64)
@@ -35,7 +36,11 @@ def flood_profile():
         out.append((int(tiles[k]) if k < 32 else -1, round(float(t[k + 1] - t[k]) / 1e3, 1),
                     f"rounds avg {rounds[k] / max(tiles[k], 1):.1f} max {maxr[k]}, items/tile {items[k] / max(tiles[k], 1):.0f}" if k < 32 else ""))
     fin = round(float(t[35] - t[min(sweeps, 34)]) / 1e3, 1)
-    return f"sweeps (tiles visited, us): {out}, final phase {fin} us, flood total {round(float(t[35] - t[0]) / 1e3, 1)} us"
+    phs = ""
+    if ph[4] > 0:
+        phs = (f", block-wide visits in sweeps>=3: {int(ph[4] / 256) if False else int(ph[4])} visits, kclk per visit load {ph[0] / ph[4] / 1e3:.1f} "
+               f"queue {ph[1] / ph[4] / 1e3:.1f} rounds {ph[2] / ph[4] / 1e3:.1f} store {ph[3] / ph[4] / 1e3:.1f}")
+    return f"sweeps (tiles visited, us): {out}{phs}, final phase {fin} us, flood total {round(float(t[35] - t[0]) / 1e3, 1)} us"
 
 
 tag = "legacy" if os.environ.get("MBS_PP_LEGACY") == "1" else "tiled"
