@@ -225,6 +225,11 @@ struct Stats {
     unsigned int dbg_maxrounds[32];
     unsigned int dbg_items[32];     // queue entries processed, per sweep
     unsigned long long dbg_phase[5]; // block-wide visits in sweeps >= 3: clocks in load / queue build / rounds / store, count
+    // exact fallback (tiled path)
+    unsigned int n_bad;             // order-dependent pixels recorded by the flood (entries of the bad-pixel list)
+    unsigned int need_global;       // a component could not be re-flooded on its own: whole-image sequential flood
+    unsigned int n_reflooded;       // mask components re-flooded on their own
+    unsigned int pool_top;          // heap pool allocator of the per-component floods
 };
 
 // path compression + component areas + component / pixel counts in one pass
@@ -722,7 +727,7 @@ __device__ __forceinline__ int l16_root_index(unsigned v16, int y, int x, int W)
 }
 
 template <bool BOUNDARY>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 5)
 front_ccl_kernel(const float *__restrict__ border, const float *__restrict__ cell, int H, int W, int ld, float th_seed,
                  float th_cell, float *__restrict__ cell_s, uint16_t *__restrict__ L16, int *G, int *area,
                  int *__restrict__ roots_list, int list_cap, unsigned *bitmap, Stats *st) {
@@ -879,11 +884,15 @@ front_ccl_kernel(const float *__restrict__ border, const float *__restrict__ cel
         return ones << start;
     };
     unsigned startbits = 0;               // pixel k is the first pixel of its run
+    unsigned char rs[16];                 // first column of pixel k's run
 #pragma unroll
     for (int k = 0; k < 16; ++k) {
+        rs[k] = 0;
         if (!((sdbits >> k) & 1u)) continue;
         const int r = k * 4 + rq;
-        if (run_start(row_mask(r), c) == c) {
+        const int st0 = run_start(row_mask(r), c);
+        rs[k] = static_cast<unsigned char>(st0);
+        if (st0 == c) {
             startbits |= 1u << k;
             s_uf[r * CT + c] = r * CT + c;
             s_cnt[r * CT + c] = 0;
@@ -923,7 +932,7 @@ front_ccl_kernel(const float *__restrict__ border, const float *__restrict__ cel
         const int y = y0 + r, x = x0 + c;
         const bool sd = (sdbits >> k) & 1u;
         int rt = 0;
-        if (sd) rt = uf_find_v(s_uf, r * CT + run_start(row_mask(r), c));
+        if (sd) rt = uf_find_v(s_uf, r * CT + rs[k]);
         const bool isroot = sd && rt == r * CT + c;
         if (y < H && x < W) {
             const unsigned v = ((mkbits >> k) & 1u ? L16_MASK : 0u) | (sd ? (L16_SEED | static_cast<unsigned>(rt)) : 0u);
@@ -1136,6 +1145,8 @@ struct FloodParams {
     const uint16_t *L16;             // fused mode: seeds / mask / local roots from front_ccl_kernel
     const int *marker_at_root;       // fused mode: marker id of every tile-local root (mid_kernel phase 4)
     int light_init_max, light_items_max;   // a warp-level revisit is abandoned (and finished block-wide) beyond these sizes
+    int *badlist;                          // fused mode: order-dependent pixels (exact fallback re-floods their mask components)
+    int bad_cap;
     int light_min_tiles;                   // warp-level revisits only if the block has at least this many tiles to revisit
     int chase_heavy, chase_light;          // pixels a thread follows straight ahead per queue entry (block-wide / warp-level visit)
     float th_mask;                   // threshold sweeps: mask = img > th_mask instead of the mask bit stored by the front end
@@ -1186,11 +1197,7 @@ flood_kernel(const FloodParams p) {
     const int H = p.H, W = p.W;
     const int tiles_x = (W + CT - 1) / CT, tiles_y = (H + CT - 1) / CT;
     const int ntiles = tiles_x * tiles_y;
-    const int row = threadIdx.x >> 2, col0 = (threadIdx.x & 3) * 16;      // this thread's 16 pixels
     const int lane = threadIdx.x & 31;
-    // 16-byte accesses need aligned bases (caller-provided outputs may be offset views)
-    const bool aligned = !LAB32 && ((reinterpret_cast<uintptr_t>(p.img) | reinterpret_cast<uintptr_t>(p.L16) |
-                                     reinterpret_cast<uintptr_t>(p.state) | reinterpret_cast<uintptr_t>(p.out16)) & 15) == 0;
     int sweep = 0;
     bool overflow = false;
     auto stamp = [&](int slot) {
@@ -1222,14 +1229,17 @@ flood_kernel(const FloodParams p) {
     auto heavy_visit = [&](const int tile, const bool full_scan, const unsigned extra_edges) {
             const int tyi = tile / tiles_x, txi = tile - tyi * tiles_x;
             const int x0 = txi * CT, y0 = tyi * CT;
-            const bool fast = aligned && x0 + CT <= W && y0 + CT <= H && (W & 7) == 0;      // 16-byte rows, no ragged edge
-            const size_t rowbase = static_cast<size_t>(y0 + row) * W + x0 + col0;
             __syncthreads();   // shared tile reuse
             const long long tk0 = clock64();
             const bool fused_init = !LAB32 && sweep == 0;
             if (threadIdx.x == 0 && sweep < 32) atomicAdd(&p.st->dbg_tiles[sweep], 1u);
             if (threadIdx.x < CT * CT / 32) sFlag[threadIdx.x] = 0u;
             if (threadIdx.x < 4) sMisc[threadIdx.x] = 0;
+            // thread t owns column t % 64 of rows k*4 + t/64 (k = 0..15): a warp touches 32 adjacent columns of one row, so
+            // global accesses are coalesced and shared-memory accesses conflict free; the sixteen loads of each array are
+            // independent and issued back to back
+            const int pc = threadIdx.x & (CT - 1), pr0 = threadIdx.x >> 6;
+            const int gx = x0 + pc;
             if (fused_init) {
                 // halo: the neighbouring tiles have no state yet; they are picked up in sweep 1
                 for (int i = threadIdx.x; i < 4 * (CT + 2); i += 256) {
@@ -1238,93 +1248,67 @@ flood_kernel(const FloodParams p) {
                     const int c = side <= 1 ? j : (side == 2 ? 0 : CT + 1);
                     sS[r][c] = ST_OUTSIDE;
                 }
-                unsigned short v16[16];
-                float v[16];
-                if (fast) {
-                    const uint4 *lp = reinterpret_cast<const uint4 *>(p.L16 + rowbase);
-                    const float4 *vp = reinterpret_cast<const float4 *>(p.img + rowbase);
-                    const uint4 l0 = lp[0], l1 = lp[1];
-                    const float4 f0 = vp[0], f1 = vp[1], f2 = vp[2], f3 = vp[3];
-                    const unsigned lw[8] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w};
+#pragma unroll 1
+                for (int h = 0; h < 2; ++h) {           // two batches of eight rows (register budget)
+                    unsigned short v16[8];
+                    float v[8];
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        v16[2 * i] = static_cast<unsigned short>(lw[i] & 0xFFFFu);
-                        v16[2 * i + 1] = static_cast<unsigned short>(lw[i] >> 16);
+                    for (int k = 0; k < 8; ++k) {
+                        const int y = y0 + (h * 8 + k) * 4 + pr0;
+                        const bool in = y < H && gx < W;
+                        v16[k] = in ? p.L16[static_cast<size_t>(y) * W + gx] : static_cast<unsigned short>(0);
+                        v[k] = in ? p.img[static_cast<size_t>(y) * W + gx] : 0.0f;
                     }
-                    const float fv[16] = {f0.x, f0.y, f0.z, f0.w, f1.x, f1.y, f1.z, f1.w, f2.x, f2.y, f2.z, f2.w, f3.x, f3.y, f3.z, f3.w};
+                    if (p.use_th_mask) {
+                        // threshold sweep: one front end / labelling pass serves several cell thresholds (the seeds do not
+                        // depend on th_cell); mask = cell_s > th_cell is re-derived from the smoothed map
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) v[i] = fv[i];
-                } else {
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        const int y = y0 + row, x = x0 + col0 + i;
-                        const bool in = y < H && x < W;
-                        v16[i] = in ? p.L16[static_cast<size_t>(y) * W + x] : static_cast<unsigned short>(0);
-                        v[i] = in ? p.img[static_cast<size_t>(y) * W + x] : 0.0f;
+                        for (int k = 0; k < 8; ++k) {
+                            const bool in = y0 + (h * 8 + k) * 4 + pr0 < H && gx < W;
+                            v16[k] = static_cast<unsigned short>((v16[k] & ~L16_MASK) | ((in && v[k] > p.th_mask) ? L16_MASK : 0u));
+                        }
                     }
-                }
-                if (p.use_th_mask) {
-                    // threshold sweep: one front end / labelling pass serves several cell thresholds (the seeds do not
-                    // depend on th_cell); mask = cell_s > th_cell is re-derived from the smoothed map
+                    int mk[8];
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        const bool in = y0 + row < H && x0 + col0 + i < W;
-                        v16[i] = static_cast<unsigned short>((v16[i] & ~L16_MASK) | ((in && v[i] > p.th_mask) ? L16_MASK : 0u));
+                    for (int k = 0; k < 8; ++k) {          // independent gathers, all in flight together
+                        mk[k] = 0;
+                        if ((v16[k] & (L16_MASK | L16_SEED)) == (L16_MASK | L16_SEED))
+                            mk[k] = marker_of(v16[k], y0 + (h * 8 + k) * 4 + pr0, gx, W, p.marker_at_root);
                     }
-                }
-                int mk[16];
 #pragma unroll
-                for (int i = 0; i < 16; ++i) {          // independent gathers, all in flight together
-                    mk[i] = 0;
-                    if ((v16[i] & (L16_MASK | L16_SEED)) == (L16_MASK | L16_SEED))
-                        mk[i] = marker_of(v16[i], y0 + row, x0 + col0 + i, W, p.marker_at_root);
-                }
-#pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    unsigned long long s = ST_OUTSIDE;
-                    if (v16[i] & L16_MASK) {
-                        const unsigned vo = ord_f32(p.negate ? -v[i] : v[i]);
-                        sV[row * CT + col0 + i] = vo;
-                        s = mk[i] > 0 ? ((static_cast<unsigned long long>(vo) << 32) | (1ull << 16) | static_cast<unsigned>(mk[i] & 0xFFFF))
-                                      : ST_UNREACHED;
+                    for (int k = 0; k < 8; ++k) {
+                        const int r = (h * 8 + k) * 4 + pr0;
+                        unsigned long long s = ST_OUTSIDE;
+                        if (v16[k] & L16_MASK) {
+                            const unsigned vo = ord_f32(p.negate ? -v[k] : v[k]);
+                            sV[r * CT + pc] = vo;
+                            s = mk[k] > 0 ? ((static_cast<unsigned long long>(vo) << 32) | (1ull << 16) | static_cast<unsigned>(mk[k] & 0xFFFF))
+                                          : ST_UNREACHED;
+                        }
+                        sS[r + 1][pc + 1] = s;
                     }
-                    sS[row + 1][col0 + i + 1] = s;
-                }
-            } else if (fast) {
-                const ulonglong2 *sp = reinterpret_cast<const ulonglong2 *>(p.state + rowbase);
-                const float4 *vp = reinterpret_cast<const float4 *>(p.img + rowbase);
-                ulonglong2 sv[8];
-                float4 fv[4];
-#pragma unroll
-                for (int j = 0; j < 8; ++j) sv[j] = sp[j];
-#pragma unroll
-                for (int j = 0; j < 4; ++j) fv[j] = vp[j];
-                load_halo(x0, y0);
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    sS[row + 1][col0 + 2 * j + 1] = sv[j].x;
-                    sS[row + 1][col0 + 2 * j + 2] = sv[j].y;
-                }
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    unsigned *d = sV + row * CT + col0 + 4 * j;
-                    d[0] = ord_f32(p.negate ? -fv[j].x : fv[j].x);
-                    d[1] = ord_f32(p.negate ? -fv[j].y : fv[j].y);
-                    d[2] = ord_f32(p.negate ? -fv[j].z : fv[j].z);
-                    d[3] = ord_f32(p.negate ? -fv[j].w : fv[j].w);
                 }
             } else {
                 load_halo(x0, y0);
-#pragma unroll 4
-                for (int i = 0; i < 16; ++i) {
-                    const int y = y0 + row, x = x0 + col0 + i;
-                    const bool in = y < H && x < W;
-                    const unsigned long long s = in ? p.state[static_cast<size_t>(y) * W + x] : ST_OUTSIDE;
-                    sS[row + 1][col0 + i + 1] = s;
-                    if (LAB32) sLab[row + 1][col0 + i + 1] = in ? p.lab32[static_cast<size_t>(y) * W + x] : 0;
-                    if (in && !((s >> 16) & 1ull)) {               // floodable: needs its value
-                        const float v = p.img[static_cast<size_t>(y) * W + x];
-                        sV[row * CT + col0 + i] = ord_f32(p.negate ? -v : v);
+#pragma unroll 1
+                for (int h = 0; h < 2; ++h) {           // two batches of eight rows: 24 values in flight per thread
+                    unsigned long long sv[8];
+                    float fv[8];
+                    int lv[8];
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        const int y = y0 + (h * 8 + k) * 4 + pr0;
+                        const bool in = y < H && gx < W;
+                        sv[k] = in ? p.state[static_cast<size_t>(y) * W + gx] : ST_OUTSIDE;
+                        fv[k] = in ? p.img[static_cast<size_t>(y) * W + gx] : 0.0f;
+                        if (LAB32) lv[k] = in ? p.lab32[static_cast<size_t>(y) * W + gx] : 0;
+                    }
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        const int r = (h * 8 + k) * 4 + pr0;
+                        sS[r + 1][pc + 1] = sv[k];
+                        sV[r * CT + pc] = ord_f32(p.negate ? -fv[k] : fv[k]);
+                        if (LAB32) sLab[r + 1][pc + 1] = lv[k];
                     }
                 }
             }
@@ -1458,36 +1442,20 @@ flood_kernel(const FloodParams p) {
             unsigned edge_bits = *reinterpret_cast<volatile unsigned *>(&sMisc[2]);
             unsigned my_edges = 0;
             if (changed_any || fused_init || (LAB32 && sweep == 0)) {
-                if (fast) {
-                    ulonglong2 *dp = reinterpret_cast<ulonglong2 *>(p.state + rowbase);
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        ulonglong2 v;
-                        v.x = sS[row + 1][col0 + 2 * j + 1];
-                        v.y = sS[row + 1][col0 + 2 * j + 2];
-                        dp[j] = v;
-                        if (sweep == 0) {
-                            if (static_cast<unsigned>(v.x >> 32) < ORD_INF)
-                                my_edges |= (row == 0 ? EDGE_TOP : 0u) | (row == CT - 1 ? EDGE_BOTTOM : 0u) | (col0 + 2 * j == 0 ? EDGE_LEFT : 0u);
-                            if (static_cast<unsigned>(v.y >> 32) < ORD_INF)
-                                my_edges |= (row == 0 ? EDGE_TOP : 0u) | (row == CT - 1 ? EDGE_BOTTOM : 0u) | (col0 + 2 * j + 1 == CT - 1 ? EDGE_RIGHT : 0u);
+                for (int k = 0; k < 16; ++k) {
+                    const int r = k * 4 + pr0;
+                    const int y = y0 + r;
+                    if (y < H && gx < W) {
+                        const unsigned long long s = sS[r + 1][pc + 1];
+                        if (fused_init || !((s >> 16) & 1ull)) {
+                            p.state[static_cast<size_t>(y) * W + gx] = s;
+                            if (LAB32) p.lab32[static_cast<size_t>(y) * W + gx] = sLab[r + 1][pc + 1];
                         }
-                    }
-                } else {
-#pragma unroll 4
-                    for (int i = 0; i < 16; ++i) {
-                        const int y = y0 + row, x = x0 + col0 + i;
-                        if (y < H && x < W) {
-                            const unsigned long long s = sS[row + 1][col0 + i + 1];
-                            if (fused_init || !((s >> 16) & 1ull)) {
-                                p.state[static_cast<size_t>(y) * W + x] = s;
-                                if (LAB32) p.lab32[static_cast<size_t>(y) * W + x] = sLab[row + 1][col0 + i + 1];
-                            }
-                            // first visit: the neighbours have not seen this tile yet -- every flooded edge pixel counts
-                            if (sweep == 0 && static_cast<unsigned>(s >> 32) < ORD_INF)
-                                my_edges |= (row == 0 ? EDGE_TOP : 0u) | (row == CT - 1 ? EDGE_BOTTOM : 0u) | (col0 + i == 0 ? EDGE_LEFT : 0u) |
-                                            (col0 + i == CT - 1 ? EDGE_RIGHT : 0u);
-                        }
+                        // first visit: the neighbours have not seen this tile yet -- every flooded edge pixel counts
+                        if (sweep == 0 && static_cast<unsigned>(s >> 32) < ORD_INF)
+                            my_edges |= (r == 0 ? EDGE_TOP : 0u) | (r == CT - 1 ? EDGE_BOTTOM : 0u) | (pc == 0 ? EDGE_LEFT : 0u) |
+                                        (pc == CT - 1 ? EDGE_RIGHT : 0u);
                     }
                 }
             }
@@ -1716,28 +1684,26 @@ flood_kernel(const FloodParams p) {
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int tyi = tile / tiles_x, txi = tile - tyi * tiles_x;
         const int x0 = txi * CT, y0 = tyi * CT;
-        const bool fast = aligned && x0 + CT <= W && y0 + CT <= H && (W & 7) == 0;
-        const size_t rowbase = static_cast<size_t>(y0 + row) * W + x0 + col0;
         __syncthreads();
-        if (fast) {
-            const ulonglong2 *sp = reinterpret_cast<const ulonglong2 *>(p.state + rowbase);
-            ulonglong2 sv[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) sv[j] = sp[j];
+        {
+            const int pc = threadIdx.x & (CT - 1), pr0 = threadIdx.x >> 6;
             load_halo(x0, y0);
+#pragma unroll 1
+            for (int h = 0; h < 2; ++h) {
+                unsigned long long sv[8];
+                int lv[8];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                sS[row + 1][col0 + 2 * j + 1] = sv[j].x;
-                sS[row + 1][col0 + 2 * j + 2] = sv[j].y;
-            }
-        } else {
-            load_halo(x0, y0);
-#pragma unroll 4
-            for (int i = 0; i < 16; ++i) {
-                const int y = y0 + row, x = x0 + col0 + i;
-                const bool in = y < H && x < W;
-                sS[row + 1][col0 + i + 1] = in ? p.state[static_cast<size_t>(y) * W + x] : ST_OUTSIDE;
-                if (LAB32) sLab[row + 1][col0 + i + 1] = in ? p.lab32[static_cast<size_t>(y) * W + x] : 0;
+                for (int k = 0; k < 8; ++k) {
+                    const int y = y0 + (h * 8 + k) * 4 + pr0, x = x0 + pc;
+                    const bool in = y < H && x < W;
+                    sv[k] = in ? p.state[static_cast<size_t>(y) * W + x] : ST_OUTSIDE;
+                    if (LAB32) lv[k] = in ? p.lab32[static_cast<size_t>(y) * W + x] : 0;
+                }
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    sS[(h * 8 + k) * 4 + pr0 + 1][pc + 1] = sv[k];
+                    if (LAB32) sLab[(h * 8 + k) * 4 + pr0 + 1][pc + 1] = lv[k];
+                }
             }
         }
         __syncthreads();
@@ -1764,7 +1730,13 @@ flood_kernel(const FloodParams p) {
                 if (static_cast<unsigned>(n1 >> 32) == lmin && (LAB32 ? sLab[r][c - 1] : static_cast<int>(n1 & 0xFFFFull)) != me) bad = true;
                 if (static_cast<unsigned>(n2 >> 32) == lmin && (LAB32 ? sLab[r][c + 1] : static_cast<int>(n2 & 0xFFFFull)) != me) bad = true;
                 if (static_cast<unsigned>(n3 >> 32) == lmin && (LAB32 ? sLab[r + 1][c] : static_cast<int>(n3 & 0xFFFFull)) != me) bad = true;
-                if (bad) ++bad_total;
+                if (bad) {
+                    ++bad_total;
+                    if (p.badlist) {
+                        const unsigned pos = atomicAdd(&p.st->n_bad, 1u);
+                        if (pos < static_cast<unsigned>(p.bad_cap)) p.badlist[pos] = static_cast<int>(o);
+                    }
+                }
             }
         }
     }
@@ -1773,20 +1745,219 @@ flood_kernel(const FloodParams p) {
     stamp(35);          // block 0's end of the final phase
 }
 
-// exact fallback, part 1 (runs only when the tiled result is order dependent): explicit marker / mask images for
-// ws_sequential_kernel from the packed words of the tiled pipeline
-__global__ void expand_markers_kernel(const uint16_t *__restrict__ L16, const int *__restrict__ marker_at_root, int H, int W,
-                                      const Stats *st, int *__restrict__ markers, uint8_t *__restrict__ mask,
-                                      const float *__restrict__ img, float th_mask, int use_th_mask) {
-    if (st->ambiguous == 0 && st->overflow == 0) return;
-    const long long n = static_cast<long long>(H) * W;
-    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n; i += static_cast<long long>(gridDim.x) * blockDim.x) {
-        const int y = static_cast<int>(i / W), x = static_cast<int>(i - static_cast<long long>(y) * W);
-        const unsigned v16 = L16[i];
-        const bool m = use_th_mask ? (img[i] > th_mask) : ((v16 & L16_MASK) != 0);
-        mask[i] = m ? 1 : 0;
-        markers[i] = (m && (v16 & L16_SEED)) ? marker_of(v16, y, x, W, marker_at_root) : 0;
+// ------------------------------------------------------------------------------------------
+// Exact fallback of the tiled path, one cooperative launch that returns at once unless the flood flagged an
+// order-dependent pixel.  The flood never leaves a 4-connected component of the mask, so only the components that
+// hold a flagged pixel are re-flooded, each by ONE thread running skimage's algorithm (binary heap keyed (value, age))
+// on its own heap region; every other pixel keeps the parallel result.  A component is independent of the rest of
+// the image as long as its pop order does not depend on the heap's internal order for equal keys: that only happens
+// among marker pixels (age 0) of equal value, and only matters if they carry different labels.  Such a pair pops
+// consecutively, so it is detected during the component's own flood; then (and if the hop counter overflowed or the
+// bad-pixel list was too small) the whole image is re-flooded by the single-thread restatement, exact in every case.
+// ------------------------------------------------------------------------------------------
+__device__ void sequential_flood(const float *img, int negate, const int *markers, const uint8_t *mask, int H, int W, int *lab,
+                                 HeapItem *heap, uint16_t *out16) {
+    const int n = H * W;
+    int hn = 0;
+    for (int i = 0; i < n; ++i) {
+        const int m = mask[i] ? markers[i] : 0;
+        lab[i] = m;
+        if (m) {
+            HeapItem e;
+            e.value = flood_value(img, i, negate);
+            e.age = 0;
+            e.index = i;
+            heap_push(heap, hn, e);
+        }
     }
+    int age = 1;
+    HeapItem e, ne;
+    while (hn > 0) {
+        heap_pop(heap, hn, e);
+        const int y = e.index / W, x = e.index - y * W;
+        const int l = lab[e.index];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            int q;
+            if (k == 0) { if (y == 0) continue; q = e.index - W; }
+            else if (k == 1) { if (x == 0) continue; q = e.index - 1; }
+            else if (k == 2) { if (x + 1 >= W) continue; q = e.index + 1; }
+            else { if (y + 1 >= H) continue; q = e.index + W; }
+            if (!mask[q]) continue;
+            if (lab[q]) continue;
+            age += 1;
+            lab[q] = l;
+            ne.value = flood_value(img, q, negate);
+            ne.age = age;
+            ne.index = q;
+            heap_push(heap, hn, ne);
+        }
+    }
+    if (out16)
+        for (int i = 0; i < n; ++i) out16[i] = static_cast<uint16_t>(static_cast<unsigned int>(lab[i]));
+}
+
+struct FallbackParams {
+    const uint16_t *L16;
+    const int *marker_at_root;
+    const float *img;
+    int negate;
+    float th_mask;
+    int use_th_mask;
+    int H, W;
+    Stats *st;
+    const int *badlist;
+    int bad_cap;
+    int *markers;        // [n]
+    uint8_t *mask8;      // [n]
+    int *uf;             // [n] union-find of the 4-connected mask components
+    int *comp_area;      // [n] at roots: pixels of the component
+    int *comp_base;      // [n] at roots: start of the component's heap region
+    int *comp_cnt;       // [n] at roots: marker pixels scattered into the heap region
+    int *comp_flag;      // [n] at roots: holds an order-dependent pixel
+    int *lab;            // [n]
+    HeapItem *heap;      // [n]
+    uint16_t *out16;
+};
+
+__global__ void __launch_bounds__(256)
+fallback_kernel(const FallbackParams p) {
+    namespace cg = cooperative_groups;
+    Stats *st = p.st;
+    if (st->ambiguous == 0 && st->overflow == 0) return;            // uniform across the grid: written by the previous launch
+    cg::grid_group grid = cg::this_grid();
+    const int H = p.H, W = p.W;
+    const long long n = static_cast<long long>(H) * W;
+    const long long gtid = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+    const long long gsz = static_cast<long long>(gridDim.x) * blockDim.x;
+    // P1: explicit marker / mask images, union-find init
+    for (long long i = gtid; i < n; i += gsz) {
+        const int y = static_cast<int>(i / W), x = static_cast<int>(i - static_cast<long long>(y) * W);
+        const unsigned v16 = p.L16[i];
+        const bool m = p.use_th_mask ? (p.img[i] > p.th_mask) : ((v16 & L16_MASK) != 0);
+        const int mk = (m && (v16 & L16_SEED)) ? marker_of(v16, y, x, W, p.marker_at_root) : 0;
+        p.mask8[i] = m ? 1 : 0;
+        p.markers[i] = mk;
+        p.lab[i] = mk;
+        p.uf[i] = m ? static_cast<int>(i) : -1;
+        p.comp_area[i] = 0;
+        p.comp_cnt[i] = 0;
+        p.comp_flag[i] = 0;
+    }
+    __threadfence();
+    grid.sync();
+    // P2: 4-connected unions
+    for (long long i = gtid; i < n; i += gsz) {
+        if (!p.mask8[i]) continue;
+        const int y = static_cast<int>(i / W), x = static_cast<int>(i - static_cast<long long>(y) * W);
+        if (x > 0 && p.mask8[i - 1]) uf_union(p.uf, static_cast<int>(i), static_cast<int>(i - 1));
+        if (y > 0 && p.mask8[i - W]) uf_union(p.uf, static_cast<int>(i), static_cast<int>(i - W));
+    }
+    __threadfence();
+    grid.sync();
+    // P3: flatten, component sizes
+    for (long long i = gtid; i < n; i += gsz) {
+        if (!p.mask8[i]) continue;
+        const int r = uf_find_v(p.uf, static_cast<int>(i));
+        p.uf[i] = r;
+        atomicAdd(&p.comp_area[r], 1);
+    }
+    __threadfence();
+    grid.sync();
+    // P4: components that hold an order-dependent pixel
+    {
+        unsigned nb = *reinterpret_cast<volatile unsigned *>(&st->n_bad);
+        if (gtid == 0 && (nb > static_cast<unsigned>(p.bad_cap) || *reinterpret_cast<volatile unsigned *>(&st->overflow))) st->need_global = 1;
+        if (nb > static_cast<unsigned>(p.bad_cap)) nb = static_cast<unsigned>(p.bad_cap);
+        for (long long i = gtid; i < nb; i += gsz) {
+            const int b = p.badlist[i];
+            const int r = uf_find_v(p.uf, b);
+            p.comp_flag[r] = 1;
+        }
+    }
+    __threadfence();
+    grid.sync();
+    // P5: heap regions (bump allocation: the regions of disjoint components add up to at most n entries)
+    for (long long i = gtid; i < n; i += gsz) {
+        if (*reinterpret_cast<volatile int *>(&p.uf[i]) == static_cast<int>(i) && *reinterpret_cast<volatile int *>(&p.comp_flag[i])) {
+            p.comp_base[i] = static_cast<int>(atomicAdd(&st->pool_top, static_cast<unsigned>(*reinterpret_cast<volatile int *>(&p.comp_area[i]))));
+            atomicAdd(&st->n_reflooded, 1u);
+        }
+    }
+    __threadfence();
+    grid.sync();
+    // P6: the markers of the flagged components go into their heap regions (any order: see the header comment);
+    // every other pixel of such a component becomes unlabelled again
+    for (long long i = gtid; i < n; i += gsz) {
+        if (!p.mask8[i]) continue;
+        const int r = *reinterpret_cast<volatile int *>(&p.uf[i]);
+        if (!*reinterpret_cast<volatile int *>(&p.comp_flag[r])) continue;
+        const int mk = p.markers[i];
+        if (mk) {
+            const int slot = atomicAdd(&p.comp_cnt[r], 1);
+            HeapItem e;
+            e.value = flood_value(p.img, static_cast<int>(i), p.negate);
+            e.age = 0;
+            e.index = static_cast<int>(i);
+            p.heap[*reinterpret_cast<volatile int *>(&p.comp_base[r]) + slot] = e;
+        } else {
+            p.out16[i] = 0;
+        }
+    }
+    __threadfence();
+    grid.sync();
+    // P7: one thread per flagged component: heapify, then skimage's flood
+    for (long long i = gtid; i < n; i += gsz) {
+        if (*reinterpret_cast<volatile int *>(&p.uf[i]) != static_cast<int>(i) || !*reinterpret_cast<volatile int *>(&p.comp_flag[i])) continue;
+        HeapItem *h = p.heap + *reinterpret_cast<volatile int *>(&p.comp_base[i]);
+        int hn = *reinterpret_cast<volatile int *>(&p.comp_cnt[i]);
+        for (int s0 = hn / 2 - 1; s0 >= 0; --s0) {                  // bottom-up heap construction
+            int k = s0;
+            for (;;) {
+                const int l = 2 * k + 1, r = 2 * k + 2;
+                int sm = k;
+                if (l < hn && item_smaller(h[l], h[sm])) sm = l;
+                if (r < hn && item_smaller(h[r], h[sm])) sm = r;
+                if (sm == k) break;
+                const HeapItem t = h[k];
+                h[k] = h[sm];
+                h[sm] = t;
+                k = sm;
+            }
+        }
+        int age = 1;
+        HeapItem e, ne;
+        bool conflict = false;
+        while (hn > 0) {
+            heap_pop(h, hn, e);
+            const int l = p.lab[e.index];
+            if (e.age == 0 && hn > 0 && h[0].age == 0 && h[0].value == e.value && p.lab[h[0].index] != l) conflict = true;
+            const int y = e.index / W, x = e.index - y * W;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                int q;
+                if (k == 0) { if (y == 0) continue; q = e.index - W; }
+                else if (k == 1) { if (x == 0) continue; q = e.index - 1; }
+                else if (k == 2) { if (x + 1 >= W) continue; q = e.index + 1; }
+                else { if (y + 1 >= H) continue; q = e.index + W; }
+                if (!p.mask8[q]) continue;
+                if (p.lab[q]) continue;
+                age += 1;
+                p.lab[q] = l;
+                p.out16[q] = static_cast<uint16_t>(static_cast<unsigned int>(l));
+                ne.value = flood_value(p.img, q, p.negate);
+                ne.age = age;
+                ne.index = q;
+                heap_push(h, hn, ne);
+            }
+        }
+        if (conflict) st->need_global = 1;
+    }
+    __threadfence();
+    grid.sync();
+    // P8: last resort
+    if (gtid == 0 && *reinterpret_cast<volatile unsigned *>(&st->need_global))
+        sequential_flood(p.img, p.negate, p.markers, p.mask8, H, W, p.lab, p.heap, p.out16);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -2185,6 +2356,7 @@ struct TiledWs {
     unsigned long long *state;
     uint8_t *tile_changed;
     int *lab32;              // generic watershed only
+    int *comp_cnt, *comp_flag;   // exact fallback: per-component counters (at the component roots)
     // exact sequential fallback
     int *markers;
     uint8_t *mask8;
@@ -2197,7 +2369,8 @@ size_t tiled_ws_bytes(size_t n, int H, int W, bool generic) {
     const size_t tiles = static_cast<size_t>((H + CT - 1) / CT) * ((W + CT - 1) / CT);
     size_t b = r256(sizeof(Stats)) + r256(n * 4) + r256(n * 2) + 2 * r256(n * 4) + r256((n / 4 + 1024) * 4) +
                2 * r256((n / 32 + 2) * 4) + r256(MID_MAX_BLOCKS * 4) + r256(n * 8) + r256(2 * tiles + 256) +
-               r256(n * 4) /*markers*/ + r256(n) /*mask*/ + r256(n * 4) /*lab*/ + r256(n * sizeof(HeapItem));
+               r256(n * 4) /*markers*/ + r256(n) /*mask*/ + r256(n * 4) /*lab*/ + r256(n * sizeof(HeapItem)) +
+               2 * r256(n * 4) /*component counters / flags of the exact fallback (area / base live in the state array)*/;
     if (generic) b += r256(n * 4);
     return b + 4096;
 }
@@ -2221,12 +2394,14 @@ bool carve_tiled(TiledWs &t, void *workspace, size_t bytes, size_t n, int H, int
     t.mask8 = cv.take<uint8_t>(n);
     t.lab = cv.take<int>(n);
     t.heap = cv.take<HeapItem>(n);
+    t.comp_cnt = cv.take<int>(n);
+    t.comp_flag = cv.take<int>(n);
     t.lab32 = generic ? cv.take<int>(n) : nullptr;
     return cv.ok;
 }
 
 struct CoopCfg {
-    int mid_blocks, flood16_blocks, flood32_blocks;
+    int mid_blocks, flood16_blocks, flood32_blocks, fallback_blocks;
     bool ready;
 };
 
@@ -2240,12 +2415,16 @@ int coop_config(CoopCfg **out) {
         MBS_CHECK_CUDA(cudaFuncSetAttribute(flood_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FLOOD_SMEM16));
         MBS_CHECK_CUDA(cudaFuncSetAttribute(flood_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FLOOD_SMEM32));
         MBS_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, mid_kernel, 256, 0));
-        c.mid_blocks = sms * (per > 0 ? per : 1);
+        // list / seam / bitmap work of a few hundred thousand items between five grid barriers: a small grid keeps the
+        // barriers cheap
+        c.mid_blocks = sms * (per > 2 ? 2 : (per > 0 ? per : 1));
         if (c.mid_blocks > MID_MAX_BLOCKS) c.mid_blocks = MID_MAX_BLOCKS;
         MBS_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, flood_kernel<false>, 256, FLOOD_SMEM16));
         c.flood16_blocks = sms * (per > 0 ? per : 1);
         MBS_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, flood_kernel<true>, 256, FLOOD_SMEM32));
         c.flood32_blocks = sms * (per > 0 ? per : 1);
+        MBS_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, fallback_kernel, 256, 0));
+        c.fallback_blocks = sms * (per > 0 ? (per > 4 ? 4 : per) : 1);
         c.ready = true;
     }
     *out = &c;
@@ -2264,6 +2443,40 @@ int read_info(const TiledWs &t, int64_t *info_host, cudaStream_t stream) {
     info_host[3] = (hp->ambiguous || hp->overflow) ? 1 : 0;
     info_host[4] = hp->ambiguous;
     info_host[5] = hp->overflow;
+    info_host[6] = hp->need_global;          // whole-image sequential flood ran
+    info_host[7] = hp->n_reflooded;          // mask components re-flooded on their own
+    return 0;
+}
+
+// exact fallback of the fused paths (returns at once on the device unless the flood flagged an order-dependent pixel)
+int launch_fallback(const TiledWs &t, const CoopCfg *cfg, int H, int W, int negate, float th_mask, int use_th_mask, uint16_t *out,
+                    cudaStream_t stream) {
+    const size_t n = static_cast<size_t>(H) * W;
+    FallbackParams fb;
+    fb.L16 = t.L16;
+    fb.marker_at_root = t.area;
+    fb.img = t.cell_s;
+    fb.negate = negate;
+    fb.th_mask = th_mask;
+    fb.use_th_mask = use_th_mask;
+    fb.H = H;
+    fb.W = W;
+    fb.st = t.st;
+    fb.badlist = t.list;
+    fb.bad_cap = t.list_cap;
+    fb.markers = t.markers;
+    fb.mask8 = t.mask8;
+    fb.uf = t.G;                                                    // the seed union-find is dead after mid_kernel
+    fb.comp_area = reinterpret_cast<int *>(t.state);                // the flood state is dead after its final phase
+    fb.comp_base = reinterpret_cast<int *>(t.state) + n;
+    fb.comp_cnt = t.comp_cnt;
+    fb.comp_flag = t.comp_flag;
+    fb.lab = t.lab;
+    fb.heap = t.heap;
+    fb.out16 = out;
+    void *args[] = {(void *)&fb};
+    MBS_CHECK_CUDA(cudaLaunchCooperativeKernel((void *)fallback_kernel, dim3(cfg->fallback_blocks), dim3(256), args, 0, stream));
+    mbs::count_launch();
     return 0;
 }
 
@@ -2304,6 +2517,8 @@ int run_tiled(const float *a, const float *b, int H, int W, int ld, float th_see
         fp.chase_heavy = light_limit(2);
         fp.chase_light = light_limit(3);
         fp.light_min_tiles = light_limit(4);
+        fp.badlist = t.list;        // the root list is dead after mid_kernel
+        fp.bad_cap = t.list_cap;
         fp.state = t.state;
         fp.lab32 = nullptr;
         fp.H = H;
@@ -2318,14 +2533,8 @@ int run_tiled(const float *a, const float *b, int H, int W, int ld, float th_see
         MBS_CHECK_CUDA(cudaLaunchCooperativeKernel((void *)flood_kernel<false>, dim3(blocks), dim3(256), args, FLOOD_SMEM16, stream));
         mbs::count_launch();
     }
-    // exact fallback (both kernels return immediately unless the flood flagged an order-dependent pixel)
-    {
-        const int want = mbs::cdiv(static_cast<int>(n), 256);
-        expand_markers_kernel<<<want < 1184 ? want : 1184, 256, 0, stream>>>(t.L16, t.area, H, W, t.st, t.markers, t.mask8, t.cell_s, 0.0f, 0);
-    }
-    MBS_CHECK_LAUNCH();
-    ws_sequential_kernel<<<1, 32, 0, stream>>>(t.cell_s, BOUNDARY ? 0 : 1, t.markers, t.mask8, H, W, t.lab, t.heap, t.st, 0, out);
-    MBS_CHECK_LAUNCH();
+    rc = launch_fallback(t, cfg, H, W, BOUNDARY ? 0 : 1, 0.0f, 0, out, stream);
+    if (rc) return rc;
     if (info_host) return read_info(t, info_host, stream);
     return 0;
 }
@@ -2338,6 +2547,7 @@ __global__ void flood_reset_kernel(Stats *st) {
     st->ambiguous = 0;
     st->sweeps = 0;
     st->overflow = 0;
+    st->n_bad = st->need_global = st->n_reflooded = st->pool_top = 0;
     for (int i = 0; i < 32; ++i) st->dbg_tiles[i] = st->dbg_rounds[i] = st->dbg_maxrounds[i] = st->dbg_items[i] = 0;
 }
 }  // namespace
@@ -2392,6 +2602,8 @@ extern "C" int mbs_distance_postprocessing_sweep(const float *border, const floa
             fp.chase_heavy = light_limit(2);
             fp.chase_light = light_limit(3);
             fp.light_min_tiles = light_limit(4);
+            fp.badlist = t.list;
+            fp.bad_cap = t.list_cap;
             fp.state = t.state;
             fp.lab32 = nullptr;
             fp.H = H;
@@ -2404,12 +2616,8 @@ extern "C" int mbs_distance_postprocessing_sweep(const float *border, const floa
             void *args[] = {(void *)&fp};
             MBS_CHECK_CUDA(cudaLaunchCooperativeKernel((void *)flood_kernel<false>, dim3(blocks), dim3(256), args, FLOOD_SMEM16, stream));
             mbs::count_launch();
-            const int want = mbs::cdiv(static_cast<int>(n), 256);
-            expand_markers_kernel<<<want < 1184 ? want : 1184, 256, 0, stream>>>(t.L16, t.area, H, W, t.st, t.markers, t.mask8, t.cell_s,
-                                                                                th_cells_host[ic], 1);
-            MBS_CHECK_LAUNCH();
-            ws_sequential_kernel<<<1, 32, 0, stream>>>(t.cell_s, 1, t.markers, t.mask8, H, W, t.lab, t.heap, t.st, 0, o);
-            MBS_CHECK_LAUNCH();
+            rc = launch_fallback(t, cfg, H, W, 1, th_cells_host[ic], 1, o, stream);
+            if (rc) return rc;
             if (info_host) {
                 rc = read_info(t, info_host + (static_cast<size_t>(is) * n_cell + ic) * 8, stream);
                 if (rc) return rc;
@@ -2490,6 +2698,8 @@ extern "C" int mbs_pp_watershed(const float *image, const int32_t *markers, cons
         fp.chase_heavy = light_limit(2);
         fp.chase_light = light_limit(3);
         fp.light_min_tiles = light_limit(4);
+        fp.badlist = nullptr;
+        fp.bad_cap = 0;
         fp.state = t.state;
         fp.lab32 = t.lab32;
         fp.H = H;

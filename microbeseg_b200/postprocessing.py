@@ -37,7 +37,8 @@ def _workspace(device, nbytes):
 
 def _info_dict(info):
     return dict(n_seed_components=int(info[0]), n_markers=int(info[1]), sweeps=int(info[2]), sequential=int(info[3]),
-                ambiguous=int(info[4]), overflow=int(info[5]))
+                ambiguous=int(info[4]), overflow=int(info[5]), whole_image_sequential=int(info[6]),
+                components_reflooded=int(info[7]))
 
 
 def _as_device_map(a, device):

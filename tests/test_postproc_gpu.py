@@ -229,9 +229,27 @@ def test_full_size_properties(pp):
     assert np.array_equal(out, ref)
 
 
+def test_tie_heavy_maps_refloods_only_the_ambiguous_components(pp):
+    """Quantised distance maps (value ties everywhere) at 1024^2: the order-free flood flags order-dependent pixels and
+    the exact fallback re-floods only the mask components that hold one (per-component heap floods, one thread each);
+    the mask must equal the oracle's (skimage's FIFO tie-break incl. heap order for equal keys) bit for bit."""
+    from microbeseg_b200 import postprocessing as P
+    m = sy.synth_instance_mask(1024, 1024, 2600, 21)                 # dense: many touching cells
+    border, cell = sy.synth_distance_maps(m, 22, noise=0.0)
+    cell = (np.round(cell * 32) / 32).astype(np.float32)            # 33 levels
+    border = (np.round(border * 16) / 16).astype(np.float32)
+    b, c = torch.from_numpy(border[..., 0]).cuda(), torch.from_numpy(cell[..., 0]).cuda()
+    out = P.distance_postprocessing_device(b, c, 0.45, 0.10, want_info=True).cpu().numpy().view(np.uint16)
+    info = dict(P.last_info)
+    ref = op.distance_postprocessing(border, cell, 0.45, 0.10)
+    assert np.array_equal(out, ref)
+    assert info["ambiguous"] > 0 and info["sequential"] == 1 and info["components_reflooded"] > 0, info
+    print("\ntie-heavy 1024^2:", info)
+
+
 def test_boundary_postprocessing_vs_oracle(pp):
     """Boundary method (postprocessing.py:62-90): flat flood image -> pure FIFO order incl. heap internals."""
-    for H, W, cells, seed in [(96, 96, 14, 1), (128, 160, 40, 2), (64, 64, 0, 3)]:
+    for H, W, cells, seed in [(96, 96, 14, 1), (128, 160, 40, 2), (64, 64, 0, 3), (1024, 1024, 1300, 4)]:
         m = sy.synth_instance_mask(H, W, cells, seed)
         inner = ndimage.binary_erosion(m > 0, iterations=2)
         rng = np.random.default_rng(seed)
