@@ -225,8 +225,8 @@ def main():
 
     conv_ms = []
 
-    # MBS_PP_STREAM=0: post-processing on the network's stream (A/B knob)
-    pp_stream = torch.cuda.current_stream(device) if os.environ.get("MBS_PP_STREAM") == "0" else torch.cuda.Stream(device)
+    # post-processing on the network's stream, as FrameSegmenter does (MBS_PP_STREAM=1: separate stream, A/B knob)
+    pp_stream = torch.cuda.Stream(device) if os.environ.get("MBS_PP_STREAM") == "1" else torch.cuda.current_stream(device)
     ev_net = [torch.cuda.Event() for _ in range(2)]
     ev_pp = [torch.cuda.Event() for _ in range(2)]
 
@@ -302,8 +302,8 @@ def main():
     def step_e2e():
         inference.segment_stack(net, host_stack, ths=(th_cell, th_seed), device=device, out=out_host)
 
-    e2e_steps = max(2, args.steps // 2)
-    ms_e2e, _ = timed(step_e2e, e2e_steps, 1)
+    e2e_steps = max(3, args.steps // 2)
+    ms_e2e, _ = timed(step_e2e, e2e_steps, 2)
     e2e_value = mpx_step_all * e2e_steps / (ms_e2e / 1e3)
     sampler.stop_flag = True
     sampler.join(timeout=2)

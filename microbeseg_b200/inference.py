@@ -37,9 +37,12 @@ class FrameSegmenter:
         self._stage = {}
         self.h2d_stream = torch.cuda.Stream(self.device)
         self.d2h_stream = torch.cuda.Stream(self.device)
-        # post-processing of frame k overlaps the network of frame k+1 (MBS_PP_STREAM=0: same stream, A/B knob)
-        self.pp_stream = (torch.cuda.current_stream(self.device) if os.environ.get("MBS_PP_STREAM") == "0"
-                          else torch.cuda.Stream(self.device))
+        # Post-processing runs on the network's stream.  The persistent conv CTAs fill every SM, so a second stream gives
+        # no overlap (measured: 11.0 ms per frame either way), and the cooperative post-processing kernels -- which need the
+        # whole GPU at once -- are starved behind the queued conv launches of the next frames until the host blocks on a
+        # result, which leaves bubbles (e2e 344 vs 376 Mpx/s).  MBS_PP_STREAM=1 selects the separate stream (A/B knob).
+        self.pp_stream = (torch.cuda.Stream(self.device) if os.environ.get("MBS_PP_STREAM") == "1"
+                          else torch.cuda.current_stream(self.device))
 
     def _staging(self, shape, dtype, slot):
         key = (tuple(shape), np.dtype(dtype).str, slot)
