@@ -634,20 +634,13 @@ __global__ void gap_stats_kernel(const uint8_t *__restrict__ gap, const int *__r
         }
 }
 
-// gap map (label_closed_corr) + max with raw neighbour map and touching borders + rescale + clip (:352-358)
-__global__ void lab_compose_kernel(const uint8_t *__restrict__ gap, const int *__restrict__ gid, const GapStats *__restrict__ gs,
-                                   const uint8_t *__restrict__ border, const double *__restrict__ nraw, int H, int W, int max_gaps,
-                                   double *__restrict__ scaled) {
-    const int crop = blockIdx.z;
-    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
-    if (x >= W || y >= H) return;
-    const size_t base = static_cast<size_t>(crop) * H * W;
-    const int *g = gid + base;
-    const uint8_t *gp = gap + base;
+// gap map (label_closed_corr) + max with raw neighbour map and touching borders + rescale + clip (:352-358) at one pixel
+__device__ __forceinline__ double compose_at(const uint8_t *__restrict__ gp, const int *__restrict__ g, const GapStats *__restrict__ gsc,
+                                             const uint8_t *__restrict__ border, const double *__restrict__ nraw, int H, int W, int y, int x) {
     const int me = gp[y * W + x] ? g[y * W + x] : -1;
     float corr = 0.0f;
     if (me >= 0) {
-        const GapStats s = gs[static_cast<size_t>(crop) * max_gaps + me];
+        const GapStats s = gsc[me];
         const double th = s.cnt <= 20 ? 5.0 : (s.cnt <= 30 ? 8.0 : (s.cnt <= 50 ? 10.0 : 20.0));   // :342-349
         if (s.bsum < th) {
             corr = 0.0f;                                    // artefact: completely in the background
@@ -664,12 +657,11 @@ __global__ void lab_compose_kernel(const uint8_t *__restrict__ gap, const int *_
             }
         }
     }
-    double v = nraw[base + y * W + x];
+    double v = nraw[y * W + x];
     v = fmax(v, static_cast<double>(corr));
-    v = fmax(v, border[base + y * W + x] ? 1.0 : 0.0);
+    v = fmax(v, border[y * W + x] ? 1.0 : 0.0);
     v = 1.0 / sqrt(0.65 + 0.5 * exp(-11.0 * (v - 0.75))) - 0.19;
-    v = v < 0.0 ? 0.0 : (v > 1.0 ? 1.0 : v);
-    scaled[base + y * W + x] = v;
+    return v < 0.0 ? 0.0 : (v > 1.0 ? 1.0 : v);
 }
 
 __device__ __forceinline__ int reflect_idx(int i, int n) {
@@ -679,25 +671,33 @@ __device__ __forceinline__ int reflect_idx(int i, int n) {
     }
     return i;
 }
-// grey_closing(size=(3,3)) = 3x3 max filter then 3x3 min filter, mode 'reflect' (edge sample duplicated) -- both filters
-// in ONE pass.  S holds scaled[reflect(raw)] for the raw coordinates of the 32x8 tile with a 2-pixel apron; the dilated map
-// D at a raw position h (1-pixel apron) is the 3x3 maximum around q = reflect(h), i.e. the value the min filter would
-// read there; the output is the 3x3 minimum of D.
+// compose + grey_closing(size=(3,3)) in ONE pass (round 2: the float64 `scaled` map is never written; it cost 16 B/px of
+// traffic and a launch).  grey closing = 3x3 max filter then 3x3 min filter, mode 'reflect' (edge sample duplicated).
+// S holds compose(reflect(raw)) for the raw coordinates of the 32x32 tile with a 2-pixel apron (27 % recomputed apron);
+// the dilated map D at a raw position h (1-pixel apron) is the 3x3 maximum around q = reflect(h), i.e. the value the min
+// filter would read there; the output is the 3x3 minimum of D.
+constexpr int GT = 32;
 __global__ void __launch_bounds__(256)
-lab_grey_closing_kernel(const double *__restrict__ in, int H, int W, float *__restrict__ out) {
-    __shared__ double S[12][36 + 1];
-    __shared__ double D[10][34 + 1];
+lab_compose_closing_kernel(const uint8_t *__restrict__ gap, const int *__restrict__ gid, const GapStats *__restrict__ gs,
+                           const uint8_t *__restrict__ border, const double *__restrict__ nraw, int H, int W, int max_gaps,
+                           float *__restrict__ out) {
+    __shared__ double S[GT + 4][GT + 4 + 1];
+    __shared__ double D[GT + 2][GT + 2 + 1];
     const int crop = blockIdx.z;
-    const int x0 = blockIdx.x * 32, y0 = blockIdx.y * 8;
-    const int tid = threadIdx.y * 32 + threadIdx.x;
-    const double *p = in + static_cast<size_t>(crop) * H * W;
-    for (int i = tid; i < 12 * 36; i += 256) {
-        const int r = i / 36, c = i - r * 36;
-        S[r][c] = p[reflect_idx(y0 - 2 + r, H) * W + reflect_idx(x0 - 2 + c, W)];
+    const int x0 = blockIdx.x * GT, y0 = blockIdx.y * GT;
+    const int tid = threadIdx.x;
+    const size_t base = static_cast<size_t>(crop) * H * W;
+    const uint8_t *gp = gap + base, *bp = border + base;
+    const int *g = gid + base;
+    const double *np_ = nraw + base;
+    const GapStats *gsc = gs + static_cast<size_t>(crop) * max_gaps;
+    for (int i = tid; i < (GT + 4) * (GT + 4); i += 256) {
+        const int r = i / (GT + 4), c = i - r * (GT + 4);
+        S[r][c] = compose_at(gp, g, gsc, bp, np_, H, W, reflect_idx(y0 - 2 + r, H), reflect_idx(x0 - 2 + c, W));
     }
     __syncthreads();
-    for (int i = tid; i < 10 * 34; i += 256) {
-        const int r = i / 34, c = i - r * 34;
+    for (int i = tid; i < (GT + 2) * (GT + 2); i += 256) {
+        const int r = i / (GT + 2), c = i - r * (GT + 2);
         if (y0 - 1 + r > H || x0 - 1 + c > W) {      // beyond the 1-pixel apron of the image (ragged last tiles): never read
             D[r][c] = 0.0;
             continue;
@@ -711,14 +711,17 @@ lab_grey_closing_kernel(const double *__restrict__ in, int H, int W, float *__re
         D[r][c] = v;
     }
     __syncthreads();
-    const int x = x0 + threadIdx.x, y = y0 + threadIdx.y;
-    if (x >= W || y >= H) return;
-    double v = D[threadIdx.y + 1][threadIdx.x + 1];
+    for (int i = tid; i < GT * GT; i += 256) {
+        const int r = i / GT, c = i - r * GT;
+        const int x = x0 + c, y = y0 + r;
+        if (x >= W || y >= H) continue;
+        double v = D[r + 1][c + 1];
 #pragma unroll
-    for (int dy = 0; dy <= 2; ++dy)
+        for (int dy = 0; dy <= 2; ++dy)
 #pragma unroll
-        for (int dx = 0; dx <= 2; ++dx) v = fmin(v, D[threadIdx.y + dy][threadIdx.x + dx]);
-    out[(static_cast<size_t>(crop) * H + y) * W + x] = static_cast<float>(v);
+            for (int dx = 0; dx <= 2; ++dx) v = fmin(v, D[r + dy][c + dx]);
+        out[base + static_cast<size_t>(y) * W + x] = static_cast<float>(v);
+    }
 }
 
 inline size_t r256(size_t b) { return (b + 255) & ~static_cast<size_t>(255); }
@@ -929,9 +932,8 @@ extern "C" int mbs_distance_labels(const uint16_t *masks, int n_crops, int H, in
     MBS_CHECK_LAUNCH();
     gap_stats_kernel<<<g3, b2, 0, stream>>>(gap, gid, nraw, H, W, kMaxGaps, gs);
     MBS_CHECK_LAUNCH();
-    lab_compose_kernel<<<g3, b2, 0, stream>>>(gap, gid, gs, border, nraw, H, W, kMaxGaps, scaled);
-    MBS_CHECK_LAUNCH();
-    lab_grey_closing_kernel<<<g3, b2, 0, stream>>>(scaled, H, W, neighbor_dist);
+    lab_compose_closing_kernel<<<dim3(mbs::cdiv(W, GT), mbs::cdiv(H, GT), n_crops), 256, 0, stream>>>(gap, gid, gs, border, nraw, H, W, kMaxGaps,
+                                                                                                  neighbor_dist);
     MBS_CHECK_LAUNCH();
     if (max_mal_out)
         MBS_CHECK_CUDA(cudaMemcpy2DAsync(max_mal_out, sizeof(int), &info[0].max_mal, sizeof(CropInfo), sizeof(int), n_crops,

@@ -89,7 +89,9 @@ def run_sharded(fn, n, specs, transport="auto"):
             for o in outs:
                 o.flush()
             _barrier()                                   # every rank's rows are in the shared arrays
-            result = [np.array(o) for o in outs] if rank == 0 else None
+            # rank 0 keeps the mapping (no copy of the gathered data); the names are removed below, the pages live as
+            # long as the returned arrays do
+            result = outs if rank == 0 else None
         finally:
             del outs
             _barrier()
