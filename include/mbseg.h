@@ -246,6 +246,15 @@ int mbs_distance_postprocessing_sweep(const float *border, const float *cell, in
                                       int n_seed, const float *th_cells_host, int n_cell, uint16_t *out, void *workspace,
                                       size_t workspace_bytes, int64_t *info_host, void *stream);
 
+/*
+ * Criteria of the boundary method (src/training/losses.py:16-21, 71-96; 3 classes): nn.CrossEntropyLoss (with_dice = 0)
+ * or ce_dice = cross entropy + 0.5 * sum_c c * dice_c over the channels 1, 2 of softmax(logits) (with_dice = 1).
+ * logits: float32 planar [3][M] (M = N*H*W pixels of the batch), labels: uint8 [M] in {0,1,2};
+ * loss_accum += loss (device float, caller zeroes it); grad: float32 [3][M] = dloss/dlogits; sums7: device double[7] scratch.
+ */
+int mbs_ce_dice_loss(const float *logits, const uint8_t *labels, long long M, int with_dice, float *loss_accum, float *grad,
+                     double *sums7, void *stream);
+
 /* ---------------------------------------------------------------------------------------- */
 /* mask -> polygon ROI encoding                                           */
 /* ---------------------------------------------------------------------------------------- */

@@ -18,6 +18,7 @@
 
 #include <climits>
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
 
 #include "../../include/mbseg.h"
@@ -904,7 +905,14 @@ extern "C" int mbs_distance_labels(const uint16_t *masks, int n_crops, int H, in
         int smem = want > smem_opt ? smem_opt : static_cast<int>(want);
         if (smem < 4096) smem = 4096;
         dim3 gc(max_id, n_crops);
-        lab_cell_kernel<<<gc, 256, smem, stream>>>(masks, H, W, ids, cs, info, cell_dist, nraw, smem / 6);
+        // latency-bound CTAs (serial column scans, ~300 own pixels per instance): small blocks, many resident per SM
+        static int cell_threads = 0;
+        if (!cell_threads) {
+            const char *e = getenv("MBS_LAB_CELL_THREADS");       // A/B knob
+            cell_threads = e ? atoi(e) : 128;
+            if (cell_threads < 32 || cell_threads > 256) cell_threads = 128;
+        }
+        lab_cell_kernel<<<gc, cell_threads, smem, stream>>>(masks, H, W, ids, cs, info, cell_dist, nraw, smem / 6);
         MBS_CHECK_LAUNCH();
         long long wantc = 2ll * (static_cast<long long>(H) + 6) * (W + 6);
         int smemc = wantc > smem_opt ? smem_opt : static_cast<int>(wantc);

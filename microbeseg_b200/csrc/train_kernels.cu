@@ -387,6 +387,88 @@ smoothl1_kernel(const float *__restrict__ pred, const float *__restrict__ target
     }
 }
 
+// Criteria of the boundary method (losses.py:16-21, 71-96), 3 classes, logits planar [3][M], labels uint8 [M]:
+//   'ce'      : nn.CrossEntropyLoss()  = mean over pixels of -log softmax(z)[y]
+//   'ce_dice' : ce + 0.5 * sum_{c=1,2} c * dice_c,  dice_c = 1 - (2 sum(g_c p_c) + 1) / (sum(g_c^2) + sum(p_c^2) + 1)
+//               with p = softmax(z), g = one_hot(y), sums over the WHOLE batch (losses.py:58-63, 90-94).
+// Pass 1 accumulates the seven sums, pass 2 writes dloss/dz and the loss value.
+// sums: [0] ce, [1..2] sum g_c p_c, [3..4] sum p_c^2, [5..6] sum g_c   (c = 1, 2)
+__device__ __forceinline__ void softmax3(float z0, float z1, float z2, float &p0, float &p1, float &p2, float &lse) {
+    const float m = fmaxf(z0, fmaxf(z1, z2));
+    const float e0 = expf(z0 - m), e1 = expf(z1 - m), e2 = expf(z2 - m);
+    const float s = e0 + e1 + e2;
+    p0 = e0 / s; p1 = e1 / s; p2 = e2 / s;
+    lse = m + logf(s);
+}
+
+__global__ void __launch_bounds__(256)
+ce_dice_sums_kernel(const float *__restrict__ z, const uint8_t *__restrict__ y, long long M, double *sums) {
+    float a[7] = {0, 0, 0, 0, 0, 0, 0};
+    for (long long p = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; p < M; p += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const float z0 = z[p], z1 = z[M + p], z2 = z[2 * M + p];
+        float p0, p1, p2, lse;
+        softmax3(z0, z1, z2, p0, p1, p2, lse);
+        const int c = y[p];
+        a[0] += lse - (c == 0 ? z0 : (c == 1 ? z1 : z2));
+        a[1] += c == 1 ? p1 : 0.0f;
+        a[2] += c == 2 ? p2 : 0.0f;
+        a[3] += p1 * p1;
+        a[4] += p2 * p2;
+        a[5] += c == 1 ? 1.0f : 0.0f;
+        a[6] += c == 2 ? 1.0f : 0.0f;
+    }
+    __shared__ float s_part[8][7];
+#pragma unroll
+    for (int k = 0; k < 7; ++k) {
+        const float v = warp_sum(a[k]);
+        if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5][k] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < 7) {
+        double t = 0.0;
+        for (int w = 0; w < 8; ++w) t += static_cast<double>(s_part[w][threadIdx.x]);
+        atomicAdd(&sums[threadIdx.x], t);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+ce_dice_grad_kernel(const float *__restrict__ z, const uint8_t *__restrict__ y, long long M, int with_dice, const double *__restrict__ sums,
+                    float *loss, float *__restrict__ g) {
+    const float invM = 1.0f / static_cast<float>(M);
+    // dice_c = 1 - N_c / D_c;  d dice_c / d p_c(pixel) = -(2 g_c D_c - 2 p_c N_c) / D_c^2;  weight 0.5 * c
+    float N1 = 0, N2 = 0, D1 = 1, D2 = 1;
+    if (with_dice) {
+        N1 = static_cast<float>(2.0 * sums[1] + 1.0);
+        N2 = static_cast<float>(2.0 * sums[2] + 1.0);
+        D1 = static_cast<float>(sums[5] + sums[3] + 1.0);
+        D2 = static_cast<float>(sums[6] + sums[4] + 1.0);
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        float l = static_cast<float>(sums[0]) * invM;
+        if (with_dice) l += 0.5f * (1.0f * (1.0f - N1 / D1) + 2.0f * (1.0f - N2 / D2));
+        atomicAdd(loss, l);
+    }
+    for (long long p = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; p < M; p += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const float z0 = z[p], z1 = z[M + p], z2 = z[2 * M + p];
+        float p0, p1, p2, lse;
+        softmax3(z0, z1, z2, p0, p1, p2, lse);
+        const int c = y[p];
+        float g0 = (p0 - (c == 0 ? 1.0f : 0.0f)) * invM, g1 = (p1 - (c == 1 ? 1.0f : 0.0f)) * invM, g2 = (p2 - (c == 2 ? 1.0f : 0.0f)) * invM;
+        if (with_dice) {
+            const float dp1 = -0.5f * 1.0f * (2.0f * (c == 1 ? 1.0f : 0.0f) * D1 - 2.0f * p1 * N1) / (D1 * D1);
+            const float dp2 = -0.5f * 2.0f * (2.0f * (c == 2 ? 1.0f : 0.0f) * D2 - 2.0f * p2 * N2) / (D2 * D2);
+            // softmax Jacobian: dz_j = sum_c dp_c * p_c * (delta_cj - p_j)
+            const float t = dp1 * p1 + dp2 * p2;
+            g0 += -p0 * t;
+            g1 += dp1 * p1 - p1 * t;
+            g2 += dp2 * p2 - p2 * t;
+        }
+        g[p] = g0;
+        g[M + p] = g1;
+        g[2 * M + p] = g2;
+    }
+}
+
 // head backward: dy[p][c] = g[p] * w[c];  dw[c] += sum_p g[p] * y[p][c];  dw[C] (= db) += sum_p g[p]
 __global__ void __launch_bounds__(256)
 head_bwd_kernel(const float *__restrict__ g, const __nv_bfloat16 *__restrict__ y, long long M, int C, const float *__restrict__ w,
@@ -667,6 +749,19 @@ extern "C" int mbs_regression_loss(const float *pred, const float *target, long 
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     MBS_REQUIRE(M > 0 && kind >= 0 && kind <= 2, "regression_loss: bad shape / kind");
     smoothl1_kernel<<<grid_for(M, 256 * 8, 148 * 8), 256, 0, stream>>>(pred, target, M, loss_accum, grad, kind);
+    MBS_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int mbs_ce_dice_loss(const float *logits, const uint8_t *labels, long long M, int with_dice, float *loss_accum, float *grad,
+                                double *sums7, void *stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    MBS_REQUIRE(M > 0 && logits && labels && loss_accum && grad && sums7, "ce_dice_loss: bad arguments");
+    MBS_CHECK_CUDA(cudaMemsetAsync(sums7, 0, 7 * sizeof(double), stream));
+    const int grid = grid_for(M, 256 * 8, 148 * 8);
+    ce_dice_sums_kernel<<<grid, 256, 0, stream>>>(logits, labels, M, sums7);
+    MBS_CHECK_LAUNCH();
+    ce_dice_grad_kernel<<<grid, 256, 0, stream>>>(logits, labels, M, with_dice, sums7, loss_accum, grad);
     MBS_CHECK_LAUNCH();
     return 0;
 }

@@ -20,6 +20,7 @@ BN_EPS = 1e-5
 BN_MOMENTUM = 0.1
 ACT_NONE, ACT_RELU, ACT_MISH = 0, 1, 4
 _LOSS_KINDS = {'smooth_l1': 0, 'l1': 1, 'l2': 2}      # get_loss(loss_function, 'distance'), losses.py:24-35
+_BOUNDARY_LOSSES = {'ce': 0, 'ce_dice': 1}           # get_loss(loss_function, 'boundary'), losses.py:16-21 (value = with_dice)
 
 
 class GradBuckets:
@@ -86,12 +87,18 @@ class _Layer:
 
 
 class TrainEngine:
-    """Forward + backward of one DUNet on one GPU; fills ``param.grad`` (fp32) for every parameter."""
+    """Forward + backward of one network on one GPU; fills ``param.grad`` (fp32) for every parameter.
+    Distance method: DUNet with loss 'smooth_l1' | 'l1' | 'l2' (two regression heads); boundary method: UNet with three
+    output classes and loss 'ce' | 'ce_dice' (losses.py:16-21, 71-96)."""
 
     def __init__(self, net, use_graph=True, loss='smooth_l1'):
-        from .unets import DUNet
-        if not isinstance(net, DUNet):
-            raise NotImplementedError("training is built for the DU (distance) network")
+        from .unets import DUNet, UNet
+        self.boundary = loss in _BOUNDARY_LOSSES
+        if self.boundary:
+            if not isinstance(net, UNet) or net.ch_out != 3:
+                raise NotImplementedError("loss 'ce' / 'ce_dice' trains the boundary method: a 'U' network with ch_out=3")
+        elif not isinstance(net, DUNet):
+            raise NotImplementedError("the distance criteria ('smooth_l1', 'l1', 'l2') train the DU (distance) network")
         net._check_supported()
         if net._chans[0] % 64 != 0 or net.pool_method != 'conv' or net.normalization != 'bn':
             raise NotImplementedError("the CUDA training step needs filters[0] % 64 == 0, pool_method 'conv' and normalization "
@@ -104,9 +111,9 @@ class TrainEngine:
         # evaluates mish'(z) -- still one activation-sized tensor per layer
         self.act = ACT_RELU if net.act_fun == "relu" else ACT_MISH
         self.conv_act = ACT_RELU if net.act_fun == "relu" else ACT_NONE
-        if loss not in _LOSS_KINDS:
+        if loss not in _LOSS_KINDS and loss not in _BOUNDARY_LOSSES:
             raise Exception('Loss unknown')                 # get_loss, losses.py:33-34
-        self.loss_kind = _LOSS_KINDS[loss]
+        self.loss_kind = _BOUNDARY_LOSSES[loss] + 16 if self.boundary else _LOSS_KINDS[loss]
         self.net = net
         self.L = nat.lib()
         self.dev = next(net.parameters()).device
@@ -267,8 +274,9 @@ class TrainEngine:
         self.tape.append(lay)
         return lay
 
-    def forward_backward(self, img, border_label, cell_label, world_size=1):
+    def forward_backward(self, img, border_label, cell_label=None, world_size=1):
         """img / labels: [N,1,H,W] float32 CUDA tensors (img normalised to [-1,1] as the reference's ToTensor does).
+        Boundary method: ``border_label`` is the [N,H,W] class image (0 / 1 / 2) and ``cell_label`` stays None.
         Returns the loss (0-d tensor) and leaves the gradients in ``param.grad``.
 
         The first call of a given batch shape runs eagerly (it warms up every kernel configuration and records the
@@ -293,9 +301,10 @@ class TrainEngine:
             t.data_ptr() for t in list(self.net.parameters()) + list(self.net.buffers()))
         st = self._graphs.get(key)
         if st is None:
-            st = {"in": [torch.empty_like(t, dtype=torch.float32) for t in (img, border_label, cell_label)]}
+            st = {"in": [None if t is None else torch.empty_like(t, dtype=torch.float32) for t in (img, border_label, cell_label)]}
             for d, s_ in zip(st["in"], (img, border_label, cell_label)):
-                d.copy_(s_)
+                if d is not None:
+                    d.copy_(s_)
             torch.cuda.synchronize(self.dev)
             self.L.mbs_launch_count(1)
             side = torch.cuda.Stream(self.dev)
@@ -318,7 +327,8 @@ class TrainEngine:
             st["grads"] = [(p, self._buckets.views[p]) for p in self.net.parameters()]
             self._graphs = {key: st}                             # one live capture (its private pool holds every activation)
         for d, s_ in zip(st["in"], (img, border_label, cell_label)):
-            d.copy_(s_)
+            if d is not None:
+                d.copy_(s_)
         for g, k in st["graphs"]:
             g.replay()
             if k is not None and self.world_size > 1:
@@ -370,35 +380,56 @@ class TrainEngine:
                     xcur = lb.y
                 dec[name] = chain
                 head = convs[nl - 1]
-                pred = torch.empty((n, H, W), dtype=torch.float32, device=self.dev)
-                hw = head.weight.detach().float().reshape(-1).contiguous()
-                nat.check(self.L.mbs_head_fwd(xcur.data_ptr(), n * H * W, hw.numel(), hw.data_ptr(), head.bias.data_ptr(),
-                                              pred.data_ptr(), self._sp()), "head_fwd")
+                n_out = head.weight.shape[0]
+                hw = head.weight.detach().float().reshape(n_out, -1).contiguous()
+                pred = torch.empty((n_out, n, H, W), dtype=torch.float32, device=self.dev)      # planar per output channel
+                for k in range(n_out):
+                    nat.check(self.L.mbs_head_fwd(xcur.data_ptr(), n * H * W, hw.shape[1], hw[k].data_ptr(), head.bias[k:k + 1].data_ptr(),
+                                                  pred[k].data_ptr(), self._sp()), "head_fwd")
                 preds.append(pred)
                 heads.append((head, hw))
                 last.append(xcur)
             # ---------------- loss ----------------
             loss = torch.zeros(1, dtype=torch.float32, device=self.dev)
             gpred = []
-            for pred, tgt in zip(preds, targets):
-                g = torch.empty_like(pred)
-                t = tgt.reshape(n, H, W).contiguous().float()
-                nat.check(self.L.mbs_regression_loss(pred.data_ptr(), t.data_ptr(), n * H * W, self.loss_kind, loss.data_ptr(),
-                                                     g.data_ptr(), self._sp()), "regression_loss")
+            if self.boundary:
+                # one 'U' decoder with three class logits; label image with classes 0 / 1 / 2 (train.py:468-470, 483-484)
+                lab8 = border_label.reshape(n, H, W).to(torch.uint8).contiguous()
+                g = torch.empty_like(preds[0])
+                sums = torch.empty(7, dtype=torch.float64, device=self.dev)
+                nat.check(self.L.mbs_ce_dice_loss(preds[0].data_ptr(), lab8.data_ptr(), n * H * W, self.loss_kind - 16, loss.data_ptr(),
+                                                  g.data_ptr(), sums.data_ptr(), self._sp()), "ce_dice_loss")
                 gpred.append(g)
+            else:
+                for pred, tgt in zip(preds, targets):
+                    g = torch.empty_like(pred)
+                    t = tgt.reshape(n, H, W).contiguous().float()
+                    nat.check(self.L.mbs_regression_loss(pred.data_ptr(), t.data_ptr(), n * H * W, self.loss_kind, loss.data_ptr(),
+                                                         g.data_ptr(), self._sp()), "regression_loss")
+                    gpred.append(g)
             # ---------------- backward ----------------
             skip_grads = [[] for _ in range(nl)]          # contributions to d(skip_l)
             bott_grads = []
             for di, name in enumerate(net.decoder_names):
                 head, hw = heads[di]
                 y_last = last[di]
-                c0 = hw.numel()
-                dy = torch.empty_like(y_last)
-                dwdb = torch.empty(c0 + 1, dtype=torch.float32, device=self.dev)
-                nat.check(self.L.mbs_head_bwd(gpred[di].data_ptr(), y_last.data_ptr(), n * H * W, c0, hw.data_ptr(),
-                                              dy.data_ptr(), dwdb.data_ptr(), self._sp()), "head_bwd")
-                self._set_grad(head.weight, dwdb[:c0])
-                self._set_grad(head.bias, dwdb[c0:])
+                n_out, c0 = hw.shape
+                dys, dws = [], []
+                for k in range(n_out):
+                    dyk = torch.empty_like(y_last)
+                    dwdb = torch.empty(c0 + 1, dtype=torch.float32, device=self.dev)
+                    nat.check(self.L.mbs_head_bwd(gpred[di][k].data_ptr(), y_last.data_ptr(), n * H * W, c0, hw[k].data_ptr(),
+                                                  dyk.data_ptr(), dwdb.data_ptr(), self._sp()), "head_bwd")
+                    dys.append(dyk)
+                    dws.append(dwdb)
+                dy = self._sum(dys)
+                if n_out == 1:
+                    self._set_grad(head.weight, dws[0][:c0])
+                    self._set_grad(head.bias, dws[0][c0:])
+                else:
+                    stacked = torch.stack(dws)
+                    self._set_grad(head.weight, stacked[:, :c0].contiguous())
+                    self._set_grad(head.bias, stacked[:, c0].contiguous())
                 for (lu, la, lb, l) in reversed(dec[name]):
                     dy = self._bwd_conv(lb, dy)[0]
                     dup, dskip = self._bwd_conv(la, dy)
@@ -542,7 +573,7 @@ def broadcast_module_state(net, src=0):
     nat.note_raw_write()
 
 
-def train_step(engine, optimizer, img, border_label, cell_label, world_size=1):
+def train_step(engine, optimizer, img, border_label, cell_label=None, world_size=1):
     """One optimisation step as in train.py:473-493 (zero_grad, forward, loss, backward, step)."""
     optimizer.zero_grad(set_to_none=True)
     loss = engine.forward_backward(img, border_label, cell_label, world_size)

@@ -243,3 +243,23 @@ def dunet_train_loss(params, x, border_label, cell_label, act="relu", loss="smoo
         outs.append(F.conv2d(y, params[f"{name}Conv.{k}.weight"], params[f"{name}Conv.{k}.bias"]))
     crit = {'smooth_l1': torch.nn.SmoothL1Loss, 'l1': torch.nn.L1Loss, 'l2': torch.nn.MSELoss}[loss]()      # losses.py:24-35
     return crit(outs[0], border_label) + crit(outs[1], cell_label)
+
+
+def unet_train_loss(params, x, label, act="relu", loss="ce_dice"):
+    """boundary method: 'U' net (one decoder, 3 class logits) in train() mode + ce / ce_dice (train.py:483-484)"""
+    from . import losses as ol
+    nl = n_levels(params)
+    skips = []
+    for i in range(nl - 1):
+        x = _conv_block_train(x, params, f"encoderConv.{i}", act)
+        skips.append(x)
+        x = F.conv2d(x, params[f"pooling.{i}.conv_pool.0.weight"], params[f"pooling.{i}.conv_pool.0.bias"], stride=2, padding=1)
+        x = _bn_train(_act(x, act), params, f"pooling.{i}.conv_pool.2")
+    y = _conv_block_train(x, params, f"encoderConv.{nl - 1}", act)
+    for i, sk in enumerate(skips[::-1]):
+        y = F.conv_transpose2d(y, params[f"decoderUpconv.{i}.up.0.weight"], params[f"decoderUpconv.{i}.up.0.bias"], stride=2)
+        y = _bn_train(y, params, f"decoderUpconv.{i}.norm")
+        y = _conv_block_train(torch.cat([y, sk], 1), params, f"decoderConv.{i}", act)
+    k = len(skips)
+    logits = F.conv2d(y, params[f"decoderConv.{k}.weight"], params[f"decoderConv.{k}.bias"])
+    return ol.boundary_loss(logits, label, loss)

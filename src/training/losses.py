@@ -1,17 +1,35 @@
 """Drop-in module path of the reference (`from src.training.losses import get_loss`, train.py:18).
 
-The CUDA training step evaluates the distance-method criteria itself (`TrainEngine(net, loss='smooth_l1' | 'l1' | 'l2')`,
-`mbs_regression_loss`); this function keeps the reference's return type for callers that only inspect it."""
+The CUDA training step evaluates the criteria itself: `TrainEngine(net, loss='smooth_l1' | 'l1' | 'l2')` for the distance
+method (`mbs_regression_loss`) and `TrainEngine(net, loss='ce' | 'ce_dice')` for the boundary method (`mbs_ce_dice_loss`,
+losses.py:16-21, 71-96).  This function keeps the reference's return types for callers that only inspect them; the
+returned objects carry the name the engine expects in `.mbs_loss`."""
 import torch.nn as nn
 
 
+class _BoundaryCriterion:
+    """tag object for the boundary method: the CUDA step computes the loss and its gradient (`mbs_ce_dice_loss`)"""
+
+    def __init__(self, name):
+        self.mbs_loss = name
+
+    def __call__(self, y_pred, y_true):
+        raise RuntimeError("microbeseg_b200: boundary criteria run inside TrainEngine(net, loss=%r) on the CUDA path "
+                           "(no autograd / CPU fallback)" % self.mbs_loss)
+
+
 def get_loss(loss_function, label_type):
-    """losses.py:6-37 for the distance method (the boundary method's ce / ce_dice are not built)."""
+    """losses.py:6-37"""
+    if label_type == 'boundary':
+        if loss_function not in ('ce_dice', 'ce'):
+            raise Exception('Loss unknown')
+        return _BoundaryCriterion(loss_function)
     if label_type == 'distance':
         table = {'l1': nn.L1Loss, 'l2': nn.MSELoss, 'smooth_l1': nn.SmoothL1Loss}
         if loss_function not in table:
             raise Exception('Loss unknown')
-        return {'border': table[loss_function](), 'cell': table[loss_function]()}
-    if label_type == 'boundary':
-        raise NotImplementedError("training losses of the boundary method (ce, ce_dice) are not built")
-    raise Exception('Loss unknown')
+        crit = {'border': table[loss_function](), 'cell': table[loss_function]()}
+        for c in crit.values():
+            c.mbs_loss = loss_function
+        return crit
+    raise UnboundLocalError("local variable 'criterion' referenced before assignment")      # what the reference does for other label types

@@ -4,6 +4,7 @@
   python tests/golden/make_golden.py net          # the REAL reference DUNet (/root/reference) on CPU
   python tests/golden/make_golden.py labels       # oracle/labels.py on seeded synthetic instance masks
   python tests/golden/make_golden.py ranger       # the REAL reference Ranger optimizer (/root/reference) on CPU
+  python tests/golden/make_golden.py losses       # the REAL reference ce_dice / CrossEntropyLoss (/root/reference) on CPU
 
 The post-processing goldens are produced by the oracle restatement (scikit-image cannot run in
 this image -> "parity unpinned" for the skimage pieces, see oracle/postproc.py); the network
@@ -124,8 +125,34 @@ def make_ranger():
         print("ranger", name, "final |p0|", float(np.abs(out[f"s{RANGER_STEPS}_p0"]).mean()))
 
 
+def make_losses():
+    """loss value and dloss/dlogits of the boundary-method criteria from the reference's own losses.py (torch autograd, fp32)"""
+    import importlib.util
+    import torch
+    spec = importlib.util.spec_from_file_location("reference_losses", "/root/reference/src/training/losses.py")
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    for seed, (n, h, w) in enumerate([(2, 24, 40), (3, 33, 17)]):
+        rng = np.random.default_rng(8100 + seed)
+        logits = (rng.standard_normal((n, 3, h, w)) * 2.0).astype(np.float32)
+        labels = rng.integers(0, 3, (n, h, w)).astype(np.int64)
+        labels[0, :4] = 0                                         # a stretch of pure background
+        out = {"logits": logits, "labels": labels}
+        for kind in ("ce_dice", "ce"):
+            crit = mod.get_loss(kind, "boundary")
+            z = torch.from_numpy(logits).clone().requires_grad_(True)
+            loss = crit(z, torch.from_numpy(labels))
+            loss.backward()
+            out[kind + "_loss"] = np.float32(loss.item())
+            out[kind + "_grad"] = z.grad.numpy().copy()
+        np.savez_compressed(os.path.join(HERE, f"ce_dice_s{seed}.npz"), **out)
+        print("losses", seed, float(out["ce_dice_loss"]), float(out["ce_loss"]))
+
+
 if __name__ == "__main__":
-    what = sys.argv[1:] or ["postproc", "net", "labels", "ranger"]
+    what = sys.argv[1:] or ["postproc", "net", "labels", "ranger", "losses"]
+    if "losses" in what:
+        make_losses()
     if "ranger" in what:
         make_ranger()
     if "postproc" in what:

@@ -191,4 +191,69 @@ def test_other_distance_criteria(native_lib, loss):
             r = params[name].grad
             assert torch.allclose(p.grad, r, rtol=0.1, atol=0.05 * float(r.abs().max()) + 1e-4), (name, p.grad, r)
     with pytest.raises(Exception):
-        TrainEngine(net, loss="ce")
+        TrainEngine(net, loss="ce")                                     # boundary criteria need the 'U' net
+    with pytest.raises(Exception):
+        TrainEngine(net, loss="huber")
+
+
+def test_boundary_criteria_kernel_vs_reference_fixtures(native_lib):
+    """mbs_ce_dice_loss (loss value + dloss/dlogits) against fixtures produced by the REAL reference losses.py
+    (ce_dice :71-96, nn.CrossEntropyLoss :19-20): fp32 with different summation order -> rtol 2e-5."""
+    import glob
+    from microbeseg_b200 import _native as nat
+    files = sorted(glob.glob(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ce_dice_*.npz")))
+    assert len(files) >= 2
+    for f in files:
+        g = np.load(f)
+        n, _, h, w = g["logits"].shape
+        M = n * h * w
+        z = torch.from_numpy(np.ascontiguousarray(g["logits"].transpose(1, 0, 2, 3))).cuda()       # planar [3][N*H*W]
+        lab = torch.from_numpy(g["labels"].astype(np.uint8)).cuda()
+        for kind, with_dice in (("ce_dice", 1), ("ce", 0)):
+            loss = torch.zeros(1, device="cuda")
+            grad = torch.empty_like(z)
+            sums = torch.empty(7, dtype=torch.float64, device="cuda")
+            nat.check(native_lib.mbs_ce_dice_loss(z.data_ptr(), lab.data_ptr(), M, with_dice, loss.data_ptr(), grad.data_ptr(),
+                                                  sums.data_ptr(), nat.stream_ptr()), "ce_dice_loss")
+            ref_l, ref_g = float(g[kind + "_loss"]), g[kind + "_grad"].transpose(1, 0, 2, 3)
+            assert abs(float(loss) - ref_l) <= 2e-5 * abs(ref_l), (kind, float(loss), ref_l)
+            got = grad.cpu().numpy()
+            assert np.allclose(got, ref_g, rtol=2e-4, atol=2e-6 * np.abs(ref_g).max()), (kind, np.abs(got - ref_g).max())
+
+
+@pytest.mark.parametrize("loss", ["ce_dice", "ce"])
+def test_boundary_method_training_step(native_lib, loss):
+    """'U' net with three class logits (the boundary method, train.py:468-484): loss within 2e-2 of the fp32 torch-autograd
+    reference of the same graph, head gradients close, a few Adam steps reduce the loss"""
+    from microbeseg_b200.adam import Adam
+    from microbeseg_b200.training import TrainEngine, train_step
+    from microbeseg_b200.unets import build_unet
+    filters = (64, 128)
+    net = build_unet("U", "relu", "conv", "bn", torch.device("cuda:0"), 1, ch_in=1, ch_out=3, filters=list(filters))
+    sd = onet.seeded_state_dict(onet.reference_layout_template("U", filters, ch_out=3), 17)
+    net.load_state_dict(sd)
+    net.train()
+    rng = np.random.default_rng(17)
+    img = torch.from_numpy(rng.uniform(-1, 1, (2, 1, 32, 48)).astype(np.float32)).cuda()
+    lab = torch.from_numpy(rng.integers(0, 3, (2, 32, 48)).astype(np.int64)).cuda()
+    eng = TrainEngine(net, use_graph=False, loss=loss)
+    got = float(eng.forward_backward(img, lab))
+    params = {k: v.clone().cuda().requires_grad_(v.dtype.is_floating_point and "running" not in k) for k, v in sd.items()
+              if v.dtype.is_floating_point}
+    with torch.enable_grad():
+        ref = onet.unet_train_loss(params, img, lab, "relu", loss)
+        ref.backward()
+    assert abs(got - float(ref.detach())) <= 2e-2 * abs(float(ref.detach())), (got, float(ref.detach()))
+    for name, p in net.named_parameters():
+        assert p.grad is not None and torch.isfinite(p.grad).all(), name
+        if name.startswith("decoderConv.1."):                          # the 1x1 head (3 x 64 weights, 3 biases)
+            r = params[name].grad
+            rel = float((p.grad - r).norm() / (r.norm() + 1e-12))
+            assert rel < 0.05, (name, rel)
+    opt = Adam(net.parameters(), lr=8e-4, amsgrad=True)
+    eng2 = TrainEngine(net, use_graph=True, loss=loss)
+    with torch.enable_grad():
+        losses = [float(train_step(eng2, opt, img, lab)) for _ in range(10)]
+    assert all(np.isfinite(losses)) and losses[-1] < losses[0], losses
+    with pytest.raises(NotImplementedError):
+        TrainEngine(net, loss="smooth_l1")                             # distance criteria need the DU net
