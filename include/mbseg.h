@@ -255,6 +255,23 @@ int mbs_distance_postprocessing_sweep(const float *border, const float *cell, in
 int mbs_ce_dice_loss(const float *logits, const uint8_t *labels, long long M, int with_dice, float *loss_accum, float *grad,
                      double *sums7, void *stream);
 
+/*
+ * fp32 check mode: one convolution of the network as a plain CUDA-core fp32 direct convolution, no bf16,
+ * no tensor cores.  Same operators as mbs_conv_gemm (Conv2d 3x3 s1 / s2, ConvTranspose2d 2x2 s2, 1x1 head; bias, activation,
+ * folded eval BatchNorm; torch.cat as two sources), float32 NHWC in and out, weights float32 [tap][Cin][Cout].
+ * mode: 0 = 3x3 s1, 1 = 3x3 s2, 2 = transposed 2x2 s2, 4 = 1x1.  Diagnostic path (microbeseg_b200.unets.forward_check_fp32).
+ */
+typedef struct {
+    int mode, N, H, W;
+    const float *src0; int C0;
+    const float *src1; int C1;
+    const float *weight; int Cout;
+    const float *bias, *scale, *shift;       /* scale / shift may be NULL (identity) */
+    int act;
+    float *dst;
+} mbs_convref_desc;
+int mbs_conv_ref_f32(const mbs_convref_desc *d, void *stream);
+
 /* ---------------------------------------------------------------------------------------- */
 /* mask -> polygon ROI encoding                                           */
 /* ---------------------------------------------------------------------------------------- */

@@ -40,6 +40,14 @@ class ConvDesc(ctypes.Structure):
                 ("head_w", c_void_p), ("head_b", c_float * 4), ("head_n", c_int), ("head_out", c_void_p)]
 
 
+class ConvRefDesc(ctypes.Structure):
+    """mirror of mbs_convref_desc (include/mbseg.h): fp32 check mode"""
+    _fields_ = [("mode", c_int), ("N", c_int), ("H", c_int), ("W", c_int),
+                ("src0", c_void_p), ("C0", c_int), ("src1", c_void_p), ("C1", c_int),
+                ("weight", c_void_p), ("Cout", c_int),
+                ("bias", c_void_p), ("scale", c_void_p), ("shift", c_void_p), ("act", c_int), ("dst", c_void_p)]
+
+
 class RangerTensor(ctypes.Structure):
     """mirror of mbs_ranger_tensor (include/mbseg.h)"""
     _fields_ = [("p", c_void_p), ("g", c_void_p), ("exp_avg", c_void_p), ("exp_avg_sq", c_void_p), ("slow", c_void_p),
@@ -105,6 +113,7 @@ _SIGS = {
     "mbs_pp_watershed": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_size_t, c_void_p,
                                  c_int, c_void_p]),
     "mbs_instance_stats": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "mbs_conv_ref_f32": (c_int, [ctypes.POINTER(ConvRefDesc), c_void_p]),
     "mbs_contour_first": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     "mbs_contour_trace": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
 }

@@ -2415,9 +2415,8 @@ int coop_config(CoopCfg **out) {
         MBS_CHECK_CUDA(cudaFuncSetAttribute(flood_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FLOOD_SMEM16));
         MBS_CHECK_CUDA(cudaFuncSetAttribute(flood_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FLOOD_SMEM32));
         MBS_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, mid_kernel, 256, 0));
-        // list / seam / bitmap work of a few hundred thousand items between five grid barriers: a small grid keeps the
-        // barriers cheap
-        c.mid_blocks = sms * (per > 2 ? 2 : (per > 0 ? per : 1));
+        // a full grid: the phases are latency bound (measured at 4096^2: 1184 blocks 74 us, 296 blocks 102 us)
+        c.mid_blocks = sms * (per > 0 ? per : 1);
         if (c.mid_blocks > MID_MAX_BLOCKS) c.mid_blocks = MID_MAX_BLOCKS;
         MBS_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, flood_kernel<false>, 256, FLOOD_SMEM16));
         c.flood16_blocks = sms * (per > 0 ? per : 1);

@@ -172,8 +172,11 @@ class TrainEngine:
         if cap is not None:
             cap["cur"].capture_end()
             cap["graphs"].append((cap["cur"], k))
-            cap["cur"] = torch.cuda.CUDAGraph()
-            cap["cur"].capture_begin(pool=cap["pool"])
+            if k + 1 < len(self._buckets.ranges):
+                cap["cur"] = torch.cuda.CUDAGraph()
+                cap["cur"].capture_begin(pool=cap["pool"])
+            else:
+                cap["cur"] = None                     # the last gradient of the step: nothing is launched after it
         elif self.world_size > 1:
             self._buckets.allreduce(k, self.world_size)
 
@@ -317,8 +320,10 @@ class TrainEngine:
                     st["loss"] = self._forward_backward(*st["in"])
                 finally:
                     self._capture = None
-                    cap["cur"].capture_end()
-                cap["graphs"].append((cap["cur"], None))
+                    if cap["cur"] is not None:
+                        cap["cur"].capture_end()
+                if cap["cur"] is not None:
+                    cap["graphs"].append((cap["cur"], None))
             torch.cuda.current_stream(self.dev).wait_stream(side)
             st["graphs"] = cap["graphs"]
             st["launches"] = int(self.L.mbs_launch_count(0))     # kernels of this library inside one replay of all graphs

@@ -131,6 +131,83 @@ class _NetBase(nn.Module):
             self._engine_key = key
         return self._engine
 
+    # -- fp32 check mode -------------------------------------------------------------------------
+    @torch.no_grad()
+    def forward_check_fp32(self, x):
+        """The eval-mode forward with every convolution as a plain CUDA-core fp32 direct convolution (``mbs_conv_ref_f32``:
+        no bf16, no tensor cores) through the SAME layer plan as the product engine.  Diagnostic only (~1 s per 2048^2
+        frame): against the fp32 oracle it checks the plan to ~1e-6 at full frame size; the bf16 product path compared
+        with it shows the precision policy alone (SURVEY.md 8(c) "fp32 check mode").  BatchNorm networks only.
+        ``x``: normalised [N,1,H,W] float CUDA tensor.  Returns the list of head maps [N,ch,H,W] float32."""
+        if self.training:
+            raise RuntimeError("forward_check_fp32 is the eval-mode forward")
+        if not x.is_cuda or self.normalization != 'bn' or self.pool_method != 'conv':
+            raise NotImplementedError("fp32 check mode: CUDA tensors, pool_method 'conv', normalization 'bn'")
+        L = nat.lib()
+        act = _ACT_CODES[self.act_fun]
+        n, _, H, W = x.shape
+        nl = len(self._chans)
+        if H % (1 << (nl - 1)) or W % (1 << (nl - 1)):
+            raise RuntimeError(f"model input {H}x{W} is not divisible by {1 << (nl - 1)}")
+        dev = x.device
+
+        def conv(mode, src0, src1, weight, bias, bn, a, h, w):
+            if mode == 2:
+                wt = weight.detach().float().permute(2, 3, 0, 1).reshape(4, weight.shape[0], weight.shape[1]).contiguous()
+                cout, ho, wo = weight.shape[1], 2 * h, 2 * w
+            else:
+                k = weight.shape[2]
+                wt = weight.detach().float().permute(2, 3, 1, 0).reshape(k * k, weight.shape[1], weight.shape[0]).contiguous()
+                cout = weight.shape[0]
+                ho, wo = (h // 2, w // 2) if mode == 1 else (h, w)
+            d = nat.ConvRefDesc()
+            d.mode, d.N, d.H, d.W = mode, n, h, w
+            d.src0, d.C0 = src0.data_ptr(), src0.shape[-1]
+            d.src1, d.C1 = (src1.data_ptr(), src1.shape[-1]) if src1 is not None else (None, 0)
+            d.weight, d.Cout = wt.data_ptr(), cout
+            b = bias.detach().float().contiguous()
+            d.bias = b.data_ptr()
+            keep = [wt, b]
+            if bn is not None:
+                scale = (bn.weight.float() / torch.sqrt(bn.running_var.float() + bn.eps)).contiguous()
+                shift = (bn.bias.float() - bn.running_mean.float() * scale).contiguous()
+                d.scale, d.shift = scale.data_ptr(), shift.data_ptr()
+                keep += [scale, shift]
+            else:
+                d.scale, d.shift = None, None
+            d.act = a
+            out = torch.empty((n, ho, wo, cout), dtype=torch.float32, device=dev)
+            d.dst = out.data_ptr()
+            nat.check(L.mbs_conv_ref_f32(ctypes.byref(d), nat.stream_ptr()), "conv_ref_f32")
+            return out
+
+        with torch.cuda.device(dev):
+            cur = x.float().permute(0, 2, 3, 1).contiguous()                 # NHWC, C = 1
+            skips = []
+            for l in range(nl):
+                blk = self.encoderConv[l].conv
+                cur = conv(0, cur, None, blk[0].weight, blk[0].bias, blk[2], act, H >> l, W >> l)
+                cur = conv(0, cur, None, blk[3].weight, blk[3].bias, blk[5], act, H >> l, W >> l)
+                skips.append(cur)
+                if l < nl - 1:
+                    pl = self.pooling[l].conv_pool
+                    cur = conv(1, cur, None, pl[0].weight, pl[0].bias, pl[2], act, H >> l, W >> l)
+            outs = []
+            for name in self.decoder_names:
+                ups, convs = getattr(self, name + "Upconv"), getattr(self, name + "Conv")
+                y = skips[nl - 1]
+                for i in range(nl - 1):
+                    l = nl - 2 - i
+                    up = conv(2, y, None, ups[i].up[0].weight, ups[i].up[0].bias, ups[i].norm, 0, H >> (l + 1), W >> (l + 1))
+                    blk = convs[i].conv
+                    y = conv(0, up, skips[l], blk[0].weight, blk[0].bias, blk[2], act, H >> l, W >> l)     # cat([up, skip], 1)
+                    y = conv(0, y, None, blk[3].weight, blk[3].bias, blk[5], act, H >> l, W >> l)
+                head = convs[nl - 1]
+                o = conv(4, y, None, head.weight, head.bias, None, 0, H, W)
+                outs.append(o.permute(0, 3, 1, 2).contiguous())
+            torch.cuda.current_stream(dev).synchronize()                      # the temporaries above stay alive until here
+        return outs
+
     def _check_supported(self):
         if self.pool_method not in ('conv', 'max') or self.normalization not in ('bn', 'gn', 'in'):
             raise NotImplementedError(

@@ -421,6 +421,30 @@ def test_full_network_at_baseline_sizes_vs_fp32_oracle(native_lib, size, seed):
     assert native_lib.mbs_debug_flags(1) == 0
 
 
+@pytest.mark.parametrize("filters,act,size", [((64, 1024), "relu", 1024), ((64, 256), "mish", 256)])
+def test_fp32_check_mode_matches_the_fp32_oracle(native_lib, filters, act, size):
+    """SURVEY 8(c) "fp32/TF32-free check mode": the product's layer plan with every convolution as a plain CUDA-core fp32
+    direct convolution (net.forward_check_fp32) against the fp32 oracle on BASELINE config 1 (1024^2): max |err| <=
+    1e-4 * scale (measured ~1e-5: summation order only).  This separates the two error sources: plan / wiring errors
+    would show here at full frame size, the bf16 policy shows in test_full_network_at_baseline_sizes_vs_fp32_oracle."""
+    from microbeseg_b200 import synthetic as sy
+    torch.set_grad_enabled(False)
+    net, sd = _build(filters, act, 23)
+    img = sy.synth_frame(size, size, 1234)
+    x = torch.from_numpy(_norm(img)[None, None])
+    ob, oc = onet.dunet_forward(sd, x, act)
+    cb, cc = net.forward_check_fp32(x.cuda())
+    rows = _err_rows((("border", cb, ob), ("cell", cc, oc)))
+    print(f"\nfp32 check mode {filters} {act} {size}^2 vs fp32 oracle: {rows}")
+    for r in rows:
+        assert r["max"] <= 1e-4 * r["scale"], r
+    b, c = net(x.cuda())                       # and the bf16 product path against the check mode: the policy error alone
+    for got, ref in ((b, cb), (c, cc)):
+        e = (got - ref).abs()
+        scale = max(1.0, float(ref.abs().max()))
+        assert float(e.max()) <= 3e-2 * scale and float(e.mean()) <= 4e-3 * scale
+
+
 def test_instance_level_agreement_with_fp32_reference_path(native_lib):
     """north_star: the bf16 CUDA path and the fp32 reference path must agree at instance level (stated threshold:
     mean AP@0.5 >= 0.99, matched mean IoU >= 0.95 per frame; map errors on these O(1) maps: max <= 5e-2,
