@@ -170,13 +170,26 @@ int mbs_head_bwd(const float *g, const void *y, long long M, int C, const float 
 /* layout / glue kernels of the backward pass */
 /* data-gradient filter of a 3x3 conv: packed[ci][tap][co] = bf16(w[co][ci][8 - tap]) from the reference-layout weight */
 int mbs_pack_conv3x3_dgrad(const float *w, int Cout, int Cin, void *packed, void *stream);
+/* Every GEMM-packed bf16 weight of one training step in ONE launch (replaces the per-layer mbs_pack_* calls inside the
+ * reference's step, src/training/train.py:473-493, where cuDNN re-reads the fp32 weights itself).  One job per layer:
+ *   kind 0, Conv2d 3x3        w[cout][cin][3][3]: fwd[co][tap][ci] = w[co][ci][tap], dgrad[ci][tap][co] = w[co][ci][8 - tap]
+ *   kind 1, ConvTranspose 2x2 w[cin][cout][2][2]: fwd[q*cout + co][ci] = w[ci][co][q], dgrad[ci][q][co] = w[ci][co][q]
+ * cout and cin multiples of 32; fwd / dgrad may be NULL; one CTA per 32 x 32 channel tile, tile0 = prefix sum of the
+ * jobs' tile counts (cout/32 * cin/32), total_tiles = their sum.  jobs_dev: DEVICE array. */
+typedef struct {
+    const void *w;
+    void *fwd, *dgrad;
+    int cout, cin, kind, tile0;
+} mbs_pack_job;
+int mbs_pack_train_weights(const mbs_pack_job *jobs_dev, int n_jobs, int total_tiles, void *stream);
 /* weight gradient g[co][tap][ci] (mbs_conv_wgrad layout) -> reference layout out[co][ci][3][3] */
 int mbs_unpack_conv3x3_grad(const float *g, int Cout, int Cin, float *out, void *stream);
 /* nn.MaxPool2d(2, 2) on contiguous NHWC bf16 (build_unet pool_method = 'max', unets.py:306-307,363-364) */
 int mbs_maxpool2x2(const void *src, int N, int H, int W, int C, void *dst, void *stream);
 int mbs_zero_insert_up2(const void *src, int N, int H, int W, int C, void *dst, void *stream);
 int mbs_add3_bf16(const void *a, const void *b, const void *c, long long n, void *out, void *stream);
-int mbs_first_conv_wgrad(const float *x, const void *dz, int N, int H, int W, int C, float *dw, void *stream);
+/* scratch: >= 592 * C * 9 floats (mbs_bn_scratch_floats(2048) is enough); per-block partial sums, reduced in a fixed order */
+int mbs_first_conv_wgrad(const float *x, const void *dz, int N, int H, int W, int C, float *dw, float *scratch, void *stream);
 /* weight gradient on the tensor cores, straight from the NHWC bf16 activations (no layout copies):
  *   out[m][tap][out_coff + n] += sum over pixels o of a[sA*o + offA(tap)][m] * b[sB*o + offB(tap)][n]
  * kind 0/1: conv3x3 stride 1/2 -- a = dz [N,Ho,Wo,Cm], b = x [N,s*Ho,s*Wo,Cn] (autograd of unets.py:112-134,

@@ -62,6 +62,12 @@ class WgradDesc(ctypes.Structure):
                 ("out", c_void_p), ("out_ld", c_int), ("out_coff", c_int)]
 
 
+class PackJob(ctypes.Structure):
+    """mirror of mbs_pack_job (include/mbseg.h)"""
+    _fields_ = [("w", c_void_p), ("fwd", c_void_p), ("dgrad", c_void_p), ("cout", c_int), ("cin", c_int), ("kind", c_int),
+                ("tile0", c_int)]
+
+
 _SIGS = {
     "mbs_last_error": (ctypes.c_char_p, []),
     "mbs_version": (c_int, []),
@@ -90,6 +96,7 @@ _SIGS = {
     "mbs_bn_train_fwd": (c_int, [c_void_p, ctypes.c_longlong, c_int, c_void_p, c_void_p, c_float, c_void_p, c_void_p,
                                  c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     "mbs_pack_conv3x3_dgrad": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p]),
+    "mbs_pack_train_weights": (c_int, [c_void_p, c_int, c_int, c_void_p]),
     "mbs_unpack_conv3x3_grad": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "mbs_bn_train_bwd": (c_int, [c_void_p, c_void_p, ctypes.c_longlong, c_int, c_void_p, c_void_p, c_void_p, c_int,
                                  c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
@@ -104,7 +111,7 @@ _SIGS = {
     "mbs_maxpool2x2": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "mbs_zero_insert_up2": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "mbs_add3_bf16": (c_int, [c_void_p, c_void_p, c_void_p, ctypes.c_longlong, c_void_p, c_void_p]),
-    "mbs_first_conv_wgrad": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "mbs_first_conv_wgrad": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "mbs_conv_wgrad": (c_int, [ctypes.POINTER(WgradDesc), c_void_p]),
     "mbs_ranger_step": (c_int, [c_void_p, c_int, c_int, c_float, c_float, c_float, c_float, c_float, c_int, c_int, c_float,
                                 c_void_p]),

@@ -183,28 +183,51 @@ __global__ void __launch_bounds__(256) reduce_partials_kernel(const float *__res
     }
 }
 
-// also turns the sums scratch into the affine of the apply pass: sums[c] = gamma*invstd, sums[C+c] = beta - mean*gamma*invstd
-// and updates the running statistics like nn.BatchNorm2d.forward in training mode (unbiased variance, momentum).
-__global__ void bn_finalize_kernel(float *sums, long long M, int C, float eps, const float *__restrict__ gamma,
-                                   const float *__restrict__ beta, float *mean, float *invstd, float momentum,
-                                   float *running_mean, float *running_var, long long *num_batches_tracked) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= C) return;
-    const double m = static_cast<double>(sums[c]) / static_cast<double>(M);
-    double var = static_cast<double>(sums[C + c]) / static_cast<double>(M) - m * m;
+// reduce_partials_kernel (both accumulators of 32 channels per CTA, same summation order) + bn_finalize_kernel in one
+// launch: part[b][2][C] per-block sums -> sums[c] = gamma*invstd, sums[C+c] = beta - mean*gamma*invstd, mean, invstd and
+// the running statistics.
+__global__ void __launch_bounds__(256)
+bn_reduce_finalize_kernel(const float *__restrict__ part, int nblocks, float *sums, long long M, int C, float eps,
+                          const float *__restrict__ gamma, const float *__restrict__ beta, float *mean, float *invstd, float momentum,
+                          float *running_mean, float *running_var, long long *num_batches_tracked) {
+    __shared__ float s_part[2][8][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int c = blockIdx.x * 32 + tx;
+    const int n = 2 * C;
+#pragma unroll
+    for (int a = 0; a < 2; ++a) {
+        const int i = a * C + c;
+        float s0 = 0.0f, s1 = 0.0f;
+        if (c < C) {
+            int b = ty;
+            for (; b + 8 < nblocks; b += 16) {
+                s0 += part[static_cast<size_t>(b) * n + i];
+                s1 += part[static_cast<size_t>(b + 8) * n + i];
+            }
+            if (b < nblocks) s0 += part[static_cast<size_t>(b) * n + i];
+        }
+        s_part[a][ty][tx] = s0 + s1;
+    }
+    __syncthreads();
+    if (ty != 0 || c >= C) return;
+    float t0 = 0.0f, t1 = 0.0f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { t0 += s_part[0][k][tx]; t1 += s_part[1][k][tx]; }
+    const double m = static_cast<double>(t0) / static_cast<double>(M);
+    double var = static_cast<double>(t1) / static_cast<double>(M) - m * m;
     if (var < 0.0) var = 0.0;
-    mean[c] = static_cast<float>(m);
-    invstd[c] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+    const float mf = static_cast<float>(m), isf = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+    mean[c] = mf;
+    invstd[c] = isf;
     if (running_mean) {
         const float var_u = static_cast<float>(M > 1 ? var * static_cast<double>(M) / static_cast<double>(M - 1) : var);
-        // the two-step form of running.mul_(1 - momentum).add_(stat, alpha=momentum)
-        running_mean[c] = running_mean[c] * (1.0f - momentum) + mean[c] * momentum;
+        running_mean[c] = running_mean[c] * (1.0f - momentum) + mf * momentum;
         running_var[c] = running_var[c] * (1.0f - momentum) + var_u * momentum;
         if (c == 0 && num_batches_tracked) *num_batches_tracked += 1;
     }
-    const float k = gamma[c] * invstd[c];
+    const float k = gamma[c] * isf;
     sums[c] = k;
-    sums[C + c] = fmaf(-mean[c], k, beta[c]);
+    sums[C + c] = fmaf(-mf, k, beta[c]);
 }
 
 // GroupNorm(groups, C) / InstanceNorm2d(C) of ONE sample in eval mode (unets.py:129-132): statistics over the sample's own
@@ -339,19 +362,26 @@ bn_bwd_apply_kernel(const __nv_bfloat16 *__restrict__ dy, const __nv_bfloat16 *_
     block_channel_atomic<1, true>(acc, C, threadIdx.x < ppb * tpp ? c0 : C, dbias);
 }
 
-// 1x1 head forward: pred[p] = sum_c y[p][c] * w[c] + b
-__global__ void head_fwd_kernel(const __nv_bfloat16 *__restrict__ y, long long M, int C, const float *__restrict__ w,
-                                const float *__restrict__ b, float *__restrict__ pred) {
-    const long long p = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (p >= M) return;
-    float acc = 0.0f;
-    const __nv_bfloat162 *row = reinterpret_cast<const __nv_bfloat162 *>(y + p * C);
-    for (int c = 0; c < C / 2; ++c) {
-        const __nv_bfloat162 v = row[c];
-        acc = fmaf(__bfloat162float(v.x), w[2 * c], acc);
-        acc = fmaf(__bfloat162float(v.y), w[2 * c + 1], acc);
+// 1x1 head forward: pred[p] = sum_c y[p][c] * w[c] + b.  C/8 consecutive lanes share a pixel (16-byte loads, a warp
+// reads 512 contiguous bytes) and combine with shuffles; C/8 must be a power of two <= 32.
+__global__ void __launch_bounds__(256) head_fwd_kernel(const __nv_bfloat16 *__restrict__ y, long long M, int C, const float *__restrict__ w,
+                                                       const float *__restrict__ b, float *__restrict__ pred) {
+    const int tpp = C / 8, c0 = (threadIdx.x % tpp) * 8, ppb = 256 / tpp;
+    float wv[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) wv[j] = w[c0 + j];
+    const float bias = b[0];
+    for (long long p = static_cast<long long>(blockIdx.x) * ppb + threadIdx.x / tpp; p < M; p += static_cast<long long>(gridDim.x) * ppb) {
+        Bf16x8 v;
+        v.raw = ldg16(y + p * C + c0);
+        float f[8];
+        v.unpack(f);
+        float acc = 0.0f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc = fmaf(f[j], wv[j], acc);
+        for (int o = tpp >> 1; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (c0 == 0) pred[p] = acc + bias;
     }
-    pred[p] = acc + b[0];
 }
 
 // The distance-method criteria of losses.py:24-35 with reduction 'mean': loss += sum / M and g = dloss/dpred.
@@ -527,6 +557,68 @@ __global__ void __launch_bounds__(256) pack_dgrad3x3_kernel(const float *__restr
     }
 }
 
+// Every GEMM-packed bf16 weight of one training step in ONE launch (the per-layer pack kernels cost ~90 launches and
+// 1.2 ms per step, mostly strided 2-byte writes).  A job is one conv layer; a CTA owns a 32 x 32 (co, ci) tile of it,
+// reads the fp32 reference-layout weight once (runs of 32*taps floats) and writes both packed forms in 64-byte runs:
+//   conv3x3  w[co][ci][3][3]:  fwd[co][t][ci] = w[co][ci][t]        dgrad[ci][t][co] = w[co][ci][8 - t]
+//   convT2x2 w[ci][co][2][2]:  fwd[q*Cout + co][ci] = w[ci][co][q]  dgrad[ci][q][co] = w[ci][co][q]
+__global__ void __launch_bounds__(256) pack_train_weights_kernel(const mbs_pack_job *__restrict__ jobs, int n_jobs) {
+    __shared__ float tile[32][32 * 9 + 1];
+    int j = 0;
+    while (j + 1 < n_jobs && static_cast<int>(blockIdx.x) >= jobs[j + 1].tile0) ++j;
+    const mbs_pack_job job = jobs[j];
+    const int local = static_cast<int>(blockIdx.x) - job.tile0;
+    const float *__restrict__ w = static_cast<const float *>(job.w);
+    __nv_bfloat16 *fwd = static_cast<__nv_bfloat16 *>(job.fwd), *dg = static_cast<__nv_bfloat16 *>(job.dgrad);
+    if (job.kind == 0) {
+        const int Cout = job.cout, Cin = job.cin;
+        const int tci = Cin / 32;
+        const int co0 = (local / tci) * 32, ci0 = (local % tci) * 32;
+        for (int i = threadIdx.x; i < 32 * 288; i += 256) {
+            const int r = i / 288, k = i - r * 288;
+            tile[r][k] = w[(static_cast<size_t>(co0 + r) * Cin + ci0) * 9 + k];
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < 32 * 9 * 4; i += 256) {
+            const int c8 = (i & 3) * 8, t = (i >> 2) % 9, r = i / 36;
+            float f[8];
+            if (fwd) {                       // row (co = r, tap t): 8 consecutive input channels
+#pragma unroll
+                for (int q = 0; q < 8; ++q) f[q] = tile[r][(c8 + q) * 9 + t];
+                *reinterpret_cast<uint4 *>(fwd + (static_cast<size_t>(co0 + r) * 9 + t) * Cin + ci0 + c8) = Bf16x8::pack(f);
+            }
+            if (dg) {                        // row (ci = r, tap t): 8 consecutive output channels, filter flipped
+#pragma unroll
+                for (int q = 0; q < 8; ++q) f[q] = tile[c8 + q][r * 9 + (8 - t)];
+                *reinterpret_cast<uint4 *>(dg + (static_cast<size_t>(ci0 + r) * 9 + t) * Cout + co0 + c8) = Bf16x8::pack(f);
+            }
+        }
+    } else {
+        const int Cout = job.cout, Cin = job.cin;          // w[Cin][Cout][2][2]
+        const int tco = Cout / 32;
+        const int ci0 = (local / tco) * 32, co0 = (local % tco) * 32;
+        for (int i = threadIdx.x; i < 32 * 128; i += 256) {
+            const int r = i >> 7, k = i & 127;
+            tile[r][k] = w[(static_cast<size_t>(ci0 + r) * Cout + co0) * 4 + k];
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < 32 * 4 * 4; i += 256) {
+            const int c8 = (i & 3) * 8, q = (i >> 2) & 3, r = i >> 4;
+            float f[8];
+            if (fwd) {                       // row (q, co = r): 8 consecutive input channels
+#pragma unroll
+                for (int k = 0; k < 8; ++k) f[k] = tile[c8 + k][r * 4 + q];
+                *reinterpret_cast<uint4 *>(fwd + (static_cast<size_t>(q) * Cout + co0 + r) * Cin + ci0 + c8) = Bf16x8::pack(f);
+            }
+            if (dg) {                        // row (ci = r, q): 8 consecutive output channels
+#pragma unroll
+                for (int k = 0; k < 8; ++k) f[k] = tile[r][(c8 + k) * 4 + q];
+                *reinterpret_cast<uint4 *>(dg + (static_cast<size_t>(ci0 + r) * 4 + q) * Cout + co0 + c8) = Bf16x8::pack(f);
+            }
+        }
+    }
+}
+
 // Weight gradient from the GEMM layout g[co][t][ci] to the reference layout out[co][ci][3][3] (fp32)
 __global__ void __launch_bounds__(256) unpack_grad3x3_kernel(const float *__restrict__ g, int Cin, float *__restrict__ out) {
     __shared__ float tile[9][256 + 1];
@@ -595,45 +687,58 @@ __global__ void add3_kernel(const __nv_bfloat16 *__restrict__ a, const __nv_bflo
     *reinterpret_cast<__nv_bfloat162 *>(out + i) = __floats2bfloat162_rn(s0, s1);
 }
 
-// first conv (Cin = 1) weight gradient: dW[co][t] = sum_{n,y,x} dz[n][y][x][co] * x[n][y+ky-1][x+kx-1]
+// first conv (Cin = 1) weight gradient: dW[co][t] = sum_{n,y,x} dz[n][y][x][co] * x[n][y+ky-1][x+kx-1].
+// C/8 consecutive threads share a pixel (16-byte dz loads, the nine x taps are warp-broadcast loads), every thread keeps
+// 9 x 8 partial sums in registers; the block combines them through shared memory in a fixed order and writes its partial
+// to part[blockIdx.x][C*9] (summed by reduce_partials_kernel: deterministic, no atomics).
 __global__ void __launch_bounds__(256)
-first_conv_wgrad_kernel(const float *__restrict__ x, const __nv_bfloat16 *__restrict__ dz, int N, int H, int W, int C, float *dw) {
-    // thread = (channel c = threadIdx.x % C, pixel lane); each block walks a strided set of pixels
-    extern __shared__ float s_acc[];       // [C][9]
-    for (int i = threadIdx.x; i < C * 9; i += blockDim.x) s_acc[i] = 0.0f;
-    __syncthreads();
-    const int c = threadIdx.x % C, pl = threadIdx.x / C, lanes = blockDim.x / C;
-    float acc[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-    // a block walks whole image rows (no per-pixel 64-bit div / mod: that arithmetic used to dominate this kernel)
-    const int rows = N * H;
-    for (int row = blockIdx.x; row < rows; row += gridDim.x) {
-        const int yy = row % H;
-        const float *xr = x + static_cast<size_t>(row) * W;                 // x is [N][H][W]: same row index
-        const __nv_bfloat16 *gr = dz + static_cast<size_t>(row) * W * C + c;
-        const bool up = yy > 0, down = yy + 1 < H;
-        for (int xx = pl; xx < W; xx += lanes) {
-            const float g = __bfloat162float(gr[static_cast<size_t>(xx) * C]);
-            if (g == 0.0f) continue;
-            const bool left = xx > 0, right = xx + 1 < W;
-            if (up) {
-                if (left) acc[0] = fmaf(g, xr[xx - W - 1], acc[0]);
-                acc[1] = fmaf(g, xr[xx - W], acc[1]);
-                if (right) acc[2] = fmaf(g, xr[xx - W + 1], acc[2]);
-            }
-            if (left) acc[3] = fmaf(g, xr[xx - 1], acc[3]);
-            acc[4] = fmaf(g, xr[xx], acc[4]);
-            if (right) acc[5] = fmaf(g, xr[xx + 1], acc[5]);
-            if (down) {
-                if (left) acc[6] = fmaf(g, xr[xx + W - 1], acc[6]);
-                acc[7] = fmaf(g, xr[xx + W], acc[7]);
-                if (right) acc[8] = fmaf(g, xr[xx + W + 1], acc[8]);
-            }
+first_conv_wgrad_kernel(const float *__restrict__ x, const __nv_bfloat16 *__restrict__ dz, int N, int H, int W, int C, float *part) {
+    __shared__ float s_red[2048];                   // [pixel slot][C]: ppb * C = 2048 floats
+    const int tpp = C / 8, c0 = (threadIdx.x % tpp) * 8, ppb = 256 / tpp;
+    float acc[9][8];
+#pragma unroll
+    for (int t = 0; t < 9; ++t)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[t][j] = 0.0f;
+    const long long M = static_cast<long long>(N) * H * W;
+    for (long long p = static_cast<long long>(blockIdx.x) * ppb + threadIdx.x / tpp; p < M; p += static_cast<long long>(gridDim.x) * ppb) {
+        Bf16x8 v;
+        v.raw = ldg16(dz + p * C + c0);
+        float g[8];
+        v.unpack(g);
+        const int xx = static_cast<int>(p % W);
+        const int yy = static_cast<int>((p / W) % H);
+        const float *xc = x + p;                        // x is [N][H][W]: same flat pixel index
+        const bool up = yy > 0, down = yy + 1 < H, left = xx > 0, right = xx + 1 < W;
+        float xv[9];
+        xv[0] = (up && left) ? __ldg(xc - W - 1) : 0.0f;
+        xv[1] = up ? __ldg(xc - W) : 0.0f;
+        xv[2] = (up && right) ? __ldg(xc - W + 1) : 0.0f;
+        xv[3] = left ? __ldg(xc - 1) : 0.0f;
+        xv[4] = __ldg(xc);
+        xv[5] = right ? __ldg(xc + 1) : 0.0f;
+        xv[6] = (down && left) ? __ldg(xc + W - 1) : 0.0f;
+        xv[7] = down ? __ldg(xc + W) : 0.0f;
+        xv[8] = (down && right) ? __ldg(xc + W + 1) : 0.0f;
+#pragma unroll
+        for (int t = 0; t < 9; ++t)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[t][j] = fmaf(g[j], xv[t], acc[t][j]);
+    }
+    const int slot = threadIdx.x / tpp;
+    float *out = part + static_cast<size_t>(blockIdx.x) * C * 9;
+#pragma unroll 1
+    for (int t = 0; t < 9; ++t) {
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < 8; ++j) s_red[slot * C + c0 + j] = acc[t][j];
+        __syncthreads();
+        for (int c = threadIdx.x; c < C; c += 256) {
+            float sum = 0.0f;
+            for (int sl = 0; sl < ppb; ++sl) sum += s_red[sl * C + c];
+            out[c * 9 + t] = sum;
         }
     }
-#pragma unroll
-    for (int t = 0; t < 9; ++t) atomicAdd(&s_acc[c * 9 + t], acc[t]);
-    __syncthreads();
-    for (int i = threadIdx.x; i < C * 9; i += blockDim.x) atomicAdd(&dw[i], s_acc[i]);
 }
 
 constexpr int BN_MAX_BLOCKS = 148 * 4;
@@ -670,10 +775,8 @@ extern "C" int mbs_bn_train_fwd(const void *a, long long M, int C, const float *
     else
         bn_stats_kernel<false><<<grid, 256, 0, stream>>>(static_cast<const __nv_bfloat16 *>(a), M, C, part);
     MBS_CHECK_LAUNCH();
-    reduce_partials_kernel<<<mbs::cdiv(2 * C, 32), 256, 0, stream>>>(part, grid, 2 * C, sums_scratch);
-    MBS_CHECK_LAUNCH();
-    bn_finalize_kernel<<<mbs::cdiv(C, 128), 128, 0, stream>>>(sums_scratch, M, C, eps, gamma, beta, mean, invstd, momentum,
-                                                              running_mean, running_var, num_batches_tracked);
+    bn_reduce_finalize_kernel<<<mbs::cdiv(C, 32), 256, 0, stream>>>(part, grid, sums_scratch, M, C, eps, gamma, beta, mean, invstd,
+                                                                    momentum, running_mean, running_var, num_batches_tracked);
     MBS_CHECK_LAUNCH();
     if (act == MBS_ACT_MISH)
         bn_apply_kernel<true><<<grid, 256, 0, stream>>>(static_cast<const __nv_bfloat16 *>(a), M, C, sums_scratch,
@@ -734,8 +837,8 @@ extern "C" int mbs_bn_train_bwd(const void *dy, const void *a, long long M, int 
 
 extern "C" int mbs_head_fwd(const void *y, long long M, int C, const float *w, const float *b_dev, float *pred, void *stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-    MBS_REQUIRE(M > 0 && C > 0 && C % 2 == 0, "head_fwd: bad shape");
-    head_fwd_kernel<<<static_cast<int>((M + 255) / 256), 256, 0, stream>>>(static_cast<const __nv_bfloat16 *>(y), M, C, w, b_dev, pred);
+    MBS_REQUIRE(M > 0 && C >= 8 && C <= 256 && (C & (C - 1)) == 0, "head_fwd: C must be a power of two in [8, 256]");
+    head_fwd_kernel<<<grid_rows(M, C), 256, 0, stream>>>(static_cast<const __nv_bfloat16 *>(y), M, C, w, b_dev, pred);
     MBS_CHECK_LAUNCH();
     return 0;
 }
@@ -786,6 +889,14 @@ extern "C" int mbs_pack_conv3x3_dgrad(const float *w, int Cout, int Cin, void *p
     return 0;
 }
 
+extern "C" int mbs_pack_train_weights(const mbs_pack_job *jobs_dev, int n_jobs, int total_tiles, void *stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    MBS_REQUIRE(jobs_dev && n_jobs > 0 && total_tiles > 0, "pack_train_weights: bad arguments");
+    pack_train_weights_kernel<<<total_tiles, 256, 0, stream>>>(jobs_dev, n_jobs);
+    MBS_CHECK_LAUNCH();
+    return 0;
+}
+
 extern "C" int mbs_unpack_conv3x3_grad(const float *g, int Cout, int Cin, float *out, void *stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     MBS_REQUIRE(g && out && Cout > 0 && Cin > 0, "unpack_conv3x3_grad: bad arguments");
@@ -824,11 +935,15 @@ extern "C" int mbs_add3_bf16(const void *a, const void *b, const void *c, long l
     return 0;
 }
 
-extern "C" int mbs_first_conv_wgrad(const float *x, const void *dz, int N, int H, int W, int C, float *dw, void *stream_) {
+extern "C" int mbs_first_conv_wgrad(const float *x, const void *dz, int N, int H, int W, int C, float *dw, float *scratch,
+                                    void *stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-    MBS_REQUIRE(C > 0 && 256 % C == 0, "first_conv_wgrad: C must divide 256");
-    MBS_CHECK_CUDA(cudaMemsetAsync(dw, 0, static_cast<size_t>(C) * 9 * sizeof(float), stream));
-    first_conv_wgrad_kernel<<<148 * 4, 256, C * 9 * sizeof(float), stream>>>(x, static_cast<const __nv_bfloat16 *>(dz), N, H, W, C, dw);
+    MBS_REQUIRE(x && dz && dw && scratch && C >= 8 && C <= 256 && (C & (C - 1)) == 0, "first_conv_wgrad: C must be a power of two in [8, 256]");
+    const long long M = static_cast<long long>(N) * H * W;
+    const int grid = grid_rows(M, C);          // scratch: grid * C * 9 floats (<= mbs_bn_scratch_floats(2048))
+    first_conv_wgrad_kernel<<<grid, 256, 0, stream>>>(x, static_cast<const __nv_bfloat16 *>(dz), N, H, W, C, scratch);
+    MBS_CHECK_LAUNCH();
+    reduce_partials_kernel<<<mbs::cdiv(C * 9, 32), 256, 0, stream>>>(scratch, grid, C * 9, dw);
     MBS_CHECK_LAUNCH();
     return 0;
 }

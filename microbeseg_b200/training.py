@@ -128,6 +128,7 @@ class TrainEngine:
         self._order, self._buckets = [], None
         self.world_size = 1
         self._capture = None
+        self._packs = None
 
     # ---- small helpers ------------------------------------------------------------------------
     def _ones(self, c):
@@ -184,11 +185,39 @@ class TrainEngine:
         if self._buckets is not None:
             self._buckets.finish()
 
-    def _pack3x3(self, w):
-        cout, cin = w.shape[0], w.shape[1]
-        out = torch.empty((cout, 9, cin), dtype=torch.bfloat16, device=self.dev)
-        nat.check(self.L.mbs_pack_conv3x3_weight(w.data_ptr(), cout, cin, out.data_ptr(), self._sp()))
-        return out
+    def _pack_all(self):
+        """GEMM-packed bf16 copies of every conv / transposed-conv weight (forward and data-gradient forms) in ONE
+        launch per step; the packed buffers are persistent, the job table is rebuilt when a weight's storage moves."""
+        net = self.net
+        convs = []
+        for m in net.modules():
+            if isinstance(m, torch.nn.Conv2d) and m.kernel_size == (3, 3) and m.in_channels > 1:
+                convs.append((m, 0))
+            elif isinstance(m, torch.nn.ConvTranspose2d):
+                convs.append((m, 1))
+        key = tuple(m.weight.data_ptr() for m, _ in convs)
+        if self._packs is None or self._packs["key"] != key:
+            jobs = (nat.PackJob * len(convs))()
+            bufs, tile0 = {}, 0
+            for i, (m, kind) in enumerate(convs):
+                w = m.weight
+                if w.dtype != torch.float32 or not w.is_contiguous():
+                    raise RuntimeError("training needs contiguous fp32 parameters")
+                cout, cin = (w.shape[0], w.shape[1]) if kind == 0 else (w.shape[1], w.shape[0])
+                if cout % 32 or cin % 32:
+                    raise RuntimeError("training needs conv channel counts that are multiples of 32")
+                taps = 9 if kind == 0 else 4
+                fwd = torch.empty((cout, 9, cin) if kind == 0 else (4 * cout, cin), dtype=torch.bfloat16, device=self.dev)
+                dg = torch.empty((cin, taps, cout), dtype=torch.bfloat16, device=self.dev)
+                bufs[m] = (fwd, dg)
+                j = jobs[i]
+                j.w, j.fwd, j.dgrad = w.data_ptr(), fwd.data_ptr(), dg.data_ptr()
+                j.cout, j.cin, j.kind, j.tile0 = cout, cin, kind, tile0
+                tile0 += (cout // 32) * (cin // 32)
+            table = torch.frombuffer(bytearray(bytes(jobs)), dtype=torch.uint8).to(self.dev)
+            self._packs = {"key": key, "bufs": bufs, "table": table, "n": len(convs), "tiles": tile0}
+        pk = self._packs
+        nat.check(self.L.mbs_pack_train_weights(pk["table"].data_ptr(), pk["n"], pk["tiles"], self._sp()), "pack_train_weights")
 
     def _conv(self, mode, n, h, w, srcs, packed, cout, bias, act, dst):
         d = nat.ConvDesc()
@@ -240,7 +269,7 @@ class TrainEngine:
         cout = conv.weight.shape[0]
         ho, wo = (h // 2, w // 2) if stride == 2 else (h, w)
         lay.a = torch.empty((n, ho, wo, cout), dtype=torch.bfloat16, device=self.dev)
-        self._conv(1 if stride == 2 else 0, n, h, w, srcs, self._pack3x3(conv.weight.detach().float().contiguous()), cout,
+        self._conv(1 if stride == 2 else 0, n, h, w, srcs, self._packs["bufs"][conv][0], cout,
                    conv.bias.detach().float(), self.conv_act, lay.a)
         self._bn_fwd(lay)
         self.tape.append(lay)
@@ -268,9 +297,7 @@ class TrainEngine:
         lay.name, lay.kind, lay.conv, lay.bn, lay.act, lay.srcs = name, "up", conv, block.norm, ACT_NONE, [x]
         n, h, w, cin = x.shape
         cout = conv.weight.shape[1]
-        packed = torch.empty((4 * cout, cin), dtype=torch.bfloat16, device=self.dev)
-        wt = conv.weight.detach().float().contiguous()
-        nat.check(self.L.mbs_pack_convT2x2_weight(wt.data_ptr(), cin, cout, packed.data_ptr(), self._sp()))
+        packed = self._packs["bufs"][conv][0]
         lay.a = torch.empty((n, 2 * h, 2 * w, cout), dtype=torch.bfloat16, device=self.dev)
         self._conv(2, n, h, w, [x], packed, cout, conv.bias.detach().float(), ACT_NONE, lay.a)
         self._bn_fwd(lay)
@@ -308,6 +335,7 @@ class TrainEngine:
             for d, s_ in zip(st["in"], (img, border_label, cell_label)):
                 if d is not None:
                     d.copy_(s_)
+            self._pack_all()                    # (re)builds the packed-weight buffers and their job table outside the capture
             torch.cuda.synchronize(self.dev)
             self.L.mbs_launch_count(1)
             side = torch.cuda.Stream(self.dev)
@@ -354,6 +382,7 @@ class TrainEngine:
         self.tape = []
         with torch.cuda.device(self.dev), torch.no_grad():
             x = img.reshape(n, H, W).contiguous().float()
+            self._pack_all()
             # ---------------- forward ----------------
             enc_a, enc_b, pools = [], [], []
             cur = None
@@ -498,9 +527,7 @@ class TrainEngine:
         nat.check(self.L.mbs_unpack_conv3x3_grad(dwp.data_ptr(), cout, cin, dw.data_ptr(), self._sp()), "unpack_grad")
         self._set_grad(conv.weight, dw)
         # data gradient: full-resolution stride-1 conv with the flipped, transposed filter [Cin][9][Cout]
-        packed = torch.empty((cin, 9, cout), dtype=torch.bfloat16, device=self.dev)
-        nat.check(self.L.mbs_pack_conv3x3_dgrad(conv.weight.detach().float().contiguous().data_ptr(), cout, cin,
-                                                packed.data_ptr(), self._sp()), "pack_dgrad")
+        packed = self._packs["bufs"][conv][1]
         src = dz
         h, w = ho, wo
         if stride2:
@@ -522,7 +549,8 @@ class TrainEngine:
         dz = self._bn_bwd(lay, dy)
         n, h, w, c = dz.shape
         dw = torch.empty((c, 9), dtype=torch.float32, device=self.dev)
-        nat.check(self.L.mbs_first_conv_wgrad(lay.x_f32.data_ptr(), dz.data_ptr(), n, h, w, c, dw.data_ptr(), self._sp()),
+        nat.check(self.L.mbs_first_conv_wgrad(lay.x_f32.data_ptr(), dz.data_ptr(), n, h, w, c, dw.data_ptr(),
+                                              self._scratch.data_ptr(), self._sp()),
                   "first_conv_wgrad")
         self._set_grad(conv.weight, dw)
 
@@ -537,7 +565,7 @@ class TrainEngine:
         self._wgrad(2, n, h, w, dup, cout, x, cin, g, cin, 0)
         self._set_grad(conv.weight, g.permute(2, 0, 1).reshape(cin, cout, 2, 2))
         # data gradient = 2x2 stride-2 convolution of d(up) with W[ci][co][q]
-        packed = conv.weight.detach().float().permute(0, 2, 3, 1).reshape(cin, 4, cout).to(torch.bfloat16).contiguous()
+        packed = self._packs["bufs"][conv][1]
         dx = torch.empty((n, h, w, cin), dtype=torch.bfloat16, device=self.dev)
         self._conv(3, n, 2 * h, 2 * w, [dup], packed, cin, self._zeros(cin), ACT_NONE, dx)
         return dx
