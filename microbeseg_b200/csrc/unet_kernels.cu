@@ -893,6 +893,7 @@ struct WgradNhwcParams {
     int kind;                  // 0 conv s1, 1 conv s2, 2 convT
     int pair;                  // 1: rows 0-63 / 64-127 of the tile are two taps of the same 64 output channels
     int taps, tap_items;
+    int tpi, cn_tile;          // taps stacked along the N tile (non-pair conv kinds): N tile = tpi x cn_tile input channels
     int Cm, Cn;
     int m_tiles, n_tiles, splits;
     float *out;
@@ -937,7 +938,12 @@ wgrad_nhwc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const int item = t % p.tap_items; t /= p.tap_items;
     const int n_tile = t % p.n_tiles;
     const int m_tile = t / p.n_tiles;
-    const int n0 = n_tile * BN;
+    const int n0 = n_tile * p.cn_tile;
+    // N tile = tpi taps x cn_tile input channels (narrow layers: one dz tile feeds several taps, so the L2 -> smem
+    // traffic per MMA is that of a 256-column tile); the last item of a layer may hold fewer taps
+    const int tap_base = item * p.tpi;
+    const int nvalid = min(p.tpi, p.taps - tap_base);
+    const int boxes_per_tap = p.cn_tile / 64;
     // the two 64-row blocks of the A tile: channel offset, tap, validity
     int blk_c[2], blk_tap[2];
     bool blk_ok[2];
@@ -951,7 +957,7 @@ wgrad_nhwc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     } else {
         blk_c[0] = m_tile * 128;
         blk_c[1] = m_tile * 128 + 64;
-        blk_tap[0] = blk_tap[1] = item;
+        blk_tap[0] = blk_tap[1] = tap_base;
         blk_ok[0] = true;
         blk_ok[1] = blk_c[1] < p.Cm;
         if (!blk_ok[1]) blk_c[1] = blk_c[0];
@@ -982,7 +988,9 @@ wgrad_nhwc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         if (warp == 0) {
             if (lane == 0) {
                 // pixel offsets of the boxes for this item
-                int ax[2], ay[2], bx, by;
+                int ax[2], ay[2];
+                const bool b_shift = !(p.kind == 2 || p.pair);       // conv kinds without pairing: the tap shift sits on x
+                const int n_boxes = p.pair || p.kind == 2 ? BN / 64 : nvalid * boxes_per_tap;
                 for (int b = 0; b < 2; ++b) {
                     const int tp = blk_tap[b];
                     if (p.kind == 2) {            // convT: A = d(up) at 2o + (dy, dx)
@@ -995,12 +1003,6 @@ wgrad_nhwc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                         ax[b] = ay[b] = 0;
                     }
                 }
-                if (p.kind == 2 || p.pair) {
-                    bx = by = 0;
-                } else {
-                    bx = blk_tap[0] % 3 - 1;
-                    by = blk_tap[0] / 3 - 1;
-                }
                 const int ppi = p.ptx * p.pty;
                 int it = 0;
                 for (int k = k0; k < k1; ++k, ++it) {
@@ -1010,21 +1012,26 @@ wgrad_nhwc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                     const int s = it % STAGES;
                     const uint32_t ph = (it / STAGES) & 1;
                     mbar_wait(empty_bar(s), ph ^ 1u);
-                    mbar_expect_tx(full_bar(s), A_TILE + B_TILE);
+                    mbar_expect_tx(full_bar(s), A_TILE + n_boxes * WG_BLOCK);
                     for (int b = 0; b < 2; ++b)
                         tma_load_4d(sA + s * A_TILE + b * WG_BLOCK, &tmA, full_bar(s), blk_c[b], p.sA * ox0 + ax[b],
                                     p.sA * oy0 + ay[b], img);
 #pragma unroll
-                    for (int j = 0; j < BN / 64; ++j)
-                        tma_load_4d(sB + s * B_TILE + j * WG_BLOCK, &tmB, full_bar(s), n0 + 64 * j, p.sB * ox0 + bx,
-                                    p.sB * oy0 + by, img);
+                    for (int j = 0; j < BN / 64; ++j) {
+                        if (j >= n_boxes) break;
+                        const int tj = j / boxes_per_tap, tap = tap_base + tj;
+                        const int bx = b_shift ? tap % 3 - 1 : 0, by = b_shift ? tap / 3 - 1 : 0;
+                        tma_load_4d(sB + s * B_TILE + j * WG_BLOCK, &tmB, full_bar(s), n0 + 64 * (j - tj * boxes_per_tap),
+                                    p.sB * ox0 + bx, p.sB * oy0 + by, img);
+                    }
                 }
             }
             __syncwarp();
         } else if (warp == 1) {
             if (lane == 0) {
                 // both operands MN-major: bits 15 / 16 of the instruction descriptor
-                constexpr uint32_t idesc = make_idesc(BM, BN) | (1u << 15) | (1u << 16);
+                const int n_cols = p.pair || p.kind == 2 ? BN : nvalid * p.cn_tile;
+                const uint32_t idesc = make_idesc(BM, n_cols) | (1u << 15) | (1u << 16);
                 for (int it = 0; it < num_k_iters; ++it) {
                     const int s = it % STAGES;
                     const uint32_t ph = (it / STAGES) & 1;
@@ -1051,8 +1058,10 @@ wgrad_nhwc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             for (int c = half * (BN / 2); c < (half + 1) * (BN / 2); c += 32) {
                 uint32_t r[32];
                 tmem_ld32(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(c), r);
-                if (blk_ok[b] && m < p.Cm && n0 + c < p.Cn) {
-                    float *dst = p.out + (static_cast<size_t>(m) * p.taps + blk_tap[b]) * p.out_ld + p.out_coff + n0 + c;
+                const int tj = c / p.cn_tile;                    // tap slot of this 32-column chunk inside the N tile
+                const int cc = c - tj * p.cn_tile;
+                if (blk_ok[b] && m < p.Cm && tj < nvalid && n0 + cc < p.Cn) {
+                    float *dst = p.out + (static_cast<size_t>(m) * p.taps + blk_tap[b] + tj) * p.out_ld + p.out_coff + n0 + cc;
 #pragma unroll
                     for (int j = 0; j < 32; j += 4)
                         red_add_v4(dst + j, __uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
@@ -1551,6 +1560,15 @@ bool wgrad_halo_enabled() {
     return v == 1;
 }
 
+bool wgrad_stack_enabled() {     // MBS_NO_WGRAD_STACK=1 (A/B runs): one tap per N tile for the narrow layers
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("MBS_NO_WGRAD_STACK");
+        v = (e && e[0] == '1') ? 0 : 1;
+    }
+    return v == 1;
+}
+
 bool pair_enabled() {
     static int v = -1;
     if (v < 0) {
@@ -1734,7 +1752,7 @@ extern "C" int mbs_conv_wgrad(const mbs_wgrad_desc *d, void *stream_) {
     wp.taps = d->kind == 2 ? 4 : 9;
     wp.sA = d->kind == 2 ? 2 : 1;
     wp.sB = d->kind == 1 ? 2 : 1;
-    wp.pair = (d->kind == 0 && d->Cm == 64) ? 1 : 0;
+    wp.pair = ((d->kind == 0 || d->kind == 2) && d->Cm == 64) ? 1 : 0;     // two taps x 64 output channels per 128-row tile
     wp.tap_items = wp.pair ? (wp.taps + 1) / 2 : wp.taps;
     // K chunk = 64 pixels: 8x8 patches; narrow grids use taller patches
     wp.pw = d->Wo >= 8 ? 8 : (d->Wo >= 4 ? 4 : 2);
@@ -1766,9 +1784,18 @@ extern "C" int mbs_conv_wgrad(const mbs_wgrad_desc *d, void *stream_) {
         MBS_CHECK_LAUNCH();
         return 0;
     }
-    const int bn = d->Cn % 256 == 0 ? 256 : (d->Cn % 128 == 0 ? 128 : 64);
+    int bn = d->Cn % 256 == 0 ? 256 : (d->Cn % 128 == 0 ? 128 : 64);
+    wp.tpi = 1;
+    wp.cn_tile = bn;
+    if (!wp.pair && d->kind != 2 && (d->Cn == 128 || d->Cn == 64) && wgrad_stack_enabled()) {
+        // narrow inputs: stack 2 / 4 taps along a 256-column N tile (one dz tile feeds them all)
+        wp.tpi = 256 / d->Cn;
+        wp.cn_tile = d->Cn;
+        wp.tap_items = mbs::cdiv(wp.taps, wp.tpi);
+        bn = 256;
+    }
     wp.m_tiles = wp.pair ? 1 : mbs::cdiv(d->Cm, 128);
-    wp.n_tiles = d->Cn / bn;
+    wp.n_tiles = d->Cn / wp.cn_tile;
     const int tiles = wp.m_tiles * wp.n_tiles * wp.tap_items;
     const int patches = d->N * wp.ptx * wp.pty;
     int splits = mbs::cdiv(2 * sm_count(), tiles);
