@@ -166,7 +166,9 @@ int mbs_smoothl1(const float *pred, const float *target, long long M, float *los
  * *loss_accum += loss (zeroed by the caller), grad = dloss/dpred */
 int mbs_regression_loss(const float *pred, const float *target, long long M, int kind, float *loss_accum, float *grad,
                         void *stream);
-int mbs_head_bwd(const float *g, const void *y, long long M, int C, const float *w, void *dy, float *dw_db, void *stream);
+/* scratch: >= 592 * (C + 1) floats (per-block partial sums, reduced in a fixed order: bitwise reproducible) */
+int mbs_head_bwd(const float *g, const void *y, long long M, int C, const float *w, void *dy, float *dw_db, float *scratch,
+                 void *stream);
 /* layout / glue kernels of the backward pass */
 /* data-gradient filter of a 3x3 conv: packed[ci][tap][co] = bf16(w[co][ci][8 - tap]) from the reference-layout weight */
 int mbs_pack_conv3x3_dgrad(const float *w, int Cout, int Cin, void *packed, void *stream);
@@ -200,8 +202,19 @@ typedef struct {
     const void *a; int Cm, lda, coffa;
     const void *b; int Cn, ldb, coffb;
     float *out; int out_ld, out_coff;
+    int partial;    /* 0: accumulate into the zeroed `out` with vector reductions (summation order varies from run to run);
+                     * 1: deterministic -- `out` is a scratch buffer [splits][Cm][taps][Cn] (splits = mbs_conv_wgrad_splits(d),
+                     *    out_ld / out_coff ignored), every K split stores its tile; mbs_wgrad_reduce sums them in order */
 } mbs_wgrad_desc;
 int mbs_conv_wgrad(const mbs_wgrad_desc *d, void *stream);
+/* number of K splits mbs_conv_wgrad uses for this descriptor on the current device (-1: bad descriptor) */
+int mbs_conv_wgrad_splits(const mbs_wgrad_desc *d);
+/* Ordered sum over the K splits of up to two partial buffers (the two sources of a concatenated input; part1 may be NULL)
+ * and the layout change to the reference's parameter layout in one pass:
+ *   layout 0 (Conv2d 3x3):        out[co][coff_s + ci][3][3] = sum_k part_s[k][co][tap][ci]     (out: [Cm][cn0 + cn1][3][3])
+ *   layout 1 (ConvTranspose 2x2): out[ci][co][2][2]          = sum_k part0[k][co][q][ci]        (out: [cn0][Cm][2][2]) */
+int mbs_wgrad_reduce(const float *part0, int splits0, int cn0, const float *part1, int splits1, int cn1, int Cm, int layout,
+                     float *out, void *stream);
 
 /* ---------------------------------------------------------------------------------------- */
 /* Ranger optimizer step (RAdam + gradient centralisation + lookahead), replaces the per-tensor loop of    */

@@ -59,7 +59,7 @@ class WgradDesc(ctypes.Structure):
     _fields_ = [("kind", c_int), ("N", c_int), ("Ho", c_int), ("Wo", c_int),
                 ("a", c_void_p), ("Cm", c_int), ("lda", c_int), ("coffa", c_int),
                 ("b", c_void_p), ("Cn", c_int), ("ldb", c_int), ("coffb", c_int),
-                ("out", c_void_p), ("out_ld", c_int), ("out_coff", c_int)]
+                ("out", c_void_p), ("out_ld", c_int), ("out_coff", c_int), ("partial", c_int)]
 
 
 class PackJob(ctypes.Structure):
@@ -107,12 +107,14 @@ _SIGS = {
     "mbs_smoothl1": (c_int, [c_void_p, c_void_p, ctypes.c_longlong, c_void_p, c_void_p, c_void_p]),
     "mbs_regression_loss": (c_int, [c_void_p, c_void_p, ctypes.c_longlong, c_int, c_void_p, c_void_p, c_void_p]),
     "mbs_ce_dice_loss": (c_int, [c_void_p, c_void_p, ctypes.c_longlong, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
-    "mbs_head_bwd": (c_int, [c_void_p, c_void_p, ctypes.c_longlong, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "mbs_head_bwd": (c_int, [c_void_p, c_void_p, ctypes.c_longlong, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "mbs_maxpool2x2": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "mbs_zero_insert_up2": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "mbs_add3_bf16": (c_int, [c_void_p, c_void_p, c_void_p, ctypes.c_longlong, c_void_p, c_void_p]),
     "mbs_first_conv_wgrad": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "mbs_conv_wgrad": (c_int, [ctypes.POINTER(WgradDesc), c_void_p]),
+    "mbs_conv_wgrad_splits": (c_int, [ctypes.POINTER(WgradDesc)]),
+    "mbs_wgrad_reduce": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "mbs_ranger_step": (c_int, [c_void_p, c_int, c_int, c_float, c_float, c_float, c_float, c_float, c_int, c_int, c_float,
                                 c_void_p]),
     "mbs_adam_step": (c_int, [c_void_p, c_int, c_int, c_float, c_float, c_float, c_float, c_float, c_float, c_int, c_void_p]),

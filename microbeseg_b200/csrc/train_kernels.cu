@@ -502,7 +502,8 @@ ce_dice_grad_kernel(const float *__restrict__ z, const uint8_t *__restrict__ y, 
 // head backward: dy[p][c] = g[p] * w[c];  dw[c] += sum_p g[p] * y[p][c];  dw[C] (= db) += sum_p g[p]
 __global__ void __launch_bounds__(256)
 head_bwd_kernel(const float *__restrict__ g, const __nv_bfloat16 *__restrict__ y, long long M, int C, const float *__restrict__ w,
-                __nv_bfloat16 *__restrict__ dy, float *dw_db) {
+                __nv_bfloat16 *__restrict__ dy, float *part_dw, float *part_db) {
+    __shared__ float s_g[8];
     const int tpp = C / 8, c0 = (threadIdx.x % tpp) * 8, ppb = 256 / tpp;
     float acc[1][8] = {};
     float gsum = 0.0f;
@@ -525,9 +526,17 @@ head_bwd_kernel(const float *__restrict__ g, const __nv_bfloat16 *__restrict__ y
             if (c0 == 0) gsum += gp;
         }
     }
-    block_channel_atomic<1>(acc, C, threadIdx.x < ppb * tpp ? c0 : C, dw_db);
+    // per-block partial sums, combined in a fixed order by reduce_partials_kernel (no atomics: bitwise reproducible)
+    block_channel_atomic<1, true>(acc, C, threadIdx.x < ppb * tpp ? c0 : C, part_dw);
     gsum = warp_sum(gsum);
-    if ((threadIdx.x & 31) == 0 && gsum != 0.0f) atomicAdd(&dw_db[C], gsum);
+    if ((threadIdx.x & 31) == 0) s_g[threadIdx.x >> 5] = gsum;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.0f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) t += s_g[k];
+        part_db[blockIdx.x] = t;
+    }
 }
 
 // Data-gradient filter of a 3x3 conv in GEMM-packed form: out[ci][t][co] = bf16(w[co][ci][8 - t]) (spatially flipped,
@@ -630,6 +639,53 @@ __global__ void __launch_bounds__(256) unpack_grad3x3_kernel(const float *__rest
     }
     __syncthreads();
     for (int i = threadIdx.x; i < n * 9; i += 256) out[(static_cast<size_t>(co) * Cin + ci0) * 9 + i] = tile[i % 9][i / 9];
+}
+
+// Deterministic end of the weight gradient: out = sum over the K splits (in split order) of the partial tiles written by
+// mbs_conv_wgrad(partial = 1), and the layout change to the reference's parameter layout in the same pass.
+//   part_s: [splits_s][Cm][TAPS][cn_s] for the (up to two) sources of a concatenated input
+//   LAYOUT 0: out[co][coff_s + ci][TAPS] (Conv2d weight [Cout][Cin][3][3]);  LAYOUT 1: out[ci][co][TAPS] (ConvTranspose2d
+//   weight [Cin][Cout][2][2]).  One CTA = one output channel co and CI input channels; SG thread groups share the splits
+//   and are combined through shared memory in a fixed order.
+template <int TAPS, int CI, int SG, int LAYOUT>
+__global__ void __launch_bounds__(CI * SG)
+wgrad_reduce_kernel(const float *__restrict__ part0, int splits0, int cn0, const float *__restrict__ part1, int splits1, int cn1,
+                    int Cm, float *__restrict__ out) {
+    __shared__ float s_sum[SG][TAPS][CI + 1];
+    const int co = blockIdx.x;
+    const int ci0 = blockIdx.y * CI;                       // channel offset in the concatenated input
+    const bool second = ci0 >= cn0;
+    const float *__restrict__ part = second ? part1 : part0;
+    const int splits = second ? splits1 : splits0, cn = second ? cn1 : cn0;
+    const int cl0 = second ? ci0 - cn0 : ci0;              // channel offset inside this source
+    const int tx = threadIdx.x % CI, ty = threadIdx.x / CI;
+    const bool live = cl0 + tx < cn;
+    const size_t split_stride = static_cast<size_t>(Cm) * TAPS * cn;
+    float acc[TAPS];
+#pragma unroll
+    for (int t = 0; t < TAPS; ++t) acc[t] = 0.0f;
+    if (live) {
+        const float *src = part + static_cast<size_t>(co) * TAPS * cn + cl0 + tx;
+        for (int k = ty; k < splits; k += SG) {
+#pragma unroll
+            for (int t = 0; t < TAPS; ++t) acc[t] += src[k * split_stride + static_cast<size_t>(t) * cn];
+        }
+    }
+#pragma unroll
+    for (int t = 0; t < TAPS; ++t) s_sum[ty][t][tx] = acc[t];
+    __syncthreads();
+    const int cin_total = cn0 + cn1;
+    for (int i = threadIdx.x; i < CI * TAPS; i += CI * SG) {
+        const int c = i / TAPS, t = i - c * TAPS;
+        if (cl0 + c >= cn) continue;
+        float v = 0.0f;
+#pragma unroll
+        for (int g = 0; g < SG; ++g) v += s_sum[g][t][c];
+        if (LAYOUT == 0)
+            out[(static_cast<size_t>(co) * cin_total + ci0) * TAPS + i] = v;       // CI * TAPS contiguous floats per CTA
+        else
+            out[(static_cast<size_t>(ci0 + c) * Cm + co) * TAPS + t] = v;
+    }
 }
 
 // nn.MaxPool2d(kernel_size=2, stride=2) on NHWC bf16 (pool_method = 'max', unets.py:306-307,363-364): 8 channels per thread
@@ -870,12 +926,17 @@ extern "C" int mbs_ce_dice_loss(const float *logits, const uint8_t *labels, long
 }
 
 extern "C" int mbs_head_bwd(const float *g, const void *y, long long M, int C, const float *w, void *dy, float *dw_db,
-                            void *stream_) {
+                            float *scratch, void *stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-    MBS_REQUIRE(M > 0 && C >= 8 && C % 8 == 0 && C <= 2048 && 256 % (C / 8) == 0, "head_bwd: bad shape");
-    MBS_CHECK_CUDA(cudaMemsetAsync(dw_db, 0, (C + 1) * sizeof(float), stream));
-    head_bwd_kernel<<<grid_rows(M, C), 256, 0, stream>>>(g, static_cast<const __nv_bfloat16 *>(y), M, C, w,
-                                                                      static_cast<__nv_bfloat16 *>(dy), dw_db);
+    MBS_REQUIRE(M > 0 && C >= 8 && C % 8 == 0 && C <= 2048 && 256 % (C / 8) == 0 && scratch, "head_bwd: bad shape");
+    const int grid = grid_rows(M, C);
+    float *part_dw = scratch, *part_db = scratch + static_cast<size_t>(grid) * C;       // (C + 1) * grid floats
+    head_bwd_kernel<<<grid, 256, 0, stream>>>(g, static_cast<const __nv_bfloat16 *>(y), M, C, w, static_cast<__nv_bfloat16 *>(dy), part_dw,
+                                              part_db);
+    MBS_CHECK_LAUNCH();
+    reduce_partials_kernel<<<mbs::cdiv(C, 32), 256, 0, stream>>>(part_dw, grid, C, dw_db);
+    MBS_CHECK_LAUNCH();
+    reduce_partials_kernel<<<1, 256, 0, stream>>>(part_db, grid, 1, dw_db + C);
     MBS_CHECK_LAUNCH();
     return 0;
 }
@@ -901,6 +962,26 @@ extern "C" int mbs_unpack_conv3x3_grad(const float *g, int Cout, int Cin, float 
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     MBS_REQUIRE(g && out && Cout > 0 && Cin > 0, "unpack_conv3x3_grad: bad arguments");
     unpack_grad3x3_kernel<<<dim3(Cout, mbs::cdiv(Cin, 256)), 256, 0, stream>>>(g, Cin, out);
+    MBS_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int mbs_wgrad_reduce(const float *part0, int splits0, int cn0, const float *part1, int splits1, int cn1, int Cm, int layout,
+                                float *out, void *stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    MBS_REQUIRE(part0 && out && splits0 > 0 && cn0 > 0 && cn0 % 64 == 0 && Cm > 0 && (layout == 0 || layout == 1),
+                "wgrad_reduce: bad arguments");
+    MBS_REQUIRE(part1 ? (splits1 > 0 && cn1 > 0 && cn1 % 64 == 0 && layout == 0) : (splits1 == 0 && cn1 == 0),
+                "wgrad_reduce: bad second source");
+    const dim3 grid(Cm, (cn0 + cn1) / 64);
+    const bool many = splits0 >= 8 || splits1 >= 8;
+    if (layout == 0) {
+        if (many) wgrad_reduce_kernel<9, 64, 4, 0><<<grid, 256, 0, stream>>>(part0, splits0, cn0, part1, splits1, cn1, Cm, out);
+        else wgrad_reduce_kernel<9, 64, 1, 0><<<grid, 64, 0, stream>>>(part0, splits0, cn0, part1, splits1, cn1, Cm, out);
+    } else {
+        if (many) wgrad_reduce_kernel<4, 64, 4, 1><<<grid, 256, 0, stream>>>(part0, splits0, cn0, nullptr, 0, 0, Cm, out);
+        else wgrad_reduce_kernel<4, 64, 1, 1><<<grid, 64, 0, stream>>>(part0, splits0, cn0, nullptr, 0, 0, Cm, out);
+    }
     MBS_CHECK_LAUNCH();
     return 0;
 }

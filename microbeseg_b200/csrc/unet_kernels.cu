@@ -896,9 +896,14 @@ struct WgradNhwcParams {
     int tpi, cn_tile;          // taps stacked along the N tile (non-pair conv kinds): N tile = tpi x cn_tile input channels
     int Cm, Cn;
     int m_tiles, n_tiles, splits;
+    int per;                   // pixel patches per K split (every split is non-empty)
+    int partial;               // 1: out is [splits][Cm][taps][Cn], each split stores its tile (no atomics: ordered reduce later)
     float *out;
     int out_ld, out_coff;
 };
+__device__ __forceinline__ void st_v4(float *addr, float a, float b, float c, float d) {
+    *reinterpret_cast<float4 *>(addr) = make_float4(a, b, c, d);
+}
 
 __device__ __forceinline__ uint64_t make_sw128_mn_desc(uint32_t saddr, uint32_t lbo_bytes) {
     uint64_t d = 0;
@@ -963,7 +968,7 @@ wgrad_nhwc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         if (!blk_ok[1]) blk_c[1] = blk_c[0];
     }
     const int patches = p.N * p.ptx * p.pty;
-    const int per = (patches + p.splits - 1) / p.splits;
+    const int per = p.per;
     const int k0 = split * per;
     const int k1 = min(patches, k0 + per);
     const int num_k_iters = max(0, k1 - k0);
@@ -1061,11 +1066,18 @@ wgrad_nhwc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 const int tj = c / p.cn_tile;                    // tap slot of this 32-column chunk inside the N tile
                 const int cc = c - tj * p.cn_tile;
                 if (blk_ok[b] && m < p.Cm && tj < nvalid && n0 + cc < p.Cn) {
-                    float *dst = p.out + (static_cast<size_t>(m) * p.taps + blk_tap[b] + tj) * p.out_ld + p.out_coff + n0 + cc;
+                    if (p.partial) {
+                        float *dst = p.out + ((static_cast<size_t>(split) * p.Cm + m) * p.taps + blk_tap[b] + tj) * p.Cn + n0 + cc;
 #pragma unroll
-                    for (int j = 0; j < 32; j += 4)
-                        red_add_v4(dst + j, __uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
-                                   __uint_as_float(r[j + 3]));
+                        for (int j = 0; j < 32; j += 4)
+                            st_v4(dst + j, __uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+                    } else {
+                        float *dst = p.out + (static_cast<size_t>(m) * p.taps + blk_tap[b] + tj) * p.out_ld + p.out_coff + n0 + cc;
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4)
+                            red_add_v4(dst + j, __uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
+                                       __uint_as_float(r[j + 3]));
+                    }
                 }
             }
             tcgen05_fence_before();
@@ -1124,7 +1136,7 @@ wgrad_halo64_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const int n_chunk = blockIdx.x / p.splits;
     const int n0 = n_chunk * 64;
     const int patches = p.N * p.ptx * p.pty;
-    const int per = (patches + p.splits - 1) / p.splits;
+    const int per = p.per;
     const int k0 = split * per;
     const int k1 = min(patches, k0 + per);
     const int num_k_iters = max(0, k1 - k0);
@@ -1202,7 +1214,12 @@ wgrad_halo64_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 tmem_ld32(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(c), r);
                 const int pr = c >> 6;
                 const int tap = 8 - 2 * pr - blk;
-                if (tap >= 0) {
+                if (tap >= 0 && p.partial) {
+                    float *dst = p.out + ((static_cast<size_t>(split) * 64 + m) * 9 + tap) * p.Cn + n0 + (c & 63);
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4)
+                        st_v4(dst + j, __uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+                } else if (tap >= 0) {
                     float *dst = p.out + (static_cast<size_t>(m) * 9 + tap) * p.out_ld + p.out_coff + n0 + (c & 63);
 #pragma unroll
                     for (int j = 0; j < 32; j += 4)
@@ -1731,14 +1748,18 @@ int launch_wgrad_nhwc(const CUtensorMap &a, const CUtensorMap &b, const WgradNhw
     return 0;
 }
 
-extern "C" int mbs_conv_wgrad(const mbs_wgrad_desc *d, void *stream_) {
-    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+namespace {
+struct WgradPlan {
+    WgradNhwcParams wp;
+    bool halo;
+    int bn, grid;
+};
+// one place decides tiling and the K split, so that mbs_conv_wgrad_splits() and the launch always agree
+int plan_wgrad(const mbs_wgrad_desc *d, WgradPlan &pl) {
     MBS_REQUIRE(d != nullptr && d->kind >= 0 && d->kind <= 2, "wgrad: bad descriptor");
     MBS_REQUIRE(d->Cm > 0 && d->Cm % 64 == 0 && d->Cn > 0 && d->Cn % 64 == 0, "wgrad: channel counts must be multiples of 64 (got %d, %d)", d->Cm, d->Cn);
-    MBS_REQUIRE(d->N > 0 && d->Ho > 0 && d->Wo > 0 && d->a && d->b && d->out, "wgrad: bad shape / null operand");
-    MBS_REQUIRE(d->out_ld % 4 == 0 && d->out_coff % 4 == 0 && (reinterpret_cast<uintptr_t>(d->out) & 15) == 0,
-                "wgrad: the gradient buffer must allow 16-byte vector reductions");
-    WgradNhwcParams wp;
+    MBS_REQUIRE(d->N > 0 && d->Ho > 0 && d->Wo > 0, "wgrad: bad shape");
+    WgradNhwcParams &wp = pl.wp;
     memset(&wp, 0, sizeof(wp));
     wp.N = d->N;
     wp.Ho = d->Ho;
@@ -1749,6 +1770,7 @@ extern "C" int mbs_conv_wgrad(const mbs_wgrad_desc *d, void *stream_) {
     wp.out = d->out;
     wp.out_ld = d->out_ld;
     wp.out_coff = d->out_coff;
+    wp.partial = d->partial ? 1 : 0;
     wp.taps = d->kind == 2 ? 4 : 9;
     wp.sA = d->kind == 2 ? 2 : 1;
     wp.sB = d->kind == 1 ? 2 : 1;
@@ -1759,18 +1781,72 @@ extern "C" int mbs_conv_wgrad(const mbs_wgrad_desc *d, void *stream_) {
     wp.ph = 64 / wp.pw;
     wp.ptx = mbs::cdiv(d->Wo, wp.pw);
     wp.pty = mbs::cdiv(d->Ho, wp.ph);
-    if (d->kind == 0 && d->Cm == 64 && d->Wo >= 8 && d->Ho >= 8 && wgrad_halo_enabled()) {
+    wp.tpi = 1;
+    pl.halo = d->kind == 0 && d->Cm == 64 && d->Wo >= 8 && d->Ho >= 8 && wgrad_halo_enabled();
+    int splits;
+    if (pl.halo) {
         // full-resolution layers: all nine taps per CTA from one halo patch (see wgrad_halo64_kernel)
         wp.pw = wp.ph = 8;
         wp.ptx = mbs::cdiv(d->Wo, 8);
         wp.pty = mbs::cdiv(d->Ho, 8);
-        const int chunks = d->Cn / 64;
-        const int patches = d->N * wp.ptx * wp.pty;
-        int splits = mbs::cdiv(sm_count(), chunks);      // one resident CTA per SM: one wave, fewest partial-tile reductions
-        if (splits > patches) splits = patches;
-        wp.splits = splits;
-        CUtensorMap a, b;
-        int rc = make_act_map(&a, d->a, d->N, d->Ho, d->Wo, d->Cm, d->lda, d->coffa, 1, 10, 10);
+        pl.bn = 64;
+        wp.cn_tile = 64;
+        splits = mbs::cdiv(sm_count(), d->Cn / 64);      // one resident CTA per SM: one wave, fewest partial-tile reductions
+    } else {
+        int bn = d->Cn % 256 == 0 ? 256 : (d->Cn % 128 == 0 ? 128 : 64);
+        wp.cn_tile = bn;
+        if (!wp.pair && d->kind != 2 && (d->Cn == 128 || d->Cn == 64) && wgrad_stack_enabled()) {
+            // narrow inputs: stack 2 / 4 taps along a 256-column N tile (one dz tile feeds them all)
+            wp.tpi = 256 / d->Cn;
+            wp.cn_tile = d->Cn;
+            wp.tap_items = mbs::cdiv(wp.taps, wp.tpi);
+            bn = 256;
+        }
+        pl.bn = bn;
+        wp.m_tiles = wp.pair ? 1 : mbs::cdiv(d->Cm, 128);
+        wp.n_tiles = d->Cn / wp.cn_tile;
+        // the kernels hold one CTA per SM (192 KB of operand stages): fill ONE wave when the tiles fit, otherwise the split
+        // (<= 4) with the fewest wave-equivalents; fewer splits = less partial-tile traffic
+        const int tiles = wp.m_tiles * wp.n_tiles * wp.tap_items, sms = sm_count();
+        if (tiles <= sms) {
+            splits = sms / tiles;
+        } else {
+            splits = 1;
+            double best = 1e30;
+            for (int sp = 1; sp <= 4; ++sp) {
+                const double cost = static_cast<double>(mbs::cdiv(tiles * sp, sms)) / sp;
+                if (cost < best - 1e-9) { best = cost; splits = sp; }
+            }
+        }
+    }
+    const int patches = d->N * wp.ptx * wp.pty;
+    if (splits > patches) splits = patches;
+    if (splits < 1) splits = 1;
+    wp.per = mbs::cdiv(patches, splits);
+    wp.splits = mbs::cdiv(patches, wp.per);              // every split owns at least one patch
+    pl.grid = (pl.halo ? d->Cn / 64 : wp.m_tiles * wp.n_tiles * wp.tap_items) * wp.splits;
+    return 0;
+}
+}  // namespace
+
+extern "C" int mbs_conv_wgrad_splits(const mbs_wgrad_desc *d) {
+    WgradPlan pl;
+    if (plan_wgrad(d, pl)) return -1;
+    return pl.wp.splits;
+}
+
+extern "C" int mbs_conv_wgrad(const mbs_wgrad_desc *d, void *stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    WgradPlan pl;
+    int rc = plan_wgrad(d, pl);
+    if (rc) return rc;
+    MBS_REQUIRE(d->a && d->b && d->out, "wgrad: null operand");
+    MBS_REQUIRE((reinterpret_cast<uintptr_t>(d->out) & 15) == 0 && (d->partial || (d->out_ld % 4 == 0 && d->out_coff % 4 == 0)),
+                "wgrad: the gradient buffer must allow 16-byte vector accesses");
+    const WgradNhwcParams &wp = pl.wp;
+    CUtensorMap a, b;
+    if (pl.halo) {
+        rc = make_act_map(&a, d->a, d->N, d->Ho, d->Wo, d->Cm, d->lda, d->coffa, 1, 10, 10);
         if (rc) return rc;
         rc = make_act_map(&b, d->b, d->N, d->Ho, d->Wo, d->Cn, d->ldb, d->coffb, 1, 8, 8);
         if (rc) return rc;
@@ -1780,37 +1856,17 @@ extern "C" int mbs_conv_wgrad(const mbs_wgrad_desc *d, void *stream_) {
             MBS_CHECK_CUDA(cudaFuncSetAttribute(wgrad_halo64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WH_DYN));
             configured[dev] = true;
         }
-        wgrad_halo64_kernel<<<chunks * splits, NUM_THREADS, WH_DYN, stream>>>(a, b, wp);
+        wgrad_halo64_kernel<<<pl.grid, NUM_THREADS, WH_DYN, stream>>>(a, b, wp);
         MBS_CHECK_LAUNCH();
         return 0;
     }
-    int bn = d->Cn % 256 == 0 ? 256 : (d->Cn % 128 == 0 ? 128 : 64);
-    wp.tpi = 1;
-    wp.cn_tile = bn;
-    if (!wp.pair && d->kind != 2 && (d->Cn == 128 || d->Cn == 64) && wgrad_stack_enabled()) {
-        // narrow inputs: stack 2 / 4 taps along a 256-column N tile (one dz tile feeds them all)
-        wp.tpi = 256 / d->Cn;
-        wp.cn_tile = d->Cn;
-        wp.tap_items = mbs::cdiv(wp.taps, wp.tpi);
-        bn = 256;
-    }
-    wp.m_tiles = wp.pair ? 1 : mbs::cdiv(d->Cm, 128);
-    wp.n_tiles = d->Cn / wp.cn_tile;
-    const int tiles = wp.m_tiles * wp.n_tiles * wp.tap_items;
-    const int patches = d->N * wp.ptx * wp.pty;
-    int splits = mbs::cdiv(2 * sm_count(), tiles);
-    if (splits > patches) splits = patches;
-    if (splits < 1) splits = 1;
-    wp.splits = splits;
-    CUtensorMap a, b;
-    int rc = make_act_map(&a, d->a, d->N, wp.sA * d->Ho, wp.sA * d->Wo, d->Cm, d->lda, d->coffa, wp.sA, wp.pw, wp.ph);
+    rc = make_act_map(&a, d->a, d->N, wp.sA * d->Ho, wp.sA * d->Wo, d->Cm, d->lda, d->coffa, wp.sA, wp.pw, wp.ph);
     if (rc) return rc;
     rc = make_act_map(&b, d->b, d->N, wp.sB * d->Ho, wp.sB * d->Wo, d->Cn, d->ldb, d->coffb, wp.sB, wp.pw, wp.ph);
     if (rc) return rc;
-    const int grid = tiles * splits;
-    if (bn == 256) return launch_wgrad_nhwc<256, 4>(a, b, wp, grid, stream);
-    if (bn == 128) return launch_wgrad_nhwc<128, 6>(a, b, wp, grid, stream);
-    return launch_wgrad_nhwc<64, 8>(a, b, wp, grid, stream);
+    if (pl.bn == 256) return launch_wgrad_nhwc<256, 4>(a, b, wp, pl.grid, stream);
+    if (pl.bn == 128) return launch_wgrad_nhwc<128, 6>(a, b, wp, pl.grid, stream);
+    return launch_wgrad_nhwc<64, 8>(a, b, wp, pl.grid, stream);
 }
 
 extern "C" int mbs_first_conv(const void *img, int in_dtype, int H, int W, int pad_y, int pad_x, float norm_lo,

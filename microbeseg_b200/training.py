@@ -251,15 +251,27 @@ class TrainEngine:
                                           ACT_MISH if lay.act == ACT_MISH else ACT_NONE, self._sp()),
                   "bn_train_fwd")
 
-    def _wgrad(self, kind, n, ho, wo, a, cm, b, cn, out, out_ld, out_coff):
+    def _wgrad(self, kind, n, ho, wo, a, cm, b, cn):
         """weight gradient on the tensor cores straight from the NHWC bf16 activations: ``a`` = dz (conv) / d(up)
-        (transposed conv), ``b`` = the layer input; accumulates into out[m][tap][out_coff + n] (fp32)."""
+        (transposed conv), ``b`` = the layer input.  Deterministic: every K split stores its fp32 tile into a scratch
+        buffer [splits][cm][taps][cn] (returned with the split count); ``_wgrad_reduce`` sums the splits in order."""
         d = nat.WgradDesc()
         d.kind, d.N, d.Ho, d.Wo = kind, n, ho, wo
         d.a, d.Cm, d.lda, d.coffa = a.data_ptr(), cm, a.shape[-1], 0
         d.b, d.Cn, d.ldb, d.coffb = b.data_ptr(), cn, b.shape[-1], 0
-        d.out, d.out_ld, d.out_coff = out.data_ptr(), out_ld, out_coff
+        d.out, d.out_ld, d.out_coff, d.partial = None, cn, 0, 1
+        splits = int(self.L.mbs_conv_wgrad_splits(ctypes.byref(d)))
+        if splits <= 0:
+            nat.check(1, "conv_wgrad_splits")
+        part = torch.empty((splits, cm, 4 if kind == 2 else 9, cn), dtype=torch.float32, device=self.dev)
+        d.out = part.data_ptr()
         nat.check(self.L.mbs_conv_wgrad(ctypes.byref(d), self._sp()), "conv_wgrad")
+        return part, splits
+
+    def _wgrad_reduce(self, parts, cm, layout, out):
+        (p0, s0), (p1, s1) = parts[0], (parts[1] if len(parts) > 1 else (None, 0))
+        nat.check(self.L.mbs_wgrad_reduce(p0.data_ptr(), s0, p0.shape[-1], p1.data_ptr() if p1 is not None else None, s1,
+                                          p1.shape[-1] if p1 is not None else 0, cm, layout, out.data_ptr(), self._sp()), "wgrad_reduce")
 
     # ---- forward ------------------------------------------------------------------------------
     def _fwd_conv(self, name, conv, bn, srcs, stride=1):
@@ -453,7 +465,7 @@ class TrainEngine:
                     dyk = torch.empty_like(y_last)
                     dwdb = torch.empty(c0 + 1, dtype=torch.float32, device=self.dev)
                     nat.check(self.L.mbs_head_bwd(gpred[di][k].data_ptr(), y_last.data_ptr(), n * H * W, c0, hw[k].data_ptr(),
-                                                  dyk.data_ptr(), dwdb.data_ptr(), self._sp()), "head_bwd")
+                                                  dyk.data_ptr(), dwdb.data_ptr(), self._scratch.data_ptr(), self._sp()), "head_bwd")
                     dys.append(dyk)
                     dws.append(dwdb)
                 dy = self._sum(dys)
@@ -517,14 +529,11 @@ class TrainEngine:
         cins = [s.shape[-1] for s in lay.srcs]
         cin = sum(cins)
         stride2 = lay.kind == "s2"
-        # weight gradient: dW[co][tap][ci] (GEMM-packed layout) -> reference layout [Cout,Cin,3,3]
-        dwp = torch.zeros((cout, 9, cin), dtype=torch.float32, device=self.dev)
-        off = 0
-        for s, cs in zip(lay.srcs, cins):
-            self._wgrad(1 if stride2 else 0, n, ho, wo, dz, cout, s, cs, dwp, cin, off)
-            off += cs
+        # weight gradient: per-split tiles dW[k][co][tap][ci] per source -> ordered sum in the reference layout [Cout,Cin,3,3]
+        assert len(lay.srcs) <= 2
+        parts = [self._wgrad(1 if stride2 else 0, n, ho, wo, dz, cout, s, cs) for s, cs in zip(lay.srcs, cins)]
         dw = self._grad_buf(conv.weight)
-        nat.check(self.L.mbs_unpack_conv3x3_grad(dwp.data_ptr(), cout, cin, dw.data_ptr(), self._sp()), "unpack_grad")
+        self._wgrad_reduce(parts, cout, 0, dw)
         self._set_grad(conv.weight, dw)
         # data gradient: full-resolution stride-1 conv with the flipped, transposed filter [Cin][9][Cout]
         packed = self._packs["bufs"][conv][1]
@@ -561,9 +570,9 @@ class TrainEngine:
         x = lay.srcs[0]
         n, h, w, cin = x.shape
         cout = dup.shape[-1]
-        g = torch.zeros((cout, 4, cin), dtype=torch.float32, device=self.dev)
-        self._wgrad(2, n, h, w, dup, cout, x, cin, g, cin, 0)
-        self._set_grad(conv.weight, g.permute(2, 0, 1).reshape(cin, cout, 2, 2))
+        dw = self._grad_buf(conv.weight)                   # [cin, cout, 2, 2]
+        self._wgrad_reduce([self._wgrad(2, n, h, w, dup, cout, x, cin)], cout, 1, dw)
+        self._set_grad(conv.weight, dw)
         # data gradient = 2x2 stride-2 convolution of d(up) with W[ci][co][q]
         packed = self._packs["bufs"][conv][1]
         dx = torch.empty((n, h, w, cin), dtype=torch.bfloat16, device=self.dev)
