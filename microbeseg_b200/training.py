@@ -82,6 +82,40 @@ class GradBuckets:
         self._works = []
 
 
+def _pad64(c):
+    return (int(c) + 63) // 64 * 64
+
+
+class _Padded:
+    """Zero-padded fp32 twin of a parameter / buffer whose channel dimensions are not multiples of 64 (the reference's
+    low-memory fallback nets, filters = [32, 512] / [32, 256], train.py:283-288).  The tensor-core kernels work on
+    64-channel groups; padded output channels have zero weights / bias / beta, so their activations, their gradients
+    and every gradient that touches a padded input channel are EXACT zeros and the real region is sliced back out."""
+    __slots__ = ("src", "buf", "index", "writeback")
+
+    def __init__(self, src, dims, fill, writeback=False):
+        shape = list(src.shape)
+        per_dim = {}
+        for dim, parts in dims:
+            idx, off = [], 0
+            for c in parts:
+                idx.append(torch.arange(c, device=src.device) + off)
+                off += _pad64(c)
+            per_dim[dim] = torch.cat(idx)
+            shape[dim] = off
+        index, n_idx, k = [], len(per_dim), 0
+        for d in range(max(per_dim) + 1):
+            if d in per_dim:
+                view = [1] * n_idx                    # broadcastable index tensors: the result keeps the dimension order
+                view[k] = -1
+                index.append(per_dim[d].view(view))
+                k += 1
+            else:
+                index.append(slice(None))
+        self.src, self.index, self.writeback = src, tuple(index), writeback
+        self.buf = torch.full(shape, float(fill), dtype=torch.float32, device=src.device)
+
+
 class _Layer:
     __slots__ = ("name", "kind", "conv", "bn", "act", "srcs", "a", "y", "mean", "invstd", "geom", "x_f32")
 
@@ -100,9 +134,9 @@ class TrainEngine:
         elif not isinstance(net, DUNet):
             raise NotImplementedError("the distance criteria ('smooth_l1', 'l1', 'l2') train the DU (distance) network")
         net._check_supported()
-        if net._chans[0] % 64 != 0 or net.pool_method != 'conv' or net.normalization != 'bn':
-            raise NotImplementedError("the CUDA training step needs filters[0] % 64 == 0, pool_method 'conv' and normalization "
-                                      "'bn' (what the reference's TrainWorker builds, train.py:184-188)")
+        if net.pool_method != 'conv' or net.normalization != 'bn':
+            raise NotImplementedError("the CUDA training step needs pool_method 'conv' and normalization 'bn' "
+                                      "(what the reference's TrainWorker builds, train.py:184-188)")
         if net.act_fun not in ("relu", "mish"):
             raise NotImplementedError("training on the CUDA path supports act_fun='relu' (Adam recipe) and 'mish' "
                                       "(Ranger recipe), the two the reference trains with (train.py:174)")
@@ -129,6 +163,66 @@ class TrainEngine:
         self.world_size = 1
         self._capture = None
         self._packs = None
+        # narrow levels (filters[0] = 32: the reference's out-of-memory fallbacks) run zero-padded to 64 channels
+        self._pad = {}
+        if any(c % 64 for c in self.chans):
+            self._build_padding()
+
+    # ---- channel padding of the narrow nets ---------------------------------------------------------
+    def _build_padding(self):
+        net, ch = self.net, self.chans
+        nl = len(ch)
+
+        def reg(t, dims, fill=0.0, writeback=False):
+            if any(_pad64(c) != c for _, parts in dims for c in parts):
+                self._pad[t] = _Padded(t, dims, fill, writeback)
+
+        def reg_bn(bn, c):
+            reg(bn.weight, [(0, [c])], 1.0)
+            reg(bn.bias, [(0, [c])])
+            reg(bn.running_mean, [(0, [c])], 0.0, True)
+            reg(bn.running_var, [(0, [c])], 1.0, True)
+
+        def reg_conv(conv, cout, in_parts):
+            reg(conv.weight, [(0, [cout])] + ([(1, in_parts)] if in_parts else []))
+            reg(conv.bias, [(0, [cout])])
+
+        for l in range(nl):
+            blk = net.encoderConv[l]
+            reg_conv(blk.conv[0], ch[l], [ch[l - 1]] if l else None)
+            reg_bn(blk.conv[2], ch[l])
+            reg_conv(blk.conv[3], ch[l], [ch[l]])
+            reg_bn(blk.conv[5], ch[l])
+            if l < nl - 1:
+                reg_conv(net.pooling[l].conv_pool[0], ch[l], [ch[l]])
+                reg_bn(net.pooling[l].conv_pool[2], ch[l])
+        for name in net.decoder_names:
+            ups, convs = getattr(net, name + "Upconv"), getattr(net, name + "Conv")
+            for i in range(nl - 1):
+                l = nl - 2 - i
+                up = ups[i].up[0]                                   # ConvTranspose2d weight [Cin][Cout][2][2]
+                reg(up.weight, [(0, [ch[l + 1]]), (1, [ch[l]])])
+                reg(up.bias, [(0, [ch[l]])])
+                reg_bn(ups[i].norm, ch[l])
+                reg_conv(convs[i].conv[0], ch[l], [ch[l], ch[l]])      # torch.cat([up, skip]): each source padded on its own
+                reg_bn(convs[i].conv[2], ch[l])
+                reg_conv(convs[i].conv[3], ch[l], [ch[l]])
+                reg_bn(convs[i].conv[5], ch[l])
+            reg(convs[nl - 1].weight, [(1, [ch[0]])])
+
+    def _v(self, t):
+        """the tensor the kernels see: the zero-padded twin of a narrow parameter / buffer, else the tensor itself"""
+        pd = self._pad.get(t)
+        return t.detach() if pd is None else pd.buf
+
+    def _refresh_padded(self):
+        for pd in self._pad.values():
+            pd.buf[pd.index] = pd.src.detach()
+
+    def _writeback_padded(self):
+        for pd in self._pad.values():
+            if pd.writeback:
+                pd.src.copy_(pd.buf[pd.index])
 
     # ---- small helpers ------------------------------------------------------------------------
     def _ones(self, c):
@@ -149,11 +243,17 @@ class TrainEngine:
     # ---- gradient placement / data-parallel exchange ---------------------------------------------
     def _grad_buf(self, param):
         """where the kernel that produces ``param``'s gradient writes it: its slice of the flat bucket buffer"""
+        pd = self._pad.get(param)
+        if pd is not None:                              # narrow layer: the kernel fills a padded buffer, _set_grad slices it
+            return torch.empty(pd.buf.shape, dtype=torch.float32, device=self.dev)
         if self._buckets is not None:
             return self._buckets.views[param]
         return torch.empty(param.shape, dtype=torch.float32, device=self.dev)
 
     def _set_grad(self, param, tensor):
+        pd = self._pad.get(param)
+        if pd is not None:
+            tensor = tensor.reshape(pd.buf.shape)[pd.index]
         if self._buckets is None:                       # first (eager) step: remember the production order
             param.grad = tensor.reshape(param.shape).contiguous()
             self._order.append(param)
@@ -195,12 +295,12 @@ class TrainEngine:
                 convs.append((m, 0))
             elif isinstance(m, torch.nn.ConvTranspose2d):
                 convs.append((m, 1))
-        key = tuple(m.weight.data_ptr() for m, _ in convs)
+        key = tuple(self._v(m.weight).data_ptr() for m, _ in convs)
         if self._packs is None or self._packs["key"] != key:
             jobs = (nat.PackJob * len(convs))()
             bufs, tile0 = {}, 0
             for i, (m, kind) in enumerate(convs):
-                w = m.weight
+                w = self._v(m.weight)
                 if w.dtype != torch.float32 or not w.is_contiguous():
                     raise RuntimeError("training needs contiguous fp32 parameters")
                 cout, cin = (w.shape[0], w.shape[1]) if kind == 0 else (w.shape[1], w.shape[0])
@@ -244,10 +344,10 @@ class TrainEngine:
         lay.mean = torch.empty(c, dtype=torch.float32, device=self.dev)
         lay.invstd = torch.empty(c, dtype=torch.float32, device=self.dev)
         # batch statistics, y = BN(a), and the running statistics (torch defaults: momentum 0.1, unbiased variance)
-        nat.check(self.L.mbs_bn_train_fwd(a.data_ptr(), m, c, bn.weight.data_ptr(), bn.bias.data_ptr(), BN_EPS,
+        nat.check(self.L.mbs_bn_train_fwd(a.data_ptr(), m, c, self._v(bn.weight).data_ptr(), self._v(bn.bias).data_ptr(), BN_EPS,
                                           lay.y.data_ptr(), self._scratch.data_ptr(), lay.mean.data_ptr(),
-                                          lay.invstd.data_ptr(), BN_MOMENTUM, bn.running_mean.data_ptr(),
-                                          bn.running_var.data_ptr(), bn.num_batches_tracked.data_ptr(),
+                                          lay.invstd.data_ptr(), BN_MOMENTUM, self._v(bn.running_mean).data_ptr(),
+                                          self._v(bn.running_var).data_ptr(), bn.num_batches_tracked.data_ptr(),
                                           ACT_MISH if lay.act == ACT_MISH else ACT_NONE, self._sp()),
                   "bn_train_fwd")
 
@@ -278,11 +378,11 @@ class TrainEngine:
         lay = _Layer()
         lay.name, lay.kind, lay.conv, lay.bn, lay.act, lay.srcs = name, ("s2" if stride == 2 else "s1"), conv, bn, self.act, srcs
         n, h, w = srcs[0].shape[:3]
-        cout = conv.weight.shape[0]
+        cout = self._v(conv.weight).shape[0]
         ho, wo = (h // 2, w // 2) if stride == 2 else (h, w)
         lay.a = torch.empty((n, ho, wo, cout), dtype=torch.bfloat16, device=self.dev)
         self._conv(1 if stride == 2 else 0, n, h, w, srcs, self._packs["bufs"][conv][0], cout,
-                   conv.bias.detach().float(), self.conv_act, lay.a)
+                   self._v(conv.bias).float(), self.conv_act, lay.a)
         self._bn_fwd(lay)
         self.tape.append(lay)
         return lay
@@ -291,10 +391,10 @@ class TrainEngine:
         lay = _Layer()
         lay.name, lay.kind, lay.conv, lay.bn, lay.act, lay.srcs, lay.x_f32 = "enc0a", "first", conv, bn, self.act, [], x
         n, h, w = x.shape
-        c = conv.weight.shape[0]
+        c = self._v(conv.weight).shape[0]
         lay.a = torch.empty((n, h, w, c), dtype=torch.bfloat16, device=self.dev)
-        wt = conv.weight.detach().float().reshape(c, 9).contiguous()
-        b = conv.bias.detach().float().contiguous()
+        wt = self._v(conv.weight).float().reshape(c, 9).contiguous()
+        b = self._v(conv.bias).float().contiguous()
         for i in range(n):
             nat.check(self.L.mbs_first_conv(x[i].data_ptr(), 2, h, w, 0, 0, 1.0, 0.0, None, wt.data_ptr(), b.data_ptr(),
                                             self._ones(c).data_ptr(), self._zeros(c).data_ptr(), c, self.conv_act,
@@ -308,10 +408,10 @@ class TrainEngine:
         conv = block.up[0]
         lay.name, lay.kind, lay.conv, lay.bn, lay.act, lay.srcs = name, "up", conv, block.norm, ACT_NONE, [x]
         n, h, w, cin = x.shape
-        cout = conv.weight.shape[1]
+        cout = self._v(conv.weight).shape[1]
         packed = self._packs["bufs"][conv][0]
         lay.a = torch.empty((n, 2 * h, 2 * w, cout), dtype=torch.bfloat16, device=self.dev)
-        self._conv(2, n, h, w, [x], packed, cout, conv.bias.detach().float(), ACT_NONE, lay.a)
+        self._conv(2, n, h, w, [x], packed, cout, self._v(conv.bias).float(), ACT_NONE, lay.a)
         self._bn_fwd(lay)
         self.tape.append(lay)
         return lay
@@ -394,6 +494,7 @@ class TrainEngine:
         self.tape = []
         with torch.cuda.device(self.dev), torch.no_grad():
             x = img.reshape(n, H, W).contiguous().float()
+            self._refresh_padded()
             self._pack_all()
             # ---------------- forward ----------------
             enc_a, enc_b, pools = [], [], []
@@ -427,7 +528,7 @@ class TrainEngine:
                 dec[name] = chain
                 head = convs[nl - 1]
                 n_out = head.weight.shape[0]
-                hw = head.weight.detach().float().reshape(n_out, -1).contiguous()
+                hw = self._v(head.weight).float().reshape(n_out, -1).contiguous()
                 pred = torch.empty((n_out, n, H, W), dtype=torch.float32, device=self.dev)      # planar per output channel
                 for k in range(n_out):
                     nat.check(self.L.mbs_head_fwd(xcur.data_ptr(), n * H * W, hw.shape[1], hw[k].data_ptr(), head.bias[k:k + 1].data_ptr(),
@@ -491,6 +592,7 @@ class TrainEngine:
                 dy = self._bwd_conv(enc_a[l], dy)[0]          # gradient w.r.t. pool_{l-1}.y
                 dsk = self._bwd_conv(pools[l - 1], dy)[0]      # ... w.r.t. skip_{l-1}
                 dy = self._sum(skip_grads[l - 1] + [dsk])
+            self._writeback_padded()
         self.tape = []
         return loss[0]
 
@@ -514,7 +616,7 @@ class TrainEngine:
         dgb = torch.empty(2 * c, dtype=torch.float32, device=self.dev)
         dbias = torch.empty(c, dtype=torch.float32, device=self.dev)
         nat.check(self.L.mbs_bn_train_bwd(dy.data_ptr(), a.data_ptr(), m, c, lay.mean.data_ptr(), lay.invstd.data_ptr(),
-                                          bn.weight.data_ptr(), lay.act, dz.data_ptr(), dgb.data_ptr(), dbias.data_ptr(),
+                                          self._v(bn.weight).data_ptr(), lay.act, dz.data_ptr(), dgb.data_ptr(), dbias.data_ptr(),
                                           self._scratch.data_ptr(), self._sp()), "bn_train_bwd")
         self._set_grad(bn.weight, dgb[:c])
         self._set_grad(bn.bias, dgb[c:])

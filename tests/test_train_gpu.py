@@ -44,7 +44,11 @@ def _reference(sd, img, bl, cl, autocast=False, act="relu"):
 
 @pytest.mark.parametrize("filters,n,h,w,act", [((64, 128), 2, 32, 48, "relu"), ((64, 256), 3, 64, 64, "relu"),
                                                ((64, 1024), 2, 128, 96, "relu"), ((64, 256), 2, 64, 48, "mish"),
-                                               ((64, 1024), 2, 96, 128, "mish")])
+                                               ((64, 1024), 2, 96, 128, "mish"),
+                                               # the reference's out-of-memory fallbacks (train.py:283-288): 32-channel
+                                               # levels run zero-padded to 64 channels, gradients sliced back
+                                               ((32, 128), 2, 32, 48, "relu"), ((32, 512), 2, 64, 64, "relu"),
+                                               ((32, 256), 2, 64, 48, "mish")])
 def test_loss_and_gradients_vs_torch_autograd(native_lib, filters, n, h, w, act):
     """relu = the Adam recipe, mish = the Ranger recipe (train.py:174)"""
     net, sd, eng, img, bl, cl = _setup(filters, 7, n, h, w, act=act)
@@ -90,6 +94,25 @@ def test_running_statistics_and_optimizer_step(native_lib):
     assert not torch.equal(rm0, net.encoderConv[0].conv[2].running_mean)
     assert int(net.encoderConv[0].conv[2].num_batches_tracked) == 100 + 8       # seeded state dict starts at 100
     net.eval()                                                      # and the trained weights run on the inference path
+    with torch.no_grad():
+        b, c = net(img)
+    assert torch.isfinite(b).all() and torch.isfinite(c).all()
+
+
+def test_narrow_fallback_net_trains(native_lib):
+    """filters = [32, 512]-style nets (train.py:283-288): captured steps with the fused Adam; the 32-wide BatchNorm
+    buffers get their running statistics back from the padded twins and the trained weights run on the inference path."""
+    from microbeseg_b200.adam import Adam
+    from microbeseg_b200.training import train_step
+    net, sd, eng, img, bl, cl = _setup((32, 128), 5, 2, 32, 32, graph=True)
+    opt = Adam(net.parameters(), lr=8e-4, betas=(0.9, 0.999), eps=1e-08, weight_decay=0, amsgrad=True)
+    bn0 = net.encoderConv[0].conv[2]
+    rm0 = bn0.running_mean.clone()
+    losses = [float(train_step(eng, opt, img, bl, cl)) for _ in range(8)]
+    assert losses[-1] < losses[0], losses
+    assert bn0.running_mean.shape == (32,) and not torch.equal(rm0, bn0.running_mean)
+    assert all(p.grad is not None and p.grad.shape == p.shape for p in net.parameters())
+    net.eval()
     with torch.no_grad():
         b, c = net(img)
     assert torch.isfinite(b).all() and torch.isfinite(c).all()
