@@ -157,28 +157,32 @@ __global__ void __launch_bounds__(256) bn_stats_kernel(const __nv_bfloat16 *__re
     block_channel_atomic<2, true>(acc, C, threadIdx.x < ppb * tpp ? c0 : C, sums);
 }
 
-// out[i] = sum over blocks of part[b][i].  32 consecutive i per CTA (128-byte rows), 8 thread rows split the blocks and
-// combine through shared memory in a fixed order (deterministic); a 1-D version with one thread per i walked ~300
-// dependent-latency loads and took 23 us per call.
-__global__ void __launch_bounds__(256) reduce_partials_kernel(const float *__restrict__ part, int nblocks, int n, float *__restrict__ out) {
-    __shared__ float s_part[8][33];
+// out[i] = sum over blocks of part[b][i].  32 consecutive i per CTA (128-byte rows), 32 thread rows split the blocks
+// (<= 19 independent loads per thread: these launches are pure latency) and combine through shared memory in a fixed
+// order (deterministic).
+constexpr int RP_ROWS = 32;
+__device__ __forceinline__ float column_partial(const float *__restrict__ part, int nblocks, int n, int i, int ty) {
+    float s0 = 0.0f, s1 = 0.0f, s2 = 0.0f, s3 = 0.0f;
+    int b = ty;
+    for (; b + 3 * RP_ROWS < nblocks; b += 4 * RP_ROWS) {
+        s0 += part[static_cast<size_t>(b) * n + i];
+        s1 += part[static_cast<size_t>(b + RP_ROWS) * n + i];
+        s2 += part[static_cast<size_t>(b + 2 * RP_ROWS) * n + i];
+        s3 += part[static_cast<size_t>(b + 3 * RP_ROWS) * n + i];
+    }
+    for (; b < nblocks; b += RP_ROWS) s0 += part[static_cast<size_t>(b) * n + i];
+    return (s0 + s1) + (s2 + s3);
+}
+__global__ void __launch_bounds__(32 * RP_ROWS) reduce_partials_kernel(const float *__restrict__ part, int nblocks, int n, float *__restrict__ out) {
+    __shared__ float s_part[RP_ROWS][33];
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const int i = blockIdx.x * 32 + tx;
-    float s0 = 0.0f, s1 = 0.0f;
-    if (i < n) {
-        int b = ty;
-        for (; b + 8 < nblocks; b += 16) {
-            s0 += part[static_cast<size_t>(b) * n + i];
-            s1 += part[static_cast<size_t>(b + 8) * n + i];
-        }
-        if (b < nblocks) s0 += part[static_cast<size_t>(b) * n + i];
-    }
-    s_part[ty][tx] = s0 + s1;
+    s_part[ty][tx] = i < n ? column_partial(part, nblocks, n, i, ty) : 0.0f;
     __syncthreads();
     if (ty == 0 && i < n) {
         float t = 0.0f;
 #pragma unroll
-        for (int k = 0; k < 8; ++k) t += s_part[k][tx];
+        for (int k = 0; k < RP_ROWS; ++k) t += s_part[k][tx];
         out[i] = t;
     }
 }
@@ -186,33 +190,21 @@ __global__ void __launch_bounds__(256) reduce_partials_kernel(const float *__res
 // reduce_partials_kernel (both accumulators of 32 channels per CTA, same summation order) + bn_finalize_kernel in one
 // launch: part[b][2][C] per-block sums -> sums[c] = gamma*invstd, sums[C+c] = beta - mean*gamma*invstd, mean, invstd and
 // the running statistics.
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(32 * RP_ROWS)
 bn_reduce_finalize_kernel(const float *__restrict__ part, int nblocks, float *sums, long long M, int C, float eps,
                           const float *__restrict__ gamma, const float *__restrict__ beta, float *mean, float *invstd, float momentum,
                           float *running_mean, float *running_var, long long *num_batches_tracked) {
-    __shared__ float s_part[2][8][33];
+    __shared__ float s_part[2][RP_ROWS][33];
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const int c = blockIdx.x * 32 + tx;
     const int n = 2 * C;
-#pragma unroll
-    for (int a = 0; a < 2; ++a) {
-        const int i = a * C + c;
-        float s0 = 0.0f, s1 = 0.0f;
-        if (c < C) {
-            int b = ty;
-            for (; b + 8 < nblocks; b += 16) {
-                s0 += part[static_cast<size_t>(b) * n + i];
-                s1 += part[static_cast<size_t>(b + 8) * n + i];
-            }
-            if (b < nblocks) s0 += part[static_cast<size_t>(b) * n + i];
-        }
-        s_part[a][ty][tx] = s0 + s1;
-    }
+    s_part[0][ty][tx] = c < C ? column_partial(part, nblocks, n, c, ty) : 0.0f;
+    s_part[1][ty][tx] = c < C ? column_partial(part, nblocks, n, C + c, ty) : 0.0f;
     __syncthreads();
     if (ty != 0 || c >= C) return;
     float t0 = 0.0f, t1 = 0.0f;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) { t0 += s_part[0][k][tx]; t1 += s_part[1][k][tx]; }
+    for (int k = 0; k < RP_ROWS; ++k) { t0 += s_part[0][k][tx]; t1 += s_part[1][k][tx]; }
     const double m = static_cast<double>(t0) / static_cast<double>(M);
     double var = static_cast<double>(t1) / static_cast<double>(M) - m * m;
     if (var < 0.0) var = 0.0;
@@ -651,7 +643,7 @@ template <int TAPS, int CI, int SG, int LAYOUT>
 __global__ void __launch_bounds__(CI * SG)
 wgrad_reduce_kernel(const float *__restrict__ part0, int splits0, int cn0, const float *__restrict__ part1, int splits1, int cn1,
                     int Cm, float *__restrict__ out) {
-    __shared__ float s_sum[SG][TAPS][CI + 1];
+    __shared__ float s_sum[SG][TAPS][CI + 1];          // SG = 16, TAPS = 9: 37 KB
     const int co = blockIdx.x;
     const int ci0 = blockIdx.y * CI;                       // channel offset in the concatenated input
     const bool second = ci0 >= cn0;
@@ -831,7 +823,7 @@ extern "C" int mbs_bn_train_fwd(const void *a, long long M, int C, const float *
     else
         bn_stats_kernel<false><<<grid, 256, 0, stream>>>(static_cast<const __nv_bfloat16 *>(a), M, C, part);
     MBS_CHECK_LAUNCH();
-    bn_reduce_finalize_kernel<<<mbs::cdiv(C, 32), 256, 0, stream>>>(part, grid, sums_scratch, M, C, eps, gamma, beta, mean, invstd,
+    bn_reduce_finalize_kernel<<<mbs::cdiv(C, 32), 32 * RP_ROWS, 0, stream>>>(part, grid, sums_scratch, M, C, eps, gamma, beta, mean, invstd,
                                                                     momentum, running_mean, running_var, num_batches_tracked);
     MBS_CHECK_LAUNCH();
     if (act == MBS_ACT_MISH)
@@ -853,7 +845,7 @@ extern "C" int mbs_sample_group_norm(const void *a, long long M, int C, int grou
     float *part = scratch + 2 * C;
     bn_stats_kernel<false><<<grid, 256, 0, stream>>>(static_cast<const __nv_bfloat16 *>(a), M, C, part);
     MBS_CHECK_LAUNCH();
-    reduce_partials_kernel<<<mbs::cdiv(2 * C, 32), 256, 0, stream>>>(part, grid, 2 * C, scratch);
+    reduce_partials_kernel<<<mbs::cdiv(2 * C, 32), 32 * RP_ROWS, 0, stream>>>(part, grid, 2 * C, scratch);
     MBS_CHECK_LAUNCH();
     group_norm_finalize_kernel<<<1, 256, 2 * groups * sizeof(float), stream>>>(scratch, M, C, groups, eps, gamma, beta);
     MBS_CHECK_LAUNCH();
@@ -880,13 +872,13 @@ extern "C" int mbs_bn_train_bwd(const void *dy, const void *a, long long M, int 
         bn_bwd_reduce_kernel<false><<<grid, 256, 0, stream>>>(static_cast<const __nv_bfloat16 *>(dy),
                                                               static_cast<const __nv_bfloat16 *>(a), M, C, mean, invstd, part);
     MBS_CHECK_LAUNCH();
-    reduce_partials_kernel<<<mbs::cdiv(2 * C, 32), 256, 0, stream>>>(part, grid, 2 * C, dgamma_dbeta);
+    reduce_partials_kernel<<<mbs::cdiv(2 * C, 32), 32 * RP_ROWS, 0, stream>>>(part, grid, 2 * C, dgamma_dbeta);
     MBS_CHECK_LAUNCH();
     bn_bwd_apply_kernel<<<grid, 256, 0, stream>>>(static_cast<const __nv_bfloat16 *>(dy), static_cast<const __nv_bfloat16 *>(a), M,
                                                   C, mean, invstd, gamma, dgamma_dbeta, act, static_cast<__nv_bfloat16 *>(dz),
                                                   part);
     MBS_CHECK_LAUNCH();
-    reduce_partials_kernel<<<mbs::cdiv(C, 32), 256, 0, stream>>>(part, grid, C, dbias);
+    reduce_partials_kernel<<<mbs::cdiv(C, 32), 32 * RP_ROWS, 0, stream>>>(part, grid, C, dbias);
     MBS_CHECK_LAUNCH();
     return 0;
 }
@@ -934,9 +926,9 @@ extern "C" int mbs_head_bwd(const float *g, const void *y, long long M, int C, c
     head_bwd_kernel<<<grid, 256, 0, stream>>>(g, static_cast<const __nv_bfloat16 *>(y), M, C, w, static_cast<__nv_bfloat16 *>(dy), part_dw,
                                               part_db);
     MBS_CHECK_LAUNCH();
-    reduce_partials_kernel<<<mbs::cdiv(C, 32), 256, 0, stream>>>(part_dw, grid, C, dw_db);
+    reduce_partials_kernel<<<mbs::cdiv(C, 32), 32 * RP_ROWS, 0, stream>>>(part_dw, grid, C, dw_db);
     MBS_CHECK_LAUNCH();
-    reduce_partials_kernel<<<1, 256, 0, stream>>>(part_db, grid, 1, dw_db + C);
+    reduce_partials_kernel<<<1, 32 * RP_ROWS, 0, stream>>>(part_db, grid, 1, dw_db + C);
     MBS_CHECK_LAUNCH();
     return 0;
 }
@@ -976,10 +968,10 @@ extern "C" int mbs_wgrad_reduce(const float *part0, int splits0, int cn0, const 
     const dim3 grid(Cm, (cn0 + cn1) / 64);
     const bool many = splits0 >= 8 || splits1 >= 8;
     if (layout == 0) {
-        if (many) wgrad_reduce_kernel<9, 64, 4, 0><<<grid, 256, 0, stream>>>(part0, splits0, cn0, part1, splits1, cn1, Cm, out);
+        if (many) wgrad_reduce_kernel<9, 64, 16, 0><<<grid, 1024, 0, stream>>>(part0, splits0, cn0, part1, splits1, cn1, Cm, out);
         else wgrad_reduce_kernel<9, 64, 1, 0><<<grid, 64, 0, stream>>>(part0, splits0, cn0, part1, splits1, cn1, Cm, out);
     } else {
-        if (many) wgrad_reduce_kernel<4, 64, 4, 1><<<grid, 256, 0, stream>>>(part0, splits0, cn0, nullptr, 0, 0, Cm, out);
+        if (many) wgrad_reduce_kernel<4, 64, 16, 1><<<grid, 1024, 0, stream>>>(part0, splits0, cn0, nullptr, 0, 0, Cm, out);
         else wgrad_reduce_kernel<4, 64, 1, 1><<<grid, 64, 0, stream>>>(part0, splits0, cn0, nullptr, 0, 0, Cm, out);
     }
     MBS_CHECK_LAUNCH();
@@ -1024,7 +1016,7 @@ extern "C" int mbs_first_conv_wgrad(const float *x, const void *dz, int N, int H
     const int grid = grid_rows(M, C);          // scratch: grid * C * 9 floats (<= mbs_bn_scratch_floats(2048))
     first_conv_wgrad_kernel<<<grid, 256, 0, stream>>>(x, static_cast<const __nv_bfloat16 *>(dz), N, H, W, C, scratch);
     MBS_CHECK_LAUNCH();
-    reduce_partials_kernel<<<mbs::cdiv(C * 9, 32), 256, 0, stream>>>(scratch, grid, C * 9, dw);
+    reduce_partials_kernel<<<mbs::cdiv(C * 9, 32), 32 * RP_ROWS, 0, stream>>>(scratch, grid, C * 9, dw);
     MBS_CHECK_LAUNCH();
     return 0;
 }

@@ -1238,6 +1238,140 @@ wgrad_halo64_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 }
 
 // ------------------------------------------------------------------------------------------
+// Weight gradient of the wide stride-1 layers (Cout, Cin multiples of 128): one filter ROW per CTA.
+//
+// The generic kernel streams 48 KiB of operands per 512 MMA cycles (94 B/clk/SM); both operands are private to the CTA,
+// so nothing is shared in L2 and the chip-wide L2 -> SM bandwidth (~42 B/clk/SM) caps it at ~750 TFLOP/s.  Here a CTA
+// owns 128 output channels x 128 input channels x the three taps (ky, 0..2): per 8x8 pixel patch it loads x once
+// (2 x 8 KiB) and dz with a 1-pixel halo once (2 x 12.5 KiB) for 3 x 4 MMAs of 64 cycles = 54 B/clk/SM.  Same operand
+// trick as wgrad_halo64_kernel: sum_o dz[o] x[o+t] = sum_p dz[p-t] x[p], tap t reads the halo patch from pixel offset
+// (2-ky)*10 + (2-kx); the two 64-channel blocks of the A tile are the two halo slots (leading byte offset = slot size).
+// ------------------------------------------------------------------------------------------
+constexpr int W3_A_SLOT = 13 * 1024;
+constexpr int W3_STAGE = 2 * W3_A_SLOT + 2 * WG_BLOCK;         // 42 KiB
+constexpr int W3_STAGES = 5;
+constexpr int W3_DYN = W3_STAGES * W3_STAGE + 8 * (2 * W3_STAGES + 1) + 16 + 1024;
+
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+wgrad_row3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const WgradNhwcParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t base = (raw + 1023u) & ~1023u;
+    uint8_t *gbase = smem_raw + (base - raw);
+    const uint32_t sBar = base + W3_STAGES * W3_STAGE;
+    auto full_bar = [&](int s) { return sBar + 8u * s; };
+    auto empty_bar = [&](int s) { return sBar + 8u * (W3_STAGES + s); };
+    const uint32_t tfull_bar = sBar + 8u * (2 * W3_STAGES);
+    volatile uint32_t *tmem_ptr = reinterpret_cast<volatile uint32_t *>(gbase + W3_STAGES * W3_STAGE + 8 * (2 * W3_STAGES + 1));
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    int t = blockIdx.x;
+    const int split = t % p.splits; t /= p.splits;
+    const int ky = t % 3; t /= 3;
+    const int n_tile = t % p.n_tiles;
+    const int m_tile = t / p.n_tiles;
+    const int m0 = m_tile * 128, n0 = n_tile * 128;
+    const int patches = p.N * p.ptx * p.pty;
+    const int k0 = split * p.per;
+    const int k1 = min(patches, k0 + p.per);
+    const int num_k_iters = max(0, k1 - k0);
+
+    if (threadIdx.x == 0) {
+        prefetch_tmap(&tmA);
+        prefetch_tmap(&tmB);
+        for (int s = 0; s < W3_STAGES; ++s) {
+            mbar_init(full_bar(s), 1);
+            mbar_init(empty_bar(s), 1);
+        }
+        mbar_init(tfull_bar, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(smem_u32(const_cast<uint32_t *>(tmem_ptr)), 512);
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    if (num_k_iters > 0) {
+        if (warp == 0) {
+            if (lane == 0) {
+                const int ppi = p.ptx * p.pty;
+                int it = 0;
+                for (int k = k0; k < k1; ++k, ++it) {
+                    const int img = k / ppi;
+                    const int r = k - img * ppi;
+                    const int oy0 = (r / p.ptx) * 8, ox0 = (r % p.ptx) * 8;
+                    const int s = it % W3_STAGES;
+                    const uint32_t ph = (it / W3_STAGES) & 1;
+                    const uint32_t st = base + s * W3_STAGE;
+                    mbar_wait(empty_bar(s), ph ^ 1u);
+                    mbar_expect_tx(full_bar(s), 2 * 100 * 128 + 2 * WG_BLOCK);
+                    tma_load_4d(st, &tmA, full_bar(s), m0, ox0 - 1, oy0 - 1, img);                      // dz, 10 x 10 halo boxes
+                    tma_load_4d(st + W3_A_SLOT, &tmA, full_bar(s), m0 + 64, ox0 - 1, oy0 - 1, img);
+                    tma_load_4d(st + 2 * W3_A_SLOT, &tmB, full_bar(s), n0, ox0, oy0, img);              // x, 8 x 8 boxes
+                    tma_load_4d(st + 2 * W3_A_SLOT + WG_BLOCK, &tmB, full_bar(s), n0 + 64, ox0, oy0, img);
+                }
+            }
+            __syncwarp();
+        } else if (warp == 1) {
+            if (lane == 0) {
+                constexpr uint32_t idesc = make_idesc(BM, 128) | (1u << 15) | (1u << 16);
+                for (int it = 0; it < num_k_iters; ++it) {
+                    const int s = it % W3_STAGES;
+                    const uint32_t ph = (it / W3_STAGES) & 1;
+                    mbar_wait(full_bar(s), ph);
+                    tcgen05_fence_after();
+                    const uint32_t a_slot = base + s * W3_STAGE, b_slot = a_slot + 2 * W3_A_SLOT;
+#pragma unroll
+                    for (int kx = 0; kx < 3; ++kx) {
+                        const int off = (2 - ky) * 10 + (2 - kx);          // halo pixel offset of tap (ky, kx)
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {                      // 16 pixels = two 8-pixel patch rows per MMA
+                            const uint64_t adesc = make_sw128_mn_desc2(a_slot + off * 128 + k * 2 * 1280, W3_A_SLOT, 1280);
+                            const uint64_t bdesc = make_sw128_mn_desc2(b_slot + k * 2048, WG_BLOCK, 1024);
+                            umma_f16(tmem_base + static_cast<uint32_t>(kx * 128), adesc, bdesc, idesc, (it > 0 || k > 0) ? 1u : 0u);
+                        }
+                    }
+                    umma_commit(empty_bar(s));
+                }
+                umma_commit(tfull_bar);
+            }
+            __syncwarp();
+        } else {
+            const int e = warp - 2, quad = warp & 3, half = e >> 2;
+            const int m = m0 + quad * 32 + lane;                       // output channel (TMEM lane)
+            mbar_wait(tfull_bar, 0);
+            tcgen05_fence_after();
+#pragma unroll 1
+            for (int c = half * 192; c < (half + 1) * 192; c += 32) {
+                uint32_t r[32];
+                tmem_ld32(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(c), r);
+                const int tap = ky * 3 + (c >> 7);
+                const int n = n0 + (c & 127);
+                if (p.partial) {
+                    float *dst = p.out + ((static_cast<size_t>(split) * p.Cm + m) * 9 + tap) * p.Cn + n;
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4)
+                        st_v4(dst + j, __uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+                } else {
+                    float *dst = p.out + (static_cast<size_t>(m) * 9 + tap) * p.out_ld + p.out_coff + n;
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4)
+                        red_add_v4(dst + j, __uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
+                                   __uint_as_float(r[j + 3]));
+                }
+            }
+            tcgen05_fence_before();
+        }
+    }
+    __syncthreads();
+    if (warp == 1) {
+        tcgen05_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // first layer: normalise + pad + Conv2d(1,C,3,p=1) + act + BN(eval), CUDA cores (K = 9)
 // ------------------------------------------------------------------------------------------
 // Block = 32x8 output pixels.  The normalised (and padded) input patch incl. its 1-pixel halo is staged
@@ -1577,6 +1711,15 @@ bool wgrad_halo_enabled() {
     return v == 1;
 }
 
+bool wgrad_row3_enabled() {      // MBS_NO_WGRAD_ROW3=1 (A/B runs): wide stride-1 layers through the generic kernel
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("MBS_NO_WGRAD_ROW3");
+        v = (e && e[0] == '1') ? 0 : 1;
+    }
+    return v == 1;
+}
+
 bool wgrad_stack_enabled() {     // MBS_NO_WGRAD_STACK=1 (A/B runs): one tap per N tile for the narrow layers
     static int v = -1;
     if (v < 0) {
@@ -1751,9 +1894,22 @@ int launch_wgrad_nhwc(const CUtensorMap &a, const CUtensorMap &b, const WgradNhw
 namespace {
 struct WgradPlan {
     WgradNhwcParams wp;
-    bool halo;
+    bool halo, row3;
     int bn, grid;
 };
+// The weight-gradient kernels hold one CTA per SM (~190 KB of operand stages): fill ONE wave when the tiles fit, otherwise
+// the split (<= 4) with the fewest wave-equivalents; fewer splits = less partial-tile traffic.
+int split_rule(int tiles) {
+    const int sms = sm_count();
+    if (tiles <= sms) return sms / tiles;
+    int splits = 1;
+    double best = 1e30;
+    for (int sp = 1; sp <= 4; ++sp) {
+        const double cost = static_cast<double>(mbs::cdiv(tiles * sp, sms)) / sp;
+        if (cost < best - 1e-9) { best = cost; splits = sp; }
+    }
+    return splits;
+}
 // one place decides tiling and the K split, so that mbs_conv_wgrad_splits() and the launch always agree
 int plan_wgrad(const mbs_wgrad_desc *d, WgradPlan &pl) {
     MBS_REQUIRE(d != nullptr && d->kind >= 0 && d->kind <= 2, "wgrad: bad descriptor");
@@ -1783,8 +1939,20 @@ int plan_wgrad(const mbs_wgrad_desc *d, WgradPlan &pl) {
     wp.pty = mbs::cdiv(d->Ho, wp.ph);
     wp.tpi = 1;
     pl.halo = d->kind == 0 && d->Cm == 64 && d->Wo >= 8 && d->Ho >= 8 && wgrad_halo_enabled();
+    pl.row3 = !pl.halo && d->kind == 0 && d->Cm % 128 == 0 && d->Cn % 128 == 0 && d->Wo >= 8 && d->Ho >= 8 && wgrad_row3_enabled();
     int splits;
-    if (pl.halo) {
+    if (pl.row3) {
+        // wide stride-1 layers: one filter row (three taps) per CTA from one halo patch (see wgrad_row3_kernel)
+        wp.pw = wp.ph = 8;
+        wp.ptx = mbs::cdiv(d->Wo, 8);
+        wp.pty = mbs::cdiv(d->Ho, 8);
+        pl.bn = 128;
+        wp.cn_tile = 128;
+        wp.m_tiles = d->Cm / 128;
+        wp.n_tiles = d->Cn / 128;
+        wp.tap_items = 3;
+        splits = split_rule(wp.m_tiles * wp.n_tiles * 3);
+    } else if (pl.halo) {
         // full-resolution layers: all nine taps per CTA from one halo patch (see wgrad_halo64_kernel)
         wp.pw = wp.ph = 8;
         wp.ptx = mbs::cdiv(d->Wo, 8);
@@ -1805,26 +1973,14 @@ int plan_wgrad(const mbs_wgrad_desc *d, WgradPlan &pl) {
         pl.bn = bn;
         wp.m_tiles = wp.pair ? 1 : mbs::cdiv(d->Cm, 128);
         wp.n_tiles = d->Cn / wp.cn_tile;
-        // the kernels hold one CTA per SM (192 KB of operand stages): fill ONE wave when the tiles fit, otherwise the split
-        // (<= 4) with the fewest wave-equivalents; fewer splits = less partial-tile traffic
-        const int tiles = wp.m_tiles * wp.n_tiles * wp.tap_items, sms = sm_count();
-        if (tiles <= sms) {
-            splits = sms / tiles;
-        } else {
-            splits = 1;
-            double best = 1e30;
-            for (int sp = 1; sp <= 4; ++sp) {
-                const double cost = static_cast<double>(mbs::cdiv(tiles * sp, sms)) / sp;
-                if (cost < best - 1e-9) { best = cost; splits = sp; }
-            }
-        }
+        splits = split_rule(wp.m_tiles * wp.n_tiles * wp.tap_items);
     }
     const int patches = d->N * wp.ptx * wp.pty;
     if (splits > patches) splits = patches;
     if (splits < 1) splits = 1;
     wp.per = mbs::cdiv(patches, splits);
     wp.splits = mbs::cdiv(patches, wp.per);              // every split owns at least one patch
-    pl.grid = (pl.halo ? d->Cn / 64 : wp.m_tiles * wp.n_tiles * wp.tap_items) * wp.splits;
+    pl.grid = (pl.halo ? d->Cn / 64 : wp.m_tiles * wp.n_tiles * wp.tap_items) * wp.splits;     // row3: tap_items = 3 rows
     return 0;
 }
 }  // namespace
@@ -1845,6 +2001,21 @@ extern "C" int mbs_conv_wgrad(const mbs_wgrad_desc *d, void *stream_) {
                 "wgrad: the gradient buffer must allow 16-byte vector accesses");
     const WgradNhwcParams &wp = pl.wp;
     CUtensorMap a, b;
+    if (pl.row3) {
+        rc = make_act_map(&a, d->a, d->N, d->Ho, d->Wo, d->Cm, d->lda, d->coffa, 1, 10, 10);
+        if (rc) return rc;
+        rc = make_act_map(&b, d->b, d->N, d->Ho, d->Wo, d->Cn, d->ldb, d->coffb, 1, 8, 8);
+        if (rc) return rc;
+        static bool configured[mbs::kMaxDevices] = {false};
+        const int dev = mbs::current_device();
+        if (!configured[dev]) {
+            MBS_CHECK_CUDA(cudaFuncSetAttribute(wgrad_row3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, W3_DYN));
+            configured[dev] = true;
+        }
+        wgrad_row3_kernel<<<pl.grid, NUM_THREADS, W3_DYN, stream>>>(a, b, wp);
+        MBS_CHECK_LAUNCH();
+        return 0;
+    }
     if (pl.halo) {
         rc = make_act_map(&a, d->a, d->N, d->Ho, d->Wo, d->Cm, d->lda, d->coffa, 1, 10, 10);
         if (rc) return rc;
