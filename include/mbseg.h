@@ -254,8 +254,9 @@ int mbs_labels_max_mal(const uint16_t *masks, int n_crops, int H, int W, int max
  * search_radius < 0: derived per crop from its own max_mal on the device; radius_hint (>= the
  * largest radius in the batch, or -1) only sizes the shared-memory window.
  * cell_dist / neighbor_dist: float32 [n_crops][H][W].  error_out (optional, int32 [n_crops]):
- * bit 0 = an instance window/bounding box did not fit in shared memory, bit 1 = more than 4096
- * gap components. */
+ * bit 0 = the bounding box of an instance wider than 58 px did not fit the closing kernel's shared memory
+ * (> ~110 k pixels), bit 1 = more than 4096 gap components.  EDT search windows of any size are handled
+ * (shared memory, or a per-crop global buffer for windows that do not fit). */
 int mbs_distance_labels(const uint16_t *masks, int n_crops, int H, int W, int max_id, int search_radius,
                         int radius_hint, float *cell_dist, float *neighbor_dist, int32_t *max_mal_out,
                         int32_t *error_out, void *workspace, size_t workspace_bytes, void *stream);

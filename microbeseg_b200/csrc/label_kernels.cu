@@ -140,25 +140,15 @@ __global__ void lab_window_kernel(CellStats *cs, int ids, int total, int H, int 
 // one CTA per (instance, crop): exact EDT of the instance and of "everything but the other
 // instances" inside the search window (distance_label :280-330)
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
-lab_cell_kernel(const uint16_t *__restrict__ masks, int H, int W, int ids, const CellStats *cs, CropInfo *info,
-                float *__restrict__ cell_dist, double *__restrict__ nraw, int smem_cap_elems) {
-    const int crop = blockIdx.y;
-    const int id = blockIdx.x + 1;
-    if (id >= ids) return;
-    const CellStats s = cs[static_cast<size_t>(crop) * ids + id];
-    if (s.cnt == 0) return;
-    const int wh = s.wy1 - s.wy0, ww = s.wx1 - s.wx0;
-    if (wh <= 0 || ww <= 0) return;           // empty crop: np.max(...) of an empty EDT -> skipped
-    if (wh * ww > smem_cap_elems) {
-        if (threadIdx.x == 0) atomicOr(&info[crop].error, 1);
-        return;
-    }
-    extern __shared__ unsigned short sm[];
+// `sm`: 3 * wh * ww unsigned shorts of scratch -- shared memory (lab_cell_kernel) or, for windows that do not fit, a
+// per-crop global buffer (lab_cell_big_kernel); every exit is block-uniform, so the function can be called in a loop.
+__device__ void cell_edt(const uint16_t *__restrict__ masks, int H, int W, int crop, int id, const CellStats &s, int wh, int ww,
+                         unsigned short *sm, float *__restrict__ cell_dist, double *__restrict__ nraw) {
     unsigned short *lab = sm;                 // [wh][ww] labels
     unsigned short *g1 = sm + wh * ww;        // vertical distance to the nearest pixel with label != id (own pixels)
     unsigned short *g2 = g1 + wh * ww;        // vertical distance to the nearest pixel of ANOTHER instance
     __shared__ unsigned int s_max1, s_max2, s_any_bg, s_any_other, s_any_own;
+    __syncthreads();                          // a previous call's readers of the shared flags are done
     if (threadIdx.x == 0) { s_max1 = 0; s_max2 = 0; s_any_bg = 0; s_any_other = 0; s_any_own = 0; }
     const uint16_t *m = masks + static_cast<size_t>(crop) * H * W;
     for (int i = threadIdx.x; i < wh * ww; i += blockDim.x) {
@@ -262,6 +252,38 @@ lab_cell_kernel(const uint16_t *__restrict__ masks, int H, int W, int ids, const
             v = 1.0 - q;                                                  // :327 (own mask == 1 here)
         }
         nraw[o] = v;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+lab_cell_kernel(const uint16_t *__restrict__ masks, int H, int W, int ids, const CellStats *cs, CropInfo *info,
+                float *__restrict__ cell_dist, double *__restrict__ nraw, int smem_cap_elems) {
+    const int crop = blockIdx.y;
+    const int id = blockIdx.x + 1;
+    if (id >= ids) return;
+    const CellStats s = cs[static_cast<size_t>(crop) * ids + id];
+    if (s.cnt == 0) return;
+    const int wh = s.wy1 - s.wy0, ww = s.wx1 - s.wx0;
+    if (wh <= 0 || ww <= 0) return;           // empty crop: np.max(...) of an empty EDT -> skipped
+    if (wh * ww > smem_cap_elems) return;     // window larger than shared memory: lab_cell_big_kernel takes it
+    extern __shared__ unsigned short sm[];
+    cell_edt(masks, H, W, crop, id, s, wh, ww, sm, cell_dist, nraw);
+}
+
+// Instances whose search window exceeds shared memory (max_mal >~ 130 px): one CTA per crop walks them one after the
+// other with the window state in a per-crop global buffer (3 * H * W unsigned shorts).  Rare and slow, but exact -- the
+// reference has no size limit (train_data_representations.py:280-330).
+__global__ void __launch_bounds__(256)
+lab_cell_big_kernel(const uint16_t *__restrict__ masks, int H, int W, int ids, const CellStats *cs, unsigned short *scratch,
+                    size_t scratch_stride, float *__restrict__ cell_dist, double *__restrict__ nraw, int smem_cap_elems) {
+    const int crop = blockIdx.x;
+    unsigned short *sm = scratch + static_cast<size_t>(crop) * scratch_stride;
+    for (int id = 1; id < ids; ++id) {
+        const CellStats s = cs[static_cast<size_t>(crop) * ids + id];
+        if (s.cnt == 0) continue;
+        const int wh = s.wy1 - s.wy0, ww = s.wx1 - s.wx0;
+        if (wh <= 0 || ww <= 0 || wh * ww <= smem_cap_elems) continue;
+        cell_edt(masks, H, W, crop, id, s, wh, ww, sm, cell_dist, nraw);
     }
 }
 
@@ -913,6 +935,10 @@ extern "C" int mbs_distance_labels(const uint16_t *masks, int n_crops, int H, in
             if (cell_threads < 32 || cell_threads > 256) cell_threads = 128;
         }
         lab_cell_kernel<<<gc, cell_threads, smem, stream>>>(masks, H, W, ids, cs, info, cell_dist, nraw, smem / 6);
+        MBS_CHECK_LAUNCH();
+        if (full > smem)         // windows larger than shared memory are possible: the global-memory walk picks them up
+            lab_cell_big_kernel<<<n_crops, 256, 0, stream>>>(masks, H, W, ids, cs, reinterpret_cast<unsigned short *>(scaled),
+                                                             static_cast<size_t>(H) * W * 4, cell_dist, nraw, smem / 6);
         MBS_CHECK_LAUNCH();
         long long wantc = 2ll * (static_cast<long long>(H) + 6) * (W + 6);
         int smemc = wantc > smem_opt ? smem_opt : static_cast<int>(wantc);

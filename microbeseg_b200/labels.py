@@ -37,7 +37,7 @@ def _check_err(err):
     e = err.cpu().numpy()
     if e.any():
         raise RuntimeError(f"distance_labels: crops {np.flatnonzero(e).tolist()[:8]} exceeded a device limit "
-                           f"(bit0: instance window too large for shared memory, bit1: > 4096 gaps): {e[e != 0][:8]}")
+                           f"(bit0: an instance wider than 58 px whose bounding box (+6) does not fit the closing kernel's shared memory, bit1: > 4096 gaps): {e[e != 0][:8]}")
 
 
 def _run(masks_dev, max_id, search_radius, radius_hint, err=None):

@@ -51,6 +51,21 @@ def test_touching_cells_gaps_and_borders(lab):
     _check(lab.distance_label(m, 20), ref, "dense")
 
 
+def test_instance_window_larger_than_shared_memory(lab):
+    """max_mal ~ 300 px -> search radius 225 -> a 450 x 450 window (202 500 elements) cannot live in shared memory
+    (cap ~38 k): those instances go through the global-memory walk (lab_cell_big_kernel) -- same exact result."""
+    H, W = 512, 512
+    yy, xx = np.mgrid[0:H, 0:W]
+    m = np.zeros((H, W), np.uint16)
+    m[((yy - 250) / 60.0) ** 2 + ((xx - 256) / 150.0) ** 2 <= 1] = 1         # major axis ~300 px
+    m[((yy - 80) / 30.0) ** 2 + ((xx - 100) / 40.0) ** 2 <= 1] = 2
+    m[((yy - 420) / 35.0) ** 2 + ((xx - 380) / 60.0) ** 2 <= 1] = 3
+    m[(np.abs(yy - 330) <= 12) & (np.abs(xx - 120) <= 12)] = 4
+    mal = ol.max_major_axis_length(m)
+    assert mal > 250 and int(lab.max_major_axis_lengths(m)[0]) == mal
+    _check(lab.get_label(m, 'distance', mal), ol.get_label(m, 'distance', mal), "big window")
+
+
 def test_large_and_word_crossing_instances(lab):
     """instances wider than the 64-column bit window (byte-wise closing fallback OR-ing into the bit image), instances
     straddling the 64-pixel word boundaries of the bit rows, cells at the image border, width not a multiple of 64"""
