@@ -329,6 +329,35 @@ int mbs_contour_trace(const uint16_t *mask, int H, int W, int n_labels, const in
 int mbs_instance_stats(const uint16_t *masks, int n_frames, int H, int W, int max_id, int32_t *area, double *major,
                        double *minor, void *workspace, size_t workspace_bytes, void *stream);
 
+/* ---------------------------------------------------------------------------------------- */
+/* training-time augmentations, batched on the device (replace the per-sample NumPy / imgaug /  */
+/* scipy transforms of src/training/mytransforms.py:13-406 that run in the DataLoader workers). */
+/* The random decisions and parameters are drawn on the HOST in the reference's own call order  */
+/* (microbeseg_b200/augment.py); these entry points apply them.  uint16 images [n][H][W].       */
+/* ---------------------------------------------------------------------------------------- */
+/* Flip (mytransforms.py:129-233, 8 dihedral maps: exact), Scaling (:326-379) and Rotate (:271-323) (imgaug Affine =
+ * cv2.warpAffine about the image centre, constant border 0).  mats_dev: [n][6] float64 INVERSE maps,
+ * (sx, sy) = M * (x, y, 1) for output pixel (x, y); modes_dev: [n] 0 copy, 1 nearest (order 0: uint8 labels, dihedral
+ * maps), 2 bilinear (order 1: images and float labels).  dtype: MBS_IN_U8 / U16 / F32.  src != dst. */
+int mbs_aug_warp(const void *src, void *dst, int dtype, int n, int H, int W, const double *mats_dev, const int *modes_dev,
+                 void *stream);
+size_t mbs_aug_workspace_bytes(int n);
+/* Contrast (mytransforms.py:64-126) in place: modes_dev [n]: 0 none, 1 percentile stretch (np.percentile(img, (q0, q1))
+ * + skimage rescale_intensity to the dtype range), 2 contrast + gamma adjustment; params_dev [n][4] float64 = {q0, q1,
+ * factor, gamma}.  The CLAHE branch (skimage equalize_adapthist) is not built. */
+int mbs_aug_contrast(uint16_t *img, int n, int H, int W, const int *modes_dev, const double *params_dev, void *workspace,
+                     size_t workspace_bytes, void *stream);
+/* Blur (mytransforms.py:38-61) in place: scipy.ndimage.gaussian_filter(img (H,W,1), sigma) bit for bit (float64
+ * accumulation in scipy's order, 'reflect', truncation into uint16 after each of the three axis passes).
+ * weights_dev: [n][17] float64 kernels from the host (numpy's arithmetic), radius_dev: [n] (0 = no blur, <= 8). */
+int mbs_aug_blur(uint16_t *img, uint16_t *tmp, int n, int H, int W, const double *weights_dev, const int *radius_dev, void *stream);
+/* Noise (mytransforms.py:236-268: additive Gaussian noise, sigma = noise_frac * max(img), samples rounded, clipped to
+ * uint16; counter-based generator, reproducible for a seed) + ToTensor's min_max_normalization (utils.py:50-74):
+ * out = 2 * (clip(img, min, max) - min) / (max - min) - 1 in float32.  img_out / out: either may be NULL. */
+int mbs_aug_noise_normalize(const uint16_t *img, int n, int H, int W, const float *noise_frac_dev, unsigned long long seed,
+                            float min_value, float max_value, uint16_t *img_out, float *out, void *workspace,
+                            size_t workspace_bytes, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -123,6 +123,12 @@ _SIGS = {
                                  c_int, c_void_p]),
     "mbs_instance_stats": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "mbs_conv_ref_f32": (c_int, [ctypes.POINTER(ConvRefDesc), c_void_p]),
+    "mbs_aug_warp": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "mbs_aug_workspace_bytes": (c_size_t, [c_int]),
+    "mbs_aug_contrast": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "mbs_aug_blur": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "mbs_aug_noise_normalize": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, ctypes.c_ulonglong, c_float, c_float, c_void_p,
+                                        c_void_p, c_void_p, c_size_t, c_void_p]),
     "mbs_contour_first": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     "mbs_contour_trace": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
 }

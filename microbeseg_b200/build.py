@@ -6,7 +6,7 @@ import sys
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB = os.path.join(_HERE, "libmbseg.so")
-SOURCES = ["lib.cu", "unet_kernels.cu", "postproc_kernels.cu", "label_kernels.cu", "train_kernels.cu", "optim_kernels.cu", "contour_kernels.cu", "check_kernels.cu"]
+SOURCES = ["lib.cu", "unet_kernels.cu", "postproc_kernels.cu", "label_kernels.cu", "train_kernels.cu", "optim_kernels.cu", "contour_kernels.cu", "check_kernels.cu", "augment_kernels.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--use_fast_math=false"]
 
