@@ -1314,56 +1314,78 @@ flood_kernel(const FloodParams p) {
             }
             __syncthreads();
             const long long tk1 = clock64();
-            // initial work list.  First visit: every floodable pixel next to a flooded one; later visits: the floodable
-            // pixels on the tile edges next to a flooded halo pixel (the inside is already at its fixed point)
+            // initial work list = one bit per pixel.  First visit: every floodable pixel next to a flooded one; later visits:
+            // the floodable pixels on the tile edges next to a flooded halo pixel (the inside is already at its fixed point).
+            // A warp covers 32 adjacent columns of one row = exactly one word of the bitmap: a ballot and a plain store.
             const bool first_visit = full_scan;
+            if (first_visit) {
 #pragma unroll 4
-            for (int i = 0; i < 16; ++i) {
-                const int r = i * 4 + (threadIdx.x >> 6), c = threadIdx.x & (CT - 1);     // a warp = 32 adjacent columns: no bank conflicts
-                const unsigned long long s = sS[r + 1][c + 1];
-                bool want = false;
-                if (!((s >> 16) & 1ull)) {
-                    if (first_visit) {
+                for (int i = 0; i < 16; ++i) {
+                    const int r = i * 4 + (threadIdx.x >> 6), c = threadIdx.x & (CT - 1);
+                    const unsigned long long s = sS[r + 1][c + 1];
+                    bool want = false;
+                    if (!((s >> 16) & 1ull))
                         want = static_cast<unsigned>(sS[r][c + 1] >> 32) < ORD_INF || static_cast<unsigned>(sS[r + 2][c + 1] >> 32) < ORD_INF ||
                                static_cast<unsigned>(sS[r + 1][c] >> 32) < ORD_INF || static_cast<unsigned>(sS[r + 1][c + 2] >> 32) < ORD_INF;
-                    } else {
-                        want = (r == 0 && static_cast<unsigned>(sS[0][c + 1] >> 32) < ORD_INF) ||
-                               (r == CT - 1 && static_cast<unsigned>(sS[CT + 1][c + 1] >> 32) < ORD_INF) ||
-                               (c == 0 && static_cast<unsigned>(sS[r + 1][0] >> 32) < ORD_INF) ||
-                               (c == CT - 1 && static_cast<unsigned>(sS[r + 1][CT + 1] >> 32) < ORD_INF);
-                    }
+                    const unsigned m = __ballot_sync(0xffffffffu, want);
+                    if (lane == 0) sFlag[(r * CT + c) >> 5] = m;
                 }
-                const unsigned m = __ballot_sync(0xffffffffu, want);
-                if (m) {
-                    int base = 0;
-                    if (lane == __ffs(m) - 1) base = atomicAdd(&sMisc[0], __popc(m));
-                    base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
-                    if (want) {
-                        const int idx = r * CT + c;
-                        sQ[base + __popc(m & ((1u << lane) - 1u))] = static_cast<unsigned short>(idx);
-                        atomicOr(&sFlag[idx >> 5], 1u << (idx & 31));
-                    }
+            } else {
+                // the bitmap was cleared before the tile was loaded; 4 x 64 edge pixels = one per thread
+                const int side = threadIdx.x >> 6, k = threadIdx.x & (CT - 1);
+                const int r = side == 0 ? 0 : (side == 1 ? CT - 1 : k), c = side <= 1 ? k : (side == 2 ? 0 : CT - 1);
+                const int hr = side == 0 ? 0 : (side == 1 ? CT + 1 : k + 1), hc = side <= 1 ? k + 1 : (side == 2 ? 0 : CT + 1);
+                const unsigned long long s = sS[r + 1][c + 1];
+                if (!((s >> 16) & 1ull) && static_cast<unsigned>(sS[hr][hc] >> 32) < ORD_INF) {
+                    const int idx = r * CT + c;
+                    atomicOr(&sFlag[idx >> 5], 1u << (idx & 31));
                 }
             }
-            __syncthreads();
             const long long tk2 = clock64();
-            int qc = 0;
+            // Rounds.  The work list IS the bitmap: a thread that changes a pixel marks the lateral neighbours with
+            // fire-and-forget shared-memory reductions (no returned value, no queue counter: nothing in the dependent chain of
+            // a chase step waits for an atomic).  Each round first compacts the set bits into a list (so that the items are
+            // dealt evenly to the threads) and clears the bitmap; the block barriers between compaction and evaluation order
+            // "cleared before the neighbours are read" and "state written before the flag is consumed".
             unsigned n_rounds = 0, n_items = 0;
+            int *sWarpTot = sMisc + 4;                   // [8]
             for (;;) {
-                const int n = *reinterpret_cast<volatile int *>(&sMisc[qc]);
+                __syncthreads();                         // flags of the previous round (or of the initial scan) are complete
+                const int w = threadIdx.x >> 1, hbit = (threadIdx.x & 1) * 16;
+                unsigned bits = (sFlag[w] >> hbit) & 0xFFFFu;
+                const int cnt = __popc(bits);
+                int incl = cnt;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int v = __shfl_up_sync(0xffffffffu, incl, o);
+                    if (lane >= o) incl += v;
+                }
+                if (lane == 31) sWarpTot[threadIdx.x >> 5] = incl;
+                if (!(threadIdx.x & 1)) sFlag[w] = 0u;   // both readers of the word are adjacent lanes of this (converged) warp
+                __syncthreads();
+                int basep = 0, n = 0;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const int v = sWarpTot[k];
+                    if (k < (threadIdx.x >> 5)) basep += v;
+                    n += v;
+                }
                 if (n == 0) break;
+                int pos = basep + incl - cnt;
+                while (bits) {
+                    const int bpos = __ffs(bits) - 1;
+                    bits &= bits - 1;
+                    sQ[pos++] = static_cast<unsigned short>(w * 32 + hbit + bpos);
+                }
+                __syncthreads();
                 ++n_rounds;
                 n_items += static_cast<unsigned>(n);
-                const unsigned short *qin = sQ + qc * CT * CT;
-                unsigned short *qout = sQ + (qc ^ 1) * CT * CT;
+                const int CHASE = p.chase_heavy;
                 for (int i = threadIdx.x; i < n; i += 256) {
-                    int idx = qin[i];
-                    atomicAnd(&sFlag[idx >> 5], ~(1u << (idx & 31)));      // dequeued before the neighbours are read
-                    __threadfence_block();
-                    // One queue entry = one evaluation plus a CHASE: while a pixel changes, the thread carries on with
-                    // the neighbour straight ahead (away from the neighbour the new state came from), so a front crosses
-                    // up to CHASE pixels per round along rows / columns instead of one.
-                    const int CHASE = p.chase_heavy;
+                    int idx = sQ[i];
+                    // One list entry = one evaluation plus a CHASE: while a pixel changes, the thread carries on with the
+                    // neighbour straight ahead (away from the neighbour the new state came from), so a front crosses up to
+                    // CHASE pixels per round along rows / columns instead of one.
 #pragma unroll 1
                     for (int step = 0; step <= CHASE; ++step) {
                         const int r = (idx >> 6) + 1, c = (idx & (CT - 1)) + 1;
@@ -1396,9 +1418,8 @@ flood_kernel(const FloodParams p) {
                         }
                         if (!ch) break;
                         *reinterpret_cast<volatile unsigned long long *>(&sS[r][c]) = ns;
-                        __threadfence_block();
                         // the pixel straight ahead is handled by this thread in the next step; the other floodable
-                        // neighbours inside the tile are queued (their "fixed" bit never changes: reuse n0..n3)
+                        // neighbours inside the tile are marked (their "fixed" bit never changes: reuse n0..n3)
                         const int ahead = 3 - bi;                        // came from up -> go down, left -> right, ...
                         bool w0 = r > 1 && !((n0 >> 16) & 1ull), w1 = c > 1 && !((n1 >> 16) & 1ull);
                         bool w2 = c < CT && !((n2 >> 16) & 1ull), w3 = r < CT && !((n3 >> 16) & 1ull);
@@ -1407,19 +1428,10 @@ flood_kernel(const FloodParams p) {
                             if (ahead == 0) w0 = false; else if (ahead == 1) w1 = false; else if (ahead == 2) w2 = false; else w3 = false;
                         }
                         const int i0 = idx - CT, i1 = idx - 1, i2 = idx + 1, i3 = idx + CT;
-                        unsigned o0 = ~0u, o1 = ~0u, o2 = ~0u, o3 = ~0u;
-                        if (w0) o0 = atomicOr(&sFlag[i0 >> 5], 1u << (i0 & 31)) & (1u << (i0 & 31));
-                        if (w1) o1 = atomicOr(&sFlag[i1 >> 5], 1u << (i1 & 31)) & (1u << (i1 & 31));
-                        if (w2) o2 = atomicOr(&sFlag[i2 >> 5], 1u << (i2 & 31)) & (1u << (i2 & 31));
-                        if (w3) o3 = atomicOr(&sFlag[i3 >> 5], 1u << (i3 & 31)) & (1u << (i3 & 31));
-                        const int cnt = (o0 == 0) + (o1 == 0) + (o2 == 0) + (o3 == 0);
-                        if (cnt) {
-                            int pos = atomicAdd(&sMisc[qc ^ 1], cnt);
-                            if (o0 == 0) qout[pos++] = static_cast<unsigned short>(i0);
-                            if (o1 == 0) qout[pos++] = static_cast<unsigned short>(i1);
-                            if (o2 == 0) qout[pos++] = static_cast<unsigned short>(i2);
-                            if (o3 == 0) qout[pos++] = static_cast<unsigned short>(i3);
-                        }
+                        if (w0) atomicOr(&sFlag[i0 >> 5], 1u << (i0 & 31));
+                        if (w1) atomicOr(&sFlag[i1 >> 5], 1u << (i1 & 31));
+                        if (w2) atomicOr(&sFlag[i2 >> 5], 1u << (i2 & 31));
+                        if (w3) atomicOr(&sFlag[i3 >> 5], 1u << (i3 & 31));
                         const unsigned eb = (r == 1 ? EDGE_TOP : 0u) | (r == CT ? EDGE_BOTTOM : 0u) | (c == 1 ? EDGE_LEFT : 0u) | (c == CT ? EDGE_RIGHT : 0u);
                         if (eb) atomicOr(reinterpret_cast<unsigned *>(&sMisc[2]), eb);
                         sMisc[3] = 1;
@@ -1427,10 +1439,6 @@ flood_kernel(const FloodParams p) {
                         idx = ahead == 0 ? i0 : (ahead == 1 ? i1 : (ahead == 2 ? i2 : i3));
                     }
                 }
-                __syncthreads();
-                if (threadIdx.x == 0) sMisc[qc] = 0;
-                qc ^= 1;
-                __syncthreads();
             }
             const long long tk3 = clock64();
             if (threadIdx.x == 0 && sweep < 32) {
