@@ -870,6 +870,177 @@ conv_halo64_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
 }
 
 // ------------------------------------------------------------------------------------------
+// Halo tiles with STREAMED weights for the wide stride-1 layers (Cout = 128: two stacked pixel tiles, Cout >= 256).
+//
+// ncu on the generic kernel (512 -> 512 @256^2): tensor pipe 74 %, L2 -> SM 10.5 TB/s = 44 B/clk/SM, i.e. AT the chip-wide
+// L2 delivery cap (~6300 B/clk): every tap re-reads its 16 KiB A patch from L2 (9 x per 64-channel chunk) next to the
+// 32 KiB weight tile.  Here ONE TMA box brings the (16*MT + 2) x 10 pixel halo patch of a chunk (23 / 43.5 KiB) and the
+// nine taps are nine UMMA descriptors into it (same trick as conv_halo64_kernel); the weight tiles stream through their
+// own ring, one per (tap, chunk).  L2 -> SM traffic per chunk: 9 x 16 + 9 x 32 = 432 KiB -> 23 + 288 = 311 KiB (BN = 256).
+// K order: chunk-major, tap inside (the generic kernel: tap-major) -- fp32 accumulation order differs, nothing else.
+// ------------------------------------------------------------------------------------------
+template <int BN, int MT, int SA, int SB>
+struct HsPlan {
+    static constexpr int HALO_ROWS = MT * HT_H + 2;
+    static constexpr int A_BYTES_ = HALO_W * HALO_ROWS * 128;
+    static constexpr int A_SLOT = (A_BYTES_ + 1023) / 1024 * 1024;
+    static constexpr int B_BYTES = BN * BK * 2;
+    static constexpr int OFF_A = 0;
+    static constexpr int OFF_B = SA * A_SLOT;
+    static constexpr int OFF_EPI = OFF_B + SB * B_BYTES;
+    static constexpr int EPI_BYTES = EPI_WARPS * 1024 + 2 * 4 * 128 * 4;
+    static constexpr int OFF_BAR = OFF_EPI + EPI_BYTES;            // fullA[SA], emptyA[SA], fullB[SB], emptyB[SB], tfull[2], tempty[2]
+    static constexpr int OFF_TMEM = OFF_BAR + 8 * (2 * SA + 2 * SB + 4);
+    static constexpr int OFF_PAR = (OFF_TMEM + 8 + 15) / 16 * 16;
+    static int dyn_bytes(int cout) { return OFF_PAR + 1024 + 3 * cout * 4; }
+};
+
+template <int BN, int MT, int SA, int SB>
+__global__ void __launch_bounds__(threads_for_groups(2), 1)
+conv_hstream_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
+                    const __grid_constant__ CUtensorMap tmB, const ConvKParams p) {
+    using Plan = HsPlan<BN, MT, SA, SB>;
+    static_assert(2 * MT * BN <= 512, "accumulators exceed TMEM");
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t base = (raw + 1023u) & ~1023u;
+    uint8_t *gbase = smem_raw + (base - raw);
+    const uint32_t sA = base + Plan::OFF_A;
+    const uint32_t sB = base + Plan::OFF_B;
+    const uint32_t sBar = base + Plan::OFF_BAR;
+    auto fullA = [&](int s) { return sBar + 8u * s; };
+    auto emptyA = [&](int s) { return sBar + 8u * (SA + s); };
+    auto fullB = [&](int s) { return sBar + 8u * (2 * SA + s); };
+    auto emptyB = [&](int s) { return sBar + 8u * (2 * SA + SB + s); };
+    auto tfull_bar = [&](int b) { return sBar + 8u * (2 * SA + 2 * SB + b); };
+    auto tempty_bar = [&](int b) { return sBar + 8u * (2 * SA + 2 * SB + 2 + b); };
+    volatile uint32_t *tmem_ptr = reinterpret_cast<volatile uint32_t *>(gbase + Plan::OFF_TMEM);
+    float *s_par = reinterpret_cast<float *>(gbase + Plan::OFF_PAR);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int chunks = p.chunks0 + p.chunks1;
+    const int tiles_per_img = p.tiles_x * p.tiles_y;
+
+    if (threadIdx.x == 0) {
+        prefetch_tmap(&tmA0);
+        if (p.chunks1 > 0) prefetch_tmap(&tmA1);
+        prefetch_tmap(&tmB);
+        for (int s = 0; s < SA; ++s) { mbar_init(fullA(s), 1); mbar_init(emptyA(s), 1); }
+        for (int s = 0; s < SB; ++s) { mbar_init(fullB(s), 1); mbar_init(emptyB(s), 1); }
+        for (int b = 0; b < 2; ++b) { mbar_init(tfull_bar(b), 1); mbar_init(tempty_bar(b), 8); }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(smem_u32(const_cast<uint32_t *>(tmem_ptr)), 2 * MT * BN);
+    if (warp >= 2) {
+        for (int j = threadIdx.x - 64; j < p.Cout; j += threads_for_groups(2) - 64) {
+            s_par[j] = p.bias[j];
+            s_par[p.Cout + j] = p.scale[j];
+            s_par[2 * p.Cout + j] = p.shift[j];
+        }
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ===== TMA producer: one halo patch per (tile, chunk), one weight tile per (tile, chunk, tap) =====
+            int ia = 0, ib = 0;
+            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+                const int n_tile = tile % p.n_tiles;
+                const int m_tile = tile / p.n_tiles;
+                const int tx = m_tile % p.tiles_x;
+                const int ty = (m_tile / p.tiles_x) % p.tiles_y;
+                const int img = m_tile / tiles_per_img;
+                const int x0 = tx * HT_W, y0 = ty * (HT_H * MT), n0 = n_tile * BN;
+                for (int cc = 0; cc < chunks; ++cc, ++ia) {
+                    const int sa = ia % SA;
+                    mbar_wait(emptyA(sa), ((ia / SA) & 1) ^ 1u);
+                    mbar_expect_tx(fullA(sa), Plan::A_BYTES_);
+                    if (cc < p.chunks0)
+                        tma_load_4d(sA + sa * Plan::A_SLOT, &tmA0, fullA(sa), cc * BK, x0 - 1, y0 - 1, img);
+                    else
+                        tma_load_4d(sA + sa * Plan::A_SLOT, &tmA1, fullA(sa), (cc - p.chunks0) * BK, x0 - 1, y0 - 1, img);
+#pragma unroll 1
+                    for (int tap = 0; tap < 9; ++tap, ++ib) {
+                        const int sb = ib % SB;
+                        mbar_wait(emptyB(sb), ((ib / SB) & 1) ^ 1u);
+                        mbar_expect_tx(fullB(sb), Plan::B_BYTES);
+                        tma_load_2d(sB + sb * Plan::B_BYTES, &tmB, fullB(sb), (tap * chunks + cc) * BK, n0);
+                    }
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        // ===== MMA issuer (single thread) =====
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc(BM, BN);
+            int ia = 0, ib = 0, lt = 0;
+            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++lt) {
+                const int buf = lt & 1;
+                mbar_wait(tempty_bar(buf), ((lt >> 1) & 1) ^ 1u);
+                tcgen05_fence_after();
+                const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(buf * MT * BN);
+                for (int cc = 0; cc < chunks; ++cc, ++ia) {
+                    const int sa = ia % SA;
+                    mbar_wait(fullA(sa), (ia / SA) & 1);
+                    tcgen05_fence_after();
+                    const uint32_t a_slot = sA + sa * Plan::A_SLOT;
+#pragma unroll 1
+                    for (int tap = 0; tap < 9; ++tap, ++ib) {
+                        const int sb = ib % SB;
+                        mbar_wait(fullB(sb), (ib / SB) & 1);
+                        tcgen05_fence_after();
+                        const uint32_t a_tap = a_slot + static_cast<uint32_t>(((tap / 3) * HALO_W + (tap % 3)) * 128);
+                        const uint64_t bdesc = make_sw128_desc(sB + sb * Plan::B_BYTES);
+#pragma unroll
+                        for (int mt = 0; mt < MT; ++mt) {
+                            const uint64_t adesc = make_sw128_desc_sbo(a_tap + static_cast<uint32_t>(mt * HT_H * HALO_W * 128), HALO_W * 128);
+#pragma unroll
+                            for (int k = 0; k < BK / 16; ++k)
+                                umma_f16(tmem_d + static_cast<uint32_t>(mt * BN), adesc + 2u * k, bdesc + 2u * k, idesc,
+                                         (cc > 0 || tap > 0 || k > 0) ? 1u : 0u);
+                        }
+                        umma_commit(emptyB(sb));
+                    }
+                    umma_commit(emptyA(sa));
+                }
+                umma_commit(tfull_bar(buf));
+            }
+        }
+        __syncwarp();
+    } else {
+        const int e = warp - 2;
+        const int quad = warp & 3;
+        const int half = e >> 2;
+        const uint32_t s_epi = base + Plan::OFF_EPI + static_cast<uint32_t>(e) * 1024u;
+        float *s_head = reinterpret_cast<float *>(gbase + Plan::OFF_EPI + EPI_WARPS * 1024);
+        int lt = 0;
+        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++lt) {
+            const int n_tile = tile % p.n_tiles;
+            const int m_tile = tile / p.n_tiles;
+            const int tx = m_tile % p.tiles_x;
+            const int ty = (m_tile / p.tiles_x) % p.tiles_y;
+            const int img = m_tile / tiles_per_img;
+            const int x0 = tx * HT_W, y0 = ty * (HT_H * MT), n0 = n_tile * BN;
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt)
+                epilogue_tile<BN, HT_W>(p, s_par, s_epi, s_head, tmem_base, tfull_bar(lt & 1), tempty_bar(lt & 1), lt, quad, half, lane,
+                                        x0, y0 + mt * HT_H, img, n0, false, (lt & 1) * MT * BN + mt * BN, mt == 0, mt == MT - 1);
+        }
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tcgen05_fence_after();
+        tmem_dealloc(tmem_base, 2 * MT * BN);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // Weight gradient straight from the NHWC activations (no channel-major copies).
 //
 //   G[m][tap][n] += sum over pixels o of  A[sA*o + offA(tap)][m] * B[sB*o + offB(tap)][n]
@@ -1693,6 +1864,31 @@ int launch_halo(const CUtensorMap &a0, const CUtensorMap &a1, const CUtensorMap 
     return 0;
 }
 
+template <int BN, int MT, int SA, int SB>
+int launch_hstream(const CUtensorMap &a0, const CUtensorMap &a1, const CUtensorMap &b, const ConvKParams &kp, cudaStream_t stream) {
+    using Plan = HsPlan<BN, MT, SA, SB>;
+    static int configured_bytes[mbs::kMaxDevices] = {0};
+    const int dyn = Plan::dyn_bytes(kp.Cout);
+    const int dev = mbs::current_device();
+    if (dyn > configured_bytes[dev]) {
+        MBS_CHECK_CUDA(cudaFuncSetAttribute(conv_hstream_kernel<BN, MT, SA, SB>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn));
+        configured_bytes[dev] = dyn;
+    }
+    const int grid = kp.num_tiles < sm_count() ? kp.num_tiles : sm_count();
+    conv_hstream_kernel<BN, MT, SA, SB><<<grid, threads_for_groups(2), dyn, stream>>>(a0, a1, b, kp);
+    MBS_CHECK_LAUNCH();
+    return 0;
+}
+
+bool hstream_enabled() {     // MBS_NO_HSTREAM=1 (A/B runs): wide stride-1 convs through the generic kernel
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("MBS_NO_HSTREAM");
+        v = (e && e[0] == '1') ? 0 : 1;
+    }
+    return v == 1;
+}
+
 int epi_variant() {     // MBS_EPI_VARIANT (A/B runs): 0 default; 1 = transposed convs on 128-column tiles; 3 = 4 epilogue groups in the halo kernel
     static int v = -1;
     if (v < 0) {
@@ -1824,6 +2020,32 @@ extern "C" int mbs_conv_gemm(const mbs_conv_desc *d, void *stream_) {
         // reads bound this layer, and more epilogue warps compete for the same smem bandwidth
         if (epi_variant() == 3) return launch_halo<1, 3, 4>(a0, a1, b, dm, kp, stream);
         return launch_halo<1, 4, 2>(a0, a1, b, dm, kp, stream);
+    }
+
+    if (hstream_enabled() && d->mode == MBS_CONV3X3_S1 && d->Cout % 128 == 0 && d->Cout <= 1024 && d->head_out == nullptr) {
+        // wide stride-1 layers: halo tiles + streamed weights (see conv_hstream_kernel); the choice depends on the layer
+        // shape only, never on the frame size, so tiled and whole-frame inference stay bit-identical
+        const bool wide = d->Cout % 256 == 0;
+        const int mt = wide ? 1 : 2;
+        kp.tiles_x = mbs::cdiv(kp.Wm, HT_W);
+        kp.tiles_y = mbs::cdiv(kp.Hm, HT_H * mt);
+        kp.n_tiles = d->Cout / (wide ? 256 : 128);
+        const long long tiles_ll = static_cast<long long>(d->N) * kp.tiles_x * kp.tiles_y * kp.n_tiles;
+        MBS_REQUIRE(tiles_ll > 0 && tiles_ll < (1ll << 31), "too many tiles");
+        kp.num_tiles = static_cast<int>(tiles_ll);
+        CUtensorMap a0, a1, b;
+        int rc = make_act_map(&a0, d->src0, d->N, d->H, d->W, d->C0, d->ld0, d->coff0, 1, HALO_W, mt * HT_H + 2);
+        if (rc) return rc;
+        if (d->C1 > 0) {
+            rc = make_act_map(&a1, d->src1, d->N, d->H, d->W, d->C1, d->ld1, d->coff1, 1, HALO_W, mt * HT_H + 2);
+            if (rc) return rc;
+        } else {
+            a1 = a0;
+        }
+        rc = make_weight_map(&b, d->weight, d->Cout, 9 * (d->C0 + d->C1), wide ? 256 : 128);
+        if (rc) return rc;
+        if (wide) return launch_hstream<256, 1, 2, 4>(a0, a1, b, kp, stream);
+        return launch_hstream<128, 2, 2, 6>(a0, a1, b, kp, stream);
     }
 
     const int ncols = d->mode == MBS_CONVT2X2_S2 ? 4 * d->Cout : d->Cout;

@@ -34,11 +34,18 @@ def _norm(img):
     return 2 * (img.astype(np.float32) - lo) / (hi - lo) - 1
 
 
-def _check(got, ref, what, loose=1.0):
+def _check(got, ref, what, loose=1.0, policy=None):
+    """``policy``: the fp32 oracle evaluated with the CUDA path's bf16 storage policy (oracle/net.py, policy='bf16').  The
+    maximum over a few thousand pixels of a heavy-tailed error field moves with every change of the fp32 accumulation
+    order (these He-init nets amplify a single flipped bf16 rounding), so the bound on the maximum is
+    max(2e-2, 1.25 x the policy oracle's own maximum error) -- the criterion of the full-size test; the mean is stable."""
     scale = max(1.0, float(np.abs(ref).max()))
     err = np.abs(got - ref)
     assert np.isfinite(got).all(), what
-    assert err.max() <= loose * REL_MAX * scale, (what, err.max(), scale)
+    lim = loose * REL_MAX
+    if policy is not None:
+        lim = max(lim, 1.25 * float(np.abs(policy - ref).max()) / scale)
+    assert err.max() <= lim * scale, (what, err.max(), scale, lim)
     assert err.mean() <= loose * REL_MEAN * scale, (what, err.mean(), scale)
 
 
@@ -57,8 +64,13 @@ def test_against_reference_goldens(native_lib):
         # group / instance norm cannot be folded into the conv epilogue: the activation is rounded to bf16 once more
         # (before AND after the normalisation), measured error 1.7x that of the BatchNorm nets -> 2x tolerance
         loose = 2.0 if ("norm" in g.files and str(g["norm"]) != "bn") else 1.0
-        _check(border[0, 0].cpu().numpy(), g["border"], f + ":border", loose)
-        _check(cell[0, 0].cpu().numpy(), g["cell"], f + ":cell", loose)
+        pol = (None, None)
+        if loose == 1.0 and ("pool" not in g.files or str(g["pool"]) == "conv"):
+            sd = onet.seeded_state_dict(onet.reference_layout_template("DU", filters), seed)
+            pb, pc = onet.dunet_forward(sd, x.cpu(), act, policy="bf16")
+            pol = (pb[0, 0].numpy(), pc[0, 0].numpy())
+        _check(border[0, 0].cpu().numpy(), g["border"], f + ":border", loose, pol[0])
+        _check(cell[0, 0].cpu().numpy(), g["cell"], f + ":cell", loose, pol[1])
         b2, c2 = net(x)                                     # bitwise reproducible (no atomics in the statistics)
         assert torch.equal(border, b2) and torch.equal(cell, c2)
         assert native_lib.mbs_debug_flags(1) == 0
