@@ -888,7 +888,7 @@ struct HsPlan {
     static constexpr int OFF_A = 0;
     static constexpr int OFF_B = SA * A_SLOT;
     static constexpr int OFF_EPI = OFF_B + SB * B_BYTES;
-    static constexpr int EPI_BYTES = EPI_WARPS * 1024 + 2 * 4 * 128 * 4;
+    static constexpr int EPI_BYTES = EPI_WARPS * 2048 + 2 * 4 * 128 * 4;     // 2 KiB of staging per epilogue warp (transposing epilogue)
     static constexpr int OFF_BAR = OFF_EPI + EPI_BYTES;            // fullA[SA], emptyA[SA], fullB[SB], emptyB[SB], tfull[2], tempty[2]
     static constexpr int OFF_TMEM = OFF_BAR + 8 * (2 * SA + 2 * SB + 4);
     static constexpr int OFF_PAR = (OFF_TMEM + 8 + 15) / 16 * 16;
@@ -1037,6 +1037,206 @@ conv_hstream_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
     if (warp == 1) {
         tcgen05_fence_after();
         tmem_dealloc(tmem_base, 2 * MT * BN);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Cout = 128: the same halo / streamed-weight scheme with the operand roles SWAPPED.
+//
+// With pixels as the M operand a 128-channel layer issues M = 128, N = 128 MMAs: 4 KiB (A) + 4 KiB (B) of shared-memory
+// operand reads per 64 cycles = 128 B/clk, the shared-memory bandwidth itself (ncu: tensor pipe 61-66 %, whatever the
+// L2 traffic).  Here D^T[cout][pixel] = W[cout][k] * X[pixel][k]^T: the 128 output channels are the M rows (weight tile =
+// A operand, K-major as TMA delivers it), 256 pixels (an 8 x 32 tile of the halo patch, one descriptor with the 10-pixel
+// row pitch as stride byte offset) are the N columns: 12 KiB per 128 cycles = 96 B/clk, as for the Cout >= 256 layers.
+// The accumulator comes out channel-major (TMEM lane = channel): per-channel bias / affine are per-thread scalars, and
+// the epilogue transposes 32 x 32 blocks through shared memory so that global stores are 16-byte NHWC vectors.
+// ------------------------------------------------------------------------------------------
+template <int TW>
+__device__ __forceinline__ void epilogue_tile_T(const ConvKParams &p, const float *s_par, uint32_t s_epi, uint32_t tmem_base, uint32_t tfull,
+                                                uint32_t tempty, int lt, int quad, int half, int lane, int x0, int y0, int img, int acc_col) {
+    mbar_wait(tfull, (lt >> 1) & 1);
+    tcgen05_fence_after();
+    const int ch = quad * 32 + lane;
+    const float bias = s_par[ch], sc = s_par[p.Cout + ch], sh = s_par[2 * p.Cout + ch];
+#pragma unroll 1
+    for (int c = half * 128; c < (half + 1) * 128; c += 32) {
+        uint32_t r[32];
+        tmem_ld32(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(acc_col + c), r);
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) + bias;
+        switch (p.act) {      // one uniform branch per 32 pixels
+            case MBS_ACT_RELU:
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.0f);
+                break;
+            case MBS_ACT_LEAKYRELU:
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = v[j] > 0.0f ? v[j] : 0.01f * v[j];
+                break;
+            case MBS_ACT_ELU:
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = v[j] > 0.0f ? v[j] : expm1f(v[j]);
+                break;
+            case MBS_ACT_MISH:
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], MBS_ACT_MISH);
+                break;
+            default: break;
+        }
+        // stage [pixel][channel] (64 B per pixel for this warp's 32 channels); lanes = consecutive channels: conflict free
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            const __nv_bfloat16 h = __float2bfloat16_rn(fmaf(v[j], sc, sh));
+            asm volatile("st.shared.b16 [%0], %1;" ::"r"(s_epi + static_cast<uint32_t>(j * 64 + lane * 2)), "h"(*reinterpret_cast<const unsigned short *>(&h)) : "memory");
+        }
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int unit = i * 32 + lane;
+            const int px = unit >> 2, c8 = unit & 3;
+            uint32_t v0, v1, v2, v3;
+            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v0), "=r"(v1), "=r"(v2), "=r"(v3) : "r"(s_epi + static_cast<uint32_t>(px * 64 + c8 * 16)) : "memory");
+            const int col = c + px;
+            const int qy = y0 + col / TW, qx = x0 + col % TW;
+            if (qy < p.Hm && qx < p.Wm) {
+                const size_t off = ((static_cast<size_t>(img) * p.Hd + qy) * p.Wd + qx) * p.ldd + p.coffd + quad * 32 + c8 * 8;
+                *reinterpret_cast<uint4 *>(p.dst + off) = make_uint4(v0, v1, v2, v3);
+            }
+        }
+        __syncwarp();
+    }
+    tcgen05_fence_before();
+    __syncwarp();
+    if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tempty) : "memory");
+}
+
+template <int SA, int SB>
+__global__ void __launch_bounds__(threads_for_groups(2), 1)
+conv_hstreamT_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
+                     const __grid_constant__ CUtensorMap tmB, const ConvKParams p) {
+    using Plan = HsPlan<128, 2, SA, SB>;          // halo patch of an 8 x 32 pixel tile, 128-row weight tiles
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t base = (raw + 1023u) & ~1023u;
+    uint8_t *gbase = smem_raw + (base - raw);
+    const uint32_t sA = base + Plan::OFF_A;
+    const uint32_t sB = base + Plan::OFF_B;
+    const uint32_t sBar = base + Plan::OFF_BAR;
+    auto fullA = [&](int s) { return sBar + 8u * s; };
+    auto emptyA = [&](int s) { return sBar + 8u * (SA + s); };
+    auto fullB = [&](int s) { return sBar + 8u * (2 * SA + s); };
+    auto emptyB = [&](int s) { return sBar + 8u * (2 * SA + SB + s); };
+    auto tfull_bar = [&](int b) { return sBar + 8u * (2 * SA + 2 * SB + b); };
+    auto tempty_bar = [&](int b) { return sBar + 8u * (2 * SA + 2 * SB + 2 + b); };
+    volatile uint32_t *tmem_ptr = reinterpret_cast<volatile uint32_t *>(gbase + Plan::OFF_TMEM);
+    float *s_par = reinterpret_cast<float *>(gbase + Plan::OFF_PAR);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int chunks = p.chunks0 + p.chunks1;
+    const int tiles_per_img = p.tiles_x * p.tiles_y;
+
+    if (threadIdx.x == 0) {
+        prefetch_tmap(&tmA0);
+        if (p.chunks1 > 0) prefetch_tmap(&tmA1);
+        prefetch_tmap(&tmB);
+        for (int s = 0; s < SA; ++s) { mbar_init(fullA(s), 1); mbar_init(emptyA(s), 1); }
+        for (int s = 0; s < SB; ++s) { mbar_init(fullB(s), 1); mbar_init(emptyB(s), 1); }
+        for (int b = 0; b < 2; ++b) { mbar_init(tfull_bar(b), 1); mbar_init(tempty_bar(b), 8); }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(smem_u32(const_cast<uint32_t *>(tmem_ptr)), 512);
+    if (warp >= 2) {
+        for (int j = threadIdx.x - 64; j < 128; j += threads_for_groups(2) - 64) {
+            s_par[j] = p.bias[j];
+            s_par[128 + j] = p.scale[j];
+            s_par[256 + j] = p.shift[j];
+        }
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int ia = 0, ib = 0;
+            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+                const int tx = tile % p.tiles_x;
+                const int ty = (tile / p.tiles_x) % p.tiles_y;
+                const int img = tile / tiles_per_img;
+                const int x0 = tx * HT_W, y0 = ty * (HT_H * 2);
+                for (int cc = 0; cc < chunks; ++cc, ++ia) {
+                    const int sa = ia % SA;
+                    mbar_wait(emptyA(sa), ((ia / SA) & 1) ^ 1u);
+                    mbar_expect_tx(fullA(sa), Plan::A_BYTES_);
+                    if (cc < p.chunks0)
+                        tma_load_4d(sA + sa * Plan::A_SLOT, &tmA0, fullA(sa), cc * BK, x0 - 1, y0 - 1, img);
+                    else
+                        tma_load_4d(sA + sa * Plan::A_SLOT, &tmA1, fullA(sa), (cc - p.chunks0) * BK, x0 - 1, y0 - 1, img);
+#pragma unroll 1
+                    for (int tap = 0; tap < 9; ++tap, ++ib) {
+                        const int sb = ib % SB;
+                        mbar_wait(emptyB(sb), ((ib / SB) & 1) ^ 1u);
+                        mbar_expect_tx(fullB(sb), Plan::B_BYTES);
+                        tma_load_2d(sB + sb * Plan::B_BYTES, &tmB, fullB(sb), (tap * chunks + cc) * BK, 0);
+                    }
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc(BM, 256);       // M = 128 output channels, N = 256 pixels
+            int ia = 0, ib = 0, lt = 0;
+            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++lt) {
+                const int buf = lt & 1;
+                mbar_wait(tempty_bar(buf), ((lt >> 1) & 1) ^ 1u);
+                tcgen05_fence_after();
+                const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(buf * 256);
+                for (int cc = 0; cc < chunks; ++cc, ++ia) {
+                    const int sa = ia % SA;
+                    mbar_wait(fullA(sa), (ia / SA) & 1);
+                    tcgen05_fence_after();
+                    const uint32_t a_slot = sA + sa * Plan::A_SLOT;
+#pragma unroll 1
+                    for (int tap = 0; tap < 9; ++tap, ++ib) {
+                        const int sb = ib % SB;
+                        mbar_wait(fullB(sb), (ib / SB) & 1);
+                        tcgen05_fence_after();
+                        const uint64_t wdesc = make_sw128_desc(sB + sb * Plan::B_BYTES);
+                        const uint64_t xdesc = make_sw128_desc_sbo(a_slot + static_cast<uint32_t>(((tap / 3) * HALO_W + (tap % 3)) * 128), HALO_W * 128);
+#pragma unroll
+                        for (int k = 0; k < BK / 16; ++k)
+                            umma_f16(tmem_d, wdesc + 2u * k, xdesc + 2u * k, idesc, (cc > 0 || tap > 0 || k > 0) ? 1u : 0u);
+                        umma_commit(emptyB(sb));
+                    }
+                    umma_commit(emptyA(sa));
+                }
+                umma_commit(tfull_bar(buf));
+            }
+        }
+        __syncwarp();
+    } else {
+        const int e = warp - 2;
+        const int quad = warp & 3;
+        const int half = e >> 2;
+        const uint32_t s_epi = base + Plan::OFF_EPI + static_cast<uint32_t>(e) * 2048u;       // 32 pixels x 64 B per warp
+        int lt = 0;
+        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++lt) {
+            const int tx = tile % p.tiles_x;
+            const int ty = (tile / p.tiles_x) % p.tiles_y;
+            const int img = tile / tiles_per_img;
+            epilogue_tile_T<HT_W>(p, s_par, s_epi, tmem_base, tfull_bar(lt & 1), tempty_bar(lt & 1), lt, quad, half, lane, tx * HT_W,
+                                  ty * (HT_H * 2), img, (lt & 1) * 256);
+        }
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tcgen05_fence_after();
+        tmem_dealloc(tmem_base, 512);
     }
 }
 
@@ -1880,13 +2080,29 @@ int launch_hstream(const CUtensorMap &a0, const CUtensorMap &a1, const CUtensorM
     return 0;
 }
 
-bool hstream_enabled() {     // MBS_NO_HSTREAM=1 (A/B runs): wide stride-1 convs through the generic kernel
+template <int SA, int SB>
+int launch_hstreamT(const CUtensorMap &a0, const CUtensorMap &a1, const CUtensorMap &b, const ConvKParams &kp, cudaStream_t stream) {
+    using Plan = HsPlan<128, 2, SA, SB>;
+    static int configured_bytes[mbs::kMaxDevices] = {0};
+    const int dyn = Plan::dyn_bytes(128);
+    const int dev = mbs::current_device();
+    if (dyn > configured_bytes[dev]) {
+        MBS_CHECK_CUDA(cudaFuncSetAttribute(conv_hstreamT_kernel<SA, SB>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn));
+        configured_bytes[dev] = dyn;
+    }
+    const int grid = kp.num_tiles < sm_count() ? kp.num_tiles : sm_count();
+    conv_hstreamT_kernel<SA, SB><<<grid, threads_for_groups(2), dyn, stream>>>(a0, a1, b, kp);
+    MBS_CHECK_LAUNCH();
+    return 0;
+}
+
+int hstream_enabled() {     // MBS_NO_HSTREAM=1 (A/B runs): wide stride-1 convs through the generic kernel; =2: no role-swapped Cout = 128 variant
     static int v = -1;
     if (v < 0) {
         const char *e = getenv("MBS_NO_HSTREAM");
-        v = (e && e[0] == '1') ? 0 : 1;
+        v = (e && e[0] == '1') ? 0 : ((e && e[0] == '2') ? 2 : 1);
     }
-    return v == 1;
+    return v;
 }
 
 int epi_variant() {     // MBS_EPI_VARIANT (A/B runs): 0 default; 1 = transposed convs on 128-column tiles; 3 = 4 epilogue groups in the halo kernel
@@ -2045,6 +2261,8 @@ extern "C" int mbs_conv_gemm(const mbs_conv_desc *d, void *stream_) {
         rc = make_weight_map(&b, d->weight, d->Cout, 9 * (d->C0 + d->C1), wide ? 256 : 128);
         if (rc) return rc;
         if (wide) return launch_hstream<256, 1, 2, 4>(a0, a1, b, kp, stream);
+        // Cout == 128: operand roles swapped (channels = M rows, 256 pixels = N columns), see conv_hstreamT_kernel
+        if (d->Cout == 128 && hstream_enabled() != 2) return launch_hstreamT<2, 6>(a0, a1, b, kp, stream);
         return launch_hstream<128, 2, 2, 6>(a0, a1, b, kp, stream);
     }
 
