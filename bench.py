@@ -38,7 +38,7 @@ def load_peaks():
     return dict(hbm=6650.0, tf_burst=1590.0, tf_sustained=1400.0, src="fallback")
 
 
-CONV_TRAFFIC_CSV = "profiles/r01_conv_dram_traffic_frame_v3.csv"
+CONV_TRAFFIC_CSV = "profiles/r02_conv_dram_traffic_frame.csv"
 
 
 def conv_traffic_from_profile(path=None):
@@ -52,7 +52,7 @@ def conv_traffic_from_profile(path=None):
     try:
         for ln in open(path).read().splitlines()[1:]:
             f = ln.rsplit(",", 3)            # the kernel name holds template commas: split the three numbers off the right
-            if len(f) == 4 and f[0].startswith(("conv_gemm_kernel", "conv_halo64_kernel")):
+            if len(f) == 4 and f[0].startswith(("conv_gemm_kernel", "conv_halo64_kernel", "conv_hstream")):
                 tot += (float(f[1]) + float(f[2])) * 1e6
                 n += 1
     except Exception:

@@ -156,6 +156,46 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64
         "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// Warp-uniform variants: called by ALL lanes of the MMA warp in converged code, one elected lane issues.  Inside an
+// `if (lane == 0)` region the compiler wraps every UTCHMMA (its operands live in uniform registers) in an ELECT +
+// BRA.U.ANY uniformisation loop -- ~10 SASS instructions and a branch per MMA, more than the 32 cycles an N = 64 MMA takes.
+__device__ __forceinline__ void umma_f16_w(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p, q;\n"
+        "elect.sync _|q, 0xffffffff;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// descriptors as (low word, high word): the high words are loop constants and the low words (start address field) advance
+// by compile-time constants, so an MMA costs two 32-bit adds, the pack and the issue
+template <bool ACC>
+__device__ __forceinline__ void umma_f16_w2(uint32_t tmem_d, uint32_t alo, uint32_t ahi, uint32_t blo, uint32_t bhi, uint32_t idesc) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p, q;\n"
+        ".reg .b64 da, db;\n"
+        "mov.b64 da, {%1, %2};\n"
+        "mov.b64 db, {%3, %4};\n"
+        "elect.sync _|q, 0xffffffff;\n"
+        "setp.ne.b32 p, %6, 0;\n"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n"
+        "}\n" ::"r"(tmem_d),
+        "r"(alo), "r"(ahi), "r"(blo), "r"(bhi), "r"(idesc), "n"(ACC ? 1 : 0)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit_w(uint32_t bar) {
+    asm volatile(
+        "{\n"
+        ".reg .pred q;\n"
+        "elect.sync _|q, 0xffffffff;\n"
+        "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n"
+        "}\n" ::"r"(bar)
+        : "memory");
+}
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -363,7 +403,7 @@ __device__ __forceinline__ void epilogue_tile(const ConvKParams &p, const float 
 // which writes full lines, clips at the tensor boundary and keeps the LSU free.  The transposed conv uses a
 // 5-D view (C, dx, x, dy, y) of the 2x up-sampled destination, so its pixel-shuffle scatter is one box too.
 constexpr int STAGE_TILE_BYTES = 128 * 128;
-template <int BN, int TW, int NG>
+template <int BN, int TW, int NG, bool PAIR = false, int DEPTH = 1>
 __device__ __forceinline__ void epilogue_tile_tma(const ConvKParams &p, const CUtensorMap *tmD, const float *s_par,
                                                   uint32_t s_stage, uint32_t tmem_base, uint32_t tfull0,
                                                   uint32_t tempty0, int lt, int group, int quad, int lane, bool leader,
@@ -371,7 +411,10 @@ __device__ __forceinline__ void epilogue_tile_tma(const ConvKParams &p, const CU
     constexpr int CHUNKS = BN / 64;
     // BN == 64: whole tiles are dealt round-robin to the groups, each group owning one TMEM accumulator
     // (a group may run ahead of the others, so it must not share an mbarrier phase sequence with them)
-    constexpr int NBUF = CHUNKS == 1 ? NG : 2;
+    // DEPTH accumulators per group: the MMAs of tile i only wait for the epilogue of tile i - DEPTH * NG.  With one
+    // accumulator per group a tile costs (MMA + epilogue) / NG -- MMA and epilogue of the same buffer serialise -- and the
+    // epilogue of a 64-column tile (~3600 cycles of dependent TMEM load -> math -> smem chains) dwarfs its 1152 MMA cycles.
+    constexpr int NBUF = CHUNKS == 1 ? NG * DEPTH : 2;
     if (CHUNKS == 1 && (lt % NG) != group) return;
     const int buf = lt % NBUF;
     const uint32_t tfull = tfull0 + 8u * buf, tempty = tempty0 + 8u * buf;
@@ -485,7 +528,10 @@ __device__ __forceinline__ void epilogue_tile_tma(const ConvKParams &p, const CU
     tcgen05_fence_before();
     __syncwarp();
     if (lane == 0) {
-        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tempty) : "memory");
+        if (PAIR)     // 2-CTA pair: the MMA issuer lives in the even CTA; clearing the peer bit addresses ITS barrier
+            asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(tempty & 0xFEFFFFFFu) : "memory");
+        else
+            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tempty) : "memory");
     }
     if (BN == 64 && has_head) {
         const int py = y0 + row / TW, px = x0 + row % TW;
@@ -620,7 +666,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         __syncwarp();
     } else if (warp == 1) {
         // ===== MMA issuer (single thread) =====
-        if (lane == 0) {
+        {       // all lanes run the issue loop in converged code, one elected lane issues (umma_f16_w)
             constexpr uint32_t idesc = make_idesc(BM, BN);
             int it_g = 0, lt = 0;
             for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++lt) {
@@ -640,13 +686,13 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
 #pragma unroll
                         for (int k = 0; k < BK / 16; ++k) {
                             // advance 32 bytes (16 bf16) inside the 128-byte swizzle row: +2 in the >>4 encoding
-                            umma_f16(tmem_d + static_cast<uint32_t>(mt * BN), adesc + (mt * (A_BYTES >> 4)) + 2u * k,
+                            umma_f16_w(tmem_d + static_cast<uint32_t>(mt * BN), adesc + (mt * (A_BYTES >> 4)) + 2u * k,
                                      bdesc + 2u * k, idesc, (it > 0 || k > 0) ? 1u : 0u);
                         }
                     }
-                    umma_commit(empty_bar(s));  // frees the smem slot when these MMAs retire
+                    umma_commit_w(empty_bar(s));  // frees the smem slot when these MMAs retire
                 }
-                umma_commit(tfull_bar(buf));     // accumulators of this work item complete
+                umma_commit_w(tfull_bar(buf));     // accumulators of this work item complete
             }
         }
         __syncwarp();
@@ -716,8 +762,9 @@ struct HaloPlan {
     static constexpr int OFF_A = 9 * CHUNKS * W_TILE_BYTES;
     static constexpr int OFF_EPI = OFF_A + STAGES * HALO_SLOT;
     static constexpr int EPI_BYTES = NG * STAGE_TILE_BYTES;    // TMA-store staging, one tile per epilogue group
-    static constexpr int OFF_BAR = OFF_EPI + EPI_BYTES;        // full[S], empty[S], tfull[NG], tempty[NG], wbar
-    static constexpr int OFF_TMEM = OFF_BAR + 8 * (2 * STAGES + 2 * NG + 1);
+    static constexpr int NBUF = 2 * NG;                        // TMEM accumulators (two per epilogue group)
+    static constexpr int OFF_BAR = OFF_EPI + EPI_BYTES;        // full[S], empty[S], tfull[NBUF], tempty[NBUF], wbar
+    static constexpr int OFF_TMEM = OFF_BAR + 8 * (2 * STAGES + 2 * NBUF + 1);
     static constexpr int OFF_PAR = (OFF_TMEM + 8 + 15) / 16 * 16;
     static constexpr int DYN_BYTES = OFF_PAR + 7 * 64 * 4 + 1024;
 };
@@ -739,7 +786,7 @@ conv_halo64_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
                    const ConvKParams p) {
     using Plan = HaloPlan<CHUNKS, STAGES, NG>;
     constexpr int BN = 64;
-    static_assert(NG == 2 || NG == 4, "TMEM allocations are powers of two");
+    static_assert(NG == 2 || NG == 4, "TMEM allocations are powers of two (2 * NG * 64 columns)");
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;
@@ -750,8 +797,9 @@ conv_halo64_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
     auto full_bar = [&](int s) { return sBar + 8u * s; };
     auto empty_bar = [&](int s) { return sBar + 8u * (STAGES + s); };
     auto tfull_bar = [&](int b) { return sBar + 8u * (2 * STAGES + b); };
-    auto tempty_bar = [&](int b) { return sBar + 8u * (2 * STAGES + NG + b); };
-    const uint32_t w_bar = sBar + 8u * (2 * STAGES + 2 * NG);
+    constexpr int NBUF = Plan::NBUF;
+    auto tempty_bar = [&](int b) { return sBar + 8u * (2 * STAGES + NBUF + b); };
+    const uint32_t w_bar = sBar + 8u * (2 * STAGES + 2 * NBUF);
     volatile uint32_t *tmem_ptr = reinterpret_cast<volatile uint32_t *>(gbase + Plan::OFF_TMEM);
     float *s_par = reinterpret_cast<float *>(gbase + Plan::OFF_PAR);
 
@@ -767,14 +815,14 @@ conv_halo64_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
             mbar_init(full_bar(s), 1);
             mbar_init(empty_bar(s), 1);
         }
-        for (int b = 0; b < NG; ++b) {
+        for (int b = 0; b < NBUF; ++b) {
             mbar_init(tfull_bar(b), 1);
             mbar_init(tempty_bar(b), 4);     // BN == 64: tiles are dealt round-robin to the epilogue groups
         }
         mbar_init(w_bar, 1);
         fence_barrier_init();
     }
-    if (warp == 1) tmem_alloc(smem_u32(const_cast<uint32_t *>(tmem_ptr)), NG * BN);
+    if (warp == 1) tmem_alloc(smem_u32(const_cast<uint32_t *>(tmem_ptr)), 2 * NG * BN);
     if (warp >= 2) {
         for (int j = threadIdx.x - 64; j < 64; j += threads_for_groups(NG) - 64) {
             s_par[j] = p.bias[j];
@@ -811,14 +859,14 @@ conv_halo64_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
         }
         __syncwarp();
     } else if (warp == 1) {
-        // ===== MMA issuer =====
-        if (lane == 0) {
+        // ===== MMA issuer: the whole warp runs the loop in converged code, one elected lane issues (see umma_f16_w) =====
+        {
             constexpr uint32_t idesc = make_idesc(BM, BN);
             mbar_wait(w_bar, 0);
             int it_g = 0, lt = 0;
             for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++lt) {
-                const int buf = lt % NG;
-                mbar_wait(tempty_bar(buf), ((lt / NG) & 1) ^ 1u);
+                const int buf = lt % NBUF;
+                mbar_wait(tempty_bar(buf), ((lt / NBUF) & 1) ^ 1u);
                 tcgen05_fence_after();
                 const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(buf * BN);
 #pragma unroll
@@ -828,18 +876,26 @@ conv_halo64_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
                     mbar_wait(full_bar(s), ph);
                     tcgen05_fence_after();
                     const uint32_t a_slot = sA + s * HALO_SLOT;
+                    const uint64_t adesc0 = make_sw128_desc_sbo(a_slot, HALO_W * 128);
+                    const uint64_t bdesc0 = make_sw128_desc(sW + cc * W_TILE_BYTES);
+                    const uint32_t alo = static_cast<uint32_t>(adesc0), ahi = static_cast<uint32_t>(adesc0 >> 32);
+                    const uint32_t blo = static_cast<uint32_t>(bdesc0), bhi = static_cast<uint32_t>(bdesc0 >> 32);
 #pragma unroll
                     for (int tap = 0; tap < 9; ++tap) {
-                        const uint32_t a_tap = a_slot + static_cast<uint32_t>(((tap / 3) * HALO_W + (tap % 3)) * 128);
-                        const uint64_t adesc = make_sw128_desc_sbo(a_tap, HALO_W * 128);
-                        const uint64_t bdesc = make_sw128_desc(sW + (tap * CHUNKS + cc) * W_TILE_BYTES);
 #pragma unroll
-                        for (int k = 0; k < BK / 16; ++k)
-                            umma_f16(tmem_d, adesc + 2u * k, bdesc + 2u * k, idesc, (cc > 0 || tap > 0 || k > 0) ? 1u : 0u);
+                        for (int k = 0; k < BK / 16; ++k) {
+                            // start-address fields (>> 4): tap shift inside the halo patch, weight tile of the tap, 32-byte K step
+                            const uint32_t da = static_cast<uint32_t>((((tap / 3) * HALO_W + (tap % 3)) * 128 + k * 32) >> 4);
+                            const uint32_t db = static_cast<uint32_t>((tap * CHUNKS * W_TILE_BYTES + k * 32) >> 4);
+                            if (cc == 0 && tap == 0 && k == 0)
+                                umma_f16_w2<false>(tmem_d, alo + da, ahi, blo + db, bhi, idesc);
+                            else
+                                umma_f16_w2<true>(tmem_d, alo + da, ahi, blo + db, bhi, idesc);
+                        }
                     }
-                    umma_commit(empty_bar(s));
+                    umma_commit_w(empty_bar(s));
                 }
-                umma_commit(tfull_bar(buf));
+                umma_commit_w(tfull_bar(buf));
             }
         }
         __syncwarp();
@@ -856,8 +912,8 @@ conv_halo64_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
             const int tx = tile % p.tiles_x;
             const int ty = (tile / p.tiles_x) % p.tiles_y;
             const int img = tile / tiles_per_img;
-            epilogue_tile_tma<BN, HT_W, NG>(p, &tmD, s_par, s_stage, tmem_base, tfull_bar(0), tempty_bar(0), lt, group,
-                                            quad, lane, leader, tx * HT_W, ty * HT_H, img, 0, has_head, pending);
+            epilogue_tile_tma<BN, HT_W, NG, false, 2>(p, &tmD, s_par, s_stage, tmem_base, tfull_bar(0), tempty_bar(0), lt, group,
+                                                      quad, lane, leader, tx * HT_W, ty * HT_H, img, 0, has_head, pending);
         }
         if (leader && pending) tma_store_wait_all();
     }
@@ -865,7 +921,245 @@ conv_halo64_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
     __syncthreads();
     if (warp == 1) {
         tcgen05_fence_after();
-        tmem_dealloc(tmem_base, NG * BN);
+        tmem_dealloc(tmem_base, 2 * NG * BN);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// conv_halo64_kernel as a 2-CTA PAIR (cta_group::2, cluster of two CTAs on neighbouring SMs).
+//
+// M = 128, N = 64 MMAs read 4 KiB (A) + 2 KiB (B) of shared memory per 32 cycles = 192 B/clk against 128 B/clk of
+// shared-memory bandwidth: the full-resolution Cout = 64 layers sit at 46-51 % of the tensor pipe.  With cta_group::2 one
+// instruction drives both SMs' tensor cores on M = 256 (each CTA's own 128-pixel tile) and each CTA supplies HALF of the
+// weight tile (32 of the 64 output channels): 4 + 1 KiB per 32 cycles = 160 B/clk.  The even CTA issues every MMA; both
+// CTAs load their own halo patches (the odd CTA's TMA signals the even CTA's mbarrier: .cta_group::2 loads with the peer bit
+// of the barrier address cleared), stage / accumulator hand-backs are multicast commits to both CTAs, the odd CTA's
+// epilogue warps arrive on the even CTA's "accumulator drained" barrier.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_4d_2sm(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(dst),
+        "l"(map), "r"(bar & 0xFEFFFFFFu), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_2sm(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+                 "l"(map), "r"(bar & 0xFEFFFFFFu), "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void umma_f16_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    const uint32_t z = 0;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, {%5, %5, %5, %5, %5, %5, %5, %5}, p;\n"
+        "}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(z)
+        : "memory");
+}
+__device__ __forceinline__ void umma_f16_2sm_w(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    const uint32_t z = 0;       // all lanes call, one elected lane issues (see umma_f16_w)
+    asm volatile(
+        "{\n"
+        ".reg .pred p, q;\n"
+        "elect.sync _|q, 0xffffffff;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "@q tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, {%5, %5, %5, %5, %5, %5, %5, %5}, p;\n"
+        "}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(z)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit_2sm_w(uint32_t bar) {
+    const unsigned short mask = 3;
+    asm volatile(
+        "{\n"
+        ".reg .pred q;\n"
+        "elect.sync _|q, 0xffffffff;\n"
+        "@q tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n"
+        "}\n" ::"r"(bar), "h"(mask)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit_2sm(uint32_t bar) {      // arrives on the barrier at this offset in BOTH CTAs
+    const unsigned short mask = 3;
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask)
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_2sm(uint32_t dst_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_2sm(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+
+constexpr int W_HALF_BYTES = 32 * 128;                         // one (tap, chunk) weight tile, this CTA's 32 output channels
+
+template <int CHUNKS, int STAGES, int NG>
+struct HaloPairPlan {
+    static constexpr int OFF_W = 0;
+    static constexpr int OFF_A = 9 * CHUNKS * W_HALF_BYTES;
+    static constexpr int OFF_EPI = OFF_A + STAGES * HALO_SLOT;
+    static constexpr int EPI_BYTES = NG * STAGE_TILE_BYTES;
+    static constexpr int OFF_BAR = OFF_EPI + EPI_BYTES;        // full[S], empty[S], tfull[NG], tempty[NG], wbar
+    static constexpr int OFF_TMEM = OFF_BAR + 8 * (2 * STAGES + 2 * NG + 1);
+    static constexpr int OFF_PAR = (OFF_TMEM + 8 + 15) / 16 * 16;
+    static constexpr int DYN_BYTES = OFF_PAR + 7 * 64 * 4 + 1024;
+};
+
+template <int CHUNKS, int STAGES, int NG>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(threads_for_groups(NG), 1)
+conv_halo64_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
+                        const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmD, const ConvKParams p) {
+    using Plan = HaloPairPlan<CHUNKS, STAGES, NG>;
+    constexpr int BN = 64;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t base = (raw + 1023u) & ~1023u;
+    uint8_t *gbase = smem_raw + (base - raw);
+    const uint32_t sW = base + Plan::OFF_W;
+    const uint32_t sA = base + Plan::OFF_A;
+    const uint32_t sBar = base + Plan::OFF_BAR;
+    auto full_bar = [&](int s) { return sBar + 8u * s; };
+    auto empty_bar = [&](int s) { return sBar + 8u * (STAGES + s); };
+    auto tfull_bar = [&](int b) { return sBar + 8u * (2 * STAGES + b); };
+    auto tempty_bar = [&](int b) { return sBar + 8u * (2 * STAGES + NG + b); };
+    const uint32_t w_bar = sBar + 8u * (2 * STAGES + 2 * NG);
+    volatile uint32_t *tmem_ptr = reinterpret_cast<volatile uint32_t *>(gbase + Plan::OFF_TMEM);
+    float *s_par = reinterpret_cast<float *>(gbase + Plan::OFF_PAR);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int rank = static_cast<int>(cluster_ctarank());
+    const bool lead = rank == 0;
+    const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
+    const int tiles_per_img = p.tiles_x * p.tiles_y;
+    const int num_pairs = (p.num_tiles + 1) >> 1;
+
+    if (threadIdx.x == 0) {
+        prefetch_tmap(&tmA0);
+        if (CHUNKS > 1) prefetch_tmap(&tmA1);
+        prefetch_tmap(&tmB);
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(full_bar(s), 1);       // used in the even CTA only: its producer's arrive + both CTAs' TMA bytes
+            mbar_init(empty_bar(s), 1);      // multicast commit from the even CTA's MMA thread
+        }
+        for (int b = 0; b < NG; ++b) {
+            mbar_init(tfull_bar(b), 1);      // multicast commit
+            mbar_init(tempty_bar(b), 8);     // used in the even CTA only: 4 epilogue warps of each CTA
+        }
+        mbar_init(w_bar, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc_2sm(smem_u32(const_cast<uint32_t *>(tmem_ptr)), NG * BN);
+    if (warp >= 2) {
+        for (int j = threadIdx.x - 64; j < 64; j += threads_for_groups(NG) - 64) {
+            s_par[j] = p.bias[j];
+            s_par[64 + j] = p.scale[j];
+            s_par[128 + j] = p.shift[j];
+            for (int h = 0; h < p.head_n; ++h) s_par[(3 + h) * 64 + j] = p.head_w[h * 64 + j];
+        }
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    cluster_sync_all();                      // both CTAs' barriers are initialised before any remote arrive / multicast commit
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    auto my_tile = [&](int pair) {
+        const int t = 2 * pair + rank;
+        return t < p.num_tiles ? t : p.num_tiles - 1;      // odd tile count: the odd CTA repeats the last tile (identical stores)
+    };
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ===== TMA producer (both CTAs): this CTA's half of the weights once, then one halo patch per (pair, chunk) =====
+            if (lead) mbar_expect_tx(w_bar, 2 * 9 * CHUNKS * W_HALF_BYTES);
+            for (int t = 0; t < 9 * CHUNKS; ++t) tma_load_2d_2sm(sW + t * W_HALF_BYTES, &tmB, w_bar, t * BK, 32 * rank);
+            int it_g = 0;
+            for (int pair = cluster_id; pair < num_pairs; pair += num_clusters) {
+                const int tile = my_tile(pair);
+                const int tx = tile % p.tiles_x;
+                const int ty = (tile / p.tiles_x) % p.tiles_y;
+                const int img = tile / tiles_per_img;
+                const int x0 = tx * HT_W, y0 = ty * HT_H;
+#pragma unroll
+                for (int cc = 0; cc < CHUNKS; ++cc, ++it_g) {
+                    const int s = it_g % STAGES;
+                    const uint32_t ph = (it_g / STAGES) & 1;
+                    mbar_wait(empty_bar(s), ph ^ 1u);
+                    if (lead) mbar_expect_tx(full_bar(s), 2 * HALO_BYTES);
+                    tma_load_4d_2sm(sA + s * HALO_SLOT, cc == 0 ? &tmA0 : &tmA1, full_bar(s), 0, x0 - 1, y0 - 1, img);
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        // ===== MMA issuer: one thread of the EVEN CTA drives both tensor cores =====
+        if (lead) {
+            constexpr uint32_t idesc = make_idesc(256, BN);
+            mbar_wait(w_bar, 0);
+            int it_g = 0, lt = 0;
+            for (int pair = cluster_id; pair < num_pairs; pair += num_clusters, ++lt) {
+                const int buf = lt % NG;
+                mbar_wait(tempty_bar(buf), ((lt / NG) & 1) ^ 1u);
+                tcgen05_fence_after();
+                const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(buf * BN);
+#pragma unroll
+                for (int cc = 0; cc < CHUNKS; ++cc, ++it_g) {
+                    const int s = it_g % STAGES;
+                    const uint32_t ph = (it_g / STAGES) & 1;
+                    mbar_wait(full_bar(s), ph);
+                    tcgen05_fence_after();
+                    const uint32_t a_slot = sA + s * HALO_SLOT;
+#pragma unroll
+                    for (int tap = 0; tap < 9; ++tap) {
+                        const uint32_t a_tap = a_slot + static_cast<uint32_t>(((tap / 3) * HALO_W + (tap % 3)) * 128);
+                        const uint64_t adesc = make_sw128_desc_sbo(a_tap, HALO_W * 128);
+                        const uint64_t bdesc = make_sw128_desc(sW + (tap * CHUNKS + cc) * W_HALF_BYTES);
+#pragma unroll
+                        for (int k = 0; k < BK / 16; ++k)
+                            umma_f16_2sm_w(tmem_d, adesc + 2u * k, bdesc + 2u * k, idesc, (cc > 0 || tap > 0 || k > 0) ? 1u : 0u);
+                    }
+                    umma_commit_2sm_w(empty_bar(s));
+                }
+                umma_commit_2sm_w(tfull_bar(buf));
+            }
+        }
+        __syncwarp();
+    } else {
+        const int e = warp - 2;
+        const int quad = warp & 3;
+        const int group = e >> 2;
+        const uint32_t s_stage = base + Plan::OFF_EPI + static_cast<uint32_t>(group) * STAGE_TILE_BYTES;
+        const bool has_head = p.head_out != nullptr;
+        const bool leader = (e & 3) == 0 && lane == 0;
+        bool pending = false;
+        int lt = 0;
+        for (int pair = cluster_id; pair < num_pairs; pair += num_clusters, ++lt) {
+            const int tile = my_tile(pair);
+            const int tx = tile % p.tiles_x;
+            const int ty = (tile / p.tiles_x) % p.tiles_y;
+            const int img = tile / tiles_per_img;
+            epilogue_tile_tma<BN, HT_W, NG, true>(p, &tmD, s_par, s_stage, tmem_base, tfull_bar(0), tempty_bar(0), lt, group, quad, lane,
+                                                  leader, tx * HT_W, ty * HT_H, img, 0, has_head, pending);
+        }
+        if (leader && pending) tma_store_wait_all();
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    cluster_sync_all();                      // the peer's tensor core reads this CTA's weight half until its last MMA retires
+    if (warp == 1) {
+        tcgen05_fence_after();
+        tmem_dealloc_2sm(tmem_base, NG * BN);
     }
 }
 
@@ -976,7 +1270,7 @@ conv_hstream_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
         __syncwarp();
     } else if (warp == 1) {
         // ===== MMA issuer (single thread) =====
-        if (lane == 0) {
+        {       // all lanes run the issue loop in converged code, one elected lane issues (umma_f16_w)
             constexpr uint32_t idesc = make_idesc(BM, BN);
             int ia = 0, ib = 0, lt = 0;
             for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++lt) {
@@ -1001,14 +1295,14 @@ conv_hstream_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
                             const uint64_t adesc = make_sw128_desc_sbo(a_tap + static_cast<uint32_t>(mt * HT_H * HALO_W * 128), HALO_W * 128);
 #pragma unroll
                             for (int k = 0; k < BK / 16; ++k)
-                                umma_f16(tmem_d + static_cast<uint32_t>(mt * BN), adesc + 2u * k, bdesc + 2u * k, idesc,
+                                umma_f16_w(tmem_d + static_cast<uint32_t>(mt * BN), adesc + 2u * k, bdesc + 2u * k, idesc,
                                          (cc > 0 || tap > 0 || k > 0) ? 1u : 0u);
                         }
-                        umma_commit(emptyB(sb));
+                        umma_commit_w(emptyB(sb));
                     }
-                    umma_commit(emptyA(sa));
+                    umma_commit_w(emptyA(sa));
                 }
-                umma_commit(tfull_bar(buf));
+                umma_commit_w(tfull_bar(buf));
             }
         }
         __syncwarp();
@@ -1187,7 +1481,7 @@ conv_hstreamT_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_cons
         }
         __syncwarp();
     } else if (warp == 1) {
-        if (lane == 0) {
+        {       // all lanes run the issue loop in converged code, one elected lane issues (umma_f16_w)
             constexpr uint32_t idesc = make_idesc(BM, 256);       // M = 128 output channels, N = 256 pixels
             int ia = 0, ib = 0, lt = 0;
             for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++lt) {
@@ -1209,12 +1503,12 @@ conv_hstreamT_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_cons
                         const uint64_t xdesc = make_sw128_desc_sbo(a_slot + static_cast<uint32_t>(((tap / 3) * HALO_W + (tap % 3)) * 128), HALO_W * 128);
 #pragma unroll
                         for (int k = 0; k < BK / 16; ++k)
-                            umma_f16(tmem_d, wdesc + 2u * k, xdesc + 2u * k, idesc, (cc > 0 || tap > 0 || k > 0) ? 1u : 0u);
-                        umma_commit(emptyB(sb));
+                            umma_f16_w(tmem_d, wdesc + 2u * k, xdesc + 2u * k, idesc, (cc > 0 || tap > 0 || k > 0) ? 1u : 0u);
+                        umma_commit_w(emptyB(sb));
                     }
-                    umma_commit(emptyA(sa));
+                    umma_commit_w(emptyA(sa));
                 }
-                umma_commit(tfull_bar(buf));
+                umma_commit_w(tfull_bar(buf));
             }
         }
         __syncwarp();
@@ -1404,7 +1698,7 @@ wgrad_nhwc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             }
             __syncwarp();
         } else if (warp == 1) {
-            if (lane == 0) {
+            {       // all lanes run the issue loop in converged code, one elected lane issues (umma_f16_w)
                 // both operands MN-major: bits 15 / 16 of the instruction descriptor
                 const int n_cols = p.pair || p.kind == 2 ? BN : nvalid * p.cn_tile;
                 const uint32_t idesc = make_idesc(BM, n_cols) | (1u << 15) | (1u << 16);
@@ -1417,11 +1711,11 @@ wgrad_nhwc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                     for (int k = 0; k < 4; ++k) {      // 16 pixels (2 KiB) per MMA
                         const uint64_t adesc = make_sw128_mn_desc(sA + s * A_TILE + k * 2048, WG_BLOCK);
                         const uint64_t bdesc = make_sw128_mn_desc(sB + s * B_TILE + k * 2048, WG_BLOCK);
-                        umma_f16(tmem_base, adesc, bdesc, idesc, (it > 0 || k > 0) ? 1u : 0u);
+                        umma_f16_w(tmem_base, adesc, bdesc, idesc, (it > 0 || k > 0) ? 1u : 0u);
                     }
-                    umma_commit(empty_bar(s));
+                    umma_commit_w(empty_bar(s));
                 }
-                umma_commit(tfull_bar);
+                umma_commit_w(tfull_bar);
             }
             __syncwarp();
         } else {
@@ -1547,7 +1841,7 @@ wgrad_halo64_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             }
             __syncwarp();
         } else if (warp == 1) {
-            if (lane == 0) {
+            {       // all lanes run the issue loop in converged code, one elected lane issues (umma_f16_w)
                 constexpr uint32_t idesc = make_idesc(BM, 64) | (1u << 15) | (1u << 16);
                 for (int it = 0; it < num_k_iters; ++it) {
                     const int s = it % WH_STAGES;
@@ -1565,12 +1859,12 @@ wgrad_halo64_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                         for (int k = 0; k < 4; ++k) {      // 16 pixels = two 8-pixel patch rows per MMA
                             const uint64_t adesc = make_sw128_mn_desc2(a_slot + o1 * 128 + k * 2 * 1280, lbo, 1280);
                             const uint64_t bdesc = make_sw128_mn_desc2(b_slot + k * 2048, 8192, 1024);
-                            umma_f16(tmem_base + static_cast<uint32_t>(pr * 64), adesc, bdesc, idesc, (it > 0 || k > 0) ? 1u : 0u);
+                            umma_f16_w(tmem_base + static_cast<uint32_t>(pr * 64), adesc, bdesc, idesc, (it > 0 || k > 0) ? 1u : 0u);
                         }
                     }
-                    umma_commit(empty_bar(s));
+                    umma_commit_w(empty_bar(s));
                 }
-                umma_commit(tfull_bar);
+                umma_commit_w(tfull_bar);
             }
             __syncwarp();
         } else {
@@ -1685,7 +1979,7 @@ wgrad_row3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             }
             __syncwarp();
         } else if (warp == 1) {
-            if (lane == 0) {
+            {       // all lanes run the issue loop in converged code, one elected lane issues (umma_f16_w)
                 constexpr uint32_t idesc = make_idesc(BM, 128) | (1u << 15) | (1u << 16);
                 for (int it = 0; it < num_k_iters; ++it) {
                     const int s = it % W3_STAGES;
@@ -1700,12 +1994,12 @@ wgrad_row3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                         for (int k = 0; k < 4; ++k) {                      // 16 pixels = two 8-pixel patch rows per MMA
                             const uint64_t adesc = make_sw128_mn_desc2(a_slot + off * 128 + k * 2 * 1280, W3_A_SLOT, 1280);
                             const uint64_t bdesc = make_sw128_mn_desc2(b_slot + k * 2048, WG_BLOCK, 1024);
-                            umma_f16(tmem_base + static_cast<uint32_t>(kx * 128), adesc, bdesc, idesc, (it > 0 || k > 0) ? 1u : 0u);
+                            umma_f16_w(tmem_base + static_cast<uint32_t>(kx * 128), adesc, bdesc, idesc, (it > 0 || k > 0) ? 1u : 0u);
                         }
                     }
-                    umma_commit(empty_bar(s));
+                    umma_commit_w(empty_bar(s));
                 }
-                umma_commit(tfull_bar);
+                umma_commit_w(tfull_bar);
             }
             __syncwarp();
         } else {
@@ -2064,6 +2358,42 @@ int launch_halo(const CUtensorMap &a0, const CUtensorMap &a1, const CUtensorMap 
     return 0;
 }
 
+template <int CHUNKS, int STAGES, int NG>
+int launch_halo_pair(const CUtensorMap &a0, const CUtensorMap &a1, const CUtensorMap &b, const CUtensorMap &dmap,
+                     const ConvKParams &kp, cudaStream_t stream) {
+    using Plan = HaloPairPlan<CHUNKS, STAGES, NG>;
+    static int max_clusters[mbs::kMaxDevices] = {0};
+    const int dev = mbs::current_device();
+    if (!max_clusters[dev]) {
+        MBS_CHECK_CUDA(cudaFuncSetAttribute(conv_halo64_pair_kernel<CHUNKS, STAGES, NG>,
+                                            cudaFuncAttributeMaxDynamicSharedMemorySize, Plan::DYN_BYTES));
+        // persistent kernel: exactly as many 2-CTA clusters as can be co-resident (GPCs with an odd SM count leave one SM out)
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(sm_count() & ~1);
+        cfg.blockDim = dim3(threads_for_groups(NG));
+        cfg.dynamicSmemBytes = Plan::DYN_BYTES;
+        cudaLaunchAttribute attr;
+        attr.id = cudaLaunchAttributeClusterDimension;
+        attr.val.clusterDim.x = 2;
+        attr.val.clusterDim.y = 1;
+        attr.val.clusterDim.z = 1;
+        cfg.attrs = &attr;
+        cfg.numAttrs = 1;
+        int n = 0;
+        if (cudaOccupancyMaxActiveClusters(&n, conv_halo64_pair_kernel<CHUNKS, STAGES, NG>, &cfg) != cudaSuccess || n <= 0) {
+            cudaGetLastError();
+            n = sm_count() / 2;
+        }
+        max_clusters[dev] = n;
+        if (getenv("MBS_VERBOSE")) fprintf(stderr, "[mbseg] halo pair kernel: %d co-resident 2-CTA clusters\n", n);
+    }
+    int grid = 2 * max_clusters[dev];
+    if (grid > ((kp.num_tiles + 1) & ~1)) grid = (kp.num_tiles + 1) & ~1;
+    conv_halo64_pair_kernel<CHUNKS, STAGES, NG><<<grid, threads_for_groups(NG), Plan::DYN_BYTES, stream>>>(a0, a1, b, dmap, kp);
+    MBS_CHECK_LAUNCH();
+    return 0;
+}
+
 template <int BN, int MT, int SA, int SB>
 int launch_hstream(const CUtensorMap &a0, const CUtensorMap &a1, const CUtensorMap &b, const ConvKParams &kp, cudaStream_t stream) {
     using Plan = HsPlan<BN, MT, SA, SB>;
@@ -2112,6 +2442,15 @@ int epi_variant() {     // MBS_EPI_VARIANT (A/B runs): 0 default; 1 = transposed
         v = e ? atoi(e) : 0;
     }
     return v;
+}
+
+bool halo_pair_enabled() {      // MBS_NO_HALO_PAIR=1 (A/B runs): full-resolution Cout = 64 layers on single CTAs
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("MBS_NO_HALO_PAIR");
+        v = (e && e[0] == '1') ? 0 : 1;
+    }
+    return v == 1;
 }
 
 bool wgrad_halo_enabled() {
@@ -2224,12 +2563,20 @@ extern "C" int mbs_conv_gemm(const mbs_conv_desc *d, void *stream_) {
         } else {
             a1 = a0;
         }
-        rc = make_weight_map(&b, d->weight, 64, 9 * (d->C0 + d->C1), 64);
+        // measured (2048^2): two sources 0.529 -> 0.459 ms as a pair; one source 0.276 ms either way (the pair costs two SMs per
+        // cluster of scheduling freedom and gains nothing there)
+        const bool pair2 = halo_pair_enabled() && d->C1 > 0 && kp.num_tiles >= 2 * sm_count();
+        rc = make_weight_map(&b, d->weight, 64, 9 * (d->C0 + d->C1), pair2 ? 32 : 64);
         if (rc) return rc;
         CUtensorMap dm = a0;
         if (d->dst) {
             rc = make_act_map(&dm, d->dst, d->N, kp.Hd, kp.Wd, d->Cout, d->ldd, d->coffd, 1, HT_W, HT_H);
             if (rc) return rc;
+        }
+        if (pair2) {
+            // 2-CTA pairs (cta_group::2): each CTA supplies half of every weight tile (see conv_halo64_pair_kernel); the
+            // accumulation order is that of the single-CTA kernel, so results are bit-identical whichever runs
+            return launch_halo_pair<2, 4, 2>(a0, a1, b, dm, kp, stream);
         }
         if (d->C1 > 0) return launch_halo<2, 2, 2>(a0, a1, b, dm, kp, stream);
         // measured: 4 epilogue groups do not help here (64->64 @2048^2: 0.333 vs 0.324 ms) -- the MMAs' own smem

@@ -1,0 +1,52 @@
+"""A/B of the 2-CTA pair kernel on the full-resolution Cout = 64 layers: bit-identity with the single-CTA kernel and time."""
+import ctypes, os, subprocess, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+from microbeseg_b200 import _native as nat
+L = nat.lib(); dev = torch.device("cuda:0")
+torch.manual_seed(0)
+def run(C1, H, W, head):
+    x0 = torch.randn(1, H, W, 64, device=dev).bfloat16()
+    x1 = torch.randn(1, H, W, 64, device=dev).bfloat16() if C1 else None
+    w = (torch.randn(64, 9, 64 + C1, device=dev) * 0.05).bfloat16().contiguous()
+    bias = torch.randn(64, device=dev); sc = torch.rand(64, device=dev) + 0.5; sh = torch.randn(64, device=dev)
+    dst = torch.zeros(1, H, W, 64, device=dev, dtype=torch.bfloat16)
+    d = nat.ConvDesc()
+    d.mode, d.N, d.H, d.W = 0, 1, H, W
+    d.src0, d.C0, d.ld0, d.coff0 = x0.data_ptr(), 64, 64, 0
+    d.src1, d.C1, d.ld1, d.coff1 = (x1.data_ptr() if C1 else None), C1, (64 if C1 else 0), 0
+    d.weight, d.Cout = w.data_ptr(), 64
+    d.bias, d.scale, d.shift, d.act = bias.data_ptr(), sc.data_ptr(), sh.data_ptr(), 1
+    hw = torch.randn(2, 64, device=dev)
+    ho = torch.zeros(1, 2, H, W, device=dev)
+    if head:
+        d.dst, d.ldd, d.coffd = None, 64, 0
+        d.head_w, d.head_n, d.head_out = hw.data_ptr(), 2, ho.data_ptr()
+        d.head_b[0], d.head_b[1] = 0.1, -0.2
+    else:
+        d.dst, d.ldd, d.coffd = dst.data_ptr(), 64, 0
+        d.head_w, d.head_n, d.head_out = None, 0, None
+    for _ in range(3):
+        nat.check(L.mbs_conv_gemm(ctypes.byref(d), nat.stream_ptr()), "conv")
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(10):
+        nat.check(L.mbs_conv_gemm(ctypes.byref(d), nat.stream_ptr()), "conv")
+    e1.record(); torch.cuda.synchronize()
+    assert L.mbs_debug_flags(1) == 0, "barrier timeout"
+    return (ho if head else dst).float().cpu().numpy(), e0.elapsed_time(e1) / 10
+if len(sys.argv) > 1:
+    outs = {}
+    for C1, H, W, head in ((0, 2048, 2048, 0), (64, 2048, 2048, 0), (0, 2048, 2048, 1), (0, 1000, 1416, 0), (64, 520, 2056, 1)):
+        o, ms = run(C1, H, W, head)
+        print(sys.argv[1], (C1, H, W, head), f"{ms:.3f} ms", float(np.abs(o).mean()), flush=True)
+        np.save(f"/tmp/halo_{sys.argv[1]}_{C1}_{H}_{W}_{head}.npy", o)
+else:
+    env = dict(os.environ)
+    subprocess.check_call([sys.executable, __file__, "pair"], env=env)
+    env["MBS_NO_HALO_PAIR"] = "1"
+    subprocess.check_call([sys.executable, __file__, "single"], env=env)
+    for C1, H, W, head in ((0, 2048, 2048, 0), (64, 2048, 2048, 0), (0, 2048, 2048, 1), (0, 1000, 1416, 0), (64, 520, 2056, 1)):
+        a = np.load(f"/tmp/halo_pair_{C1}_{H}_{W}_{head}.npy"); b = np.load(f"/tmp/halo_single_{C1}_{H}_{W}_{head}.npy")
+        print((C1, H, W, head), "bit identical" if np.array_equal(a, b) else f"DIFF max {np.abs(a - b).max()} frac {(a != b).mean()}")
