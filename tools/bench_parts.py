@@ -193,6 +193,30 @@ def bench_c5(dev, rank, world, peaks, steps=10, warmup=3, per_gpu_batch=8, size=
             t = torch.tensor([e2e_ms], device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             e2e_ms = float(t.item())
+        # the augmentation pipeline that feeds the step (mytransforms.py 'train' transform), batched on the device
+        aug_rec = None
+        if rank == 0:
+            import random
+            from microbeseg_b200.augment import GpuAugmenter, draw_params
+            na = 64
+            ai = torch.from_numpy(np.stack([sy.synth_frame(S, S, 900 + i) for i in range(8)]).astype(np.uint16).view(np.int16)).to(dev).repeat(na // 8, 1, 1)
+            al = torch.from_numpy(np.tile(neigh[:8], (na // 8, 1, 1))[:na]).to(dev)
+            ac = torch.from_numpy(np.tile(cell[:8], (na // 8, 1, 1))[:na]).to(dev)
+            aug = GpuAugmenter(0, 65535, seed=1)
+            params = draw_params(na, random.Random(5), np.random.RandomState(5))
+            for _ in range(2):
+                aug(ai, al, ac, params)
+            ams = ev_time(lambda: aug(ai, al, ac, params), 5, warm=1)
+            aug_rec = {"crops_per_s": na / (ams / 1e3), "ms_per_batch": ams, "batch": na,
+                       "api": "microbeseg_b200.augment.GpuAugmenter (Flip, Contrast, Scaling, Rotate, Blur, Noise, ToTensor; parameters drawn on the host)"}
+            if torch_baseline:
+                from oracle import augment as oa
+                t0 = time.perf_counter()
+                for i in range(8):
+                    oa.apply({"image": np.ascontiguousarray(ai[i].cpu().numpy().view(np.uint16))[..., None],
+                              "border_label": neigh[i % len(neigh)][..., None], "cell_label": cell[i % len(cell)][..., None]}, params[i])
+                aug_rec["cpu_baseline"] = {"value": 8 / (time.perf_counter() - t0), "unit": "crops/s", "cores": 1, "kind": "port",
+                                           "sample": "8 crops through oracle/augment.py (NumPy / scipy, one DataLoader worker)"}
         base = {}
         if rank == 0 and torch_baseline:
             from oracle import net as onet
@@ -234,7 +258,7 @@ def bench_c5(dev, rank, world, peaks, steps=10, warmup=3, per_gpu_batch=8, size=
             "roofline": {"bound": "tensor", "achieved": ach, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
                          "frac": ach / peaks["tf_sustained"], "note": "per GPU, 3 x forward FLOPs (7.475 MFLOP/px)",
                          "peak_source": peaks["src"] + " (sustained cuBLAS bf16)"},
-            "reference_same_gpu": base}
+            "reference_same_gpu": base, "augment": aug_rec}
 
 
 def bench_gpu_reference(dev, size=2048, seed=2000, reps=3):
