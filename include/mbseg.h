@@ -114,6 +114,10 @@ int mbs_distance_postprocessing(const float *border, const float *cell, int H, i
                                 float th_seed, float th_cell, uint16_t *out, void *workspace,
                                 size_t workspace_bytes, int64_t *info_host, void *stream);
 
+/* Softmax over the three class planes of the boundary network, crop of the pads and channel-last layout in one pass
+ * (replaces F.softmax(prediction, dim=1)[0, :, pads...].permute(1, 2, 0), src/inference/infer.py:371-374).
+ * logits: 3 planes `plane_stride` floats apart, row pitch ld; (y0, x0): first kept pixel; prob: (H,W,3) float32. */
+int mbs_softmax3_hwc(const float *logits, size_t plane_stride, int ld, int y0, int x0, int H, int W, float *prob, void *stream);
 /* boundary method (replaces src/inference/postprocessing.py:62-90): prediction = softmax probabilities
  * (H,W,3) float32, channel-last as the reference passes them; the flood image is flat, so the result is
  * pure FIFO order and is produced by the exact sequential flood whenever two markers share a mask region. */

@@ -85,6 +85,7 @@ _SIGS = {
     "mbs_distance_postprocessing_sweep": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p,
                                                   c_void_p, c_size_t, c_void_p, c_void_p]),
     "mbs_boundary_postprocessing": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_size_t, c_void_p, c_void_p]),
+    "mbs_softmax3_hwc": (c_int, [c_void_p, c_size_t, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "mbs_pp_front": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_float, c_void_p, c_void_p, c_void_p,
                              c_void_p]),
     "mbs_pp_label8": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),

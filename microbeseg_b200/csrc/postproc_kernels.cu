@@ -2634,6 +2634,33 @@ extern "C" int mbs_distance_postprocessing_sweep(const float *border, const floa
     return 0;
 }
 
+// softmax over the three class planes of the boundary net + crop + channel-last layout in one pass (replaces
+// F.softmax(prediction, dim=1)[..., pads:, pads:].permute(...) of infer.py:371-374): exp(z - max) / sum as torch evaluates it
+namespace {
+__global__ void softmax3_hwc_kernel(const float *__restrict__ logits, size_t plane, int ld, int y0, int x0, int H, int W,
+                                    float *__restrict__ prob) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= W) return;
+    const size_t i = static_cast<size_t>(y0 + y) * ld + x0 + x;
+    const float z0 = logits[i], z1 = logits[plane + i], z2 = logits[2 * plane + i];
+    const float m = fmaxf(z0, fmaxf(z1, z2));
+    const float e0 = expf(z0 - m), e1 = expf(z1 - m), e2 = expf(z2 - m);
+    const float sum = (e0 + e1) + e2;
+    float *o = prob + (static_cast<size_t>(y) * W + x) * 3;
+    o[0] = e0 / sum;
+    o[1] = e1 / sum;
+    o[2] = e2 / sum;
+}
+}  // namespace
+
+extern "C" int mbs_softmax3_hwc(const float *logits, size_t plane_stride, int ld, int y0, int x0, int H, int W, float *prob,
+                                void *stream_) {
+    MBS_REQUIRE(logits && prob && H > 0 && W > 0 && ld >= x0 + W && y0 >= 0 && x0 >= 0, "softmax3_hwc: bad arguments");
+    softmax3_hwc_kernel<<<dim3(mbs::cdiv(W, 256), H), 256, 0, static_cast<cudaStream_t>(stream_)>>>(logits, plane_stride, ld, y0, x0, H, W, prob);
+    MBS_CHECK_LAUNCH();
+    return 0;
+}
+
 extern "C" size_t mbs_postproc_workspace_bytes(int H, int W) {
     const size_t n = static_cast<size_t>(H) * W;
     const size_t a = tiled_ws_bytes(n, H, W, true), b = legacy_postproc_workspace_bytes(H, W);

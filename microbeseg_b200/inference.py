@@ -13,6 +13,7 @@ import os
 import numpy as np
 import torch
 
+from . import _native as nat
 from . import postprocessing as pp
 from .utils import model_input_pads
 
@@ -118,7 +119,11 @@ class FrameSegmenter:
                     else:
                         # boundary method: softmax over the 3 classes, channel-last crop (infer.py:371-374)
                         maps.record_stream(self.pp_stream)
-                        prob = torch.softmax(maps, dim=1)[0, :, pads[0] + cy:, pads[1] + cx:].permute(1, 2, 0)
+                        hp, wp = maps.shape[-2], maps.shape[-1]
+                        y0, x0 = pads[0] + cy, pads[1] + cx
+                        prob = torch.empty((hp - y0, wp - x0, 3), dtype=torch.float32, device=maps.device)
+                        nat.check(nat.lib().mbs_softmax3_hwc(maps.data_ptr(), hp * wp, wp, y0, x0, hp - y0, wp - x0, prob.data_ptr(),
+                                                             nat.stream_ptr(self.pp_stream)), "softmax3_hwc")
                         run = lambda dst: pp.boundary_postprocessing_device(prob, out=dst)
                     if (cy, cx) == (0, 0):
                         run(st["dev_out"])

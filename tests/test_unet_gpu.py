@@ -335,6 +335,20 @@ def test_single_decoder_unet_with_three_channel_head(native_lib):
     _check(got.cpu().numpy(), ref.numpy(), "unet3")
 
 
+def test_softmax3_hwc_vs_torch(native_lib):
+    """mbs_softmax3_hwc (softmax over the 3 class planes + crop + channel-last, infer.py:371-374) vs torch.softmax: float32
+    exp / divide on both sides, tolerance 2e-7 absolute on probabilities"""
+    from microbeseg_b200 import _native as nat
+    g = torch.Generator(device="cpu").manual_seed(3)
+    logits = (torch.randn(1, 3, 80, 112, generator=g) * 4).cuda()
+    y0, x0 = 16, 22
+    prob = torch.empty((80 - y0, 112 - x0, 3), dtype=torch.float32, device="cuda")
+    nat.check(native_lib.mbs_softmax3_hwc(logits.data_ptr(), 80 * 112, 112, y0, x0, 80 - y0, 112 - x0, prob.data_ptr(), nat.stream_ptr()))
+    ref = torch.softmax(logits, dim=1)[0, :, y0:, x0:].permute(1, 2, 0)
+    assert float((prob - ref).abs().max()) <= 2e-7
+    assert float((prob.sum(-1) - 1).abs().max()) <= 1e-6
+
+
 def test_boundary_model_frame_loop(native_lib):
     """U net + softmax + boundary_postprocessing through the frame loop (infer.py:365-374)."""
     from microbeseg_b200 import synthetic as sy
