@@ -335,6 +335,20 @@ def test_single_decoder_unet_with_three_channel_head(native_lib):
     _check(got.cpu().numpy(), ref.numpy(), "unet3")
 
 
+def test_pair_kernel_is_bit_identical_to_single_cta_kernel(native_lib):
+    """conv_halo64_pair_kernel (cta_group::2, cluster of two CTAs, half weight tile per CTA) vs conv_halo64_kernel on the same
+    layers: same accumulation order, so the outputs (bf16 tensors and fused fp32 heads) must be IDENTICAL.  The kernel choice is
+    an environment knob read once per process, hence the subprocesses (tools/probe_halo_pair.py)."""
+    import subprocess, sys
+    root = os.path.dirname(HERE)
+    env = dict(os.environ, PROBE_SMALL="1")
+    out = subprocess.run([sys.executable, os.path.join(root, "tools", "probe_halo_pair.py")], env=env, capture_output=True, text=True,
+                         timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.startswith("(")]
+    assert len(lines) == 3 and all(l.endswith("bit identical") for l in lines), out.stdout
+
+
 def test_softmax3_hwc_vs_torch(native_lib):
     """mbs_softmax3_hwc (softmax over the 3 class planes + crop + channel-last, infer.py:371-374) vs torch.softmax: float32
     exp / divide on both sides, tolerance 2e-7 absolute on probabilities"""
