@@ -278,12 +278,39 @@ lab_cell_big_kernel(const uint16_t *__restrict__ masks, int H, int W, int ids, c
                     size_t scratch_stride, float *__restrict__ cell_dist, double *__restrict__ nraw, int smem_cap_elems) {
     const int crop = blockIdx.x;
     unsigned short *sm = scratch + static_cast<size_t>(crop) * scratch_stride;
-    for (int id = 1; id < ids; ++id) {
-        const CellStats s = cs[static_cast<size_t>(crop) * ids + id];
-        if (s.cnt == 0) continue;
-        const int wh = s.wy1 - s.wy0, ww = s.wx1 - s.wx0;
-        if (wh <= 0 || ww <= 0 || wh * ww <= smem_cap_elems) continue;
-        cell_edt(masks, H, W, crop, id, s, wh, ww, sm, cell_dist, nraw);
+    // the usual case is "none": all threads look for oversized windows in parallel and the CTA leaves at once
+    __shared__ int s_list[256];
+    __shared__ int s_n;
+    for (int id0 = 1; id0 < ids; id0 += 256 * 64) {           // chunks of ids (a chunk never yields more than 256 * 64 candidates)
+        if (threadIdx.x == 0) s_n = 0;
+        __syncthreads();
+        for (int id = id0 + threadIdx.x; id < ids && id < id0 + 256 * 64; id += 256) {
+            const CellStats s = cs[static_cast<size_t>(crop) * ids + id];
+            const int wh = s.wy1 - s.wy0, ww = s.wx1 - s.wx0;
+            if (s.cnt != 0 && wh > 0 && ww > 0 && wh * ww > smem_cap_elems) {
+                const int pos = atomicAdd(&s_n, 1);
+                if (pos < 256) s_list[pos] = id;
+            }
+        }
+        __syncthreads();
+        const int n = s_n;
+        if (n == 0) continue;
+        if (n <= 256) {
+            for (int k = 0; k < n; ++k) {
+                const int id = s_list[k];
+                const CellStats s = cs[static_cast<size_t>(crop) * ids + id];
+                cell_edt(masks, H, W, crop, id, s, s.wy1 - s.wy0, s.wx1 - s.wx0, sm, cell_dist, nraw);
+            }
+        } else {                                              // more than 256 oversized instances in the chunk: plain walk
+            for (int id = id0; id < ids && id < id0 + 256 * 64; ++id) {
+                const CellStats s = cs[static_cast<size_t>(crop) * ids + id];
+                if (s.cnt == 0) continue;
+                const int wh = s.wy1 - s.wy0, ww = s.wx1 - s.wx0;
+                if (wh <= 0 || ww <= 0 || wh * ww <= smem_cap_elems) continue;
+                cell_edt(masks, H, W, crop, id, s, wh, ww, sm, cell_dist, nraw);
+            }
+        }
+        __syncthreads();
     }
 }
 
@@ -528,23 +555,60 @@ __global__ void lab_erode_gap_bits_kernel(const unsigned long long *__restrict__
 }
 
 // border_label(label) == 2  <=>  foreground pixel with a different positive id in its 3x3 neighbourhood
-__global__ void lab_border_kernel(const uint16_t *__restrict__ masks, int H, int W, uint8_t *__restrict__ border) {
+// eight pixels of a row per thread: three 16-byte row loads (+ the two edge pixels) instead of 72 two-byte loads, one 8-byte store
+__global__ void __launch_bounds__(256) lab_border_kernel(const uint16_t *__restrict__ masks, int H, int W, uint8_t *__restrict__ border) {
     const int crop = blockIdx.z;
-    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
-    if (x >= W || y >= H) return;
+    const int x0 = (blockIdx.x * 32 + (threadIdx.x & 31)) * 8, y = blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (x0 >= W || y >= H) return;
     const uint16_t *m = masks + static_cast<size_t>(crop) * H * W;
-    const int l = m[y * W + x];
-    bool b = false;
-    if (l) {
-        for (int dy = -1; dy <= 1; ++dy)
-            for (int dx = -1; dx <= 1; ++dx) {
-                const int yy = y + dy, xx = x + dx;
-                if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
-                const int o = m[yy * W + xx];
-                b |= (o != 0 && o != l);
+    uint8_t *out = border + (static_cast<size_t>(crop) * H + y) * W + x0;
+    const bool vec = (W & 7) == 0;            // rows are 16-byte aligned and whole groups of eight
+    unsigned short r[3][10];
+#pragma unroll
+    for (int dy = 0; dy < 3; ++dy) {
+        const int yy = y + dy - 1;
+        if (yy < 0 || yy >= H) {
+#pragma unroll
+            for (int i = 0; i < 10; ++i) r[dy][i] = 0;
+            continue;
+        }
+        const uint16_t *row = m + static_cast<size_t>(yy) * W;
+        r[dy][0] = x0 > 0 ? row[x0 - 1] : 0;
+        if (vec) {
+            const uint4 v = *reinterpret_cast<const uint4 *>(row + x0);
+            const unsigned w4[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                r[dy][1 + 2 * i] = static_cast<unsigned short>(w4[i] & 0xFFFFu);
+                r[dy][2 + 2 * i] = static_cast<unsigned short>(w4[i] >> 16);
             }
+        } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) r[dy][1 + i] = x0 + i < W ? row[x0 + i] : 0;
+        }
+        r[dy][9] = x0 + 8 < W ? row[x0 + 8] : 0;
     }
-    border[(static_cast<size_t>(crop) * H + y) * W + x] = b;
+    unsigned long long packed = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const unsigned l = r[1][i + 1];
+        bool b = false;
+        if (l) {
+#pragma unroll
+            for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+                for (int dx = 0; dx < 3; ++dx) {
+                    const unsigned o = r[dy][i + dx];       // out-of-image neighbours read as 0 (skipped by the reference)
+                    b |= (o != 0 && o != l);
+                }
+        }
+        packed |= static_cast<unsigned long long>(b ? 1u : 0u) << (8 * i);
+    }
+    if (vec) {
+        *reinterpret_cast<unsigned long long *>(out) = packed;
+    } else {
+        for (int i = 0; i < 8 && x0 + i < W; ++i) out[i] = static_cast<uint8_t>((packed >> (8 * i)) & 1u);
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -948,7 +1012,7 @@ extern "C" int mbs_distance_labels(const uint16_t *masks, int n_crops, int H, in
         lab_close_cell_kernel<<<2 * 148, 256, smemc, stream>>>(masks, H, W, WW, ids, cs, info, lbits, smemc, big_list);
         MBS_CHECK_LAUNCH();
     }
-    lab_border_kernel<<<g3, b2, 0, stream>>>(masks, H, W, border);
+    lab_border_kernel<<<dim3(mbs::cdiv(W, 256), mbs::cdiv(H, 8), n_crops), 256, 0, stream>>>(masks, H, W, border);
     MBS_CHECK_LAUNCH();
     const int nwords = static_cast<int>((static_cast<long long>(n_crops) * H * WW + 255) / 256);
     lab_dilate_bits_kernel<<<nwords, 256, 0, stream>>>(lbits, H, W, WW, n_crops, dbits);
