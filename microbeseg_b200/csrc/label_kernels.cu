@@ -182,15 +182,15 @@ __device__ void cell_edt(const uint16_t *__restrict__ masks, int H, int W, int c
     __syncthreads();
     if (!s_any_own) return;                   // instance has no pixel inside its window: max EDT == 0 -> `continue`
     const bool any_bg = s_any_bg != 0, any_other = s_any_other != 0;
-    // row minimisation for the instance's pixels; squared distances are exact integers
-    unsigned int lmax1 = 0, lmax2 = 0;
+    // row minimisation for the instance's pixels; squared distances are exact integers.  Pass 1: distance to "not my id".
+    unsigned int lmax1 = 0;
     for (int i = threadIdx.x; i < wh * ww; i += blockDim.x) {
         if (lab[i] != id) continue;
         const int y = i / ww, x = i - y * ww;
-        unsigned int b1 = 0xFFFFFFFFu, b2 = 0xFFFFFFFFu;
+        unsigned int b1 = 0xFFFFFFFFu;
         // exact minimum over all columns, visited outwards from x: once dx^2 alone reaches the best squared distance
         // no farther column can improve it
-        const unsigned short *r1 = g1 + y * ww, *r2 = g2 + y * ww;
+        const unsigned short *r1 = g1 + y * ww;
         if (any_bg) {
             const int kmax = x > ww - 1 - x ? x : ww - 1 - x;
             for (int k = 0; k <= kmax; ++k) {
@@ -209,7 +209,25 @@ __device__ void cell_edt(const uint16_t *__restrict__ masks, int H, int W, int c
             // scipy's feature transform of an all-foreground array points at (-1, 0)
             b1 = static_cast<unsigned int>((y + 1) * (y + 1) + x * x);
         }
-        if (any_other) {
+        lmax1 = b1 > lmax1 ? b1 : lmax1;
+        // park the exact squared distance in the output array (bit pattern); the same thread converts it below
+        const size_t o = (static_cast<size_t>(crop) * H + s.wy0 + y) * W + s.wx0 + x;
+        cell_dist[o] = __uint_as_float(b1);
+    }
+    atomicMax(&s_max1, lmax1);
+    __syncthreads();
+    // Pass 2: distance to the other instances.  It only matters below den = min(max1 + 3, max2) (:321, larger values are
+    // clipped to 1), so the outward search starts from the bound (floor(max1 + 3) + 1)^2: a pixel without a site inside it
+    // has d2 >= max1 + 3, hence max2 >= max1 + 3, den = max1 + 3 and its value clips -- exact, and the search is short.
+    const unsigned int cap = static_cast<unsigned int>(floor(sqrt(static_cast<double>(s_max1)) + 3.0)) + 1u;
+    const unsigned int cap2 = cap < 65535u ? cap * cap : 0xFFFFFFFFu;
+    unsigned int lmax2 = 0;
+    if (any_other) {
+        for (int i = threadIdx.x; i < wh * ww; i += blockDim.x) {
+            if (lab[i] != id) continue;
+            const int y = i / ww, x = i - y * ww;
+            unsigned int b2 = cap2;
+            const unsigned short *r2 = g2 + y * ww;
             const int kmax = x > ww - 1 - x ? x : ww - 1 - x;
             for (int k = 0; k <= kmax; ++k) {
                 const unsigned int dx2 = static_cast<unsigned int>(k * k);
@@ -223,16 +241,11 @@ __device__ void cell_edt(const uint16_t *__restrict__ masks, int H, int W, int c
                     if (g != kInf16) { const unsigned int d = dx2 + g * g; b2 = d < b2 ? d : b2; }
                 }
             }
+            lmax2 = b2 > lmax2 ? b2 : lmax2;        // a capped value (>= cap2) keeps max2 >= (max1 + 3)^2, which is all den needs
+            const size_t o = (static_cast<size_t>(crop) * H + s.wy0 + y) * W + s.wx0 + x;
+            nraw[o] = __longlong_as_double(static_cast<long long>(b2));
         }
-        lmax1 = b1 > lmax1 ? b1 : lmax1;
-        if (any_other) lmax2 = b2 > lmax2 ? b2 : lmax2;
-        // park the exact squared distances in the output arrays (bit patterns); the same thread converts them
-        // below once the per-instance maxima are known
-        const size_t o = (static_cast<size_t>(crop) * H + s.wy0 + y) * W + s.wx0 + x;
-        cell_dist[o] = __uint_as_float(b1);
-        nraw[o] = __longlong_as_double(static_cast<long long>(any_other ? b2 : 0u));
     }
-    atomicMax(&s_max1, lmax1);
     atomicMax(&s_max2, lmax2);
     __syncthreads();
     const double max1 = sqrt(static_cast<double>(s_max1));               // np.max(EDT) (> 0: own pixels exist)
