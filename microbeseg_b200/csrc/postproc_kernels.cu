@@ -2436,9 +2436,14 @@ int coop_config(CoopCfg **out) {
         MBS_CHECK_CUDA(cudaFuncSetAttribute(flood_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FLOOD_SMEM16));
         MBS_CHECK_CUDA(cudaFuncSetAttribute(flood_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FLOOD_SMEM32));
         MBS_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, mid_kernel, 256, 0));
-        // a full grid: the phases are latency bound (measured at 4096^2: 1184 blocks 74 us, 296 blocks 102 us)
-        c.mid_blocks = sms * (per > 0 ? per : 1);
+        // the phases are latency bound; measured (config 3 / 2048^2 maps, whole pipeline): 1184 blocks 0.675 / 0.268 ms,
+        // 592 blocks 0.674 / 0.255 ms, 296 blocks 0.703 / 0.264 ms, 148 blocks 0.768 / 0.275 ms
+        c.mid_blocks = sms * (per > 4 ? 4 : (per > 0 ? per : 1));
         if (c.mid_blocks > MID_MAX_BLOCKS) c.mid_blocks = MID_MAX_BLOCKS;
+        if (const char *e = getenv("MBS_MID_BLOCKS")) {       // A/B knob
+            const int v = atoi(e);
+            if (v >= 1 && v <= c.mid_blocks) c.mid_blocks = v;
+        }
         MBS_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, flood_kernel<false>, 256, FLOOD_SMEM16));
         c.flood16_blocks = sms * (per > 0 ? per : 1);
         MBS_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, flood_kernel<true>, 256, FLOOD_SMEM32));
