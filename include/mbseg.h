@@ -95,6 +95,15 @@ typedef struct {
 } mbs_conv_desc;
 
 int mbs_conv_gemm(const mbs_conv_desc *d, void *stream);
+
+/* The first layer FUSED into the second convolution of the top encoder block (enc0b, 64 -> 64 channels, 3x3 stride 1):
+ * producer warps of the tensor-core kernel compute the first layer's halo patches straight into shared memory, so its
+ * 64-channel full-resolution output never exists in global memory.  Results are bit-identical to mbs_first_conv followed
+ * by mbs_conv_gemm(conv2).  img: N contiguous frames [N][H][W]; conv2: mode MBS_CONV3X3_S1, N, H + pad_y, W + pad_x,
+ * C0 = 64, C1 = 0, Cout = 64, no head (src0 is ignored).  Replaces unets.py:112-134 of the first ConvBlock. */
+int mbs_first_conv_halo64(const void *img, int in_dtype, int N, int H, int W, int pad_y, int pad_x, float norm_lo,
+                          float norm_hi, const float *lohi_dev, const float *weight, const float *bias, const float *scale,
+                          const float *shift, int act, const mbs_conv_desc *conv2, void *stream);
 /* pack helpers: f32 reference-layout weights -> bf16 GEMM layout (device to device) */
 int mbs_pack_conv3x3_weight(const float *w_oihw, int Cout, int Cin, void *packed_bf16, void *stream);
 int mbs_pack_convT2x2_weight(const float *w_iohw, int Cin, int Cout, void *packed_bf16, void *stream);

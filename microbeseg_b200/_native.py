@@ -75,6 +75,8 @@ _SIGS = {
     "mbs_debug_flags": (c_int, [c_int]),
     "mbs_first_conv": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_float, c_float, c_void_p, c_void_p,
                                c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_void_p]),
+    "mbs_first_conv_halo64": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_float, c_void_p,
+                                      c_void_p, c_void_p, c_void_p, c_void_p, c_int, ctypes.POINTER(ConvDesc), c_void_p]),
     "mbs_frame_minmax": (c_int, [c_void_p, c_int, ctypes.c_longlong, c_void_p, c_void_p, c_void_p]),
     "mbs_conv_gemm": (c_int, [ctypes.POINTER(ConvDesc), c_void_p]),
     "mbs_pack_conv3x3_weight": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p]),

@@ -100,6 +100,31 @@ __device__ __forceinline__ void fence_barrier_init() {
 __device__ __forceinline__ void fence_proxy_async() {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
+__device__ __forceinline__ uint64_t pack_f32x2(float a, float b) {
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+    return r;
+}
+__device__ __forceinline__ void unpack_f32x2(uint64_t v, float &a, float &b) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+}
+__device__ __forceinline__ uint64_t fma_f32x2(uint64_t a, uint64_t b, uint64_t c) {   // sm_100 FFMA2
+    uint64_t d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ void st_shared_v2(uint32_t addr, uint32_t a, uint32_t b) {
+    asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(a), "r"(b) : "memory");
+}
+__device__ __forceinline__ void named_bar_sync(int id, int threads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
 __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1,
                                             int c2, int c3) {
     asm volatile(
@@ -779,14 +804,30 @@ __device__ __forceinline__ uint64_t make_sw128_desc_sbo(uint32_t saddr, uint32_t
     return d;
 }
 
-template <int CHUNKS, int STAGES, int NG>
-__global__ void __launch_bounds__(threads_for_groups(NG), 1)
+// FIRST: the network's first layer (normalise + pad + Conv2d(1,64,3) + act + BN affine, see first_conv_kernel) is computed by
+// four extra producer warps straight into the swizzled halo stages -- the A operand never exists in global memory (saves
+// one 64-channel full-resolution write + read per frame).  Same FFMA2 chains as first_conv_kernel, so the bf16 values in
+// shared memory are bit-identical to what TMA would have loaded from first_conv_kernel's output.
+struct FirstParams {
+    const void *img;
+    int H, W, pad_y, pad_x;
+    float lo, hi;
+    const float *lohi_dev;
+    const float *weight, *bias, *scale, *shift;
+    int act;
+};
+constexpr int FIRST_IN_W = HALO_W + 2, FIRST_IN_H = HALO_H + 2;     // input patch of one halo patch (12 x 20)
+constexpr int FIRST_THREADS = 256;
+
+template <int CHUNKS, int STAGES, int NG, bool FIRST = false, typename T = uint8_t, bool RELU1 = false>
+__global__ void __launch_bounds__(threads_for_groups(NG) + (FIRST ? FIRST_THREADS : 0), 1)
 conv_halo64_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                    const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmD,
-                   const ConvKParams p) {
+                   const ConvKParams p, const FirstParams f) {
     using Plan = HaloPlan<CHUNKS, STAGES, NG>;
     constexpr int BN = 64;
     static_assert(NG == 2 || NG == 4, "TMEM allocations are powers of two (2 * NG * 64 columns)");
+    static_assert(!FIRST || CHUNKS == 1, "the fused first layer is the only source");
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;
@@ -842,7 +883,7 @@ conv_halo64_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
             mbar_expect_tx(w_bar, 9 * CHUNKS * W_TILE_BYTES);
             for (int t = 0; t < 9 * CHUNKS; ++t) tma_load_2d(sW + t * W_TILE_BYTES, &tmB, w_bar, t * BK, 0);
             int it_g = 0;
-            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+            for (int tile = blockIdx.x; !FIRST && tile < p.num_tiles; tile += gridDim.x) {
                 const int tx = tile % p.tiles_x;
                 const int ty = (tile / p.tiles_x) % p.tiles_y;
                 const int img = tile / tiles_per_img;
@@ -899,6 +940,152 @@ conv_halo64_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
             }
         }
         __syncwarp();
+    } else if (FIRST && warp >= 2 + 4 * NG) {
+        // ===== first-layer producer warps: compute the halo patch of every tile into its swizzled stage =====
+        // thread = (4-channel group g, position lane pl); two halo positions per iteration (independent FFMA2 chains)
+        const int tp = threadIdx.x - threads_for_groups(NG);
+        const int g = tp & 15;
+        const int pl = tp >> 4;
+        constexpr int LANES = FIRST_THREADS / 16;
+        float *s_in = s_par + 7 * 64;         // [FIRST_IN_H][FIRST_IN_W] normalised input patch
+        const T *img_base = static_cast<const T *>(f.img);
+        float lo = f.lo, hi = f.hi;
+        if (f.lohi_dev) {
+            lo = f.lohi_dev[0];
+            hi = f.lohi_dev[1];
+        }
+        const float range = hi - lo;
+        const int Hp = f.H + f.pad_y, Wp = f.W + f.pad_x;
+        // channels 0,1 of the group as FFMA2 chains (fma.rn.f32x2: 4 cycles of the fmaheavy pipe per warp instruction),
+        // channels 2,3 as scalar FFMA chains (either FMA pipe): measured, an all-FFMA2 producer is bound by fmaheavy alone
+        uint64_t w2[9], b2, sc2, sh2;
+        float w1[2][9], b1[2], sc1[2], sh1[2];
+        {
+            const int ca = g * 4;
+#pragma unroll
+            for (int t = 0; t < 9; ++t) {
+                w2[t] = pack_f32x2(f.weight[ca * 9 + t], f.weight[(ca + 1) * 9 + t]);
+                w1[0][t] = f.weight[(ca + 2) * 9 + t];
+                w1[1][t] = f.weight[(ca + 3) * 9 + t];
+            }
+            b2 = pack_f32x2(f.bias[ca], f.bias[ca + 1]);
+            sc2 = pack_f32x2(f.scale[ca], f.scale[ca + 1]);
+            sh2 = pack_f32x2(f.shift[ca], f.shift[ca + 1]);
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                b1[u] = f.bias[ca + 2 + u];
+                sc1[u] = f.scale[ca + 2 + u];
+                sh1[u] = f.shift[ca + 2 + u];
+            }
+        }
+        constexpr int IN_N = FIRST_IN_H * FIRST_IN_W;                       // 240 <= FIRST_THREADS: one value per thread
+        static_assert(IN_N <= FIRST_THREADS, "one input value per producer thread");
+        const int in_r = tp / FIRST_IN_W, in_c = tp - in_r * FIRST_IN_W;
+        // raw input value of a tile's patch: the load is issued one tile ahead, the value is converted / normalised only
+        // after the FMA work of the current tile (finish), so the global latency hides behind it
+        int kind = 0;      // 0: conv zero padding, 1: pad value (frame min), 2: pixel
+        auto load_raw = [&](int tx, int ty, int img) -> T {
+            const int yy = ty * HT_H - 2 + in_r, xx = tx * HT_W - 2 + in_c;
+            kind = 0;
+            T raw = T(0);
+            if (tp < IN_N && yy >= 0 && yy < Hp && xx >= 0 && xx < Wp) {
+                kind = 1;
+                if (yy >= f.pad_y && xx >= f.pad_x) {
+                    kind = 2;
+                    raw = img_base[(static_cast<size_t>(img) * f.H + (yy - f.pad_y)) * f.W + (xx - f.pad_x)];
+                }
+            }
+            return raw;
+        };
+        auto finish = [&](T rawv) -> float {
+            if (kind == 0) return 0.0f;
+            const float raw = kind == 2 ? static_cast<float>(rawv) : lo;
+            return hi < lo ? raw : __fsub_rn(__fdiv_rn(__fmul_rn(2.0f, __fsub_rn(raw, lo)), range), 1.0f);
+        };
+        // one halo position, 4 channels, first_conv_kernel's summation order per channel
+        auto item = [&](const float (&in)[9], uint32_t (&out)[2]) {
+            uint64_t a = b2;
+            float c0 = b1[0], c1 = b1[1];
+#pragma unroll
+            for (int t = 0; t < 9; ++t) {
+                a = fma_f32x2(pack_f32x2(in[t], in[t]), w2[t], a);
+                c0 = __fmaf_rn(in[t], w1[0][t], c0);
+                c1 = __fmaf_rn(in[t], w1[1][t], c1);
+            }
+            float o0, o1;
+            unpack_f32x2(a, o0, o1);
+            if (RELU1) {
+                o0 = fmaxf(o0, 0.0f);
+                o1 = fmaxf(o1, 0.0f);
+                c0 = fmaxf(c0, 0.0f);
+                c1 = fmaxf(c1, 0.0f);
+            } else if (f.act != MBS_ACT_NONE) {
+                o0 = apply_act(o0, f.act);
+                o1 = apply_act(o1, f.act);
+                c0 = apply_act(c0, f.act);
+                c1 = apply_act(c1, f.act);
+            }
+            unpack_f32x2(fma_f32x2(pack_f32x2(o0, o1), sc2, sh2), o0, o1);
+            c0 = __fmaf_rn(c0, sc1[0], sh1[0]);
+            c1 = __fmaf_rn(c1, sc1[1], sh1[1]);
+            __nv_bfloat162 h0 = __floats2bfloat162_rn(o0, o1), h1 = __floats2bfloat162_rn(c0, c1);
+            out[0] = *reinterpret_cast<uint32_t *>(&h0);
+            out[1] = *reinterpret_cast<uint32_t *>(&h1);
+        };
+        // tile coordinates are carried from the prefetch to the next iteration (one set of divisions per tile)
+        int tile = blockIdx.x;
+        int tx = 0, ty = 0, img = 0;
+        if (tile < p.num_tiles) {
+            tx = tile % p.tiles_x;
+            ty = (tile / p.tiles_x) % p.tiles_y;
+            img = tile / tiles_per_img;
+        }
+        T rawv = tile < p.num_tiles ? load_raw(tx, ty, img) : T(0);
+        for (int it_g = 0; tile < p.num_tiles; ++it_g) {
+            const int x0 = tx * HT_W - 1, y0 = ty * HT_H - 1;       // image position of halo pixel (0, 0)
+            if (tp < IN_N) s_in[tp] = finish(rawv);
+            named_bar_sync(8, FIRST_THREADS);
+            tile += gridDim.x;
+            if (tile < p.num_tiles) {
+                tx = tile % p.tiles_x;
+                ty = (tile / p.tiles_x) % p.tiles_y;
+                img = tile / tiles_per_img;
+                rawv = load_raw(tx, ty, img);
+            }
+            const int s = it_g % STAGES;
+            mbar_wait(empty_bar(s), ((it_g / STAGES) & 1) ^ 1u);
+            const uint32_t slot = sA + s * HALO_SLOT;
+#pragma unroll 1
+            for (int pos0 = pl; pos0 < HALO_W * HALO_H; pos0 += 2 * LANES) {
+                float in[2][9];
+                bool live[2];
+                int pos[2];
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                    pos[q] = pos0 + q * LANES;
+                    const int pc = pos[q] < HALO_W * HALO_H ? pos[q] : pl;       // clamp: the value is not stored
+                    const int hy = pc / HALO_W, hx = pc - hy * HALO_W;
+                    live[q] = x0 + hx >= 0 && x0 + hx < Wp && y0 + hy >= 0 && y0 + hy < Hp;
+                    const float *ip = s_in + hy * FIRST_IN_W + hx;
+#pragma unroll
+                    for (int t = 0; t < 9; ++t) in[q][t] = ip[(t / 3) * FIRST_IN_W + (t % 3)];
+                }
+                uint32_t out[2][2];
+                item(in[0], out[0]);
+                item(in[1], out[1]);
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                    if (pos[q] >= HALO_W * HALO_H) continue;
+                    // outside the layer's output = the conv's zero padding (what TMA zero fill gave);
+                    // SWIZZLE_128B: 16-byte chunk index XOR (128-byte row index mod 8); the slot is 1024-byte aligned
+                    st_shared_v2(slot + pos[q] * 128 + (((g >> 1) ^ (pos[q] & 7)) << 4) + ((g & 1) << 3),
+                                 live[q] ? out[q][0] : 0u, live[q] ? out[q][1] : 0u);
+                }
+            }
+            fence_proxy_async();               // generic-proxy stores -> visible to the tensor core's async-proxy reads
+            named_bar_sync(8, FIRST_THREADS);  // also: everyone is done reading s_in
+            if (tp == 0) mbar_arrive(full_bar(s));
+        }
     } else {
         const int e = warp - 2;
         const int quad = warp & 3;
@@ -2046,19 +2233,6 @@ wgrad_row3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 constexpr int FC_TW = 32, FC_TH = 36;   // tall tiles (a multiple of 3 rows): the 96 per-thread weight/affine loads amortise over 36 rows
 static_assert(FC_TH % 3 == 0, "the row loop rotates three register rows");
 
-__device__ __forceinline__ uint64_t pack_f32x2(float a, float b) {
-    uint64_t r;
-    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
-    return r;
-}
-__device__ __forceinline__ void unpack_f32x2(uint64_t v, float &a, float &b) {
-    asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
-}
-__device__ __forceinline__ uint64_t fma_f32x2(uint64_t a, uint64_t b, uint64_t c) {   // sm_100 FFMA2
-    uint64_t d;
-    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
-    return d;
-}
 // Persistent: each CTA keeps its 8-channel slice of the weights / affine in registers and walks 32x36-pixel tiles.
 template <typename T, bool RELU>
 __global__ void __launch_bounds__(256, 2)
@@ -2353,7 +2527,29 @@ int launch_halo(const CUtensorMap &a0, const CUtensorMap &a1, const CUtensorMap 
         configured[dev] = true;
     }
     const int grid = kp.num_tiles < sm_count() ? kp.num_tiles : sm_count();
-    conv_halo64_kernel<CHUNKS, STAGES, NG><<<grid, threads_for_groups(NG), Plan::DYN_BYTES, stream>>>(a0, a1, b, dmap, kp);
+    conv_halo64_kernel<CHUNKS, STAGES, NG><<<grid, threads_for_groups(NG), Plan::DYN_BYTES, stream>>>(a0, a1, b, dmap, kp,
+                                                                                                       FirstParams{});
+    MBS_CHECK_LAUNCH();
+    return 0;
+}
+
+template <typename T, bool RELU1>
+int launch_halo_first(const CUtensorMap &b, const CUtensorMap &dmap, const ConvKParams &kp, const FirstParams &fp,
+                      cudaStream_t stream) {
+    constexpr int STAGES = 4, NG = 2;
+    using Plan = HaloPlan<1, STAGES, NG>;
+    constexpr int DYN = Plan::DYN_BYTES + 1024;      // + the producers' input patch behind the epilogue parameters
+    static_assert(FIRST_IN_H * FIRST_IN_W * 4 <= 1024, "input patch");
+    static bool configured[mbs::kMaxDevices] = {false};
+    const int dev = mbs::current_device();
+    if (!configured[dev]) {
+        MBS_CHECK_CUDA(cudaFuncSetAttribute(conv_halo64_kernel<1, STAGES, NG, true, T, RELU1>,
+                                            cudaFuncAttributeMaxDynamicSharedMemorySize, DYN));
+        configured[dev] = true;
+    }
+    const int grid = kp.num_tiles < sm_count() ? kp.num_tiles : sm_count();
+    conv_halo64_kernel<1, STAGES, NG, true, T, RELU1>
+        <<<grid, threads_for_groups(NG) + FIRST_THREADS, DYN, stream>>>(b, b, b, dmap, kp, fp);
     MBS_CHECK_LAUNCH();
     return 0;
 }
@@ -2860,6 +3056,72 @@ extern "C" int mbs_first_conv(const void *img, int in_dtype, int H, int W, int p
     }
 #undef MBS_FIRST_CONV
     MBS_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int mbs_first_conv_halo64(const void *img, int in_dtype, int N, int H, int W, int pad_y, int pad_x, float norm_lo,
+                                     float norm_hi, const float *lohi_dev, const float *weight, const float *bias,
+                                     const float *scale, const float *shift, int act, const mbs_conv_desc *d, void *stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    MBS_REQUIRE(d != nullptr && img != nullptr, "null argument");
+    MBS_REQUIRE(d->mode == MBS_CONV3X3_S1 && d->C0 == 64 && d->C1 == 0 && d->Cout == 64,
+                "fused first layer: the second convolution must be 3x3 stride 1, 64 -> 64 channels");
+    MBS_REQUIRE(d->N == N && d->H == H + pad_y && d->W == W + pad_x, "fused first layer: descriptor / frame size mismatch");
+    MBS_REQUIRE(d->head_out == nullptr && d->dst != nullptr, "fused first layer: plain destination only");
+    MBS_REQUIRE(((reinterpret_cast<uintptr_t>(d->dst) + static_cast<size_t>(d->coffd) * 2) & 15) == 0 && (d->ldd * 2) % 16 == 0,
+                "destination view must be 16-byte aligned");
+    ConvKParams kp;
+    memset(&kp, 0, sizeof(kp));
+    kp.mode = d->mode;
+    kp.act = d->act;
+    kp.Hm = kp.Hd = d->H;
+    kp.Wm = kp.Wd = d->W;
+    kp.tiles_x = mbs::cdiv(kp.Wm, HT_W);
+    kp.tiles_y = mbs::cdiv(kp.Hm, HT_H);
+    kp.n_tiles = 1;
+    kp.chunks0 = 1;
+    kp.taps = 9;
+    kp.Cout = 64;
+    kp.bias = d->bias;
+    kp.scale = d->scale;
+    kp.shift = d->shift;
+    kp.dst = static_cast<__nv_bfloat16 *>(d->dst);
+    kp.ldd = d->ldd;
+    kp.coffd = d->coffd;
+    const long long tiles_ll = static_cast<long long>(N) * kp.tiles_x * kp.tiles_y;
+    MBS_REQUIRE(tiles_ll > 0 && tiles_ll < (1ll << 31), "too many tiles");
+    kp.num_tiles = static_cast<int>(tiles_ll);
+    CUtensorMap b, dm;
+    int rc = make_weight_map(&b, d->weight, 64, 9 * 64, 64);
+    if (rc) return rc;
+    rc = make_act_map(&dm, d->dst, N, kp.Hd, kp.Wd, 64, d->ldd, d->coffd, 1, HT_W, HT_H);
+    if (rc) return rc;
+    FirstParams fp;
+    fp.img = img;
+    fp.H = H;
+    fp.W = W;
+    fp.pad_y = pad_y;
+    fp.pad_x = pad_x;
+    fp.lo = norm_lo;
+    fp.hi = norm_hi;
+    fp.lohi_dev = lohi_dev;
+    fp.weight = weight;
+    fp.bias = bias;
+    fp.scale = scale;
+    fp.shift = shift;
+    fp.act = act;
+    switch (in_dtype) {
+        case MBS_IN_U8:
+            return act == MBS_ACT_RELU ? launch_halo_first<uint8_t, true>(b, dm, kp, fp, stream)
+                                       : launch_halo_first<uint8_t, false>(b, dm, kp, fp, stream);
+        case MBS_IN_U16:
+            return act == MBS_ACT_RELU ? launch_halo_first<uint16_t, true>(b, dm, kp, fp, stream)
+                                       : launch_halo_first<uint16_t, false>(b, dm, kp, fp, stream);
+        case MBS_IN_F32:
+            return act == MBS_ACT_RELU ? launch_halo_first<float, true>(b, dm, kp, fp, stream)
+                                       : launch_halo_first<float, false>(b, dm, kp, fp, stream);
+        default: MBS_REQUIRE(false, "fused first layer: unknown input dtype %d", in_dtype);
+    }
     return 0;
 }
 

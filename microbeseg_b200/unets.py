@@ -11,6 +11,7 @@ BatchNorm folded into the conv epilogue, ``torch.cat`` expressed as a second K s
 head fused into the last conv.  No fallback: anything the CUDA path does not cover raises.
 """
 import ctypes
+import os
 
 import torch
 import torch.nn as nn
@@ -427,7 +428,7 @@ class _Engine:
         return t
 
     # -- launches ------------------------------------------------------------------------------
-    def _conv(self, mode, name, n, h, w, src0, src1, dst, head=None, head_out=None, act=None):
+    def _conv(self, mode, name, n, h, w, src0, src1, dst, head=None, head_out=None, act=None, first=None):
         packed, bias, scale, shift, cin, cout = self.p[name]
         d = nat.ConvDesc()
         d.mode, d.N, d.H, d.W = mode, n, h, w
@@ -453,7 +454,14 @@ class _Engine:
                 d.head_b[k] = b
         else:
             d.head_w, d.head_n, d.head_out = None, 0, None
-        nat.check(self.L.mbs_conv_gemm(ctypes.byref(d), nat.stream_ptr()), name)
+        if first is not None:      # the network's first layer is produced inside this convolution's kernel
+            img, h0, w0, pad_y, pad_x, lo, hi, lohi_dev, w1, b1, sc1, sh1 = first
+            nat.check(self.L.mbs_first_conv_halo64(img.data_ptr(), _IN_CODES[img.dtype], n, h0, w0, pad_y, pad_x, lo, hi,
+                                                   lohi_dev.data_ptr() if lohi_dev is not None else None,
+                                                   w1.data_ptr(), b1.data_ptr(), sc1.data_ptr(), sh1.data_ptr(),
+                                                   self.act, ctypes.byref(d), nat.stream_ptr()), name)
+        else:
+            nat.check(self.L.mbs_conv_gemm(ctypes.byref(d), nat.stream_ptr()), name)
         self.last_conv_launches += 1
         if name in self.norms and dst is not None:
             self._apply_norm(name, dst)
@@ -482,7 +490,11 @@ class _Engine:
             pool = [self._buf(f"pool_{l}", (n, H >> (l + 1), W >> (l + 1), ch[l])) for l in range(nl - 1)]
             # encoder
             packed, bias, scale, shift, _, c0 = self.p["enc0a"]
-            for b in range(n):
+            # no normalisation layer between the two convolutions of the top block and 64 channels: the first layer is
+            # computed inside enc0b's tensor-core kernel (mbs_first_conv_halo64, bit-identical to the two-launch path)
+            fused_first = (c0 == 64 and ch[0] == 64 and "enc0a" not in self.norms and "enc0b" not in self.norms
+                           and os.environ.get("MBS_FIRST_FUSE", "0") == "1")
+            for b in range(0 if fused_first else n):
                 nat.check(self.L.mbs_first_conv(img[b].data_ptr(), _IN_CODES[img.dtype], h0, w0, pad_y, pad_x, lo, hi,
                                                 lohi_dev.data_ptr() if lohi_dev is not None else None,
                                                 packed.data_ptr(), bias.data_ptr(), scale.data_ptr(),
@@ -495,7 +507,11 @@ class _Engine:
             for l in range(nl):
                 if l > 0:
                     self._conv(0, f"enc{l}a", n, H >> l, W >> l, pool[l - 1], None, t1[l])
-                self._conv(0, f"enc{l}b", n, H >> l, W >> l, t1[l], None, skip[l])
+                if l == 0 and fused_first:
+                    self._conv(0, "enc0b", n, H, W, t1[0], None, skip[0],
+                               first=(img, h0, w0, pad_y, pad_x, lo, hi, lohi_dev, packed, bias, scale, shift))
+                else:
+                    self._conv(0, f"enc{l}b", n, H >> l, W >> l, t1[l], None, skip[l])
                 if l < nl - 1:
                     if self.net.pool_method == 'max':          # nn.MaxPool2d(2, 2), unets.py:363-364
                         nat.check(self.L.mbs_maxpool2x2(skip[l].data_ptr(), n, H >> l, W >> l, ch[l], pool[l].data_ptr(),

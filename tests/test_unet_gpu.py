@@ -349,6 +349,30 @@ def test_pair_kernel_is_bit_identical_to_single_cta_kernel(native_lib):
     assert len(lines) == 3 and all(l.endswith("bit identical") for l in lines), out.stdout
 
 
+@pytest.mark.parametrize("act", ["relu", "mish"])
+def test_fused_first_layer_is_bit_identical_to_two_launches(native_lib, act, monkeypatch):
+    """mbs_first_conv_halo64 (first layer computed by producer warps inside enc0b's tensor-core kernel) vs mbs_first_conv +
+    mbs_conv_gemm: same FFMA2 chains and the same MMA order, so both network outputs must be IDENTICAL -- uint16 / uint8 /
+    float32 frames, with padding, ragged tiles (H not a multiple of 16) and a batch of two."""
+    torch.set_grad_enabled(False)
+    net, sd = _build((64, 128), act, 77)
+    rng = np.random.default_rng(77)
+    cases = [(rng.integers(200, 5000, (50, 70)).astype(np.uint16).view(np.int16), [14, 58], 200.0, 4999.0),
+             (rng.integers(3, 250, (24, 40)).astype(np.uint8), [0, 0], 3.0, 249.0),
+             (rng.standard_normal((2, 72, 88)).astype(np.float32), [0, 0], 1.0, -1.0),      # already normalised, batch of 2
+             (rng.integers(0, 60000, (297, 333)).astype(np.uint16).view(np.int16), [3, 3], 0.0, 59999.0)]
+    for img, pads, lo, hi in cases:
+        dev = torch.from_numpy(img).cuda()
+        outs = []
+        for knob in ("1", "0"):
+            monkeypatch.setenv("MBS_FIRST_FUSE", knob)
+            o = net.engine().run(dev if dev.dim() == 3 else dev[None], pads[0], pads[1], lo, hi)
+            outs.append([t.clone() for t in o])
+        for a, b in zip(*outs):
+            assert torch.equal(a, b), (img.shape, img.dtype, float((a - b).abs().max()))
+        assert all(torch.isfinite(t).all() for t in outs[0])
+
+
 def test_softmax3_hwc_vs_torch(native_lib):
     """mbs_softmax3_hwc (softmax over the 3 class planes + crop + channel-last, infer.py:371-374) vs torch.softmax: float32
     exp / divide on both sides, tolerance 2e-7 absolute on probabilities"""
