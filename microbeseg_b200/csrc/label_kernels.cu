@@ -140,22 +140,51 @@ __global__ void lab_window_kernel(CellStats *cs, int ids, int total, int H, int 
 // one CTA per (instance, crop): exact EDT of the instance and of "everything but the other
 // instances" inside the search window (distance_label :280-330)
 // ---------------------------------------------------------------------------------------------
-// `sm`: 3 * wh * ww unsigned shorts of scratch -- shared memory (lab_cell_kernel) or, for windows that do not fit, a
+// `sm`: 4 * wh * ww unsigned shorts of scratch -- shared memory (lab_cell_kernel) or, for windows that do not fit, a
 // per-crop global buffer (lab_cell_big_kernel); every exit is block-uniform, so the function can be called in a loop.
 __device__ void cell_edt(const uint16_t *__restrict__ masks, int H, int W, int crop, int id, const CellStats &s, int wh, int ww,
                          unsigned short *sm, float *__restrict__ cell_dist, double *__restrict__ nraw) {
     unsigned short *lab = sm;                 // [wh][ww] labels
     unsigned short *g1 = sm + wh * ww;        // vertical distance to the nearest pixel with label != id (own pixels)
     unsigned short *g2 = g1 + wh * ww;        // vertical distance to the nearest pixel of ANOTHER instance
-    __shared__ unsigned int s_max1, s_max2, s_any_bg, s_any_other, s_any_own;
+    unsigned short *own = g2 + wh * ww;       // compact list of the instance's pixels (window indices)
+    // An instance covers ~10-15 % of its search window: the three per-pixel passes below walk the compact list instead of
+    // the window (no divergence between own / foreign lanes, ~7x fewer iterations).  Windows of more than 65536 pixels
+    // (lab_cell_big_kernel only) do not fit 16-bit indices and walk the window.
+    const int n_win = wh * ww;
+    const bool use_list = n_win <= 65536;
+    __shared__ unsigned int s_max1, s_max2, s_any_bg, s_any_other, s_any_own, s_n_own;
     __syncthreads();                          // a previous call's readers of the shared flags are done
-    if (threadIdx.x == 0) { s_max1 = 0; s_max2 = 0; s_any_bg = 0; s_any_other = 0; s_any_own = 0; }
+    if (threadIdx.x == 0) { s_max1 = 0; s_max2 = 0; s_any_bg = 0; s_any_other = 0; s_any_own = 0; s_n_own = 0; }
+    __syncthreads();
     const uint16_t *m = masks + static_cast<size_t>(crop) * H * W;
-    for (int i = threadIdx.x; i < wh * ww; i += blockDim.x) {
-        const int y = i / ww, x = i - y * ww;
-        lab[i] = m[static_cast<size_t>(s.wy0 + y) * W + s.wx0 + x];
+    {
+        // one window row per warp and step (no index division; warp-uniform trip counts for the full-mask ballots)
+        const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+        for (int y = wid; y < wh; y += nw) {
+            const uint16_t *mrow = m + static_cast<size_t>(s.wy0 + y) * W + s.wx0;
+            for (int xb = 0; xb < ww; xb += 32) {
+                const int x = xb + lane;
+                bool mine = false;
+                if (x < ww) {
+                    const unsigned short l = mrow[x];
+                    lab[y * ww + x] = l;
+                    mine = l == id;
+                }
+                if (use_list) {
+                    const unsigned int bal = __ballot_sync(0xFFFFFFFFu, mine);
+                    if (bal) {
+                        unsigned int pos = 0;
+                        if (lane == 0) pos = atomicAdd(&s_n_own, __popc(bal));
+                        pos = __shfl_sync(0xFFFFFFFFu, pos, 0);
+                        if (mine) own[pos + __popc(bal & ((1u << lane) - 1u))] = static_cast<unsigned short>(y * ww + x);
+                    }
+                }
+            }
+        }
     }
     __syncthreads();
+    const int n_own = static_cast<int>(s_n_own);
     // column scans (one thread per column): nearest site above / below
     for (int t = threadIdx.x; t < 2 * ww; t += blockDim.x) {
         const int x = t >> 1, which = t & 1;  // which = 0: sites are "not my id", 1: sites are other instances
@@ -184,8 +213,9 @@ __device__ void cell_edt(const uint16_t *__restrict__ masks, int H, int W, int c
     const bool any_bg = s_any_bg != 0, any_other = s_any_other != 0;
     // row minimisation for the instance's pixels; squared distances are exact integers.  Pass 1: distance to "not my id".
     unsigned int lmax1 = 0;
-    for (int i = threadIdx.x; i < wh * ww; i += blockDim.x) {
-        if (lab[i] != id) continue;
+    for (int j = threadIdx.x; j < (use_list ? n_own : n_win); j += blockDim.x) {
+        const int i = use_list ? own[j] : j;
+        if (!use_list && lab[i] != id) continue;
         const int y = i / ww, x = i - y * ww;
         unsigned int b1 = 0xFFFFFFFFu;
         // exact minimum over all columns, visited outwards from x: once dx^2 alone reaches the best squared distance
@@ -223,8 +253,9 @@ __device__ void cell_edt(const uint16_t *__restrict__ masks, int H, int W, int c
     const unsigned int cap2 = cap < 65535u ? cap * cap : 0xFFFFFFFFu;
     unsigned int lmax2 = 0;
     if (any_other) {
-        for (int i = threadIdx.x; i < wh * ww; i += blockDim.x) {
-            if (lab[i] != id) continue;
+        for (int j = threadIdx.x; j < (use_list ? n_own : n_win); j += blockDim.x) {
+            const int i = use_list ? own[j] : j;
+            if (!use_list && lab[i] != id) continue;
             const int y = i / ww, x = i - y * ww;
             unsigned int b2 = cap2;
             const unsigned short *r2 = g2 + y * ww;
@@ -251,8 +282,9 @@ __device__ void cell_edt(const uint16_t *__restrict__ masks, int H, int W, int c
     const double max1 = sqrt(static_cast<double>(s_max1));               // np.max(EDT) (> 0: own pixels exist)
     const double max2 = sqrt(static_cast<double>(s_max2));
     const double den = fmin(max1 + 3.0, max2);                           // :321
-    for (int i = threadIdx.x; i < wh * ww; i += blockDim.x) {
-        if (lab[i] != id) continue;
+    for (int j = threadIdx.x; j < (use_list ? n_own : n_win); j += blockDim.x) {
+        const int i = use_list ? own[j] : j;
+        if (!use_list && lab[i] != id) continue;
         const int y = i / ww, x = i - y * ww;
         const size_t o = (static_cast<size_t>(crop) * H + s.wy0 + y) * W + s.wx0 + x;
         const double d1 = sqrt(static_cast<double>(__float_as_uint(cell_dist[o])));
@@ -734,9 +766,15 @@ __global__ void gap_stats_kernel(const uint8_t *__restrict__ gap, const int *__r
         }
 }
 
+// rescale + clip (:355-358)
+__device__ __forceinline__ double rescale_clip(double v) {
+    v = 1.0 / sqrt(0.65 + 0.5 * exp(-11.0 * (v - 0.75))) - 0.19;
+    return v < 0.0 ? 0.0 : (v > 1.0 ? 1.0 : v);
+}
 // gap map (label_closed_corr) + max with raw neighbour map and touching borders + rescale + clip (:352-358) at one pixel
 __device__ __forceinline__ double compose_at(const uint8_t *__restrict__ gp, const int *__restrict__ g, const GapStats *__restrict__ gsc,
-                                             const uint8_t *__restrict__ border, const double *__restrict__ nraw, int H, int W, int y, int x) {
+                                             const uint8_t *__restrict__ border, const double *__restrict__ nraw, int H, int W, int y, int x,
+                                             double at_zero) {
     const int me = gp[y * W + x] ? g[y * W + x] : -1;
     float corr = 0.0f;
     if (me >= 0) {
@@ -760,8 +798,10 @@ __device__ __forceinline__ double compose_at(const uint8_t *__restrict__ gp, con
     double v = nraw[y * W + x];
     v = fmax(v, static_cast<double>(corr));
     v = fmax(v, border[y * W + x] ? 1.0 : 0.0);
-    v = 1.0 / sqrt(0.65 + 0.5 * exp(-11.0 * (v - 0.75))) - 0.19;
-    return v < 0.0 ? 0.0 : (v > 1.0 ? 1.0 : v);
+    // ~85 % of the pixels are plain background (v == 0): they take the value the same instructions gave for 0 (computed
+    // once per block from a run-time zero, so the compiler cannot fold it with host arithmetic) and skip ~100 FP64 ops
+    if (v == 0.0) return at_zero;
+    return rescale_clip(v);
 }
 
 __device__ __forceinline__ int reflect_idx(int i, int n) {
@@ -780,9 +820,15 @@ constexpr int GT = 32;
 __global__ void __launch_bounds__(256)
 lab_compose_closing_kernel(const uint8_t *__restrict__ gap, const int *__restrict__ gid, const GapStats *__restrict__ gs,
                            const uint8_t *__restrict__ border, const double *__restrict__ nraw, int H, int W, int max_gaps,
-                           float *__restrict__ out) {
-    __shared__ double S[GT + 4][GT + 4 + 1];
-    __shared__ double D[GT + 2][GT + 2 + 1];
+                           float *__restrict__ out, double zero) {
+    // float32 rounding is monotone, so float(min(max(doubles))) == min(max(float(doubles))): the composed value is rounded
+    // once and the two 3x3 filters run on floats (one FMNMX per comparison instead of ~10 instructions per fp64 max)
+    __shared__ float S[GT + 4][GT + 4 + 1];
+    __shared__ float D[GT + 2][GT + 2 + 1];
+    __shared__ double s_at_zero;
+    if (threadIdx.x == 0) s_at_zero = rescale_clip(zero);
+    __syncthreads();
+    const double at_zero = s_at_zero;
     const int crop = blockIdx.z;
     const int x0 = blockIdx.x * GT, y0 = blockIdx.y * GT;
     const int tid = threadIdx.x;
@@ -793,21 +839,21 @@ lab_compose_closing_kernel(const uint8_t *__restrict__ gap, const int *__restric
     const GapStats *gsc = gs + static_cast<size_t>(crop) * max_gaps;
     for (int i = tid; i < (GT + 4) * (GT + 4); i += 256) {
         const int r = i / (GT + 4), c = i - r * (GT + 4);
-        S[r][c] = compose_at(gp, g, gsc, bp, np_, H, W, reflect_idx(y0 - 2 + r, H), reflect_idx(x0 - 2 + c, W));
+        S[r][c] = static_cast<float>(compose_at(gp, g, gsc, bp, np_, H, W, reflect_idx(y0 - 2 + r, H), reflect_idx(x0 - 2 + c, W), at_zero));
     }
     __syncthreads();
     for (int i = tid; i < (GT + 2) * (GT + 2); i += 256) {
         const int r = i / (GT + 2), c = i - r * (GT + 2);
         if (y0 - 1 + r > H || x0 - 1 + c > W) {      // beyond the 1-pixel apron of the image (ragged last tiles): never read
-            D[r][c] = 0.0;
+            D[r][c] = 0.0f;
             continue;
         }
         const int qy = reflect_idx(y0 - 1 + r, H) - (y0 - 2), qx = reflect_idx(x0 - 1 + c, W) - (x0 - 2);   // indices into S
-        double v = S[qy][qx];
+        float v = S[qy][qx];
 #pragma unroll
         for (int dy = -1; dy <= 1; ++dy)
 #pragma unroll
-            for (int dx = -1; dx <= 1; ++dx) v = fmax(v, S[qy + dy][qx + dx]);
+            for (int dx = -1; dx <= 1; ++dx) v = fmaxf(v, S[qy + dy][qx + dx]);
         D[r][c] = v;
     }
     __syncthreads();
@@ -815,12 +861,12 @@ lab_compose_closing_kernel(const uint8_t *__restrict__ gap, const int *__restric
         const int r = i / GT, c = i - r * GT;
         const int x = x0 + c, y = y0 + r;
         if (x >= W || y >= H) continue;
-        double v = D[r + 1][c + 1];
+        float v = D[r + 1][c + 1];
 #pragma unroll
         for (int dy = 0; dy <= 2; ++dy)
 #pragma unroll
-            for (int dx = 0; dx <= 2; ++dx) v = fmin(v, D[r + dy][c + dx]);
-        out[base + static_cast<size_t>(y) * W + x] = static_cast<float>(v);
+            for (int dx = 0; dx <= 2; ++dx) v = fminf(v, D[r + dy][c + dx]);
+        out[base + static_cast<size_t>(y) * W + x] = v;
     }
 }
 
@@ -998,8 +1044,8 @@ extern "C" int mbs_distance_labels(const uint16_t *masks, int n_crops, int H, in
         const int smem_opt = smem_opt_dev[dev];
         // size the launch for the largest window the radius can produce, capped by the device limit
         const int R = search_radius >= 0 ? search_radius : (radius_hint >= 0 ? radius_hint : (H > W ? H : W));
-        long long want = 3ll * 2 * (2ll * R) * (2ll * R);
-        const long long full = 3ll * 2 * H * W;
+        long long want = 4ll * 2 * (2ll * R) * (2ll * R);
+        const long long full = 4ll * 2 * H * W;
         if (want > full) want = full;
         int smem = want > smem_opt ? smem_opt : static_cast<int>(want);
         if (smem < 4096) smem = 4096;
@@ -1009,13 +1055,13 @@ extern "C" int mbs_distance_labels(const uint16_t *masks, int n_crops, int H, in
         if (!cell_threads) {
             const char *e = getenv("MBS_LAB_CELL_THREADS");       // A/B knob
             cell_threads = e ? atoi(e) : 128;
-            if (cell_threads < 32 || cell_threads > 256) cell_threads = 128;
+            if (cell_threads < 32 || cell_threads > 256 || cell_threads % 32) cell_threads = 128;   // whole warps (full-mask ballots)
         }
-        lab_cell_kernel<<<gc, cell_threads, smem, stream>>>(masks, H, W, ids, cs, info, cell_dist, nraw, smem / 6);
+        lab_cell_kernel<<<gc, cell_threads, smem, stream>>>(masks, H, W, ids, cs, info, cell_dist, nraw, smem / 8);
         MBS_CHECK_LAUNCH();
         if (full > smem)         // windows larger than shared memory are possible: the global-memory walk picks them up
             lab_cell_big_kernel<<<n_crops, 256, 0, stream>>>(masks, H, W, ids, cs, reinterpret_cast<unsigned short *>(scaled),
-                                                             static_cast<size_t>(H) * W * 4, cell_dist, nraw, smem / 6);
+                                                             static_cast<size_t>(H) * W * 4, cell_dist, nraw, smem / 8);
         MBS_CHECK_LAUNCH();
         long long wantc = 2ll * (static_cast<long long>(H) + 6) * (W + 6);
         int smemc = wantc > smem_opt ? smem_opt : static_cast<int>(wantc);
@@ -1044,7 +1090,7 @@ extern "C" int mbs_distance_labels(const uint16_t *masks, int n_crops, int H, in
     gap_stats_kernel<<<g3, b2, 0, stream>>>(gap, gid, nraw, H, W, kMaxGaps, gs);
     MBS_CHECK_LAUNCH();
     lab_compose_closing_kernel<<<dim3(mbs::cdiv(W, GT), mbs::cdiv(H, GT), n_crops), 256, 0, stream>>>(gap, gid, gs, border, nraw, H, W, kMaxGaps,
-                                                                                                  neighbor_dist);
+                                                                                                  neighbor_dist, 0.0);
     MBS_CHECK_LAUNCH();
     if (max_mal_out)
         MBS_CHECK_CUDA(cudaMemcpy2DAsync(max_mal_out, sizeof(int), &info[0].max_mal, sizeof(CropInfo), sizeof(int), n_crops,
