@@ -153,14 +153,20 @@ __device__ void cell_edt(const uint16_t *__restrict__ masks, int H, int W, int c
     // (lab_cell_big_kernel only) do not fit 16-bit indices and walk the window.
     const int n_win = wh * ww;
     const bool use_list = n_win <= 65536;
-    __shared__ unsigned int s_max1, s_max2, s_any_bg, s_any_other, s_any_own, s_n_own;
+    __shared__ unsigned int s_max1, s_max2, s_any_other, s_n_own;
+    __shared__ int s_bx0, s_bx1, s_by0, s_by1;
     __syncthreads();                          // a previous call's readers of the shared flags are done
-    if (threadIdx.x == 0) { s_max1 = 0; s_max2 = 0; s_any_bg = 0; s_any_other = 0; s_any_own = 0; s_n_own = 0; }
+    if (threadIdx.x == 0) {
+        s_max1 = 0; s_max2 = 0; s_any_other = 0; s_n_own = 0;
+        s_bx0 = ww; s_bx1 = -1; s_by0 = wh; s_by1 = -1;
+    }
     __syncthreads();
     const uint16_t *m = masks + static_cast<size_t>(crop) * H * W;
     {
-        // one window row per warp and step (no index division; warp-uniform trip counts for the full-mask ballots)
+        // one window row per warp and step (no index division; warp-uniform trip counts for the full-mask ballots);
+        // also the bounding box of the instance inside the window
         const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+        int bx0 = ww, bx1 = -1, by0 = wh, by1 = -1;
         for (int y = wid; y < wh; y += nw) {
             const uint16_t *mrow = m + static_cast<size_t>(s.wy0 + y) * W + s.wx0;
             for (int xb = 0; xb < ww; xb += 32) {
@@ -171,74 +177,89 @@ __device__ void cell_edt(const uint16_t *__restrict__ masks, int H, int W, int c
                     lab[y * ww + x] = l;
                     mine = l == id;
                 }
-                if (use_list) {
-                    const unsigned int bal = __ballot_sync(0xFFFFFFFFu, mine);
-                    if (bal) {
-                        unsigned int pos = 0;
-                        if (lane == 0) pos = atomicAdd(&s_n_own, __popc(bal));
+                const unsigned int bal = __ballot_sync(0xFFFFFFFFu, mine);
+                if (bal) {
+                    const int lo = xb + __ffs(bal) - 1, hi = xb + 31 - __clz(bal);
+                    bx0 = lo < bx0 ? lo : bx0;
+                    bx1 = hi > bx1 ? hi : bx1;
+                    by0 = y < by0 ? y : by0;
+                    by1 = y;
+                    unsigned int pos = 0;
+                    if (lane == 0) pos = atomicAdd(&s_n_own, __popc(bal));
+                    if (use_list) {
                         pos = __shfl_sync(0xFFFFFFFFu, pos, 0);
                         if (mine) own[pos + __popc(bal & ((1u << lane) - 1u))] = static_cast<unsigned short>(y * ww + x);
                     }
                 }
             }
         }
+        if (lane == 0 && bx1 >= 0) {          // warp-uniform values (derived from ballots)
+            atomicMin(&s_bx0, bx0);
+            atomicMax(&s_bx1, bx1);
+            atomicMin(&s_by0, by0);
+            atomicMax(&s_by1, by1);
+        }
     }
     __syncthreads();
     const int n_own = static_cast<int>(s_n_own);
-    // column scans (one thread per column): nearest site above / below
-    for (int t = threadIdx.x; t < 2 * ww; t += blockDim.x) {
-        const int x = t >> 1, which = t & 1;  // which = 0: sites are "not my id", 1: sites are other instances
-        unsigned short *g = which ? g2 : g1;
-        int d = -1;                           // distance to the last site seen going down (-1: none yet)
-        bool any_site = false, own = false;
-        for (int y = 0; y < wh; ++y) {
-            const int l = lab[y * ww + x];
-            const bool site = which ? (l != 0 && l != id) : (l != id);
-            any_site |= site; own |= (l == id);
-            d = site ? 0 : (d < 0 ? -1 : d + 1);
-            g[y * ww + x] = d < 0 ? kInf16 : static_cast<unsigned short>(d);
+    if (n_own == 0) return;                   // instance has no pixel inside its window: max EDT == 0 -> `continue`
+    const bool any_bg = n_own < n_win;
+    const int bx0 = s_bx0, bx1 = s_bx1, by0 = s_by0, by1 = s_by1;
+    // Column scans (one thread per column): vertical distance to the nearest site above / below, only where it can matter.
+    // sites = pixels that are not the instance (g) or pixels of other instances (which = 1); rows r0..r1, columns c0..c1.
+    auto scan_columns = [&](unsigned short *g, bool others, int c0, int c1, int r0, int r1) {
+        bool any_site = false;
+        for (int x = c0 + static_cast<int>(threadIdx.x); x <= c1; x += blockDim.x) {
+            int d = -1;                       // distance to the last site seen going down (-1: none yet)
+            for (int y = r0; y <= r1; ++y) {
+                const int l = lab[y * ww + x];
+                const bool site = others ? (l != 0 && l != id) : (l != id);
+                any_site |= site;
+                d = site ? 0 : (d < 0 ? -1 : d + 1);
+                g[y * ww + x] = d < 0 ? kInf16 : static_cast<unsigned short>(d);
+            }
+            d = -1;
+            for (int y = r1; y >= r0; --y) {
+                const int l = lab[y * ww + x];
+                const bool site = others ? (l != 0 && l != id) : (l != id);
+                d = site ? 0 : (d < 0 ? -1 : d + 1);
+                if (d >= 0 && d < g[y * ww + x]) g[y * ww + x] = static_cast<unsigned short>(d);
+            }
         }
-        d = -1;
-        for (int y = wh - 1; y >= 0; --y) {
-            const int l = lab[y * ww + x];
-            const bool site = which ? (l != 0 && l != id) : (l != id);
-            d = site ? 0 : (d < 0 ? -1 : d + 1);
-            if (d >= 0 && d < g[y * ww + x]) g[y * ww + x] = static_cast<unsigned short>(d);
+        return any_site;
+    };
+    // exact minimum over the columns c0..c1 of row y, visited outwards from x: once dx^2 alone reaches the best squared
+    // distance no farther column can improve it
+    auto row_min = [&](const unsigned short *r, int x, int c0, int c1, unsigned int b) {
+        const int kmax = x - c0 > c1 - x ? x - c0 : c1 - x;
+        for (int k = 0; k <= kmax; ++k) {
+            const unsigned int dx2 = static_cast<unsigned int>(k * k);
+            if (dx2 >= b) break;
+            if (x - k >= c0) {
+                const unsigned int g = r[x - k];
+                if (g != kInf16) { const unsigned int d = dx2 + g * g; b = d < b ? d : b; }
+            }
+            if (k && x + k <= c1) {
+                const unsigned int g = r[x + k];
+                if (g != kInf16) { const unsigned int d = dx2 + g * g; b = d < b ? d : b; }
+            }
         }
-        if (any_site) { if (which) s_any_other = 1; else s_any_bg = 1; }
-        if (own) s_any_own = 1;
-    }
+        return b;
+    };
+    // Pass 1: distance to "not my id".  The nearest such pixel of an instance pixel lies inside the instance's bounding box
+    // grown by one pixel (a site farther out has a closer site between it and the pixel), so only that part of the window is
+    // scanned and searched.
+    const int c0a = bx0 > 0 ? bx0 - 1 : 0, c1a = bx1 + 1 < ww ? bx1 + 1 : ww - 1;
+    const int r0a = by0 > 0 ? by0 - 1 : 0, r1a = by1 + 1 < wh ? by1 + 1 : wh - 1;
+    if (any_bg) scan_columns(g1, false, c0a, c1a, r0a, r1a);
     __syncthreads();
-    if (!s_any_own) return;                   // instance has no pixel inside its window: max EDT == 0 -> `continue`
-    const bool any_bg = s_any_bg != 0, any_other = s_any_other != 0;
-    // row minimisation for the instance's pixels; squared distances are exact integers.  Pass 1: distance to "not my id".
     unsigned int lmax1 = 0;
     for (int j = threadIdx.x; j < (use_list ? n_own : n_win); j += blockDim.x) {
         const int i = use_list ? own[j] : j;
         if (!use_list && lab[i] != id) continue;
         const int y = i / ww, x = i - y * ww;
-        unsigned int b1 = 0xFFFFFFFFu;
-        // exact minimum over all columns, visited outwards from x: once dx^2 alone reaches the best squared distance
-        // no farther column can improve it
-        const unsigned short *r1 = g1 + y * ww;
-        if (any_bg) {
-            const int kmax = x > ww - 1 - x ? x : ww - 1 - x;
-            for (int k = 0; k <= kmax; ++k) {
-                const unsigned int dx2 = static_cast<unsigned int>(k * k);
-                if (dx2 >= b1) break;
-                if (x - k >= 0) {
-                    const unsigned int g = r1[x - k];
-                    if (g != kInf16) { const unsigned int d = dx2 + g * g; b1 = d < b1 ? d : b1; }
-                }
-                if (k && x + k < ww) {
-                    const unsigned int g = r1[x + k];
-                    if (g != kInf16) { const unsigned int d = dx2 + g * g; b1 = d < b1 ? d : b1; }
-                }
-            }
-        } else {
-            // scipy's feature transform of an all-foreground array points at (-1, 0)
-            b1 = static_cast<unsigned int>((y + 1) * (y + 1) + x * x);
-        }
+        // all-foreground window: scipy's feature transform points at (-1, 0)
+        const unsigned int b1 = any_bg ? row_min(g1 + y * ww, x, c0a, c1a, 0xFFFFFFFFu) : static_cast<unsigned int>((y + 1) * (y + 1) + x * x);
         lmax1 = b1 > lmax1 ? b1 : lmax1;
         // park the exact squared distance in the output array (bit pattern); the same thread converts it below
         const size_t o = (static_cast<size_t>(crop) * H + s.wy0 + y) * W + s.wx0 + x;
@@ -249,29 +270,23 @@ __device__ void cell_edt(const uint16_t *__restrict__ masks, int H, int W, int c
     // Pass 2: distance to the other instances.  It only matters below den = min(max1 + 3, max2) (:321, larger values are
     // clipped to 1), so the outward search starts from the bound (floor(max1 + 3) + 1)^2: a pixel without a site inside it
     // has d2 >= max1 + 3, hence max2 >= max1 + 3, den = max1 + 3 and its value clips -- exact, and the search is short.
+    // For the same reason only the bounding box grown by `cap` is scanned; other instances farther away than that change
+    // nothing (every value clips, as if there were none).
     const unsigned int cap = static_cast<unsigned int>(floor(sqrt(static_cast<double>(s_max1)) + 3.0)) + 1u;
     const unsigned int cap2 = cap < 65535u ? cap * cap : 0xFFFFFFFFu;
+    const int capi = cap < 65535u ? static_cast<int>(cap) : 65535;
+    const int c0b = bx0 > capi ? bx0 - capi : 0, c1b = bx1 + capi < ww ? bx1 + capi : ww - 1;
+    const int r0b = by0 > capi ? by0 - capi : 0, r1b = by1 + capi < wh ? by1 + capi : wh - 1;
+    if (scan_columns(g2, true, c0b, c1b, r0b, r1b)) s_any_other = 1;
+    __syncthreads();
+    const bool any_other = s_any_other != 0;
     unsigned int lmax2 = 0;
     if (any_other) {
         for (int j = threadIdx.x; j < (use_list ? n_own : n_win); j += blockDim.x) {
             const int i = use_list ? own[j] : j;
             if (!use_list && lab[i] != id) continue;
             const int y = i / ww, x = i - y * ww;
-            unsigned int b2 = cap2;
-            const unsigned short *r2 = g2 + y * ww;
-            const int kmax = x > ww - 1 - x ? x : ww - 1 - x;
-            for (int k = 0; k <= kmax; ++k) {
-                const unsigned int dx2 = static_cast<unsigned int>(k * k);
-                if (dx2 >= b2) break;
-                if (x - k >= 0) {
-                    const unsigned int g = r2[x - k];
-                    if (g != kInf16) { const unsigned int d = dx2 + g * g; b2 = d < b2 ? d : b2; }
-                }
-                if (k && x + k < ww) {
-                    const unsigned int g = r2[x + k];
-                    if (g != kInf16) { const unsigned int d = dx2 + g * g; b2 = d < b2 ? d : b2; }
-                }
-            }
+            const unsigned int b2 = row_min(g2 + y * ww, x, c0b, c1b, cap2);
             lmax2 = b2 > lmax2 ? b2 : lmax2;        // a capped value (>= cap2) keeps max2 >= (max1 + 3)^2, which is all den needs
             const size_t o = (static_cast<size_t>(crop) * H + s.wy0 + y) * W + s.wx0 + x;
             nraw[o] = __longlong_as_double(static_cast<long long>(b2));
@@ -694,7 +709,51 @@ __device__ __forceinline__ void for_gap_pixels(const uint8_t *__restrict__ gap, 
             if (gap[i]) f(i);
     }
 }
+// 8-connected union of the gap pixels.  Fast path (W a multiple of 16: a thread's 16 bytes never straddle a row): the
+// thread works on RUNS -- pixels of a run link to the run's first pixel with one atomicMin each (no find chains), and a
+// run is united once with every run of the row above that touches columns [a-1, b+1] instead of up to three unions per
+// pixel.  The resulting partition is the same as that of the per-pixel path below.
 __global__ void gap_merge_kernel(const uint8_t *__restrict__ gap, long long n, int H, int W, int *L) {
+    if ((W & 15) == 0 && (reinterpret_cast<uintptr_t>(gap) & 15) == 0) {
+        const long long i0 = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) * 16;
+        if (i0 >= n) return;
+        const uint4 v = *reinterpret_cast<const uint4 *>(gap + i0);
+        if (!(v.x | v.y | v.z | v.w)) return;
+        auto bits4 = [](unsigned w) { return (w & 1u) | ((w >> 7) & 2u) | ((w >> 14) & 4u) | ((w >> 21) & 8u); };   // bytes are 0 / 1
+        auto bits16 = [&](const uint4 &q) { return bits4(q.x) | (bits4(q.y) << 4) | (bits4(q.z) << 8) | (bits4(q.w) << 12); };
+        const unsigned cur = bits16(v);
+        const int HW = H * W;
+        const int pix = static_cast<int>(i0 % HW);
+        const int y = pix / W, x0 = pix - y * W;
+        const int g0 = static_cast<int>(i0);
+        unsigned above = 0;                       // bit p + 1 <-> column x0 + p of the row above, p = -1 .. 16
+        if (y > 0) {
+            above = bits16(*reinterpret_cast<const uint4 *>(gap + i0 - W)) << 1;
+            if (x0 > 0 && gap[i0 - W - 1]) above |= 1u;
+            if (x0 + 16 < W && gap[i0 - W + 16]) above |= 1u << 17;
+        }
+        const bool left = x0 > 0 && gap[i0 - 1];
+        unsigned rest = cur;
+        while (rest) {
+            const int a = __ffs(rest) - 1;
+            const int len = __ffs(~(cur >> a)) - 1;                 // run [a, a + len)
+            const int ia = g0 + a;
+            for (int k = a + 1; k < a + len; ++k) {
+                const int old = atomicMin(&L[g0 + k], ia);
+                if (old != g0 + k && old != ia) uf_union(L, old, ia);   // a pixel below had linked it already
+            }
+            if (a == 0 && left) uf_union(L, ia, ia - 1);
+            unsigned am = above & (((1u << (len + 2)) - 1u) << a);   // columns a - 1 .. a + len of the row above
+            while (am) {
+                const int q = __ffs(am) - 1;
+                uf_union(L, ia, g0 - W + q - 1);
+                const int l2 = __ffs(~(above >> q)) - 1;            // skip the rest of that run
+                am &= ~(((1u << l2) - 1u) << q);
+            }
+            rest &= ~(((1u << len) - 1u) << a);
+        }
+        return;
+    }
     for_gap_pixels(gap, n, [&](long long gi) {
         const int HW = H * W;
         const int base = static_cast<int>(gi / HW) * HW;
