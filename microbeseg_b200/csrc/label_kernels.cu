@@ -56,12 +56,17 @@ __global__ void lab_init_stats_kernel(CellStats *cs, int total) {
 // Per-instance integer statistics.  All pixels of an instance hit the same ten addresses, so plain atomics
 // serialise; a warp (32 consecutive pixels of one row) first groups its lanes by instance id and reduces each
 // group with REDUX (__reduce_*_sync), then ONE lane per group issues the atomics.
+// A block of 32 x 8 threads walks kRowsPerBlock rows (a warp is a piece of one row): with one row group per block these
+// light kernels were bound by the block launch rate (80 k blocks per 200 crops), not by their work.
+constexpr int kRowsPerBlock = 64;
 __global__ void lab_accum_kernel(const uint16_t *__restrict__ masks, int H, int W, int ids, CellStats *cs) {
     const int crop = blockIdx.z;
-    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31;
+    const int y_end = min(H, static_cast<int>(blockIdx.y + 1) * kRowsPerBlock);
+  for (int y = blockIdx.y * kRowsPerBlock + threadIdx.y; y < y_end; y += blockDim.y) {      // warp-uniform trip count
     int id = 0;
-    if (x < W && y < H) id = masks[(static_cast<size_t>(crop) * H + y) * W + x];
+    if (x < W) id = masks[(static_cast<size_t>(crop) * H + y) * W + x];
     const bool valid = id != 0 && id < ids;
     unsigned remaining = __ballot_sync(0xffffffffu, valid);
     while (remaining) {
@@ -91,6 +96,7 @@ __global__ void lab_accum_kernel(const uint16_t *__restrict__ masks, int H, int 
         }
         remaining &= ~grp;
     }
+  }
 }
 
 // 4*sqrt(eigenvalue) of the inertia tensor [[mu02, -mu11], [-mu11, mu20]] / n  (skimage regionprops)
@@ -563,7 +569,9 @@ __global__ void lab_dilate_bits_kernel(const unsigned long long *__restrict__ in
 // gap = ~label_bin & (erode(dil) ^ label_bin) as BYTES for the component labelling (bottom_hat_closing :58-59)
 // ... and L[i] = i at the gap pixels: the union-find arrays are only ever touched where gap != 0 (gaps are ~1 % of the
 // pixels, so the labelling passes below read one byte per pixel instead of 4-byte ids).
-__global__ void lab_erode_gap_bits_kernel(const unsigned long long *__restrict__ dil, const unsigned long long *__restrict__ lbits,
+// lbits: in = closed-label bits of word t, out = the gap bits of word t (each thread reads and writes only its own word;
+// gap_stats_kernel uses the bit image to reject pixels without a gap in their 3x3 neighbourhood)
+__global__ void lab_erode_gap_bits_kernel(const unsigned long long *__restrict__ dil, unsigned long long *lbits,
                                           int H, int W, int WW, int n_crops, uint8_t *__restrict__ gap, int *__restrict__ L) {
     const long long t = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (t >= static_cast<long long>(n_crops) * H * WW) return;
@@ -591,6 +599,7 @@ __global__ void lab_erode_gap_bits_kernel(const unsigned long long *__restrict__
     {
         const int pix0 = static_cast<int>((crop * H + y) * W + 64 * w);
         unsigned long long rest = valid < 64 ? (g & ((1ull << valid) - 1)) : g;
+        lbits[t] = rest;
         while (rest) {
             const int b = __ffsll(static_cast<long long>(rest)) - 1;
             L[pix0 + b] = pix0 + b;
@@ -618,8 +627,12 @@ __global__ void lab_erode_gap_bits_kernel(const unsigned long long *__restrict__
 // eight pixels of a row per thread: three 16-byte row loads (+ the two edge pixels) instead of 72 two-byte loads, one 8-byte store
 __global__ void __launch_bounds__(256) lab_border_kernel(const uint16_t *__restrict__ masks, int H, int W, uint8_t *__restrict__ border) {
     const int crop = blockIdx.z;
-    const int x0 = (blockIdx.x * 32 + (threadIdx.x & 31)) * 8, y = blockIdx.y * 8 + (threadIdx.x >> 5);
-    if (x0 >= W || y >= H) return;
+    // groups of eight pixels numbered row-major over the crop: consecutive lanes take consecutive groups across row ends,
+    // so every lane has work whatever W is (W = 320: 40 groups per row)
+    const int ngx = (W + 7) >> 3;
+    const int t = blockIdx.x * 256 + threadIdx.x;
+    const int y = t / ngx, x0 = (t - y * ngx) * 8;
+    if (y >= H) return;
     const uint16_t *m = masks + static_cast<size_t>(crop) * H * W;
     uint8_t *out = border + (static_cast<size_t>(crop) * H + y) * W + x0;
     const bool vec = (W & 7) == 0;            // rows are 16-byte aligned and whole groups of eight
@@ -789,40 +802,84 @@ __global__ void gap_assign_kernel(const uint8_t *__restrict__ gap, const int *__
         if (L[i] != i) gid[i] = gid[L[i]];
     });
 }
-__global__ void gap_stats_kernel(const uint8_t *__restrict__ gap, const int *__restrict__ gid, const double *__restrict__ nraw, int H,
-                                 int W, int max_gaps, GapStats *gs) {
+__global__ void gap_stats_kernel(const uint8_t *__restrict__ gap, const int *__restrict__ gid, const double *__restrict__ nraw,
+                                 const unsigned long long *__restrict__ gbits, int WW, int H, int W, int max_gaps, GapStats *gs) {
     const int crop = blockIdx.z;
-    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
-    if (x >= W || y >= H) return;
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y_end = min(H, static_cast<int>(blockIdx.y + 1) * kRowsPerBlock);
+  for (int y = blockIdx.y * kRowsPerBlock + threadIdx.y; y < y_end; y += blockDim.y) {      // warp-uniform trip count
+    const bool inside = x < W;                // no early exit of single lanes: the warp aggregates below (a warp is a row piece)
+    // ~97 % of the pixels have no gap pixel in their 3x3 neighbourhood: they are rejected on the gap BIT image (three
+    // words that the whole warp shares) before any per-pixel load
+    const unsigned long long *rows = gbits + static_cast<size_t>(crop) * H * WW;
+    const int w = x >> 6, b = x & 63;
+    auto near3 = [&](int yy) -> unsigned {       // bits {x-1, x, x+1} of row yy (bits beyond W are zero)
+        const unsigned long long *r = rows + static_cast<size_t>(yy) * WW;
+        const unsigned long long c = r[w];
+        unsigned m = static_cast<unsigned>((c >> b) & 1ull) << 1;
+        m |= b > 0 ? static_cast<unsigned>((c >> (b - 1)) & 1ull) : (w > 0 ? static_cast<unsigned>(r[w - 1] >> 63) : 0u);
+        m |= (b < 63 ? static_cast<unsigned>((c >> (b + 1)) & 1ull) : (w + 1 < WW ? static_cast<unsigned>(r[w + 1] & 1ull) : 0u)) << 2;
+        return m;
+    };
+    unsigned mid = 0, any = 0;        // any: bit 3 * (dy + 1) + (dx + 1) <-> neighbour (dy, dx) is a gap pixel
+    if (inside) {
+        mid = near3(y);
+        any = mid << 3;
+        if (y > 0) any |= near3(y - 1);
+        if (y + 1 < H) any |= near3(y + 1) << 6;
+    }
+    if (!__any_sync(0xffffffffu, any != 0)) continue;
     const size_t base = static_cast<size_t>(crop) * H * W;
     const int *g = gid + base;
     const uint8_t *gp = gap + base;
     GapStats *S = gs + static_cast<size_t>(crop) * max_gaps;
-    const int me = gp[y * W + x] ? g[y * W + x] : -1;
-    if (me >= 0) {
-        atomicAdd(&S[me].cnt, 1ull);
-        atomicAdd(&S[me].sy, static_cast<unsigned long long>(y));
-        atomicAdd(&S[me].sx, static_cast<unsigned long long>(x));
-        atomicAdd(&S[me].syy, static_cast<unsigned long long>(y) * y);
-        atomicAdd(&S[me].sxx, static_cast<unsigned long long>(x) * x);
-        atomicAdd(&S[me].sxy, static_cast<unsigned long long>(x) * y);
-    }
-    // obj_boundary = dilate3x3(obj) ^ obj : this pixel belongs to the boundary of every *other* gap it touches
-    const double v = nraw[base + y * W + x];
-    if (v == 0.0) return;
-    int seen[8];
-    int ns = 0;
-    for (int dy = -1; dy <= 1; ++dy)
-        for (int dx = -1; dx <= 1; ++dx) {
-            if (!dy && !dx) continue;
-            const int yy = y + dy, xx = x + dx;
-            if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
-            const int o = gp[yy * W + xx] ? g[yy * W + xx] : -1;
-            if (o < 0 || o == me) continue;
-            bool dup = false;
-            for (int k = 0; k < ns; ++k) dup |= (seen[k] == o);
-            if (!dup) { seen[ns++] = o; atomicAdd(&S[o].bsum, v); }
+    const int me = (mid & 2u) ? g[y * W + x] : -1;
+    {
+        // all pixels of a gap hit the same six addresses: group the warp's lanes by gap id, reduce each group with REDUX,
+        // one lane per group issues the atomics (as lab_accum_kernel)
+        const int lane = threadIdx.x & 31;
+        unsigned remaining = __ballot_sync(0xffffffffu, me >= 0);
+        while (remaining) {
+            const int leader = __ffs(remaining) - 1;
+            const int cur = __shfl_sync(0xffffffffu, me, leader);
+            const bool mine = me == cur;
+            const unsigned grp = __ballot_sync(0xffffffffu, mine);
+            if (mine) {
+                const unsigned ux = static_cast<unsigned>(x), uy = static_cast<unsigned>(y);
+                const unsigned sx = __reduce_add_sync(grp, ux), sxx = __reduce_add_sync(grp, ux * ux);
+                if (lane == leader) {
+                    const unsigned long long c = __popc(grp);       // same row: y is common to the group
+                    atomicAdd(&S[cur].cnt, c);
+                    atomicAdd(&S[cur].sy, c * uy);
+                    atomicAdd(&S[cur].sx, static_cast<unsigned long long>(sx));
+                    atomicAdd(&S[cur].syy, c * uy * uy);
+                    atomicAdd(&S[cur].sxx, static_cast<unsigned long long>(sxx));
+                    atomicAdd(&S[cur].sxy, static_cast<unsigned long long>(sx) * uy);
+                }
+            }
+            remaining &= ~grp;
         }
+    }
+    if (!any) continue;
+    // obj_boundary = dilate3x3(obj) ^ obj : this pixel belongs to the boundary of every *other* gap it touches
+    const unsigned nb = any & ~(1u << 4);
+    if (!nb) continue;
+    const double v = nraw[base + y * W + x];
+    // the ids of the neighbouring gap pixels: independent (predicated) loads issued together -- the bit image says where
+    // they are, so there is no load -> branch -> load chain per neighbour
+    int o[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) o[k] = (nb >> k) & 1u ? g[(y + k / 3 - 1) * W + x + k % 3 - 1] : -1;
+    if (v == 0.0) continue;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+        if (o[k] < 0 || o[k] == me) continue;
+        bool dup = false;
+#pragma unroll
+        for (int j = 0; j < k; ++j) dup |= (o[j] == o[k]);
+        if (!dup) atomicAdd(&S[o[k]].bsum, v);
+    }
+  }
 }
 
 // rescale + clip (:355-358)
@@ -998,7 +1055,7 @@ extern "C" int mbs_labels_max_mal(const uint16_t *masks, int n_crops, int H, int
     CropInfo *info = reinterpret_cast<CropInfo *>(static_cast<char *>(workspace) +
                                                   r256(static_cast<size_t>(n_crops) * ids * sizeof(CellStats)));
     const int total = n_crops * ids;
-    dim3 b2(32, 8), g3(mbs::cdiv(W, 32), mbs::cdiv(H, 8), n_crops);
+    dim3 b2(32, 8), g3(mbs::cdiv(W, 32), mbs::cdiv(H, kRowsPerBlock), n_crops);
     MBS_CHECK_CUDA(cudaMemsetAsync(info, 0, n_crops * sizeof(CropInfo), stream));
     lab_init_stats_kernel<<<mbs::cdiv(total, 256), 256, 0, stream>>>(cs, total);
     MBS_CHECK_LAUNCH();
@@ -1036,7 +1093,7 @@ extern "C" int mbs_instance_stats(const uint16_t *masks, int n_frames, int H, in
     MBS_REQUIRE(static_cast<long long>(n_frames) * ids < (1ll << 31), "instance_stats: too many (frame, id) pairs");
     CellStats *cs = reinterpret_cast<CellStats *>(workspace);
     const int total = n_frames * ids;
-    dim3 b2(32, 8), g3(mbs::cdiv(W, 32), mbs::cdiv(H, 8), n_frames);
+    dim3 b2(32, 8), g3(mbs::cdiv(W, 32), mbs::cdiv(H, kRowsPerBlock), n_frames);
     lab_init_stats_kernel<<<mbs::cdiv(total, 256), 256, 0, stream>>>(cs, total);
     MBS_CHECK_LAUNCH();
     lab_accum_kernel<<<g3, b2, 0, stream>>>(masks, H, W, ids, cs);
@@ -1073,7 +1130,7 @@ extern "C" int mbs_distance_labels(const uint16_t *masks, int n_crops, int H, in
     int *big_list = reinterpret_cast<int *>(take((static_cast<size_t>(n_crops) * ids + 1) * sizeof(int)));
 
     const int total = n_crops * ids;
-    dim3 b2(32, 8), g3(mbs::cdiv(W, 32), mbs::cdiv(H, 8), n_crops);
+    dim3 b2(32, 8), g3(mbs::cdiv(W, 32), mbs::cdiv(H, kRowsPerBlock), n_crops);
     MBS_CHECK_CUDA(cudaMemsetAsync(info, 0, n_crops * sizeof(CropInfo), stream));
     MBS_CHECK_CUDA(cudaMemsetAsync(gs, 0, static_cast<size_t>(n_crops) * kMaxGaps * sizeof(GapStats), stream));
     MBS_CHECK_CUDA(cudaMemsetAsync(nraw, 0, px * 8, stream));
@@ -1130,7 +1187,7 @@ extern "C" int mbs_distance_labels(const uint16_t *masks, int n_crops, int H, in
         lab_close_cell_kernel<<<2 * 148, 256, smemc, stream>>>(masks, H, W, WW, ids, cs, info, lbits, smemc, big_list);
         MBS_CHECK_LAUNCH();
     }
-    lab_border_kernel<<<dim3(mbs::cdiv(W, 256), mbs::cdiv(H, 8), n_crops), 256, 0, stream>>>(masks, H, W, border);
+    lab_border_kernel<<<dim3(mbs::cdiv(mbs::cdiv(W, 8) * H, 256), 1, n_crops), 256, 0, stream>>>(masks, H, W, border);
     MBS_CHECK_LAUNCH();
     const int nwords = static_cast<int>((static_cast<long long>(n_crops) * H * WW + 255) / 256);
     lab_dilate_bits_kernel<<<nwords, 256, 0, stream>>>(lbits, H, W, WW, n_crops, dbits);
@@ -1146,7 +1203,7 @@ extern "C" int mbs_distance_labels(const uint16_t *masks, int n_crops, int H, in
     MBS_CHECK_LAUNCH();
     gap_assign_kernel<<<nb16, 256, 0, stream>>>(gap, L, static_cast<long long>(px), gid);
     MBS_CHECK_LAUNCH();
-    gap_stats_kernel<<<g3, b2, 0, stream>>>(gap, gid, nraw, H, W, kMaxGaps, gs);
+    gap_stats_kernel<<<g3, b2, 0, stream>>>(gap, gid, nraw, lbits, WW, H, W, kMaxGaps, gs);
     MBS_CHECK_LAUNCH();
     lab_compose_closing_kernel<<<dim3(mbs::cdiv(W, GT), mbs::cdiv(H, GT), n_crops), 256, 0, stream>>>(gap, gid, gs, border, nraw, H, W, kMaxGaps,
                                                                                                   neighbor_dist, 0.0);
