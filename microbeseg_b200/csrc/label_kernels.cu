@@ -42,7 +42,8 @@ struct CropInfo {
     int error;                 // bit 0: window too large for shared memory, bit 1: too many gaps
 };
 
-constexpr unsigned short kInf16 = 0xFFFF;
+// "no site in this column": 2^15, so that k^2 + g^2 stays below 2^32 without a test (crop sides are < 32768, checked)
+constexpr unsigned short kInf16 = 0x8000;
 
 __global__ void lab_init_stats_kernel(CellStats *cs, int total) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -241,14 +242,14 @@ __device__ void cell_edt(const uint16_t *__restrict__ masks, int H, int W, int c
         for (int k = 0; k <= kmax; ++k) {
             const unsigned int dx2 = static_cast<unsigned int>(k * k);
             if (dx2 >= b) break;
-            if (x - k >= c0) {
-                const unsigned int g = r[x - k];
-                if (g != kInf16) { const unsigned int d = dx2 + g * g; b = d < b ? d : b; }
-            }
-            if (k && x + k <= c1) {
-                const unsigned int g = r[x + k];
-                if (g != kInf16) { const unsigned int d = dx2 + g * g; b = d < b ? d : b; }
-            }
+            // branch-free step: clamped (always readable) loads, out-of-range sides masked afterwards; a column without a
+            // site holds kInf16, whose square exceeds every real squared distance (and the capped start value of pass 2)
+            const int xl = x - k, xr = x + k;
+            const unsigned int gl = r[xl >= c0 ? xl : c0], gr = r[xr <= c1 ? xr : c1];
+            const unsigned int dl = xl >= c0 ? dx2 + gl * gl : 0xFFFFFFFFu;
+            const unsigned int dr = xr <= c1 ? dx2 + gr * gr : 0xFFFFFFFFu;
+            const unsigned int dm = dl < dr ? dl : dr;
+            b = dm < b ? dm : b;
         }
         return b;
     };
@@ -1107,7 +1108,7 @@ extern "C" int mbs_distance_labels(const uint16_t *masks, int n_crops, int H, in
                                    int radius_hint, float *cell_dist, float *neighbor_dist, int32_t *max_mal_out, int32_t *error_out,
                                    void *workspace, size_t workspace_bytes, void *stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-    MBS_REQUIRE(n_crops > 0 && H > 0 && W > 0 && max_id >= 0 && max_id <= 65535, "distance_labels: bad arguments");
+    MBS_REQUIRE(n_crops > 0 && H > 0 && W > 0 && H < 32768 && W < 32768 && max_id >= 0 && max_id <= 65535, "distance_labels: bad arguments");
     const size_t px = static_cast<size_t>(n_crops) * H * W;
     MBS_REQUIRE(px < (1ull << 31), "distance_labels: batch too large (use fewer crops per call)");
     MBS_REQUIRE(workspace_bytes >= mbs_labels_workspace_bytes(n_crops, H, W, max_id), "distance_labels: workspace too small");
