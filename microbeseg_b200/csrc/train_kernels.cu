@@ -720,6 +720,32 @@ __global__ void zero_insert_kernel(const __nv_bfloat16 *__restrict__ src, int N,
     *reinterpret_cast<uint4 *>(dst + i) = v;
 }
 
+// eight elements (16 bytes) per thread and step, grid-stride (the two-element kernel below is the fallback for odd sizes /
+// unaligned views); the same float additions in the same order, so results are identical
+__global__ void __launch_bounds__(256)
+add3_vec8_kernel(const uint4 *__restrict__ a, const uint4 *__restrict__ b, const uint4 *__restrict__ c, long long n8,
+                 uint4 *__restrict__ out) {
+    auto add2 = [](unsigned x, unsigned y, unsigned z, bool has_c) {
+        const __nv_bfloat162 xv = *reinterpret_cast<const __nv_bfloat162 *>(&x), yv = *reinterpret_cast<const __nv_bfloat162 *>(&y);
+        float s0 = __bfloat162float(xv.x) + __bfloat162float(yv.x), s1 = __bfloat162float(xv.y) + __bfloat162float(yv.y);
+        if (has_c) {
+            const __nv_bfloat162 zv = *reinterpret_cast<const __nv_bfloat162 *>(&z);
+            s0 += __bfloat162float(zv.x);
+            s1 += __bfloat162float(zv.y);
+        }
+        const __nv_bfloat162 r = __floats2bfloat162_rn(s0, s1);
+        return *reinterpret_cast<const unsigned *>(&r);
+    };
+    const bool has_c = c != nullptr;
+    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n8;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const uint4 x = a[i], y = b[i];
+        const uint4 z = has_c ? c[i] : make_uint4(0, 0, 0, 0);
+        out[i] = make_uint4(add2(x.x, y.x, z.x, has_c), add2(x.y, y.y, z.y, has_c), add2(x.z, y.z, z.z, has_c),
+                            add2(x.w, y.w, z.w, has_c));
+    }
+}
+
 __global__ void add3_kernel(const __nv_bfloat16 *__restrict__ a, const __nv_bfloat16 *__restrict__ b,
                             const __nv_bfloat16 *__restrict__ c, long long n, __nv_bfloat16 *__restrict__ out) {
     const long long i = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) * 2;
@@ -1001,6 +1027,17 @@ extern "C" int mbs_zero_insert_up2(const void *src, int N, int H, int W, int C, 
 extern "C" int mbs_add3_bf16(const void *a, const void *b, const void *c, long long n, void *out, void *stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     MBS_REQUIRE(n > 0 && n % 2 == 0, "add3: bad size");
+    const uintptr_t al = reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(c) |
+                         reinterpret_cast<uintptr_t>(out);
+    if (n % 8 == 0 && (al & 15) == 0) {
+        const long long n8 = n / 8;
+        const long long want = (n8 + 255) / 256;
+        const int grid = static_cast<int>(want < 148 * 16 ? want : 148 * 16);
+        add3_vec8_kernel<<<grid, 256, 0, stream>>>(static_cast<const uint4 *>(a), static_cast<const uint4 *>(b),
+                                                   static_cast<const uint4 *>(c), n8, static_cast<uint4 *>(out));
+        MBS_CHECK_LAUNCH();
+        return 0;
+    }
     add3_kernel<<<static_cast<int>((n / 2 + 255) / 256), 256, 0, stream>>>(
         static_cast<const __nv_bfloat16 *>(a), static_cast<const __nv_bfloat16 *>(b), static_cast<const __nv_bfloat16 *>(c), n,
         static_cast<__nv_bfloat16 *>(out));
