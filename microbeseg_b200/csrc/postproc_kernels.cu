@@ -232,6 +232,7 @@ struct Stats {
     unsigned int pool_top;          // heap pool allocator of the per-component floods
     unsigned int tile_counter;      // sweep 0 of flood_kernel: next tile to visit (dynamic assignment: visit costs vary 3x)
     unsigned int tile_counter2;     // the same for the final phase (4096 tiles on 444 blocks: 9.2 -> 10 visits when dealt statically)
+    unsigned int dbg_maxclk[32];    // longest block-wide visit of each sweep (clock64 ticks)
 };
 
 // path compression + component areas + component / pixel counts in one pass
@@ -1481,6 +1482,7 @@ flood_kernel(const FloodParams p) {
             if (sweep >= 3) {
                 const long long tk4 = clock64();
                 ph[0] += tk1 - tk0; ph[1] += tk2 - tk1; ph[2] += tk3 - tk2; ph[3] += tk4 - tk3; ph[4] += 1;
+                if (threadIdx.x == 0 && sweep < 32) atomicMax(&p.st->dbg_maxclk[sweep], static_cast<unsigned int>(tk4 - tk0));
             }
     };
     stamp(0);

@@ -25,7 +25,8 @@ def timeit(b, c, out, reps=20):
 def flood_profile():
     """per-sweep instrumentation written by flood_kernel into the Stats block at the head of the workspace"""
     ws = max(pp._WS.values(), key=lambda t: t.numel())
-    raw = ws[:888].cpu().numpy()
+    raw = ws[:1040].cpu().numpy()
+    maxclk = raw[912:1040].view(np.uint32)
     ph = raw[848:888].view(np.uint64).astype(np.float64)
     rounds, maxr, items = (raw[464 + 128 * k:592 + 128 * k].view(np.uint32) for k in range(3))
     tiles = raw[44:172].view(np.uint32)
@@ -34,7 +35,7 @@ def flood_profile():
     out = []
     for k in range(min(sweeps, 33)):
         out.append((int(tiles[k]) if k < 32 else -1, round(float(t[k + 1] - t[k]) / 1e3, 1),
-                    f"rounds avg {rounds[k] / max(tiles[k], 1):.1f} max {maxr[k]}, items/tile {items[k] / max(tiles[k], 1):.0f}" if k < 32 else ""))
+                    f"rounds avg {rounds[k] / max(tiles[k], 1):.1f} max {maxr[k]}, items/tile {items[k] / max(tiles[k], 1):.0f}, longest visit {maxclk[k] / 1e3:.1f} kclk" if k < 32 else ""))
     fin = round(float(t[35] - t[min(sweeps, 34)]) / 1e3, 1)
     phs = ""
     if ph[4] > 0:
