@@ -273,6 +273,12 @@ int mbs_labels_max_mal(const uint16_t *masks, int n_crops, int H, int W, int max
 int mbs_distance_labels(const uint16_t *masks, int n_crops, int H, int W, int max_id, int search_radius,
                         int radius_hint, float *cell_dist, float *neighbor_dist, int32_t *max_mal_out,
                         int32_t *error_out, void *workspace, size_t workspace_bytes, void *stream);
+/* The same with cell_clip > 0: cell_dist = clip(EDT, 0, cell_clip) / cell_clip instead of the per-instance normalisation --
+ * cell_distance_label(apply_clipping=True, clip_val) of the 'cell_dist_clipped' label type (train_data_representations.py:246-256).
+ * cell_clip <= 0 is mbs_distance_labels. */
+int mbs_distance_labels_ex(const uint16_t *masks, int n_crops, int H, int W, int max_id, int search_radius,
+                           int radius_hint, float cell_clip, float *cell_dist, float *neighbor_dist, int32_t *max_mal_out,
+                           int32_t *error_out, void *workspace, size_t workspace_bytes, void *stream);
 
 /*
  * Threshold sweep of the evaluation (src/evaluation/eval.py:128-129, 395-412: one prediction post-processed for every

@@ -96,6 +96,8 @@ _SIGS = {
     "mbs_labels_max_mal": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
     "mbs_distance_labels": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
                                     c_void_p, c_void_p, c_size_t, c_void_p]),
+    "mbs_distance_labels_ex": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p,
+                                       c_void_p, c_void_p, c_size_t, c_void_p]),
     "mbs_bn_train_fwd": (c_int, [c_void_p, ctypes.c_longlong, c_int, c_void_p, c_void_p, c_float, c_void_p, c_void_p,
                                  c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     "mbs_pack_conv3x3_dgrad": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p]),

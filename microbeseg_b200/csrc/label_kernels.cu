@@ -150,7 +150,7 @@ __global__ void lab_window_kernel(CellStats *cs, int ids, int total, int H, int 
 // `sm`: 4 * wh * ww unsigned shorts of scratch -- shared memory (lab_cell_kernel) or, for windows that do not fit, a
 // per-crop global buffer (lab_cell_big_kernel); every exit is block-uniform, so the function can be called in a loop.
 __device__ void cell_edt(const uint16_t *__restrict__ masks, int H, int W, int crop, int id, const CellStats &s, int wh, int ww,
-                         unsigned short *sm, float *__restrict__ cell_dist, double *__restrict__ nraw) {
+                         unsigned short *sm, float *__restrict__ cell_dist, double *__restrict__ nraw, float cell_clip) {
     unsigned short *lab = sm;                 // [wh][ww] labels
     unsigned short *g1 = sm + wh * ww;        // vertical distance to the nearest pixel with label != id (own pixels)
     unsigned short *g2 = g1 + wh * ww;        // vertical distance to the nearest pixel of ANOTHER instance
@@ -310,7 +310,9 @@ __device__ void cell_edt(const uint16_t *__restrict__ masks, int H, int W, int c
         const int y = i / ww, x = i - y * ww;
         const size_t o = (static_cast<size_t>(crop) * H + s.wy0 + y) * W + s.wx0 + x;
         const double d1 = sqrt(static_cast<double>(__float_as_uint(cell_dist[o])));
-        cell_dist[o] = static_cast<float>(d1 / max1);                    // :292, cast :361
+        // :292, cast :361 -- or cell_distance_label(apply_clipping=True) (:246-256): the raw EDT clipped to clip_val, / clip_val
+        cell_dist[o] = cell_clip > 0.0f ? static_cast<float>(fmin(d1, static_cast<double>(cell_clip)) / static_cast<double>(cell_clip))
+                                        : static_cast<float>(d1 / max1);
         double v = 0.0;
         if (any_other) {
             const double d2 = sqrt(static_cast<double>(static_cast<unsigned int>(__double_as_longlong(nraw[o]))));
@@ -324,7 +326,7 @@ __device__ void cell_edt(const uint16_t *__restrict__ masks, int H, int W, int c
 
 __global__ void __launch_bounds__(256)
 lab_cell_kernel(const uint16_t *__restrict__ masks, int H, int W, int ids, const CellStats *cs, CropInfo *info,
-                float *__restrict__ cell_dist, double *__restrict__ nraw, int smem_cap_elems) {
+                float *__restrict__ cell_dist, double *__restrict__ nraw, int smem_cap_elems, float cell_clip) {
     const int crop = blockIdx.y;
     const int id = blockIdx.x + 1;
     if (id >= ids) return;
@@ -334,7 +336,7 @@ lab_cell_kernel(const uint16_t *__restrict__ masks, int H, int W, int ids, const
     if (wh <= 0 || ww <= 0) return;           // empty crop: np.max(...) of an empty EDT -> skipped
     if (wh * ww > smem_cap_elems) return;     // window larger than shared memory: lab_cell_big_kernel takes it
     extern __shared__ unsigned short sm[];
-    cell_edt(masks, H, W, crop, id, s, wh, ww, sm, cell_dist, nraw);
+    cell_edt(masks, H, W, crop, id, s, wh, ww, sm, cell_dist, nraw, cell_clip);
 }
 
 // Instances whose search window exceeds shared memory (max_mal >~ 130 px): one CTA per crop walks them one after the
@@ -342,7 +344,7 @@ lab_cell_kernel(const uint16_t *__restrict__ masks, int H, int W, int ids, const
 // reference has no size limit (train_data_representations.py:280-330).
 __global__ void __launch_bounds__(256)
 lab_cell_big_kernel(const uint16_t *__restrict__ masks, int H, int W, int ids, const CellStats *cs, unsigned short *scratch,
-                    size_t scratch_stride, float *__restrict__ cell_dist, double *__restrict__ nraw, int smem_cap_elems) {
+                    size_t scratch_stride, float *__restrict__ cell_dist, double *__restrict__ nraw, int smem_cap_elems, float cell_clip) {
     const int crop = blockIdx.x;
     unsigned short *sm = scratch + static_cast<size_t>(crop) * scratch_stride;
     // the usual case is "none": all threads look for oversized windows in parallel and the CTA leaves at once
@@ -366,7 +368,7 @@ lab_cell_big_kernel(const uint16_t *__restrict__ masks, int H, int W, int ids, c
             for (int k = 0; k < n; ++k) {
                 const int id = s_list[k];
                 const CellStats s = cs[static_cast<size_t>(crop) * ids + id];
-                cell_edt(masks, H, W, crop, id, s, s.wy1 - s.wy0, s.wx1 - s.wx0, sm, cell_dist, nraw);
+                cell_edt(masks, H, W, crop, id, s, s.wy1 - s.wy0, s.wx1 - s.wx0, sm, cell_dist, nraw, cell_clip);
             }
         } else {                                              // more than 256 oversized instances in the chunk: plain walk
             for (int id = id0; id < ids && id < id0 + 256 * 64; ++id) {
@@ -374,7 +376,7 @@ lab_cell_big_kernel(const uint16_t *__restrict__ masks, int H, int W, int ids, c
                 if (s.cnt == 0) continue;
                 const int wh = s.wy1 - s.wy0, ww = s.wx1 - s.wx0;
                 if (wh <= 0 || ww <= 0 || wh * ww <= smem_cap_elems) continue;
-                cell_edt(masks, H, W, crop, id, s, wh, ww, sm, cell_dist, nraw);
+                cell_edt(masks, H, W, crop, id, s, wh, ww, sm, cell_dist, nraw, cell_clip);
             }
         }
         __syncthreads();
@@ -1107,6 +1109,13 @@ extern "C" int mbs_instance_stats(const uint16_t *masks, int n_frames, int H, in
 extern "C" int mbs_distance_labels(const uint16_t *masks, int n_crops, int H, int W, int max_id, int search_radius,
                                    int radius_hint, float *cell_dist, float *neighbor_dist, int32_t *max_mal_out, int32_t *error_out,
                                    void *workspace, size_t workspace_bytes, void *stream_) {
+    return mbs_distance_labels_ex(masks, n_crops, H, W, max_id, search_radius, radius_hint, 0.0f, cell_dist, neighbor_dist, max_mal_out,
+                                  error_out, workspace, workspace_bytes, stream_);
+}
+
+extern "C" int mbs_distance_labels_ex(const uint16_t *masks, int n_crops, int H, int W, int max_id, int search_radius,
+                                      int radius_hint, float cell_clip, float *cell_dist, float *neighbor_dist, int32_t *max_mal_out,
+                                      int32_t *error_out, void *workspace, size_t workspace_bytes, void *stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     MBS_REQUIRE(n_crops > 0 && H > 0 && W > 0 && H < 32768 && W < 32768 && max_id >= 0 && max_id <= 65535, "distance_labels: bad arguments");
     const size_t px = static_cast<size_t>(n_crops) * H * W;
@@ -1174,11 +1183,11 @@ extern "C" int mbs_distance_labels(const uint16_t *masks, int n_crops, int H, in
             cell_threads = e ? atoi(e) : 128;
             if (cell_threads < 32 || cell_threads > 256 || cell_threads % 32) cell_threads = 128;   // whole warps (full-mask ballots)
         }
-        lab_cell_kernel<<<gc, cell_threads, smem, stream>>>(masks, H, W, ids, cs, info, cell_dist, nraw, smem / 8);
+        lab_cell_kernel<<<gc, cell_threads, smem, stream>>>(masks, H, W, ids, cs, info, cell_dist, nraw, smem / 8, cell_clip);
         MBS_CHECK_LAUNCH();
         if (full > smem)         // windows larger than shared memory are possible: the global-memory walk picks them up
             lab_cell_big_kernel<<<n_crops, 256, 0, stream>>>(masks, H, W, ids, cs, reinterpret_cast<unsigned short *>(scaled),
-                                                             static_cast<size_t>(H) * W * 4, cell_dist, nraw, smem / 8);
+                                                             static_cast<size_t>(H) * W * 4, cell_dist, nraw, smem / 8, cell_clip);
         MBS_CHECK_LAUNCH();
         long long wantc = 2ll * (static_cast<long long>(H) + 6) * (W + 6);
         int smemc = wantc > smem_opt ? smem_opt : static_cast<int>(wantc);

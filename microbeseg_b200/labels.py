@@ -40,7 +40,7 @@ def _check_err(err):
                            f"(bit0: an instance wider than 58 px whose bounding box (+6) does not fit the closing kernel's shared memory, bit1: > 4096 gaps): {e[e != 0][:8]}")
 
 
-def _run(masks_dev, max_id, search_radius, radius_hint, err=None):
+def _run(masks_dev, max_id, search_radius, radius_hint, err=None, cell_clip=0.0):
     """``err``: int32 [n] device tensor that collects the per-crop limit flags (checked later by the caller, no
     synchronisation here); None = check immediately."""
     L = nat.lib()
@@ -54,9 +54,9 @@ def _run(masks_dev, max_id, search_radius, radius_hint, err=None):
         err = torch.zeros(n, dtype=torch.int32, device=device)
     ws = torch.empty(L.mbs_labels_workspace_bytes(n, H, W, max_id), dtype=torch.uint8, device=device)
     with torch.cuda.device(device):
-        nat.check(L.mbs_distance_labels(masks_dev.data_ptr(), n, H, W, max_id, int(search_radius), int(radius_hint),
-                                        cell.data_ptr(), neigh.data_ptr(), mal.data_ptr(), err.data_ptr(),
-                                        ws.data_ptr(), ws.numel(), nat.stream_ptr()), "distance_labels")
+        nat.check(L.mbs_distance_labels_ex(masks_dev.data_ptr(), n, H, W, max_id, int(search_radius), int(radius_hint),
+                                           float(cell_clip), cell.data_ptr(), neigh.data_ptr(), mal.data_ptr(), err.data_ptr(),
+                                           ws.data_ptr(), ws.numel(), nat.stream_ptr()), "distance_labels")
     if not deferred:
         _check_err(err)
     return cell, neigh, mal
@@ -115,9 +115,14 @@ def get_label(mask, label_type, max_mal):
         # cell_distance_label(apply_clipping=False) (:220-258) is the cell half of distance_label: same windows, same
         # normalised EDTs, same `+=` (cells whose EDT is all zero add zeros there and are skipped here)
         return distance_label(mask, search_radius=int(np.ceil(0.75 * max_mal)))[0]
-    if label_type in ('adapted_border', 'j4', 'cell_dist_clipped'):
+    if label_type == 'cell_dist_clipped':
+        # cell_distance_label(apply_clipping=True) (:246-256): the raw per-instance EDTs, clipped to clip_val = 5 and scaled
+        dev, max_id = _masks_to_device(mask, _device())
+        r = int(np.ceil(0.75 * max_mal))
+        return _run(dev, max_id, r, r, cell_clip=5.0)[0][0].cpu().numpy()
+    if label_type in ('adapted_border', 'j4'):
         raise NotImplementedError(f"label type {label_type!r} is not built on the CUDA path "
-                                  "('distance', 'cell_dist', 'boundary', 'border' are)")
+                                  "('distance', 'cell_dist', 'cell_dist_clipped', 'boundary', 'border' are)")
     raise Exception('Label type not known')
 
 

@@ -105,16 +105,19 @@ def boundary_label(label):
     return np.maximum(label_bin, 2 * boundary).astype(np.uint8)
 
 
-def cell_distance_label(label, search_radius):
-    """train_data_representations.py:220-258 with apply_clipping=False"""
+def cell_distance_label(label, search_radius, apply_clipping=False, clip_val=5):
+    """train_data_representations.py:220-258"""
     label_dist = np.zeros(label.shape, np.float64)
     for prop in regionprops(label):
         nucleus = label == prop.label
         ys, xs = _window(prop.centroid, search_radius, label.shape)
         d = distance_transform_edt(nucleus[ys, xs])
-        if d.max() > 0:
+        if d.max() > 0 and not apply_clipping:
             d = d / d.max()
         label_dist[ys, xs] += d
+    if apply_clipping:
+        label_dist = np.clip(label_dist, 0, clip_val)      # :252-256
+        label_dist = label_dist / clip_val
     return label_dist.astype(np.float32)
 
 
@@ -216,6 +219,8 @@ def get_label(mask, label_type, max_mal):
         return border_label(mask)
     if label_type == 'cell_dist':
         return cell_distance_label(mask, search_radius=int(np.ceil(0.75 * max_mal)))
+    if label_type == 'cell_dist_clipped':
+        return cell_distance_label(mask, search_radius=int(np.ceil(0.75 * max_mal)), apply_clipping=True)
     if label_type != 'distance':
         raise Exception('Label type not known')
     return distance_label(mask, search_radius=int(np.ceil(0.75 * max_mal)))

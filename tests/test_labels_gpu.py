@@ -136,8 +136,9 @@ def test_boundary_border_and_cell_dist_label_types():
             got, want = lab.get_label(m, lt, 0), ol.get_label(m, lt, 0)
             assert got.dtype == np.uint8 and got.shape == m.shape and np.array_equal(got, want), lt
         mal = ol.max_major_axis_length(m) if n else 1
-        got, want = lab.get_label(m, "cell_dist", mal), ol.get_label(m, "cell_dist", mal)
-        assert got.dtype == np.float32 and np.array_equal(got, want)
+        for lt in ("cell_dist", "cell_dist_clipped"):      # per-instance normalised EDT / EDT clipped to 5 px and scaled
+            got, want = lab.get_label(m, lt, mal), ol.get_label(m, lt, mal)
+            assert got.dtype == np.float32 and np.array_equal(got, want), lt
     with pytest.raises(NotImplementedError):
         lab.get_label(m, "j4", 10)
     with pytest.raises(Exception):
