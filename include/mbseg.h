@@ -259,6 +259,11 @@ size_t mbs_labels_workspace_bytes(int n_crops, int H, int W, int max_id);
 /* label types 'boundary' (mode 0, train_data_representations.py:75-99) and 'border' (mode 1, :102-126) of the
  * baseline boundary method: uint8 [n_crops][H][W], 0 background / 1 nucleus / 2 boundary resp. touching border */
 int mbs_boundary_border_labels(const uint16_t *masks, int n_crops, int H, int W, int mode, uint8_t *out, void *stream);
+/* j4_label (train_data_representations.py:158-190; 0 background, 1 cell, 2 touching, 3 gap): bottom hat of the binary mask with
+ * disk(se_radius) (scipy binary_closing, border_value 0) and the "more than one instance in the (2k+1)^2 window" test of
+ * compute_neighbor_instances (:193-217).  tmp: n_crops*H*W bytes of scratch. */
+int mbs_j4_labels(const uint16_t *masks, int n_crops, int H, int W, int k_neighbors, int se_radius, uint8_t *out, uint8_t *tmp,
+                  void *stream);
 /* masks: uint16 [n_crops][H][W] instance ids (0 = background, ids <= max_id).
  * max_mal_out: int32 [n_crops] = int(ceil(max regionprops.major_axis_length)) per crop. */
 int mbs_labels_max_mal(const uint16_t *masks, int n_crops, int H, int W, int max_id, int32_t *max_mal_out,

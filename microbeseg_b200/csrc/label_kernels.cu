@@ -1026,6 +1026,79 @@ __global__ void simple_label_kernel(const uint16_t *__restrict__ masks, int H, i
 }
 }  // namespace
 
+namespace {
+// j4_label (train_data_representations.py:158-190): 0 background, 1 cell, 2 touching, 3 gap.
+// pass 1: binary_dilation(label > 0, disk(r)) (border_value = 0: outside the image is empty)
+__global__ void j4_dilate_kernel(const uint16_t *__restrict__ masks, int H, int W, int r, uint8_t *__restrict__ dil) {
+    const int crop = blockIdx.z;
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= W || y >= H) return;
+    const uint16_t *m = masks + static_cast<size_t>(crop) * H * W;
+    bool any = false;
+    for (int dy = -r; dy <= r && !any; ++dy) {
+        const int yy = y + dy;
+        if (yy < 0 || yy >= H) continue;
+        for (int dx = -r; dx <= r; ++dx) {
+            if (dx * dx + dy * dy > r * r) continue;          // skimage.morphology.disk
+            const int xx = x + dx;
+            if (xx >= 0 && xx < W && m[yy * W + xx]) { any = true; break; }
+        }
+    }
+    dil[(static_cast<size_t>(crop) * H + y) * W + x] = any ? 1 : 0;
+}
+// pass 2: binary_erosion of the dilation (border_value = 0: a structuring-element pixel outside the image erodes, scipy's
+// binary_closing passes the same border value to both steps) -> bottom hat at background pixels; number of distinct
+// instances in the (2k+1)^2 window (zero padded) > 1 -> touching
+__global__ void j4_compose_kernel(const uint16_t *__restrict__ masks, const uint8_t *__restrict__ dil, int H, int W, int r, int k,
+                                  uint8_t *__restrict__ out) {
+    const int crop = blockIdx.z;
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= W || y >= H) return;
+    const uint16_t *m = masks + static_cast<size_t>(crop) * H * W;
+    const uint8_t *d = dil + static_cast<size_t>(crop) * H * W;
+    const int l = m[y * W + x];
+    uint8_t v;
+    if (l) {
+        bool touching = false;                                // a second positive id in the window (it always holds l itself)
+        for (int dy = -k; dy <= k && !touching; ++dy) {
+            const int yy = y + dy;
+            if (yy < 0 || yy >= H) continue;
+            for (int dx = -k; dx <= k; ++dx) {
+                const int xx = x + dx;
+                if (xx < 0 || xx >= W) continue;
+                const int o = m[yy * W + xx];
+                if (o && o != l) { touching = true; break; }
+            }
+        }
+        v = touching ? 2 : 1;
+    } else {
+        bool closed = true;
+        for (int dy = -r; dy <= r && closed; ++dy)
+            for (int dx = -r; dx <= r; ++dx) {
+                if (dx * dx + dy * dy > r * r) continue;
+                const int yy = y + dy, xx = x + dx;
+                if (yy < 0 || yy >= H || xx < 0 || xx >= W || !d[yy * W + xx]) { closed = false; break; }
+            }
+        v = closed ? 3 : 0;
+    }
+    out[(static_cast<size_t>(crop) * H + y) * W + x] = v;
+}
+}  // namespace
+
+extern "C" int mbs_j4_labels(const uint16_t *masks, int n_crops, int H, int W, int k_neighbors, int se_radius, uint8_t *out,
+                             uint8_t *tmp, void *stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    MBS_REQUIRE(masks && out && tmp && n_crops > 0 && n_crops <= 65535 && H > 0 && W > 0 && k_neighbors >= 0 && k_neighbors <= 16 &&
+                    se_radius >= 0 && se_radius <= 16,
+                "j4_labels: bad arguments");
+    dim3 block(32, 8), grid((W + 31) / 32, (H + 7) / 8, n_crops);
+    j4_dilate_kernel<<<grid, block, 0, stream>>>(masks, H, W, se_radius, tmp);
+    MBS_CHECK_LAUNCH();
+    j4_compose_kernel<<<grid, block, 0, stream>>>(masks, tmp, H, W, se_radius, k_neighbors, out);
+    MBS_CHECK_LAUNCH();
+    return 0;
+}
+
 extern "C" int mbs_boundary_border_labels(const uint16_t *masks, int n_crops, int H, int W, int mode, uint8_t *out,
                                           void *stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);

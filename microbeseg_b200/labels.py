@@ -103,6 +103,20 @@ def border_label(label):
     return _simple_label(label, 1)
 
 
+def j4_label(label, k_neighbors=2, se_radius=4):
+    """Pena / J4 label image (train_data_representations.py:158-190): uint8, 0 background, 1 cell, 2 touching, 3 gap."""
+    L = nat.lib()
+    dev, _ = _masks_to_device(label, _device())
+    n, H, W = dev.shape
+    out = torch.empty((n, H, W), dtype=torch.uint8, device=dev.device)
+    tmp = torch.empty((n, H, W), dtype=torch.uint8, device=dev.device)
+    with torch.cuda.device(dev.device):
+        nat.check(L.mbs_j4_labels(dev.data_ptr(), n, H, W, int(k_neighbors), int(se_radius), out.data_ptr(), tmp.data_ptr(),
+                                  nat.stream_ptr()), "j4_labels")
+    res = out.cpu().numpy()
+    return res[0] if np.asarray(label).ndim == 2 else res
+
+
 def get_label(mask, label_type, max_mal):
     """Calculate training data representation / label (train_data_representations.py:11-37)."""
     if label_type == 'distance':
@@ -120,9 +134,11 @@ def get_label(mask, label_type, max_mal):
         dev, max_id = _masks_to_device(mask, _device())
         r = int(np.ceil(0.75 * max_mal))
         return _run(dev, max_id, r, r, cell_clip=5.0)[0][0].cpu().numpy()
-    if label_type in ('adapted_border', 'j4'):
-        raise NotImplementedError(f"label type {label_type!r} is not built on the CUDA path "
-                                  "('distance', 'cell_dist', 'cell_dist_clipped', 'boundary', 'border' are)")
+    if label_type == 'j4':
+        return j4_label(mask)
+    if label_type == 'adapted_border':
+        raise NotImplementedError("label type 'adapted_border' (cv2.Canny) is not built on the CUDA path "
+                                  "('distance', 'cell_dist', 'cell_dist_clipped', 'boundary', 'border', 'j4' are)")
     raise Exception('Label type not known')
 
 

@@ -133,6 +133,29 @@ def border_label(label):
     return np.maximum(label_bin, 2 * border).astype(np.uint8)
 
 
+def j4_label(label, k_neighbors=2, se_radius=4):
+    """train_data_representations.py:158-190 with compute_neighbor_instances (:193-217): scipy's binary_closing (the real
+    dependency) + the window count of distinct positive ids on the zero-padded mask"""
+    label_bin = label > 0
+    label_bottom_hat = ndimage.binary_closing(label_bin, disk(se_radius)) ^ label_bin
+    k = k_neighbors
+    padded = np.pad(label, pad_width=k, constant_values=0)
+    n_neighbors = np.zeros(label.shape, np.int64)
+    for y in range(label.shape[0]):
+        for x in range(label.shape[1]):
+            crop = padded[y:y + 2 * k + 1, x:x + 2 * k + 1]
+            n_neighbors[y, x] = len(set(crop[crop > 0].tolist()))
+    label_bg = (~label_bin) & (~label_bottom_hat)
+    label_gap = (~label_bin) & label_bottom_hat
+    label_touching = label_bin & (n_neighbors > 1)
+    label_cell = ~(label_bg | label_gap | label_touching)
+    j4 = np.maximum(label_bg, 2 * label_cell)
+    j4 = np.maximum(j4, 3 * label_touching)
+    j4 = np.maximum(j4, 4 * label_gap)
+    j4 -= 1
+    return j4.astype(np.uint8)
+
+
 def bottom_hat_closing(label):
     """train_data_representations.py:40-72 -> (gap labels int, gap map float32)"""
     label_bin = np.zeros_like(label, dtype=bool)
@@ -221,6 +244,8 @@ def get_label(mask, label_type, max_mal):
         return cell_distance_label(mask, search_radius=int(np.ceil(0.75 * max_mal)))
     if label_type == 'cell_dist_clipped':
         return cell_distance_label(mask, search_radius=int(np.ceil(0.75 * max_mal)), apply_clipping=True)
+    if label_type == 'j4':
+        return j4_label(mask)
     if label_type != 'distance':
         raise Exception('Label type not known')
     return distance_label(mask, search_radius=int(np.ceil(0.75 * max_mal)))

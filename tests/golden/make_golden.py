@@ -5,6 +5,7 @@
   python tests/golden/make_golden.py labels       # oracle/labels.py on seeded synthetic instance masks
   python tests/golden/make_golden.py ranger       # the REAL reference Ranger optimizer (/root/reference) on CPU
   python tests/golden/make_golden.py losses       # the REAL reference ce_dice / CrossEntropyLoss (/root/reference) on CPU
+  python tests/golden/make_golden.py simple_labels  # the REAL reference boundary_label / border_label / j4_label on CPU
 
 The post-processing goldens are produced by the oracle restatement (scikit-image cannot run in
 this image -> "parity unpinned" for the skimage pieces, see oracle/postproc.py); the network
@@ -80,6 +81,46 @@ def make_labels():
         print("labels", H, W, seed, "max_mal", mal, "cells", int(m.max()))
 
 
+def _import_reference_label_module():
+    """The reference's own train_data_representations.py, imported by path.  scikit-image and cv2 are not installed here: the
+    module-level imports are satisfied with stubs, of which only ``skimage.morphology.disk`` is ever CALLED by the functions
+    used below (boundary_label, border_label, j4_label: scipy + numpy otherwise) -- it is the published one-line definition
+    ``x^2 + y^2 <= r^2`` on the (2r+1)^2 grid.  regionprops / label / cv2 stay unusable stubs (None)."""
+    import importlib.util
+    import types
+    from oracle import labels as ol
+    sk, skm, skme, cv2 = (types.ModuleType(n) for n in ("skimage", "skimage.morphology", "skimage.measure", "cv2"))
+    skm.disk = ol.disk
+    sk.morphology, sk.measure = skm, skme
+    skme.regionprops = skme.label = None
+    saved = {k: sys.modules.get(k) for k in ("skimage", "skimage.morphology", "skimage.measure", "cv2")}
+    sys.modules.update({"skimage": sk, "skimage.morphology": skm, "skimage.measure": skme, "cv2": cv2})
+    try:
+        spec = importlib.util.spec_from_file_location("reference_tdr", "/root/reference/src/training/train_data_representations.py")
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+    return mod
+
+
+def make_simple_labels():
+    """boundary / border / j4 label images from the reference's OWN functions (train_data_representations.py:75-190)"""
+    from microbeseg_b200 import synthetic as sy
+    mod = _import_reference_label_module()
+    for H, W, n, seed in [(72, 96, 18, 41), (64, 64, 30, 42)]:
+        m = sy.synth_instance_mask(H, W, n, seed, (7.0, 12.0), (5.0, 9.0)).astype(np.uint16)
+        m[0:5, 0:6] = 900                  # touches the image corner
+        m[0:5, 6:11] = 901                 # and a neighbour
+        out = {"mask": m, "boundary": mod.boundary_label(m), "border": mod.border_label(m), "j4": mod.j4_label(m)}
+        np.savez_compressed(os.path.join(HERE, f"simple_labels_{H}x{W}_s{seed}.npz"), **out)
+        print("simple labels", H, W, seed, {k: np.bincount(v.ravel()).tolist() for k, v in out.items() if k != "mask"})
+
+
 RANGER_SHAPES = [(8, 4, 3, 3), (8,), (6, 8, 2, 2), (5, 7), (3,), (2, 1100)]
 RANGER_CASES = {"default": dict(lr=0.05), "wd_convonly": dict(lr=0.02, weight_decay=0.01, gc_conv_only=True, k=4),
                 "nogc": dict(lr=0.05, use_gc=False, betas=(0.9, 0.99))}
@@ -150,7 +191,9 @@ def make_losses():
 
 
 if __name__ == "__main__":
-    what = sys.argv[1:] or ["postproc", "net", "labels", "ranger", "losses"]
+    what = sys.argv[1:] or ["postproc", "net", "labels", "ranger", "losses", "simple_labels"]
+    if "simple_labels" in what:
+        make_simple_labels()
     if "losses" in what:
         make_losses()
     if "ranger" in what:

@@ -3,6 +3,8 @@
 cell_dist involves only integer squared distances, IEEE sqrt and division -> bit exact.
 neighbor_dist additionally goes through exp() (numpy's and CUDA's float64 exp may differ in the last
 bit) -> after the float32 cast at most 1 float32 ulp (tolerance 1.2e-7 absolute on [0,1] maps)."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -132,7 +134,7 @@ def test_boundary_border_and_cell_dist_label_types():
         if n:
             m[0:5, 0:6] = 900            # touches the image corner
             m[0:5, 6:11] = 901           # and a neighbour
-        for lt in ("boundary", "border"):
+        for lt in ("boundary", "border", "j4"):
             got, want = lab.get_label(m, lt, 0), ol.get_label(m, lt, 0)
             assert got.dtype == np.uint8 and got.shape == m.shape and np.array_equal(got, want), lt
         mal = ol.max_major_axis_length(m) if n else 1
@@ -140,9 +142,22 @@ def test_boundary_border_and_cell_dist_label_types():
             got, want = lab.get_label(m, lt, mal), ol.get_label(m, lt, mal)
             assert got.dtype == np.float32 and np.array_equal(got, want), lt
     with pytest.raises(NotImplementedError):
-        lab.get_label(m, "j4", 10)
+        lab.get_label(m, "adapted_border", 10)
     with pytest.raises(Exception):
         lab.get_label(m, "nonsense", 10)
+
+
+def test_simple_label_types_against_the_reference_fixtures():
+    """boundary / border / j4 through the CUDA path vs fixtures produced by the reference's own functions
+    (tests/golden/simple_labels_*.npz, see make_golden.py simple_labels): bit-exact"""
+    import glob
+    from microbeseg_b200 import labels as lab
+    files = sorted(glob.glob(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "simple_labels_*.npz")))
+    assert len(files) >= 2
+    for f in files:
+        g = np.load(f)
+        for lt in ("boundary", "border", "j4"):
+            assert np.array_equal(lab.get_label(g["mask"], lt, 0), g[lt]), (f, lt)
 
 
 def test_create_labels_host_paths_agree(native_lib):

@@ -20,6 +20,20 @@ def test_golden_labels():
         assert np.array_equal(cd, g["cell_dist"]) and np.array_equal(nd, g["neighbor_dist"]), f
 
 
+def test_simple_label_types_against_the_reference_functions():
+    """boundary / border / j4 label images: the fixtures were produced by the reference's OWN functions
+    (train_data_representations.py:75-190, imported by path in tests/golden/make_golden.py simple_labels; scipy + numpy,
+    skimage's one-line disk() stubbed) -- the oracle must reproduce them exactly"""
+    files = sorted(glob.glob(os.path.join(HERE, "golden", "simple_labels_*.npz")))
+    assert len(files) >= 2
+    for f in files:
+        g = np.load(f)
+        m = g["mask"]
+        assert np.array_equal(ol.boundary_label(m), g["boundary"]), f
+        assert np.array_equal(ol.border_label(m), g["border"]), f
+        assert np.array_equal(ol.j4_label(m), g["j4"]), f
+
+
 def test_restated_skimage_pieces():
     d = ol.disk(3)
     assert d.shape == (7, 7) and d.sum() == 29 and d[0, 3] == 1 and d[0, 2] == 0
