@@ -6,6 +6,9 @@
   python tests/golden/make_golden.py ranger       # the REAL reference Ranger optimizer (/root/reference) on CPU
   python tests/golden/make_golden.py losses       # the REAL reference ce_dice / CrossEntropyLoss (/root/reference) on CPU
   python tests/golden/make_golden.py simple_labels  # the REAL reference boundary_label / border_label / j4_label on CPU
+  python tests/golden/make_golden.py labels_refbody # the REAL reference distance_label body over restated regionprops / label
+  python tests/golden/make_golden.py postproc_refbody # the REAL reference post-processing bodies over restated label / regionprops / watershed
+  python tests/golden/make_golden.py aji          # the REAL reference get_fast_aji_plus (stats_utils.py) on CPU
 
 The post-processing goldens are produced by the oracle restatement (scikit-image cannot run in
 this image -> "parity unpinned" for the skimage pieces, see oracle/postproc.py); the network
@@ -34,6 +37,131 @@ def make_postproc():
                             th_seed=0.45, th_cell=0.10, mask_u16=out, cell_smooth=im["cell"],
                             n_markers=im["n_markers"])
         print("postproc", H, W, seed, "objects", int(out.max()))
+
+
+def _import_reference_postprocessing():
+    """The reference's own src/inference/postprocessing.py, imported by path.  scikit-image is not installed here, so
+    ``skimage.measure.label`` / ``regionprops`` / ``skimage.segmentation.watershed`` are the oracle's RESTATEMENTS
+    (oracle/postproc.py::label8, bincount areas, oracle/watershed.c): the function bodies that run are the reference's own
+    (thresholds, np.tan, area filter loop, relabelling, casts), only those three primitives remain restated."""
+    import importlib.util
+    import types
+    from oracle import postproc as op
+
+    def _hw(a):
+        a = np.asarray(a)
+        return (a[..., 0], True) if a.ndim == 3 and a.shape[-1] == 1 else (a, False)
+
+    def label(img, background=0, **kw):
+        a, was3 = _hw(img)
+        lab = op.label8(a != background)[0].astype(np.int64)
+        return lab[..., None] if was3 else lab
+
+    class _P:
+        def __init__(self, lab_id, area):
+            self.label, self.area = int(lab_id), int(area)
+
+    def regionprops(lab):
+        a, _ = _hw(lab)
+        counts = np.bincount(a.ravel())
+        return [_P(i, c) for i, c in enumerate(counts) if i > 0 and c > 0]
+
+    def watershed(image, markers=None, mask=None, watershed_line=False, **kw):
+        assert not watershed_line and not kw
+        im, was3 = _hw(image)
+        out = op.watershed(np.asarray(im, dtype=np.float64), _hw(markers)[0], _hw(mask)[0])
+        return out[..., None] if was3 else out
+
+    sk, sks, skme = (types.ModuleType(n) for n in ("skimage", "skimage.segmentation", "skimage.measure"))
+    sks.watershed, skme.label, skme.regionprops = watershed, label, regionprops
+    sk.segmentation, sk.measure = sks, skme
+    names = ("skimage", "skimage.segmentation", "skimage.measure")
+    saved = {k: sys.modules.get(k) for k in names}
+    sys.modules.update({"skimage": sk, "skimage.segmentation": sks, "skimage.measure": skme})
+    try:
+        spec = importlib.util.spec_from_file_location("reference_postprocessing", "/root/reference/src/inference/postprocessing.py")
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+    return mod
+
+
+def make_postproc_refbody():
+    """distance_postprocessing / boundary_postprocessing: the reference's own function bodies (postprocessing.py:7-90) over
+    the restated label / regionprops / watershed.  Pins everything in oracle/postproc.py except those three primitives (and
+    shows whether the host's float32 np.tan, which the reference calls, agrees with the oracle's float32(tan(float64)) policy)."""
+    from scipy import ndimage
+    from microbeseg_b200 import synthetic as sy
+    from oracle import postproc as op
+    mod = _import_reference_postprocessing()
+    for H, W, n_cells, seed in [(96, 128, 40, 61), (128, 112, 70, 62), (64, 64, 0, 63)]:
+        m = sy.synth_instance_mask(H, W, n_cells, seed)
+        border, cell = sy.synth_distance_maps(m, seed + 100)            # (H, W, 1) float32, as the frame loop passes them
+        ref = mod.distance_postprocessing(border, cell, 0.45, 0.10)
+        same = (np.array_equal(ref, op.distance_postprocessing(border, cell, 0.45, 0.10, tan_mode="host")),
+                np.array_equal(ref, op.distance_postprocessing(border, cell, 0.45, 0.10)))
+        inner = ndimage.binary_erosion(m > 0, iterations=2)
+        rng = np.random.default_rng(seed)
+        logits = rng.normal(0, 0.3, (H, W, 3)).astype(np.float32)
+        logits[..., 0] += np.where(m == 0, 3.0, 0.0)
+        logits[..., 1] += np.where(inner, 3.0, 0.0)
+        logits[..., 2] += np.where((m > 0) & ~inner, 2.0, 0.0)
+        e = np.exp(logits - logits.max(-1, keepdims=True))
+        prob = (e / e.sum(-1, keepdims=True)).astype(np.float32)
+        refb = mod.boundary_postprocessing(prob)
+        sameb = np.array_equal(refb, op.boundary_postprocessing(prob))
+        np.savez_compressed(os.path.join(HERE, f"refbody_postproc_{H}x{W}_s{seed}.npz"), border=border, cell=cell, th_seed=0.45,
+                            th_cell=0.10, mask_u16=ref, prob=prob, boundary_mask_u16=refb)
+        print("postproc refbody", H, W, seed, "objects", int(ref.max()), int(refb.max()),
+              "oracle == reference body (host tan, f64 tan policy, boundary):", same, sameb)
+
+
+def make_aji():
+    """AJI+ values from the reference's OWN src/evaluation/stats_utils.py::get_fast_aji_plus (numpy + scipy's
+    linear_sum_assignment; the module-level cv2 / matplotlib imports, which that function never touches, are empty stubs)."""
+    import importlib.util
+    import types
+    from microbeseg_b200 import synthetic as sy
+    names = ("cv2", "matplotlib", "matplotlib.pyplot")
+    saved = {k: sys.modules.get(k) for k in names}
+    mpl, plt = types.ModuleType("matplotlib"), types.ModuleType("matplotlib.pyplot")
+    mpl.pyplot = plt
+    sys.modules.update({"cv2": types.ModuleType("cv2"), "matplotlib": mpl, "matplotlib.pyplot": plt})
+    try:
+        spec = importlib.util.spec_from_file_location("reference_stats_utils", "/root/reference/src/evaluation/stats_utils.py")
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+    cases = {}
+    for k, (H, W, n, seed) in enumerate([(96, 128, 30, 71), (128, 128, 60, 72), (64, 80, 9, 73)]):
+        t = sy.synth_instance_mask(H, W, n, seed).astype(np.int32)
+        p = sy.synth_instance_mask(H, W, n, seed).astype(np.int32)
+        rng = np.random.default_rng(seed)
+        p = np.roll(p, (int(rng.integers(-3, 4)), int(rng.integers(-3, 4))), (0, 1))      # shifted prediction
+        drop = rng.choice(np.arange(1, n + 1), size=max(1, n // 6), replace=False)          # missed cells
+        p[np.isin(p, drop)] = 0
+        if n > 4:
+            p[p == 2] = 1                                                                   # a merge (ids stay contiguous below)
+        ids = np.unique(p[p > 0])
+        remap = np.zeros(int(p.max()) + 1, np.int32)
+        remap[ids] = np.arange(1, len(ids) + 1)
+        p = remap[p]                       # the metric expects contiguous ids (the reference feeds measure.label output)
+        cases[f"true{k}"], cases[f"pred{k}"] = t, p
+        cases[f"aji{k}"] = np.float64(mod.get_fast_aji_plus(t, p))
+        cases[f"aji_swapped{k}"] = np.float64(mod.get_fast_aji_plus(p, t))
+        print("aji+", H, W, seed, float(cases[f"aji{k}"]), float(cases[f"aji_swapped{k}"]))
+    cases["n"] = np.int32(3)
+    np.savez_compressed(os.path.join(HERE, "aji_plus_reference.npz"), **cases)
 
 
 def make_net(only=None):
@@ -81,20 +209,43 @@ def make_labels():
         print("labels", H, W, seed, "max_mal", mal, "cells", int(m.max()))
 
 
-def _import_reference_label_module():
-    """The reference's own train_data_representations.py, imported by path.  scikit-image and cv2 are not installed here: the
-    module-level imports are satisfied with stubs, of which only ``skimage.morphology.disk`` is ever CALLED by the functions
-    used below (boundary_label, border_label, j4_label: scipy + numpy otherwise) -- it is the published one-line definition
-    ``x^2 + y^2 <= r^2`` on the (2r+1)^2 grid.  regionprops / label / cv2 stay unusable stubs (None)."""
+def _import_reference_label_module(restated_measure=False):
+    """The reference's own train_data_representations.py, imported by path, with the reference's own src/utils/utils.py
+    (json + numpy only) behind ``from src.utils.utils import get_nucleus_ids``.  scikit-image and cv2 are not installed here:
+    the module-level imports are satisfied with stubs.
+      * ``skimage.morphology.disk`` is the published one-line definition ``x^2 + y^2 <= r^2`` on the (2r+1)^2 grid;
+      * restated_measure=False: regionprops / label / cv2 stay unusable (None) -- boundary_label, border_label and j4_label never
+        touch them (scipy + numpy otherwise);
+      * restated_measure=True: ``skimage.measure.label`` / ``regionprops`` are the oracle's RESTATEMENTS (oracle/labels.py::label8,
+        regionprops), so distance_label / bottom_hat_closing / cell_distance_label run the reference's own function bodies and
+        only those two scikit-image primitives remain restated."""
     import importlib.util
     import types
     from oracle import labels as ol
-    sk, skm, skme, cv2 = (types.ModuleType(n) for n in ("skimage", "skimage.morphology", "skimage.measure", "cv2"))
+    names = ("skimage", "skimage.morphology", "skimage.measure", "cv2", "src", "src.utils", "src.utils.utils")
+    sk, skm, skme, cv2, src, srcu = (types.ModuleType(n) for n in names[:6])
     skm.disk = ol.disk
     sk.morphology, sk.measure = skm, skme
     skme.regionprops = skme.label = None
-    saved = {k: sys.modules.get(k) for k in ("skimage", "skimage.morphology", "skimage.measure", "cv2")}
-    sys.modules.update({"skimage": sk, "skimage.morphology": skm, "skimage.measure": skme, "cv2": cv2})
+    if restated_measure:
+        class _Props:
+            def __init__(self, r):
+                self._r = r
+                self.label, self.area, self.centroid = r.label, r.area, r.centroid
+                self.equivalent_diameter = float(np.sqrt(4.0 * r.area / np.pi))
+
+            minor_axis_length = property(lambda self: self._r.minor_axis_length)
+            major_axis_length = property(lambda self: self._r.major_axis_length)
+
+        skme.regionprops = lambda lab: [_Props(r) for r in ol.regionprops(lab)]
+        skme.label = lambda img, *a, **k: ol.label8(np.asarray(img) > 0)[0]
+    spec_u = importlib.util.spec_from_file_location("src.utils.utils", "/root/reference/src/utils/utils.py")
+    ref_utils = importlib.util.module_from_spec(spec_u)
+    spec_u.loader.exec_module(ref_utils)
+    src.utils, srcu.utils = srcu, ref_utils
+    saved = {k: sys.modules.get(k) for k in names}
+    sys.modules.update({"skimage": sk, "skimage.morphology": skm, "skimage.measure": skme, "cv2": cv2, "src": src, "src.utils": srcu,
+                        "src.utils.utils": ref_utils})
     try:
         spec = importlib.util.spec_from_file_location("reference_tdr", "/root/reference/src/training/train_data_representations.py")
         mod = importlib.util.module_from_spec(spec)
@@ -106,6 +257,28 @@ def _import_reference_label_module():
             else:
                 sys.modules[k] = v
     return mod
+
+
+def make_labels_refbody():
+    """distance_label / cell_distance_label(clipped) / bottom_hat_closing: the reference's own function bodies
+    (train_data_representations.py:40-72, 220-361) on top of the restated regionprops / label (see above).  The fixtures pin
+    everything in oracle/labels.py except those two primitives."""
+    from microbeseg_b200 import synthetic as sy
+    from oracle import labels as ol
+    mod = _import_reference_label_module(restated_measure=True)
+    np.float = float          # the reference uses the removed NumPy alias np.float (train_data_representations.py:231, 276)
+    for H, W, n, seed in [(112, 144, 26, 51), (96, 96, 40, 52)]:
+        m = sy.synth_instance_mask(H, W, n, seed, (9.0, 16.0), (7.0, 12.0)).astype(np.uint16)
+        mal = ol.max_major_axis_length(m)
+        R = int(np.ceil(0.75 * mal))
+        cd, nd = mod.distance_label(m, R)
+        clipped = mod.cell_distance_label(m, R, apply_clipping=True)
+        gaps, gap_map = mod.bottom_hat_closing(m)
+        ocd, ond = ol.distance_label(m, R)
+        same = (np.array_equal(cd, ocd), np.array_equal(nd, ond), np.array_equal(clipped, ol.get_label(m, "cell_dist_clipped", mal)))
+        np.savez_compressed(os.path.join(HERE, f"refbody_labels_{H}x{W}_s{seed}.npz"), mask=m, max_mal=mal, cell_dist=cd,
+                            neighbor_dist=nd, cell_dist_clipped=clipped, gaps=gaps.astype(np.int32), gap_map=gap_map)
+        print("labels refbody", H, W, seed, "max_mal", mal, "gaps", int(gaps.max()), "oracle == reference body:", same)
 
 
 def make_simple_labels():
@@ -191,9 +364,15 @@ def make_losses():
 
 
 if __name__ == "__main__":
-    what = sys.argv[1:] or ["postproc", "net", "labels", "ranger", "losses", "simple_labels"]
+    what = sys.argv[1:] or ["postproc", "net", "labels", "ranger", "losses", "simple_labels", "labels_refbody", "postproc_refbody", "aji"]
     if "simple_labels" in what:
         make_simple_labels()
+    if "labels_refbody" in what:
+        make_labels_refbody()
+    if "postproc_refbody" in what:
+        make_postproc_refbody()
+    if "aji" in what:
+        make_aji()
     if "losses" in what:
         make_losses()
     if "ranger" in what:

@@ -47,6 +47,18 @@ def test_aji_plus_matches_oracle(native_lib):
     assert ev.aji_plus(t, q) == 0.0
 
 
+def test_aji_plus_against_the_reference_function(native_lib):
+    """GPU pair counting + the reference's own assignment call vs values from the reference's get_fast_aji_plus
+    (tests/golden/aji_plus_reference.npz); relabel=False: the fixture masks are fed as they are, like the function itself"""
+    import os
+    from microbeseg_b200 import evaluation as ev
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "aji_plus_reference.npz"))
+    for k in range(int(g["n"])):
+        t, p = g[f"true{k}"].astype(np.uint16), g[f"pred{k}"].astype(np.uint16)
+        assert abs(ev.aji_plus(t, p, relabel=False) - float(g[f"aji{k}"])) < 1e-12
+        assert abs(ev.aji_plus(p, t, relabel=False) - float(g[f"aji_swapped{k}"])) < 1e-12
+
+
 def test_threshold_sweep_equals_single_calls_and_oracle(native_lib):
     from microbeseg_b200 import evaluation as ev, postprocessing as pp, synthetic as sy
     m = sy.synth_instance_mask(256, 256, 70, 5)

@@ -160,6 +160,23 @@ def test_simple_label_types_against_the_reference_fixtures():
             assert np.array_equal(lab.get_label(g["mask"], lt, 0), g[lt]), (f, lt)
 
 
+def test_distance_labels_against_the_reference_function_bodies():
+    """CUDA path vs tests/golden/refbody_labels_*.npz (the reference's own distance_label / cell_distance_label bodies over
+    the restated regionprops / label, see make_golden.py labels_refbody): cell maps bit-exact, neighbor map within 1 ulp"""
+    import glob
+    from microbeseg_b200 import labels as lab
+    files = sorted(glob.glob(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "refbody_labels_*.npz")))
+    assert len(files) >= 2
+    for f in files:
+        g = np.load(f)
+        m, mal = g["mask"], int(g["max_mal"])
+        cd, nd = lab.get_label(m, "distance", mal)
+        assert np.array_equal(cd, g["cell_dist"]), f
+        assert np.abs(nd.astype(np.float64) - g["neighbor_dist"]).max() <= 1.2e-7, f
+        assert np.array_equal(lab.get_label(m, "cell_dist_clipped", mal), g["cell_dist_clipped"]), f
+        assert int(lab.max_major_axis_lengths(m[None])[0]) == mal
+
+
 def test_create_labels_host_paths_agree(native_lib):
     """host path of config 4: pipelined pinned staging into fresh arrays, into caller-provided NumPy arrays and straight
     into caller-provided PINNED tensors (no host copy) all give the bytes of the device-resident entry"""

@@ -37,6 +37,18 @@ def test_aji_plus_hand_computed():
     assert em.aji_plus(t, q) == 0.0
 
 
+def test_aji_plus_against_the_reference_function():
+    """tests/golden/aji_plus_reference.npz: values computed by the reference's OWN get_fast_aji_plus
+    (src/evaluation/stats_utils.py:98-179, imported by path in make_golden.py aji; numpy + scipy only) -- the oracle must
+    reproduce them exactly (same pairwise sums, same linear_sum_assignment call)"""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "aji_plus_reference.npz"))
+    for k in range(int(g["n"])):
+        t, p = g[f"true{k}"], g[f"pred{k}"]
+        assert em.aji_plus(t, p) == float(g[f"aji{k}"])
+        assert em.aji_plus(p, t) == float(g[f"aji_swapped{k}"])
+
+
 def test_aji_plus_is_invariant_to_id_permutation_and_symmetric_in_pairing():
     rng = np.random.default_rng(3)
     t = np.zeros((40, 40), int)

@@ -34,6 +34,24 @@ def test_simple_label_types_against_the_reference_functions():
         assert np.array_equal(ol.j4_label(m), g["j4"]), f
 
 
+def test_distance_label_against_the_reference_function_bodies():
+    """tests/golden/refbody_labels_*.npz: outputs of the reference's OWN distance_label / cell_distance_label(clipping) /
+    bottom_hat_closing (train_data_representations.py:40-72, 220-361, imported by path) running on top of the restated
+    regionprops / measure.label -- so everything in oracle/labels.py except those two scikit-image primitives is pinned to the
+    reference's code"""
+    files = sorted(glob.glob(os.path.join(HERE, "golden", "refbody_labels_*.npz")))
+    assert len(files) >= 2
+    for f in files:
+        g = np.load(f)
+        m, mal = g["mask"], int(g["max_mal"])
+        assert ol.max_major_axis_length(m) == mal
+        cd, nd = ol.get_label(m, "distance", mal)
+        assert np.array_equal(cd, g["cell_dist"]) and np.array_equal(nd, g["neighbor_dist"]), f
+        assert np.array_equal(ol.get_label(m, "cell_dist_clipped", mal), g["cell_dist_clipped"]), f
+        gaps, gap_map = ol.bottom_hat_closing(m)
+        assert np.array_equal(gaps, g["gaps"]) and np.array_equal(gap_map, g["gap_map"]), f
+
+
 def test_restated_skimage_pieces():
     d = ol.disk(3)
     assert d.shape == (7, 7) and d.sum() == 29 and d[0, 3] == 1 and d[0, 2] == 0

@@ -53,6 +53,21 @@ def test_golden_postproc():
         assert im["n_markers"] == int(g["n_markers"])
 
 
+def test_against_the_reference_function_bodies():
+    """tests/golden/refbody_postproc_*.npz: outputs of the reference's OWN distance_postprocessing / boundary_postprocessing
+    (postprocessing.py:7-90, imported by path in make_golden.py postproc_refbody) running on top of the restated
+    measure.label / regionprops / watershed -- everything in oracle/postproc.py except those three scikit-image primitives is
+    pinned to the reference's code (the reference calls the host's float32 np.tan: both tan policies give these masks)"""
+    files = sorted(glob.glob(os.path.join(HERE, "golden", "refbody_postproc_*.npz")))
+    assert len(files) >= 3
+    for f in files:
+        g = np.load(f)
+        for mode in ("f64", "host"):
+            out = op.distance_postprocessing(g["border"], g["cell"], float(g["th_seed"]), float(g["th_cell"]), tan_mode=mode)
+            assert np.array_equal(out, g["mask_u16"]), (f, mode)
+        assert np.array_equal(op.boundary_postprocessing(g["prob"]), g["boundary_mask_u16"]), f
+
+
 def test_heap_flood_equals_order_free_formulation():
     rng = np.random.default_rng(5)
     n_amb = 0

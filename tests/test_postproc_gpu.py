@@ -153,6 +153,18 @@ def test_golden_fixtures(pp):
         assert np.array_equal(out, g["mask_u16"]), f
 
 
+def test_against_the_reference_function_bodies(pp):
+    """CUDA path vs tests/golden/refbody_postproc_*.npz (the reference's own distance_postprocessing /
+    boundary_postprocessing bodies over the restated label / regionprops / watershed): bit-exact"""
+    files = sorted(glob.glob(os.path.join(HERE, "golden", "refbody_postproc_*.npz")))
+    assert len(files) >= 3
+    for f in files:
+        g = np.load(f)
+        out = pp.distance_postprocessing(g["border"], g["cell"], float(g["th_seed"]), float(g["th_cell"]))
+        assert np.array_equal(out, g["mask_u16"]), f
+        assert np.array_equal(pp.boundary_postprocessing(g["prob"]), g["boundary_mask_u16"]), f
+
+
 @pytest.mark.parametrize("H,W,cells,seed", [(128, 128, 60, 1), (512, 512, 300, 2), (300, 777, 250, 3),
                                             (1024, 1024, 1300, 4)])
 def test_distance_postprocessing_bit_exact(pp, H, W, cells, seed):
