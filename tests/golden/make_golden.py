@@ -9,6 +9,7 @@
   python tests/golden/make_golden.py labels_refbody # the REAL reference distance_label body over restated regionprops / label
   python tests/golden/make_golden.py postproc_refbody # the REAL reference post-processing bodies over restated label / regionprops / watershed
   python tests/golden/make_golden.py aji          # the REAL reference get_fast_aji_plus (stats_utils.py) on CPU
+  python tests/golden/make_golden.py augment      # the REAL reference 'train' transform on seeds without imgaug / CLAHE draws
 
 The post-processing goldens are produced by the oracle restatement (scikit-image cannot run in
 this image -> "parity unpinned" for the skimage pieces, see oracle/postproc.py); the network
@@ -162,6 +163,103 @@ def make_aji():
         print("aji+", H, W, seed, float(cases[f"aji{k}"]), float(cases[f"aji_swapped{k}"]))
     cases["n"] = np.int32(3)
     np.savez_compressed(os.path.join(HERE, "aji_plus_reference.npz"), **cases)
+
+
+def make_augment():
+    """The reference's OWN 'train' transform (mytransforms.py: Flip, Contrast, Scaling, Rotate, Blur, Noise, ToTensor in a
+    Compose) for seeds on which neither an imgaug transform (Scaling / Rotate / Noise) nor CLAHE is drawn -- those need imgaug /
+    scikit-image, which are not installed.  Stubs: ``torchvision.transforms.Compose`` (a loop over callables),
+    ``skimage.exposure.rescale_intensity`` (restated: clip to in_range, scale to the dtype range -- parity unpinned),
+    ``src.utils.utils`` is the reference's own module.  Pins the RNG call order, the decision thresholds and the bodies of Flip,
+    Contrast (stretch / contrast + gamma), Blur and ToTensor of oracle/augment.py + microbeseg_b200.augment.draw_params."""
+    import importlib.util
+    import random
+    import types
+    import torch
+    from microbeseg_b200 import synthetic as sy
+    from microbeseg_b200.augment import draw_params
+
+    def rescale_intensity(img, in_range):
+        p0, p1 = in_range
+        out = np.clip(img, p0, p1).astype(np.float64)
+        if p0 != p1:
+            out = (out - p0) / (p1 - p0)
+        return (out * float(np.iinfo(img.dtype).max)).astype(img.dtype)
+
+    def unusable(*a, **k):
+        raise RuntimeError("imgaug / CLAHE are not available: this seed must be skipped")
+
+    class Compose:
+        def __init__(self, ts):
+            self.ts = ts
+
+        def __call__(self, x):
+            for t in self.ts:
+                x = t(x)
+            return x
+
+    names = ("imgaug", "imgaug.augmenters", "skimage", "skimage.exposure", "torchvision", "torchvision.transforms", "src", "src.utils",
+             "src.utils.utils")
+    mods = {n: types.ModuleType(n) for n in names[:6]}
+    mods["imgaug"].augmenters = mods["imgaug.augmenters"]
+    for attr in ("Sequential", "AdditiveGaussianNoise", "Affine"):
+        setattr(mods["imgaug.augmenters"], attr, unusable)
+    mods["skimage"].exposure = mods["skimage.exposure"]
+    mods["skimage.exposure"].equalize_adapthist = unusable
+    mods["skimage.exposure"].rescale_intensity = rescale_intensity
+    mods["torchvision"].transforms = mods["torchvision.transforms"]
+    mods["torchvision.transforms"].Compose = Compose
+    spec_u = importlib.util.spec_from_file_location("src.utils.utils", "/root/reference/src/utils/utils.py")
+    ref_utils = importlib.util.module_from_spec(spec_u)
+    spec_u.loader.exec_module(ref_utils)
+    src, srcu = types.ModuleType("src"), types.ModuleType("src.utils")
+    src.utils, srcu.utils = srcu, ref_utils
+    mods.update({"src": src, "src.utils": srcu, "src.utils.utils": ref_utils})
+    saved = {k: sys.modules.get(k) for k in names}
+    sys.modules.update(mods)
+    try:
+        spec = importlib.util.spec_from_file_location("reference_mytransforms", "/root/reference/src/training/mytransforms.py")
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+    tf = mod.augmentors("distance", 0, 65535)["train"]
+    H = W = 64
+    out, kept, seen = {}, [], set()
+    for seed in range(400):
+        random.seed(seed)
+        np.random.seed(seed)
+        try:
+            p = draw_params(1, py_random=random, np_random=np.random, clahe="error")[0]
+        except NotImplementedError:
+            continue
+        if p["scale"] is not None or p["rotate"] is not None or p["noise"]:
+            continue
+        kind = (p["flip"], p["contrast"], p["percentiles"] if p["contrast"] == 1 else None, p["blur_sigma"] is not None)
+        if kind in seen:
+            continue
+        seen.add(kind)
+        m = sy.synth_instance_mask(H, W, 10, 900 + seed)
+        img = sy.synth_frame(H, W, 900 + seed)[..., None].astype(np.uint16)
+        rng = np.random.default_rng(seed)
+        bl, cl = rng.random((H, W, 1)).astype(np.float32), rng.random((H, W, 1)).astype(np.float32)
+        random.seed(seed)
+        np.random.seed(seed)
+        ti, tb, tc = tf({"image": img.copy(), "border_label": bl.copy(), "cell_label": cl.copy(), "id": "x"})
+        k = len(kept)
+        out[f"image{k}"], out[f"border{k}"], out[f"cell{k}"] = img, bl, cl
+        out[f"t_image{k}"], out[f"t_border{k}"], out[f"t_cell{k}"] = ti.numpy(), tb.numpy(), tc.numpy()
+        kept.append(seed)
+        if len(kept) == 24:
+            break
+    out["seeds"] = np.array(kept, np.int64)
+    np.savez_compressed(os.path.join(HERE, "augment_reference.npz"), **out)
+    print("augment: seeds", kept)
+    print("   kinds (flip, contrast, percentiles, blur):", sorted(seen, key=str))
 
 
 def make_net(only=None):
@@ -364,7 +462,7 @@ def make_losses():
 
 
 if __name__ == "__main__":
-    what = sys.argv[1:] or ["postproc", "net", "labels", "ranger", "losses", "simple_labels", "labels_refbody", "postproc_refbody", "aji"]
+    what = sys.argv[1:] or ["postproc", "net", "labels", "ranger", "losses", "simple_labels", "labels_refbody", "postproc_refbody", "aji", "augment"]
     if "simple_labels" in what:
         make_simple_labels()
     if "labels_refbody" in what:
@@ -373,6 +471,8 @@ if __name__ == "__main__":
         make_postproc_refbody()
     if "aji" in what:
         make_aji()
+    if "augment" in what:
+        make_augment()
     if "losses" in what:
         make_losses()
     if "ranger" in what:

@@ -95,6 +95,33 @@ def test_full_random_pipeline_against_oracle(native_lib):
     assert t.shape == (24, 1, 64, 64) and np.abs(t - rt).max() <= 3.01 * LSB
 
 
+def test_against_the_reference_transform(native_lib):
+    """GpuAugmenter vs tests/golden/augment_reference.npz (the reference's own 'train' Compose on seeds without imgaug / CLAHE
+    draws, see make_golden.py augment): labels and pure Flip / Blur samples bit exact, stretch within 1 LSB, contrast + gamma
+    within 2 LSB of the uint16 image (the module's stated bars)"""
+    import os
+    from microbeseg_b200.augment import draw_params
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "augment_reference.npz"))
+    seeds = [int(s) for s in g["seeds"]]
+    params = []
+    for seed in seeds:
+        random.seed(seed)
+        np.random.seed(seed)
+        params.append(draw_params(1, py_random=random, np_random=np.random, clahe="error")[0])
+    n = len(seeds)
+    imgs = np.stack([g[f"image{k}"][..., 0] for k in range(n)])
+    bl = np.stack([g[f"border{k}"][..., 0] for k in range(n)])
+    cl = np.stack([g[f"cell{k}"][..., 0] for k in range(n)])
+    t, b, c, _ = _run(imgs, bl, cl, params)
+    for k, p in enumerate(params):
+        assert np.array_equal(b[k], g[f"t_border{k}"]) and np.array_equal(c[k], g[f"t_cell{k}"]), seeds[k]
+        d = np.abs(t[k] - g[f"t_image{k}"]).max()
+        lim = 0.0 if p["contrast"] == 0 else (1.01 * LSB if p["contrast"] == 1 else 2.01 * LSB)
+        if p["contrast"] and p["blur_sigma"] is not None:
+            lim += 1.01 * LSB                      # the blur rounds the (<= 1-2 LSB different) image again
+        assert d <= lim, (seeds[k], p, d / LSB)
+
+
 def test_noise_distribution_and_reproducibility(native_lib):
     n, s = 4, 128
     imgs = np.full((n, s, s), 30000, np.uint16)

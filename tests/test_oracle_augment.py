@@ -73,3 +73,24 @@ def test_contrast_restatements():
     assert np.abs(g.astype(np.int64) - img.astype(np.int64)).max() <= 2          # identity parameters up to float32 rounding
     t = oa.to_tensor_image(img, 0, 65535)
     assert t.shape == (1, 40, 40) and t.dtype == np.float32 and -1 <= t.min() and t.max() <= 1
+
+
+def test_against_the_reference_transform():
+    """tests/golden/augment_reference.npz: outputs of the reference's OWN 'train' Compose (mytransforms.py:25-33: Flip, Contrast,
+    Scaling, Rotate, Blur, Noise, ToTensor; imported by path in make_golden.py augment) on 24 seeds where neither an imgaug
+    transform nor CLAHE is drawn.  draw_params with the same seeded generators + oracle/augment.py::apply must give the very same
+    tensors: pins the RNG call order, the probabilities and the Flip / Contrast / Blur / ToTensor bodies to the reference's code."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "augment_reference.npz"))
+    kinds = set()
+    for k, seed in enumerate(g["seeds"]):
+        random.seed(int(seed))
+        np.random.seed(int(seed))
+        p = ga.draw_params(1, py_random=random, np_random=np.random, clahe="error")[0]
+        assert p["scale"] is None and p["rotate"] is None and p["noise"] == 0
+        r = oa.apply({"image": g[f"image{k}"], "border_label": g[f"border{k}"], "cell_label": g[f"cell{k}"]}, p)
+        assert np.array_equal(r["tensor"], g[f"t_image{k}"]), seed
+        assert np.array_equal(np.transpose(r["border_label"], (2, 0, 1)), g[f"t_border{k}"]), seed
+        assert np.array_equal(np.transpose(r["cell_label"], (2, 0, 1)), g[f"t_cell{k}"]), seed
+        kinds.add((p["flip"], p["contrast"], p["blur_sigma"] is not None))
+    assert {k[0] for k in kinds} == {0, 1, 2, 3, 4, 6, 7} and {k[1] for k in kinds} == {0, 1, 2} and {k[2] for k in kinds} == {False, True}
