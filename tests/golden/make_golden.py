@@ -10,6 +10,7 @@
   python tests/golden/make_golden.py postproc_refbody # the REAL reference post-processing bodies over restated label / regionprops / watershed
   python tests/golden/make_golden.py aji          # the REAL reference get_fast_aji_plus (stats_utils.py) on CPU
   python tests/golden/make_golden.py augment      # the REAL reference 'train' transform on seeds without imgaug / CLAHE draws
+  python tests/golden/make_golden.py utils        # the REAL reference zero_pad_model_input / min_max_normalization
 
 The post-processing goldens are produced by the oracle restatement (scikit-image cannot run in
 this image -> "parity unpinned" for the skimage pieces, see oracle/postproc.py); the network
@@ -262,6 +263,44 @@ def make_augment():
     print("   kinds (flip, contrast, percentiles, blur):", sorted(seen, key=str))
 
 
+def make_utils():
+    """zero_pad_model_input / min_max_normalization from the reference's OWN src/utils/utils.py (json + numpy only)."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("reference_utils", "/root/reference/src/utils/utils.py")
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    out = {}
+    shapes = [(50, 70), (64, 64), (65, 8192), (1000, 1000), (2048, 2048), (2049, 100), (321, 4097), (8192, 8192), (1, 1), (6080, 6081),
+              (33, 40, 3)]
+    rng = np.random.default_rng(5)
+    for k, shp in enumerate(shapes):
+        small = tuple(min(d, 96) for d in shp[:2]) + tuple(shp[2:])      # content check on a small array of the same rank
+        out[f"shape{k}"] = np.array(shp, np.int64)
+        padded, pads = mod.zero_pad_model_input(np.zeros(shp, np.uint8), pad_val=3)
+        out[f"pads{k}"], out[f"padded_shape{k}"] = np.array(pads, np.int64), np.array(padded.shape, np.int64)
+        img = rng.integers(0, 200, small).astype(np.uint16)
+        padded, pads = mod.zero_pad_model_input(img, pad_val=7)
+        out[f"small{k}"], out[f"small_padded{k}"], out[f"small_pads{k}"] = img, padded, np.array(pads, np.int64)
+    out["n_shapes"] = np.int64(len(shapes))
+    imgs = [rng.integers(0, 65535, (9, 11)).astype(np.uint16), rng.integers(0, 255, (7, 5)).astype(np.uint8),
+            rng.integers(100, 4000, (6, 6, 1)).astype(np.uint16)]
+    k = 0
+    for img in imgs:
+        for lo, hi in [(None, None), (0, 65535), (200, 3000), (int(img.min()), int(img.max()))]:
+            out[f"mm_in{k}"], out[f"mm_lo{k}"], out[f"mm_hi{k}"] = img, np.int64(-1 if lo is None else lo), np.int64(-1 if hi is None else hi)
+            out[f"mm_out{k}"] = mod.min_max_normalization(img.copy(), min_value=lo, max_value=hi)
+            k += 1
+    out["n_mm"] = np.int64(k)
+    try:
+        mod.zero_pad_model_input(np.zeros((9000, 9000), np.uint8))
+        out["too_big_raises"] = np.int64(0)
+    except Exception:
+        out["too_big_raises"] = np.int64(1)
+    padded, pads = mod.zero_pad_model_input(np.zeros((9000, 100), np.uint8)) if False else (None, None)
+    np.savez_compressed(os.path.join(HERE, "utils_reference.npz"), **out)
+    print("utils: shapes", len(shapes), "normalisations", k, "too big raises", int(out["too_big_raises"]))
+
+
 def make_net(only=None):
     import importlib.util
     import torch
@@ -462,7 +501,7 @@ def make_losses():
 
 
 if __name__ == "__main__":
-    what = sys.argv[1:] or ["postproc", "net", "labels", "ranger", "losses", "simple_labels", "labels_refbody", "postproc_refbody", "aji", "augment"]
+    what = sys.argv[1:] or ["postproc", "net", "labels", "ranger", "losses", "simple_labels", "labels_refbody", "postproc_refbody", "aji", "augment", "utils"]
     if "simple_labels" in what:
         make_simple_labels()
     if "labels_refbody" in what:
@@ -473,6 +512,8 @@ if __name__ == "__main__":
         make_aji()
     if "augment" in what:
         make_augment()
+    if "utils" in what:
+        make_utils()
     if "losses" in what:
         make_losses()
     if "ranger" in what:

@@ -6,6 +6,7 @@ import subprocess
 import sys
 
 import numpy as np
+import pytest
 import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
@@ -70,6 +71,29 @@ def test_zero_pad_model_input_matches_reference_semantics():
     assert model_input_pads(9000, 100) == [28]          # reference quirk: one pad only, no exception
     x = min_max_normalization(np.array([[0, 5, 10]], np.uint16))
     assert x.dtype == np.float32 and x.tolist() == [[-1.0, 0.0, 1.0]]
+
+
+def test_utils_against_the_reference_functions():
+    """tests/golden/utils_reference.npz: pads / padded arrays / normalised images from the reference's OWN
+    zero_pad_model_input and min_max_normalization (src/utils/utils.py:50-74, 124-163, imported by path in make_golden.py utils)"""
+    from microbeseg_b200.utils import min_max_normalization, model_input_pads, zero_pad_model_input
+    g = np.load(os.path.join(ROOT, "tests", "golden", "utils_reference.npz"))
+    for k in range(int(g["n_shapes"])):
+        shp = tuple(int(v) for v in g[f"shape{k}"])
+        padded, pads = zero_pad_model_input(np.zeros(shp, np.uint8), pad_val=3)
+        assert list(pads) == g[f"pads{k}"].tolist() and padded.shape == tuple(g[f"padded_shape{k}"].tolist()), shp
+        if len(shp) == 2:
+            assert model_input_pads(*shp) == g[f"pads{k}"].tolist()
+        out, pads = zero_pad_model_input(g[f"small{k}"], pad_val=7)
+        assert list(pads) == g[f"small_pads{k}"].tolist() and out.dtype == g[f"small_padded{k}"].dtype
+        assert np.array_equal(out, g[f"small_padded{k}"]), shp
+    for k in range(int(g["n_mm"])):
+        lo, hi = int(g[f"mm_lo{k}"]), int(g[f"mm_hi{k}"])
+        out = min_max_normalization(g[f"mm_in{k}"].copy(), min_value=None if lo < 0 else lo, max_value=None if hi < 0 else hi)
+        assert out.dtype == np.float32 and np.array_equal(out, g[f"mm_out{k}"]), k
+    assert int(g["too_big_raises"]) == 1
+    with pytest.raises(Exception):
+        zero_pad_model_input(np.zeros((9000, 9000), np.uint8))
 
 
 def test_tiff_roundtrip_and_cli_surface(tmp_path):
