@@ -214,7 +214,8 @@ def segment_stack(net, stack, ths=(0.10, 0.45), device=None, frames=None, out=No
         stack = stack[None]
     T = stack.shape[0]
     if out is None:
-        out = np.zeros(stack.shape, dtype=np.uint16)
+        from . import staging
+        out = staging.host_empty(stack.shape, np.uint16, zero=True)      # large stacks: anonymous mapping with 2 MiB pages
     seg = FrameSegmenter(net, ths, device)
     todo = list(range(T)) if frames is None else list(frames)
     pending = None

@@ -171,7 +171,7 @@ def create_labels(masks, out=None):
     device = _device()
     pinned_out = out is not None and all(isinstance(o, torch.Tensor) and o.is_pinned() for o in out)
     if out is None:
-        cells, neighs = np.empty((n, H, W), np.float32), np.empty((n, H, W), np.float32)
+        cells, neighs = staging.host_empty((n, H, W), np.float32), staging.host_empty((n, H, W), np.float32)
     else:
         cells, neighs = out
         for o in (cells, neighs):
