@@ -106,7 +106,7 @@ def distance_postprocessing(border_prediction, cell_prediction, th_seed, th_cell
     border = _as_device_map(border_prediction, device)
     cell = _as_device_map(cell_prediction, device)
     out = distance_postprocessing_device(border, cell, th_seed, th_cell)
-    res = np.empty(tuple(out.shape), dtype=np.uint16)
+    res = staging.host_empty(tuple(out.shape), np.uint16)
     with torch.cuda.device(device):
         staging.download(out, res)
     # np.squeeze as in postprocessing.py:59 (a 1xW frame comes back 1-D, exactly like the reference)

@@ -23,7 +23,7 @@ _lock = threading.Lock()
 
 
 def host_empty(shape, dtype, zero=False):
-    """Host array for large results (``zero=True``: guaranteed zero-filled, else uninitialised like ``np.empty``).  Arrays of 64 MiB and more come from an anonymous
+    """Host array for large results (``zero=True``: guaranteed zero-filled, else uninitialised like ``np.empty``).  Arrays of 16 MiB and more come from an anonymous
     mapping with MADV_HUGEPAGE: with transparent huge pages in "madvise" mode the first touch of a plain ``np.empty`` costs a
     page fault per 4 KiB (0.8 s per GB measured here, more than the PCIe transfer of the same data), 2 MiB pages make it 3-4x
     cheaper.  Falls back to ``np.empty`` where the call is not available."""
@@ -32,7 +32,7 @@ def host_empty(shape, dtype, zero=False):
     count = int(np.prod(shape))
     nbytes = count * dtype.itemsize
     plain = np.zeros if zero else np.empty
-    if nbytes < (64 << 20) or not hasattr(mmap, "MADV_HUGEPAGE"):
+    if nbytes < (16 << 20) or not hasattr(mmap, "MADV_HUGEPAGE"):
         return plain(shape, dtype)
     try:
         m = mmap.mmap(-1, (nbytes + (2 << 20) - 1) & ~((2 << 20) - 1), flags=mmap.MAP_PRIVATE | mmap.MAP_ANONYMOUS)
