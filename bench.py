@@ -52,7 +52,7 @@ def conv_traffic_from_profile(path=None):
     try:
         for ln in open(path).read().splitlines()[1:]:
             f = ln.rsplit(",", 3)            # the kernel name holds template commas: split the three numbers off the right
-            if len(f) == 4 and f[0].startswith(("conv_gemm_kernel", "conv_halo64_kernel", "conv_hstream")):
+            if len(f) == 4 and f[0].startswith(("conv_gemm_kernel", "conv_halo64_", "conv_hstream")):
                 tot += (float(f[1]) + float(f[2])) * 1e6
                 n += 1
     except Exception:
