@@ -834,7 +834,6 @@ __global__ void gap_stats_kernel(const uint8_t *__restrict__ gap, const int *__r
     if (!__any_sync(0xffffffffu, any != 0)) continue;
     const size_t base = static_cast<size_t>(crop) * H * W;
     const int *g = gid + base;
-    const uint8_t *gp = gap + base;
     GapStats *S = gs + static_cast<size_t>(crop) * max_gaps;
     const int me = (mid & 2u) ? g[y * W + x] : -1;
     {
