@@ -1,5 +1,5 @@
 """One-off robustness run: label generation on random crop sizes / densities vs the oracle (bit-exact cell_dist,
-neighbor_dist within 1 float32 ulp), plus boundary / border label types."""
+neighbor_dist within 1 float32 ulp), plus the boundary / border / cell_dist_clipped / j4 label types."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
@@ -24,6 +24,9 @@ for case in range(int(sys.argv[2]) if len(sys.argv) > 2 else 40):
     ok = np.array_equal(gc, rc) and np.abs(gn.astype(np.float64) - rn).max() <= 1.2e-7
     ok &= np.array_equal(lab.get_label(m, "boundary", 0), ol.get_label(m, "boundary", 0))
     ok &= np.array_equal(lab.get_label(m, "border", 0), ol.get_label(m, "border", 0))
+    ok &= np.array_equal(lab.get_label(m, "cell_dist_clipped", mal), ol.get_label(m, "cell_dist_clipped", mal))
+    if H * W <= 12000:                            # the oracle's window count is a Python loop over the pixels
+        ok &= np.array_equal(lab.get_label(m, "j4", 0), ol.get_label(m, "j4", 0))
     if not ok:
         bad += 1
         print("MISMATCH case", case, H, W, n, float(np.abs(gc - rc).max()), float(np.abs(gn - rn).max()), flush=True)
