@@ -41,6 +41,29 @@ def make_postproc():
         print("postproc", H, W, seed, "objects", int(out.max()))
 
 
+def _real_skimage():
+    """scikit-image itself, if this environment has it: the *_refbody generators then import the reference modules WITHOUT stubs, so
+    the fixtures pin the restated primitives (measure.label, regionprops, watershed) as well.  Not the case in the build image."""
+    try:
+        import skimage                                      # noqa: F401
+        from skimage import measure, segmentation           # noqa: F401
+        return skimage.__version__
+    except Exception:
+        return None
+
+
+def _plain_reference_import(name, path):
+    import importlib.util
+    sys.path.insert(0, "/root/reference")
+    try:
+        spec = importlib.util.spec_from_file_location(name, path)
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+    finally:
+        sys.path.remove("/root/reference")
+    return mod
+
+
 def _import_reference_postprocessing():
     """The reference's own src/inference/postprocessing.py, imported by path.  scikit-image is not installed here, so
     ``skimage.measure.label`` / ``regionprops`` / ``skimage.segmentation.watershed`` are the oracle's RESTATEMENTS
@@ -49,6 +72,9 @@ def _import_reference_postprocessing():
     import importlib.util
     import types
     from oracle import postproc as op
+    if _real_skimage():
+        print("   scikit-image", _real_skimage(), "found: importing the reference post-processing without stubs")
+        return _plain_reference_import("reference_postprocessing", "/root/reference/src/inference/postprocessing.py")
 
     def _hw(a):
         a = np.asarray(a)
@@ -359,6 +385,13 @@ def _import_reference_label_module(restated_measure=False):
     import importlib.util
     import types
     from oracle import labels as ol
+    if _real_skimage():
+        print("   scikit-image", _real_skimage(), "found: importing the reference label module without skimage stubs")
+        try:
+            import cv2                                       # noqa: F401
+        except Exception:
+            sys.modules["cv2"] = types.ModuleType("cv2")   # only adapted_border_label uses it
+        return _plain_reference_import("reference_tdr", "/root/reference/src/training/train_data_representations.py")
     names = ("skimage", "skimage.morphology", "skimage.measure", "cv2", "src", "src.utils", "src.utils.utils")
     sk, skm, skme, cv2, src, srcu = (types.ModuleType(n) for n in names[:6])
     skm.disk = ol.disk
