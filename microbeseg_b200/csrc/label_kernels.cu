@@ -339,7 +339,7 @@ lab_cell_kernel(const uint16_t *__restrict__ masks, int H, int W, int ids, const
     cell_edt(masks, H, W, crop, id, s, wh, ww, sm, cell_dist, nraw, cell_clip);
 }
 
-// Instances whose search window exceeds shared memory (max_mal >~ 130 px): one CTA per crop walks them one after the
+// Instances whose search window exceeds shared memory (max_mal >~ 113 px): one CTA per crop walks them one after the
 // other with the window state in a per-crop global buffer (3 * H * W unsigned shorts).  Rare and slow, but exact -- the
 // reference has no size limit (train_data_representations.py:280-330).
 __global__ void __launch_bounds__(256)
